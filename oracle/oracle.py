@@ -1,0 +1,165 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes wrapper over oracle/liblvo_oracle.so (the CPU restatement of the reference's hot path).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+ALGO_LOBSTER, ALGO_SUBSENSE, ALGO_PAWCS = 0, 1, 2
+MODE_REFERENCE, MODE_SNAPSHOT = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [("rel_lbsp_threshold", C.c_float), ("lbsp_threshold_offset", C.c_int), ("desc_dist_threshold", C.c_int),
+                ("color_dist_threshold", C.c_int), ("n_samples", C.c_int), ("n_required", C.c_int),
+                ("n_samples_for_moving_avgs", C.c_int), ("n_global_words", C.c_int), ("median_blur_kernel_size", C.c_int)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liblvo_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.lvo_last_error.restype = C.c_char_p
+        _LIB.lvo_apply_sequence.restype = C.c_double
+        _LIB.lvo_cdist3.restype = C.c_uint64
+        _LIB.lvo_cdist4.restype = C.c_uint64
+        _LIB.lvo_cdist2.restype = C.c_uint64
+    return _LIB
+
+
+class OracleError(RuntimeError):
+    pass
+
+
+def _chk(rc):
+    if rc != 0:
+        raise OracleError(lib().lvo_last_error().decode())
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+STATE_DTYPES = {
+    "roi": np.uint8, "lastfg": np.uint8, "lastcolor": np.uint8, "lastdesc": np.uint16, "lut": np.uint8,
+    "bg_color": np.uint8, "bg_desc": np.uint16, "T": np.float32, "R": np.float32, "v": np.float32,
+    "Dlast": np.float32, "DminLT": np.float32, "DminST": np.float32, "rawLT": np.float32, "rawST": np.float32,
+    "finLT": np.float32, "finST": np.float32, "dsLT": np.float32, "dsST": np.float32, "unstable": np.uint8,
+    "blinks": np.uint8, "lastraw": np.uint8, "lastrawblink": np.uint8, "dilinv": np.uint8, "rawmask": np.uint8,
+    "scalars": np.float64,
+}
+SUBSENSE_STATE = ["roi", "lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "T", "R", "v", "Dlast", "DminLT",
+                  "DminST", "rawLT", "rawST", "finLT", "finST", "dsLT", "dsST", "unstable", "blinks", "lastraw",
+                  "lastrawblink", "dilinv", "scalars"]
+LOBSTER_STATE = ["roi", "lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "scalars"]
+
+
+class Oracle:
+    """Mirrors IBackgroundSubtractor (initialize / apply / getBackgroundImage) over the CPU restatement."""
+
+    def __init__(self, algo, mode=MODE_SNAPSHOT, seed=0, params=None):
+        self._h = C.c_void_p()
+        self.algo = algo
+        _chk(lib().lvo_create(algo, C.byref(params) if params is not None else None, mode, C.c_uint64(seed), C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().lvo_destroy(self._h)
+            self._h = None
+
+    def initialize(self, img, roi=None):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        rp = None
+        if roi is not None:
+            roi, rp = _u8(roi)
+        _chk(lib().lvo_initialize(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, c, rp))
+        self.shape = (h, w, c)
+
+    def apply(self, img, lr=0.0):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        h, w, c = self.shape
+        assert img.size == h * w * c
+        mask = np.empty((h, w), np.uint8)
+        _chk(lib().lvo_apply(self._h, img.ctypes.data_as(C.POINTER(C.c_uint8)), mask.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_double(lr)))
+        return mask
+
+    def apply_sequence(self, frames, lrs):
+        """frames: [n,H,W,(C)] uint8; returns (seconds inside apply, last mask)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n = frames.shape[0]
+        h, w, c = self.shape
+        lrs = np.ascontiguousarray(lrs, dtype=np.float64)
+        mask = np.empty((h, w), np.uint8)
+        t = lib().lvo_apply_sequence(self._h, frames.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.c_size_t(h * w * c),
+                                     mask.ctypes.data_as(C.POINTER(C.c_uint8)), lrs.ctypes.data_as(C.POINTER(C.c_double)))
+        if t < 0:
+            raise OracleError(lib().lvo_last_error().decode())
+        return t, mask
+
+    def refresh_model(self, frac, force_fg=False):
+        _chk(lib().lvo_refresh_model(self._h, C.c_float(frac), int(force_fg)))
+
+    def set_auto_model_reset(self, v):
+        _chk(lib().lvo_set_auto_model_reset(self._h, int(v)))
+
+    def get_background_image(self):
+        h, w, c = self.shape
+        out = np.empty((h, w, c), np.uint8)
+        _chk(lib().lvo_get_background_image(self._h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out[..., 0] if c == 1 else out
+
+    def get_background_descriptors_image(self):
+        h, w, c = self.shape
+        out = np.empty((h, w, c), np.uint16)
+        _chk(lib().lvo_get_background_descriptors_image(self._h, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out[..., 0] if c == 1 else out
+
+    def state_get(self, name):
+        n = C.c_size_t()
+        _chk(lib().lvo_state_size(self._h, name.encode(), C.byref(n)))
+        out = np.empty(n.value // np.dtype(STATE_DTYPES[name]).itemsize, STATE_DTYPES[name])
+        _chk(lib().lvo_state_get(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), n))
+        return out
+
+    def state_set(self, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=STATE_DTYPES[name])
+        _chk(lib().lvo_state_set(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes)))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        lib().lvo_get_stats(self._h, out)
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+
+def lbsp_compute(img, ref=None, rel=None, thr=0):
+    """LBSP::compute2 (dense). rel=None -> absolute threshold `thr`; else relative `rel` with offset `thr`."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros((h, w, c), np.uint16)
+    rp = None
+    if ref is not None:
+        ref = np.ascontiguousarray(ref, dtype=np.uint8)
+        assert ref.shape == img.shape
+        rp = ref.ctypes.data_as(C.POINTER(C.c_uint8))
+    _chk(lib().lvo_lbsp_compute(img.ctypes.data_as(C.POINTER(C.c_uint8)), rp, w, h, c, int(rel is not None),
+                                C.c_float(rel if rel is not None else 0.0), int(thr), out.ctypes.data_as(C.POINTER(C.c_uint16))))
+    return out[..., 0] if c == 1 else out
