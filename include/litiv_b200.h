@@ -1,0 +1,104 @@
+/* litiv_b200 — C ABI of the B200-native change-detection hot path.
+ *
+ * This is the boundary a `lv::CUDA` specialisation of the reference's background subtractors binds to.
+ * The reference declares that slot but leaves it empty ("missing impl"):
+ *   modules/video/include/litiv/video/BackgroundSubtractionUtils.hpp:136-138
+ *   modules/video/include/litiv/video/BackgroundSubtractorLBSP.hpp:77-80
+ *   modules/video/src/BackgroundSubtractorLOBSTER.cpp:400-403
+ * and its calling code is already written in apps/changedet/src/main.cpp:236-344.
+ *
+ * Plain pointers and sizes only; all image buffers are caller-owned host memory unless the name says `_device`.
+ * Every function returns 0 on success; on failure the message is available from lvb_last_error() (thread-local),
+ * mirroring the text of the reference's lvAssert_ exceptions (utils/defines.hpp.in:109-113).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef LITIV_B200_H
+#define LITIV_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lvb_context* lvb_handle;
+
+enum { LVB_ALGO_LOBSTER = 0, LVB_ALGO_SUBSENSE = 1, LVB_ALGO_PAWCS = 2 };
+
+/* Constructor parameters of the three algorithms (reference defaults in brackets):
+ *   SuBSENSE  BackgroundSubtractorSuBSENSE.hpp:52-57  desc offset [3], min colour dist [30], N [50], required [2], avg window [100], rel [0.333]
+ *   LOBSTER   BackgroundSubtractorLOBSTER.hpp:50-55   desc thr [4], colour thr [30], N [35], required [2], lbsp offset [0], rel [0.333]
+ *   PAWCS     BackgroundSubtractorPAWCS.hpp:51-55     desc offset [2], min colour dist [20], max local words [50], avg window [100], rel [0.333] */
+typedef struct lvb_params {
+    float rel_lbsp_threshold;
+    int32_t lbsp_threshold_offset;
+    int32_t desc_dist_threshold;      /* SuBSENSE/PAWCS: nDescDistThresholdOffset ; LOBSTER: nDescDistThreshold */
+    int32_t color_dist_threshold;     /* SuBSENSE/PAWCS: nMinColorDistThreshold  ; LOBSTER: nColorDistThreshold */
+    int32_t n_samples;                /* nBGSamples / nMaxNbWords */
+    int32_t n_required;               /* nRequiredBGSamples */
+    int32_t n_samples_for_moving_avgs;
+    int32_t n_global_words;           /* PAWCS */
+    int32_t median_blur_kernel_size;  /* BGSLBSP_DEFAULT_MEDIAN_BLUR_KERNEL_SIZE [9] */
+} lvb_params;
+
+const char* lvb_last_error(void);
+/* number of visible CUDA devices (0 when none / driver missing) */
+int lvb_device_count(void);
+/* fills the reference's default constructor arguments for `algo` */
+int lvb_default_params(int algo, lvb_params* out);
+
+/* constructor of BackgroundSubtractor{LOBSTER,SuBSENSE,PAWCS}_<lv::CUDA>; `seed` keys the Philox stream that replaces libc rand() */
+int lvb_create(int algo, const lvb_params* params_or_null, int device, uint64_t seed, lvb_handle* out);
+int lvb_destroy(lvb_handle h);
+
+/* IIBackgroundSubtractor::initialize(img, ROI)  (BackgroundSubtractionUtils.hpp:28-30; SuBSENSE.cpp:107-186; LOBSTER.cpp:443-457)
+ * img: 8UC1/8UC3 rows of `step` bytes; roi: null (all pixels) or 8UC1 {0,255} of the same size, continuous */
+int lvb_initialize(lvb_handle h, const uint8_t* img, int width, int height, int channels, size_t step, const uint8_t* roi_or_null);
+/* IBackgroundSubtractor::apply(img, fgmask, learningRate) (SuBSENSE.cpp:188-612; LOBSTER.cpp:459-581); img continuous, fgmask W*H bytes */
+int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
+/* same, enqueued on the instance's stream; lvb_sync() waits and delivers the mask passed to the matching lvb_apply_async */
+int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
+int lvb_sync(lvb_handle h);
+/* n independent streams, one frame each (the lv::WorkerPool pattern of apps/changedet/src/main.cpp:148-154) */
+int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, double learning_rate);
+/* device-resident variant: d_img rows of d_step bytes, d_fgmask W*H bytes (or null), asynchronous on the instance's stream */
+int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);
+
+/* getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649; LOBSTER.cpp:583-620) */
+int lvb_get_background_image(lvb_handle h, uint8_t* out);
+int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out);
+/* refreshModel(fSamplesRefreshFrac, bForceFGUpdate) (SuBSENSE.cpp:80-105; LOBSTER.cpp:410-441) */
+int lvb_refresh_model(lvb_handle h, float frac, int force_fg);
+/* setAutomaticModelReset / getROICopy / setROI (BackgroundSubtractionUtils.cpp:24-52) */
+int lvb_set_auto_model_reset(lvb_handle h, int enabled);
+int lvb_get_roi(lvb_handle h, uint8_t* out);
+int lvb_set_roi(lvb_handle h, const uint8_t* roi);
+/* getDefaultLearningRate (SuBSENSE/PAWCS 0, LOBSTER 16) */
+double lvb_default_learning_rate(int algo);
+
+/* LBSP::compute2 dense (features2d/src/LBSP.cpp:102-152, 231-237): use_rel=0 -> absolute threshold `thr`;
+ * use_rel=1 -> saturate(ref*rel + thr). ref_or_null = LBSP::setReference image. out: [H][W][C] u16, 2-px border untouched. */
+int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref_or_null, int width, int height, int channels,
+                     int use_rel, float rel, int thr, uint16_t* out, int device);
+
+/* parity / debug: named state buffers in the reference's layout (sample-major [N][H][W][C], maps [H][W]); see DESIGN.md */
+int lvb_state_size(lvb_handle h, const char* name, size_t* bytes);
+int lvb_state_get(lvb_handle h, const char* name, void* out, size_t bytes);
+int lvb_state_set(lvb_handle h, const char* name, const void* in, size_t bytes);
+/* instrumentation: out[0..4] = roi_px, samples_scanned, sample_writes, fg_px, frames (accumulated while enabled) */
+int lvb_set_collect_stats(lvb_handle h, int enabled);
+int lvb_get_stats(lvb_handle h, uint64_t out[5]);
+/* number of kernels this library launched since the process started (bench.py's gpu_launches) */
+uint64_t lvb_kernel_launch_count(void);
+/* per-launch timing of the dominant kernel (phase A) with CUDA events on the instance's stream: enable, run frames, read+reset */
+int lvb_set_profile(lvb_handle h, int enabled);
+int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches);
+/* page-locked host buffers: frames / masks living in them are copied straight to / from the device (no staging copy) */
+int lvb_host_alloc(void** out, size_t bytes);
+int lvb_host_free(void* p);
+/* CUDA stream of the instance (cudaStream_t as void*) so callers can time on it with CUDA events */
+void* lvb_stream(lvb_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,329 @@
+"""Python mirror of the reference's IBackgroundSubtractor surface over the C ABI (include/litiv_b200.h).
+
+Method names follow the reference (modules/video/include/litiv/video/BackgroundSubtractionUtils.hpp:24-47):
+initialize(img, roi) / apply(img, learningRate) -> fgmask / getBackgroundImage() / refreshModel(...).
+The library has no CPU fallback: if the CUDA extension is missing or no device is present, calls raise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import build as _build
+
+ALGO_LOBSTER, ALGO_SUBSENSE, ALGO_PAWCS = 0, 1, 2
+_LIB = None
+
+EXPORTS = [
+    "lvb_last_error", "lvb_device_count", "lvb_default_params", "lvb_create", "lvb_destroy", "lvb_initialize", "lvb_apply",
+    "lvb_apply_async", "lvb_sync", "lvb_apply_batch", "lvb_apply_device", "lvb_get_background_image",
+    "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
+    "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
+    "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
+    "lvb_host_alloc", "lvb_host_free",
+]
+
+
+class LitivError(RuntimeError):
+    """Raised where the reference would throw lv::Exception (utils/defines.hpp.in:109-113)."""
+
+
+class Params(C.Structure):
+    _fields_ = [("rel_lbsp_threshold", C.c_float), ("lbsp_threshold_offset", C.c_int32), ("desc_dist_threshold", C.c_int32),
+                ("color_dist_threshold", C.c_int32), ("n_samples", C.c_int32), ("n_required", C.c_int32),
+                ("n_samples_for_moving_avgs", C.c_int32), ("n_global_words", C.c_int32), ("median_blur_kernel_size", C.c_int32)]
+
+
+def lib_path():
+    return _build.SO
+
+
+def lib():
+    """Loads the in-tree CUDA extension; fails loudly if it has not been built (no fallback path exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_build.SO):
+            raise LitivError("litiv_b200/liblitiv_b200.so is missing: run `python -m litiv_b200.build` (needs nvcc); there is no CPU fallback")
+        L = C.CDLL(_build.SO)
+        L.lvb_last_error.restype = C.c_char_p
+        L.lvb_default_learning_rate.restype = C.c_double
+        L.lvb_kernel_launch_count.restype = C.c_uint64
+        L.lvb_stream.restype = C.c_void_p
+        L.lvb_stream.argtypes = [C.c_void_p]
+        L.lvb_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        L.lvb_destroy.argtypes = [C.c_void_p]
+        L.lvb_initialize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+        L.lvb_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.lvb_apply_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.lvb_sync.argtypes = [C.c_void_p]
+        L.lvb_apply_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.lvb_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]
+        L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_get_background_descriptors_image.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_refresh_model.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.lvb_set_auto_model_reset.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_get_roi.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_set_roi.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_state_size.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.lvb_state_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.lvb_state_set.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t]
+        L.lvb_set_collect_stats.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_lbsp_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
+        L.lvb_default_params.argtypes = [C.c_int, C.c_void_p]
+        L.lvb_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvb_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
+        L.lvb_host_free.argtypes = [C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _chk(rc):
+    if rc != 0:
+        raise LitivError(lib().lvb_last_error().decode())
+
+
+def device_count():
+    return lib().lvb_device_count()
+
+
+def default_params(algo):
+    p = Params()
+    _chk(lib().lvb_default_params(algo, C.byref(p)))
+    return p
+
+
+def kernel_launch_count():
+    return int(lib().lvb_kernel_launch_count())
+
+
+STATE_DTYPES = {
+    "roi": np.uint8, "lastfg": np.uint8, "lastcolor": np.uint8, "lastdesc": np.uint16, "lut": np.uint8,
+    "bg_color": np.uint8, "bg_desc": np.uint16, "T": np.float32, "R": np.float32, "v": np.float32,
+    "Dlast": np.float32, "DminLT": np.float32, "DminST": np.float32, "rawLT": np.float32, "rawST": np.float32,
+    "finLT": np.float32, "finST": np.float32, "dsLT": np.float32, "dsST": np.float32, "unstable": np.uint8,
+    "blinks": np.uint8, "lastraw": np.uint8, "lastrawblink": np.uint8, "dilinv": np.uint8, "rawmask": np.uint8,
+    "ghost": np.uint8, "scalars": np.float64,
+}
+
+
+class _BackgroundSubtractor:
+    """Common drop-in surface (IIBackgroundSubtractor + IBackgroundSubtractorLBSP)."""
+    ALGO = None
+
+    def __init__(self, params=None, device=0, seed=0):
+        self._h = C.c_void_p()
+        self._params = params
+        _chk(lib().lvb_create(self.ALGO, C.byref(params) if params is not None else None, device, seed, C.byref(self._h)))
+        self.shape = None
+        self._pending_mask = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.lvb_destroy(h)
+            self._h = None
+
+    # -- reference API -------------------------------------------------------------------------
+    def initialize(self, img, roi=None):
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0:
+            raise LitivError("provided image for initialization must be non-empty, continuous, and of type 8UC1/3/4")
+        img = np.ascontiguousarray(img)
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        rp = None
+        if roi is not None:
+            roi = np.ascontiguousarray(roi)
+            if roi.dtype != np.uint8 or roi.shape != (h, w):
+                raise LitivError("provided ROI mat size must be equal to the init frame size, and its type must be 8UC1")
+            rp = roi.ctypes.data
+        _chk(lib().lvb_initialize(self._h, img.ctypes.data, w, h, c, w * c, rp))
+        self.shape = (h, w, c)
+
+    def _check_img(self, img):
+        if self.shape is None:
+            raise LitivError("algo & model must be initialized first")
+        img = np.asarray(img)
+        h, w, c = self.shape
+        if img.dtype != np.uint8 or img.shape != ((h, w) if c == 1 and img.ndim == 2 else (h, w, c)):
+            raise LitivError("input image type/size mismatch with initialization type/size")
+        return np.ascontiguousarray(img)
+
+    def apply(self, img, learningRate=None, out=None):
+        img = self._check_img(img)
+        lr = self.getDefaultLearningRate() if learningRate is None else learningRate
+        mask = np.empty(self.shape[:2], np.uint8) if out is None else out
+        _chk(lib().lvb_apply(self._h, img.ctypes.data, mask.ctypes.data, float(lr)))
+        return mask
+
+    def apply_async(self, img, learningRate=None):
+        img = self._check_img(img)
+        lr = self.getDefaultLearningRate() if learningRate is None else learningRate
+        self._pending_mask = np.empty(self.shape[:2], np.uint8)
+        self._pending_img = img
+        _chk(lib().lvb_apply_async(self._h, img.ctypes.data, self._pending_mask.ctypes.data, float(lr)))
+
+    def sync(self):
+        _chk(lib().lvb_sync(self._h))
+        m, self._pending_mask = self._pending_mask, None
+        return m
+
+    def apply_device(self, d_img_ptr, d_step, d_mask_ptr=None, learningRate=None):
+        """device-resident frame (raw CUDA pointers, e.g. torch tensor .data_ptr()); asynchronous on self.stream"""
+        lr = self.getDefaultLearningRate() if learningRate is None else learningRate
+        _chk(lib().lvb_apply_device(self._h, d_img_ptr, d_step, d_mask_ptr, float(lr)))
+
+    def getBackgroundImage(self):
+        if self.shape is None:
+            raise LitivError("algo must be initialized first")
+        h, w, c = self.shape
+        out = np.empty((h, w, c), np.uint8)
+        _chk(lib().lvb_get_background_image(self._h, out.ctypes.data))
+        return out[..., 0] if c == 1 else out
+
+    def getBackgroundDescriptorsImage(self):
+        if self.shape is None:
+            raise LitivError("algo must be initialized first")
+        h, w, c = self.shape
+        out = np.empty((h, w, c), np.uint16)
+        _chk(lib().lvb_get_background_descriptors_image(self._h, out.ctypes.data))
+        return out[..., 0] if c == 1 else out
+
+    def getDefaultLearningRate(self):
+        return lib().lvb_default_learning_rate(self.ALGO)
+
+    def setAutomaticModelReset(self, enabled):
+        _chk(lib().lvb_set_auto_model_reset(self._h, int(bool(enabled))))
+
+    def getROICopy(self):
+        h, w, _ = self.shape
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().lvb_get_roi(self._h, out.ctypes.data))
+        return out
+
+    def setROI(self, roi):
+        roi = np.ascontiguousarray(roi, dtype=np.uint8)
+        _chk(lib().lvb_set_roi(self._h, roi.ctypes.data))
+
+    def refreshModel(self, fSamplesRefreshFrac, bForceFGUpdate=False):
+        _chk(lib().lvb_refresh_model(self._h, float(fSamplesRefreshFrac), int(bool(bForceFGUpdate))))
+
+    # -- parity / instrumentation --------------------------------------------------------------
+    @property
+    def stream(self):
+        return lib().lvb_stream(self._h)
+
+    def state_get(self, name):
+        n = C.c_size_t()
+        _chk(lib().lvb_state_size(self._h, name.encode(), C.byref(n)))
+        out = np.empty(n.value // np.dtype(STATE_DTYPES[name]).itemsize, STATE_DTYPES[name])
+        _chk(lib().lvb_state_get(self._h, name.encode(), out.ctypes.data, n.value))
+        return out
+
+    def state_set(self, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=STATE_DTYPES[name])
+        _chk(lib().lvb_state_set(self._h, name.encode(), arr.ctypes.data, arr.nbytes))
+
+    def set_profile(self, enabled):
+        _chk(lib().lvb_set_profile(self._h, int(bool(enabled))))
+
+    def get_profile(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _chk(lib().lvb_get_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def set_collect_stats(self, enabled):
+        _chk(lib().lvb_set_collect_stats(self._h, int(bool(enabled))))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        _chk(lib().lvb_get_stats(self._h, out))
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+
+class BackgroundSubtractorSuBSENSE(_BackgroundSubtractor):
+    """BackgroundSubtractorSuBSENSE_<lv::CUDA> (reference ctor: BackgroundSubtractorSuBSENSE.hpp:52-57)."""
+    ALGO = ALGO_SUBSENSE
+
+    def __init__(self, nDescDistThresholdOffset=3, nMinColorDistThreshold=30, nBGSamples=50, nRequiredBGSamples=2,
+                 nSamplesForMovingAvgs=100, fRelLBSPThreshold=0.333, device=0, seed=0):
+        p = default_params(ALGO_SUBSENSE)
+        p.desc_dist_threshold, p.color_dist_threshold, p.n_samples = nDescDistThresholdOffset, nMinColorDistThreshold, nBGSamples
+        p.n_required, p.n_samples_for_moving_avgs, p.rel_lbsp_threshold = nRequiredBGSamples, nSamplesForMovingAvgs, fRelLBSPThreshold
+        super().__init__(p, device, seed)
+
+
+class BackgroundSubtractorLOBSTER(_BackgroundSubtractor):
+    """BackgroundSubtractorLOBSTER_<lv::CUDA> (reference ctor: BackgroundSubtractorLOBSTER.hpp:50-55)."""
+    ALGO = ALGO_LOBSTER
+
+    def __init__(self, nDescDistThreshold=4, nColorDistThreshold=30, nBGSamples=35, nRequiredBGSamples=2,
+                 nLBSPThresholdOffset=0, fRelLBSPThreshold=0.333, device=0, seed=0):
+        p = default_params(ALGO_LOBSTER)
+        p.desc_dist_threshold, p.color_dist_threshold, p.n_samples = nDescDistThreshold, nColorDistThreshold, nBGSamples
+        p.n_required, p.lbsp_threshold_offset, p.rel_lbsp_threshold = nRequiredBGSamples, nLBSPThresholdOffset, fRelLBSPThreshold
+        super().__init__(p, device, seed)
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array over page-locked host memory (lvb_host_alloc); frames/masks in it skip the staging copy"""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    _chk(lib().lvb_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    return arr
+
+
+def apply_batch(subtractors, imgs, learningRate):
+    """n independent streams, one frame each, overlapped on the GPU (lvb_apply_batch)."""
+    n = len(subtractors)
+    imgs = [s._check_img(i) for s, i in zip(subtractors, imgs)]
+    masks = [np.empty(s.shape[:2], np.uint8) for s in subtractors]
+    hs = (C.c_void_p * n)(*[s._h for s in subtractors])
+    ip = (C.c_void_p * n)(*[i.ctypes.data for i in imgs])
+    mp = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+    _chk(lib().lvb_apply_batch(hs, ip, mp, n, float(learningRate)))
+    return masks
+
+
+class LBSP:
+    """Dense LBSP extractor (features2d LBSP::compute2). LBSP(20) -> absolute threshold; LBSP(0.333, 0) -> relative."""
+
+    def __init__(self, threshold, nThresholdOffset=None, device=0):
+        if isinstance(threshold, float) or nThresholdOffset is not None:
+            if threshold < 0:
+                raise LitivError("relative LBSP threshold must be non-negative")
+            self.rel, self.thr = float(threshold), int(nThresholdOffset or 0)
+        else:
+            self.rel, self.thr = None, int(threshold)
+        self.ref = None
+        self.device = device
+
+    def setReference(self, img):
+        self.ref = None if img is None else np.ascontiguousarray(img, dtype=np.uint8)
+
+    def windowSize(self):
+        return (5, 5)
+
+    def borderSize(self):
+        return 2
+
+    def descriptorSize(self):
+        return 2
+
+    def compute2(self, img):
+        img = np.ascontiguousarray(img)
+        if img.dtype != np.uint8 or img.size == 0:
+            raise LitivError("input image must be non-empty, continuous, and of type 8UC1/8UC3")
+        h, w = img.shape[:2]
+        c = 1 if img.ndim == 2 else img.shape[2]
+        out = np.zeros((h, w, c), np.uint16)
+        rp = None
+        if self.ref is not None:
+            if self.ref.shape != img.shape:
+                raise LitivError("ref image must be empty, or of the same size/type as the input image")
+            rp = self.ref.ctypes.data
+        _chk(lib().lvb_lbsp_compute(img.ctypes.data, rp, w, h, c, int(self.rel is not None), self.rel or 0.0, self.thr, out.ctypes.data, self.device))
+        return out[..., 0] if c == 1 else out

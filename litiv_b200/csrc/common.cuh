@@ -1,0 +1,186 @@
+// litiv_b200 — device-side building blocks shared by every kernel (sm_100a only).
+//   * Philox4x32-10 counter RNG (replaces libc rand())
+//   * LBSP 16-bit double-cross lookup/threshold on packed bytes (features2d LBSP.hpp:193-224, 275-319)
+//   * sampling patterns (utils opencv.hpp:859-966)
+//   * bit-packed row helpers for the mask post-processing
+//   * TMA (cp.async.bulk.tensor) + mbarrier PTX wrappers
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace lvb {
+
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10
+// ---------------------------------------------------------------------------------------------
+enum { DOM_APPLY = 0, DOM_REFRESH = 1, DOM_REFRESH_START = 2, DOM_PAWCS_A = 3, DOM_PAWCS_B = 4 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for(int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+/// block `blk` of 4 draws for (frame,pixel); each draw is 31 bits like libc rand()
+__device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t frame, uint32_t pixel, uint32_t blk, uint32_t domain) {
+    uint4 r = philox4x32_10(make_uint4(frame, pixel, blk, domain), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    r.x >>= 1; r.y >>= 1; r.z >>= 1; r.w >>= 1;
+    return r;
+}
+__device__ __forceinline__ uint32_t philox_draw(uint64_t seed, uint32_t frame, uint32_t pixel, uint32_t site, uint32_t domain) {
+    const uint4 r = philox_block(seed, frame, pixel, site >> 2, domain);
+    const uint32_t k = site & 3;
+    return k == 0 ? r.x : k == 1 ? r.y : k == 2 ? r.z : r.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LBSP on packed bytes
+// ---------------------------------------------------------------------------------------------
+// bit n <-> (dx,dy): LBSP.hpp:292-294
+__device__ __constant__ const signed char c_lbsp_dx[16] = {-2, 2, 0, 0, -2, 2, 2, -2, 0, -1, 0, 1, -1, 1, 1, -1};
+__device__ __constant__ const signed char c_lbsp_dy[16] = { 0, 0,-2, 2,  2,-2, 2, -2, 1,  0,-1, 0, -1, 1,-1,  1};
+
+struct Lookup16 { uint32_t w[4]; }; // 16 neighbour bytes, byte n of the array = neighbour n
+
+/// gather the 16 neighbours of channel c around (sx,sy) from an interleaved byte tile in shared memory
+template<int CH>
+__device__ __forceinline__ Lookup16 lbsp_lookup_smem(const uchar* tile, int pitch, int sx, int sy, int c) {
+    const uchar* p = tile + sy * pitch + sx * CH + c;
+    Lookup16 L;
+#define LVB_NB(dx, dy) ((uint32_t)p[(dy) * pitch + (dx) * CH])
+    L.w[0] = LVB_NB(-2, 0) | (LVB_NB(2, 0) << 8) | (LVB_NB(0, -2) << 16) | (LVB_NB(0, 2) << 24);
+    L.w[1] = LVB_NB(-2, 2) | (LVB_NB(2, -2) << 8) | (LVB_NB(2, 2) << 16) | (LVB_NB(-2, -2) << 24);
+    L.w[2] = LVB_NB(0, 1) | (LVB_NB(-1, 0) << 8) | (LVB_NB(0, -1) << 16) | (LVB_NB(1, 0) << 24);
+    L.w[3] = LVB_NB(-1, -1) | (LVB_NB(1, 1) << 8) | (LVB_NB(1, -1) << 16) | (LVB_NB(-1, 1) << 24);
+#undef LVB_NB
+    return L;
+}
+
+/// desc = sum_n (|val_n - ref| > t) << n   (strict >, unsigned) — LBSP.hpp:193-224
+__device__ __forceinline__ uint32_t lbsp_threshold(const Lookup16& L, uint32_t ref, uint32_t t) {
+    const uint32_t r4 = ref * 0x01010101u, t4 = t * 0x01010101u;
+    uint32_t d = 0;
+#pragma unroll
+    for(int i = 0; i < 4; ++i) {
+        const uint32_t gt = __vsetgtu4(__vabsdiffu4(L.w[i], r4), t4);      // 0/1 per byte
+        d |= (((gt * 0x00204081u) >> 21) & 0xFu) << (4 * i);                // gather the 4 flag bits
+    }
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling patterns
+// ---------------------------------------------------------------------------------------------
+__device__ __constant__ const signed char c_nb3[8][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
+__device__ __constant__ const signed char c_nb5[24][2] = {
+    {-2, 2}, {-1, 2}, {0, 2}, {1, 2}, {2, 2}, {-2, 1}, {-1, 1}, {0, 1}, {1, 1}, {2, 1}, {-2, 0}, {-1, 0},
+    {1, 0}, {2, 0}, {-2, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, -1}, {-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}};
+__device__ __constant__ const unsigned char c_pat7[49] = {
+    2, 4, 6, 7, 6, 4, 2, 4, 8, 12, 14, 12, 8, 4, 6, 12, 21, 25, 21, 12, 6, 7, 14, 25, 28, 25, 14, 7,
+    6, 12, 21, 25, 21, 12, 6, 4, 8, 12, 14, 12, 8, 4, 2, 4, 6, 7, 6, 4, 2};
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/// opencv.hpp:873-891,909-925 — walk the 7x7 integer Gaussian, clamp to [2,dim-3]
+__device__ __forceinline__ void sample_pos_7x7(uint32_t rnd, int& sx, int& sy, int ox, int oy, int W, int H) {
+    int r = 1 + (int)(rnd % 512u);
+    int i = 0;
+    for(; i < 49; ++i) { r -= c_pat7[i]; if(r <= 0) break; }
+    if(i > 48) i = 48; // unreachable (weights sum to 512)
+    sx = clampi(ox + (i % 7) - 3, 2, W - 3);
+    sy = clampi(oy + (i / 7) - 3, 2, H - 3);
+}
+/// neighbour code: bit 5 set = 3x3 pattern (index in low bits), else 5x5 pattern index
+__device__ __forceinline__ void neighbor_from_code(uint32_t code, int& nx, int& ny, int ox, int oy, int W, int H) {
+    int dx, dy;
+    if(code & 32u) { dx = c_nb3[code & 7u][0]; dy = c_nb3[code & 7u][1]; }
+    else { dx = c_nb5[code & 31u][0]; dy = c_nb5[code & 31u][1]; }
+    nx = clampi(ox + dx, 2, W - 3);
+    ny = clampi(oy + dy, 2, H - 3);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bit-packed rows (1 bit / pixel, 32 pixels / word, row pitch WW words, bits >= W are kept zero)
+// ---------------------------------------------------------------------------------------------
+enum { FILL_ZERO = 0, FILL_ONE = 1, FILL_REPL = 2 };
+
+template<int FILL>
+__device__ __forceinline__ uint32_t row_word(const uint32_t* __restrict__ row, int wi, int WW, int W) {
+    if(wi < 0) {
+        if(FILL == FILL_ZERO) return 0u;
+        if(FILL == FILL_ONE) return 0xFFFFFFFFu;
+        return (row[0] & 1u) ? 0xFFFFFFFFu : 0u;
+    }
+    const int rem = W & 31;
+    if(wi >= WW) {
+        if(FILL == FILL_ZERO) return 0u;
+        if(FILL == FILL_ONE) return 0xFFFFFFFFu;
+        const uint32_t last = row[WW - 1] >> ((W - 1) & 31);
+        return (last & 1u) ? 0xFFFFFFFFu : 0u;
+    }
+    uint32_t w = row[wi];
+    if(rem && wi == WW - 1) {
+        const uint32_t valid = (1u << rem) - 1u;
+        if(FILL == FILL_ONE) w |= ~valid;
+        else if(FILL == FILL_REPL) { if((w >> (rem - 1)) & 1u) w |= ~valid; }
+    }
+    return w;
+}
+/// word whose bit i = source bit (i+d) of the (left,cur,right) triple, |d| <= 31
+__device__ __forceinline__ uint32_t shift_bits(uint32_t left, uint32_t cur, uint32_t right, int d) {
+    if(d == 0) return cur;
+    return d > 0 ? __funnelshift_r(cur, right, d) : __funnelshift_l(left, cur, -d);
+}
+template<int R, bool DILATE>
+__device__ __forceinline__ uint32_t hmorph(uint32_t left, uint32_t cur, uint32_t right) {
+    uint32_t acc = cur;
+#pragma unroll
+    for(int d = 1; d <= R; ++d) {
+        if(DILATE) acc |= shift_bits(left, cur, right, d) | shift_bits(left, cur, right, -d);
+        else acc &= shift_bits(left, cur, right, d) & shift_bits(left, cur, right, -d);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA + mbarrier (PTX ISA 8.x, sm_90+/sm_100a)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LVB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LVB_DONE_%=;\n"
+        "bra LVB_WAIT_%=;\n"
+        "LVB_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+/// 2-D tiled bulk tensor load global -> shared, completion counted on `bar` (out-of-bounds elements read as 0)
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+} // namespace lvb

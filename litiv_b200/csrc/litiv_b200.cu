@@ -1,0 +1,843 @@
+// litiv_b200 — host side of the C ABI (include/litiv_b200.h): per-stream context, HBM layout, kernel sequencing.
+// Single translation unit: the kernels live in the .cuh files included below.
+#include "../../include/litiv_b200.h"
+#include "lobster.cuh"
+#include "postproc.cuh"
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include <cmath>
+#include <cstring>
+#include <atomic>
+#include <algorithm>
+
+using namespace lvb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call); } while(0)
+#define LAUNCHED() do { ++g_launches; CK(cudaGetLastError()); } while(0)
+#define REQUIRE(cond, msg) do { if(!(cond)) throw std::runtime_error(msg); } while(0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if(!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+/// tensor map over an interleaved byte image so one TMA box = (TILE_W+4)x(TILE_H+4) pixels incl. the LBSP halo
+bool make_image_tmap(CUtensorMap* map, const void* ptr, int W, int H, int C, size_t pitch) {
+    std::memset(map, 0, sizeof(*map));
+    EncodeTiledFn fn = get_encode_fn();
+    if(!fn || ((uintptr_t)ptr & 15) || (pitch & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)W * C, (cuuint64_t)H};
+    const cuuint64_t gstr[1] = {(cuuint64_t)pitch};
+    const cuuint32_t box[2] = {(cuuint32_t)tile_pitch(C), (cuuint32_t)TILE_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template<typename T> T* dalloc(size_t n, bool zero = true) {
+    T* p = nullptr;
+    CK(cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)));
+    if(zero) CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return p;
+}
+
+void morph_rect_host(const uint8_t* src, uint8_t* dst, int W, int H, int r) { // dilate only (ROI border ring, init-time)
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) {
+        uint8_t v = 0;
+        for(int dy = -r; dy <= r && !v; ++dy) for(int dx = -r; dx <= r; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if(yy >= 0 && yy < H && xx >= 0 && xx < W && src[(size_t)yy * W + xx]) { v = 255; break; }
+        }
+        dst[(size_t)y * W + x] = v;
+    }
+}
+
+} // namespace
+
+struct lvb_context {
+    int algo = 0, device = 0;
+    Params P{};
+    uint64_t seed = 0;
+    int W = 0, H = 0, C = 0, Wp = 0, WW = 0, dsW = 0, dsH = 0;
+    size_t plane = 0;
+    cudaStream_t stream = nullptr;
+    bool initialized = false;
+    int num_sms = 0, flood_blocks_per_sm = 0;
+    // frame staging
+    uint8_t* d_img = nullptr; size_t ipitch = 0; CUtensorMap tmap_img; int use_tma = 0;
+    const uint8_t* ext_ptr = nullptr; size_t ext_pitch = 0; CUtensorMap tmap_ext; int ext_tma = 0;
+    uint8_t* d_mask = nullptr;
+    uint8_t* h_img = nullptr; uint8_t* h_mask = nullptr; uint8_t* user_mask = nullptr;
+    // model + maps
+    void* bg_color = nullptr; void* bg_desc = nullptr;
+    float4* maps = nullptr; float2* fin = nullptr;
+    void* last_color = nullptr; void* last_desc = nullptr; void* tmp_desc = nullptr;
+    uint32_t* bits = nullptr; // all bit planes, one allocation
+    uint32_t *roi_bits, *raw, *lastraw, *lastrawblink, *blinks, *tmpA, *pre, *reach, *comb, *lastfg, *dilinv, *unstable, *ghost[2], *intent_bits;
+    int ghost_idx = 0;
+    ushort* intents = nullptr;
+    uint8_t* lut = nullptr;
+    FrameCtl* ctl = nullptr;
+    float* dsLT = nullptr; float* dsST = nullptr;
+    std::vector<uint8_t> roi_host;
+    size_t orig_roi_count = 0, roi_count = 0;
+    int collect_stats = 0, median_k = 9;
+    uint64_t stat_frames = 0;
+    bool pending = false;
+    bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
+    bool direct_mask = false;
+
+    size_t col_bytes() const { return C == 1 ? 1 : 4; }
+    size_t desc_bytes() const { return C == 1 ? 2 : 8; }
+
+    void free_all() {
+        void* ptrs[] = {d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST};
+        for(void* p : ptrs) if(p) cudaFree(p);
+        d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
+        bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        if(h_img) cudaFreeHost(h_img);
+        if(h_mask) cudaFreeHost(h_mask);
+        h_img = h_mask = nullptr;
+        initialized = false;
+    }
+};
+
+namespace {
+
+dim3 tile_grid(const lvb_context* c) { return dim3(c->Wp / 32, (c->H + 7) / 8); }
+dim3 word_grid(const lvb_context* c) { return dim3((c->WW + 255) / 256, c->H); }
+
+void get_ctl(lvb_context* c, FrameCtl& f) {
+    CK(cudaMemcpyAsync(&f, c->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+void put_ctl(lvb_context* c, const FrameCtl& f) {
+    CK(cudaMemcpyAsync(c->ctl, &f, sizeof(FrameCtl), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+void launch_refresh(lvb_context* c) {
+    RefreshArgs R{};
+    R.W = c->W; R.H = c->H; R.Wp = c->Wp; R.WW = c->WW; R.CH = c->C; R.N = c->P.n_samples; R.plane = c->plane;
+    R.bg_color = c->bg_color; R.bg_desc = c->bg_desc; R.last_color = c->last_color; R.last_desc = c->last_desc;
+    R.roi_bits = c->roi_bits; R.lastfg_bits = c->lastfg; R.maps = c->algo == LVB_ALGO_SUBSENSE ? c->maps : nullptr;
+    R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
+    if(c->C == 1) refresh_model_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(R);
+    else refresh_model_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(R);
+    LAUNCHED();
+    refresh_done_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
+    LAUNCHED();
+}
+
+
+} // namespace
+
+__global__ void refresh_start_kernel(FrameCtl* ctl, uint64_t seed, uint32_t N) {
+    ctl->refresh_start = philox_draw(seed, ctl->refresh_epoch, 0, 0, DOM_REFRESH_START) % N;
+}
+
+namespace {
+
+/// host-requested refreshModel(frac, force): fill the request in FrameCtl, then the same kernels the frame tail uses
+void request_refresh(lvb_context* c, float frac, bool force) {
+    REQUIRE(c->initialized, "algo must be initialized first");
+    REQUIRE(frac > 0.0f && frac <= 1.0f, "model refresh must be given as a non-null fraction");
+    FrameCtl f; get_ctl(c, f);
+    const uint32_t N = (uint32_t)c->P.n_samples;
+    f.do_refresh = 1; f.set_T_one = 0; f.refresh_force = force ? 1 : 0;
+    f.refresh_count = frac < 1.0f ? (uint32_t)(frac * (float)N) : N;
+    f.refresh_start = 0;
+    put_ctl(c, f);
+    if(frac < 1.0f) { refresh_start_kernel<<<1, 1, 0, c->stream>>>(c->ctl, c->seed, N); LAUNCHED(); }
+    launch_refresh(c);
+    CK(cudaStreamSynchronize(c->stream));
+}
+
+void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size_t step, const uint8_t* roi) {
+    REQUIRE(img && W > 0 && H > 0 && (C == 1 || C == 3 || C == 4), "provided image for initialization must be non-empty, continuous, and of type 8UC1/3/4");
+    REQUIRE(C != 4, "8UC4 input is accepted by the reference's initialize() but its apply() has no 4-channel path; use 8UC1 or 8UC3");
+    REQUIRE(W >= 5 && H >= 5, "image too small for the 5x5 LBSP pattern");
+    REQUIRE(W <= 8192, "frame width above 8192 pixels is not supported");
+    REQUIRE(step >= (size_t)W * C, "row step smaller than a row");
+    CK(cudaSetDevice(c->device));
+    // ROI (BackgroundSubtractionUtils.cpp:82-99, validateROI :28-36)
+    std::vector<uint8_t> r((size_t)W * H, 255);
+    if(roi) {
+        for(size_t i = 0; i < (size_t)W * H; ++i) REQUIRE(roi[i] == 0 || roi[i] == 255, "provided ROI mat values must be 0 or 255 only");
+        std::vector<uint8_t> dil((size_t)W * H);
+        morph_rect_host(roi, dil.data(), W, H, 2);
+        for(size_t i = 0; i < (size_t)W * H; ++i) r[i] = roi[i] | (dil[i] ? 128 : 0); // 255/2 saturate-rounds to 128
+    } else if(c->roi_host.size() == (size_t)W * H && c->W == W && c->H == H) r = c->roi_host; // reuse last ROI if sizes match (:87-88)
+    size_t orig = 0, fin = 0;
+    for(uint8_t v : r) orig += v != 0;
+    REQUIRE(orig > 0, "provided ROI mat contains no useful pixels");
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(x < 2 || y < 2 || x >= W - 2 || y >= H - 2) r[(size_t)y * W + x] = 0;
+    for(uint8_t v : r) fin += v != 0;
+    REQUIRE(fin > 0, "provided ROI mat contains no useful pixels away from borders (descriptors will hit image bounds)");
+
+    c->free_all();
+    c->W = W; c->H = H; c->C = C; c->Wp = (W + 31) / 32 * 32; c->WW = c->Wp / 32; c->plane = (size_t)H * c->Wp;
+    c->dsW = W / 8; c->dsH = H / 8;
+    c->roi_host = r; c->orig_roi_count = orig; c->roi_count = fin;
+    const int N = c->P.n_samples;
+    c->ipitch = ((size_t)W * C + 127) / 128 * 128;
+    c->d_img = dalloc<uint8_t>(c->ipitch * H);
+    c->d_mask = dalloc<uint8_t>((size_t)W * H);
+    CK(cudaMallocHost((void**)&c->h_img, (size_t)W * H * C));
+    CK(cudaMallocHost((void**)&c->h_mask, (size_t)W * H));
+    c->use_tma = make_image_tmap(&c->tmap_img, c->d_img, W, H, C, c->ipitch) ? 1 : 0;
+    c->ext_ptr = nullptr;
+    c->bg_color = dalloc<uint8_t>((size_t)N * c->plane * c->col_bytes());
+    c->bg_desc = dalloc<uint8_t>((size_t)N * c->plane * c->desc_bytes());
+    c->last_color = dalloc<uint8_t>(c->plane * c->col_bytes());
+    c->last_desc = dalloc<uint8_t>(c->plane * c->desc_bytes());
+    c->tmp_desc = dalloc<uint8_t>(c->plane * c->desc_bytes());
+    const size_t bp = (size_t)H * c->WW;
+    c->bits = dalloc<uint32_t>(bp * 15);
+    uint32_t** planes[] = {&c->roi_bits, &c->raw, &c->lastraw, &c->lastrawblink, &c->blinks, &c->tmpA, &c->pre, &c->reach, &c->comb,
+                           &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
+    for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
+    c->ghost_idx = 0;
+    c->intents = dalloc<ushort>(c->plane);
+    c->lut = dalloc<uint8_t>(256);
+    c->ctl = dalloc<FrameCtl>(1);
+    {   // bit-packed ROI
+        std::vector<uint32_t> rb(bp, 0);
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(r[(size_t)y * W + x]) rb[(size_t)y * c->WW + (x >> 5)] |= 1u << (x & 31);
+        CK(cudaMemcpy(c->roi_bits, rb.data(), bp * 4, cudaMemcpyHostToDevice));
+    }
+    {   // LBSP threshold LUT (BackgroundSubtractorLBSP.cpp:29-30, 42-43; quirk Q2)
+        uint8_t lut[256];
+        for(int t = 0; t < 256; ++t) {
+            const float v = C == 1 ? ((float)t * c->P.rel_lbsp_threshold + (float)c->P.lbsp_threshold_offset) / 3 : (float)t * c->P.rel_lbsp_threshold + (float)c->P.lbsp_threshold_offset;
+            const long q = std::lrint((double)v);
+            lut[t] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+        }
+        CK(cudaMemcpy(c->lut, lut, 256, cudaMemcpyHostToDevice));
+    }
+    FrameCtl f{};
+    f.frame_idx = 1; f.aLT = 1.0f; f.aST = 1.0f; f.roi_count = (uint32_t)fin;
+    f.auto_reset = 1; f.median_k = c->P.median_blur_kernel_size;
+    if(c->algo == LVB_ALGO_SUBSENSE) { // SuBSENSE.cpp:112-128
+        const int tot = W * H, qvga = 320 * 240;
+        if(orig >= (size_t)tot / 2 && tot >= qvga) {
+            f.lr_scaling = 1; f.auto_reset = 1; f.use3x3 = !(tot > qvga * 2);
+            const int rawk = std::min((int)std::floor((float)tot / qvga + 0.5f) + c->P.median_blur_kernel_size, 14);
+            f.median_k = (rawk % 2) ? rawk : rawk - 1;
+            f.t_lower = 2.0f; f.t_upper = 256.0f;
+        } else {
+            f.lr_scaling = 0; f.auto_reset = 0; f.use3x3 = 1; f.median_k = c->P.median_blur_kernel_size;
+            f.t_lower = 4.0f; f.t_upper = 512.0f;
+        }
+        if(f.lr_scaling) REQUIRE(W % 8 == 0 && H % 8 == 0, "frame-level analysis needs frame sizes that are multiples of 8 (other sizes: not implemented yet)");
+        c->maps = dalloc<float4>(c->plane * 2);
+        c->fin = dalloc<float2>(c->plane);
+        c->dsLT = dalloc<float>((size_t)c->dsW * c->dsH * C);
+        c->dsST = dalloc<float>((size_t)c->dsW * c->dsH * C);
+        std::vector<float4> m(c->plane * 2);
+        for(size_t i = 0; i < c->plane; ++i) { m[i * 2] = make_float4(f.t_lower, 1.0f, 10.0f, 0.f); m[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        CK(cudaMemcpy(c->maps, m.data(), m.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    c->median_k = f.median_k;
+    REQUIRE(c->median_k >= 1 && c->median_k <= 31 && (c->median_k & 1), "median blur kernel size must be odd and <= 31");
+    // first refresh request: all N slots from slot 0 (SuBSENSE.cpp:184 refreshModel(1.0f); LOBSTER.cpp:455 refreshModel(1.0f,true))
+    f.do_refresh = 1; f.refresh_epoch = 0; f.refresh_start = 0; f.refresh_count = (uint32_t)N; f.refresh_force = c->algo == LVB_ALGO_LOBSTER ? 1 : 0;
+    CK(cudaMemcpy(c->ctl, &f, sizeof(f), cudaMemcpyHostToDevice));
+    // frame upload + init kernel
+    CK(cudaMemcpy2D(c->d_img, c->ipitch, img, step, (size_t)W * C, H, cudaMemcpyHostToDevice));
+    InitArgs I{};
+    I.W = W; I.H = H; I.Wp = c->Wp; I.WW = c->WW; I.img = c->d_img; I.ipitch = c->ipitch; I.last_color = c->last_color; I.last_desc = c->last_desc;
+    I.roi_bits = c->roi_bits; I.lut = c->lut; I.use_tma = c->use_tma;
+    if(C == 1) init_frame_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(I, c->tmap_img);
+    else init_frame_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(I, c->tmap_img);
+    LAUNCHED();
+    c->initialized = true;
+    launch_refresh(c);
+    CK(cudaStreamSynchronize(c->stream));
+    c->stat_frames = 0;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    c->num_sms = prop.multiProcessorCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->flood_blocks_per_sm, pp_flood, 256, 0));
+    REQUIRE(c->flood_blocks_per_sm > 0, "cooperative flood kernel cannot be resident");
+}
+
+uint32_t lr_to_fixed(double lr) {
+    if(std::isinf(lr)) return 0xFFFFFFFFu;
+    if(lr > 0) { const double v = std::ceil(lr); return v >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)v; }
+    return 0;
+}
+
+/// enqueue one frame on the instance's stream; the frame is already in device memory at (img,pitch)
+void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUtensorMap& tmap, int use_tma, uint8_t* d_mask_out, double lr) {
+    const int W = c->W, H = c->H, C = c->C;
+    cudaStream_t st = c->stream;
+    const bool sub = c->algo == LVB_ALGO_SUBSENSE;
+    SubArgs A{};
+    A.W = W; A.H = H; A.Wp = c->Wp; A.WW = c->WW; A.N = c->P.n_samples; A.REQ = c->P.n_required; A.plane = c->plane;
+    A.img = img; A.ipitch = pitch; A.bg_color = c->bg_color; A.bg_desc = c->bg_desc; A.maps = c->maps; A.fin = c->fin;
+    A.last_color = c->last_color; A.last_desc = sub ? c->last_desc : c->tmp_desc; A.roi_bits = c->roi_bits; A.raw_bits = c->raw; A.unstable_bits = c->unstable;
+    A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
+    A.intent_bits = c->intent_bits; A.intents = c->intents; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
+    A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
+    A.use_tma = use_tma; A.collect_stats = c->collect_stats;
+    PhaseBArgs B{};
+    B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane; B.img = img; B.ipitch = pitch;
+    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_desc = A.last_desc; B.intent_bits = c->intent_bits; B.intents = c->intents;
+    PostArgs P{};
+    P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
+    P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv;
+    P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+    const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c);
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
+    if(sub) {
+        if(C == 1) subsense_phaseA<1><<<tg, tb, 0, st>>>(A, tmap); else subsense_phaseA<3><<<tg, tb, 0, st>>>(A, tmap);
+        LAUNCHED();
+        if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
+        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
+        LAUNCHED();
+        c->ghost_idx ^= 1;
+        pp_blink_dilate<<<wg, 256, 0, st>>>(P); LAUNCHED();
+        pp_erode_seed<<<wg, 256, 0, st>>>(P); LAUNCHED();
+        {
+            int bands = (H + FLOOD_BAND - 1) / FLOOD_BAND;
+            int blocks = std::max(std::min((bands + 7) / 8, c->num_sms * c->flood_blocks_per_sm), 1);
+            void* args[] = {(void*)&P, (void*)&bands};
+            CK(cudaLaunchCooperativeKernel((void*)pp_flood, dim3(blocks), dim3(256), args, 0, st));
+            LAUNCHED();
+        }
+        pp_combine<<<wg, 256, 0, st>>>(P); LAUNCHED();
+        pp_median<<<tg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
+        pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED();
+        pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED();
+        DownsampleArgs D{};
+        D.W = W; D.H = H; D.CH = C; D.dsW = c->dsW; D.dsH = c->dsH; D.img = img; D.ipitch = pitch; D.dsLT = c->dsLT; D.dsST = c->dsST; D.ctl = c->ctl;
+        const int nds = c->dsW * c->dsH;
+        if(nds > 0) {
+            if(C == 1) downsample_motion_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(D); else downsample_motion_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(D);
+            LAUNCHED();
+        }
+        TailArgs T{};
+        T.ctl = c->ctl; T.lut = c->lut; T.rel = c->P.rel_lbsp_threshold; T.lbsp_off = c->P.lbsp_threshold_offset; T.min_color = c->P.color_dist_threshold;
+        T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed;
+        subsense_tail_kernel<<<1, 256, 0, st>>>(T); LAUNCHED();
+        launch_refresh(c);
+    } else { // LOBSTER
+        if(C == 1) lobster_phaseA<1><<<tg, tb, 0, st>>>(A, tmap); else lobster_phaseA<3><<<tg, tb, 0, st>>>(A, tmap);
+        LAUNCHED();
+        if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
+        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
+        LAUNCHED();
+        pp_median<<<tg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
+        lobster_tail_kernel<<<1, 1, 0, st>>>(c->ctl); LAUNCHED();
+    }
+    if(c->collect_stats) ++c->stat_frames;
+}
+
+void check_apply(lvb_context* c, const void* img, double lr) {
+    REQUIRE(c->initialized, "algo & model must be initialized first");
+    REQUIRE(img != nullptr, "input image type/size mismatch with initialization type/size");
+    if(c->algo == LVB_ALGO_LOBSTER) REQUIRE(lr > 0, "learning rate must be a positive value; faster learning is achieved with smaller values");
+    REQUIRE(!std::isnan(lr), "learning rate must not be NaN");
+}
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if(cudaPointerGetAttributes(&at, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+void apply_async(lvb_context* c, const uint8_t* img, uint8_t* mask, double lr) {
+    check_apply(c, img, lr);
+    REQUIRE(mask != nullptr, "output mask must be provided");
+    REQUIRE(!c->pending, "a previous lvb_apply_async has not been collected with lvb_sync");
+    CK(cudaSetDevice(c->device));
+    const uint8_t* src = img;
+    if(!is_pinned(img)) { std::memcpy(c->h_img, img, (size_t)c->W * c->H * c->C); src = c->h_img; } // pageable -> pinned staging
+    CK(cudaMemcpy2DAsync(c->d_img, c->ipitch, src, (size_t)c->W * c->C, (size_t)c->W * c->C, c->H, cudaMemcpyHostToDevice, c->stream));
+    enqueue_frame(c, c->d_img, c->ipitch, c->tmap_img, c->use_tma, c->d_mask, lr);
+    c->direct_mask = is_pinned(mask);
+    CK(cudaMemcpyAsync(c->direct_mask ? mask : c->h_mask, c->d_mask, (size_t)c->W * c->H, cudaMemcpyDeviceToHost, c->stream));
+    c->user_mask = mask; c->pending = true;
+}
+void sync(lvb_context* c) {
+    CK(cudaStreamSynchronize(c->stream));
+    if(c->pending) { if(!c->direct_mask) std::memcpy(c->user_mask, c->h_mask, (size_t)c->W * c->H); c->pending = false; }
+}
+
+// ---- state export / import in the reference's layout (tests + checkpointing) ----
+struct StateDesc { const char* name; int kind; };
+enum { K_BITS, K_MAPF, K_FIN, K_COLPLANE, K_DESCPLANE, K_BGCOL, K_BGDESC, K_LUT, K_DS, K_ROI, K_SCALARS };
+
+uint32_t* bits_by_name(lvb_context* c, const std::string& n) {
+    if(n == "lastfg") return c->lastfg; if(n == "unstable") return c->unstable; if(n == "blinks") return c->blinks;
+    if(n == "lastraw") return c->lastraw; if(n == "lastrawblink") return c->lastrawblink; if(n == "dilinv") return c->dilinv;
+    if(n == "rawmask") return c->raw; if(n == "ghost") return c->ghost[c->ghost_idx];
+    return nullptr;
+}
+int map_index(const std::string& n) {
+    static const char* names[8] = {"T", "R", "v", "Dlast", "DminLT", "DminST", "rawLT", "rawST"};
+    for(int i = 0; i < 8; ++i) if(n == names[i]) return i;
+    return -1;
+}
+size_t state_bytes(lvb_context* c, const std::string& n) {
+    const size_t npx = (size_t)c->W * c->H;
+    const bool sub = c->algo == LVB_ALGO_SUBSENSE;
+    if(n == "scalars") return 16 * sizeof(double);
+    if(n == "roi") return npx;
+    if(n == "lut") return 256;
+    if(n == "lastcolor") return npx * c->C;
+    if(n == "lastdesc") return npx * c->C * 2;
+    if(n == "bg_color") return npx * c->C * c->P.n_samples;
+    if(n == "bg_desc") return npx * c->C * 2 * c->P.n_samples;
+    if(n == "lastfg" || n == "rawmask") return npx;
+    if(sub) {
+        if(bits_by_name(c, n)) return npx;
+        if(map_index(n) >= 0 || n == "finLT" || n == "finST") return npx * 4;
+        if(n == "dsLT" || n == "dsST") return (size_t)c->dsW * c->dsH * c->C * 4;
+    }
+    throw std::runtime_error("unknown state buffer: " + n);
+}
+
+void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
+    REQUIRE(c->initialized, "algo must be initialized first");
+    REQUIRE(bytes == state_bytes(c, n), "size mismatch for state buffer " + n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
+    const size_t npx = (size_t)W * H;
+    if(n == "scalars") {
+        FrameCtl f; get_ctl(c, f);
+        double* d = (double*)out; std::memset(d, 0, bytes);
+        d[0] = (double)f.frame_idx - 1; d[1] = f.frames_since_reset; d[2] = f.cooldown; d[3] = f.auto_reset; d[4] = f.lr_scaling; d[5] = f.use3x3;
+        d[6] = c->median_k; d[7] = f.t_lower; d[8] = f.t_upper; d[9] = f.last_nonzero_ratio; d[10] = (double)c->roi_count; d[11] = (double)c->orig_roi_count; d[12] = f.refresh_epoch;
+        return;
+    }
+    if(n == "roi") { std::memcpy(out, c->roi_host.data(), npx); return; }
+    if(n == "lut") { CK(cudaMemcpy(out, c->lut, 256, cudaMemcpyDeviceToHost)); return; }
+    if(uint32_t* b = bits_by_name(c, n)) {
+        std::vector<uint32_t> h((size_t)H * WW);
+        CK(cudaMemcpy(h.data(), b, h.size() * 4, cudaMemcpyDeviceToHost));
+        uint8_t* o = (uint8_t*)out;
+        const bool as01 = (n == "unstable");
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) { const bool v = (h[(size_t)y * WW + (x >> 5)] >> (x & 31)) & 1u; o[(size_t)y * W + x] = v ? (as01 ? 1 : 255) : 0; }
+        return;
+    }
+    const int mi = map_index(n);
+    if(mi >= 0) {
+        std::vector<float> h(c->plane * 8);
+        CK(cudaMemcpy(h.data(), c->maps, h.size() * 4, cudaMemcpyDeviceToHost));
+        float* o = (float*)out;
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) o[(size_t)y * W + x] = h[((size_t)y * Wp + x) * 8 + mi];
+        return;
+    }
+    if(n == "finLT" || n == "finST") {
+        std::vector<float> h(c->plane * 2);
+        CK(cudaMemcpy(h.data(), c->fin, h.size() * 4, cudaMemcpyDeviceToHost));
+        float* o = (float*)out; const int k = n == "finLT" ? 0 : 1;
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) o[(size_t)y * W + x] = h[((size_t)y * Wp + x) * 2 + k];
+        return;
+    }
+    if(n == "dsLT" || n == "dsST") { CK(cudaMemcpy(out, n == "dsLT" ? c->dsLT : c->dsST, bytes, cudaMemcpyDeviceToHost)); return; }
+    auto unpack_col = [&](const uint8_t* h, uint8_t* o) {
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k)
+            o[((size_t)y * W + x) * C + k] = C == 1 ? h[(size_t)y * Wp + x] : h[((size_t)y * Wp + x) * 4 + k];
+    };
+    auto unpack_desc = [&](const uint16_t* h, uint16_t* o) {
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k)
+            o[((size_t)y * W + x) * C + k] = C == 1 ? h[(size_t)y * Wp + x] : h[((size_t)y * Wp + x) * 4 + k];
+    };
+    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes()); CK(cudaMemcpy(h.data(), c->last_color, h.size(), cudaMemcpyDeviceToHost)); unpack_col(h.data(), (uint8_t*)out); return; }
+    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2); CK(cudaMemcpy(h.data(), c->last_desc, h.size() * 2, cudaMemcpyDeviceToHost)); unpack_desc(h.data(), (uint16_t*)out); return; }
+    if(n == "bg_color") {
+        std::vector<uint8_t> h(c->plane * c->col_bytes());
+        for(int s = 0; s < c->P.n_samples; ++s) {
+            CK(cudaMemcpy(h.data(), (uint8_t*)c->bg_color + (size_t)s * h.size(), h.size(), cudaMemcpyDeviceToHost));
+            unpack_col(h.data(), (uint8_t*)out + (size_t)s * npx * C);
+        }
+        return;
+    }
+    if(n == "bg_desc") {
+        std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2);
+        for(int s = 0; s < c->P.n_samples; ++s) {
+            CK(cudaMemcpy(h.data(), (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.size() * 2, cudaMemcpyDeviceToHost));
+            unpack_desc(h.data(), (uint16_t*)out + (size_t)s * npx * C);
+        }
+        return;
+    }
+    throw std::runtime_error("unknown state buffer: " + n);
+}
+
+void state_set(lvb_context* c, const std::string& n, const void* in, size_t bytes) {
+    REQUIRE(c->initialized, "algo must be initialized first");
+    REQUIRE(bytes == state_bytes(c, n), "size mismatch for state buffer " + n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
+    const size_t npx = (size_t)W * H;
+    if(n == "scalars") {
+        const double* d = (const double*)in;
+        FrameCtl f; get_ctl(c, f);
+        f.frame_idx = (uint32_t)d[0] + 1; f.frames_since_reset = (uint32_t)d[1]; f.cooldown = (uint32_t)d[2]; f.auto_reset = d[3] != 0;
+        f.refresh_epoch = (uint32_t)d[12];
+        if(c->algo == LVB_ALGO_SUBSENSE) {
+            f.lr_scaling = d[4] != 0; f.use3x3 = d[5] != 0; c->median_k = (int)d[6]; f.median_k = c->median_k;
+            f.t_lower = (float)d[7]; f.t_upper = (float)d[8]; f.last_nonzero_ratio = (float)d[9];
+            const uint32_t avg = (uint32_t)c->P.n_samples_for_moving_avgs;
+            f.aLT = 1.0f / (float)std::min(f.frame_idx, avg); f.aST = 1.0f / (float)std::min(f.frame_idx, avg / 4u);
+        }
+        put_ctl(c, f);
+        return;
+    }
+    REQUIRE(n != "roi", "use lvb_set_roi");
+    if(n == "lut") { CK(cudaMemcpy(c->lut, in, 256, cudaMemcpyHostToDevice)); return; }
+    if(uint32_t* b = bits_by_name(c, n)) {
+        std::vector<uint32_t> h((size_t)H * WW, 0);
+        const uint8_t* s = (const uint8_t*)in;
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(s[(size_t)y * W + x]) h[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
+        CK(cudaMemcpy(b, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        return;
+    }
+    const int mi = map_index(n);
+    if(mi >= 0) {
+        std::vector<float> h(c->plane * 8);
+        CK(cudaMemcpy(h.data(), c->maps, h.size() * 4, cudaMemcpyDeviceToHost));
+        const float* s = (const float*)in;
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) h[((size_t)y * Wp + x) * 8 + mi] = s[(size_t)y * W + x];
+        CK(cudaMemcpy(c->maps, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        if(mi == 3 || mi == 7) { // ghost flag is derived state: rawST > 0.995 && Dlast < 0.01 inside the ROI
+            std::vector<uint32_t> g((size_t)H * WW, 0);
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) {
+                const float* px = &h[((size_t)y * Wp + x) * 8];
+                if(c->roi_host[(size_t)y * W + x] && px[7] > 0.995f && px[3] < 0.010f) g[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
+            }
+            CK(cudaMemcpy(c->ghost[c->ghost_idx], g.data(), g.size() * 4, cudaMemcpyHostToDevice));
+        }
+        return;
+    }
+    if(n == "finLT" || n == "finST") {
+        std::vector<float> h(c->plane * 2);
+        CK(cudaMemcpy(h.data(), c->fin, h.size() * 4, cudaMemcpyDeviceToHost));
+        const float* s = (const float*)in; const int k = n == "finLT" ? 0 : 1;
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) h[((size_t)y * Wp + x) * 2 + k] = s[(size_t)y * W + x];
+        CK(cudaMemcpy(c->fin, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        return;
+    }
+    if(n == "dsLT" || n == "dsST") { CK(cudaMemcpy(n == "dsLT" ? c->dsLT : c->dsST, in, bytes, cudaMemcpyHostToDevice)); return; }
+    auto pack_col = [&](const uint8_t* s, uint8_t* h) {
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k) {
+            if(C == 1) h[(size_t)y * Wp + x] = s[(size_t)y * W + x]; else h[((size_t)y * Wp + x) * 4 + k] = s[((size_t)y * W + x) * C + k];
+        }
+    };
+    auto pack_desc = [&](const uint16_t* s, uint16_t* h) {
+        for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k) {
+            if(C == 1) h[(size_t)y * Wp + x] = s[(size_t)y * W + x]; else h[((size_t)y * Wp + x) * 4 + k] = s[((size_t)y * W + x) * C + k];
+        }
+    };
+    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes(), 0); pack_col((const uint8_t*)in, h.data()); CK(cudaMemcpy(c->last_color, h.data(), h.size(), cudaMemcpyHostToDevice)); return; }
+    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); CK(cudaMemcpy(c->last_desc, h.data(), h.size() * 2, cudaMemcpyHostToDevice)); return; }
+    if(n == "bg_color") {
+        std::vector<uint8_t> h(c->plane * c->col_bytes(), 0);
+        for(int s = 0; s < c->P.n_samples; ++s) {
+            pack_col((const uint8_t*)in + (size_t)s * npx * C, h.data());
+            CK(cudaMemcpy((uint8_t*)c->bg_color + (size_t)s * h.size(), h.data(), h.size(), cudaMemcpyHostToDevice));
+        }
+        return;
+    }
+    if(n == "bg_desc") {
+        std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0);
+        for(int s = 0; s < c->P.n_samples; ++s) {
+            pack_desc((const uint16_t*)in + (size_t)s * npx * C, h.data());
+            CK(cudaMemcpy((uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        }
+        return;
+    }
+    throw std::runtime_error("unknown state buffer: " + n);
+}
+
+void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
+    REQUIRE(c->initialized, "algo must be initialized first");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->W * c->H * c->C;
+    uint8_t* dc = nullptr; uint16_t* dd = nullptr;
+    if(out_color) dc = dalloc<uint8_t>(n, false); else dd = dalloc<uint16_t>(n, false);
+    if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
+    else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if(e == cudaSuccess) e = out_color ? cudaMemcpyAsync(out_color, dc, n, cudaMemcpyDeviceToHost, c->stream) : cudaMemcpyAsync(out_desc, dd, n * 2, cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(dc); cudaFree(dd);
+    CK(e);
+}
+
+} // namespace
+
+#define LVB_TRY try {
+#define LVB_CATCH } catch(const std::exception& e) { g_err = e.what(); return 1; } return 0;
+
+extern "C" {
+
+const char* lvb_last_error(void) { return g_err.c_str(); }
+
+int lvb_device_count(void) {
+    int n = 0;
+    if(cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lvb_default_params(int algo, lvb_params* out) {
+    LVB_TRY
+    REQUIRE(out != nullptr, "null output");
+    REQUIRE(algo >= 0 && algo <= 2, "unknown algorithm id");
+    lvb_params p{};
+    p.rel_lbsp_threshold = 0.333f; p.lbsp_threshold_offset = 0; p.median_blur_kernel_size = 9; p.n_samples_for_moving_avgs = 100; p.n_global_words = 25;
+    if(algo == LVB_ALGO_LOBSTER) { p.desc_dist_threshold = 4; p.color_dist_threshold = 30; p.n_samples = 35; p.n_required = 2; }
+    if(algo == LVB_ALGO_SUBSENSE) { p.desc_dist_threshold = 3; p.color_dist_threshold = 30; p.n_samples = 50; p.n_required = 2; }
+    if(algo == LVB_ALGO_PAWCS) { p.desc_dist_threshold = 2; p.color_dist_threshold = 20; p.n_samples = 50; p.n_required = 0; }
+    *out = p;
+    LVB_CATCH
+}
+double lvb_default_learning_rate(int algo) { return algo == LVB_ALGO_LOBSTER ? 16.0 : 0.0; }
+
+int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lvb_handle* out) {
+    LVB_TRY
+    REQUIRE(out != nullptr, "null output handle");
+    REQUIRE(algo == LVB_ALGO_LOBSTER || algo == LVB_ALGO_SUBSENSE, algo == LVB_ALGO_PAWCS ? "PAWCS is not available in this build" : "unknown algorithm id");
+    lvb_params p;
+    if(params) p = *params; else lvb_default_params(algo, &p);
+    REQUIRE(p.n_samples > 0 && p.n_required <= p.n_samples, "algo cannot require more sample matches than sample count in model");
+    REQUIRE(p.n_samples <= 255, "at most 255 samples per pixel are supported");
+    REQUIRE(p.color_dist_threshold > 0 || p.desc_dist_threshold > 0, "distance thresholds must be positive values");
+    REQUIRE(p.rel_lbsp_threshold >= 0, "relative threshold for LBSP features must be non-negative");
+    REQUIRE(p.n_samples_for_moving_avgs >= 4, "moving average window must be >= 4");
+    int ndev = lvb_device_count();
+    REQUIRE(ndev > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
+    REQUIRE(device >= 0 && device < ndev, "invalid CUDA device id");
+    CK(cudaSetDevice(device));
+    lvb_context* c = new lvb_context();
+    c->algo = algo; c->device = device; c->seed = seed;
+    static_assert(sizeof(Params) == sizeof(lvb_params), "params mirror out of sync");
+    std::memcpy(&c->P, &p, sizeof(p));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if(e != cudaSuccess) { delete c; CK(e); }
+    *out = c;
+    LVB_CATCH
+}
+int lvb_destroy(lvb_handle h) {
+    if(!h) return 0;
+    cudaSetDevice(h->device);
+    if(h->stream) { cudaStreamSynchronize(h->stream); }
+    h->free_all();
+    if(h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+void* lvb_stream(lvb_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int lvb_initialize(lvb_handle h, const uint8_t* img, int width, int height, int channels, size_t step, const uint8_t* roi) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    do_initialize(h, img, width, height, channels, step, roi);
+    LVB_CATCH
+}
+int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double lr) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    apply_async(h, img, fgmask, lr);
+    sync(h);
+    LVB_CATCH
+}
+int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double lr) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    apply_async(h, img, fgmask, lr);
+    LVB_CATCH
+}
+int lvb_sync(lvb_handle h) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    CK(cudaSetDevice(h->device));
+    sync(h);
+    LVB_CATCH
+}
+int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* masks, int n, double lr) {
+    LVB_TRY
+    REQUIRE(hs && imgs && masks && n >= 0, "bad batch arguments");
+    for(int i = 0; i < n; ++i) { REQUIRE(hs[i] != nullptr, "null handle in batch"); apply_async(hs[i], imgs[i], masks[i], lr); }
+    for(int i = 0; i < n; ++i) { CK(cudaSetDevice(hs[i]->device)); sync(hs[i]); }
+    LVB_CATCH
+}
+int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_mask, double lr) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    check_apply(h, d_img, lr);
+    REQUIRE(d_step >= (size_t)h->W * h->C, "row step smaller than a row");
+    CK(cudaSetDevice(h->device));
+    if(h->ext_ptr != d_img || h->ext_pitch != d_step) {
+        h->ext_tma = make_image_tmap(&h->tmap_ext, d_img, h->W, h->H, h->C, d_step) ? 1 : 0;
+        h->ext_ptr = d_img; h->ext_pitch = d_step;
+    }
+    enqueue_frame(h, d_img, d_step, h->tmap_ext, h->ext_tma, d_mask ? d_mask : h->d_mask, lr);
+    LVB_CATCH
+}
+int lvb_get_background_image(lvb_handle h, uint8_t* out) {
+    LVB_TRY
+    REQUIRE(h && out, "null argument");
+    get_bg_image(h, out, nullptr);
+    LVB_CATCH
+}
+int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out) {
+    LVB_TRY
+    REQUIRE(h && out, "null argument");
+    get_bg_image(h, nullptr, out);
+    LVB_CATCH
+}
+int lvb_refresh_model(lvb_handle h, float frac, int force_fg) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    CK(cudaSetDevice(h->device));
+    request_refresh(h, frac, force_fg != 0);
+    LVB_CATCH
+}
+int lvb_set_auto_model_reset(lvb_handle h, int enabled) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    REQUIRE(h->initialized, "algo must be initialized first");
+    CK(cudaSetDevice(h->device));
+    FrameCtl f; get_ctl(h, f); f.auto_reset = enabled ? 1 : 0; put_ctl(h, f);
+    LVB_CATCH
+}
+int lvb_get_roi(lvb_handle h, uint8_t* out) {
+    LVB_TRY
+    REQUIRE(h && out, "null argument");
+    REQUIRE(!h->roi_host.empty(), "no ROI set");
+    std::memcpy(out, h->roi_host.data(), h->roi_host.size());
+    LVB_CATCH
+}
+int lvb_set_roi(lvb_handle h, const uint8_t* roi) {
+    LVB_TRY
+    REQUIRE(h && roi, "provided ROI must be non-empty and of type 8UC1");
+    REQUIRE(h->initialized, "setROI before initialize(): pass the ROI to lvb_initialize instead");
+    // IIBackgroundSubtractor::setROI (BackgroundSubtractionUtils.cpp:38-48): validate, then re-initialise from the current background image
+    const size_t npx = (size_t)h->W * h->H;
+    size_t nz = 0;
+    for(size_t i = 0; i < npx; ++i) nz += roi[i] != 0;
+    REQUIRE(nz > 0, "provided ROI must have at least one valid pixel");
+    std::vector<uint8_t> bg(npx * h->C), r(roi, roi + npx);
+    get_bg_image(h, bg.data(), nullptr);
+    do_initialize(h, bg.data(), h->W, h->H, h->C, (size_t)h->W * h->C, r.data());
+    LVB_CATCH
+}
+int lvb_state_size(lvb_handle h, const char* name, size_t* bytes) {
+    LVB_TRY
+    REQUIRE(h && name && bytes, "null argument");
+    REQUIRE(h->initialized, "algo must be initialized first");
+    *bytes = state_bytes(h, name);
+    LVB_CATCH
+}
+int lvb_state_get(lvb_handle h, const char* name, void* out, size_t bytes) {
+    LVB_TRY
+    REQUIRE(h && name && out, "null argument");
+    state_get(h, name, out, bytes);
+    LVB_CATCH
+}
+int lvb_state_set(lvb_handle h, const char* name, const void* in, size_t bytes) {
+    LVB_TRY
+    REQUIRE(h && name && in, "null argument");
+    state_set(h, name, in, bytes);
+    LVB_CATCH
+}
+int lvb_set_collect_stats(lvb_handle h, int enabled) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    h->collect_stats = enabled ? 1 : 0;
+    LVB_CATCH
+}
+int lvb_get_stats(lvb_handle h, uint64_t out[5]) {
+    LVB_TRY
+    REQUIRE(h && out, "null argument");
+    REQUIRE(h->initialized, "algo must be initialized first");
+    CK(cudaSetDevice(h->device));
+    FrameCtl f; get_ctl(h, f);
+    out[0] = (uint64_t)h->roi_count * h->stat_frames; out[1] = f.stat_scanned; out[2] = f.stat_writes; out[3] = f.stat_fg; out[4] = h->stat_frames;
+    LVB_CATCH
+}
+uint64_t lvb_kernel_launch_count(void) { return g_launches.load(); }
+int lvb_set_profile(lvb_handle h, int enabled) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    h->profile = enabled != 0;
+    LVB_CATCH
+}
+int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches) {
+    LVB_TRY
+    REQUIRE(h && ms_total && launches, "null argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for(size_t i = 0; i + 1 < h->prof_events.size(); i += 2) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, h->prof_events[i], h->prof_events[i + 1]));
+        h->prof_ms += ms; ++h->prof_n;
+        cudaEventDestroy(h->prof_events[i]); cudaEventDestroy(h->prof_events[i + 1]);
+    }
+    h->prof_events.clear();
+    *ms_total = h->prof_ms; *launches = h->prof_n;
+    h->prof_ms = 0; h->prof_n = 0;
+    LVB_CATCH
+}
+int lvb_host_alloc(void** out, size_t bytes) {
+    LVB_TRY
+    REQUIRE(out != nullptr, "null argument");
+    CK(cudaMallocHost(out, bytes));
+    LVB_CATCH
+}
+int lvb_host_free(void* p) { if(p) cudaFreeHost(p); return 0; }
+
+int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C, int use_rel, float rel, int thr, uint16_t* out, int device) {
+    LVB_TRY
+    REQUIRE(img && out && (C == 1 || C == 3), "input image must be non-empty, continuous, and of type 8UC1/8UC3");
+    REQUIRE(W >= 5 && H >= 5, "input image size is too small to compute descriptors with current patch size");
+    REQUIRE(!use_rel || rel >= 0, "lbsp internal relative threshold must be non-negative");
+    REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const size_t pitch = ((size_t)W * C + 127) / 128 * 128, nout = (size_t)W * H * C;
+    uint8_t* d_img = dalloc<uint8_t>(pitch * H), *d_ref = nullptr;
+    uint16_t* d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    try {
+        d_out = dalloc<uint16_t>(nout, false);
+        CK(cudaMemcpy2D(d_img, pitch, img, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice));
+        if(ref) { d_ref = dalloc<uint8_t>(pitch * H); CK(cudaMemcpy2D(d_ref, pitch, ref, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice)); }
+        CK(cudaMemcpy(d_out, out, nout * 2, cudaMemcpyHostToDevice)); // the 2-px border keeps the caller's content, as in the reference
+        CUtensorMap tmap;
+        LbspArgs A{};
+        A.W = W; A.H = H; A.img = d_img; A.ipitch = pitch; A.ref = d_ref; A.rpitch = pitch; A.out = d_out; A.use_rel = use_rel; A.rel = rel; A.thr = thr;
+        A.use_tma = make_image_tmap(&tmap, d_img, W, H, C, pitch) ? 1 : 0;
+        const dim3 g((W + 31) / 32, (H + 7) / 8), b(32, 8);
+        if(C == 1) lbsp_dense_kernel<1><<<g, b>>>(A, tmap); else lbsp_dense_kernel<3><<<g, b>>>(A, tmap);
+        LAUNCHED();
+        CK(cudaMemcpy(out, d_out, nout * 2, cudaMemcpyDeviceToHost));
+    } catch(...) { cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out); throw; }
+    cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out);
+    (void)e;
+    LVB_CATCH
+}
+
+} // extern "C"

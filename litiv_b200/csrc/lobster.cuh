@@ -1,0 +1,230 @@
+// litiv_b200 — LOBSTER per-frame kernel (replaces BackgroundSubtractorLOBSTER_<NonParallel>::apply,
+// reference video/src/BackgroundSubtractorLOBSTER.cpp:459-581), the dense LBSP extractor
+// (LBSP::compute2, features2d/src/LBSP.cpp:102-152) and the shared initialisation / background-image kernels.
+#pragma once
+#include "subsense.cuh"
+
+namespace lvb {
+
+template<int CH>
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    constexpr int PITCH = tile_pitch(CH);
+    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uchar s_lut[256];
+    __shared__ uint32_t s_cnt[4];
+
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    s_lut[tid] = A.lut[tid];
+    if(tid < 4) s_cnt[tid] = 0;
+    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool in_img = (x < A.W) && (y < A.H);
+    const int wi = y * A.WW + (x >> 5);
+    const uint32_t lane_bit = 1u << (x & 31);
+    const uint32_t w_roi = (y < A.H && (x >> 5) < A.WW) ? A.roi_bits[wi] : 0u;
+    const bool active = in_img && (w_roi & lane_bit);
+    const size_t pix = (size_t)y * A.Wp + x;
+    const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+    bool is_fg = false, has_intent = false;
+    uint32_t scanned = 0, writes = 0;
+
+    uint32_t cur[CH];
+    Col cur_pack;
+#pragma unroll
+    for(int c = 0; c < CH; ++c) cur[c] = s_tile[sy * PITCH + sx * CH + c];
+    if constexpr (CH == 1) cur_pack = (uchar)cur[0]; else cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16);
+
+    if(active) {
+        const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
+        const uint32_t colorThr = (uint32_t)A.min_color, descThr = (uint32_t)A.desc_off;
+        const uint32_t totD = descThr * 3u, totC = colorThr * 3u, scD = totD >> 1, scC = totC >> 1;
+        Lookup16 L[CH];
+#pragma unroll
+        for(int c = 0; c < CH; ++c) L[c] = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+        const Col* bgc = (const Col*)A.bg_color + pix;
+        const Desc* bgd = (const Desc*)A.bg_desc + pix;
+        uint32_t good = 0, s = 0;
+        while(good < REQ && s < N) { // LOBSTER.cpp:481-495 / :533-553
+            const Col bc = bgc[(size_t)s * A.plane];
+            bool ok = true;
+            uint32_t tc = 0;
+#pragma unroll
+            for(int c = 0; c < CH; ++c) {
+                const uint32_t b = col_get(bc, c);
+                const uint32_t cd = cur[c] > b ? cur[c] - b : b - cur[c];
+                ok = ok && (cd <= (CH == 1 ? colorThr / 2u : scC));
+                tc += cd;
+            }
+            if(ok) {
+                const Desc bd = bgd[(size_t)s * A.plane];
+                uint32_t td = 0;
+#pragma unroll
+                for(int c = 0; c < CH; ++c) {
+                    const uint32_t b = col_get(bc, c);
+                    const uint32_t dd = __popc(lbsp_threshold(L[c], b, s_lut[b]) ^ desc_get(bd, c));
+                    ok = ok && (dd <= (CH == 1 ? descThr : scD));
+                    td += dd;
+                }
+                if(CH != 1) ok = ok && (td <= totD) && (tc <= totC);
+                if(ok) ++good;
+            }
+            ++s;
+        }
+        scanned = s;
+        if(good < REQ) is_fg = true;
+        else {
+            const uint32_t frame = A.ctl->frame_idx;
+            const uint32_t pixid = (uint32_t)(y * A.W + x);
+            const uint32_t LR = A.lr_fixed;
+            const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
+            const bool own = (rnd.x % LR) == 0, nb = (rnd.z % LR) == 0;
+            if(own || nb) {
+                uint32_t intra[CH];
+#pragma unroll
+                for(int c = 0; c < CH; ++c) intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+                Desc intra_pack;
+                if constexpr (CH == 1) intra_pack = (ushort)intra[0]; else intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]);
+                if(own) {
+                    const uint32_t slot = rnd.y % N;
+                    ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
+                    ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                    ++writes;
+                }
+                if(nb) {
+                    const uint32_t code = 32u | (rnd.w % 8u);
+                    const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
+                    A.intents[pix] = (ushort)((code << 8) | slot);
+                    ((Desc*)A.last_desc)[pix] = intra_pack; // scratch plane read by phase B (not the reference's m_oLastDescFrame)
+                    has_intent = true;
+                }
+            }
+        }
+    }
+    if(in_img) ((Col*)A.last_color)[pix] = cur_pack; // whole frame (:580)
+
+    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
+    const uint32_t b_int = __ballot_sync(0xFFFFFFFFu, has_intent);
+    if(threadIdx.x == 0 && y < A.H && (x >> 5) < A.WW) { A.raw_bits[wi] = b_raw; A.intent_bits[wi] = b_int; }
+    if(A.collect_stats) {
+        uint32_t sc = scanned, wr = writes + (has_intent ? 1u : 0u);
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
+        if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[2], wr); atomicAdd(&s_cnt[3], __popc(b_raw)); }
+        __syncthreads();
+        if(tid == 0) {
+            atomicAdd(&A.ctl->stat_scanned, (unsigned long long)s_cnt[1]);
+            atomicAdd(&A.ctl->stat_writes, (unsigned long long)s_cnt[2]);
+            atomicAdd(&A.ctl->stat_fg, (unsigned long long)s_cnt[3]);
+        }
+    }
+}
+__global__ void lobster_tail_kernel(FrameCtl* ctl) { ctl->frame_idx += 1; }
+
+/// initialisation (BackgroundSubtractionUtils.cpp:117-154 + BackgroundSubtractorLBSP.cpp:21-65):
+/// last_color = init image inside the ROI, last_desc = intra LBSP for ROI pixels strictly inside the 2-px border + 1 (Q4)
+struct InitArgs {
+    int W, H, Wp, WW;
+    const uchar* img; size_t ipitch;
+    void* last_color; void* last_desc;
+    const uint32_t* roi_bits; const uchar* lut;
+    int use_tma;
+};
+template<int CH>
+__global__ void __launch_bounds__(TILE_W * TILE_H) init_frame_kernel(const InitArgs A, const __grid_constant__ CUtensorMap tmap) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    constexpr int PITCH = tile_pitch(CH);
+    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if(x >= A.W || y >= A.H) return;
+    const bool roi = (A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u;
+    const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+    uint32_t cur[CH], d[CH];
+#pragma unroll
+    for(int c = 0; c < CH; ++c) {
+        cur[c] = roi ? s_tile[sy * PITCH + sx * CH + c] : 0u;
+        d[c] = 0;
+        if(roi && x > 2 && y > 2 && x < A.W - 2 && y < A.H - 2) {
+            const Lookup16 L = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+            d[c] = lbsp_threshold(L, cur[c], A.lut[cur[c]]);
+        }
+    }
+    const size_t pix = (size_t)y * A.Wp + x;
+    if constexpr (CH == 1) { ((Col*)A.last_color)[pix] = (uchar)cur[0]; ((Desc*)A.last_desc)[pix] = (ushort)d[0]; }
+    else { ((Col*)A.last_color)[pix] = cur[0] | (cur[1] << 8) | (cur[2] << 16); ((Desc*)A.last_desc)[pix] = make_uint2(d[0] | (d[1] << 16), d[2]); }
+}
+
+/// getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649, LOBSTER.cpp:583-620):
+/// float mean accumulated sample by sample (x/N each), converted round-half-even with saturation
+template<int CH>
+__global__ void __launch_bounds__(256) background_image_kernel(const void* bg_color, const void* bg_desc, size_t plane, int N, int W, int H, int Wp,
+                                                                uchar* out_color, ushort* out_desc) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(x >= W || y >= H) return;
+    const size_t pix = (size_t)y * Wp + x, o = ((size_t)y * W + x) * CH;
+    float acc[CH];
+#pragma unroll
+    for(int c = 0; c < CH; ++c) acc[c] = 0.f;
+    for(int s = 0; s < N; ++s) {
+        if(out_color) {
+            const Col v = ((const Col*)bg_color)[(size_t)s * plane + pix];
+#pragma unroll
+            for(int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], __fdiv_rn((float)col_get(v, c), (float)N));
+        } else {
+            const Desc v = ((const Desc*)bg_desc)[(size_t)s * plane + pix];
+#pragma unroll
+            for(int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], __fdiv_rn((float)desc_get(v, c), (float)N));
+        }
+    }
+#pragma unroll
+    for(int c = 0; c < CH; ++c) {
+        if(out_color) out_color[o + c] = (uchar)fminf(fmaxf(rintf(acc[c]), 0.f), 255.f);
+        else out_desc[o + c] = (ushort)fminf(fmaxf(rintf(acc[c]), 0.f), 65535.f);
+    }
+}
+
+/// dense LBSP (LBSP::compute2): intra (ref == image) or inter (separate reference image), absolute or relative threshold
+struct LbspArgs {
+    int W, H;
+    const uchar* img; size_t ipitch;
+    const uchar* ref; size_t rpitch;   // null -> intra
+    ushort* out;                       // [H][W][CH], the 2-px border is left untouched
+    int use_rel; float rel; int thr;
+    int use_tma;
+};
+template<int CH>
+__global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_dense_kernel(const LbspArgs A, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int PITCH = tile_pitch(CH);
+    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if(x < 2 || y < 2 || x >= A.W - 2 || y >= A.H - 2) return;
+    const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+    const uint32_t tabs = (uint32_t)min(max(A.thr, 0), 255);
+#pragma unroll
+    for(int c = 0; c < CH; ++c) {
+        const uint32_t ref = A.ref ? A.ref[(size_t)y * A.rpitch + x * CH + c] : s_tile[sy * PITCH + sx * CH + c];
+        uint32_t t = tabs;
+        if(A.use_rel) t = (uint32_t)fminf(fmaxf(rintf(__fadd_rn(__fmul_rn((float)ref, A.rel), (float)A.thr)), 0.f), 255.f);
+        const Lookup16 L = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+        A.out[((size_t)y * A.W + x) * CH + c] = (ushort)lbsp_threshold(L, ref, t);
+    }
+}
+
+} // namespace lvb

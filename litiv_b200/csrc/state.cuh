@@ -1,0 +1,74 @@
+// litiv_b200 — device-resident state of one video stream (one background subtractor instance).
+//
+// HBM layout (Wp = W rounded up to 32 pixels so every row starts on a 32-bit mask word; WW = Wp/32):
+//   model colour  : [N][H][Wp]  3ch: u32 (B,G,R,0) / 1ch: u8         sample-major SoA, a warp reads 128 B per sample row
+//   model desc    : [N][H][Wp]  3ch: uint2 (d0|d1<<16, d2) / 1ch: u16
+//   feedback maps : [H][Wp] x 8 f32 interleaved (T,R,v,Dlast | DminLT,DminST,rawLT,rawST) = 2 x float4 per pixel
+//   final-segm EMA: [H][Wp] float2 (LT,ST)
+//   last colour / last desc: [H][Wp] same packing as one model sample
+//   masks         : bit-packed [H][WW] u32 (roi, raw, lastraw, lastrawblink, blinks, lastfg, dilinv, unstable, ghost x2, intent bits)
+//   nb intents    : [H][Wp] u16 (neighbour code << 8 | slot), valid where the intent bit is set
+//   frame scalars : FrameCtl (device) so that a whole frame needs no host round trip
+#pragma once
+#include "common.cuh"
+
+namespace lvb {
+
+struct Params { // mirrors include/litiv_b200.h : lvb_params
+    float rel_lbsp_threshold;
+    int lbsp_threshold_offset;
+    int desc_dist_threshold;
+    int color_dist_threshold;
+    int n_samples;
+    int n_required;
+    int n_samples_for_moving_avgs;
+    int n_global_words;
+    int median_blur_kernel_size;
+};
+
+struct FrameCtl {
+    uint32_t frame_idx;        // index of the frame being processed (1-based, == reference m_nFrameIdx after ++)
+    float aLT, aST;            // rolling average factors of the current frame
+    float t_lower, t_upper;    // current learning-rate caps
+    uint32_t cooldown, frames_since_reset, auto_reset, lr_scaling, use3x3;
+    int32_t median_k;
+    float last_nonzero_ratio;
+    uint32_t nonzero_count;    // accumulators, cleared by the tail kernel
+    unsigned long long tot_color_diff;
+    uint32_t do_refresh, refresh_epoch, refresh_start, refresh_count, refresh_force, set_T_one;
+    uint32_t flood_changed[2];
+    uint32_t roi_count;
+    unsigned long long stat_scanned, stat_writes, stat_fg; // optional instrumentation
+    uint32_t pad[8];
+};
+
+template<int CH> struct Pack;
+template<> struct Pack<3> { typedef uint32_t Col; typedef uint2 Desc; };
+template<> struct Pack<1> { typedef uchar Col; typedef ushort Desc; };
+
+__device__ __forceinline__ uint32_t desc_get(const uint2& d, int c) { return c == 0 ? (d.x & 0xFFFFu) : c == 1 ? (d.x >> 16) : (d.y & 0xFFFFu); }
+__device__ __forceinline__ uint32_t desc_get(const ushort& d, int) { return d; }
+__device__ __forceinline__ uint32_t col_get(const uint32_t& v, int c) { return (v >> (8 * c)) & 0xFFu; }
+__device__ __forceinline__ uint32_t col_get(const uchar& v, int) { return v; }
+
+struct SubArgs {
+    int W, H, Wp, WW, N, REQ;
+    size_t plane;              // H*Wp
+    const uchar* img; size_t ipitch;  // current frame, interleaved bytes
+    void* bg_color; void* bg_desc;
+    float4* maps;              // 2 float4 per pixel
+    float2* fin;
+    void* last_color; void* last_desc;
+    const uint32_t* roi_bits;
+    uint32_t* raw_bits; uint32_t* unstable_bits; const uint32_t* blinks_bits; const uint32_t* lastfg_bits;
+    const uint32_t* ghost_prev; uint32_t* ghost_cur;
+    uint32_t* intent_bits; ushort* intents;
+    const uchar* lut;
+    FrameCtl* ctl;
+    uint64_t seed;
+    uint32_t lr_fixed;         // 0: use ceil(T(x)) ; else the ceil'd override (0xFFFFFFFF for +inf)
+    int min_color, desc_off;
+    int use_tma, collect_stats;
+};
+
+} // namespace lvb

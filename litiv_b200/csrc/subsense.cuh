@@ -1,0 +1,489 @@
+// litiv_b200 — SuBSENSE per-frame kernels (replaces BackgroundSubtractorSuBSENSE_::apply,
+// reference video/src/BackgroundSubtractorSuBSENSE.cpp:188-612, and refreshModel :80-105).
+//
+// Frame = phase A (classification + feedback, 1 thread / pixel, reads only frame-start state)
+//       -> phase B (deferred neighbour-sample writes, gathered per target pixel in raster order of the source)
+//       -> bit-packed post-processing (postproc.cuh) -> frame tail (LUT adaptation, frame-level reset logic)
+//       -> conditional refresh.
+#pragma once
+#include "state.cuh"
+
+namespace lvb {
+
+constexpr int TILE_W = 32, TILE_H = 8, HALO = 2;
+constexpr int TILE_ROWS = TILE_H + 2 * HALO;
+__host__ __device__ constexpr int tile_pitch(int ch) { return ((TILE_W + 2 * HALO) * ch + 15) / 16 * 16; }
+
+/// stage the (TILE_W+4)x(TILE_H+4) input tile into shared memory: one TMA bulk tensor copy (zero-filled
+/// outside the image) or, when the frame pitch is not TMA-compatible, a cooperative byte copy.
+template<int CH>
+__device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUtensorMap* tmap, int use_tma,
+                                           const uchar* img, size_t ipitch, int W, int H, int x0, int y0) {
+    constexpr int PITCH = tile_pitch(CH);
+    if(use_tma) {
+        if(threadIdx.x == 0 && threadIdx.y == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if(threadIdx.x == 0 && threadIdx.y == 0) {
+            mbar_expect_tx(bar, PITCH * TILE_ROWS);
+            tma_load_2d(tile, tmap, (x0 - HALO) * CH, y0 - HALO, bar);
+        }
+        mbar_wait(bar, 0);
+    } else {
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+        const int rowbytes = (TILE_W + 2 * HALO) * CH;
+        for(int i = tid; i < rowbytes * TILE_ROWS; i += nt) {
+            const int r = i / rowbytes, b = i - r * rowbytes;
+            const int gy = y0 - HALO + r, gb = (x0 - HALO) * CH + b;
+            uchar v = 0;
+            if(gy >= 0 && gy < H && gb >= 0 && gb < W * CH) v = img[(size_t)gy * ipitch + gb];
+            tile[r * PITCH + b] = v;
+        }
+        __syncthreads();
+    }
+}
+
+template<int CH>
+__global__ void __launch_bounds__(TILE_W * TILE_H)
+subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    constexpr int PITCH = tile_pitch(CH);
+    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uchar s_lut[256];
+    __shared__ uint32_t s_cnt[4];
+
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    s_lut[tid] = A.lut[tid];
+    if(tid < 4) s_cnt[tid] = 0;
+    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    __syncthreads();
+
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool in_img = (x < A.W) && (y < A.H);
+    const int wi = y * A.WW + (x >> 5);
+    const uint32_t lane_bit = 1u << (x & 31);
+    uint32_t w_roi = 0, w_unst = 0, w_blink = 0, w_lastfg = 0;
+    if(y < A.H && (x >> 5) < A.WW) {
+        w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; w_blink = A.blinks_bits[wi]; w_lastfg = A.lastfg_bits[wi];
+    }
+    const bool active = in_img && (w_roi & lane_bit);
+    const size_t pix = (size_t)y * A.Wp + x;
+
+    bool is_fg = false, unstable_new = false, ghost_new = false, has_intent = false, nonzero = false;
+    uint32_t scanned = 0, writes = 0;
+
+    if(active) {
+        const FrameCtl* ctl = A.ctl;
+        const float aLT = ctl->aLT, aST = ctl->aST, t_lower = ctl->t_lower, t_upper = ctl->t_upper;
+        const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, use3x3 = ctl->use3x3;
+        const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
+        const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
+
+        float4 m0 = A.maps[pix * 2], m1 = A.maps[pix * 2 + 1];
+        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
+        const float2 fin = A.fin[pix];
+        const bool unstable_old = (w_unst & lane_bit) != 0, blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
+
+        // thresholds (SuBSENSE.cpp:222-223 / :355-359)
+        uint32_t thrC = (uint32_t)(__fsub_rn(__fmul_rn(R, (float)A.min_color), (float)(unstable_old ? 0 : A.min_color / 5)));
+        if(CH == 1) thrC >>= 1;
+        const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
+        const uint32_t totC = thrC * 3u, totD = thrD * 3u, scC = totC >> 1;
+
+        const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+        Lookup16 L[CH];
+        uint32_t cur[CH], intra[CH];
+#pragma unroll
+        for(int c = 0; c < CH; ++c) {
+            L[c] = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+            cur[c] = s_tile[sy * PITCH + sx * CH + c];
+            intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+        }
+        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
+
+        // sample-consensus scan (:229-253 / :367-395): all colour gates first (no side effects), then the descriptor
+        const Col* bgc = (const Col*)A.bg_color + pix;
+        const Desc* bgd = (const Desc*)A.bg_desc + pix;
+        uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
+        while(good < REQ && s < N) {
+            const Col bc = bgc[(size_t)s * A.plane];
+            bool ok = true;
+            uint32_t cd[CH];
+#pragma unroll
+            for(int c = 0; c < CH; ++c) {
+                const uint32_t b = col_get(bc, c);
+                cd[c] = cur[c] > b ? cur[c] - b : b - cur[c];
+                ok = ok && (cd[c] <= (CH == 1 ? thrC : scC));
+            }
+            if(ok) {
+                const Desc bd = bgd[(size_t)s * A.plane];
+                uint32_t totDesc = 0, totSum = 0;
+#pragma unroll
+                for(int c = 0; c < CH; ++c) {
+                    const uint32_t b = col_get(bc, c), d = desc_get(bd, c);
+                    const uint32_t inter = lbsp_threshold(L[c], b, s_lut[b]);
+                    const uint32_t dd = (__popc(intra[c] ^ d) + __popc(inter ^ d)) >> 1;
+                    if(CH == 1) {
+                        const uint32_t sum = min((dd >> 2) * 15u + cd[c], 255u);
+                        ok = ok && (dd <= thrD) && (sum <= thrC);
+                        totDesc = dd; totSum = sum;
+                    } else {
+                        const uint32_t sum = min((dd >> 1) * 15u + cd[c], 255u);
+                        ok = ok && (sum <= scC);
+                        totDesc += dd; totSum += sum;
+                    }
+                }
+                if(CH != 1) ok = ok && !(totDesc > totD || totSum > totC);
+                if(ok) { minDesc = min(minDesc, totDesc); minSum = min(minSum, totSum); ++good; }
+            }
+            ++s;
+        }
+        scanned = s;
+
+        // D_last (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
+        const Col lc = ((const Col*)A.last_color)[pix];
+        const Desc ld = ((const Desc*)A.last_desc)[pix];
+        uint32_t lastL1 = 0, lastHd = 0;
+#pragma unroll
+        for(int c = 0; c < CH; ++c) {
+            const uint32_t b = col_get(lc, c);
+            lastL1 += cur[c] > b ? cur[c] - b : b - cur[c];
+            lastHd += __popc(desc_get(ld, c) ^ intra[c]);
+        }
+        if(CH != 1) lastL1 &= 0xFFu;
+        const float normLast = __fdiv_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 2.0f);
+        Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
+
+        Col cur_pack; Desc intra_pack;
+        if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
+        else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
+
+        const uint32_t pixid = (uint32_t)(y * A.W + x);
+        const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
+        const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
+        const float baseMin = __fdiv_rn(__fadd_rn(__fdiv_rn((float)minSum, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange)), 2.0f);
+        if(good < REQ) { // foreground (:256-269 / :398-413)
+            is_fg = true;
+            const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
+            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
+            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(normMin, aST));
+            rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT);
+            rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
+            if(cooldown && (rnd.x % 2u) == 0) {
+                const uint32_t slot = rnd.y % N;
+                ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
+                ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                ++writes;
+            }
+        } else { // background (:270-301 / :414-450)
+            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(baseMin, aLT));
+            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
+            rawLT = __fmul_rn(rawLT, oneLT);
+            rawST = __fmul_rn(rawST, oneST);
+            const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
+            if((rnd.x % LR) == 0) {
+                const uint32_t slot = rnd.y % N;
+                ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
+                ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                ++writes;
+            }
+            const bool cur3 = use3x3 && !unstable_new;
+            const uint32_t code = cur3 ? (32u | (rnd.z % 8u)) : (rnd.z % 24u);
+            int nx, ny;
+            neighbor_from_code(code, nx, ny, x, y, A.W, A.H);
+            const bool nb_ghost = (A.ghost_prev[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u;
+            const uint32_t n_rand = rnd.w;
+            if((n_rand % (cur3 ? LR : (LR / 2u + 1u))) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
+                const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
+                A.intents[pix] = (ushort)((code << 8) | slot);
+                has_intent = true;
+            }
+        }
+        // T(x) (:302-311 / :451-460)
+        const float dmin = fminf(DminLT, DminST), dmax = fmaxf(DminLT, DminST);
+        if(lastfg || (dmin < 0.1f && is_fg)) {
+            if(T < t_upper) T = __fadd_rn(T, __fdiv_rn(0.5f, __fmul_rn(dmax, V)));
+        } else if(T > t_lower)
+            T = __fsub_rn(T, __fdiv_rn(__fmul_rn(0.25f, V), dmax));
+        if(T < t_lower) T = t_lower; else if(T > t_upper) T = t_upper;
+        // v(x) (:312-318 / :461-467)
+        if(dmax > 0.1f && blink) V = __fadd_rn(V, 1.0f);
+        else if(V > 0.1f) {
+            V = __fsub_rn(V, lastfg ? (0.1f / 4) : unstable_new ? (0.1f / 2) : 0.1f);
+            if(V < 0.1f) V = 0.1f;
+        }
+        // R(x) (:319-325 / :468-474); std::pow(float,int) evaluates in double (Q7): the square is exact in fp64
+        const double rr = (double)__fadd_rn(1.0f, __fmul_rn(dmin, 2.0f));
+        if((double)R < __dmul_rn(rr, rr)) R = __fadd_rn(R, __fmul_rn(0.01f, __fsub_rn(V, 0.1f)));
+        else {
+            R = __fsub_rn(R, __fdiv_rn(0.01f, V));
+            if(R < 1.0f) R = 1.0f;
+        }
+        uint32_t pc = 0;
+#pragma unroll
+        for(int c = 0; c < CH; ++c) pc += __popc(intra[c]);
+        nonzero = pc >= (CH == 1 ? 2u : 4u);
+        ghost_new = (rawST > 0.995f) && (Dlast < 0.010f);
+
+        A.maps[pix * 2] = make_float4(T, R, V, Dlast);
+        A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
+        ((Col*)A.last_color)[pix] = cur_pack;
+        ((Desc*)A.last_desc)[pix] = intra_pack;
+    }
+
+    // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
+    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
+    const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
+    const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
+    const uint32_t b_int = __ballot_sync(0xFFFFFFFFu, has_intent);
+    const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
+    if(threadIdx.x == 0 && y < A.H && (x >> 5) < A.WW) {
+        A.raw_bits[wi] = b_raw; A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; A.intent_bits[wi] = b_int;
+        atomicAdd(&s_cnt[0], __popc(b_nz));
+    }
+    if(A.collect_stats) {
+        uint32_t sc = scanned, wr = writes + (has_intent ? 1u : 0u);
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
+        if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[2], wr); atomicAdd(&s_cnt[3], __popc(b_raw)); }
+    }
+    __syncthreads();
+    if(tid == 0) {
+        if(s_cnt[0]) atomicAdd(&A.ctl->nonzero_count, s_cnt[0]);
+        if(A.collect_stats) {
+            atomicAdd(&A.ctl->stat_scanned, (unsigned long long)s_cnt[1]);
+            atomicAdd(&A.ctl->stat_writes, (unsigned long long)s_cnt[2]);
+            atomicAdd(&A.ctl->stat_fg, (unsigned long long)s_cnt[3]);
+        }
+    }
+}
+
+/// Phase B: apply the queued neighbour writes. One thread per TARGET pixel gathers the intents of the 5x5
+/// sources around it in raster order, so the last writer in raster order wins (oracle MODE_SNAPSHOT rule).
+struct PhaseBArgs {
+    int W, H, Wp, WW, CH;
+    size_t plane;
+    const uchar* img; size_t ipitch;
+    void* bg_color; void* bg_desc;
+    const void* last_desc;     // == this frame's intra descriptors for every active pixel
+    const uint32_t* intent_bits; const ushort* intents;
+};
+
+template<int CH>
+__global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
+    const int wi = x >> 5, xb = x & 31;
+#pragma unroll
+    for(int dy = -2; dy <= 2; ++dy) {
+        const int qy = y + dy; // always inside the image
+        const uint32_t* row = A.intent_bits + (size_t)qy * A.WW;
+        const uint32_t left = wi > 0 ? row[wi - 1] : 0u, cur = row[wi], right = wi + 1 < A.WW ? row[wi + 1] : 0u;
+        // 5-bit window: bit k <-> source x-2+k
+        const unsigned long long lo = ((unsigned long long)cur << 32) | left, hi = ((unsigned long long)right << 32) | cur;
+        uint32_t win = (xb >= 2) ? (uint32_t)(hi >> (xb - 2)) & 31u : (uint32_t)(lo >> (30 + xb)) & 31u;
+        while(win) {
+            const int k = __ffs(win) - 1;
+            win &= win - 1;
+            const int qx = x - 2 + k;
+            const size_t qpix = (size_t)qy * A.Wp + qx;
+            const uint32_t it = A.intents[qpix];
+            int tx, ty;
+            neighbor_from_code(it >> 8, tx, ty, qx, qy, A.W, A.H);
+            if(tx == x && ty == y) {
+                const uint32_t slot = it & 0xFFu;
+                const size_t dst = (size_t)slot * A.plane + (size_t)y * A.Wp + x;
+                const uchar* src = A.img + (size_t)qy * A.ipitch + (size_t)qx * CH;
+                if constexpr (CH == 1) ((Col*)A.bg_color)[dst] = src[0];
+                else ((Col*)A.bg_color)[dst] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+                ((Desc*)A.bg_desc)[dst] = ((const Desc*)A.last_desc)[qpix];
+            }
+        }
+    }
+}
+
+/// refreshModel (SuBSENSE.cpp:80-105 / LOBSTER.cpp:410-441): one thread per ROI pixel; runs only when
+/// ctl->do_refresh is set (the frame tail decides on the device). Also applies the "T(x)=1" reset (:592).
+struct RefreshArgs {
+    int W, H, Wp, WW, CH, N;
+    size_t plane;
+    void* bg_color; void* bg_desc;
+    const void* last_color; void* last_desc;
+    const uint32_t* roi_bits; const uint32_t* lastfg_bits;
+    float4* maps;
+    const uchar* lut;
+    FrameCtl* ctl;
+    uint64_t seed;
+    int recompute_desc;        // LOBSTER: descriptor of the sampled pixel is recomputed from last_color
+};
+
+template<int CH>
+__global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    const FrameCtl* ctl = A.ctl;
+    if(!ctl->do_refresh) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(x >= A.W || y >= A.H) return;
+    const size_t pix = (size_t)y * A.Wp + x;
+    if(ctl->set_T_one && A.maps) A.maps[pix * 2].x = 1.0f;
+    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
+    const bool force = ctl->refresh_force != 0;
+    if(!force && ((A.lastfg_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
+    const uint32_t N = (uint32_t)A.N, start = ctl->refresh_start, count = ctl->refresh_count, epoch = ctl->refresh_epoch;
+    const uint32_t pixid = (uint32_t)(y * A.W + x);
+    const Col* lc = (const Col*)A.last_color;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    uint32_t have_blk = 0xFFFFFFFFu;
+    for(uint32_t i = start; i < start + count; ++i) {
+        const uint32_t rs = i % N;
+        if((rs >> 2) != have_blk) { have_blk = rs >> 2; rnd = philox_block(A.seed, epoch, pixid, have_blk, DOM_REFRESH); }
+        const uint32_t r = (rs & 3) == 0 ? rnd.x : (rs & 3) == 1 ? rnd.y : (rs & 3) == 2 ? rnd.z : rnd.w;
+        int sx, sy;
+        sample_pos_7x7(r, sx, sy, x, y, A.W, A.H);
+        if(!force && ((A.lastfg_bits[sy * A.WW + (sx >> 5)] >> (sx & 31)) & 1u)) continue;
+        const size_t sp = (size_t)sy * A.Wp + sx;
+        const Col col = lc[sp];
+        Desc d;
+        if(A.recompute_desc) {
+            uint32_t dd[CH];
+#pragma unroll
+            for(int c = 0; c < CH; ++c) {
+                Lookup16 L;
+#pragma unroll
+                for(int q = 0; q < 4; ++q) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for(int b = 0; b < 4; ++b) {
+                        const int n = q * 4 + b;
+                        const Col nc = lc[(size_t)(sy + c_lbsp_dy[n]) * A.Wp + (sx + c_lbsp_dx[n])];
+                        w |= col_get(nc, c) << (8 * b);
+                    }
+                    L.w[q] = w;
+                }
+                const uint32_t ref = col_get(col, c);
+                dd[c] = lbsp_threshold(L, ref, A.lut[ref]);
+            }
+            if constexpr (CH == 1) d = (ushort)dd[0]; else d = make_uint2(dd[0] | (dd[1] << 16), dd[2]);
+            ((Desc*)A.last_desc)[sp] = d; // idempotent: a pure function of last_color
+        } else d = ((const Desc*)A.last_desc)[sp];
+        ((Col*)A.bg_color)[(size_t)rs * A.plane + pix] = col;
+        ((Desc*)A.bg_desc)[(size_t)rs * A.plane + pix] = d;
+    }
+}
+
+/// frame-level analysis (SuBSENSE.cpp:567-583): 8x8 area mean -> two EMAs -> sum of truncated max-channel |ST-LT|
+struct DownsampleArgs {
+    int W, H, CH, dsW, dsH;
+    const uchar* img; size_t ipitch;
+    float* dsLT; float* dsST;
+    FrameCtl* ctl;
+};
+template<int CH>
+__global__ void __launch_bounds__(128) downsample_motion_kernel(const DownsampleArgs A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long diff = 0;
+    if(i < A.dsW * A.dsH && A.ctl->lr_scaling) {
+        const int dx = i % A.dsW, dy = i / A.dsW;
+        const float aLT = A.ctl->aLT, aST = A.ctl->aST;
+        uint32_t sum[CH];
+#pragma unroll
+        for(int c = 0; c < CH; ++c) sum[c] = 0;
+        for(int r = 0; r < 8; ++r) {
+            const uchar* p = A.img + (size_t)(dy * 8 + r) * A.ipitch + (size_t)dx * 8 * CH;
+#pragma unroll
+            for(int b = 0; b < 8; ++b)
+#pragma unroll
+                for(int c = 0; c < CH; ++c) sum[c] += p[b * CH + c];
+        }
+        uint32_t best = 0;
+#pragma unroll
+        for(int c = 0; c < CH; ++c) {
+            const float v = fminf(fmaxf(rintf(__fmul_rn((float)sum[c], 1.0f / 64)), 0.f), 255.f);
+            const size_t k = (size_t)i * CH + c;
+            const float lt = __fadd_rn(__fmul_rn(v, aLT), __fmul_rn(A.dsLT[k], __fsub_rn(1.0f, aLT)));
+            const float st = __fadd_rn(__fmul_rn(v, aST), __fmul_rn(A.dsST[k], __fsub_rn(1.0f, aST)));
+            A.dsLT[k] = lt; A.dsST[k] = st;
+            uint32_t d = (uint32_t)fabsf(__fsub_rn(st, lt));
+            if(CH == 1) d >>= 1;
+            best = max(best, d);
+        }
+        diff = best;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xFFFFFFFFu, diff, o);
+    if((threadIdx.x & 31) == 0 && diff) atomicAdd(&A.ctl->tot_color_diff, diff);
+}
+
+/// frame tail (SuBSENSE.cpp:555-611): LUT +-1 adaptation, frame-level reset / learning-rate caps, next-frame factors.
+struct TailArgs {
+    FrameCtl* ctl; uchar* lut;
+    float rel; int lbsp_off; int min_color; int avg_samples; int N; int dsW, dsH;
+    uint64_t seed;
+};
+__global__ void __launch_bounds__(256) subsense_tail_kernel(const TailArgs A) {
+    FrameCtl* ctl = A.ctl;
+    __shared__ int s_dir;
+    const int t = threadIdx.x;
+    if(t == 0) {
+        const float ratio = __fdiv_rn((float)ctl->nonzero_count, (float)ctl->roi_count);
+        const float last = ctl->last_nonzero_ratio;
+        s_dir = (ratio < 0.1f && last < 0.1f) ? -1 : (ratio > 0.5f && last > 0.5f) ? 1 : 0;
+        ctl->last_nonzero_ratio = ratio;
+        ctl->nonzero_count = 0;
+        ctl->do_refresh = 0; ctl->set_T_one = 0;
+        if(ctl->lr_scaling) {
+            const float diff_ratio = __fdiv_rn((float)ctl->tot_color_diff, (float)(A.dsW * A.dsH));
+            const uint32_t thr = (uint32_t)A.min_color / 2u;
+            if(ctl->auto_reset) {
+                if(ctl->frames_since_reset > 1000u) ctl->auto_reset = 0;
+                else if(diff_ratio >= (float)thr && ctl->cooldown == 0) {
+                    ctl->frames_since_reset = 0;
+                    // refreshModel(0.1f): (size_t)(0.1f*N) slots starting at a random position
+                    ctl->do_refresh = 1; ctl->set_T_one = 1; ctl->refresh_force = 0;
+                    ctl->refresh_count = (uint32_t)__fmul_rn(0.1f, (float)A.N);
+                    const uint32_t epoch = ctl->refresh_epoch;
+                    ctl->refresh_start = philox_draw(A.seed, epoch, 0, 0, DOM_REFRESH_START) % (uint32_t)A.N;
+                    ctl->cooldown = (uint32_t)A.avg_samples / 4u;
+                } else ctl->frames_since_reset += 1;
+            } else if(diff_ratio >= (float)(thr * 2u)) {
+                ctl->frames_since_reset = 0;
+                ctl->auto_reset = 1;
+            }
+            if(diff_ratio >= (float)(thr / 2u)) {
+                const int sh = (int)__fdiv_rn(diff_ratio, 2.0f);
+                ctl->t_lower = (float)max(sh < 31 ? (2 >> sh) : 0, 1);
+                ctl->t_upper = (float)max(sh < 31 ? (256 >> sh) : 0, 1);
+            } else { ctl->t_lower = 2.0f; ctl->t_upper = 256.0f; }
+            if(ctl->cooldown > 0) ctl->cooldown -= 1;
+            ctl->tot_color_diff = 0;
+        }
+        // next frame
+        const uint32_t f = ctl->frame_idx + 1;
+        ctl->frame_idx = f;
+        ctl->aLT = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples));
+        ctl->aST = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples / 4u));
+    }
+    __syncthreads();
+    const int dir = s_dir;
+    if(dir < 0) {
+        const float lo = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, ceilf(__fdiv_rn(__fmul_rn((float)t, A.rel), 4.0f)))), 0.f), 255.f);
+        if((float)A.lut[t] > lo) A.lut[t] -= 1;
+    } else if(dir > 0) {
+        const float hi = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, __fmul_rn(255.0f, A.rel))), 0.f), 255.f);
+        if((float)A.lut[t] < hi) A.lut[t] += 1;
+    }
+}
+/// runs after the conditional refresh: bump the epoch it consumed and drop the request
+__global__ void refresh_done_kernel(FrameCtl* ctl) {
+    if(ctl->do_refresh) { ctl->refresh_epoch += 1; ctl->do_refresh = 0; ctl->set_T_one = 0; }
+}
+
+} // namespace lvb

@@ -403,8 +403,10 @@ struct SuBSENSE : BgsBase {
                 auto_reset = true;
             }
             if(diff_ratio >= fl_thr / 2) {
-                t_lower = (float)std::max((int)FEEDBACK_T_LOWER >> (int)(diff_ratio / 2), 1);
-                t_upper = (float)std::max((int)FEEDBACK_T_UPPER >> (int)(diff_ratio / 2), 1);
+                // the reference shifts an int by (int)(ratio/2), undefined for >=32 (ratio >= 64); we define it as 0
+                const int sh = (int)(diff_ratio / 2);
+                t_lower = (float)std::max(sh < 31 ? ((int)FEEDBACK_T_LOWER >> sh) : 0, 1);
+                t_upper = (float)std::max(sh < 31 ? ((int)FEEDBACK_T_UPPER >> sh) : 0, 1);
             } else { t_lower = FEEDBACK_T_LOWER; t_upper = FEEDBACK_T_UPPER; }
             if(reset_cooldown > 0) --reset_cooldown;
         }

@@ -1,0 +1,216 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+(oracle/, snapshot mode, same Philox seed) on identical inputs.
+
+Tier 1: LBSP descriptors bit-exact (incl. the reference's golden vector).
+Tier 2: raw per-pixel classification + every integer/byte state buffer bit-exact from an identical state snapshot.
+Tier 3: end-to-end masks over a sequence: per-pixel disagreement <= TOL_MASK (we observe 0), float maps within 1e-5 rel.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from litiv_b200.synth import SynthSequence
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+FLOAT_RTOL = 1e-5   # north_star: "float feedback maps within 1e-5 relative"
+TOL_MASK = 0.0      # fraction of pixels allowed to differ GPU vs oracle(snapshot), same seed
+
+INT_STATE = ["lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "unstable", "blinks", "lastraw", "lastrawblink", "dilinv", "rawmask"]
+FLT_STATE = ["T", "R", "v", "Dlast", "DminLT", "DminST", "rawLT", "rawST", "finLT", "finST", "dsLT", "dsST"]
+
+
+def test_lbsp_golden_vector(lv):
+    g = np.load(os.path.join(GOLDEN, "lbsp_golden.npz"))
+    d = lv.LBSP(int(g["abs_threshold"])).compute2(g["crop"])
+    assert np.array_equal(d[2:63, 2:63], g["desc"][2:63, 2:63])
+    assert not d[:2].any() and not d[:, :2].any()  # border untouched
+
+
+@pytest.mark.parametrize("shape", [(37, 53, 3), (64, 64, 1), (240, 320, 3), (5, 5, 3), (9, 130, 1), (1080, 1920, 3)])
+@pytest.mark.parametrize("mode", ["abs", "rel", "rel_ref", "abs_ref"])
+def test_lbsp_matches_oracle(lv, oracle, shape, mode):
+    rng = np.random.RandomState(hash((shape, mode)) & 0xFFFF)
+    img = rng.randint(0, 256, shape).astype(np.uint8)
+    if shape[2] == 1:
+        img = img[..., 0]
+    ref = (np.clip(img.astype(int) + rng.randint(-20, 21, img.shape), 0, 255)).astype(np.uint8) if "ref" in mode else None
+    if mode.startswith("abs"):
+        ext, kw = lv.LBSP(25), dict(thr=25)
+    else:
+        ext, kw = lv.LBSP(0.333, 3), dict(rel=0.333, thr=3)
+    ext.setReference(ref)
+    got = ext.compute2(img)
+    want = oracle.lbsp_compute(img, ref=ref, **kw)
+    assert np.array_equal(got, want)
+
+
+def _mk(lv, oracle, algo, seed, **kw):
+    if algo == "subsense":
+        return lv.BackgroundSubtractorSuBSENSE(seed=seed, **kw), oracle.Oracle(oracle.ALGO_SUBSENSE, mode=oracle.MODE_SNAPSHOT, seed=seed)
+    return lv.BackgroundSubtractorLOBSTER(seed=seed, **kw), oracle.Oracle(oracle.ALGO_LOBSTER, mode=oracle.MODE_SNAPSHOT, seed=seed)
+
+
+def _compare_state(g, o, names_int, names_flt, tag):
+    for n in names_int:
+        a, b = g.state_get(n), o.state_get(n)
+        nbad = int((a != b).sum())
+        assert nbad == 0, f"{tag}: integer state '{n}' differs in {nbad} of {a.size} entries (first at {np.flatnonzero(a != b)[:5]})"
+    for n in names_flt:
+        a, b = g.state_get(n), o.state_get(n)
+        assert np.allclose(a, b, rtol=FLOAT_RTOL, atol=1e-7), f"{tag}: float map '{n}' max abs diff {np.abs(a - b).max()}"
+    sa, sb = g.state_get("scalars"), o.state_get("scalars")
+    idx = list(range(13)) if names_flt else [0, 3, 10, 11, 12]
+    assert np.allclose(sa[idx], sb[idx], rtol=1e-6), f"{tag}: scalars differ {sa[:13]} vs {sb[:13]}"
+
+
+CASES = [
+    ("subsense", 320, 240, 3, 12, None),
+    ("subsense", 320, 240, 1, 8, None),
+    ("subsense", 96, 72, 3, 8, None),       # "small" branch: no frame-level analysis, T in [4,512]
+    ("subsense", 200, 150, 3, 6, "roi"),     # ragged width (not a multiple of 32) + user ROI
+    ("lobster", 320, 240, 1, 10, None),
+    ("lobster", 320, 240, 3, 8, None),
+    ("lobster", 75, 61, 1, 6, "roi"),
+]
+
+
+@pytest.mark.parametrize("algo,w,h,c,nframes,roi", CASES)
+def test_tier2_state_parity(lv, oracle, algo, w, h, c, nframes, roi):
+    """identical snapshot -> identical raw classification and integer state, frame after frame"""
+    seq = SynthSequence(w, h, c, seed=11)
+    roi_img = None
+    if roi:
+        roi_img = np.zeros((h, w), np.uint8)
+        roi_img[h // 6:h - h // 8, w // 5:w - 3] = 255
+        roi_img[h // 2:h // 2 + 5, w // 2:w // 2 + 9] = 0
+    g, o = _mk(lv, oracle, algo, seed=7)
+    f0 = seq.frame(0)
+    g.initialize(f0, roi_img)
+    o.initialize(f0, roi_img)
+    ints = [n for n in INT_STATE if algo == "subsense" or n in ("lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "rawmask")]
+    ints_init = [n for n in ints if n != "rawmask"]
+    flts = FLT_STATE if algo == "subsense" else []
+    assert np.array_equal(g.getROICopy().ravel(), o.state_get("roi"))
+    _compare_state(g, o, ints_init, flts, f"{algo} init")
+    for t in range(1, nframes + 1):
+        f = seq.frame(t)
+        lr = (1.0 if t <= 3 else 0.0) if algo == "subsense" else 16.0
+        mg = g.apply(f, lr)
+        mo = o.apply(f, lr)
+        _compare_state(g, o, ints, flts, f"{algo} frame {t}")
+        assert np.array_equal(mg, mo), f"{algo} frame {t}: final masks differ in {(mg != mo).sum()} px"
+    assert np.array_equal(g.getBackgroundImage(), o.get_background_image())
+    assert np.array_equal(g.getBackgroundDescriptorsImage(), o.get_background_descriptors_image())
+
+
+def test_tier2_import_oracle_snapshot(lv, oracle):
+    """run the ORACLE for a while, import its whole state into the GPU object, then classify one frame on both"""
+    w, h, c = 320, 240, 3
+    seq = SynthSequence(w, h, c, seed=5)
+    g, o = _mk(lv, oracle, "subsense", seed=3)
+    f0 = seq.frame(0)
+    g.initialize(f0)
+    o.initialize(f0)
+    for t in range(1, 30):
+        o.apply(seq.frame(t), 1.0 if t <= 20 else 0.0)
+    for n in ["lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "unstable", "blinks", "lastraw", "lastrawblink", "dilinv"] + FLT_STATE + ["scalars"]:
+        g.state_set(n, o.state_get(n))
+    f = seq.frame(30)
+    mg, mo = g.apply(f, 0.0), o.apply(f, 0.0)
+    assert np.array_equal(g.state_get("rawmask"), o.state_get("rawmask"))
+    assert np.array_equal(mg, mo)
+    _compare_state(g, o, INT_STATE, FLT_STATE, "after import")
+
+
+@pytest.mark.parametrize("algo,w,h,c,n", [("subsense", 320, 240, 3, 130), ("lobster", 320, 240, 1, 80)])
+def test_tier3_sequence(lv, oracle, algo, w, h, c, n):
+    """end-to-end masks over a longer sequence with the samples/changedet learning-rate protocol (main.cpp:56)"""
+    seq = SynthSequence(w, h, c, seed=1 if algo == "subsense" else 2)
+    g, o = _mk(lv, oracle, algo, seed=0)
+    f0 = seq.frame(0)
+    g.initialize(f0)
+    o.initialize(f0)
+    worst, fm_g, fm_o = 0.0, [], []
+    for t in range(1, n):
+        f, gt = seq.frame(t, with_gt=True)
+        lr = (1.0 if t <= 50 else 0.0) if algo == "subsense" else 16.0
+        mg, mo = g.apply(f, lr), o.apply(f, lr)
+        worst = max(worst, float((mg != mo).mean()))
+        if t > 60:
+            for m, acc in ((mg, fm_g), (mo, fm_o)):
+                tp = ((m > 0) & gt).sum(); fp = ((m > 0) & ~gt).sum(); fn = ((m == 0) & gt).sum()
+                acc.append(2 * tp / max(2 * tp + fp + fn, 1))
+    assert worst <= TOL_MASK, f"per-pixel mask disagreement {worst}"
+    if fm_g:
+        assert abs(np.mean(fm_g) - np.mean(fm_o)) <= 1e-9
+    flts = FLT_STATE if algo == "subsense" else []
+    for nme in flts:
+        a, b = g.state_get(nme), o.state_get(nme)
+        assert np.allclose(a, b, rtol=FLOAT_RTOL, atol=1e-7), nme
+
+
+def test_full_size_properties(lv):
+    """1080p (BASELINE config #4 shape): size-independent properties instead of the (slow) oracle"""
+    w, h = 1920, 1080
+    seq = SynthSequence(w, h, 3, seed=4)
+    g = lv.BackgroundSubtractorSuBSENSE(seed=0)
+    f0 = seq.frame(0)
+    g.initialize(f0)
+    sc = g.state_get("scalars")
+    assert sc[5] == 0 and sc[6] == 13  # 5x5 spread, median 13 (SuBSENSE.cpp:115-117)
+    g2 = lv.BackgroundSubtractorSuBSENSE(seed=0)
+    g2.initialize(f0)
+    for t in range(1, 6):
+        f, gt = seq.frame(t, with_gt=True)
+        m, m2 = g.apply(f, 1.0), g2.apply(f, 1.0)
+        assert np.array_equal(m, m2)                       # determinism (Philox, ordered neighbour writes)
+        assert set(np.unique(m)) <= {0, 255}
+        assert not m[:2].any() and not m[-2:].any() and not m[:, :2].any() and not m[:, -2:].any()  # 2-px border stays 0
+    # a static scene stays background: feed the same frame repeatedly
+    for _ in range(3):
+        m = g.apply(f, 1.0)
+    assert (m > 0).mean() < 0.02
+    # the moving objects were detected at some point
+    assert (gt & (m2 > 0)).sum() > 0.3 * gt.sum()
+
+
+def test_async_batch_and_device_paths(lv, oracle):
+    import ctypes
+    w, h = 160, 120
+    seqs = [SynthSequence(w, h, 3, seed=20 + i) for i in range(3)]
+    subs = [lv.BackgroundSubtractorSuBSENSE(seed=i) for i in range(3)]
+    refs = [lv.BackgroundSubtractorSuBSENSE(seed=i) for i in range(3)]
+    for s, r, q in zip(subs, refs, seqs):
+        s.initialize(q.frame(0)); r.initialize(q.frame(0))
+    for t in range(1, 5):
+        frames = [q.frame(t) for q in seqs]
+        masks = lv.apply_batch(subs, frames, 1.0)
+        for r, f, m in zip(refs, frames, masks):
+            assert np.array_equal(r.apply(f, 1.0), m)
+    s, r = subs[0], refs[0]
+    f = seqs[0].frame(5)
+    s.apply_async(f, 0.0)
+    assert np.array_equal(s.sync(), r.apply(f, 0.0))
+
+
+def test_errors_match_reference_messages(lv):
+    s = lv.BackgroundSubtractorSuBSENSE()
+    with pytest.raises(lv.LitivError, match="initialized first"):
+        s.apply(np.zeros((10, 10, 3), np.uint8))
+    with pytest.raises(lv.LitivError, match="initialized first"):
+        s.getBackgroundImage()
+    s.initialize(np.zeros((40, 40, 3), np.uint8))
+    with pytest.raises(lv.LitivError, match="mismatch"):
+        s.apply(np.zeros((41, 40, 3), np.uint8))
+    with pytest.raises(lv.LitivError, match="0 or 255"):
+        s.initialize(np.zeros((40, 40, 3), np.uint8), np.full((40, 40), 7, np.uint8))
+    with pytest.raises(lv.LitivError, match="no useful pixels"):
+        s.initialize(np.zeros((40, 40, 3), np.uint8), np.zeros((40, 40), np.uint8))
+    lob = lv.BackgroundSubtractorLOBSTER()
+    lob.initialize(np.zeros((40, 40), np.uint8))
+    with pytest.raises(lv.LitivError, match="positive"):
+        lob.apply(np.zeros((40, 40), np.uint8), 0.0)
+    with pytest.raises(lv.LitivError, match="more sample matches"):
+        lv.BackgroundSubtractorSuBSENSE(nBGSamples=2, nRequiredBGSamples=3)
