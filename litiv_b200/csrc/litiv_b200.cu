@@ -10,6 +10,7 @@
 #include <cstring>
 #include <atomic>
 #include <algorithm>
+#include <cstdlib>
 
 using namespace lvb;
 
@@ -40,7 +41,8 @@ EncodeTiledFn get_encode_fn() {
 /// tensor map over an interleaved byte image so one TMA box = (TILE_W+4)x(TILE_H+4) pixels incl. the LBSP halo
 bool make_image_tmap(CUtensorMap* map, const void* ptr, int W, int H, int C, size_t pitch) {
     std::memset(map, 0, sizeof(*map));
-    EncodeTiledFn fn = get_encode_fn();
+    static const bool disabled = getenv("LVB_NO_TMA") != nullptr; // debugging aid: force the cooperative-copy staging path
+    EncodeTiledFn fn = disabled ? nullptr : get_encode_fn();
     if(!fn || ((uintptr_t)ptr & 15) || (pitch & 15)) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)W * C, (cuuint64_t)H};
     const cuuint64_t gstr[1] = {(cuuint64_t)pitch};

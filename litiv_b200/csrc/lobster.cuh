@@ -38,7 +38,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     uint32_t cur[CH];
     Col cur_pack;
 #pragma unroll
-    for(int c = 0; c < CH; ++c) cur[c] = s_tile[sy * PITCH + sx * CH + c];
+    for(int c = 0; c < CH; ++c) cur[c] = s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
     if constexpr (CH == 1) cur_pack = (uchar)cur[0]; else cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16);
 
     if(active) {
@@ -47,7 +47,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t totD = descThr * 3u, totC = colorThr * 3u, scD = totD >> 1, scC = totC >> 1;
         Lookup16 L[CH];
 #pragma unroll
-        for(int c = 0; c < CH; ++c) L[c] = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+        for(int c = 0; c < CH; ++c) L[c] = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
         const Col* bgc = (const Col*)A.bg_color + pix;
         const Desc* bgd = (const Desc*)A.bg_desc + pix;
         uint32_t good = 0, s = 0;
@@ -153,10 +153,10 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) init_frame_kernel(const InitA
     uint32_t cur[CH], d[CH];
 #pragma unroll
     for(int c = 0; c < CH; ++c) {
-        cur[c] = roi ? s_tile[sy * PITCH + sx * CH + c] : 0u;
+        cur[c] = roi ? s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c] : 0u;
         d[c] = 0;
         if(roi && x > 2 && y > 2 && x < A.W - 2 && y < A.H - 2) {
-            const Lookup16 L = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+            const Lookup16 L = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
             d[c] = lbsp_threshold(L, cur[c], A.lut[cur[c]]);
         }
     }
@@ -219,10 +219,10 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_dense_kernel(const LbspA
     const uint32_t tabs = (uint32_t)min(max(A.thr, 0), 255);
 #pragma unroll
     for(int c = 0; c < CH; ++c) {
-        const uint32_t ref = A.ref ? A.ref[(size_t)y * A.rpitch + x * CH + c] : s_tile[sy * PITCH + sx * CH + c];
+        const uint32_t ref = A.ref ? A.ref[(size_t)y * A.rpitch + x * CH + c] : s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
         uint32_t t = tabs;
         if(A.use_rel) t = (uint32_t)fminf(fmaxf(rintf(__fadd_rn(__fmul_rn((float)ref, A.rel), (float)A.thr)), 0.f), 255.f);
-        const Lookup16 L = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
+        const Lookup16 L = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
         A.out[((size_t)y * A.W + x) * CH + c] = (ushort)lbsp_threshold(L, ref, t);
     }
 }

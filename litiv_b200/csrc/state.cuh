@@ -36,7 +36,7 @@ struct FrameCtl {
     uint32_t nonzero_count;    // accumulators, cleared by the tail kernel
     unsigned long long tot_color_diff;
     uint32_t do_refresh, refresh_epoch, refresh_start, refresh_count, refresh_force, set_T_one;
-    uint32_t flood_changed[2];
+    uint32_t flood_changed[4];   // 3 rotating convergence flags of pp_flood (+1 pad)
     uint32_t roi_count;
     unsigned long long stat_scanned, stat_writes, stat_fg; // optional instrumentation
     uint32_t pad[8];

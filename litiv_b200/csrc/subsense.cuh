@@ -12,7 +12,10 @@ namespace lvb {
 
 constexpr int TILE_W = 32, TILE_H = 8, HALO = 2;
 constexpr int TILE_ROWS = TILE_H + 2 * HALO;
-__host__ __device__ constexpr int tile_pitch(int ch) { return ((TILE_W + 2 * HALO) * ch + 15) / 16 * 16; }
+// TMA boxes must start on a 16-byte boundary of the image row: the box starts TILE_SHIFT bytes before the halo's first
+// byte ((32k-2)*ch mod 16 is the same for every tile) and is TILE_SHIFT bytes wider.
+__host__ __device__ constexpr int tile_shift(int ch) { return (16 - (HALO * ch) % 16) % 16; }
+__host__ __device__ constexpr int tile_pitch(int ch) { return (tile_shift(ch) + (TILE_W + 2 * HALO) * ch + 15) / 16 * 16; }
 
 /// stage the (TILE_W+4)x(TILE_H+4) input tile into shared memory: one TMA bulk tensor copy (zero-filled
 /// outside the image) or, when the frame pitch is not TMA-compatible, a cooperative byte copy.
@@ -28,7 +31,7 @@ __device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUt
         __syncthreads();
         if(threadIdx.x == 0 && threadIdx.y == 0) {
             mbar_expect_tx(bar, PITCH * TILE_ROWS);
-            tma_load_2d(tile, tmap, (x0 - HALO) * CH, y0 - HALO, bar);
+            tma_load_2d(tile, tmap, (x0 - HALO) * CH - tile_shift(CH), y0 - HALO, bar);
         }
         mbar_wait(bar, 0);
     } else {
@@ -39,7 +42,7 @@ __device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUt
             const int gy = y0 - HALO + r, gb = (x0 - HALO) * CH + b;
             uchar v = 0;
             if(gy >= 0 && gy < H && gb >= 0 && gb < W * CH) v = img[(size_t)gy * ipitch + gb];
-            tile[r * PITCH + b] = v;
+            tile[r * PITCH + tile_shift(CH) + b] = v;
         }
         __syncthreads();
     }
@@ -100,8 +103,8 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         uint32_t cur[CH], intra[CH];
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
-            L[c] = lbsp_lookup_smem<CH>(s_tile, PITCH, sx, sy, c);
-            cur[c] = s_tile[sy * PITCH + sx * CH + c];
+            L[c] = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
+            cur[c] = s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
             intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
         }
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
