@@ -52,11 +52,21 @@ bool make_image_tmap(CUtensorMap* map, const void* ptr, int W, int H, int C, siz
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template<typename T> T* dalloc(size_t n, bool zero = true) {
+// All device work of an instance goes to ITS stream (created non-blocking): the legacy default stream is never used,
+// because a pageable cudaMemcpy may return before its DMA has landed and a non-blocking stream would not wait for it.
+template<typename T> T* dalloc(cudaStream_t st, size_t n, bool zero = true) {
     T* p = nullptr;
     CK(cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T)));
-    if(zero) CK(cudaMemset(p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    if(zero) CK(cudaMemsetAsync(p, 0, std::max<size_t>(n, 1) * sizeof(T), st));
     return p;
+}
+void h2d(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+}
+void d2h(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
 }
 
 void morph_rect_host(const uint8_t* src, uint8_t* dst, int W, int H, int r) { // dilate only (ROI border ring, init-time)
@@ -199,30 +209,30 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     c->roi_host = r; c->orig_roi_count = orig; c->roi_count = fin;
     const int N = c->P.n_samples;
     c->ipitch = ((size_t)W * C + 127) / 128 * 128;
-    c->d_img = dalloc<uint8_t>(c->ipitch * H);
-    c->d_mask = dalloc<uint8_t>((size_t)W * H);
+    c->d_img = dalloc<uint8_t>(c->stream, c->ipitch * H);
+    c->d_mask = dalloc<uint8_t>(c->stream, (size_t)W * H);
     CK(cudaMallocHost((void**)&c->h_img, (size_t)W * H * C));
     CK(cudaMallocHost((void**)&c->h_mask, (size_t)W * H));
     c->use_tma = make_image_tmap(&c->tmap_img, c->d_img, W, H, C, c->ipitch) ? 1 : 0;
     c->ext_ptr = nullptr;
-    c->bg_color = dalloc<uint8_t>((size_t)N * c->plane * c->col_bytes());
-    c->bg_desc = dalloc<uint8_t>((size_t)N * c->plane * c->desc_bytes());
-    c->last_color = dalloc<uint8_t>(c->plane * c->col_bytes());
-    c->last_desc = dalloc<uint8_t>(c->plane * c->desc_bytes());
-    c->tmp_desc = dalloc<uint8_t>(c->plane * c->desc_bytes());
+    c->bg_color = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->col_bytes());
+    c->bg_desc = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->desc_bytes());
+    c->last_color = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
+    c->last_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
+    c->tmp_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     const size_t bp = (size_t)H * c->WW;
-    c->bits = dalloc<uint32_t>(bp * 15);
+    c->bits = dalloc<uint32_t>(c->stream, bp * 15);
     uint32_t** planes[] = {&c->roi_bits, &c->raw, &c->lastraw, &c->lastrawblink, &c->blinks, &c->tmpA, &c->pre, &c->reach, &c->comb,
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
     c->ghost_idx = 0;
-    c->intents = dalloc<ushort>(c->plane);
-    c->lut = dalloc<uint8_t>(256);
-    c->ctl = dalloc<FrameCtl>(1);
+    c->intents = dalloc<ushort>(c->stream, c->plane);
+    c->lut = dalloc<uint8_t>(c->stream, 256);
+    c->ctl = dalloc<FrameCtl>(c->stream, 1);
     {   // bit-packed ROI
         std::vector<uint32_t> rb(bp, 0);
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(r[(size_t)y * W + x]) rb[(size_t)y * c->WW + (x >> 5)] |= 1u << (x & 31);
-        CK(cudaMemcpy(c->roi_bits, rb.data(), bp * 4, cudaMemcpyHostToDevice));
+        h2d(c->stream, c->roi_bits, rb.data(), bp * 4);
     }
     {   // LBSP threshold LUT (BackgroundSubtractorLBSP.cpp:29-30, 42-43; quirk Q2)
         uint8_t lut[256];
@@ -231,7 +241,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
             const long q = std::lrint((double)v);
             lut[t] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
         }
-        CK(cudaMemcpy(c->lut, lut, 256, cudaMemcpyHostToDevice));
+        h2d(c->stream, c->lut, lut, 256);
     }
     FrameCtl f{};
     f.frame_idx = 1; f.aLT = 1.0f; f.aST = 1.0f; f.roi_count = (uint32_t)fin;
@@ -248,21 +258,22 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
             f.t_lower = 4.0f; f.t_upper = 512.0f;
         }
         if(f.lr_scaling) REQUIRE(W % 8 == 0 && H % 8 == 0, "frame-level analysis needs frame sizes that are multiples of 8 (other sizes: not implemented yet)");
-        c->maps = dalloc<float4>(c->plane * 2);
-        c->fin = dalloc<float2>(c->plane);
-        c->dsLT = dalloc<float>((size_t)c->dsW * c->dsH * C);
-        c->dsST = dalloc<float>((size_t)c->dsW * c->dsH * C);
+        c->maps = dalloc<float4>(c->stream, c->plane * 2);
+        c->fin = dalloc<float2>(c->stream, c->plane);
+        c->dsLT = dalloc<float>(c->stream, (size_t)c->dsW * c->dsH * C);
+        c->dsST = dalloc<float>(c->stream, (size_t)c->dsW * c->dsH * C);
         std::vector<float4> m(c->plane * 2);
         for(size_t i = 0; i < c->plane; ++i) { m[i * 2] = make_float4(f.t_lower, 1.0f, 10.0f, 0.f); m[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
-        CK(cudaMemcpy(c->maps, m.data(), m.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        h2d(c->stream, c->maps, m.data(), m.size() * sizeof(float4));
     }
     c->median_k = f.median_k;
     REQUIRE(c->median_k >= 1 && c->median_k <= 31 && (c->median_k & 1), "median blur kernel size must be odd and <= 31");
     // first refresh request: all N slots from slot 0 (SuBSENSE.cpp:184 refreshModel(1.0f); LOBSTER.cpp:455 refreshModel(1.0f,true))
     f.do_refresh = 1; f.refresh_epoch = 0; f.refresh_start = 0; f.refresh_count = (uint32_t)N; f.refresh_force = c->algo == LVB_ALGO_LOBSTER ? 1 : 0;
-    CK(cudaMemcpy(c->ctl, &f, sizeof(f), cudaMemcpyHostToDevice));
+    h2d(c->stream, c->ctl, &f, sizeof(f));
     // frame upload + init kernel
-    CK(cudaMemcpy2D(c->d_img, c->ipitch, img, step, (size_t)W * C, H, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy2DAsync(c->d_img, c->ipitch, img, step, (size_t)W * C, H, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     InitArgs I{};
     I.W = W; I.H = H; I.Wp = c->Wp; I.WW = c->WW; I.img = c->d_img; I.ipitch = c->ipitch; I.last_color = c->last_color; I.last_desc = c->last_desc;
     I.roi_bits = c->roi_bits; I.lut = c->lut; I.use_tma = c->use_tma;
@@ -433,10 +444,10 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
         return;
     }
     if(n == "roi") { std::memcpy(out, c->roi_host.data(), npx); return; }
-    if(n == "lut") { CK(cudaMemcpy(out, c->lut, 256, cudaMemcpyDeviceToHost)); return; }
+    if(n == "lut") { d2h(c->stream, out, c->lut, 256); return; }
     if(uint32_t* b = bits_by_name(c, n)) {
         std::vector<uint32_t> h((size_t)H * WW);
-        CK(cudaMemcpy(h.data(), b, h.size() * 4, cudaMemcpyDeviceToHost));
+        d2h(c->stream, h.data(), b, h.size() * 4);
         uint8_t* o = (uint8_t*)out;
         const bool as01 = (n == "unstable");
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) { const bool v = (h[(size_t)y * WW + (x >> 5)] >> (x & 31)) & 1u; o[(size_t)y * W + x] = v ? (as01 ? 1 : 255) : 0; }
@@ -445,19 +456,19 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
     const int mi = map_index(n);
     if(mi >= 0) {
         std::vector<float> h(c->plane * 8);
-        CK(cudaMemcpy(h.data(), c->maps, h.size() * 4, cudaMemcpyDeviceToHost));
+        d2h(c->stream, h.data(), c->maps, h.size() * 4);
         float* o = (float*)out;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) o[(size_t)y * W + x] = h[((size_t)y * Wp + x) * 8 + mi];
         return;
     }
     if(n == "finLT" || n == "finST") {
         std::vector<float> h(c->plane * 2);
-        CK(cudaMemcpy(h.data(), c->fin, h.size() * 4, cudaMemcpyDeviceToHost));
+        d2h(c->stream, h.data(), c->fin, h.size() * 4);
         float* o = (float*)out; const int k = n == "finLT" ? 0 : 1;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) o[(size_t)y * W + x] = h[((size_t)y * Wp + x) * 2 + k];
         return;
     }
-    if(n == "dsLT" || n == "dsST") { CK(cudaMemcpy(out, n == "dsLT" ? c->dsLT : c->dsST, bytes, cudaMemcpyDeviceToHost)); return; }
+    if(n == "dsLT" || n == "dsST") { d2h(c->stream, out, n == "dsLT" ? c->dsLT : c->dsST, bytes); return; }
     auto unpack_col = [&](const uint8_t* h, uint8_t* o) {
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k)
             o[((size_t)y * W + x) * C + k] = C == 1 ? h[(size_t)y * Wp + x] : h[((size_t)y * Wp + x) * 4 + k];
@@ -466,12 +477,12 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k)
             o[((size_t)y * W + x) * C + k] = C == 1 ? h[(size_t)y * Wp + x] : h[((size_t)y * Wp + x) * 4 + k];
     };
-    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes()); CK(cudaMemcpy(h.data(), c->last_color, h.size(), cudaMemcpyDeviceToHost)); unpack_col(h.data(), (uint8_t*)out); return; }
-    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2); CK(cudaMemcpy(h.data(), c->last_desc, h.size() * 2, cudaMemcpyDeviceToHost)); unpack_desc(h.data(), (uint16_t*)out); return; }
+    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes()); d2h(c->stream, h.data(), c->last_color, h.size()); unpack_col(h.data(), (uint8_t*)out); return; }
+    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2); d2h(c->stream, h.data(), c->last_desc, h.size() * 2); unpack_desc(h.data(), (uint16_t*)out); return; }
     if(n == "bg_color") {
         std::vector<uint8_t> h(c->plane * c->col_bytes());
         for(int s = 0; s < c->P.n_samples; ++s) {
-            CK(cudaMemcpy(h.data(), (uint8_t*)c->bg_color + (size_t)s * h.size(), h.size(), cudaMemcpyDeviceToHost));
+            d2h(c->stream, h.data(), (uint8_t*)c->bg_color + (size_t)s * h.size(), h.size());
             unpack_col(h.data(), (uint8_t*)out + (size_t)s * npx * C);
         }
         return;
@@ -479,7 +490,7 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
     if(n == "bg_desc") {
         std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2);
         for(int s = 0; s < c->P.n_samples; ++s) {
-            CK(cudaMemcpy(h.data(), (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.size() * 2, cudaMemcpyDeviceToHost));
+            d2h(c->stream, h.data(), (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.size() * 2);
             unpack_desc(h.data(), (uint16_t*)out + (size_t)s * npx * C);
         }
         return;
@@ -509,40 +520,40 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
         return;
     }
     REQUIRE(n != "roi", "use lvb_set_roi");
-    if(n == "lut") { CK(cudaMemcpy(c->lut, in, 256, cudaMemcpyHostToDevice)); return; }
+    if(n == "lut") { h2d(c->stream, c->lut, in, 256); return; }
     if(uint32_t* b = bits_by_name(c, n)) {
         std::vector<uint32_t> h((size_t)H * WW, 0);
         const uint8_t* s = (const uint8_t*)in;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(s[(size_t)y * W + x]) h[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
-        CK(cudaMemcpy(b, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        h2d(c->stream, b, h.data(), h.size() * 4);
         return;
     }
     const int mi = map_index(n);
     if(mi >= 0) {
         std::vector<float> h(c->plane * 8);
-        CK(cudaMemcpy(h.data(), c->maps, h.size() * 4, cudaMemcpyDeviceToHost));
+        d2h(c->stream, h.data(), c->maps, h.size() * 4);
         const float* s = (const float*)in;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) h[((size_t)y * Wp + x) * 8 + mi] = s[(size_t)y * W + x];
-        CK(cudaMemcpy(c->maps, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        h2d(c->stream, c->maps, h.data(), h.size() * 4);
         if(mi == 3 || mi == 7) { // ghost flag is derived state: rawST > 0.995 && Dlast < 0.01 inside the ROI
             std::vector<uint32_t> g((size_t)H * WW, 0);
             for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) {
                 const float* px = &h[((size_t)y * Wp + x) * 8];
                 if(c->roi_host[(size_t)y * W + x] && px[7] > 0.995f && px[3] < 0.010f) g[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
             }
-            CK(cudaMemcpy(c->ghost[c->ghost_idx], g.data(), g.size() * 4, cudaMemcpyHostToDevice));
+            h2d(c->stream, c->ghost[c->ghost_idx], g.data(), g.size() * 4);
         }
         return;
     }
     if(n == "finLT" || n == "finST") {
         std::vector<float> h(c->plane * 2);
-        CK(cudaMemcpy(h.data(), c->fin, h.size() * 4, cudaMemcpyDeviceToHost));
+        d2h(c->stream, h.data(), c->fin, h.size() * 4);
         const float* s = (const float*)in; const int k = n == "finLT" ? 0 : 1;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) h[((size_t)y * Wp + x) * 2 + k] = s[(size_t)y * W + x];
-        CK(cudaMemcpy(c->fin, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+        h2d(c->stream, c->fin, h.data(), h.size() * 4);
         return;
     }
-    if(n == "dsLT" || n == "dsST") { CK(cudaMemcpy(n == "dsLT" ? c->dsLT : c->dsST, in, bytes, cudaMemcpyHostToDevice)); return; }
+    if(n == "dsLT" || n == "dsST") { h2d(c->stream, n == "dsLT" ? c->dsLT : c->dsST, in, bytes); return; }
     auto pack_col = [&](const uint8_t* s, uint8_t* h) {
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k) {
             if(C == 1) h[(size_t)y * Wp + x] = s[(size_t)y * W + x]; else h[((size_t)y * Wp + x) * 4 + k] = s[((size_t)y * W + x) * C + k];
@@ -553,13 +564,13 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             if(C == 1) h[(size_t)y * Wp + x] = s[(size_t)y * W + x]; else h[((size_t)y * Wp + x) * 4 + k] = s[((size_t)y * W + x) * C + k];
         }
     };
-    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes(), 0); pack_col((const uint8_t*)in, h.data()); CK(cudaMemcpy(c->last_color, h.data(), h.size(), cudaMemcpyHostToDevice)); return; }
-    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); CK(cudaMemcpy(c->last_desc, h.data(), h.size() * 2, cudaMemcpyHostToDevice)); return; }
+    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes(), 0); pack_col((const uint8_t*)in, h.data()); h2d(c->stream, c->last_color, h.data(), h.size()); return; }
+    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); h2d(c->stream, c->last_desc, h.data(), h.size() * 2); return; }
     if(n == "bg_color") {
         std::vector<uint8_t> h(c->plane * c->col_bytes(), 0);
         for(int s = 0; s < c->P.n_samples; ++s) {
             pack_col((const uint8_t*)in + (size_t)s * npx * C, h.data());
-            CK(cudaMemcpy((uint8_t*)c->bg_color + (size_t)s * h.size(), h.data(), h.size(), cudaMemcpyHostToDevice));
+            h2d(c->stream, (uint8_t*)c->bg_color + (size_t)s * h.size(), h.data(), h.size());
         }
         return;
     }
@@ -567,7 +578,7 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
         std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0);
         for(int s = 0; s < c->P.n_samples; ++s) {
             pack_desc((const uint16_t*)in + (size_t)s * npx * C, h.data());
-            CK(cudaMemcpy((uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+            h2d(c->stream, (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.data(), h.size() * 2);
         }
         return;
     }
@@ -579,7 +590,7 @@ void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
     CK(cudaSetDevice(c->device));
     const size_t n = (size_t)c->W * c->H * c->C;
     uint8_t* dc = nullptr; uint16_t* dd = nullptr;
-    if(out_color) dc = dalloc<uint8_t>(n, false); else dd = dalloc<uint16_t>(n, false);
+    if(out_color) dc = dalloc<uint8_t>(c->stream, n, false); else dd = dalloc<uint16_t>(c->stream, n, false);
     if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     ++g_launches;
@@ -820,14 +831,14 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
     REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
     CK(cudaSetDevice(device));
     const size_t pitch = ((size_t)W * C + 127) / 128 * 128, nout = (size_t)W * H * C;
-    uint8_t* d_img = dalloc<uint8_t>(pitch * H), *d_ref = nullptr;
+    uint8_t* d_img = dalloc<uint8_t>((cudaStream_t)0, pitch * H), *d_ref = nullptr;
     uint16_t* d_out = nullptr;
     cudaError_t e = cudaSuccess;
     try {
-        d_out = dalloc<uint16_t>(nout, false);
+        d_out = dalloc<uint16_t>((cudaStream_t)0, nout, false);
         CK(cudaMemcpy2D(d_img, pitch, img, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice));
-        if(ref) { d_ref = dalloc<uint8_t>(pitch * H); CK(cudaMemcpy2D(d_ref, pitch, ref, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice)); }
-        CK(cudaMemcpy(d_out, out, nout * 2, cudaMemcpyHostToDevice)); // the 2-px border keeps the caller's content, as in the reference
+        if(ref) { d_ref = dalloc<uint8_t>((cudaStream_t)0, pitch * H); CK(cudaMemcpy2D(d_ref, pitch, ref, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice)); }
+        h2d((cudaStream_t)0, d_out, out, nout * 2); // the 2-px border keeps the caller's content, as in the reference
         CUtensorMap tmap;
         LbspArgs A{};
         A.W = W; A.H = H; A.img = d_img; A.ipitch = pitch; A.ref = d_ref; A.rpitch = pitch; A.out = d_out; A.use_rel = use_rel; A.rel = rel; A.thr = thr;
@@ -835,7 +846,7 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
         const dim3 g((W + 31) / 32, (H + 7) / 8), b(32, 8);
         if(C == 1) lbsp_dense_kernel<1><<<g, b>>>(A, tmap); else lbsp_dense_kernel<3><<<g, b>>>(A, tmap);
         LAUNCHED();
-        CK(cudaMemcpy(out, d_out, nout * 2, cudaMemcpyDeviceToHost));
+        d2h((cudaStream_t)0, out, d_out, nout * 2);
     } catch(...) { cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out); throw; }
     cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out);
     (void)e;
