@@ -80,6 +80,11 @@ double lvb_default_learning_rate(int algo);
 int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref_or_null, int width, int height, int channels,
                      int use_rel, float rel, int thr, uint16_t* out, int device);
 
+/* the bit-packed mask operators that replace the reference's OpenCV calls (SuBSENSE.cpp:536-554), standalone on byte masks:
+ * op 0 cv::dilate / 1 cv::erode with a (2*param+1)^2 rect (param 1 or 3) ; 2 cv::medianBlur(param) on a binary mask ;
+ * 3 cv::floodFill((0,0),255)+bitwise_not ("holes": background not 4-connected to the border, needs src(0,0)==0) */
+int lvb_mask_op(int op, const uint8_t* src, uint8_t* dst, int width, int height, int param, int device);
+
 /* parity / debug: named state buffers in the reference's layout (sample-major [N][H][W][C], maps [H][W]); see DESIGN.md */
 int lvb_state_size(lvb_handle h, const char* name, size_t* bytes);
 int lvb_state_get(lvb_handle h, const char* name, void* out, size_t bytes);

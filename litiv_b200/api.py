@@ -19,7 +19,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op",
 ]
 
 
@@ -74,6 +74,7 @@ def lib():
         L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
         L.lvb_host_free.argtypes = [C.c_void_p]
+        L.lvb_mask_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -264,6 +265,17 @@ class BackgroundSubtractorLOBSTER(_BackgroundSubtractor):
         p.desc_dist_threshold, p.color_dist_threshold, p.n_samples = nDescDistThreshold, nColorDistThreshold, nBGSamples
         p.n_required, p.lbsp_threshold_offset, p.rel_lbsp_threshold = nRequiredBGSamples, nLBSPThresholdOffset, fRelLBSPThreshold
         super().__init__(p, device, seed)
+
+
+MASK_DILATE, MASK_ERODE, MASK_MEDIAN, MASK_HOLES = 0, 1, 2, 3
+
+
+def mask_op(op, mask, param=0, device=0):
+    """bit-packed GPU mask operator on a byte mask (see lvb_mask_op)"""
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(mask)
+    _chk(lib().lvb_mask_op(op, mask.ctypes.data, out.ctypes.data, mask.shape[1], mask.shape[0], param, device))
+    return out
 
 
 def pinned_empty(shape, dtype=np.uint8):

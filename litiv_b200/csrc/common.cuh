@@ -79,10 +79,6 @@ __device__ __forceinline__ uint32_t lbsp_threshold(const Lookup16& L, uint32_t r
 // ---------------------------------------------------------------------------------------------
 // sampling patterns
 // ---------------------------------------------------------------------------------------------
-__device__ __constant__ const signed char c_nb3[8][2] = {{-1, 1}, {0, 1}, {1, 1}, {-1, 0}, {1, 0}, {-1, -1}, {0, -1}, {1, -1}};
-__device__ __constant__ const signed char c_nb5[24][2] = {
-    {-2, 2}, {-1, 2}, {0, 2}, {1, 2}, {2, 2}, {-2, 1}, {-1, 1}, {0, 1}, {1, 1}, {2, 1}, {-2, 0}, {-1, 0},
-    {1, 0}, {2, 0}, {-2, -1}, {-1, -1}, {0, -1}, {1, -1}, {2, -1}, {-2, -2}, {-1, -2}, {0, -2}, {1, -2}, {2, -2}};
 __device__ __constant__ const unsigned char c_pat7[49] = {
     2, 4, 6, 7, 6, 4, 2, 4, 8, 12, 14, 12, 8, 4, 6, 12, 21, 25, 21, 12, 6, 7, 14, 25, 28, 25, 14, 7,
     6, 12, 21, 25, 21, 12, 6, 4, 8, 12, 14, 12, 8, 4, 2, 4, 6, 7, 6, 4, 2};
@@ -98,13 +94,11 @@ __device__ __forceinline__ void sample_pos_7x7(uint32_t rnd, int& sx, int& sy, i
     sx = clampi(ox + (i % 7) - 3, 2, W - 3);
     sy = clampi(oy + (i / 7) - 3, 2, H - 3);
 }
-/// neighbour code: bit 5 set = 3x3 pattern (index in low bits), else 5x5 pattern index
-__device__ __forceinline__ void neighbor_from_code(uint32_t code, int& nx, int& ny, int ox, int oy, int W, int H) {
-    int dx, dy;
-    if(code & 32u) { dx = c_nb3[code & 7u][0]; dy = c_nb3[code & 7u][1]; }
-    else { dx = c_nb5[code & 31u][0]; dy = c_nb5[code & 31u][1]; }
-    nx = clampi(ox + dx, 2, W - 3);
-    ny = clampi(oy + dy, 2, H - 3);
+/// opencv.hpp:941-966 — offset of entry r of the 3x3 (8 entries) / 5x5 (24 entries) neighbour patterns, computed
+/// arithmetically (row-major from +y, centre skipped) so divergent lanes do not serialise on a constant table
+__device__ __forceinline__ void neighbor_offset(bool use3x3, uint32_t rnd, int& dx, int& dy) {
+    if(use3x3) { const int r = (int)(rnd % 8u), k = r + (r >= 4); dx = k % 3 - 1; dy = 1 - k / 3; }
+    else { const int r = (int)(rnd % 24u), k = r + (r >= 12); dx = k % 5 - 2; dy = 2 - k / 5; }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -90,7 +90,7 @@ struct lvb_context {
     size_t plane = 0;
     cudaStream_t stream = nullptr;
     bool initialized = false;
-    int num_sms = 0, flood_blocks_per_sm = 0;
+    int uf_rs = 0; uint32_t* uf_parent = nullptr; ushort* uf_rankbase = nullptr;
     // frame staging
     uint8_t* d_img = nullptr; size_t ipitch = 0; CUtensorMap tmap_img; int use_tma = 0;
     const uint8_t* ext_ptr = nullptr; size_t ext_pitch = 0; CUtensorMap tmap_ext; int ext_tma = 0;
@@ -119,10 +119,10 @@ struct lvb_context {
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
 
     void free_all() {
-        void* ptrs[] = {d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST};
+        void* ptrs[] = {uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
         h_img = h_mask = nullptr;
@@ -226,6 +226,9 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
     c->ghost_idx = 0;
+    c->uf_rs = (W + 1) / 2 + 1;
+    c->uf_parent = dalloc<uint32_t>(c->stream, (size_t)H * c->uf_rs + 1);
+    c->uf_rankbase = dalloc<ushort>(c->stream, (size_t)H * c->WW);
     c->intents = dalloc<ushort>(c->stream, c->plane);
     c->lut = dalloc<uint8_t>(c->stream, 256);
     c->ctl = dalloc<FrameCtl>(c->stream, 1);
@@ -284,11 +287,6 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     launch_refresh(c);
     CK(cudaStreamSynchronize(c->stream));
     c->stat_frames = 0;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, c->device));
-    c->num_sms = prop.multiProcessorCount;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->flood_blocks_per_sm, pp_flood, 256, 0));
-    REQUIRE(c->flood_blocks_per_sm > 0, "cooperative flood kernel cannot be resident");
 }
 
 uint32_t lr_to_fixed(double lr) {
@@ -317,7 +315,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv;
     P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
-    const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c);
+    const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c), mg(c->Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
@@ -331,14 +329,15 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         pp_blink_dilate<<<wg, 256, 0, st>>>(P); LAUNCHED();
         pp_erode_seed<<<wg, 256, 0, st>>>(P); LAUNCHED();
         {
-            int bands = (H + FLOOD_BAND - 1) / FLOOD_BAND;
-            int blocks = std::max(std::min((bands + 7) / 8, c->num_sms * c->flood_blocks_per_sm), 1);
-            void* args[] = {(void*)&P, (void*)&bands};
-            CK(cudaLaunchCooperativeKernel((void*)pp_flood, dim3(blocks), dim3(256), args, 0, st));
-            LAUNCHED();
+            HoleArgs Hh{};
+            Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw; Hh.comb = c->comb;
+            Hh.parent = c->uf_parent; Hh.rankbase = c->uf_rankbase;
+            const int rb = (H + 7) / 8;
+            pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+            pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+            pp_holes_combine<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
         }
-        pp_combine<<<wg, 256, 0, st>>>(P); LAUNCHED();
-        pp_median<<<tg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
+        pp_median<<<mg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
         pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED();
         pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED();
         DownsampleArgs D{};
@@ -359,7 +358,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
         LAUNCHED();
-        pp_median<<<tg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
+        pp_median<<<mg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
         lobster_tail_kernel<<<1, 1, 0, st>>>(c->ctl); LAUNCHED();
     }
     if(c->collect_stats) ++c->stat_frames;
@@ -822,6 +821,51 @@ int lvb_host_alloc(void** out, size_t bytes) {
     LVB_CATCH
 }
 int lvb_host_free(void* p) { if(p) cudaFreeHost(p); return 0; }
+
+
+/// standalone mask operators on byte masks (non-zero = set): the bit-packed kernels the subtractors use, exposed so they
+/// can be checked one by one against the OpenCV-equivalent oracle ops. op: 0 dilate(r) 1 erode(r) 2 median(k) 3 holes
+/// (pixels NOT reached by cv::floodFill from (0,0), i.e. floodFill+bitwise_not) ; r in {1,3}
+int lvb_mask_op(int op, const uint8_t* src, uint8_t* dst, int W, int H, int param, int device) {
+    LVB_TRY
+    REQUIRE(src && dst && W >= 1 && H >= 1 && W <= 8192, "bad mask arguments");
+    REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const int WW = (W + 31) / 32, Wp = WW * 32;
+    const size_t bp = (size_t)H * WW;
+    std::vector<uint32_t> hb(bp, 0);
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(src[(size_t)y * W + x]) hb[(size_t)y * WW + (x >> 5)] |= 1u << (x & 31);
+    cudaStream_t st = 0;
+    uint32_t* d = dalloc<uint32_t>(st, bp * 3);
+    uint32_t* par = nullptr; ushort* rk = nullptr; uint8_t* dm = nullptr;
+    try {
+        h2d(st, d, hb.data(), bp * 4);
+        uint32_t* out = d + bp;
+        PostArgs P{};
+        P.W = W; P.H = H; P.WW = WW; P.Wp = Wp;
+        const dim3 wg((WW + 255) / 256, H);
+        if(op == 0 || op == 1) {
+            REQUIRE(param == 1 || param == 3, "morphology radius must be 1 or 3");
+            mask_morph_kernel<<<wg, 256, 0, st>>>(d, out, W, H, WW, op == 0, param); LAUNCHED();
+        } else if(op == 2) {
+            REQUIRE(param >= 1 && param <= 31 && (param & 1), "median blur kernel size must be odd and <= 31");
+            pp_median<<<dim3(Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS)), dim3(32, 8), 0, st>>>(d, out, nullptr, 0, W, H, WW, param); LAUNCHED();
+        } else if(op == 3) {
+            HoleArgs Hh{};
+            Hh.W = W; Hh.H = H; Hh.WW = WW; Hh.RS = (W + 1) / 2 + 1; Hh.pre = d; Hh.raw = d + 2 * bp; Hh.comb = out;
+            par = dalloc<uint32_t>(st, (size_t)H * Hh.RS + 1); rk = dalloc<ushort>(st, bp);
+            Hh.parent = par; Hh.rankbase = rk;
+            const int rb = (H + 7) / 8;
+            pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+            pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+            pp_holes_only<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+        } else throw std::runtime_error("unknown mask op");
+        d2h(st, hb.data(), out, bp * 4);
+    } catch(...) { cudaFree(d); cudaFree(par); cudaFree(rk); cudaFree(dm); throw; }
+    cudaFree(d); cudaFree(par); cudaFree(rk); cudaFree(dm);
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) dst[(size_t)y * W + x] = ((hb[(size_t)y * WW + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+    LVB_CATCH
+}
 
 int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C, int use_rel, float rel, int thr, uint16_t* out, int device) {
     LVB_TRY

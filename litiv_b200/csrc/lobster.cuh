@@ -98,9 +98,11 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                     ++writes;
                 }
                 if(nb) {
-                    const uint32_t code = 32u | (rnd.w % 8u);
+                    int dx, dy;
+                    neighbor_offset(true, rnd.w, dx, dy);
+                    const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
                     const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
-                    A.intents[pix] = (ushort)((code << 8) | slot);
+                    A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                     ((Desc*)A.last_desc)[pix] = intra_pack; // scratch plane read by phase B (not the reference's m_oLastDescFrame)
                     has_intent = true;
                 }

@@ -5,10 +5,8 @@
 //   border; floodFill((0,0)) + bitwise_not: background pixels not 4-connected to the image border ring.
 #pragma once
 #include "state.cuh"
-#include <cooperative_groups.h>
 
 namespace lvb {
-namespace cg = cooperative_groups;
 
 struct PostArgs {
     int W, H, WW, Wp;
@@ -59,19 +57,13 @@ __global__ void __launch_bounds__(256) pp_blink_dilate(const PostArgs A) {
     A.lastraw[i] = raw;
     A.tmpA[i] = morph_word<1, true>(A.raw, y, wi, A.H, A.WW, A.W);
 }
-/// second half of MORPH_CLOSE (erode 3x3) + seeds of the border flood (the 2-px border ring is always background)
+/// second half of MORPH_CLOSE (erode 3x3)
 __global__ void __launch_bounds__(256) pp_erode_seed(const PostArgs A) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if(wi >= A.WW) return;
     const size_t i = (size_t)y * A.WW + wi;
     const uint32_t pre = morph_word<1, false>(A.tmpA, y, wi, A.H, A.WW, A.W);
     A.pre[i] = pre;
-    const uint32_t vm = valid_mask(wi, A.WW, A.W);
-    uint32_t seed = 0;
-    if(y == 0 || y == A.H - 1) seed = vm;
-    if(wi == 0) seed |= 1u;
-    if(wi == A.WW - 1) seed |= 1u << ((A.W - 1) & 31);
-    A.reach[i] = seed & ~pre & vm;
 }
 
 /// horizontal run fill of one 32-word chunk held one word per lane: returns the bits of m connected (towards higher
@@ -91,115 +83,171 @@ __device__ __forceinline__ uint32_t fill_up_chunk(uint32_t m, uint32_t s, uint32
 }
 
 constexpr int FLOOD_MAX_CHUNKS = 8; // rows up to 8192 pixels
-constexpr int FLOOD_BAND = 16;
 
-/// one row step: seeds = own reach | vertical neighbours' reach, restricted to background m; complete horizontal fill
-__device__ __forceinline__ bool flood_row(const uint32_t* __restrict__ pre, uint32_t* reach, int y, int H, int WW, int W, int nchunks) {
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t m[FLOOD_MAX_CHUNKS], s[FLOOD_MAX_CHUNKS], old[FLOOD_MAX_CHUNKS], up[FLOOD_MAX_CHUNKS];
-    bool changed = false;
-#pragma unroll
-    for(int k = 0; k < FLOOD_MAX_CHUNKS; ++k) {
-        m[k] = 0; s[k] = 0; old[k] = 0;
-        if(k < nchunks) {
-            const int wi = k * 32 + lane;
-            if(wi < WW) {
-                const size_t i = (size_t)y * WW + wi;
-                m[k] = ~pre[i] & valid_mask(wi, WW, W);
-                old[k] = __ldcg(reach + i);
-                uint32_t v = old[k];
-                if(y > 0) v |= __ldcg(reach + i - WW);
-                if(y < H - 1) v |= __ldcg(reach + i + WW);
-                s[k] = v & m[k];
-            }
-        }
+// ---- hole filling: connected components of the background on ROW RUNS, lock-free union-find --------------------------
+// cv::floodFill(pre,(0,0),255) + bitwise_not marks the background pixels that are NOT 4-connected to the image border
+// (the 2-px border ring is always background). A background run of row y and one of row y-1 are connected iff they
+// share a column, i.e. each maximal run of (bg[y-1] & bg[y]) is one edge. Nodes: 0 = border, 1 + y*RS + rank = the
+// rank-th background run of row y. Three tiny kernels (warp per row) replace the iterative flood; cost is independent
+// of the blob geometry.
+struct HoleArgs {
+    int W, H, WW, RS;
+    const uint32_t* pre; const uint32_t* raw; uint32_t* comb;
+    uint32_t* parent; ushort* rankbase;   // parent[1 + H*RS], rankbase[H*WW]
+};
+__device__ __forceinline__ uint32_t bg_word(const uint32_t* __restrict__ pre, int y, int wi, int WW, int W) {
+    return (wi < 0 || wi >= WW) ? 0u : (~pre[(size_t)y * WW + wi] & valid_mask(wi, WW, W));
+}
+/// start bits of the background runs inside word wi (a run continuing from the previous word has no start bit here)
+__device__ __forceinline__ uint32_t run_starts(uint32_t m, uint32_t m_prev) { return m & ~((m << 1) | (m_prev >> 31)); }
+
+__device__ __forceinline__ uint32_t uf_find(uint32_t* P, uint32_t x) {
+    uint32_t p = __ldcg(P + x);
+    while(p != x) {
+        const uint32_t gp = __ldcg(P + p);
+        if(gp != p) __stcg(P + x, gp); // path halving: only ever re-points to an ancestor
+        x = p; p = gp;
     }
-    uint32_t carry = 0;
-#pragma unroll
-    for(int k = 0; k < FLOOD_MAX_CHUNKS; ++k) if(k < nchunks) up[k] = fill_up_chunk(m[k], s[k], carry);
-    carry = 0;
-#pragma unroll
-    for(int rk = 0; rk < FLOOD_MAX_CHUNKS; ++rk) {
-        const int k = nchunks - 1 - rk;
-        if(rk < nchunks) {
-            // reversed view: lane i holds the bit-reversed word of lane 31-i
-            const uint32_t mr = __brev(__shfl_sync(0xFFFFFFFFu, m[k], 31 - lane));
-            const uint32_t sr = __brev(__shfl_sync(0xFFFFFFFFu, s[k], 31 - lane));
-            const uint32_t dr = fill_up_chunk(mr, sr, carry);
-            const uint32_t down = __brev(__shfl_sync(0xFFFFFFFFu, dr, 31 - lane));
-            const uint32_t res = up[k] | down;
-            const int wi = k * 32 + lane;
-            if(wi < WW && res != old[k]) { __stcg(reach + (size_t)y * WW + wi, res); changed = true; }
-        }
+    return x;
+}
+__device__ __forceinline__ void uf_union(uint32_t* P, uint32_t a, uint32_t b) {
+    while(true) {
+        a = uf_find(P, a); b = uf_find(P, b);
+        if(a == b) return;
+        if(a < b) { const uint32_t t = a; a = b; b = t; } // hook the larger root under the smaller: node 0 (border) stays a root
+        if(atomicCAS(P + a, a, b) == a) return;
     }
-    return changed;
 }
 
-/// border flood to convergence (cv::floodFill((0,0)) equivalent). Cooperative launch; each warp owns a band of rows
-/// and sweeps it down then up per global iteration; grid-wide barrier between iterations.
-__global__ void __launch_bounds__(256) pp_flood(const PostArgs A, int bands) {
-    cg::grid_group grid = cg::this_grid();
-    const int warps_per_block = blockDim.x >> 5;
-    const int gw = blockIdx.x * warps_per_block + (threadIdx.x >> 5), nw = gridDim.x * warps_per_block;
+/// UF1: per row, number the background runs and make each its own root
+__global__ void __launch_bounds__(256) pp_holes_init(const HoleArgs A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    if(y == 0 && lane == 0) A.parent[0] = 0;
     const int nchunks = (A.WW + 31) >> 5;
-    volatile uint32_t* flags = A.ctl->flood_changed; // 3 rotating flags (see below), all zero on entry
-    __shared__ uint32_t s_flags[3];
-    for(uint32_t it = 0;; ++it) {
-        bool changed = false;
-        for(int b = gw; b < bands; b += nw) {
-            const int y0 = b * FLOOD_BAND, y1 = min(y0 + FLOOD_BAND, A.H);
-            for(int y = y0; y < y1; ++y) changed |= flood_row(A.pre, A.reach, y, A.H, A.WW, A.W, nchunks);
-            for(int y = y1 - 2; y >= y0; --y) changed |= flood_row(A.pre, A.reach, y, A.H, A.WW, A.W, nchunks);
+    uint32_t base = 0;
+    for(int k = 0; k < nchunks; ++k) {
+        const int wi = k * 32 + lane;
+        const uint32_t st = run_starts(bg_word(A.pre, y, wi, A.WW, A.W), bg_word(A.pre, y, wi - 1, A.WW, A.W));
+        uint32_t cnt = __popc(st), incl = cnt;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if(lane >= o) incl += v; }
+        const uint32_t excl = base + incl - cnt;
+        if(wi < A.WW) {
+            A.rankbase[(size_t)y * A.WW + wi] = (ushort)excl;
+            for(uint32_t r = 0; r < cnt; ++r) { const uint32_t id = 1u + (uint32_t)y * A.RS + excl + r; A.parent[id] = id; }
         }
-        if(__any_sync(0xFFFFFFFFu, changed) && (threadIdx.x & 31) == 0) atomicOr((uint32_t*)&flags[it % 3], 1u);
-        __threadfence();
-        grid.sync();
-        if(threadIdx.x == 0) {
-            s_flags[0] = flags[it % 3];
-            // flag (it+2)%3 was last read after barrier it-1 and is next written after barrier it+1: safe to clear now
-            if(blockIdx.x == 0) flags[(it + 2) % 3] = 0;
-        }
-        __syncthreads();
-        const uint32_t f = s_flags[0];
-        __syncthreads();
-        if(!f) break;
+        base += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
-    // leave all three flags zero for the next frame: flag it%3 is 0 (loop exit), (it+2)%3 cleared above, (it+1)%3 untouched since cleared
+}
+/// node id of the background run of row y that contains bit b of word wi
+__device__ __forceinline__ uint32_t run_id(const HoleArgs& A, int y, int wi, int b) {
+    const uint32_t st = run_starts(bg_word(A.pre, y, wi, A.WW, A.W), bg_word(A.pre, y, wi - 1, A.WW, A.W));
+    const uint32_t upto = b == 31 ? 0xFFFFFFFFu : ((2u << b) - 1u);
+    return 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi] + __popc(st & upto) - 1u;
+}
+/// UF2: union vertically adjacent runs, and every run touching the image border with node 0
+__global__ void __launch_bounds__(256) pp_holes_union(const HoleArgs A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    for(int wi = lane; wi < A.WW; wi += 32) {
+        const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
+        if(y > 0) {
+            const uint32_t c = m & bg_word(A.pre, y - 1, wi, A.WW, A.W);
+            const uint32_t cp = bg_word(A.pre, y, wi - 1, A.WW, A.W) & bg_word(A.pre, y - 1, wi - 1, A.WW, A.W);
+            uint32_t cs = run_starts(c, cp);
+            while(cs) { const int b = __ffs(cs) - 1; cs &= cs - 1; uf_union(A.parent, run_id(A, y - 1, wi, b), run_id(A, y, wi, b)); }
+        }
+        uint32_t touch = 0;
+        if(y == 0 || y == A.H - 1) touch = run_starts(m, bg_word(A.pre, y, wi - 1, A.WW, A.W)) | (wi == 0 ? (m & 1u) : 0u);
+        if(wi == 0) touch |= m & 1u;
+        if(wi == A.WW - 1) touch |= m & (1u << ((A.W - 1) & 31));
+        while(touch) { const int b = __ffs(touch) - 1; touch &= touch - 1; uf_union(A.parent, run_id(A, y, wi, b), 0u); }
+    }
+}
+/// UF3: runs whose root is the border node are "reached"; fill them from their start bits (carry trick), the rest of the
+/// background is holes; fused with  m = raw | holes | erode7x7(pre)  (SuBSENSE.cpp:543-546)
+__global__ void __launch_bounds__(256) pp_holes_combine(const HoleArgs A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    const int nchunks = (A.WW + 31) >> 5;
+    uint32_t carry = 0;
+    for(int k = 0; k < nchunks; ++k) {
+        const int wi = k * 32 + lane;
+        const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
+        uint32_t st = run_starts(m, bg_word(A.pre, y, wi - 1, A.WW, A.W)), rs = 0;
+        if(wi < A.WW) {
+            const uint32_t base = 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi];
+            uint32_t r = 0;
+            while(st) { const int b = __ffs(st) - 1; st &= st - 1; if(uf_find(A.parent, base + r) == 0u) rs |= 1u << b; ++r; }
+        }
+        const uint32_t reach = fill_up_chunk(m, rs, carry);
+        if(wi < A.WW) {
+            const size_t i = (size_t)y * A.WW + wi;
+            A.comb[i] = A.raw[i] | (m & ~reach) | morph_word<3, false>(A.pre, y, wi, A.H, A.WW, A.W);
+        }
+    }
 }
 
-/// m = raw | holes | erode7x7(pre)   (SuBSENSE.cpp:543-546); holes = background of `pre` not reached by the border flood
-__global__ void __launch_bounds__(256) pp_combine(const PostArgs A) {
+/// holes only (standalone operator / tests): same as pp_holes_combine without the raw / erode terms
+__global__ void __launch_bounds__(256) pp_holes_only(const HoleArgs A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    const int nchunks = (A.WW + 31) >> 5;
+    uint32_t carry = 0;
+    for(int k = 0; k < nchunks; ++k) {
+        const int wi = k * 32 + lane;
+        const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
+        uint32_t st = run_starts(m, bg_word(A.pre, y, wi - 1, A.WW, A.W)), rs = 0;
+        if(wi < A.WW) {
+            const uint32_t base = 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi];
+            uint32_t r = 0;
+            while(st) { const int b = __ffs(st) - 1; st &= st - 1; if(uf_find(A.parent, base + r) == 0u) rs |= 1u << b; ++r; }
+        }
+        const uint32_t reach = fill_up_chunk(m, rs, carry);
+        if(wi < A.WW) A.comb[(size_t)y * A.WW + wi] = m & ~reach;
+    }
+}
+/// standalone rect dilate / erode (radius 1 or 3)
+__global__ void __launch_bounds__(256) mask_morph_kernel(const uint32_t* __restrict__ src, uint32_t* dst, int W, int H, int WW, bool dilate, int r) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if(wi >= A.WW) return;
-    const size_t i = (size_t)y * A.WW + wi;
-    const uint32_t vm = valid_mask(wi, A.WW, A.W);
-    const uint32_t holes = ~A.pre[i] & ~A.reach[i] & vm;
-    A.comb[i] = A.raw[i] | holes | morph_word<3, false>(A.pre, y, wi, A.H, A.WW, A.W);
+    if(wi >= WW) return;
+    uint32_t v;
+    if(dilate) v = r == 1 ? morph_word<1, true>(src, y, wi, H, WW, W) : morph_word<3, true>(src, y, wi, H, WW, W);
+    else v = r == 1 ? morph_word<1, false>(src, y, wi, H, WW, W) : morph_word<3, false>(src, y, wi, H, WW, W);
+    dst[(size_t)y * WW + wi] = v;
 }
 
-/// k x k majority (== cv::medianBlur on a binary mask, replicated borders); one thread per pixel.
-/// Writes the bit-packed result and the byte mask handed back to the caller.
+/// k x k majority (== cv::medianBlur on a binary mask, replicated borders). Each thread owns one column of a
+/// 32 x (8*MEDIAN_ROWS) tile and slides the window down it: the k-bit row popcounts enter and leave a running sum,
+/// so a pixel costs ~2 row evaluations instead of k. Writes the bit-packed result and the caller's byte mask.
+constexpr int MEDIAN_ROWS = 16;
+__device__ __forceinline__ int median_row_count(const uint32_t* __restrict__ src, int yy, int wi, int xb, int r, uint32_t wmask, int H, int WW, int W) {
+    const uint32_t* row = src + (size_t)clampi(yy, 0, H - 1) * WW;
+    const uint32_t l = row_word<FILL_REPL>(row, wi - 1, WW, W), c = row_word<FILL_REPL>(row, wi, WW, W), rr = row_word<FILL_REPL>(row, wi + 1, WW, W);
+    const unsigned long long lo = ((unsigned long long)c << 32) | l, hi = ((unsigned long long)rr << 32) | c;
+    const uint32_t win = (xb >= r) ? (uint32_t)(hi >> (xb - r)) : (uint32_t)(lo >> (32 + xb - r));
+    return __popc(win & wmask);
+}
 __global__ void __launch_bounds__(256) pp_median(const uint32_t* __restrict__ src, uint32_t* dst, uchar* out_mask, size_t out_pitch,
                                                   int W, int H, int WW, int k) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    const int wi = x >> 5, xb = x & 31, r = k >> 1;
-    bool on = false;
-    if(x < W && y < H) {
-        const uint32_t wmask = (1u << k) - 1u;
-        int cnt = 0;
-        for(int dy = -r; dy <= r; ++dy) {
-            const int yy = clampi(y + dy, 0, H - 1);
-            const uint32_t* row = src + (size_t)yy * WW;
-            const uint32_t l = row_word<FILL_REPL>(row, wi - 1, WW, W), c = row_word<FILL_REPL>(row, wi, WW, W), rr = row_word<FILL_REPL>(row, wi + 1, WW, W);
-            const unsigned long long lo = ((unsigned long long)c << 32) | l, hi = ((unsigned long long)rr << 32) | c;
-            const uint32_t win = (xb >= r) ? (uint32_t)(hi >> (xb - r)) : (uint32_t)(lo >> (32 + xb - r));
-            cnt += __popc(win & wmask);
-        }
-        on = cnt > (k * k) / 2;
-        if(out_mask) out_mask[(size_t)y * out_pitch + x] = on ? 255 : 0;
+    const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * MEDIAN_ROWS;
+    const int wi = x >> 5, xb = x & 31, r = k >> 1, half = (k * k) / 2;
+    const uint32_t wmask = (1u << k) - 1u;
+    const bool col_ok = x < W && wi < WW;
+    int sum = 0;
+    if(col_ok && y0 < H)
+        for(int dy = -r; dy <= r; ++dy) sum += median_row_count(src, y0 + dy, wi, xb, r, wmask, H, WW, W);
+#pragma unroll 4
+    for(int i = 0; i < MEDIAN_ROWS; ++i) {
+        const int y = y0 + i;
+        if(y >= H) break; // warp-uniform: y depends on threadIdx.y only
+        if(i > 0 && col_ok) sum += median_row_count(src, y + r, wi, xb, r, wmask, H, WW, W) - median_row_count(src, y - r - 1, wi, xb, r, wmask, H, WW, W);
+        const bool on = col_ok && sum > half;
+        if(col_ok && out_mask) out_mask[(size_t)y * out_pitch + x] = on ? 255 : 0;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, on);
+        if(threadIdx.x == 0 && wi < WW) dst[(size_t)y * WW + wi] = b;
     }
-    const uint32_t b = __ballot_sync(0xFFFFFFFFu, on);
-    if(threadIdx.x == 0 && y < H && wi < WW) dst[(size_t)y * WW + wi] = b;
 }
 
 /// dilate 7x7 of the final mask + blink gating (SuBSENSE.cpp:548-551)

@@ -196,14 +196,15 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 ++writes;
             }
             const bool cur3 = use3x3 && !unstable_new;
-            const uint32_t code = cur3 ? (32u | (rnd.z % 8u)) : (rnd.z % 24u);
-            int nx, ny;
-            neighbor_from_code(code, nx, ny, x, y, A.W, A.H);
+            int dx, dy;
+            neighbor_offset(cur3, rnd.z, dx, dy);
+            const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
             const bool nb_ghost = (A.ghost_prev[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u;
             const uint32_t n_rand = rnd.w;
             if((n_rand % (cur3 ? LR : (LR / 2u + 1u))) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
                 const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
-                A.intents[pix] = (ushort)((code << 8) | slot);
+                // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
+                A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                 has_intent = true;
             }
         }
@@ -268,12 +269,13 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
 /// Phase B: apply the queued neighbour writes. One thread per TARGET pixel gathers the intents of the 5x5
 /// sources around it in raster order, so the last writer in raster order wins (oracle MODE_SNAPSHOT rule).
+/// A source at window position (k,dy) targets this pixel iff its stored offset index equals (2-dy)*5 + (4-k).
 struct PhaseBArgs {
     int W, H, Wp, WW, CH;
     size_t plane;
     const uchar* img; size_t ipitch;
     void* bg_color; void* bg_desc;
-    const void* last_desc;     // == this frame's intra descriptors for every active pixel
+    const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
     const uint32_t* intent_bits; const ushort* intents;
 };
 
@@ -298,9 +300,7 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
             const int qx = x - 2 + k;
             const size_t qpix = (size_t)qy * A.Wp + qx;
             const uint32_t it = A.intents[qpix];
-            int tx, ty;
-            neighbor_from_code(it >> 8, tx, ty, qx, qy, A.W, A.H);
-            if(tx == x && ty == y) {
+            if((int)(it >> 8) == (2 - dy) * 5 + (4 - k)) {
                 const uint32_t slot = it & 0xFFu;
                 const size_t dst = (size_t)slot * A.plane + (size_t)y * A.Wp + x;
                 const uchar* src = A.img + (size_t)qy * A.ipitch + (size_t)qx * CH;

@@ -214,3 +214,44 @@ def test_errors_match_reference_messages(lv):
         lob.apply(np.zeros((40, 40), np.uint8), 0.0)
     with pytest.raises(lv.LitivError, match="more sample matches"):
         lv.BackgroundSubtractorSuBSENSE(nBGSamples=2, nRequiredBGSamples=3)
+
+
+def _shapes(h, w, rng):
+    """nasty masks for the hole filler: nested rings, a spiral, random noise, blobs touching the border zone"""
+    m = np.zeros((h, w), np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for r0, r1 in ((30, 34), (18, 22), (6, 10)):
+        d = np.hypot(yy - h // 2, xx - w // 3)
+        m[(d >= r0) & (d < r1)] = 255
+    # square spiral
+    x0, y0, x1, y1 = w // 2 + 4, 6, w - 6, h - 6
+    while x1 - x0 > 8 and y1 - y0 > 8:
+        m[y0, x0:x1] = 255; m[y0:y1, x1 - 1] = 255; m[y1 - 1, x0 + 4:x1] = 255; m[y0 + 4:y1, x0 + 4] = 255
+        x0 += 4; y0 += 4; x1 -= 4; y1 -= 4
+        m[y0, x0:x1 - 4] = 255
+    m[rng.rand(h, w) < 0.02] = 255
+    m[:2] = 0; m[-2:] = 0; m[:, :2] = 0; m[:, -2:] = 0
+    return m
+
+
+@pytest.mark.parametrize("shape", [(96, 130), (240, 320), (61, 75), (120, 33), (1080, 1920)])
+def test_mask_ops_match_oracle(lv, oracle, shape):
+    import ctypes as C
+    h, w = shape
+    rng = np.random.RandomState(h * 7 + w)
+    L = oracle.lib()
+    for name, m in (("shapes", _shapes(h, w, rng)), ("noise", ((rng.rand(h, w) < 0.45) * 255).astype(np.uint8)), ("empty", np.zeros((h, w), np.uint8))):
+        if name != "shapes":
+            m[:2] = 0; m[-2:] = 0; m[:, :2] = 0; m[:, -2:] = 0
+        for op, r, dil in ((lv.MASK_DILATE, 1, 1), (lv.MASK_DILATE, 3, 1), (lv.MASK_ERODE, 1, 0), (lv.MASK_ERODE, 3, 0)):
+            want = np.empty_like(m)
+            L.lvo_morph_rect(m.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), w, h, r, dil)
+            assert np.array_equal(lv.mask_op(op, m, r), want), (name, op, r)
+        for k in (3, 9, 13):
+            want = np.empty_like(m)
+            L.lvo_median_binary(m.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), w, h, k)
+            assert np.array_equal(lv.mask_op(lv.MASK_MEDIAN, m, k), want), (name, "median", k)
+        flooded = m.copy()
+        L.lvo_floodfill_origin(flooded.ctypes.data_as(C.c_void_p), w, h)
+        got = lv.mask_op(lv.MASK_HOLES, m)
+        assert np.array_equal(got, 255 - flooded), (name, "holes", int((got != 255 - flooded).sum()))
