@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "litiv_b200.cu")
-SO = os.path.join(HERE, "liblitiv_b200.so")
+SO = os.environ.get("LVB_SO") or os.path.join(HERE, "liblitiv_b200.so")  # LVB_SO: load an alternative build (tuning experiments)
 
 # -fmad=false: the feedback arithmetic mirrors the reference's separate float mul/add (parity tier 3)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -221,7 +221,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     c->last_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     c->tmp_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     const size_t bp = (size_t)H * c->WW;
-    c->bits = dalloc<uint32_t>(c->stream, bp * 15);
+    c->bits = dalloc<uint32_t>(c->stream, bp * 19);
     uint32_t** planes[] = {&c->roi_bits, &c->raw, &c->lastraw, &c->lastrawblink, &c->blinks, &c->tmpA, &c->pre, &c->reach, &c->comb,
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
@@ -305,12 +305,12 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.img = img; A.ipitch = pitch; A.bg_color = c->bg_color; A.bg_desc = c->bg_desc; A.maps = c->maps; A.fin = c->fin;
     A.last_color = c->last_color; A.last_desc = sub ? c->last_desc : c->tmp_desc; A.roi_bits = c->roi_bits; A.raw_bits = c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
-    A.intent_bits = c->intent_bits; A.intents = c->intents; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
+    A.intent_bits = c->intent_bits; A.intents = c->intents; A.bitplane = (size_t)H * c->WW; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane; B.img = img; B.ipitch = pitch;
-    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_desc = A.last_desc; B.intent_bits = c->intent_bits; B.intents = c->intents;
+    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_desc = A.last_desc; B.intent_bits = c->intent_bits; B.intents = c->intents; B.bitplane = (size_t)H * c->WW;
     PostArgs P{};
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv;

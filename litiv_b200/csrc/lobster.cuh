@@ -34,6 +34,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
     bool is_fg = false, has_intent = false;
     uint32_t scanned = 0, writes = 0;
+    int intent_row = 0;
 
     uint32_t cur[CH];
     Col cur_pack;
@@ -104,7 +105,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                     const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
                     A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                     ((Desc*)A.last_desc)[pix] = intra_pack; // scratch plane read by phase B (not the reference's m_oLastDescFrame)
-                    has_intent = true;
+                    has_intent = true; intent_row = ny - y + 2;
                 }
             }
         }
@@ -112,8 +113,16 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     if(in_img) ((Col*)A.last_color)[pix] = cur_pack; // whole frame (:580)
 
     const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
-    const uint32_t b_int = __ballot_sync(0xFFFFFFFFu, has_intent);
-    if(threadIdx.x == 0 && y < A.H && (x >> 5) < A.WW) { A.raw_bits[wi] = b_raw; A.intent_bits[wi] = b_int; }
+    uint32_t b_int = 0;
+#pragma unroll
+    for(int d = 0; d < 5; ++d) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, has_intent && intent_row == d);
+        if((int)threadIdx.x == d) b_int = b;
+    }
+    if(y < A.H && (x >> 5) < A.WW) {
+        if(threadIdx.x < 5) A.intent_bits[(size_t)threadIdx.x * A.bitplane + wi] = b_int;
+        if(threadIdx.x == 0) A.raw_bits[wi] = b_raw;
+    }
     if(A.collect_stats) {
         uint32_t sc = scanned, wr = writes + (has_intent ? 1u : 0u);
 #pragma unroll

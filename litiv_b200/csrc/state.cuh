@@ -62,7 +62,7 @@ struct SubArgs {
     const uint32_t* roi_bits;
     uint32_t* raw_bits; uint32_t* unstable_bits; const uint32_t* blinks_bits; const uint32_t* lastfg_bits;
     const uint32_t* ghost_prev; uint32_t* ghost_cur;
-    uint32_t* intent_bits; ushort* intents;
+    uint32_t* intent_bits; ushort* intents; size_t bitplane;   // 5 intent planes (one per row offset) of `bitplane` words
     const uchar* lut;
     FrameCtl* ctl;
     uint64_t seed;

@@ -11,6 +11,9 @@
 namespace lvb {
 
 constexpr int TILE_W = 32, TILE_H = 8, HALO = 2;
+#ifndef PHASEA_MIN_BLOCKS
+#define PHASEA_MIN_BLOCKS 4
+#endif
 constexpr int TILE_ROWS = TILE_H + 2 * HALO;
 // TMA boxes must start on a 16-byte boundary of the image row: the box starts TILE_SHIFT bytes before the halo's first
 // byte ((32k-2)*ch mod 16 is the same for every tile) and is TILE_SHIFT bytes wider.
@@ -19,21 +22,19 @@ __host__ __device__ constexpr int tile_pitch(int ch) { return (tile_shift(ch) + 
 
 /// stage the (TILE_W+4)x(TILE_H+4) input tile into shared memory: one TMA bulk tensor copy (zero-filled
 /// outside the image) or, when the frame pitch is not TMA-compatible, a cooperative byte copy.
+/// begin() issues the copy, wait() blocks until the tile is visible to the whole CTA; independent global loads
+/// issued between the two overlap with the TMA transfer.
 template<int CH>
-__device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUtensorMap* tmap, int use_tma,
-                                           const uchar* img, size_t ipitch, int W, int H, int x0, int y0) {
+__device__ __forceinline__ void stage_tile_begin(uchar* tile, uint64_t* bar, const CUtensorMap* tmap, int use_tma,
+                                                 const uchar* img, size_t ipitch, int W, int H, int x0, int y0) {
     constexpr int PITCH = tile_pitch(CH);
     if(use_tma) {
         if(threadIdx.x == 0 && threadIdx.y == 0) {
             mbar_init(bar, 1);
             mbar_fence_init();
-        }
-        __syncthreads();
-        if(threadIdx.x == 0 && threadIdx.y == 0) {
             mbar_expect_tx(bar, PITCH * TILE_ROWS);
             tma_load_2d(tile, tmap, (x0 - HALO) * CH - tile_shift(CH), y0 - HALO, bar);
         }
-        mbar_wait(bar, 0);
     } else {
         const int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
         const int rowbytes = (TILE_W + 2 * HALO) * CH;
@@ -44,12 +45,21 @@ __device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUt
             if(gy >= 0 && gy < H && gb >= 0 && gb < W * CH) v = img[(size_t)gy * ipitch + gb];
             tile[r * PITCH + tile_shift(CH) + b] = v;
         }
-        __syncthreads();
     }
+}
+__device__ __forceinline__ void stage_tile_wait(uint64_t* bar, int use_tma) {
+    __syncthreads();               // mbarrier init (thread 0) / cooperative copy visible to everyone
+    if(use_tma) mbar_wait(bar, 0); // TMA bytes have landed (async proxy -> visible after the phase flips)
+}
+template<int CH>
+__device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUtensorMap* tmap, int use_tma,
+                                           const uchar* img, size_t ipitch, int W, int H, int x0, int y0) {
+    stage_tile_begin<CH>(tile, bar, tmap, use_tma, img, ipitch, W, H, x0, y0);
+    stage_tile_wait(bar, use_tma);
 }
 
 template<int CH>
-__global__ void __launch_bounds__(TILE_W * TILE_H)
+__global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
 subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -61,10 +71,9 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
     s_lut[tid] = A.lut[tid];
     if(tid < 4) s_cnt[tid] = 0;
-    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
-    __syncthreads();
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const bool in_img = (x < A.W) && (y < A.H);
@@ -77,8 +86,27 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const bool active = in_img && (w_roi & lane_bit);
     const size_t pix = (size_t)y * A.Wp + x;
 
+    // every global load that does not depend on the input tile is issued before waiting for the TMA copy; the first
+    // REQ (=2) samples are always scanned, so they are fetched up front instead of one DRAM round trip each
+    float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
+    float2 fin = make_float2(0, 0);
+    Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
+    Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
+    const Col* bgc = (const Col*)A.bg_color + pix;
+    const Desc* bgd = (const Desc*)A.bg_desc + pix;
+    if(active) {
+        m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1];
+        fin = A.fin[pix];
+        lc = ((const Col*)A.last_color)[pix];
+        ld = ((const Desc*)A.last_desc)[pix];
+        pre_c0 = bgc[0]; pre_d0 = bgd[0];
+        if(A.N > 1) { pre_c1 = bgc[A.plane]; pre_d1 = bgd[A.plane]; }
+    }
+    stage_tile_wait(&s_bar, A.use_tma);
+
     bool is_fg = false, unstable_new = false, ghost_new = false, has_intent = false, nonzero = false;
     uint32_t scanned = 0, writes = 0;
+    int intent_row = 0; // row offset (ty - y + 2) of the queued neighbour write
 
     if(active) {
         const FrameCtl* ctl = A.ctl;
@@ -87,9 +115,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
         const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
 
-        float4 m0 = A.maps[pix * 2], m1 = A.maps[pix * 2 + 1];
         float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
-        const float2 fin = A.fin[pix];
         const bool unstable_old = (w_unst & lane_bit) != 0, blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
 
         // thresholds (SuBSENSE.cpp:222-223 / :355-359)
@@ -110,11 +136,9 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // sample-consensus scan (:229-253 / :367-395): all colour gates first (no side effects), then the descriptor
-        const Col* bgc = (const Col*)A.bg_color + pix;
-        const Desc* bgd = (const Desc*)A.bg_desc + pix;
         uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
         while(good < REQ && s < N) {
-            const Col bc = bgc[(size_t)s * A.plane];
+            const Col bc = s == 0 ? pre_c0 : s == 1 ? pre_c1 : bgc[(size_t)s * A.plane];
             bool ok = true;
             uint32_t cd[CH];
 #pragma unroll
@@ -124,7 +148,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 ok = ok && (cd[c] <= (CH == 1 ? thrC : scC));
             }
             if(ok) {
-                const Desc bd = bgd[(size_t)s * A.plane];
+                const Desc bd = s == 0 ? pre_d0 : s == 1 ? pre_d1 : bgd[(size_t)s * A.plane];
                 uint32_t totDesc = 0, totSum = 0;
 #pragma unroll
                 for(int c = 0; c < CH; ++c) {
@@ -149,8 +173,6 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         scanned = s;
 
         // D_last (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
-        const Col lc = ((const Col*)A.last_color)[pix];
-        const Desc ld = ((const Desc*)A.last_desc)[pix];
         uint32_t lastL1 = 0, lastHd = 0;
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
@@ -205,7 +227,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
                 // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
                 A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
-                has_intent = true;
+                has_intent = true; intent_row = ny - y + 2;
             }
         }
         // T(x) (:302-311 / :451-460)
@@ -244,11 +266,20 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
     const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
     const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
-    const uint32_t b_int = __ballot_sync(0xFFFFFFFFu, has_intent);
     const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
-    if(threadIdx.x == 0 && y < A.H && (x >> 5) < A.WW) {
-        A.raw_bits[wi] = b_raw; A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; A.intent_bits[wi] = b_int;
-        atomicAdd(&s_cnt[0], __popc(b_nz));
+    uint32_t b_int = 0, b_int_any = 0; // lane d (<5) keeps the intent mask of row offset d
+#pragma unroll
+    for(int d = 0; d < 5; ++d) {
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, has_intent && intent_row == d);
+        if((int)threadIdx.x == d) b_int = b;
+        b_int_any |= b;
+    }
+    if(y < A.H && (x >> 5) < A.WW) {
+        if(threadIdx.x < 5) A.intent_bits[(size_t)threadIdx.x * A.bitplane + wi] = b_int; // one plane per row offset (phase B)
+        if(threadIdx.x == 0) {
+            A.raw_bits[wi] = b_raw; A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost;
+            atomicAdd(&s_cnt[0], __popc(b_nz));
+        }
     }
     if(A.collect_stats) {
         uint32_t sc = scanned, wr = writes + (has_intent ? 1u : 0u);
@@ -269,14 +300,15 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
 /// Phase B: apply the queued neighbour writes. One thread per TARGET pixel gathers the intents of the 5x5
 /// sources around it in raster order, so the last writer in raster order wins (oracle MODE_SNAPSHOT rule).
-/// A source at window position (k,dy) targets this pixel iff its stored offset index equals (2-dy)*5 + (4-k).
+/// A source at window position (k,dy) targets this pixel iff its stored offset index equals (2-dy)*5 + (4-k); the
+/// has-intent bits are split in 5 planes by row offset so only sources aiming at THIS row are visited.
 struct PhaseBArgs {
     int W, H, Wp, WW, CH;
     size_t plane;
     const uchar* img; size_t ipitch;
     void* bg_color; void* bg_desc;
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
-    const uint32_t* intent_bits; const ushort* intents;
+    const uint32_t* intent_bits; const ushort* intents; size_t bitplane;
 };
 
 template<int CH>
@@ -289,7 +321,7 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
 #pragma unroll
     for(int dy = -2; dy <= 2; ++dy) {
         const int qy = y + dy; // always inside the image
-        const uint32_t* row = A.intent_bits + (size_t)qy * A.WW;
+        const uint32_t* row = A.intent_bits + (size_t)(2 - dy) * A.bitplane + (size_t)qy * A.WW;
         const uint32_t left = wi > 0 ? row[wi - 1] : 0u, cur = row[wi], right = wi + 1 < A.WW ? row[wi + 1] : 0u;
         // 5-bit window: bit k <-> source x-2+k
         const unsigned long long lo = ((unsigned long long)cur << 32) | left, hi = ((unsigned long long)right << 32) | cur;
