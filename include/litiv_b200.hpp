@@ -1,0 +1,156 @@
+// litiv_b200 — header-only C++ drop-in classes over the C ABI (include/litiv_b200.h).
+//
+// Same class and method names as the reference (modules/video/include/litiv/video/BackgroundSubtractionUtils.hpp:24-47,
+// BackgroundSubtractorSuBSENSE.hpp:49-133, BackgroundSubtractorLOBSTER.hpp:133-153): initialize(img, ROI),
+// apply(img, fgmask, learningRate), getBackgroundImage, getBackgroundDescriptorsImage, refreshModel, setROI, getROICopy,
+// setAutomaticModelReset, getDefaultLearningRate. Failures throw lv::Exception-like std::runtime_error carrying the
+// reference's assertion text (the reference throws lv::Exception : std::runtime_error, utils/cxx.hpp:189-204).
+//
+// With OpenCV available (define LITIV_B200_WITH_OPENCV before including) the classes derive from cv::BackgroundSubtractor
+// and take cv::Mat / cv::InputArray exactly like the reference; without it they take the plain lvb::ImageView below.
+#pragma once
+#include "litiv_b200.h"
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#ifdef LITIV_B200_WITH_OPENCV
+#include <opencv2/core.hpp>
+#include <opencv2/video/background_segm.hpp>
+#endif
+
+namespace lvb {
+
+struct Exception : std::runtime_error { using std::runtime_error::runtime_error; };
+inline void check(int rc) { if(rc != 0) throw Exception(lvb_last_error()); }
+
+/// minimal continuous 8-bit image view {data, rows, cols, channels, step}
+struct ImageView {
+    const uint8_t* data = nullptr; int rows = 0, cols = 0, channels = 0; size_t step = 0;
+    ImageView() {}
+    ImageView(const uint8_t* d, int r, int c, int ch, size_t s = 0) : data(d), rows(r), cols(c), channels(ch), step(s ? s : (size_t)c * ch) {}
+    bool empty() const { return !data || rows <= 0 || cols <= 0; }
+    bool isContinuous() const { return step == (size_t)cols * channels; }
+#ifdef LITIV_B200_WITH_OPENCV
+    ImageView(const cv::Mat& m) : data(m.data), rows(m.rows), cols(m.cols), channels(m.channels()), step(m.step.p[0]) {
+        if(!m.empty() && m.depth() != CV_8U) throw Exception("input image type/size mismatch with initialization type/size");
+    }
+#endif
+};
+
+#ifdef LITIV_B200_WITH_OPENCV
+struct SubtractorBase : public cv::BackgroundSubtractor {
+#else
+struct SubtractorBase {
+#endif
+    virtual ~SubtractorBase() { if(m_h) lvb_destroy(m_h); }
+    SubtractorBase(const SubtractorBase&) = delete;
+    SubtractorBase& operator=(const SubtractorBase&) = delete;
+
+    /// IIBackgroundSubtractor::initialize(img) / initialize(img, ROI)
+    void initialize(const ImageView& img) { initialize(img, ImageView()); }
+    virtual void initialize(const ImageView& img, const ImageView& roi) {
+        if(img.empty()) throw Exception("provided image for initialization must be non-empty, continuous, and of type 8UC1/3/4");
+        if(!roi.empty() && (roi.rows != img.rows || roi.cols != img.cols || roi.channels != 1 || !roi.isContinuous()))
+            throw Exception("provided ROI mat size must be equal to the init frame size, and its type must be 8UC1");
+        check(lvb_initialize(m_h, img.data, img.cols, img.rows, img.channels, img.step, roi.empty() ? nullptr : roi.data));
+        m_rows = img.rows; m_cols = img.cols; m_channels = img.channels;
+    }
+    /// IBackgroundSubtractor::apply(img, fgmask, learningRate); fgmask must hold rows*cols bytes
+    virtual void apply(const ImageView& img, uint8_t* fgmask, double learningRate) {
+        if(img.rows != m_rows || img.cols != m_cols || img.channels != m_channels) throw Exception(m_rows ? "input image type/size mismatch with initialization type/size" : "algo & model must be initialized first");
+        if(!img.isContinuous()) throw Exception("input image data must be continuous");
+        check(lvb_apply(m_h, img.data, fgmask, learningRate));
+    }
+    void apply(const ImageView& img, uint8_t* fgmask) { apply(img, fgmask, getDefaultLearningRate()); }
+    void apply(const ImageView& img, std::vector<uint8_t>& fgmask, double learningRate) { fgmask.resize((size_t)m_rows * m_cols); apply(img, fgmask.data(), learningRate); }
+    /// asynchronous pair (the `apply_cuda` async mode sketched in apps/changedet/src/main.cpp:274-282)
+    void apply_async(const ImageView& img, uint8_t* fgmask, double learningRate) { check(lvb_apply_async(m_h, img.data, fgmask, learningRate)); }
+    void sync() { check(lvb_sync(m_h)); }
+    /// device-resident frame (what a cv::cuda::GpuMat overload binds to)
+    void apply_device(const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask, double learningRate) { check(lvb_apply_device(m_h, d_img, d_step, d_fgmask, learningRate)); }
+
+    virtual void getBackgroundImage(uint8_t* out) const { check(lvb_get_background_image(m_h, out)); }
+    virtual void getBackgroundDescriptorsImage(uint16_t* out) const { check(lvb_get_background_descriptors_image(m_h, out)); }
+    virtual double getDefaultLearningRate() const { return lvb_default_learning_rate(m_algo); }
+    virtual void setAutomaticModelReset(bool b) { check(lvb_set_auto_model_reset(m_h, b ? 1 : 0)); }
+    virtual void setROI(const ImageView& roi) { check(lvb_set_roi(m_h, roi.data)); }
+    virtual std::vector<uint8_t> getROICopy() const { std::vector<uint8_t> r((size_t)m_rows * m_cols); check(lvb_get_roi(m_h, r.data())); return r; }
+    void refreshModel(float fSamplesRefreshFrac, bool bForceFGUpdate = false) { check(lvb_refresh_model(m_h, fSamplesRefreshFrac, bForceFGUpdate ? 1 : 0)); }
+    lvb_handle handle() const { return m_h; }
+
+#ifdef LITIV_B200_WITH_OPENCV
+    // cv::BackgroundSubtractor interface, as in the reference
+    void initialize(const cv::Mat& img, const cv::Mat& roi) { initialize(ImageView(img), roi.empty() ? ImageView() : ImageView(roi)); }
+    void apply(cv::InputArray image, cv::OutputArray fgmask, double learningRate) override {
+        cv::Mat img = image.getMat();
+        fgmask.create(img.size(), CV_8UC1);
+        cv::Mat m = fgmask.getMat();
+        apply(ImageView(img), m.data, learningRate);
+    }
+    void getBackgroundImage(cv::OutputArray out) const override {
+        out.create(m_rows, m_cols, CV_8UC(m_channels));
+        cv::Mat m = out.getMat();
+        getBackgroundImage(m.data);
+    }
+#endif
+protected:
+    SubtractorBase(int algo, const lvb_params& p, int device, uint64_t seed) : m_algo(algo) { check(lvb_create(algo, &p, device, seed, &m_h)); }
+    static lvb_params defaults(int algo) { lvb_params p; check(lvb_default_params(algo, &p)); return p; }
+    lvb_handle m_h = nullptr;
+    int m_algo, m_rows = 0, m_cols = 0, m_channels = 0;
+};
+
+/// BackgroundSubtractorSuBSENSE_<lv::CUDA> (ctor arguments and defaults: BackgroundSubtractorSuBSENSE.hpp:52-57)
+struct BackgroundSubtractorSuBSENSE : SubtractorBase {
+    explicit BackgroundSubtractorSuBSENSE(size_t nDescDistThresholdOffset = 3, size_t nMinColorDistThreshold = 30, size_t nBGSamples = 50,
+                                          size_t nRequiredBGSamples = 2, size_t nSamplesForMovingAvgs = 100, float fRelLBSPThreshold = 0.333f,
+                                          int device = 0, uint64_t seed = 0)
+        : SubtractorBase(LVB_ALGO_SUBSENSE, make(nDescDistThresholdOffset, nMinColorDistThreshold, nBGSamples, nRequiredBGSamples, nSamplesForMovingAvgs, fRelLBSPThreshold), device, seed) {}
+private:
+    static lvb_params make(size_t d, size_t c, size_t n, size_t r, size_t a, float rel) {
+        lvb_params p = defaults(LVB_ALGO_SUBSENSE);
+        p.desc_dist_threshold = (int32_t)d; p.color_dist_threshold = (int32_t)c; p.n_samples = (int32_t)n; p.n_required = (int32_t)r;
+        p.n_samples_for_moving_avgs = (int32_t)a; p.rel_lbsp_threshold = rel;
+        return p;
+    }
+};
+
+/// BackgroundSubtractorLOBSTER_<lv::CUDA> (ctor arguments and defaults: BackgroundSubtractorLOBSTER.hpp:50-55)
+struct BackgroundSubtractorLOBSTER : SubtractorBase {
+    explicit BackgroundSubtractorLOBSTER(size_t nDescDistThreshold = 4, size_t nColorDistThreshold = 30, size_t nBGSamples = 35,
+                                         size_t nRequiredBGSamples = 2, size_t nLBSPThresholdOffset = 0, float fRelLBSPThreshold = 0.333f,
+                                         int device = 0, uint64_t seed = 0)
+        : SubtractorBase(LVB_ALGO_LOBSTER, make(nDescDistThreshold, nColorDistThreshold, nBGSamples, nRequiredBGSamples, nLBSPThresholdOffset, fRelLBSPThreshold), device, seed) {}
+private:
+    static lvb_params make(size_t d, size_t c, size_t n, size_t r, size_t off, float rel) {
+        lvb_params p = defaults(LVB_ALGO_LOBSTER);
+        p.desc_dist_threshold = (int32_t)d; p.color_dist_threshold = (int32_t)c; p.n_samples = (int32_t)n; p.n_required = (int32_t)r;
+        p.lbsp_threshold_offset = (int32_t)off; p.rel_lbsp_threshold = rel;
+        return p;
+    }
+};
+
+/// LBSP dense extractor (features2d LBSP: LBSP(size_t) absolute / LBSP(float, size_t) relative; compute2; setReference)
+struct LBSP {
+    explicit LBSP(size_t nThreshold, int device = 0) : m_abs(true), m_rel(0), m_thr((int)nThreshold), m_dev(device) {}
+    LBSP(float fRelThreshold, size_t nThresholdOffset, int device = 0) : m_abs(false), m_rel(fRelThreshold), m_thr((int)nThresholdOffset), m_dev(device) {
+        if(fRelThreshold < 0) throw Exception("relative LBSP threshold must be non-negative");
+    }
+    static constexpr int PATCH_SIZE = 5, DESC_SIZE = 2, DESC_SIZE_BITS = 16;
+    int borderSize() const { return PATCH_SIZE / 2; }
+    int descriptorSize() const { return DESC_SIZE; }
+    void setReference(const ImageView& ref) { m_ref = ref; }
+    /// out: rows*cols*channels uint16; the 2-px border is left untouched like the reference's oDesc.create()
+    void compute2(const ImageView& img, uint16_t* out) const {
+        if(!m_ref.empty() && (m_ref.rows != img.rows || m_ref.cols != img.cols || m_ref.channels != img.channels))
+            throw Exception("ref image must be empty, or of the same size/type as the input image");
+        check(lvb_lbsp_compute(img.data, m_ref.empty() ? nullptr : m_ref.data, img.cols, img.rows, img.channels, m_abs ? 0 : 1, m_rel, m_thr, out, m_dev));
+    }
+private:
+    bool m_abs; float m_rel; int m_thr, m_dev; ImageView m_ref;
+};
+
+} // namespace lvb

@@ -69,6 +69,17 @@ def test_synth_sequence_is_deterministic():
     assert not np.array_equal(f, SynthSequence(64, 48, 3, seed=8).frame(5))
 
 
+def test_cpp_shim_compiles_and_reports_errors(tmp_path):
+    """include/litiv_b200.hpp (header-only drop-in classes) compiles against the C ABI; without a GPU it must throw"""
+    from litiv_b200 import build
+    exe = tmp_path / "shim"
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp_shim_compile.cpp"),
+                           "-L" + os.path.dirname(build.SO), "-llitiv_b200", "-Wl,-rpath," + os.path.dirname(build.SO), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0
+    assert "no CPU fallback" in out.stdout or "ran on GPU" in out.stdout
+
+
 SHARD_SCRIPT = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
