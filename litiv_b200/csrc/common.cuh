@@ -64,16 +64,65 @@ __device__ __forceinline__ Lookup16 lbsp_lookup_smem(const uchar* tile, int pitc
     return L;
 }
 
-/// desc = sum_n (|val_n - ref| > t) << n   (strict >, unsigned) — LBSP.hpp:193-224
-__device__ __forceinline__ uint32_t lbsp_threshold(const Lookup16& L, uint32_t ref, uint32_t t) {
-    const uint32_t r4 = ref * 0x01010101u, t4 = t * 0x01010101u;
-    uint32_t d = 0;
+/// 5x5 neighbourhood of one pixel as five realigned row windows (bytes dxi*CH + c, dxi = dx+2), fetched with aligned
+/// 32-bit shared loads + funnel shifts instead of 16*CH byte loads; `o` = byte offset of pixel (sx-2) inside a tile row
+template<int CH> struct Window5 { uint32_t a[5][(5 * CH + 3) / 4]; };
+template<int CH>
+__device__ __forceinline__ Window5<CH> lbsp_window_smem(const uchar* tile, int pitch, int sy, int o) {
+    constexpr int NW = (5 * CH + 3) / 4;
+    Window5<CH> Wn;
+    const int sh = (o & 3) * 8;
 #pragma unroll
-    for(int i = 0; i < 4; ++i) {
-        const uint32_t gt = __vsetgtu4(__vabsdiffu4(L.w[i], r4), t4);      // 0/1 per byte
-        d |= (((gt * 0x00204081u) >> 21) & 0xFu) << (4 * i);                // gather the 4 flag bits
+    for(int r = 0; r < 5; ++r) {
+        const uint32_t* rp = (const uint32_t*)(tile + (sy - 2 + r) * pitch + (o & ~3));
+        uint32_t w[NW + 1];
+#pragma unroll
+        for(int i = 0; i <= NW; ++i) w[i] = rp[i];
+#pragma unroll
+        for(int i = 0; i < NW; ++i) Wn.a[r][i] = __funnelshift_r(w[i], w[i + 1], sh);
     }
-    return d;
+    return Wn;
+}
+/// two bytes (row ra, byte ba) and (row rb, byte bb) of the window into the low half of a word (one PRMT)
+template<int CH>
+__device__ __forceinline__ uint32_t win_pick2(const Window5<CH>& Wn, int ra, int ba, int rb, int bb) {
+    return __byte_perm(Wn.a[ra][ba >> 2], Wn.a[rb][bb >> 2], (uint32_t)((ba & 3) | ((4 + (bb & 3)) << 4)));
+}
+/// the 16 LBSP neighbours of channel c in pattern order (LBSP.hpp:292-294); rows r = dy+2, bytes (dx+2)*CH + c
+template<int CH>
+__device__ __forceinline__ Lookup16 lbsp_lookup_window(const Window5<CH>& Wn, int c) {
+#define LVB_B(dx) (((dx) + 2) * CH + c)
+    Lookup16 L;
+    L.w[0] = __byte_perm(win_pick2<CH>(Wn, 2, LVB_B(-2), 2, LVB_B(2)), win_pick2<CH>(Wn, 0, LVB_B(0), 4, LVB_B(0)), 0x5410);   // (-2,0) (2,0) (0,-2) (0,2)
+    L.w[1] = __byte_perm(win_pick2<CH>(Wn, 4, LVB_B(-2), 0, LVB_B(2)), win_pick2<CH>(Wn, 4, LVB_B(2), 0, LVB_B(-2)), 0x5410);  // (-2,2) (2,-2) (2,2) (-2,-2)
+    L.w[2] = __byte_perm(win_pick2<CH>(Wn, 3, LVB_B(0), 2, LVB_B(-1)), win_pick2<CH>(Wn, 1, LVB_B(0), 2, LVB_B(1)), 0x5410);   // (0,1) (-1,0) (0,-1) (1,0)
+    L.w[3] = __byte_perm(win_pick2<CH>(Wn, 1, LVB_B(-1), 3, LVB_B(1)), win_pick2<CH>(Wn, 1, LVB_B(1), 3, LVB_B(-1)), 0x5410);  // (-1,-1) (1,1) (1,-1) (-1,1)
+#undef LVB_B
+    return L;
+}
+template<int CH>
+__device__ __forceinline__ uint32_t win_center(const Window5<CH>& Wn, int c) {
+    const int b = 2 * CH + c;
+    return (Wn.a[2][b >> 2] >> (8 * (b & 3))) & 0xFFu;
+}
+
+/// desc = sum_n (|val_n - ref| > t) << n   (strict >, unsigned) — LBSP.hpp:193-224.
+/// VABSDIFF4 + SWAR compare give one 0/1 flag byte per neighbour; two dp4a chains with weights 1,2,4,..,128 gather
+/// the 16 flags into the descriptor bits.
+__device__ __forceinline__ uint32_t lbsp_threshold(const Lookup16& L, uint32_t ref, uint32_t t) {
+    const uint32_t r4 = __byte_perm(ref, 0, 0x0000), t4 = __byte_perm(t, 0, 0x0000);
+    const uint32_t f0 = __vsetgtu4(__vabsdiffu4(L.w[0], r4), t4), f1 = __vsetgtu4(__vabsdiffu4(L.w[1], r4), t4);
+    const uint32_t f2 = __vsetgtu4(__vabsdiffu4(L.w[2], r4), t4), f3 = __vsetgtu4(__vabsdiffu4(L.w[3], r4), t4);
+    const uint32_t lo = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(f3, 0x80402010u, __dp4a(f2, 0x08040201u, 0u));
+    return lo | (hi << 8);
+}
+
+/// x % n for x < 2^32 with magic = floor(2^32 / n): the estimated quotient is at most one too small
+__device__ __forceinline__ uint32_t fast_mod(uint32_t x, uint32_t n, uint32_t magic) {
+    uint32_t r = x - __umulhi(x, magic) * n;
+    if(n == 1u) return 0u; // floor(2^32/1) does not fit: handled apart
+    return r >= n ? r - n : r;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -308,6 +308,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.intent_bits = c->intent_bits; A.intents = c->intents; A.bitplane = (size_t)H * c->WW; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
+    A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane; B.img = img; B.ipitch = pitch;
     B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_desc = A.last_desc; B.intent_bits = c->intent_bits; B.intents = c->intents; B.bitplane = (size_t)H * c->WW;

@@ -69,6 +69,7 @@ struct SubArgs {
     uint32_t lr_fixed;         // 0: use ceil(T(x)) ; else the ceil'd override (0xFFFFFFFF for +inf)
     int min_color, desc_off;
     int use_tma, collect_stats;
+    uint32_t n_magic;          // floor(2^32 / N) for fast_mod
 };
 
 } // namespace lvb

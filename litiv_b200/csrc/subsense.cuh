@@ -124,21 +124,24 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
         const uint32_t totC = thrC * 3u, totD = thrD * 3u, scC = totC >> 1;
 
-        const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+        const int sy = threadIdx.y + HALO;
         Lookup16 L[CH];
         uint32_t cur[CH], intra[CH];
+        {
+            const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
 #pragma unroll
-        for(int c = 0; c < CH; ++c) {
-            L[c] = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
-            cur[c] = s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
-            intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+            for(int c = 0; c < CH; ++c) {
+                L[c] = lbsp_lookup_window<CH>(Wn, c);
+                cur[c] = win_center<CH>(Wn, c);
+                intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+            }
         }
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // sample-consensus scan (:229-253 / :367-395): all colour gates first (no side effects), then the descriptor
         uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
-        while(good < REQ && s < N) {
-            const Col bc = s == 0 ? pre_c0 : s == 1 ? pre_c1 : bgc[(size_t)s * A.plane];
+        // one sample: colour gate, then (only if it passes) the descriptor test; `load_desc()` fetches the descriptor lazily
+        auto test_sample = [&](const Col bc, auto&& load_desc) {
             bool ok = true;
             uint32_t cd[CH];
 #pragma unroll
@@ -148,7 +151,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 ok = ok && (cd[c] <= (CH == 1 ? thrC : scC));
             }
             if(ok) {
-                const Desc bd = s == 0 ? pre_d0 : s == 1 ? pre_d1 : bgd[(size_t)s * A.plane];
+                const Desc bd = load_desc();
                 uint32_t totDesc = 0, totSum = 0;
 #pragma unroll
                 for(int c = 0; c < CH; ++c) {
@@ -168,7 +171,17 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 if(CH != 1) ok = ok && !(totDesc > totD || totSum > totC);
                 if(ok) { minDesc = min(minDesc, totDesc); minSum = min(minSum, totSum); ++good; }
             }
-            ++s;
+        };
+        if(good < REQ && s < N) { test_sample(pre_c0, [&]() { return pre_d0; }); ++s; }   // samples 0 and 1 were prefetched
+        if(good < REQ && s < N) { test_sample(pre_c1, [&]() { return pre_d1; }); ++s; }
+        if(good < REQ && s < N) {
+            Col next_c = bgc[(size_t)s * A.plane];
+            while(good < REQ && s < N) {
+                const Col bc = next_c;
+                if(s + 1 < N) next_c = bgc[(size_t)(s + 1) * A.plane]; // software pipeline: next colour in flight during this test
+                test_sample(bc, [&]() { return bgd[(size_t)s * A.plane]; });
+                ++s;
+            }
         }
         scanned = s;
 
@@ -181,7 +194,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             lastHd += __popc(desc_get(ld, c) ^ intra[c]);
         }
         if(CH != 1) lastL1 &= 0xFFu;
-        const float normLast = __fdiv_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 2.0f);
+        const float normLast = __fmul_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 0.5f); // x/2 == x*0.5 exactly
         Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
 
         Col cur_pack; Desc intra_pack;
@@ -191,7 +204,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t pixid = (uint32_t)(y * A.W + x);
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
         const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
-        const float baseMin = __fdiv_rn(__fadd_rn(__fdiv_rn((float)minSum, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange)), 2.0f);
+        const float baseMin = __fmul_rn(__fadd_rn(__fdiv_rn((float)minSum, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange)), 0.5f);
         if(good < REQ) { // foreground (:256-269 / :398-413)
             is_fg = true;
             const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
@@ -200,7 +213,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT);
             rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
             if(cooldown && (rnd.x % 2u) == 0) {
-                const uint32_t slot = rnd.y % N;
+                const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
                 ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
                 ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
                 ++writes;
@@ -212,7 +225,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             rawST = __fmul_rn(rawST, oneST);
             const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
             if((rnd.x % LR) == 0) {
-                const uint32_t slot = rnd.y % N;
+                const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
                 ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
                 ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
                 ++writes;
@@ -224,7 +237,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             const bool nb_ghost = (A.ghost_prev[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u;
             const uint32_t n_rand = rnd.w;
             if((n_rand % (cur3 ? LR : (LR / 2u + 1u))) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
-                const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
+                const uint32_t slot = fast_mod(philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x, N, A.n_magic);
                 // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
                 A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                 has_intent = true; intent_row = ny - y + 2;
