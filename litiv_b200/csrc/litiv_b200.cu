@@ -133,6 +133,9 @@ struct lvb_context {
 namespace {
 
 dim3 tile_grid(const lvb_context* c) { return dim3(c->Wp / 32, (c->H + 7) / 8); }
+// grid / block of the kernels that stage an input tile (TILE_W x TILE_H pixels + halo) through TMA
+dim3 stage_grid(const lvb_context* c) { return dim3(c->Wp / TILE_W, (c->H + TILE_H - 1) / TILE_H); }
+const dim3 stage_block(TILE_W, TILE_H);
 dim3 word_grid(const lvb_context* c) { return dim3((c->WW + 255) / 256, c->H); }
 
 void get_ctl(lvb_context* c, FrameCtl& f) {
@@ -280,8 +283,8 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     InitArgs I{};
     I.W = W; I.H = H; I.Wp = c->Wp; I.WW = c->WW; I.img = c->d_img; I.ipitch = c->ipitch; I.last_color = c->last_color; I.last_desc = c->last_desc;
     I.roi_bits = c->roi_bits; I.lut = c->lut; I.use_tma = c->use_tma;
-    if(C == 1) init_frame_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(I, c->tmap_img);
-    else init_frame_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(I, c->tmap_img);
+    if(C == 1) init_frame_kernel<1><<<stage_grid(c), stage_block, 0, c->stream>>>(I, c->tmap_img);
+    else init_frame_kernel<3><<<stage_grid(c), stage_block, 0, c->stream>>>(I, c->tmap_img);
     LAUNCHED();
     c->initialized = true;
     launch_refresh(c);
@@ -321,7 +324,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
     if(sub) {
-        if(C == 1) subsense_phaseA<1><<<tg, tb, 0, st>>>(A, tmap); else subsense_phaseA<3><<<tg, tb, 0, st>>>(A, tmap);
+        if(C == 1) subsense_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
@@ -354,7 +357,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         subsense_tail_kernel<<<1, 256, 0, st>>>(T); LAUNCHED();
         launch_refresh(c);
     } else { // LOBSTER
-        if(C == 1) lobster_phaseA<1><<<tg, tb, 0, st>>>(A, tmap); else lobster_phaseA<3><<<tg, tb, 0, st>>>(A, tmap);
+        if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
@@ -888,7 +891,7 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
         LbspArgs A{};
         A.W = W; A.H = H; A.img = d_img; A.ipitch = pitch; A.ref = d_ref; A.rpitch = pitch; A.out = d_out; A.use_rel = use_rel; A.rel = rel; A.thr = thr;
         A.use_tma = make_image_tmap(&tmap, d_img, W, H, C, pitch) ? 1 : 0;
-        const dim3 g((W + 31) / 32, (H + 7) / 8), b(32, 8);
+        const dim3 g((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H), b(TILE_W, TILE_H);
         if(C == 1) lbsp_dense_kernel<1><<<g, b>>>(A, tmap); else lbsp_dense_kernel<3><<<g, b>>>(A, tmap);
         LAUNCHED();
         d2h((cudaStream_t)0, out, d_out, nout * 2);

@@ -19,7 +19,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    s_lut[tid] = A.lut[tid];
+    for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
     if(tid < 4) s_cnt[tid] = 0;
     stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
     __syncthreads();

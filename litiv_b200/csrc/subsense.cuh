@@ -10,7 +10,10 @@
 
 namespace lvb {
 
-constexpr int TILE_W = 32, TILE_H = 8, HALO = 2;
+#ifndef LVB_TILE_H
+#define LVB_TILE_H 8
+#endif
+constexpr int TILE_W = 32, TILE_H = LVB_TILE_H, HALO = 2; // tile of the TMA-staged kernels (one warp per tile row)
 #ifndef PHASEA_MIN_BLOCKS
 #define PHASEA_MIN_BLOCKS 4
 #endif
@@ -58,13 +61,137 @@ __device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUt
     stage_tile_wait(bar, use_tma);
 }
 
+// ---- sample-consensus scan (SuBSENSE.cpp:229-253 / :367-395) ----
+/// one sample against one pixel: colour gate, then the descriptor test. Returns whether the sample matches and
+/// its total descriptor / colour+descriptor distances.
+template<int CH>
+__device__ __forceinline__ bool subsense_test_sample(const Lookup16 (&L)[CH], const uint32_t (&cur)[CH], const uint32_t (&intra)[CH],
+                                                     const typename Pack<CH>::Col bc, const typename Pack<CH>::Desc bd,
+                                                     uint32_t thrC, uint32_t thrD, const uchar* s_lut, uint32_t& totDesc, uint32_t& totSum) {
+    const uint32_t totC = thrC * 3u, totD = thrD * 3u, scC = totC >> 1;
+    bool ok = true;
+    uint32_t cd[CH];
+#pragma unroll
+    for(int c = 0; c < CH; ++c) {
+        const uint32_t b = col_get(bc, c);
+        cd[c] = cur[c] > b ? cur[c] - b : b - cur[c];
+        ok = ok && (cd[c] <= (CH == 1 ? thrC : scC));
+    }
+    totDesc = 0; totSum = 0;
+    if(ok) {
+#pragma unroll
+        for(int c = 0; c < CH; ++c) {
+            const uint32_t b = col_get(bc, c), d = desc_get(bd, c);
+            const uint32_t inter = lbsp_threshold(L[c], b, s_lut[b]);
+            const uint32_t dd = (__popc(intra[c] ^ d) + __popc(inter ^ d)) >> 1;
+            if(CH == 1) {
+                const uint32_t sum = min((dd >> 2) * 15u + cd[c], 255u);
+                ok = ok && (dd <= thrD) && (sum <= thrC);
+                totDesc = dd; totSum = sum;
+            } else {
+                const uint32_t sum = min((dd >> 1) * 15u + cd[c], 255u);
+                ok = ok && (sum <= scC);
+                totDesc += dd; totSum += sum;
+            }
+        }
+        if(CH != 1) ok = ok && !(totDesc > totD || totSum > totC);
+    }
+    return ok;
+}
+
+/// per-pixel scan context parked in shared memory by the pixels that are still undecided after the first two samples
+/// (words): 4*CH neighbour words | packed colour | intra descriptors (CH==3: 2 words) | thrC | thrD | pixel offset
+template<int CH> struct ScanCtx {
+    static constexpr int CUR = 4 * CH, INTRA = CUR + 1, THRC = INTRA + (CH == 3 ? 2 : 1), THRD = THRC + 1, PIX = THRD + 1;
+    static constexpr int WORDS = (PIX + 1 + 3) / 4 * 4;
+};
+
+/// Tail of the scan, executed by the whole warp. Only ~15 % of the pixels need a third sample and ~0.2 % (foreground) need all
+/// N, so a per-lane loop runs at 1-5 active lanes for up to N-2 dependent DRAM round trips. Instead the k undecided pixels
+/// of the warp share its 32 lanes: each round tests 32/k' samples (k' = k rounded up to a power of two) of every undecided
+/// pixel at once, then ballots + a segmented min-reduction reproduce the sequential "stop at the REQ-th match" rule exactly.
+template<int CH>
+__device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* wctx, uchar* worder, const uchar* s_lut, bool undecided,
+                                                   uint32_t N, uint32_t REQ, uint32_t& good, uint32_t& s, uint32_t& minDesc, uint32_t& minSum) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    typedef ScanCtx<CH> X;
+    const uint32_t FULL = 0xFFFFFFFFu, lane = threadIdx.x;
+    uint32_t m = __ballot_sync(FULL, undecided);
+    while(m) {
+        const uint32_t k = __popc(m);
+        const uint32_t lg = k <= 1u ? 0u : 32u - (uint32_t)__clz(k - 1u); // log2(k')
+        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        if(undecided) worder[rank] = (uchar)lane;
+        __syncwarp();
+        const uint32_t slot = lane & ((1u << lg) - 1u), off = lane >> lg;
+        const bool has = slot < k;
+        const uint32_t src = has ? worder[slot] : 0u;
+        const uint32_t st = __shfl_sync(FULL, s | (good << 16), src);
+        const uint32_t s_src = st & 0xFFFFu, good_src = st >> 16;
+        const uint32_t smp = s_src + off;
+        const bool valid = has && smp < N;
+        bool ok = false;
+        uint32_t td = 0xFFFFFFFFu, ts = 0xFFFFFFFFu;
+        if(valid) {
+            const uint32_t* ctx = wctx + src * X::WORDS;
+            const size_t at = (size_t)smp * A.plane + ctx[X::PIX];
+            const Col bc = ((const Col*)A.bg_color)[at];
+            const Desc bd = ((const Desc*)A.bg_desc)[at];
+            Lookup16 L[CH];
+            uint32_t cur[CH], intra[CH];
+#pragma unroll
+            for(int c = 0; c < CH; ++c) {
+                const uint4 v = *(const uint4*)(ctx + 4 * c);
+                L[c].w[0] = v.x; L[c].w[1] = v.y; L[c].w[2] = v.z; L[c].w[3] = v.w;
+                cur[c] = (ctx[X::CUR] >> (8 * c)) & 0xFFu;
+            }
+            if constexpr (CH == 1) intra[0] = ctx[X::INTRA];
+            else { intra[0] = ctx[X::INTRA] & 0xFFFFu; intra[1] = ctx[X::INTRA] >> 16; intra[2] = ctx[X::INTRA + 1]; }
+            uint32_t d_, s_;
+            ok = subsense_test_sample<CH>(L, cur, intra, bc, bd, ctx[X::THRC], ctx[X::THRD], s_lut, d_, s_);
+            if(ok) { td = d_; ts = s_; }
+        }
+        const uint32_t okmask = __ballot_sync(FULL, ok);
+        const uint32_t gpat = lg == 0u ? 0xFFFFFFFFu : lg == 1u ? 0x55555555u : lg == 2u ? 0x11111111u : lg == 3u ? 0x01010101u : lg == 4u ? 0x00010001u : 1u;
+        const uint32_t gok = okmask & (gpat << slot);   // matches of my pixel, ordered by sample
+        const uint32_t need = REQ - good_src;           // >= 1 for every undecided pixel
+        uint32_t t = gok;
+        for(uint32_t i = 1; i < need && t; ++i) t &= t - 1u; // drop the need-1 first matches
+        const bool has_exit = t != 0u;
+        const uint32_t e = has_exit ? (uint32_t)__ffs(t) - 1u : 31u; // lane of the match that ends the scan
+        const uint32_t ngood = has_exit ? need : (uint32_t)__popc(gok);
+        const uint32_t left = N - min(s_src, N);
+        const uint32_t nscan = has_exit ? (e >> lg) + 1u : min(32u >> lg, left);
+        if(!(ok && lane <= e)) { td = 0xFFFFFFFFu; ts = 0xFFFFFFFFu; } // matches past the exit were never scanned
+#pragma unroll
+        for(uint32_t o = 1; o < 32u; o <<= 1) {
+            if(o >= (1u << lg)) { // warp-uniform
+                td = min(td, __shfl_xor_sync(FULL, td, o)); ts = min(ts, __shfl_xor_sync(FULL, ts, o));
+            }
+        }
+        // the pixel of rank r was served by the lanes of slot r; lane r holds its reduced result
+        const uint32_t pk = __shfl_sync(FULL, ngood | (nscan << 16), rank);
+        const uint32_t rd = __shfl_sync(FULL, td, rank), rs = __shfl_sync(FULL, ts, rank);
+        if(undecided) {
+            good += pk & 0xFFFFu; s += pk >> 16;
+            minDesc = min(minDesc, rd); minSum = min(minSum, rs);
+            undecided = good < REQ && s < N;
+        }
+        m = __ballot_sync(FULL, undecided);
+    }
+}
+
 template<int CH>
 __global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
 subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef ScanCtx<CH> X;
     constexpr int PITCH = tile_pitch(CH);
     __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(16) uint32_t s_ctx[TILE_H][32 * X::WORDS];
+    __shared__ uchar s_order[TILE_H][32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uchar s_lut[256];
     __shared__ uint32_t s_cnt[4];
@@ -72,7 +199,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
-    s_lut[tid] = A.lut[tid];
+    for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
     if(tid < 4) s_cnt[tid] = 0;
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -105,28 +232,24 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     stage_tile_wait(&s_bar, A.use_tma);
 
     bool is_fg = false, unstable_new = false, ghost_new = false, has_intent = false, nonzero = false;
-    uint32_t scanned = 0, writes = 0;
+    uint32_t writes = 0;
     int intent_row = 0; // row offset (ty - y + 2) of the queued neighbour write
+    const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
+    const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
+    uint32_t cur[CH], intra[CH];
+    uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
+    Col cur_pack = Col(); Desc intra_pack = Desc();
 
     if(active) {
-        const FrameCtl* ctl = A.ctl;
-        const float aLT = ctl->aLT, aST = ctl->aST, t_lower = ctl->t_lower, t_upper = ctl->t_upper;
-        const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, use3x3 = ctl->use3x3;
-        const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
-        const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
-
-        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
-        const bool unstable_old = (w_unst & lane_bit) != 0, blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
-
+        const float R = m0.y;
+        const bool unstable_old = (w_unst & lane_bit) != 0;
         // thresholds (SuBSENSE.cpp:222-223 / :355-359)
         uint32_t thrC = (uint32_t)(__fsub_rn(__fmul_rn(R, (float)A.min_color), (float)(unstable_old ? 0 : A.min_color / 5)));
         if(CH == 1) thrC >>= 1;
         const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
-        const uint32_t totC = thrC * 3u, totD = thrD * 3u, scC = totC >> 1;
 
         const int sy = threadIdx.y + HALO;
         Lookup16 L[CH];
-        uint32_t cur[CH], intra[CH];
         {
             const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
 #pragma unroll
@@ -136,54 +259,32 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
             }
         }
-        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
+        if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
+        else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
 
-        // sample-consensus scan (:229-253 / :367-395): all colour gates first (no side effects), then the descriptor
-        uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
-        // one sample: colour gate, then (only if it passes) the descriptor test; `load_desc()` fetches the descriptor lazily
-        auto test_sample = [&](const Col bc, auto&& load_desc) {
-            bool ok = true;
-            uint32_t cd[CH];
+        // samples 0 and 1 were prefetched
+        uint32_t d_, s_;
+        if(good < REQ && s < N) { if(subsense_test_sample<CH>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+        if(good < REQ && s < N) { if(subsense_test_sample<CH>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+        if(good < REQ && s < N) { // still undecided: park the scan context for the warp-cooperative tail
+            uint32_t* ctx = &s_ctx[threadIdx.y][threadIdx.x * X::WORDS];
 #pragma unroll
-            for(int c = 0; c < CH; ++c) {
-                const uint32_t b = col_get(bc, c);
-                cd[c] = cur[c] > b ? cur[c] - b : b - cur[c];
-                ok = ok && (cd[c] <= (CH == 1 ? thrC : scC));
-            }
-            if(ok) {
-                const Desc bd = load_desc();
-                uint32_t totDesc = 0, totSum = 0;
-#pragma unroll
-                for(int c = 0; c < CH; ++c) {
-                    const uint32_t b = col_get(bc, c), d = desc_get(bd, c);
-                    const uint32_t inter = lbsp_threshold(L[c], b, s_lut[b]);
-                    const uint32_t dd = (__popc(intra[c] ^ d) + __popc(inter ^ d)) >> 1;
-                    if(CH == 1) {
-                        const uint32_t sum = min((dd >> 2) * 15u + cd[c], 255u);
-                        ok = ok && (dd <= thrD) && (sum <= thrC);
-                        totDesc = dd; totSum = sum;
-                    } else {
-                        const uint32_t sum = min((dd >> 1) * 15u + cd[c], 255u);
-                        ok = ok && (sum <= scC);
-                        totDesc += dd; totSum += sum;
-                    }
-                }
-                if(CH != 1) ok = ok && !(totDesc > totD || totSum > totC);
-                if(ok) { minDesc = min(minDesc, totDesc); minSum = min(minSum, totSum); ++good; }
-            }
-        };
-        if(good < REQ && s < N) { test_sample(pre_c0, [&]() { return pre_d0; }); ++s; }   // samples 0 and 1 were prefetched
-        if(good < REQ && s < N) { test_sample(pre_c1, [&]() { return pre_d1; }); ++s; }
-        if(good < REQ && s < N) {
-            Col next_c = bgc[(size_t)s * A.plane];
-            while(good < REQ && s < N) {
-                const Col bc = next_c;
-                if(s + 1 < N) next_c = bgc[(size_t)(s + 1) * A.plane]; // software pipeline: next colour in flight during this test
-                test_sample(bc, [&]() { return bgd[(size_t)s * A.plane]; });
-                ++s;
-            }
+            for(int c = 0; c < CH; ++c) *(uint4*)(ctx + 4 * c) = make_uint4(L[c].w[0], L[c].w[1], L[c].w[2], L[c].w[3]);
+            if constexpr (CH == 1) { ctx[X::CUR] = cur[0]; ctx[X::INTRA] = intra[0]; }
+            else { ctx[X::CUR] = cur_pack; ctx[X::INTRA] = intra_pack.x; ctx[X::INTRA + 1] = intra_pack.y; }
+            ctx[X::THRC] = thrC; ctx[X::THRD] = thrD; ctx[X::PIX] = (uint32_t)pix;
         }
-        scanned = s;
+    }
+    subsense_scan_tail<CH>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
+    const uint32_t scanned = s;
+
+    if(active) {
+        const FrameCtl* ctl = A.ctl;
+        const float aLT = ctl->aLT, aST = ctl->aST, t_lower = ctl->t_lower, t_upper = ctl->t_upper;
+        const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, use3x3 = ctl->use3x3;
+        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
+        const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
+        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // D_last (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
         uint32_t lastL1 = 0, lastHd = 0;
@@ -196,10 +297,6 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         if(CH != 1) lastL1 &= 0xFFu;
         const float normLast = __fmul_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 0.5f); // x/2 == x*0.5 exactly
         Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
-
-        Col cur_pack; Desc intra_pack;
-        if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
-        else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
 
         const uint32_t pixid = (uint32_t)(y * A.W + x);
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);

@@ -189,6 +189,11 @@ int lvo_state_set(void* hv, const char* name, const void* in, size_t bytes) {
     std::memcpy(b.ptr, in, bytes);
     LVO_CATCH
 }
+int lvo_get_scan_hist(void* hv, uint64_t out[64]) {
+    const Stats& s = ((Handle*)hv)->base().stats;
+    for(int i = 0; i < 64; ++i) out[i] = s.scan_hist[i];
+    return 0;
+}
 /// stats: roi_px, samples_scanned, sample_writes, fg_px, frames (accumulated since initialize)
 int lvo_get_stats(void* hv, uint64_t out[5]) {
     const Stats& s = ((Handle*)hv)->base().stats;

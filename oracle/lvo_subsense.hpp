@@ -31,6 +31,7 @@ struct Params {
 
 struct Stats { // instrumentation for the roofline's algorithmic-bytes figure
     uint64_t roi_px = 0, samples_scanned = 0, sample_writes = 0, fg_px = 0, frames = 0;
+    uint64_t scan_hist[64] = {}; // histogram of the per-pixel scan depth (last bin: >= 63)
 };
 
 struct BgsBase {
@@ -239,7 +240,7 @@ struct SuBSENSE : BgsBase {
                 }
                 ++s;
             }
-            stats.samples_scanned += s;
+            stats.samples_scanned += s; stats.scan_hist[s < 63 ? s : 63] += 1;
             // :254-255 / :396-397 (Q1: the 3ch L1 wraps in uint8)
             const uchar* lc = last_color.data() + p * CH;
             ushort* ld = last_desc.data() + p * CH;

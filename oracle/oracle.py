@@ -148,6 +148,12 @@ class Oracle:
         lib().lvo_get_stats(self._h, out)
         return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
 
+    def scan_hist(self):
+        """histogram of the per-pixel scan depth accumulated since initialize (bin 63: >= 63)"""
+        out = (C.c_uint64 * 64)()
+        lib().lvo_get_scan_hist(self._h, out)
+        return np.array(list(out), dtype=np.uint64)
+
 
 def lbsp_compute(img, ref=None, rel=None, thr=0):
     """LBSP::compute2 (dense). rel=None -> absolute threshold `thr`; else relative `rel` with offset `thr`."""
