@@ -114,6 +114,16 @@ int lvo_refresh_model(void* hv, float frac, int force_fg) {
     else throw std::runtime_error("use lvo_pawcs_refresh_model");
     LVO_CATCH
 }
+int lvo_pawcs_refresh_model(void* hv, uint64_t base_occ, float decr_frac, int force_fg) {
+    LVO_TRY
+    Handle* H = (Handle*)hv;
+#ifdef LVO_WITH_PAWCS
+    if(H->algo == 2) { H->paw.refresh_model((size_t)base_occ, decr_frac, force_fg != 0); return 0; }
+#endif
+    (void)H; (void)base_occ; (void)decr_frac; (void)force_fg;
+    throw std::runtime_error("not a PAWCS instance");
+    LVO_CATCH
+}
 int lvo_get_background_image(void* hv, uint8_t* out) {
     LVO_TRY
     Handle* H = (Handle*)hv;

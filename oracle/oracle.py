@@ -62,10 +62,17 @@ STATE_DTYPES = {
     "finLT": np.float32, "finST": np.float32, "dsLT": np.float32, "dsST": np.float32, "unstable": np.uint8,
     "blinks": np.uint8, "lastraw": np.uint8, "lastrawblink": np.uint8, "dilinv": np.uint8, "rawmask": np.uint8,
     "scalars": np.float64,
+    # PAWCS
+    "illum": np.uint8, "dil": np.uint8, "lw_first": np.uint32, "lw_last": np.uint32, "lw_occ": np.uint32, "lw_color": np.uint8,
+    "lw_desc": np.uint16, "gw_weight": np.float32, "gw_map": np.float32, "gw_bits": np.uint8, "gw_color": np.uint8,
+    "gw_desc": np.uint16, "gdict": np.int32, "glut": np.uint8,
 }
 SUBSENSE_STATE = ["roi", "lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "T", "R", "v", "Dlast", "DminLT",
                   "DminST", "rawLT", "rawST", "finLT", "finST", "dsLT", "dsST", "unstable", "blinks", "lastraw",
                   "lastrawblink", "dilinv", "scalars"]
+PAWCS_STATE = ["roi", "lastfg", "lastcolor", "lastdesc", "lut", "T", "R", "v", "DminLT", "DminST", "rawLT", "rawST", "finLT", "finST",
+               "dsLT", "dsST", "unstable", "illum", "blinks", "lastraw", "lastrawblink", "dil", "dilinv", "lw_first", "lw_last", "lw_occ",
+               "lw_color", "lw_desc", "gw_weight", "gw_map", "gw_bits", "gw_color", "gw_desc", "gdict", "glut", "scalars"]
 LOBSTER_STATE = ["roi", "lastfg", "lastcolor", "lastdesc", "lut", "bg_color", "bg_desc", "scalars"]
 
 
@@ -116,6 +123,9 @@ class Oracle:
 
     def refresh_model(self, frac, force_fg=False):
         _chk(lib().lvo_refresh_model(self._h, C.c_float(frac), int(force_fg)))
+
+    def pawcs_refresh_model(self, base_occ, decr_frac, force_fg=False):
+        _chk(lib().lvo_pawcs_refresh_model(self._h, C.c_uint64(base_occ), C.c_float(decr_frac), int(force_fg)))
 
     def set_auto_model_reset(self, v):
         _chk(lib().lvo_set_auto_model_reset(self._h, int(v)))
