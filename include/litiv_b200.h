@@ -50,10 +50,10 @@ int lvb_default_params(int algo, lvb_params* out);
 int lvb_create(int algo, const lvb_params* params_or_null, int device, uint64_t seed, lvb_handle* out);
 int lvb_destroy(lvb_handle h);
 
-/* IIBackgroundSubtractor::initialize(img, ROI)  (BackgroundSubtractionUtils.hpp:28-30; SuBSENSE.cpp:107-186; LOBSTER.cpp:443-457)
+/* IIBackgroundSubtractor::initialize(img, ROI)  (BackgroundSubtractionUtils.hpp:28-30; SuBSENSE.cpp:107-186; LOBSTER.cpp:443-457; PAWCS.cpp:431-557)
  * img: 8UC1/8UC3 rows of `step` bytes; roi: null (all pixels) or 8UC1 {0,255} of the same size, continuous */
 int lvb_initialize(lvb_handle h, const uint8_t* img, int width, int height, int channels, size_t step, const uint8_t* roi_or_null);
-/* IBackgroundSubtractor::apply(img, fgmask, learningRate) (SuBSENSE.cpp:188-612; LOBSTER.cpp:459-581); img continuous, fgmask W*H bytes */
+/* IBackgroundSubtractor::apply(img, fgmask, learningRate) (SuBSENSE.cpp:188-612; LOBSTER.cpp:459-581; PAWCS.cpp:559-1523); img continuous, fgmask W*H bytes */
 int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
 /* same, enqueued on the instance's stream; lvb_sync() waits and delivers the mask passed to the matching lvb_apply_async */
 int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
@@ -63,11 +63,13 @@ int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* 
 /* device-resident variant: d_img rows of d_step bytes, d_fgmask W*H bytes (or null), asynchronous on the instance's stream */
 int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);
 
-/* getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649; LOBSTER.cpp:583-620) */
+/* getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649; LOBSTER.cpp:583-620; PAWCS.cpp:1525-1594) */
 int lvb_get_background_image(lvb_handle h, uint8_t* out);
 int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out);
 /* refreshModel(fSamplesRefreshFrac, bForceFGUpdate) (SuBSENSE.cpp:80-105; LOBSTER.cpp:410-441) */
 int lvb_refresh_model(lvb_handle h, float frac, int force_fg);
+/* BackgroundSubtractorPAWCS::refreshModel(nBaseOccCount, fOccDecrFrac, bForceFGUpdate) (PAWCS.cpp:107-429) */
+int lvb_pawcs_refresh_model(lvb_handle h, uint32_t base_occ, float decr_frac, int force_fg);
 /* setAutomaticModelReset / getROICopy / setROI (BackgroundSubtractionUtils.cpp:24-52) */
 int lvb_set_auto_model_reset(lvb_handle h, int enabled);
 int lvb_get_roi(lvb_handle h, uint8_t* out);

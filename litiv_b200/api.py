@@ -19,7 +19,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model",
 ]
 
 
@@ -60,6 +60,7 @@ def lib():
         L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_get_background_descriptors_image.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_refresh_model.argtypes = [C.c_void_p, C.c_float, C.c_int]
+        L.lvb_pawcs_refresh_model.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_int]
         L.lvb_set_auto_model_reset.argtypes = [C.c_void_p, C.c_int]
         L.lvb_get_roi.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_set_roi.argtypes = [C.c_void_p, C.c_void_p]
@@ -105,6 +106,10 @@ STATE_DTYPES = {
     "finLT": np.float32, "finST": np.float32, "dsLT": np.float32, "dsST": np.float32, "unstable": np.uint8,
     "blinks": np.uint8, "lastraw": np.uint8, "lastrawblink": np.uint8, "dilinv": np.uint8, "rawmask": np.uint8,
     "ghost": np.uint8, "scalars": np.float64,
+    # PAWCS
+    "illum": np.uint8, "dil": np.uint8, "lw_first": np.uint32, "lw_last": np.uint32, "lw_occ": np.uint32, "lw_color": np.uint8,
+    "lw_desc": np.uint16, "gw_weight": np.float32, "gw_map": np.float32, "gw_bits": np.uint8, "gw_color": np.uint8,
+    "gw_desc": np.uint16, "gdict": np.int32, "glut": np.uint8,
 }
 
 
@@ -265,6 +270,22 @@ class BackgroundSubtractorLOBSTER(_BackgroundSubtractor):
         p.desc_dist_threshold, p.color_dist_threshold, p.n_samples = nDescDistThreshold, nColorDistThreshold, nBGSamples
         p.n_required, p.lbsp_threshold_offset, p.rel_lbsp_threshold = nRequiredBGSamples, nLBSPThresholdOffset, fRelLBSPThreshold
         super().__init__(p, device, seed)
+
+
+class BackgroundSubtractorPAWCS(_BackgroundSubtractor):
+    """BackgroundSubtractorPAWCS_<lv::CUDA> (reference ctor: BackgroundSubtractorPAWCS.hpp:51-55)."""
+    ALGO = ALGO_PAWCS
+
+    def __init__(self, nDescDistThresholdOffset=2, nMinColorDistThreshold=20, nMaxNbWords=50, nSamplesForMovingAvgs=100,
+                 fRelLBSPThreshold=0.333, device=0, seed=0):
+        p = default_params(ALGO_PAWCS)
+        p.desc_dist_threshold, p.color_dist_threshold, p.n_samples = nDescDistThresholdOffset, nMinColorDistThreshold, nMaxNbWords
+        p.n_samples_for_moving_avgs, p.rel_lbsp_threshold = nSamplesForMovingAvgs, fRelLBSPThreshold
+        super().__init__(p, device, seed)
+
+    def refreshModel(self, nBaseOccCount, fOccDecrFrac, bForceFGUpdate=False):
+        """BackgroundSubtractorPAWCS::refreshModel(nBaseOccCount, fOccDecrFrac, bForceFGUpdate) (PAWCS.cpp:107-429)"""
+        _chk(lib().lvb_pawcs_refresh_model(self._h, int(nBaseOccCount), float(fOccDecrFrac), int(bool(bForceFGUpdate))))
 
 
 MASK_DILATE, MASK_ERODE, MASK_MEDIAN, MASK_HOLES = 0, 1, 2, 3

@@ -3,6 +3,7 @@
 #include "../../include/litiv_b200.h"
 #include "lobster.cuh"
 #include "postproc.cuh"
+#include "pawcs.cuh"
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -114,15 +115,26 @@ struct lvb_context {
     bool pending = false;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
     bool direct_mask = false;
+    // PAWCS
+    int NW = 0, NG = 0, gW = 0, gH = 0;
+    uint32_t paw_frame = 1;   // host mirror of FrameCtl::frame_idx (decides which frames run maintenance / the 500-frame check)
+    uint32_t *lw_first = nullptr, *lw_last = nullptr, *lw_occ = nullptr; void *lw_color = nullptr, *lw_desc = nullptr;
+    uint8_t* glut = nullptr; float *gmap = nullptr, *gmap_tmp = nullptr; GDict* gd = nullptr;
+    uint32_t *roi255 = nullptr, *illum = nullptr, *did = nullptr, *dil = nullptr, *gop_bits = nullptr;
+    uint4* paw_intents = nullptr; float* gop_w = nullptr; uint8_t* gop_g = nullptr; uint8_t* ds_roi = nullptr; uint8_t* bgimg = nullptr;
+    size_t ds_roi_count = 0;
 
     size_t col_bytes() const { return C == 1 ? 1 : 4; }
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
 
     void free_all() {
-        void* ptrs[] = {uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST};
+        void* ptrs[] = {uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+                        lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
         uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
+        paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
         h_img = h_mask = nullptr;
@@ -168,6 +180,122 @@ __global__ void refresh_start_kernel(FrameCtl* ctl, uint64_t seed, uint32_t N) {
 }
 
 namespace {
+
+
+// ---- PAWCS host side ----
+PawArgs paw_args(lvb_context* c, const uint8_t* img, size_t pitch, int use_tma, double lr);
+uint32_t lr_to_fixed(double lr);
+
+void paw_launch_refresh(lvb_context* c, const PawArgs& A, uint32_t frame_off) {
+    const dim3 tg = tile_grid(c), tb(32, 8);
+    if(c->C == 1) pawcs_refresh_local<1><<<tg, tb, 0, c->stream>>>(A, frame_off); else pawcs_refresh_local<3><<<tg, tb, 0, c->stream>>>(A, frame_off);
+    LAUNCHED();
+    if(c->C == 1) pawcs_refresh_global<1><<<1, 1024, 0, c->stream>>>(A, frame_off); else pawcs_refresh_global<3><<<1, 1024, 0, c->stream>>>(A, frame_off);
+    LAUNCHED();
+    pawcs_glut_bubble<<<tg, tb, 0, c->stream>>>(A, 1); LAUNCHED();
+    pawcs_refresh_done<<<1, 1, 0, c->stream>>>(A); LAUNCHED();
+}
+
+/// PAWCS part of initialize (PAWCS.cpp:431-557); the common part (ROI, LUT, last colour / descriptor frames) is already done
+void paw_initialize(lvb_context* c, FrameCtl& f, size_t orig) {
+    const int W = c->W, H = c->H, C = c->C;
+    REQUIRE(W % 8 == 0 && H % 8 == 0, "PAWCS: frame sizes that are not multiples of 8 are not supported yet");
+    REQUIRE(c->P.n_samples / 2 > 0, "max local/global word counts must be positive");
+    const size_t npx = (size_t)W * H, bp = (size_t)H * c->WW;
+    c->dsW = W / 8; c->dsH = H / 8; c->gW = W / 2; c->gH = H / 2;
+    std::vector<uint8_t> dsr((size_t)c->dsW * c->dsH);
+    for(int y = 0; y < c->dsH; ++y) for(int x = 0; x < c->dsW; ++x) { // cv::resize(ROI, INTER_AREA, 1/8) (:446)
+        int sum = 0;
+        for(int dy = 0; dy < 8; ++dy) for(int dx = 0; dx < 8; ++dx) sum += c->roi_host[(size_t)(y * 8 + dy) * W + x * 8 + dx];
+        const long q = std::lrint((double)((float)sum * (1.0f / 64)));
+        dsr[(size_t)y * c->dsW + x] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
+    }
+    const int maxG = c->P.n_samples / 2, qvga = 320 * 240, defk = c->P.median_blur_kernel_size;
+    c->NW = c->P.n_samples;
+    if(orig >= npx / 2 && (int)npx >= qvga) {
+        const float sc = (float)npx / qvga;
+        const int rawk = std::min((int)std::floor(0.5f + sc) + defk, defk + 4);
+        c->median_k = (rawk % 2) ? rawk : rawk - 1;
+        c->NG = maxG;
+        for(auto& v : dsr) v |= 127;
+    } else {
+        const float sc = (float)orig / qvga;
+        const int rawk = std::min((int)std::floor(0.5f + defk * sc * 2) + (defk - 4), defk);
+        c->median_k = (rawk % 2) ? rawk : rawk - 1;
+        c->NG = (int)std::min((size_t)std::pow((double)((float)maxG * sc), 2.0) + 1, (size_t)maxG);
+    }
+    if(c->median_k < 1) c->median_k = 1;
+    if(C == 1) { c->NW = std::max(c->NW / 2, 1); c->NG = std::max(c->NG / 2, 1); }
+    REQUIRE(c->NG <= PAW_MAXG, "too many global words");
+    c->ds_roi_count = 0; for(uint8_t v : dsr) c->ds_roi_count += v != 0;
+    REQUIRE(c->ds_roi_count > 0, "downsampled ROI is empty");
+    f.median_k = c->median_k; f.auto_reset = 1;
+    const int NW = c->NW, NG = c->NG;
+    cudaStream_t st = c->stream;
+    c->lw_first = dalloc<uint32_t>(st, (size_t)NW * c->plane, false);
+    c->lw_last = dalloc<uint32_t>(st, (size_t)NW * c->plane);
+    c->lw_occ = dalloc<uint32_t>(st, (size_t)NW * c->plane);
+    c->lw_color = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->col_bytes());
+    c->lw_desc = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->desc_bytes());
+    { std::vector<uint32_t> ones((size_t)NW * c->plane, 1u); h2d(st, c->lw_first, ones.data(), ones.size() * 4); } // (first=1,last=0): word not created yet
+    c->gmap = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
+    c->gmap_tmp = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
+    c->gd = dalloc<GDict>(st, 1);
+    { std::vector<uint8_t> l((size_t)NG * c->plane); for(int i = 0; i < NG; ++i) std::fill(l.begin() + (size_t)i * c->plane, l.begin() + (size_t)(i + 1) * c->plane, (uint8_t)i);
+      c->glut = dalloc<uint8_t>(st, l.size(), false); h2d(st, c->glut, l.data(), l.size()); }
+    c->paw_intents = dalloc<uint4>(st, c->plane, false);
+    c->gop_w = dalloc<float>(st, c->plane, false);
+    c->gop_g = dalloc<uint8_t>(st, c->plane, false);
+    c->ds_roi = dalloc<uint8_t>(st, dsr.size(), false); h2d(st, c->ds_roi, dsr.data(), dsr.size());
+    c->bgimg = dalloc<uint8_t>(st, npx * C);
+    c->maps = dalloc<float4>(st, c->plane * 2);
+    c->fin = dalloc<float2>(st, c->plane);
+    c->dsLT = dalloc<float>(st, (size_t)c->dsW * c->dsH * C);
+    c->dsST = dalloc<float>(st, (size_t)c->dsW * c->dsH * C);
+    { std::vector<float4> m(c->plane * 2);
+      for(size_t i = 0; i < c->plane; ++i) { m[i * 2] = make_float4(1.0f, 2.0f, 10.0f, 0.f); m[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); } // T, R, v (:473-477)
+      h2d(st, c->maps, m.data(), m.size() * sizeof(float4)); }
+    { std::vector<uint32_t> rb(bp, 0);
+      for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) if(c->roi_host[(size_t)y * W + x] == 255) rb[(size_t)y * c->WW + (x >> 5)] |= 1u << (x & 31);
+      h2d(st, c->roi255, rb.data(), bp * 4); }
+    GDict g{};
+    for(int i = 0; i < PAW_MAXG; ++i) g.dict[i] = -1;
+    g.weight_offset = PAW_WEIGHT_OFFSET; g.boot = 1; g.rep_winner = 0xFFFFFFFFu; g.g_rep = -1;
+    g.ds_roi_count = (uint32_t)c->ds_roi_count; g.nST = ((uint32_t)c->P.n_samples_for_moving_avgs / 2u) / 4u;
+    g.refresh_req = PAW_REQ_REFRESH; g.refresh_base_occ = 1; g.refresh_decr = 0.0f; g.refresh_force = 0; // refreshModel(1,0) (:555)
+    h2d(st, c->gd, &g, sizeof(g));
+    c->paw_frame = 1;
+}
+
+PawArgs paw_args(lvb_context* c, const uint8_t* img, size_t pitch, int use_tma, double lr) {
+    PawArgs A{};
+    A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.WW = c->WW; A.NW = c->NW; A.NG = c->NG; A.gW = c->gW; A.gH = c->gH; A.plane = c->plane;
+    A.img = img; A.ipitch = pitch;
+    A.lw_first = c->lw_first; A.lw_last = c->lw_last; A.lw_occ = c->lw_occ; A.lw_color = c->lw_color; A.lw_desc = c->lw_desc;
+    A.glut = c->glut; A.gmap = c->gmap; A.gmap_tmp = c->gmap_tmp; A.gd = c->gd;
+    A.maps = c->maps; A.fin = c->fin; A.last_color = c->last_color; A.last_desc = c->last_desc;
+    A.roi_bits = c->roi_bits; A.roi255_bits = c->roi255; A.raw_bits = c->raw; A.unstable_bits = c->unstable; A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg;
+    A.illum_bits = c->illum; A.did_bits = c->did; A.dil_bits = c->dil; A.dilinv_bits = c->dilinv;
+    A.intent_bits = c->intent_bits; A.intents = c->paw_intents; A.bitplane = (size_t)c->H * c->WW;
+    A.gop_bits = c->gop_bits; A.gop_w = c->gop_w; A.gop_g = c->gop_g;
+    A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed; A.lr_fixed = lr_to_fixed(lr);
+    A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold; A.use_tma = use_tma; A.collect_stats = c->collect_stats;
+    A.rel = c->P.rel_lbsp_threshold; A.lbsp_off = c->P.lbsp_threshold_offset; A.avg_samples = c->P.n_samples_for_moving_avgs;
+    A.dsW = c->dsW; A.dsH = c->dsH; A.ds_roi = c->ds_roi; A.dsLT = c->dsLT; A.dsST = c->dsST; A.bgimg = c->bgimg;
+    return A;
+}
+
+/// host-requested BackgroundSubtractorPAWCS::refreshModel(nBaseOccCount, fOccDecrFrac, bForceFGUpdate)
+void paw_request_refresh(lvb_context* c, uint32_t base_occ, float decr, bool force) {
+    REQUIRE(c->initialized, "algo must be initialized first");
+    REQUIRE(decr >= 0.0f && decr <= 1.0f, "model occurrence decrementation must be given as a non-null fraction");
+    GDict g;
+    CK(cudaMemcpyAsync(&g, c->gd, sizeof(g), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    g.refresh_req = PAW_REQ_REFRESH; g.refresh_base_occ = base_occ; g.refresh_decr = decr; g.refresh_force = force ? 1 : 0; g.set_T_one = 0;
+    CK(cudaMemcpyAsync(c->gd, &g, sizeof(g), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+    paw_launch_refresh(c, paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0), 1);
+    CK(cudaStreamSynchronize(c->stream));
+}
 
 /// host-requested refreshModel(frac, force): fill the request in FrameCtl, then the same kernels the frame tail uses
 void request_refresh(lvb_context* c, float frac, bool force) {
@@ -218,16 +346,19 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     CK(cudaMallocHost((void**)&c->h_mask, (size_t)W * H));
     c->use_tma = make_image_tmap(&c->tmap_img, c->d_img, W, H, C, c->ipitch) ? 1 : 0;
     c->ext_ptr = nullptr;
-    c->bg_color = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->col_bytes());
-    c->bg_desc = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->desc_bytes());
+    if(c->algo != LVB_ALGO_PAWCS) {
+        c->bg_color = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->col_bytes());
+        c->bg_desc = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->desc_bytes());
+    }
     c->last_color = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
     c->last_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     c->tmp_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     const size_t bp = (size_t)H * c->WW;
-    c->bits = dalloc<uint32_t>(c->stream, bp * 19);
+    c->bits = dalloc<uint32_t>(c->stream, bp * 24);
     uint32_t** planes[] = {&c->roi_bits, &c->raw, &c->lastraw, &c->lastrawblink, &c->blinks, &c->tmpA, &c->pre, &c->reach, &c->comb,
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
+    c->roi255 = c->bits + bp * 19; c->illum = c->bits + bp * 20; c->did = c->bits + bp * 21; c->dil = c->bits + bp * 22; c->gop_bits = c->bits + bp * 23; // PAWCS (intent planes: 14..18)
     c->ghost_idx = 0;
     c->uf_rs = (W + 1) / 2 + 1;
     c->uf_parent = dalloc<uint32_t>(c->stream, (size_t)H * c->uf_rs + 1);
@@ -272,6 +403,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         for(size_t i = 0; i < c->plane; ++i) { m[i * 2] = make_float4(f.t_lower, 1.0f, 10.0f, 0.f); m[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
         h2d(c->stream, c->maps, m.data(), m.size() * sizeof(float4));
     }
+    if(c->algo == LVB_ALGO_PAWCS) paw_initialize(c, f, orig);
     c->median_k = f.median_k;
     REQUIRE(c->median_k >= 1 && c->median_k <= 31 && (c->median_k & 1), "median blur kernel size must be odd and <= 31");
     // first refresh request: all N slots from slot 0 (SuBSENSE.cpp:184 refreshModel(1.0f); LOBSTER.cpp:455 refreshModel(1.0f,true))
@@ -287,7 +419,8 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     else init_frame_kernel<3><<<stage_grid(c), stage_block, 0, c->stream>>>(I, c->tmap_img);
     LAUNCHED();
     c->initialized = true;
-    launch_refresh(c);
+    if(c->algo == LVB_ALGO_PAWCS) paw_launch_refresh(c, paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0), 1);
+    else launch_refresh(c);
     CK(cudaStreamSynchronize(c->stream));
     c->stat_frames = 0;
 }
@@ -298,8 +431,69 @@ uint32_t lr_to_fixed(double lr) {
     return 0;
 }
 
+/// one PAWCS frame on the instance's stream (kernel order: see pawcs.cuh)
+void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUtensorMap& tmap, int use_tma, uint8_t* d_mask_out, double lr) {
+    const int W = c->W, H = c->H, C = c->C;
+    cudaStream_t st = c->stream;
+    const PawArgs A = paw_args(c, img, pitch, use_tma, lr);
+    const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c), mg(c->Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
+    const uint32_t frame = c->paw_frame;
+    const bool boot = frame <= PAW_BOOTSTRAP;
+    const uint32_t grate = boot ? 8u : 16u;
+    const int recalc = (frame % (grate << 5)) == 0, update = (frame % grate) == 0, check_model = (frame % PAW_BOOTSTRAP) == 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
+    if(C == 1) pawcs_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
+    LAUNCHED();
+    if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
+    pawcs_illum_kernel<<<wg, 256, 0, st>>>(A); LAUNCHED();
+    if(C == 1) pawcs_gword_replace<1><<<1, 1024, 0, st>>>(A); else pawcs_gword_replace<3><<<1, 1024, 0, st>>>(A);
+    LAUNCHED();
+    pawcs_gword_apply<<<dim3((c->gW + 31) / 32, (c->gH + 7) / 8), 256, 0, st>>>(A); LAUNCHED();
+    pawcs_gword_finish<<<1, 128, 0, st>>>(A); LAUNCHED();
+    if(C == 1) pawcs_phaseB<1><<<tg, tb, 0, st>>>(A); else pawcs_phaseB<3><<<tg, tb, 0, st>>>(A);
+    LAUNCHED();
+    if(recalc || update) { pawcs_gword_maintain<<<c->NG, 1024, 0, st>>>(A, recalc, update); LAUNCHED(); }
+    pawcs_gdict_bubble<<<1, 1, 0, st>>>(A); LAUNCHED();
+    if(update) { pawcs_glut_bubble<<<tg, tb, 0, st>>>(A, 0); LAUNCHED(); }
+    PostArgs P{};
+    P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
+    P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv; P.dil = c->dil;
+    P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+    pp_blink_dilate<<<wg, 256, 0, st>>>(P); LAUNCHED();
+    pp_erode_seed<<<wg, 256, 0, st>>>(P); LAUNCHED();
+    {
+        HoleArgs Hh{};
+        Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw; Hh.comb = c->comb;
+        Hh.parent = c->uf_parent; Hh.rankbase = c->uf_rankbase;
+        const int rb = (H + 7) / 8;
+        pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+        pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+        pp_holes_combine<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+    }
+    pp_median<<<mg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
+    pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED();
+    pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED();
+    const int nds = c->dsW * c->dsH;
+    if(C == 1) pawcs_motion_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(A); else pawcs_motion_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(A);
+    LAUNCHED();
+    if(check_model) {
+        if(C == 1) pawcs_background_kernel<1><<<tg, tb, 0, st>>>(A, c->bgimg, nullptr, 0); else pawcs_background_kernel<3><<<tg, tb, 0, st>>>(A, c->bgimg, nullptr, 0);
+        LAUNCHED();
+        if(C == 1) pawcs_model_dist_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(A); else pawcs_model_dist_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(A);
+        LAUNCHED();
+    }
+    pawcs_tail1_kernel<<<1, 256, 0, st>>>(A, check_model); LAUNCHED();
+    if(check_model) paw_launch_refresh(c, A, 0);      // moving-camera mode switch (:1486-1499)
+    pawcs_tail2_kernel<<<1, 1, 0, st>>>(A); LAUNCHED();
+    paw_launch_refresh(c, A, 1);                      // frame-level model reset (:1503-1510)
+    c->paw_frame = frame + 1;
+    if(c->collect_stats) ++c->stat_frames;
+}
+
 /// enqueue one frame on the instance's stream; the frame is already in device memory at (img,pitch)
 void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUtensorMap& tmap, int use_tma, uint8_t* d_mask_out, double lr) {
+    if(c->algo == LVB_ALGO_PAWCS) { paw_enqueue_frame(c, img, pitch, tmap, use_tma, d_mask_out, lr); return; }
     const int W = c->W, H = c->H, C = c->C;
     cudaStream_t st = c->stream;
     const bool sub = c->algo == LVB_ALGO_SUBSENSE;
@@ -406,6 +600,7 @@ uint32_t* bits_by_name(lvb_context* c, const std::string& n) {
     if(n == "lastfg") return c->lastfg; if(n == "unstable") return c->unstable; if(n == "blinks") return c->blinks;
     if(n == "lastraw") return c->lastraw; if(n == "lastrawblink") return c->lastrawblink; if(n == "dilinv") return c->dilinv;
     if(n == "rawmask") return c->raw; if(n == "ghost") return c->ghost[c->ghost_idx];
+    if(c->algo == LVB_ALGO_PAWCS) { if(n == "illum") return c->illum; if(n == "dil") return c->dil; }
     return nullptr;
 }
 int map_index(const std::string& n) {
@@ -415,8 +610,18 @@ int map_index(const std::string& n) {
 }
 size_t state_bytes(lvb_context* c, const std::string& n) {
     const size_t npx = (size_t)c->W * c->H;
-    const bool sub = c->algo == LVB_ALGO_SUBSENSE;
+    const bool paw = c->algo == LVB_ALGO_PAWCS;
+    const bool sub = c->algo == LVB_ALGO_SUBSENSE || paw;
     if(n == "scalars") return 16 * sizeof(double);
+    if(paw) {
+        const size_t nw = (size_t)c->NW, ng = (size_t)c->NG, msz = (size_t)c->gW * c->gH;
+        if(n == "lw_first" || n == "lw_last" || n == "lw_occ") return npx * nw * 4;
+        if(n == "lw_color") return npx * nw * c->C;
+        if(n == "lw_desc") return npx * nw * c->C * 2;
+        if(n == "gw_weight") return ng * 4; if(n == "gw_map") return ng * msz * 4; if(n == "gw_bits") return ng;
+        if(n == "gw_color") return ng * c->C; if(n == "gw_desc") return ng * c->C * 2; if(n == "gdict") return ng * 4; if(n == "glut") return npx * ng;
+        if(n == "bg_color" || n == "bg_desc") throw std::runtime_error("unknown state buffer: " + n);
+    }
     if(n == "roi") return npx;
     if(n == "lut") return 256;
     if(n == "lastcolor") return npx * c->C;
@@ -439,6 +644,69 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
     CK(cudaStreamSynchronize(c->stream));
     const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
     const size_t npx = (size_t)W * H;
+    if(c->algo == LVB_ALGO_PAWCS) {
+        const size_t nw = (size_t)c->NW, ng = (size_t)c->NG, msz = (size_t)c->gW * c->gH;
+        if(n == "scalars") {
+            FrameCtl f; get_ctl(c, f);
+            GDict g; CK(cudaMemcpyAsync(&g, c->gd, sizeof(g), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            double* d = (double*)out; std::memset(d, 0, bytes);
+            d[0] = (double)f.frame_idx - 1; d[1] = f.frames_since_reset; d[2] = f.cooldown; d[3] = f.auto_reset; d[4] = (double)nw; d[5] = (double)ng;
+            d[6] = c->median_k; d[7] = g.weight_offset; d[8] = g.moving_camera; d[9] = g.last_nonflat_ratio; d[10] = (double)c->roi_count; d[11] = (double)c->orig_roi_count; d[12] = f.refresh_epoch;
+            return;
+        }
+        if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
+            std::vector<uint32_t> h(nw * c->plane), fi, la;
+            d2h(c->stream, h.data(), n == "lw_first" ? c->lw_first : n == "lw_last" ? c->lw_last : c->lw_occ, h.size() * 4);
+            if(n == "lw_first") { la.resize(h.size()); d2h(c->stream, la.data(), c->lw_last, la.size() * 4); }
+            uint32_t* o = (uint32_t*)out;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                uint32_t v = h[at];
+                if(n == "lw_first" && v == 1u && la[at] == 0u) v = 0; // "not created" marker (non-ROI pixels)
+                o[((size_t)y * W + x) * nw + i] = v;
+            }
+            return;
+        }
+        if(n == "lw_color") {
+            std::vector<uint8_t> h(nw * c->plane * c->col_bytes());
+            d2h(c->stream, h.data(), c->lw_color, h.size());
+            uint8_t* o = (uint8_t*)out;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                o[(((size_t)y * W + x) * nw + i) * C + k] = C == 1 ? h[at] : h[at * 4 + k];
+            }
+            return;
+        }
+        if(n == "lw_desc") {
+            std::vector<uint16_t> h(nw * c->plane * c->desc_bytes() / 2);
+            d2h(c->stream, h.data(), c->lw_desc, h.size() * 2);
+            uint16_t* o = (uint16_t*)out;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                o[(((size_t)y * W + x) * nw + i) * C + k] = C == 1 ? h[at] : h[at * 4 + k];
+            }
+            return;
+        }
+        if(n == "glut") {
+            std::vector<uint8_t> h(ng * c->plane);
+            d2h(c->stream, h.data(), c->glut, h.size());
+            uint8_t* o = (uint8_t*)out;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < ng; ++i) o[((size_t)y * W + x) * ng + i] = h[i * c->plane + (size_t)y * Wp + x];
+            return;
+        }
+        if(n == "gw_map") { d2h(c->stream, out, c->gmap, ng * msz * 4); return; }
+        if(n == "gw_weight" || n == "gw_bits" || n == "gw_color" || n == "gw_desc" || n == "gdict") {
+            GDict g; CK(cudaMemcpyAsync(&g, c->gd, sizeof(g), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            for(size_t i = 0; i < ng; ++i) {
+                if(n == "gw_weight") ((float*)out)[i] = g.weight[i];
+                else if(n == "gw_bits") ((uint8_t*)out)[i] = (uint8_t)g.bits[i];
+                else if(n == "gdict") ((int32_t*)out)[i] = g.dict[i];
+                else if(n == "gw_color") for(int k = 0; k < C; ++k) ((uint8_t*)out)[i * C + k] = (uint8_t)(g.color[i] >> (8 * k));
+                else for(int k = 0; k < C; ++k) ((uint16_t*)out)[i * C + k] = (uint16_t)(k == 0 ? g.desc[i].x & 0xFFFFu : k == 1 ? g.desc[i].x >> 16 : g.desc[i].y & 0xFFFFu);
+            }
+            return;
+        }
+    }
     if(n == "scalars") {
         FrameCtl f; get_ctl(c, f);
         double* d = (double*)out; std::memset(d, 0, bytes);
@@ -452,7 +720,7 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
         std::vector<uint32_t> h((size_t)H * WW);
         d2h(c->stream, h.data(), b, h.size() * 4);
         uint8_t* o = (uint8_t*)out;
-        const bool as01 = (n == "unstable");
+        const bool as01 = (n == "unstable" || n == "illum");
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) { const bool v = (h[(size_t)y * WW + (x >> 5)] >> (x & 31)) & 1u; o[(size_t)y * W + x] = v ? (as01 ? 1 : 255) : 0; }
         return;
     }
@@ -508,6 +776,73 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
     CK(cudaStreamSynchronize(c->stream));
     const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
     const size_t npx = (size_t)W * H;
+    if(c->algo == LVB_ALGO_PAWCS) {
+        const size_t nw = (size_t)c->NW, ng = (size_t)c->NG, msz = (size_t)c->gW * c->gH;
+        if(n == "scalars") {
+            const double* d = (const double*)in;
+            FrameCtl f; get_ctl(c, f);
+            GDict g; CK(cudaMemcpyAsync(&g, c->gd, sizeof(g), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            f.frame_idx = (uint32_t)d[0] + 1; f.frames_since_reset = (uint32_t)d[1]; f.cooldown = (uint32_t)d[2]; f.auto_reset = d[3] != 0; f.refresh_epoch = (uint32_t)d[12];
+            g.weight_offset = (uint32_t)d[7]; g.moving_camera = d[8] != 0; g.last_nonflat_ratio = (float)d[9];
+            const bool boot = f.frame_idx <= PAW_BOOTSTRAP;
+            const uint32_t avg = (uint32_t)c->P.n_samples_for_moving_avgs, nLT = boot ? avg / 2u : avg, nST = nLT / 4u;
+            g.boot = boot; g.nST = nST;
+            f.aLT = 1.0f / (float)std::min(f.frame_idx, nLT); f.aST = 1.0f / (float)std::min(f.frame_idx, nST);
+            put_ctl(c, f);
+            CK(cudaMemcpyAsync(c->gd, &g, sizeof(g), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            c->paw_frame = f.frame_idx;
+            return;
+        }
+        if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
+            uint32_t* dst = n == "lw_first" ? c->lw_first : n == "lw_last" ? c->lw_last : c->lw_occ;
+            std::vector<uint32_t> h(nw * c->plane);
+            d2h(c->stream, h.data(), dst, h.size() * 4);
+            const uint32_t* sI = (const uint32_t*)in;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) h[i * c->plane + (size_t)y * Wp + x] = sI[((size_t)y * W + x) * nw + i];
+            h2d(c->stream, dst, h.data(), h.size() * 4);
+            return;
+        }
+        if(n == "lw_color") {
+            std::vector<uint8_t> h(nw * c->plane * c->col_bytes(), 0);
+            const uint8_t* sI = (const uint8_t*)in;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                if(C == 1) h[at] = sI[((size_t)y * W + x) * nw + i]; else h[at * 4 + k] = sI[(((size_t)y * W + x) * nw + i) * C + k];
+            }
+            h2d(c->stream, c->lw_color, h.data(), h.size());
+            return;
+        }
+        if(n == "lw_desc") {
+            std::vector<uint16_t> h(nw * c->plane * c->desc_bytes() / 2, 0);
+            const uint16_t* sI = (const uint16_t*)in;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                if(C == 1) h[at] = sI[((size_t)y * W + x) * nw + i]; else h[at * 4 + k] = sI[(((size_t)y * W + x) * nw + i) * C + k];
+            }
+            h2d(c->stream, c->lw_desc, h.data(), h.size() * 2);
+            return;
+        }
+        if(n == "glut") {
+            std::vector<uint8_t> h(ng * c->plane, 0);
+            const uint8_t* sI = (const uint8_t*)in;
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < ng; ++i) h[i * c->plane + (size_t)y * Wp + x] = sI[((size_t)y * W + x) * ng + i];
+            h2d(c->stream, c->glut, h.data(), h.size());
+            return;
+        }
+        if(n == "gw_map") { h2d(c->stream, c->gmap, in, ng * msz * 4); return; }
+        if(n == "gw_weight" || n == "gw_bits" || n == "gw_color" || n == "gw_desc" || n == "gdict") {
+            GDict g; CK(cudaMemcpyAsync(&g, c->gd, sizeof(g), cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            for(size_t i = 0; i < ng; ++i) {
+                if(n == "gw_weight") g.weight[i] = ((const float*)in)[i];
+                else if(n == "gw_bits") g.bits[i] = ((const uint8_t*)in)[i];
+                else if(n == "gdict") g.dict[i] = ((const int32_t*)in)[i];
+                else if(n == "gw_color") { uint32_t v = 0; for(int k = 0; k < C; ++k) v |= (uint32_t)((const uint8_t*)in)[i * C + k] << (8 * k); g.color[i] = v; }
+                else { const uint16_t* dd = (const uint16_t*)in + i * C; g.desc[i] = C == 1 ? make_uint2(dd[0], 0) : make_uint2((uint32_t)dd[0] | ((uint32_t)dd[1] << 16), dd[2]); }
+            }
+            CK(cudaMemcpyAsync(c->gd, &g, sizeof(g), cudaMemcpyHostToDevice, c->stream)); CK(cudaStreamSynchronize(c->stream));
+            return;
+        }
+    }
     if(n == "scalars") {
         const double* d = (const double*)in;
         FrameCtl f; get_ctl(c, f);
@@ -594,7 +929,11 @@ void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
     const size_t n = (size_t)c->W * c->H * c->C;
     uint8_t* dc = nullptr; uint16_t* dd = nullptr;
     if(out_color) dc = dalloc<uint8_t>(c->stream, n, false); else dd = dalloc<uint16_t>(c->stream, n, false);
-    if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
+    if(c->algo == LVB_ALGO_PAWCS) {
+        const PawArgs A = paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0);
+        if(c->C == 1) pawcs_background_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1); else pawcs_background_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1);
+    }
+    else if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -636,7 +975,7 @@ double lvb_default_learning_rate(int algo) { return algo == LVB_ALGO_LOBSTER ? 1
 int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lvb_handle* out) {
     LVB_TRY
     REQUIRE(out != nullptr, "null output handle");
-    REQUIRE(algo == LVB_ALGO_LOBSTER || algo == LVB_ALGO_SUBSENSE, algo == LVB_ALGO_PAWCS ? "PAWCS is not available in this build" : "unknown algorithm id");
+    REQUIRE(algo == LVB_ALGO_LOBSTER || algo == LVB_ALGO_SUBSENSE || algo == LVB_ALGO_PAWCS, "unknown algorithm id");
     lvb_params p;
     if(params) p = *params; else lvb_default_params(algo, &p);
     REQUIRE(p.n_samples > 0 && p.n_required <= p.n_samples, "algo cannot require more sample matches than sample count in model");
@@ -729,8 +1068,17 @@ int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out) {
 int lvb_refresh_model(lvb_handle h, float frac, int force_fg) {
     LVB_TRY
     REQUIRE(h != nullptr, "null handle");
+    REQUIRE(h->algo != LVB_ALGO_PAWCS, "PAWCS: use lvb_pawcs_refresh_model(base_occ, decr_frac, force_fg)");
     CK(cudaSetDevice(h->device));
     request_refresh(h, frac, force_fg != 0);
+    LVB_CATCH
+}
+int lvb_pawcs_refresh_model(lvb_handle h, uint32_t base_occ, float decr_frac, int force_fg) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    REQUIRE(h->algo == LVB_ALGO_PAWCS, "not a PAWCS instance");
+    CK(cudaSetDevice(h->device));
+    paw_request_refresh(h, base_occ, decr_frac, force_fg != 0);
     LVB_CATCH
 }
 int lvb_set_auto_model_reset(lvb_handle h, int enabled) {

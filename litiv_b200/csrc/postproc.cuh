@@ -12,7 +12,7 @@ struct PostArgs {
     int W, H, WW, Wp;
     uint32_t* raw; uint32_t* lastraw; uint32_t* lastrawblink; uint32_t* blinks;
     uint32_t* tmpA; uint32_t* pre; uint32_t* reach; uint32_t* comb;
-    uint32_t* lastfg; uint32_t* dilinv;
+    uint32_t* lastfg; uint32_t* dilinv; uint32_t* dil; // dil: optional copy of the dilated mask (PAWCS refreshModel reads it)
     uchar* out_mask; size_t out_pitch;
     float2* fin;
     FrameCtl* ctl;
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(256) pp_dilate_blink(const PostArgs A) {
     const uint32_t ninv = ~dil & valid_mask(wi, A.WW, A.W);
     A.blinks[i] = A.blinks[i] & A.dilinv[i] & ninv;
     A.dilinv[i] = ninv;
+    if(A.dil) A.dil[i] = dil;
 }
 
 /// final-segmentation EMAs (SuBSENSE.cpp:553-554): cv::addWeighted accumulates in double and rounds once
