@@ -8,7 +8,7 @@
 //       -> phase B (queued neighbour-dictionary updates, gathered per TARGET pixel in raster order of the source)
 //       -> global maintenance (every 8/16 frames) -> bit-packed post-processing (postproc.cuh)
 //       -> motion analysis + frame tail (LUT adaptation, reset / moving-camera logic on the device) -> conditional refresh.
-// The deterministic parallel semantics are the ones of oracle/lvo_pawcs.hpp MODE_SNAPSHOT.
+// The deterministic parallel semantics ("snapshot" semantics) are specified in DESIGN.md section 2.
 //
 // HBM layout (per stream; Wp = W rounded up to 32): local words are five sample-major SoA planes [NW][H][Wp]
 // (first u32, last u32, occurrences u32, colour u32 B,G,R,0, descriptors uint2): every frame every pixel re-weights all
@@ -123,7 +123,7 @@ __device__ __forceinline__ int paw_find_gword(const PawArgs& A, size_t pix, uint
 }
 
 template<int CH>
-__global__ void __launch_bounds__(TILE_W * TILE_H, 2)
+__global__ void __launch_bounds__(TILE_W * TILE_H, 3)
 pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -205,43 +205,57 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
         // local dictionary: scan while the weight sum is below its threshold (:1002-1053), bubble pass over all words (:1044-1065)
         float sum = 0.0f, last_w = FLT_MAX;
         uint32_t minColor = colorRange, minDesc = descRange;
-        bool scanning = true;
-        uint32_t nf = f0, nl = l0, no = o0;
-        for(int i = 0; i < A.NW; ++i) {
+        int i = 0;
+        uint32_t wf = f0, wl = l0, wo = o0;
+        for(; i < A.NW && sum < wthr; ++i) { // scan: one word per DRAM round trip (colour, descriptor and counters together)
             const size_t at = (size_t)i * A.plane + pix;
-            const uint32_t wf = nf, wl = nl, wo = no;
-            if(i + 1 < A.NW) { nf = A.lw_first[at + A.plane]; nl = A.lw_last[at + A.plane]; no = A.lw_occ[at + A.plane]; } // next word in flight
+            const Col bc = ((const Col*)A.lw_color)[at];
+            const Desc bd = ((const Desc*)A.lw_desc)[at];
+            if(i > 0) { wf = A.lw_first[at]; wl = A.lw_last[at]; wo = A.lw_occ[at]; }
             const float w = paw_weight(wf, wl, wo, frame, woff);
-            if(scanning && sum < wthr) {
-                ++scanned;
-                const Col bc = ((const Col*)A.lw_color)[at];
-                const Desc bd = ((const Desc*)A.lw_desc)[at];
-                uint32_t l1, cd;
-                const uint32_t mix = paw_color_dist<CH>(cur32, col_as_u32(bc), l1, cd);
-                const uint32_t ihd = paw_hdist(intra_pack, bd);
-                uint32_t ehd = 0;
+            ++scanned;
+            uint32_t l1, cd;
+            const uint32_t mix = paw_color_dist<CH>(cur32, col_as_u32(bc), l1, cd);
+            const uint32_t ihd = paw_hdist(intra_pack, bd);
+            uint32_t ehd = 0;
 #pragma unroll
-                for(int c = 0; c < CH; ++c) {
-                    const uint32_t b = col_get(bc, c);
-                    ehd += __popc(lbsp_threshold(L[c], b, s_lut[b]) ^ desc_get(bd, c));
+            for(int c = 0; c < CH; ++c) {
+                const uint32_t b = col_get(bc, c);
+                ehd += __popc(lbsp_threshold(L[c], b, s_lut[b]) ^ desc_get(bd, c));
+            }
+            const uint32_t dd = (ihd + ehd) >> 1;
+            if((!unst || flat || border) && mix <= thrC && l1 >= thrC / 2u && ihd <= thrD / 2u) { // illumination update (:1014-1030)
+                const uint32_t mod = illum_cur ? (rate / 2u + 1u) : rate;
+                if((philox_draw(A.seed, frame, pixid, 4u + (uint32_t)i, DOM_PAWCS_A) % mod) == 0u) {
+                    ((Col*)A.lw_color)[at] = cur_pack; ((Desc*)A.lw_desc)[at] = intra_pack;
+                    did = true; illum_cur = 2u;
                 }
-                const uint32_t dd = (ihd + ehd) >> 1;
-                if((!unst || flat || border) && mix <= thrC && l1 >= thrC / 2u && ihd <= thrD / 2u) { // illumination update (:1014-1030)
-                    const uint32_t mod = illum_cur ? (rate / 2u + 1u) : rate;
-                    if((philox_draw(A.seed, frame, pixid, 4u + (uint32_t)i, DOM_PAWCS_A) % mod) == 0u) {
-                        ((Col*)A.lw_color)[at] = cur_pack; ((Desc*)A.lw_desc)[at] = intra_pack;
-                        did = true; illum_cur = 2u;
-                    }
+            }
+            if(dd <= thrD && mix <= thrC) {
+                sum = __fadd_rn(sum, w);
+                A.lw_last[at] = frame;
+                if((!lastfg || moving) && w < 1.0f) A.lw_occ[at] = wo + occ_incr;
+                minColor = min(minColor, mix); minDesc = min(minDesc, dd);
+            }
+            if(w > last_w) paw_swap<CH>(A, pix, i); else last_w = w;
+        }
+        // the bubble pass continues over the rest of the dictionary (:1054-1065): only the counters are needed, CHUNK words
+        // in flight at once (a swap exchanges positions i and i-1 in memory; words already in registers are at positions > i)
+        constexpr int CHUNK = 8;
+        for(; i < A.NW; i += CHUNK) {
+            uint32_t cf[CHUNK], cl[CHUNK], co[CHUNK];
+#pragma unroll
+            for(int k = 0; k < CHUNK; ++k) {
+                if(i + k < A.NW) { const size_t at = (size_t)(i + k) * A.plane + pix; cf[k] = A.lw_first[at]; cl[k] = A.lw_last[at]; co[k] = A.lw_occ[at]; }
+                else { cf[k] = 0; cl[k] = 0; co[k] = 0; }
+            }
+#pragma unroll
+            for(int k = 0; k < CHUNK; ++k) {
+                if(i + k < A.NW) {
+                    const float w = paw_weight(cf[k], cl[k], co[k], frame, woff);
+                    if(w > last_w) paw_swap<CH>(A, pix, i + k); else last_w = w;
                 }
-                if(dd <= thrD && mix <= thrC) {
-                    sum = __fadd_rn(sum, w);
-                    A.lw_last[at] = frame;
-                    if((!lastfg || moving) && w < 1.0f) A.lw_occ[at] = wo + occ_incr;
-                    minColor = min(minColor, mix); minDesc = min(minDesc, dd);
-                }
-            } else scanning = false;
-            if(w > last_w) { paw_swap<CH>(A, pix, i); if(i + 1 < A.NW) { /* next word untouched by the swap */ } }
-            else last_w = w;
+            }
         }
 
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_PAWCS_A);
@@ -337,7 +351,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     }
 }
 
-/// illumination mask of the next frame: new[p] = did[p+1] ? (roi[p]==255) : did[p]  (oracle MODE_SNAPSHOT rule)
+/// illumination mask of the next frame: new[p] = did[p+1] ? (roi[p]==255) : did[p]  (snapshot semantics)
 __global__ void __launch_bounds__(256) pawcs_illum_kernel(const PawArgs A) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if(wi >= A.WW) return;
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A) {
 
 /// Phase B: queued neighbour-dictionary updates (PAWCS.cpp:1164-1247), gathered per TARGET pixel, raster order of the source
 template<int CH>
-__global__ void __launch_bounds__(256) pawcs_phaseB(const PawArgs A) {
+__global__ void __launch_bounds__(256, 3) pawcs_phaseB(const PawArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;

@@ -340,13 +340,13 @@ struct PAWCS : BgsBase {
                     if((!last_fg[p] || moving_camera) && w < 1.0f) lw_occ[k] += (uint32_t)occ_incr;
                     minColor = std::min(minColor, mix); minDesc = std::min(minDesc, dd);
                 }
-                if(w > last_w) lswap(k, k - 1); else last_w = w;
+                if(w > last_w) { lswap(k, k - 1); ++stats.sample_writes; } else last_w = w;
                 ++i;
             }
             stats.samples_scanned += (uint64_t)i;
             while(i < NW) { // :728-739 / :1054-1065 : the bubble pass continues over the rest of the dictionary
                 const float w = lweight(ld + i, fr);
-                if(w > last_w) lswap(ld + i, ld + i - 1); else last_w = w;
+                if(w > last_w) { lswap(ld + i, ld + i - 1); ++stats.sample_writes; } else last_w = w; // stats: dictionary swaps
                 ++i;
             }
             uchar seg = 0;
