@@ -55,8 +55,11 @@ int lvb_destroy(lvb_handle h);
 int lvb_initialize(lvb_handle h, const uint8_t* img, int width, int height, int channels, size_t step, const uint8_t* roi_or_null);
 /* IBackgroundSubtractor::apply(img, fgmask, learningRate) (SuBSENSE.cpp:188-612; LOBSTER.cpp:459-581; PAWCS.cpp:559-1523); img continuous, fgmask W*H bytes */
 int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
-/* same, enqueued on the instance's stream; lvb_sync() waits and delivers the mask passed to the matching lvb_apply_async */
+/* asynchronous form (the `apply_cuda` async mode of apps/changedet/src/main.cpp:274-282): up to TWO frames may be in flight per instance;
+ * the upload of frame k+1 overlaps the kernels of frame k, masks come back on a third stream. lvb_sync_next() waits for the OLDEST
+ * frame in flight and delivers its mask (into the buffer passed to the matching lvb_apply_async); lvb_sync() collects everything. */
 int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
+int lvb_sync_next(lvb_handle h);
 int lvb_sync(lvb_handle h);
 /* n independent streams, one frame each (the lv::WorkerPool pattern of apps/changedet/src/main.cpp:148-154) */
 int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, double learning_rate);

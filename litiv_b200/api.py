@@ -19,7 +19,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next",
 ]
 
 
@@ -55,6 +55,7 @@ def lib():
         L.lvb_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_apply_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_sync.argtypes = [C.c_void_p]
+        L.lvb_sync_next.argtypes = [C.c_void_p]
         L.lvb_apply_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         L.lvb_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]
         L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
@@ -123,6 +124,7 @@ class _BackgroundSubtractor:
         _chk(lib().lvb_create(self.ALGO, C.byref(params) if params is not None else None, device, seed, C.byref(self._h)))
         self.shape = None
         self._pending_mask = None
+        self._inflight = []
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -163,16 +165,24 @@ class _BackgroundSubtractor:
         _chk(lib().lvb_apply(self._h, img.ctypes.data, mask.ctypes.data, float(lr)))
         return mask
 
-    def apply_async(self, img, learningRate=None):
+    def apply_async(self, img, learningRate=None, out=None):
+        """enqueue one frame (up to two may be in flight); collect the masks in order with sync_next() / sync()"""
         img = self._check_img(img)
         lr = self.getDefaultLearningRate() if learningRate is None else learningRate
-        self._pending_mask = np.empty(self.shape[:2], np.uint8)
-        self._pending_img = img
-        _chk(lib().lvb_apply_async(self._h, img.ctypes.data, self._pending_mask.ctypes.data, float(lr)))
+        mask = np.empty(self.shape[:2], np.uint8) if out is None else out
+        _chk(lib().lvb_apply_async(self._h, img.ctypes.data, mask.ctypes.data, float(lr)))
+        self._inflight.append((mask, img))   # keeps the buffers alive until collected
+
+    def sync_next(self):
+        """wait for the oldest frame in flight and return its mask"""
+        _chk(lib().lvb_sync_next(self._h))
+        return self._inflight.pop(0)[0]
 
     def sync(self):
+        """collect every frame in flight; returns the newest mask"""
         _chk(lib().lvb_sync(self._h))
-        m, self._pending_mask = self._pending_mask, None
+        m = self._inflight[-1][0] if self._inflight else None
+        self._inflight = []
         return m
 
     def apply_device(self, d_img_ptr, d_step, d_mask_ptr=None, learningRate=None):

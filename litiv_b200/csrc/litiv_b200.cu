@@ -113,6 +113,12 @@ struct lvb_context {
     int collect_stats = 0, median_k = 9;
     uint64_t stat_frames = 0;
     bool pending = false;
+    // two-deep host pipeline (lvb_apply_async): slot k%2 = {device frame, device mask, pinned staging}; uploads on s_in, masks back on s_out
+    struct Slot { uint8_t* d_img = nullptr; uint8_t* d_mask = nullptr; uint8_t* h_img = nullptr; uint8_t* h_mask = nullptr; CUtensorMap tmap; int use_tma = 0;
+                  cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr; uint8_t* user_mask = nullptr; bool direct = false, busy = false; };
+    Slot slot[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    uint64_t n_submitted = 0, n_collected = 0;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
     bool direct_mask = false;
     // PAWCS
@@ -138,6 +144,12 @@ struct lvb_context {
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
         h_img = h_mask = nullptr;
+        if(slot[1].d_img) cudaFree(slot[1].d_img);
+        if(slot[1].d_mask) cudaFree(slot[1].d_mask);
+        if(slot[1].h_img) cudaFreeHost(slot[1].h_img);
+        if(slot[1].h_mask) cudaFreeHost(slot[1].h_mask);
+        for(Slot& sl : slot) { sl.d_img = sl.d_mask = sl.h_img = sl.h_mask = nullptr; sl.busy = false; }
+        n_submitted = n_collected = 0;
         initialized = false;
     }
 };
@@ -346,6 +358,18 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     CK(cudaMallocHost((void**)&c->h_mask, (size_t)W * H));
     c->use_tma = make_image_tmap(&c->tmap_img, c->d_img, W, H, C, c->ipitch) ? 1 : 0;
     c->ext_ptr = nullptr;
+    {   // pipeline slots: slot 0 aliases the buffers above, slot 1 gets its own
+        lvb_context::Slot& a = c->slot[0]; lvb_context::Slot& b = c->slot[1];
+        a.d_img = c->d_img; a.d_mask = c->d_mask; a.h_img = c->h_img; a.h_mask = c->h_mask; a.tmap = c->tmap_img; a.use_tma = c->use_tma;
+        b.d_img = dalloc<uint8_t>(c->stream, c->ipitch * H); b.d_mask = dalloc<uint8_t>(c->stream, (size_t)W * H);
+        CK(cudaMallocHost((void**)&b.h_img, (size_t)W * H * C)); CK(cudaMallocHost((void**)&b.h_mask, (size_t)W * H));
+        b.use_tma = make_image_tmap(&b.tmap, b.d_img, W, H, C, c->ipitch) ? 1 : 0;
+        if(!c->s_in) { CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
+        for(lvb_context::Slot& sl : c->slot) if(!sl.h2d_done) {
+            CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+        }
+    }
     if(c->algo != LVB_ALGO_PAWCS) {
         c->bg_color = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->col_bytes());
         c->bg_desc = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->desc_bytes());
@@ -577,19 +601,38 @@ bool is_pinned(const void* p) {
 void apply_async(lvb_context* c, const uint8_t* img, uint8_t* mask, double lr) {
     check_apply(c, img, lr);
     REQUIRE(mask != nullptr, "output mask must be provided");
-    REQUIRE(!c->pending, "a previous lvb_apply_async has not been collected with lvb_sync");
     CK(cudaSetDevice(c->device));
+    lvb_context::Slot& sl = c->slot[c->n_submitted & 1];
+    REQUIRE(!sl.busy, "two frames are already in flight: collect one with lvb_sync_next (or lvb_sync) first");
+    const size_t row = (size_t)c->W * c->C;
     const uint8_t* src = img;
-    if(!is_pinned(img)) { std::memcpy(c->h_img, img, (size_t)c->W * c->H * c->C); src = c->h_img; } // pageable -> pinned staging
-    CK(cudaMemcpy2DAsync(c->d_img, c->ipitch, src, (size_t)c->W * c->C, (size_t)c->W * c->C, c->H, cudaMemcpyHostToDevice, c->stream));
-    enqueue_frame(c, c->d_img, c->ipitch, c->tmap_img, c->use_tma, c->d_mask, lr);
-    c->direct_mask = is_pinned(mask);
-    CK(cudaMemcpyAsync(c->direct_mask ? mask : c->h_mask, c->d_mask, (size_t)c->W * c->H, cudaMemcpyDeviceToHost, c->stream));
-    c->user_mask = mask; c->pending = true;
+    if(!is_pinned(img)) { std::memcpy(sl.h_img, img, row * c->H); src = sl.h_img; } // pageable -> pinned staging
+    // upload on s_in (overlaps the previous frame's kernels), kernels on the instance stream, mask back on s_out
+    CK(cudaMemcpy2DAsync(sl.d_img, c->ipitch, src, row, row, c->H, cudaMemcpyHostToDevice, c->s_in));
+    CK(cudaEventRecord(sl.h2d_done, c->s_in));
+    CK(cudaStreamWaitEvent(c->stream, sl.h2d_done, 0));
+    enqueue_frame(c, sl.d_img, c->ipitch, sl.tmap, sl.use_tma, sl.d_mask, lr);
+    CK(cudaEventRecord(sl.compute_done, c->stream));
+    CK(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
+    sl.direct = is_pinned(mask);
+    CK(cudaMemcpyAsync(sl.direct ? mask : sl.h_mask, sl.d_mask, (size_t)c->W * c->H, cudaMemcpyDeviceToHost, c->s_out));
+    CK(cudaEventRecord(sl.d2h_done, c->s_out));
+    sl.user_mask = mask; sl.busy = true;
+    ++c->n_submitted;
+}
+/// wait for the OLDEST frame in flight and deliver its mask; returns false when nothing is pending
+bool sync_next(lvb_context* c) {
+    if(c->n_collected == c->n_submitted) return false;
+    lvb_context::Slot& sl = c->slot[c->n_collected & 1];
+    CK(cudaEventSynchronize(sl.d2h_done));
+    if(!sl.direct) std::memcpy(sl.user_mask, sl.h_mask, (size_t)c->W * c->H);
+    sl.busy = false;
+    ++c->n_collected;
+    return true;
 }
 void sync(lvb_context* c) {
+    while(sync_next(c)) {}
     CK(cudaStreamSynchronize(c->stream));
-    if(c->pending) { if(!c->direct_mask) std::memcpy(c->user_mask, c->h_mask, (size_t)c->W * c->H); c->pending = false; }
 }
 
 // ---- state export / import in the reference's layout (tests + checkpointing) ----
@@ -1001,6 +1044,9 @@ int lvb_destroy(lvb_handle h) {
     cudaSetDevice(h->device);
     if(h->stream) { cudaStreamSynchronize(h->stream); }
     h->free_all();
+    for(auto& sl : h->slot) { if(sl.h2d_done) cudaEventDestroy(sl.h2d_done); if(sl.compute_done) cudaEventDestroy(sl.compute_done); if(sl.d2h_done) cudaEventDestroy(sl.d2h_done); }
+    if(h->s_in) cudaStreamDestroy(h->s_in);
+    if(h->s_out) cudaStreamDestroy(h->s_out);
     if(h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -1031,6 +1077,13 @@ int lvb_sync(lvb_handle h) {
     REQUIRE(h != nullptr, "null handle");
     CK(cudaSetDevice(h->device));
     sync(h);
+    LVB_CATCH
+}
+int lvb_sync_next(lvb_handle h) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    CK(cudaSetDevice(h->device));
+    REQUIRE(sync_next(h), "no frame in flight");
     LVB_CATCH
 }
 int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* masks, int n, double lr) {

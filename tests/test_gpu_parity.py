@@ -195,6 +195,41 @@ def test_async_batch_and_device_paths(lv, oracle):
     assert np.array_equal(s.sync(), r.apply(f, 0.0))
 
 
+@pytest.mark.parametrize("pinned", [False, True])
+def test_two_deep_pipeline_matches_synchronous_apply(lv, pinned):
+    """lvb_apply_async keeps two frames in flight (upload of k+1 overlaps the kernels of k); masks come back in order and are
+    identical to the synchronous call's"""
+    w, h = 320, 240
+    seq = SynthSequence(w, h, 3, seed=31)
+    a, b = lv.BackgroundSubtractorSuBSENSE(seed=4), lv.BackgroundSubtractorSuBSENSE(seed=4)
+    a.initialize(seq.frame(0)); b.initialize(seq.frame(0))
+    n = 12
+    frames = [seq.frame(t) for t in range(1, n + 1)]
+    want = [b.apply(f, 1.0 if t < 6 else 0.0) for t, f in enumerate(frames)]
+    if pinned:
+        bufs = [lv.pinned_empty((h, w, 3)) for _ in range(2)]
+        outs = [lv.pinned_empty((h, w)) for _ in range(2)]
+    got = []
+    for t, f in enumerate(frames):
+        if pinned:
+            bufs[t % 2][...] = f
+            a.apply_async(bufs[t % 2], 1.0 if t < 6 else 0.0, out=outs[t % 2])
+        else:
+            a.apply_async(f, 1.0 if t < 6 else 0.0)
+        if t >= 1:
+            got.append(a.sync_next().copy())
+    got.append(a.sync_next().copy())
+    assert len(got) == n
+    for t in range(n):
+        assert np.array_equal(got[t], want[t]), f"frame {t}"
+    with pytest.raises(lv.LitivError, match="no frame in flight"):
+        a.sync_next()
+    a.apply_async(frames[0]); a.apply_async(frames[1])
+    with pytest.raises(lv.LitivError, match="already in flight"):
+        a.apply_async(frames[2])
+    a.sync()
+
+
 def test_errors_match_reference_messages(lv):
     s = lv.BackgroundSubtractorSuBSENSE()
     with pytest.raises(lv.LitivError, match="initialized first"):
