@@ -12,6 +12,7 @@
 #include <atomic>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 
 using namespace lvb;
 
@@ -118,9 +119,12 @@ struct lvb_context {
                   cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr; uint8_t* user_mask = nullptr; bool direct = false, busy = false; };
     Slot slot[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // phase B runs beside the mask post-processing
     uint64_t n_submitted = 0, n_collected = 0;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
     bool direct_mask = false;
+    // LVB_TRACE=1 (debugging aid): an event after every kernel of the main stream; lvb_get_profile prints the per-segment averages
+    bool trace_on = getenv("LVB_TRACE") != nullptr; std::vector<std::pair<const char*, cudaEvent_t>> trace;
     // PAWCS
     int NW = 0, NG = 0, gW = 0, gH = 0;
     uint32_t paw_frame = 1;   // host mirror of FrameCtl::frame_idx (decides which frames run maintenance / the 500-frame check)
@@ -177,8 +181,10 @@ void launch_refresh(lvb_context* c) {
     R.bg_color = c->bg_color; R.bg_desc = c->bg_desc; R.last_color = c->last_color; R.last_desc = c->last_desc;
     R.roi_bits = c->roi_bits; R.lastfg_bits = c->lastfg; R.maps = c->algo == LVB_ALGO_SUBSENSE ? c->maps : nullptr;
     R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
-    if(c->C == 1) refresh_model_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(R);
-    else refresh_model_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(R);
+    const dim3 tgd = tile_grid(c);
+    const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, 148 * 8);
+    if(c->C == 1) refresh_model_kernel<1><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
+    else refresh_model_kernel<3><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     LAUNCHED();
     refresh_done_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
     LAUNCHED();
@@ -364,7 +370,9 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         b.d_img = dalloc<uint8_t>(c->stream, c->ipitch * H); b.d_mask = dalloc<uint8_t>(c->stream, (size_t)W * H);
         CK(cudaMallocHost((void**)&b.h_img, (size_t)W * H * C)); CK(cudaMallocHost((void**)&b.h_mask, (size_t)W * H));
         b.use_tma = make_image_tmap(&b.tmap, b.d_img, W, H, C, c->ipitch) ? 1 : 0;
-        if(!c->s_in) { CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
+        if(!c->s_in) { CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+                       { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, lo)); }
+                       CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)); }
         for(lvb_context::Slot& sl : c->slot) if(!sl.h2d_done) {
             CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
@@ -470,13 +478,16 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     if(C == 1) pawcs_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
     LAUNCHED();
     if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
+    // phase B only touches the local dictionaries: auxiliary stream, beside the global-dictionary and mask kernels
+    CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+    if(C == 1) pawcs_phaseB<1><<<tg, tb, 0, c->s_aux>>>(A); else pawcs_phaseB<3><<<tg, tb, 0, c->s_aux>>>(A);
+    LAUNCHED();
+    CK(cudaEventRecord(c->ev_join, c->s_aux));
     pawcs_illum_kernel<<<wg, 256, 0, st>>>(A); LAUNCHED();
     if(C == 1) pawcs_gword_replace<1><<<1, 1024, 0, st>>>(A); else pawcs_gword_replace<3><<<1, 1024, 0, st>>>(A);
     LAUNCHED();
     pawcs_gword_apply<<<dim3((c->gW + 31) / 32, (c->gH + 7) / 8), 256, 0, st>>>(A); LAUNCHED();
     pawcs_gword_finish<<<1, 128, 0, st>>>(A); LAUNCHED();
-    if(C == 1) pawcs_phaseB<1><<<tg, tb, 0, st>>>(A); else pawcs_phaseB<3><<<tg, tb, 0, st>>>(A);
-    LAUNCHED();
     if(recalc || update) { pawcs_gword_maintain<<<c->NG, 1024, 0, st>>>(A, recalc, update); LAUNCHED(); }
     pawcs_gdict_bubble<<<1, 1, 0, st>>>(A); LAUNCHED();
     if(update) { pawcs_glut_bubble<<<tg, tb, 0, st>>>(A, 0); LAUNCHED(); }
@@ -484,8 +495,7 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv; P.dil = c->dil;
     P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
-    pp_blink_dilate<<<wg, 256, 0, st>>>(P); LAUNCHED();
-    pp_erode_seed<<<wg, 256, 0, st>>>(P); LAUNCHED();
+    pp_blink_close<<<wg, 256, 0, st>>>(P); LAUNCHED();
     {
         HoleArgs Hh{};
         Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw; Hh.comb = c->comb;
@@ -501,6 +511,7 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     const int nds = c->dsW * c->dsH;
     if(C == 1) pawcs_motion_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(A); else pawcs_motion_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(A);
     LAUNCHED();
+    CK(cudaStreamWaitEvent(st, c->ev_join, 0)); // everything below may read or rewrite the local dictionaries
     if(check_model) {
         if(C == 1) pawcs_background_kernel<1><<<tg, tb, 0, st>>>(A, c->bgimg, nullptr, 0); else pawcs_background_kernel<3><<<tg, tb, 0, st>>>(A, c->bgimg, nullptr, 0);
         LAUNCHED();
@@ -539,49 +550,61 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
     const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c), mg(c->Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
 
+    auto mark = [&](const char* n) { if(c->trace_on && c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); c->trace.push_back({n, e}); } };
+    mark("frame_start");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
     if(sub) {
         if(C == 1) subsense_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
-        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
+        mark("phaseA");
+        // phase B only touches the sample model: it runs on the auxiliary stream beside the mask post-processing chain
+        CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->s_aux>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->s_aux>>>(B);
         LAUNCHED();
+        {   // frame-level motion analysis only needs the input frame: also off the critical path
+            DownsampleArgs D{};
+            D.W = W; D.H = H; D.CH = C; D.dsW = c->dsW; D.dsH = c->dsH; D.img = img; D.ipitch = pitch; D.dsLT = c->dsLT; D.dsST = c->dsST; D.ctl = c->ctl;
+            const int nds = c->dsW * c->dsH;
+            if(nds > 0) {
+                if(C == 1) downsample_motion_kernel<1><<<(nds + 127) / 128, 128, 0, c->s_aux>>>(D); else downsample_motion_kernel<3><<<(nds + 127) / 128, 128, 0, c->s_aux>>>(D);
+                LAUNCHED();
+            }
+        }
+        CK(cudaEventRecord(c->ev_join, c->s_aux));
         c->ghost_idx ^= 1;
-        pp_blink_dilate<<<wg, 256, 0, st>>>(P); LAUNCHED();
-        pp_erode_seed<<<wg, 256, 0, st>>>(P); LAUNCHED();
+        pp_blink_close<<<wg, 256, 0, st>>>(P); LAUNCHED(); mark("pp_blink_close");
         {
             HoleArgs Hh{};
             Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw; Hh.comb = c->comb;
             Hh.parent = c->uf_parent; Hh.rankbase = c->uf_rankbase;
             const int rb = (H + 7) / 8;
-            pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
-            pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
-            pp_holes_combine<<<rb, 256, 0, st>>>(Hh); LAUNCHED();
+            pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_init");
+            pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_union");
+            pp_holes_combine<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_combine");
         }
-        pp_median<<<mg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
-        pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED();
-        pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED();
-        DownsampleArgs D{};
-        D.W = W; D.H = H; D.CH = C; D.dsW = c->dsW; D.dsH = c->dsH; D.img = img; D.ipitch = pitch; D.dsLT = c->dsLT; D.dsST = c->dsST; D.ctl = c->ctl;
-        const int nds = c->dsW * c->dsH;
-        if(nds > 0) {
-            if(C == 1) downsample_motion_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(D); else downsample_motion_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(D);
-            LAUNCHED();
-        }
+        pp_median<<<mg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED(); mark("pp_median");
+        pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED(); mark("pp_dilate_blink");
+        pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED(); mark("pp_final_ema");
         TailArgs T{};
         T.ctl = c->ctl; T.lut = c->lut; T.rel = c->P.rel_lbsp_threshold; T.lbsp_off = c->P.lbsp_threshold_offset; T.min_color = c->P.color_dist_threshold;
         T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed;
-        subsense_tail_kernel<<<1, 256, 0, st>>>(T); LAUNCHED();
-        launch_refresh(c);
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0)); // the tail reads the motion sum, the conditional refresh rewrites the model: after the aux stream
+        mark("join_aux");
+        subsense_tail_kernel<<<1, 256, 0, st>>>(T); LAUNCHED(); mark("subsense_tail_kernel");
+        launch_refresh(c); mark("refresh");
     } else { // LOBSTER
         if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
-        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, st>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, st>>>(B);
+        CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->s_aux>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->s_aux>>>(B);
         LAUNCHED();
+        CK(cudaEventRecord(c->ev_join, c->s_aux));
         pp_median<<<mg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
         lobster_tail_kernel<<<1, 1, 0, st>>>(c->ctl); LAUNCHED();
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     if(c->collect_stats) ++c->stat_frames;
 }
@@ -1034,7 +1057,10 @@ int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lv
     c->algo = algo; c->device = device; c->seed = seed;
     static_assert(sizeof(Params) == sizeof(lvb_params), "params mirror out of sync");
     std::memcpy(&c->P, &p, sizeof(p));
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // high priority: while phase B occupies the auxiliary (low-priority) stream the small mask kernels get SM slots first
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
     if(e != cudaSuccess) { delete c; CK(e); }
     *out = c;
     LVB_CATCH
@@ -1045,6 +1071,9 @@ int lvb_destroy(lvb_handle h) {
     if(h->stream) { cudaStreamSynchronize(h->stream); }
     h->free_all();
     for(auto& sl : h->slot) { if(sl.h2d_done) cudaEventDestroy(sl.h2d_done); if(sl.compute_done) cudaEventDestroy(sl.compute_done); if(sl.d2h_done) cudaEventDestroy(sl.d2h_done); }
+    if(h->s_aux) cudaStreamDestroy(h->s_aux);
+    if(h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if(h->ev_join) cudaEventDestroy(h->ev_join);
     if(h->s_in) cudaStreamDestroy(h->s_in);
     if(h->s_out) cudaStreamDestroy(h->s_out);
     if(h->stream) cudaStreamDestroy(h->stream);
@@ -1206,6 +1235,20 @@ int lvb_set_profile(lvb_handle h, int enabled) {
 }
 int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches) {
     LVB_TRY
+    if(h && !h->trace.empty()) {
+        CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+        std::vector<std::pair<std::string, std::pair<double, int>>> agg;
+        for(size_t k = 1; k < h->trace.size(); ++k) {
+            if(std::string(h->trace[k].first) == "frame_start") continue;
+            float ms = 0; cudaEventElapsedTime(&ms, h->trace[k - 1].second, h->trace[k].second);
+            bool found = false;
+            for(auto& a : agg) if(a.first == h->trace[k].first) { a.second.first += ms; a.second.second++; found = true; }
+            if(!found) agg.push_back({h->trace[k].first, {ms, 1}});
+        }
+        for(auto& a : agg) fprintf(stderr, "[lvb trace] %-22s %8.1f us\n", a.first.c_str(), a.second.first / a.second.second * 1e3);
+        for(auto& t : h->trace) cudaEventDestroy(t.second);
+        h->trace.clear();
+    }
     REQUIRE(h && ms_total && launches, "null argument");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));

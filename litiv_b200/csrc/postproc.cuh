@@ -57,6 +57,36 @@ __global__ void __launch_bounds__(256) pp_blink_dilate(const PostArgs A) {
     A.lastraw[i] = raw;
     A.tmpA[i] = morph_word<1, true>(A.raw, y, wi, A.H, A.WW, A.W);
 }
+/// P1 + the whole MORPH_CLOSE in one launch: erode3x3(dilate3x3(raw)) needs raw rows y-2..y+2; the dilated rows are
+/// recomputed per word (a handful of bit operations each) instead of round-tripping through a plane and a launch boundary.
+__global__ void __launch_bounds__(256) pp_blink_close(const PostArgs A) {
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if(wi >= A.WW) return;
+    const size_t i = (size_t)y * A.WW + wi;
+    const uint32_t raw = A.raw[i];
+    const uint32_t cur_blink = raw ^ A.lastraw[i];
+    A.blinks[i] = cur_blink | A.lastrawblink[i];
+    A.lastrawblink[i] = cur_blink;
+    A.lastraw[i] = raw;
+    // erode: AND over rows y-1..y+1 (rows outside the image are ignored) of the horizontally eroded dilated row; the
+    // horizontal erosion needs the dilated words wi-1, wi, wi+1 (outside the image: all ones)
+    uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+    for(int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if(yy < 0 || yy >= A.H) continue;
+        uint32_t d[3];
+#pragma unroll
+        for(int k = -1; k <= 1; ++k) {
+            const int w2 = wi + k;
+            d[k + 1] = (w2 < 0 || w2 >= A.WW) ? 0xFFFFFFFFu : morph_word<1, true>(A.raw, yy, w2, A.H, A.WW, A.W);
+        }
+        if(wi == A.WW - 1 && (A.W & 31)) d[1] |= ~valid_mask(wi, A.WW, A.W); // bits beyond the row end count as "outside"
+        if(wi + 1 == A.WW - 1 && (A.W & 31)) d[2] |= ~valid_mask(wi + 1, A.WW, A.W);
+        acc &= hmorph<1, false>(d[0], d[1], d[2]);
+    }
+    A.pre[i] = acc & valid_mask(wi, A.WW, A.W);
+}
 /// second half of MORPH_CLOSE (erode 3x3)
 __global__ void __launch_bounds__(256) pp_erode_seed(const PostArgs A) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;

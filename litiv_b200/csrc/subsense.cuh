@@ -475,13 +475,16 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
     typedef typename Pack<CH>::Desc Desc;
     const FrameCtl* ctl = A.ctl;
     if(!ctl->do_refresh) return;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if(x >= A.W || y >= A.H) return;
+    // launched every frame with a small grid (the request is decided on the device): a CTA walks 32x8 tiles grid-stride
+    const int tiles_x = A.Wp / 32, ntiles = tiles_x * ((A.H + 7) / 8);
+    for(int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int x = (tile % tiles_x) * 32 + threadIdx.x, y = (tile / tiles_x) * 8 + threadIdx.y;
+    if(x >= A.W || y >= A.H) continue;
     const size_t pix = (size_t)y * A.Wp + x;
     if(ctl->set_T_one && A.maps) A.maps[pix * 2].x = 1.0f;
-    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
+    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) continue;
     const bool force = ctl->refresh_force != 0;
-    if(!force && ((A.lastfg_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
+    if(!force && ((A.lastfg_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) continue;
     const uint32_t N = (uint32_t)A.N, start = ctl->refresh_start, count = ctl->refresh_count, epoch = ctl->refresh_epoch;
     const uint32_t pixid = (uint32_t)(y * A.W + x);
     const Col* lc = (const Col*)A.last_color;
@@ -521,6 +524,7 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
         } else d = ((const Desc*)A.last_desc)[sp];
         ((Col*)A.bg_color)[(size_t)rs * A.plane + pix] = col;
         ((Desc*)A.bg_desc)[(size_t)rs * A.plane + pix] = d;
+    }
     }
 }
 
