@@ -125,6 +125,13 @@ __device__ __forceinline__ uint32_t fast_mod(uint32_t x, uint32_t n, uint32_t ma
     return r >= n ? r - n : r;
 }
 
+/// floor(x / n) with the same magic (exact: the estimate is corrected by at most one)
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t n, uint32_t magic) {
+    if(n == 1u) return x;
+    const uint32_t q = __umulhi(x, magic);
+    return (x - q * n) >= n ? q + 1u : q;
+}
+
 // ---------------------------------------------------------------------------------------------
 // sampling patterns
 // ---------------------------------------------------------------------------------------------

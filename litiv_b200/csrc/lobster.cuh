@@ -102,7 +102,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                     int dx, dy;
                     neighbor_offset(true, rnd.w, dx, dy);
                     const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
-                    const uint32_t slot = philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x % N;
+                    const uint32_t slot = (rnd.y / N) % N; // one Philox block per pixel
                     A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                     ((Desc*)A.last_desc)[pix] = intra_pack; // scratch plane read by phase B (not the reference's m_oLastDescFrame)
                     has_intent = true; intent_row = ny - y + 2;

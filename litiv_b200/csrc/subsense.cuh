@@ -334,7 +334,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             const bool nb_ghost = (A.ghost_prev[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u;
             const uint32_t n_rand = rnd.w;
             if((n_rand % (cur3 ? LR : (LR / 2u + 1u))) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
-                const uint32_t slot = fast_mod(philox_block(A.seed, frame, pixid, 1, DOM_APPLY).x, N, A.n_magic);
+                const uint32_t slot = fast_mod(fast_div(rnd.y, N, A.n_magic), N, A.n_magic); // (d1 / N) % N: one Philox block serves the whole pixel
                 // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
                 A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
                 has_intent = true; intent_row = ny - y + 2;

@@ -286,7 +286,8 @@ struct SuBSENSE : BgsBase {
                 const float nbRawST = mode == MODE_REFERENCE ? rawST[q] : snapRawST[q];
                 if((n_rand % (cur3x3 ? LR : (LR / 2 + 1))) == 0
                    || (nbRawST > GHOSTDET_S_MIN && nbDlast < GHOSTDET_D_MAX && (n_rand % ((size_t)t_lower)) == 0)) {
-                    const size_t slot = draw(4) % N;
+                    // snapshot mode: the neighbour slot reuses draw site 1 ((d1 / N) % N) so one Philox block serves the whole pixel
+                    const size_t slot = mode == MODE_REFERENCE ? draw(4) % N : (draw(1) / N) % N;
                     if(mode == MODE_REFERENCE) write_sample(q, slot);
                     else {
                         NbWrite w; w.target = q; w.slot = (int)slot;
@@ -555,7 +556,7 @@ struct LOBSTER : BgsBase {
                 if((draw(2) % LR) == 0) {
                     int nx, ny;
                     neighbor_pos_3x3((int)draw(3), nx, ny, x, y, 2, W, H);
-                    const size_t slot = draw(4) % N;
+                    const size_t slot = mode == MODE_REFERENCE ? draw(4) % N : (draw(1) / N) % N; // snapshot: one Philox block per pixel
                     const size_t q = (size_t)ny * W + nx;
                     if(mode == MODE_REFERENCE) {
                         for(int c = 0; c < CH; ++c) { bgc((int)slot)[q * CH + c] = cur[c]; bgd((int)slot)[q * CH + c] = intra[c]; }
