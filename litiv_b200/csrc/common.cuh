@@ -107,15 +107,33 @@ __device__ __forceinline__ uint32_t win_center(const Window5<CH>& Wn, int c) {
 }
 
 /// desc = sum_n (|val_n - ref| > t) << n   (strict >, unsigned) — LBSP.hpp:193-224.
-/// VABSDIFF4 + SWAR compare give one 0/1 flag byte per neighbour; two dp4a chains with weights 1,2,4,..,128 gather
+/// VABSDIFF4 + SWAR compare give one flag byte per neighbour; two dp4a chains with weights 1,2,4,..,128 gather
 /// the 16 flags into the descriptor bits.
+/// SMALL_T: every threshold is known to be <= 127 (the LUT cap sat(off + 255*rel) is 85 with the reference's defaults), so
+/// |d| > t  <=>  bit 7 of ((d & 0x7f) + (127 - t))  OR  bit 7 of d : 3 instructions per 4 neighbours instead of 5, and the
+/// flags stay at bit 7 (the dp4a sums are 128 x the descriptor halves, folded into the final shift).
+template<bool SMALL_T = false>
 __device__ __forceinline__ uint32_t lbsp_threshold(const Lookup16& L, uint32_t ref, uint32_t t) {
-    const uint32_t r4 = __byte_perm(ref, 0, 0x0000), t4 = __byte_perm(t, 0, 0x0000);
-    const uint32_t f0 = __vsetgtu4(__vabsdiffu4(L.w[0], r4), t4), f1 = __vsetgtu4(__vabsdiffu4(L.w[1], r4), t4);
-    const uint32_t f2 = __vsetgtu4(__vabsdiffu4(L.w[2], r4), t4), f3 = __vsetgtu4(__vabsdiffu4(L.w[3], r4), t4);
-    const uint32_t lo = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
-    const uint32_t hi = __dp4a(f3, 0x80402010u, __dp4a(f2, 0x08040201u, 0u));
-    return lo | (hi << 8);
+    const uint32_t r4 = __byte_perm(ref, 0, 0x0000);
+    if constexpr (SMALL_T) {
+        const uint32_t k4 = __byte_perm(127u - t, 0, 0x0000);
+        uint32_t f[4];
+#pragma unroll
+        for(int q = 0; q < 4; ++q) {
+            const uint32_t d = __vabsdiffu4(L.w[q], r4);
+            f[q] = (((d & 0x7f7f7f7fu) + k4) | d) & 0x80808080u;
+        }
+        const uint32_t lo = __dp4a(f[1], 0x80402010u, __dp4a(f[0], 0x08040201u, 0u));
+        const uint32_t hi = __dp4a(f[3], 0x80402010u, __dp4a(f[2], 0x08040201u, 0u));
+        return (lo >> 7) | (hi << 1);
+    } else {
+        const uint32_t t4 = __byte_perm(t, 0, 0x0000);
+        const uint32_t f0 = __vsetgtu4(__vabsdiffu4(L.w[0], r4), t4), f1 = __vsetgtu4(__vabsdiffu4(L.w[1], r4), t4);
+        const uint32_t f2 = __vsetgtu4(__vabsdiffu4(L.w[2], r4), t4), f3 = __vsetgtu4(__vabsdiffu4(L.w[3], r4), t4);
+        const uint32_t lo = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
+        const uint32_t hi = __dp4a(f3, 0x80402010u, __dp4a(f2, 0x08040201u, 0u));
+        return lo | (hi << 8);
+    }
 }
 
 /// x % n for x < 2^32 with magic = floor(2^32 / n): the estimated quotient is at most one too small

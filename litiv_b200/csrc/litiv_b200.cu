@@ -107,6 +107,8 @@ struct lvb_context {
     int ghost_idx = 0;
     ushort* intents = nullptr;
     uint8_t* lut = nullptr;
+    bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
+    uint32_t* magic = nullptr; // [257] floor(2^32 / n)
     FrameCtl* ctl = nullptr;
     float* dsLT = nullptr; float* dsST = nullptr;
     std::vector<uint8_t> roi_host;
@@ -138,11 +140,11 @@ struct lvb_context {
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
 
     void free_all() {
-        void* ptrs[] = {uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {magic, uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -174,6 +176,14 @@ void put_ctl(lvb_context* c, const FrameCtl& f) {
     CK(cudaMemcpyAsync(c->ctl, &f, sizeof(FrameCtl), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 }
+
+/// true when no LUT entry can exceed 127: the current values and the cap of the +-1 adaptation (SuBSENSE.cpp:563, PAWCS.cpp:1470)
+bool lut_fits_7bit(const lvb_context* c, const uint8_t* lut) {
+    for(int i = 0; i < 256; ++i) if(lut[i] > 127) return false;
+    const float hi = std::fmin(std::fmax(std::rint((float)c->P.lbsp_threshold_offset + 255.0f * c->P.rel_lbsp_threshold), 0.f), 255.f);
+    return hi <= 127.f;
+}
+uint32_t magic_of(uint32_t n) { return n <= 1u ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / n); }
 
 void launch_refresh(lvb_context* c) {
     RefreshArgs R{};
@@ -411,6 +421,14 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
             lut[t] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
         }
         h2d(c->stream, c->lut, lut, 256);
+        c->lut_small = lut_fits_7bit(c, lut);
+    }
+    {   // floor(2^32 / n) for n = 1..256 (n = 1: 2^32 - 1, still exact with fast_mod's single correction step)
+        uint32_t mg[257];
+        mg[0] = 0; mg[1] = 0xFFFFFFFFu;
+        for(uint32_t n = 2; n <= 256; ++n) mg[n] = (uint32_t)(0x100000000ull / n);
+        c->magic = dalloc<uint32_t>(c->stream, 257, false);
+        h2d(c->stream, c->magic, mg, sizeof(mg));
     }
     FrameCtl f{};
     f.frame_idx = 1; f.aLT = 1.0f; f.aST = 1.0f; f.roi_count = (uint32_t)fin;
@@ -541,9 +559,10 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
+    A.magic = c->magic; A.lr_magic = magic_of(A.lr_fixed); A.lr2_magic = magic_of(A.lr_fixed / 2u + 1u);
     PhaseBArgs B{};
-    B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane; B.img = img; B.ipitch = pitch;
-    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_desc = A.last_desc; B.intent_bits = c->intent_bits; B.intents = c->intents; B.bitplane = (size_t)H * c->WW;
+    B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane;
+    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = A.last_desc; B.intents = c->intents;
     PostArgs P{};
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv;
@@ -555,7 +574,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
     if(sub) {
-        if(C == 1) subsense_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
+        if(c->lut_small) { if(C == 1) subsense_phaseA<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        else { if(C == 1) subsense_phaseA<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         mark("phaseA");
@@ -924,7 +944,7 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
         return;
     }
     REQUIRE(n != "roi", "use lvb_set_roi");
-    if(n == "lut") { h2d(c->stream, c->lut, in, 256); return; }
+    if(n == "lut") { h2d(c->stream, c->lut, in, 256); c->lut_small = lut_fits_7bit(c, (const uint8_t*)in); return; }
     if(uint32_t* b = bits_by_name(c, n)) {
         std::vector<uint32_t> h((size_t)H * WW, 0);
         const uint8_t* s = (const uint8_t*)in;

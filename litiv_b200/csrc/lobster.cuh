@@ -34,7 +34,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
     bool is_fg = false, has_intent = false;
     uint32_t scanned = 0, writes = 0;
-    int intent_row = 0;
+    uint32_t intent = NO_INTENT;
 
     uint32_t cur[CH];
     Col cur_pack;
@@ -103,9 +103,9 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                     neighbor_offset(true, rnd.w, dx, dy);
                     const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
                     const uint32_t slot = (rnd.y / N) % N; // one Philox block per pixel
-                    A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
+                    intent = (((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot;
                     ((Desc*)A.last_desc)[pix] = intra_pack; // scratch plane read by phase B (not the reference's m_oLastDescFrame)
-                    has_intent = true; intent_row = ny - y + 2;
+                    has_intent = true;
                 }
             }
         }
@@ -113,14 +113,8 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     if(in_img) ((Col*)A.last_color)[pix] = cur_pack; // whole frame (:580)
 
     const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
-    uint32_t b_int = 0;
-#pragma unroll
-    for(int d = 0; d < 5; ++d) {
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, has_intent && intent_row == d);
-        if((int)threadIdx.x == d) b_int = b;
-    }
+    if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame (phase B scans the plane without a has-intent mask)
     if(y < A.H && (x >> 5) < A.WW) {
-        if(threadIdx.x < 5) A.intent_bits[(size_t)threadIdx.x * A.bitplane + wi] = b_int;
         if(threadIdx.x == 0) A.raw_bits[wi] = b_raw;
     }
     if(A.collect_stats) {

@@ -70,6 +70,8 @@ struct SubArgs {
     int min_color, desc_off;
     int use_tma, collect_stats;
     uint32_t n_magic;          // floor(2^32 / N) for fast_mod
+    const uint32_t* magic;     // [257] floor(2^32 / n) (n = 1: 0xFFFFFFFF), device table for x % ceil(T(x))
+    uint32_t lr_magic, lr2_magic; // magic numbers of lr_fixed and lr_fixed/2+1 when the rate is fixed
 };
 
 } // namespace lvb

@@ -18,6 +18,7 @@ constexpr int TILE_W = 32, TILE_H = LVB_TILE_H, HALO = 2; // tile of the TMA-sta
 #define PHASEA_MIN_BLOCKS 4
 #endif
 constexpr int TILE_ROWS = TILE_H + 2 * HALO;
+constexpr uint32_t NO_INTENT = 0xFFFFu; // intents[] entry of a pixel that queued no neighbour write (valid codes are <= 0x18FF)
 // TMA boxes must start on a 16-byte boundary of the image row: the box starts TILE_SHIFT bytes before the halo's first
 // byte ((32k-2)*ch mod 16 is the same for every tile) and is TILE_SHIFT bytes wider.
 __host__ __device__ constexpr int tile_shift(int ch) { return (16 - (HALO * ch) % 16) % 16; }
@@ -64,7 +65,7 @@ __device__ __forceinline__ void stage_tile(uchar* tile, uint64_t* bar, const CUt
 // ---- sample-consensus scan (SuBSENSE.cpp:229-253 / :367-395) ----
 /// one sample against one pixel: colour gate, then the descriptor test. Returns whether the sample matches and
 /// its total descriptor / colour+descriptor distances.
-template<int CH>
+template<int CH, bool T7>
 __device__ __forceinline__ bool subsense_test_sample(const Lookup16 (&L)[CH], const uint32_t (&cur)[CH], const uint32_t (&intra)[CH],
                                                      const typename Pack<CH>::Col bc, const typename Pack<CH>::Desc bd,
                                                      uint32_t thrC, uint32_t thrD, const uchar* s_lut, uint32_t& totDesc, uint32_t& totSum) {
@@ -82,7 +83,7 @@ __device__ __forceinline__ bool subsense_test_sample(const Lookup16 (&L)[CH], co
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
             const uint32_t b = col_get(bc, c), d = desc_get(bd, c);
-            const uint32_t inter = lbsp_threshold(L[c], b, s_lut[b]);
+            const uint32_t inter = lbsp_threshold<T7>(L[c], b, s_lut[b]);
             const uint32_t dd = (__popc(intra[c] ^ d) + __popc(inter ^ d)) >> 1;
             if(CH == 1) {
                 const uint32_t sum = min((dd >> 2) * 15u + cd[c], 255u);
@@ -110,7 +111,7 @@ template<int CH> struct ScanCtx {
 /// N, so a per-lane loop runs at 1-5 active lanes for up to N-2 dependent DRAM round trips. Instead the k undecided pixels
 /// of the warp share its 32 lanes: each round tests 32/k' samples (k' = k rounded up to a power of two) of every undecided
 /// pixel at once, then ballots + a segmented min-reduction reproduce the sequential "stop at the REQ-th match" rule exactly.
-template<int CH>
+template<int CH, bool T7>
 __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* wctx, uchar* worder, const uchar* s_lut, bool undecided,
                                                    uint32_t N, uint32_t REQ, uint32_t& good, uint32_t& s, uint32_t& minDesc, uint32_t& minSum) {
     typedef typename Pack<CH>::Col Col;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
             if constexpr (CH == 1) intra[0] = ctx[X::INTRA];
             else { intra[0] = ctx[X::INTRA] & 0xFFFFu; intra[1] = ctx[X::INTRA] >> 16; intra[2] = ctx[X::INTRA + 1]; }
             uint32_t d_, s_;
-            ok = subsense_test_sample<CH>(L, cur, intra, bc, bd, ctx[X::THRC], ctx[X::THRD], s_lut, d_, s_);
+            ok = subsense_test_sample<CH, T7>(L, cur, intra, bc, bd, ctx[X::THRC], ctx[X::THRD], s_lut, d_, s_);
             if(ok) { td = d_; ts = s_; }
         }
         const uint32_t okmask = __ballot_sync(FULL, ok);
@@ -182,7 +183,11 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
     }
 }
 
-template<int CH>
+/// slice of FrameCtl staged in shared memory by the prologue (the feedback step reads it long after the state loads)
+struct CtlSlice { float aLT, aST, t_lower, t_upper; uint32_t frame, cooldown, use3x3, pad; };
+constexpr int GHOST_ROWS = TILE_H + 2 * HALO;
+
+template<int CH, bool T7>
 __global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
 subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
@@ -194,13 +199,30 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     __shared__ uchar s_order[TILE_H][32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uchar s_lut[256];
-    __shared__ uint32_t s_cnt[4];
+    __shared__ uint32_t s_cnt[5];                 // nonzero | scanned | writes | fg | warps done
+    __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
+    __shared__ uint32_t s_magic[257];             // floor(2^32 / n): x % ceil(T(x)) without a hardware divide
+    __shared__ CtlSlice s_ctl;
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    // small per-frame tables the feedback step needs: fetched here, next to the state loads, so that no dependent DRAM/L2 round
+    // trip is left after the scan
     for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
-    if(tid < 4) s_cnt[tid] = 0;
+    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
+    if(tid < 5) s_cnt[tid] = 0;
+    if(tid < GHOST_ROWS * 3) {
+        const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
+        s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
+    }
+    if(tid == 64) {
+        const FrameCtl* ctl = A.ctl;
+        CtlSlice cs;
+        cs.aLT = ctl->aLT; cs.aST = ctl->aST; cs.t_lower = ctl->t_lower; cs.t_upper = ctl->t_upper;
+        cs.frame = ctl->frame_idx; cs.cooldown = ctl->cooldown; cs.use3x3 = ctl->use3x3; cs.pad = 0;
+        s_ctl = cs;
+    }
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const bool in_img = (x < A.W) && (y < A.H);
@@ -233,7 +255,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
     bool is_fg = false, unstable_new = false, ghost_new = false, has_intent = false, nonzero = false;
     uint32_t writes = 0;
-    int intent_row = 0; // row offset (ty - y + 2) of the queued neighbour write
+    uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
     const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
     const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
     uint32_t cur[CH], intra[CH];
@@ -256,7 +278,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             for(int c = 0; c < CH; ++c) {
                 L[c] = lbsp_lookup_window<CH>(Wn, c);
                 cur[c] = win_center<CH>(Wn, c);
-                intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+                intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
             }
         }
         if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
@@ -264,8 +286,8 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 
         // samples 0 and 1 were prefetched
         uint32_t d_, s_;
-        if(good < REQ && s < N) { if(subsense_test_sample<CH>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
-        if(good < REQ && s < N) { if(subsense_test_sample<CH>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+        if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+        if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
         if(good < REQ && s < N) { // still undecided: park the scan context for the warp-cooperative tail
             uint32_t* ctx = &s_ctx[threadIdx.y][threadIdx.x * X::WORDS];
 #pragma unroll
@@ -275,13 +297,12 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             ctx[X::THRC] = thrC; ctx[X::THRD] = thrD; ctx[X::PIX] = (uint32_t)pix;
         }
     }
-    subsense_scan_tail<CH>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
+    subsense_scan_tail<CH, T7>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
     const uint32_t scanned = s;
 
     if(active) {
-        const FrameCtl* ctl = A.ctl;
-        const float aLT = ctl->aLT, aST = ctl->aST, t_lower = ctl->t_lower, t_upper = ctl->t_upper;
-        const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, use3x3 = ctl->use3x3;
+        const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
+        const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
         float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
         const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
@@ -320,8 +341,13 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
             rawLT = __fmul_rn(rawLT, oneLT);
             rawST = __fmul_rn(rawST, oneST);
+            // x % LR, x % (LR/2+1): T(x) <= 256, so the magic numbers come from a table (a fixed rate has them in the arguments)
             const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
-            if((rnd.x % LR) == 0) {
+            const uint32_t LR2 = LR / 2u + 1u;
+            const bool tab = !A.lr_fixed && LR <= 256u;
+            const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
+            const bool fastm = A.lr_fixed || tab;
+            if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
                 const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
                 ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
                 ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
@@ -331,13 +357,14 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             int dx, dy;
             neighbor_offset(cur3, rnd.z, dx, dy);
             const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
-            const bool nb_ghost = (A.ghost_prev[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u;
+            const bool nb_ghost = (s_ghost[ny - y0 + HALO][(nx >> 5) - (x0 >> 5) + 1] >> (nx & 31)) & 1u;
             const uint32_t n_rand = rnd.w;
-            if((n_rand % (cur3 ? LR : (LR / 2u + 1u))) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
+            const uint32_t nbLR = cur3 ? LR : LR2;
+            if((fastm ? fast_mod(n_rand, nbLR, cur3 ? mg : mg2) : n_rand % nbLR) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
                 const uint32_t slot = fast_mod(fast_div(rnd.y, N, A.n_magic), N, A.n_magic); // (d1 / N) % N: one Philox block serves the whole pixel
                 // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
-                A.intents[pix] = (ushort)((((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot);
-                has_intent = true; intent_row = ny - y + 2;
+                intent = (((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot;
+                has_intent = true;
             }
         }
         // T(x) (:302-311 / :451-460)
@@ -377,15 +404,8 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
     const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
     const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
-    uint32_t b_int = 0, b_int_any = 0; // lane d (<5) keeps the intent mask of row offset d
-#pragma unroll
-    for(int d = 0; d < 5; ++d) {
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, has_intent && intent_row == d);
-        if((int)threadIdx.x == d) b_int = b;
-        b_int_any |= b;
-    }
+    if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame: phase B scans the plane without a has-intent mask
     if(y < A.H && (x >> 5) < A.WW) {
-        if(threadIdx.x < 5) A.intent_bits[(size_t)threadIdx.x * A.bitplane + wi] = b_int; // one plane per row offset (phase B)
         if(threadIdx.x == 0) {
             A.raw_bits[wi] = b_raw; A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost;
             atomicAdd(&s_cnt[0], __popc(b_nz));
@@ -397,57 +417,62 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         for(int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
         if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[2], wr); atomicAdd(&s_cnt[3], __popc(b_raw)); }
     }
-    __syncthreads();
-    if(tid == 0) {
-        if(s_cnt[0]) atomicAdd(&A.ctl->nonzero_count, s_cnt[0]);
-        if(A.collect_stats) {
-            atomicAdd(&A.ctl->stat_scanned, (unsigned long long)s_cnt[1]);
-            atomicAdd(&A.ctl->stat_writes, (unsigned long long)s_cnt[2]);
-            atomicAdd(&A.ctl->stat_fg, (unsigned long long)s_cnt[3]);
+    // no closing barrier: the last warp of the CTA to get here publishes the CTA's counters (the others retire at once
+    // instead of idling behind the slowest scan tail)
+    if(threadIdx.x == 0) {
+        __threadfence_block();
+        if(atomicAdd(&s_cnt[4], 1u) == (uint32_t)TILE_H - 1u) {
+            __threadfence_block();
+            const uint32_t nz = atomicAdd(&s_cnt[0], 0u);
+            if(nz) atomicAdd(&A.ctl->nonzero_count, nz);
+            if(A.collect_stats) {
+                atomicAdd(&A.ctl->stat_scanned, (unsigned long long)atomicAdd(&s_cnt[1], 0u));
+                atomicAdd(&A.ctl->stat_writes, (unsigned long long)atomicAdd(&s_cnt[2], 0u));
+                atomicAdd(&A.ctl->stat_fg, (unsigned long long)atomicAdd(&s_cnt[3], 0u));
+            }
         }
     }
 }
 
-/// Phase B: apply the queued neighbour writes. One thread per TARGET pixel gathers the intents of the 5x5
-/// sources around it in raster order, so the last writer in raster order wins (oracle MODE_SNAPSHOT rule).
-/// A source at window position (k,dy) targets this pixel iff its stored offset index equals (2-dy)*5 + (4-k); the
-/// has-intent bits are split in 5 planes by row offset so only sources aiming at THIS row are visited.
+/// Phase B: apply the queued neighbour writes. One thread per TARGET pixel scans the intent words of the 5x5 sources
+/// around it (staged in shared memory with a 2-px halo) in raster order of the source, so for a given (target, slot) the
+/// last writer in raster order wins (oracle MODE_SNAPSHOT rule). A source at window position (k,dy) targets this pixel iff
+/// its stored offset index equals (2-dy)*5 + (4-k). Phase A rewrites the whole intent plane every frame (NO_INTENT where
+/// nothing was queued), so no has-intent mask is needed.
 struct PhaseBArgs {
     int W, H, Wp, WW, CH;
     size_t plane;
-    const uchar* img; size_t ipitch;
     void* bg_color; void* bg_desc;
+    const void* last_color;    // == this frame's colour for every pixel that queued a write
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
-    const uint32_t* intent_bits; const ushort* intents; size_t bitplane;
+    const ushort* intents;
 };
 
 template<int CH>
 __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    constexpr int TW = 32 + 4, TH = 8 + 4;
+    __shared__ ushort s_int[TH][TW + 2]; // +2: row pitch of 19 words (odd) keeps the 5-row column walk conflict-free
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for(int i = tid; i < TW * TH; i += 256) {
+        const int r = i / TW, cc = i - r * TW;
+        const int gx = x0 - 2 + cc, gy = y0 - 2 + r;
+        s_int[r][cc] = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? A.intents[(size_t)gy * A.Wp + gx] : (ushort)NO_INTENT;
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
-    const int wi = x >> 5, xb = x & 31;
 #pragma unroll
     for(int dy = -2; dy <= 2; ++dy) {
-        const int qy = y + dy; // always inside the image
-        const uint32_t* row = A.intent_bits + (size_t)(2 - dy) * A.bitplane + (size_t)qy * A.WW;
-        const uint32_t left = wi > 0 ? row[wi - 1] : 0u, cur = row[wi], right = wi + 1 < A.WW ? row[wi + 1] : 0u;
-        // 5-bit window: bit k <-> source x-2+k
-        const unsigned long long lo = ((unsigned long long)cur << 32) | left, hi = ((unsigned long long)right << 32) | cur;
-        uint32_t win = (xb >= 2) ? (uint32_t)(hi >> (xb - 2)) & 31u : (uint32_t)(lo >> (30 + xb)) & 31u;
-        while(win) {
-            const int k = __ffs(win) - 1;
-            win &= win - 1;
-            const int qx = x - 2 + k;
-            const size_t qpix = (size_t)qy * A.Wp + qx;
-            const uint32_t it = A.intents[qpix];
-            if((int)(it >> 8) == (2 - dy) * 5 + (4 - k)) {
-                const uint32_t slot = it & 0xFFu;
-                const size_t dst = (size_t)slot * A.plane + (size_t)y * A.Wp + x;
-                const uchar* src = A.img + (size_t)qy * A.ipitch + (size_t)qx * CH;
-                if constexpr (CH == 1) ((Col*)A.bg_color)[dst] = src[0];
-                else ((Col*)A.bg_color)[dst] = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16);
+#pragma unroll
+        for(int k = 0; k < 5; ++k) {
+            const uint32_t it = s_int[threadIdx.y + 2 + dy][threadIdx.x + k];
+            if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) {
+                const size_t qpix = (size_t)(y + dy) * A.Wp + (x - 2 + k);
+                const size_t dst = (size_t)(it & 0xFFu) * A.plane + (size_t)y * A.Wp + x;
+                ((Col*)A.bg_color)[dst] = ((const Col*)A.last_color)[qpix];
                 ((Desc*)A.bg_desc)[dst] = ((const Desc*)A.last_desc)[qpix];
             }
         }
