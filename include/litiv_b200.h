@@ -66,6 +66,12 @@ int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* 
 /* device-resident variant: d_img rows of d_step bytes, d_fgmask W*H bytes (or null), asynchronous on the instance's stream */
 int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);
 
+/* SuBSENSE runs its mask post-processing on a side stream of the instance (it overlaps the next frame's scan): lvb_flush makes
+ * the instance's stream (lvb_stream) wait for everything enqueued so far, so that work or events the caller puts on that stream
+ * afterwards are ordered behind the masks written by lvb_apply_device. Host-side calls (lvb_apply, lvb_sync*, state access)
+ * already wait for all streams. */
+int lvb_flush(lvb_handle h);
+
 /* getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649; LOBSTER.cpp:583-620; PAWCS.cpp:1525-1594) */
 int lvb_get_background_image(lvb_handle h, uint8_t* out);
 int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out);

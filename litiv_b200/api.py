@@ -4,6 +4,10 @@ Method names follow the reference (modules/video/include/litiv/video/BackgroundS
 initialize(img, roi) / apply(img, learningRate) -> fgmask / getBackgroundImage() / refreshModel(...).
 The library has no CPU fallback: if the CUDA extension is missing or no device is present, calls raise.
 """
+import os as _os
+# every instance drives several CUDA streams (upload, kernels, mask chain, auxiliary, read-back): with the default of 8 hardware
+# queues, streams of concurrent instances alias and serialise. Must be set before the CUDA context is created.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import ctypes as C
 import os
 import numpy as np
@@ -19,7 +23,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush",
 ]
 
 
@@ -56,6 +60,7 @@ def lib():
         L.lvb_apply_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_sync.argtypes = [C.c_void_p]
         L.lvb_sync_next.argtypes = [C.c_void_p]
+        L.lvb_flush.argtypes = [C.c_void_p]
         L.lvb_apply_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         L.lvb_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]
         L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
@@ -189,6 +194,10 @@ class _BackgroundSubtractor:
         """device-resident frame (raw CUDA pointers, e.g. torch tensor .data_ptr()); asynchronous on self.stream"""
         lr = self.getDefaultLearningRate() if learningRate is None else learningRate
         _chk(lib().lvb_apply_device(self._h, d_img_ptr, d_step, d_mask_ptr, float(lr)))
+
+    def flush(self):
+        """make self.stream wait for the side-stream work (mask chain) of every frame enqueued so far"""
+        _chk(lib().lvb_flush(self._h))
 
     def getBackgroundImage(self):
         if self.shape is None:

@@ -102,9 +102,23 @@ struct lvb_context {
     void* bg_color = nullptr; void* bg_desc = nullptr;
     float4* maps = nullptr; float2* fin = nullptr;
     void* last_color = nullptr; void* last_desc = nullptr; void* tmp_desc = nullptr;
+    // SuBSENSE: the scan of frame k+1 applies the neighbour writes queued by frame k, whose sources are frame k's colours and
+    // descriptors, while it writes frame k+1's: last_color/last_desc name the LATEST frame's planes, *_alt the spare ones
+    void* last_color_alt = nullptr; void* last_desc_alt = nullptr;
+    uint32_t nb_seq = 0;                // sequence number of the frame whose queued neighbour writes may still be pending (0: none)
     uint32_t* bits = nullptr; // all bit planes, one allocation
     uint32_t *roi_bits, *raw, *lastraw, *lastrawblink, *blinks, *tmpA, *pre, *reach, *comb, *lastfg, *dilinv, *unstable, *ghost[2], *intent_bits;
     int ghost_idx = 0;
+    // SuBSENSE runs the mask chain of frame k beside the feedback kernel of frame k and the scan of frame k+1: what the chain
+    // writes and the feedback kernel reads (previous frame's value) is double-buffered. raw/blinks/lastfg/fin always name the
+    // buffers of the LATEST frame, *_alt the spare ones the next frame will write.
+    uint32_t *raw_alt = nullptr, *blinks_alt = nullptr, *lastfg_alt = nullptr; float2* fin_alt = nullptr;
+    uint2* hand = nullptr;              // scan -> feedback hand-off
+    cudaStream_t s_post = nullptr;      // mask chain (high priority: its small kernels slip in beside the scan of the next frame)
+    cudaEvent_t ev_scan = nullptr, ev_post = nullptr, ev_ds = nullptr, ev_mask = nullptr;
+    bool post_pending = false;          // ev_post was recorded by a frame whose chain the next feedback kernel has to wait for
+    uint32_t sub_frame = 1;             // host mirror of FrameCtl::frame_idx (SuBSENSE; the final-mask EMA factors derive from it)
+    uint32_t chain_seq = 0;             // frames enqueued (sequence number written to FrameCtl::chain_done by the mask stream)
     ushort* intents = nullptr;
     uint8_t* lut = nullptr;
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
@@ -140,11 +154,11 @@ struct lvb_context {
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
 
     void free_all() {
-        void* ptrs[] = {magic, uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -168,11 +182,20 @@ dim3 stage_grid(const lvb_context* c) { return dim3(c->Wp / TILE_W, (c->H + TILE
 const dim3 stage_block(TILE_W, TILE_H);
 dim3 word_grid(const lvb_context* c) { return dim3((c->WW + 255) / 256, c->H); }
 
+/// wait for every stream of the instance (the mask chain and the auxiliary kernels run beside the instance stream)
+void sync_streams(lvb_context* c) {
+    CK(cudaStreamSynchronize(c->stream));
+    if(c->s_post) CK(cudaStreamSynchronize(c->s_post));
+    if(c->s_aux) CK(cudaStreamSynchronize(c->s_aux));
+}
+
 void get_ctl(lvb_context* c, FrameCtl& f) {
+    sync_streams(c);
     CK(cudaMemcpyAsync(&f, c->ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 }
 void put_ctl(lvb_context* c, const FrameCtl& f) {
+    sync_streams(c);
     CK(cudaMemcpyAsync(c->ctl, &f, sizeof(FrameCtl), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
 }
@@ -185,24 +208,44 @@ bool lut_fits_7bit(const lvb_context* c, const uint8_t* lut) {
 }
 uint32_t magic_of(uint32_t n) { return n <= 1u ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / n); }
 
-void launch_refresh(lvb_context* c) {
+__global__ void mark_nb_applied_kernel(FrameCtl* ctl, uint32_t seq) { ctl->nb_applied_seq = seq; }
+/// SuBSENSE leaves the neighbour writes of the latest frame queued for the next frame's scan; anything else that reads the sample
+/// model (state export, getBackgroundImage, a host-requested refreshModel) applies them first with the standalone kernel
+void flush_pending(lvb_context* c) {
+    if(c->algo != LVB_ALGO_SUBSENSE || !c->initialized || c->nb_seq == 0) return;
+    PhaseBArgs B{};
+    B.W = c->W; B.H = c->H; B.Wp = c->Wp; B.WW = c->WW; B.CH = c->C; B.plane = c->plane;
+    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents;
+    B.ctl = c->ctl; B.pending_seq = c->nb_seq;
+    const dim3 tg(c->Wp / 32, (c->H + 7) / 8), tb(32, 8);
+    if(c->C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->stream>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->stream>>>(B);
+    LAUNCHED();
+    mark_nb_applied_kernel<<<1, 1, 0, c->stream>>>(c->ctl, c->nb_seq); LAUNCHED();
+    CK(cudaStreamSynchronize(c->stream));
+}
+/// conditional refreshModel on the instance stream. wait_seq != 0 (in-frame use): the grid is kept to two CTAs per SM because
+/// a fired request polls FrameCtl::chain_done while the mask stream still needs room to run.
+void launch_refresh(lvb_context* c, uint32_t wait_seq = 0) {
     RefreshArgs R{};
     R.W = c->W; R.H = c->H; R.Wp = c->Wp; R.WW = c->WW; R.CH = c->C; R.N = c->P.n_samples; R.plane = c->plane;
     R.bg_color = c->bg_color; R.bg_desc = c->bg_desc; R.last_color = c->last_color; R.last_desc = c->last_desc;
     R.roi_bits = c->roi_bits; R.lastfg_bits = c->lastfg; R.maps = c->algo == LVB_ALGO_SUBSENSE ? c->maps : nullptr;
     R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
     const dim3 tgd = tile_grid(c);
-    const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, 148 * 8);
+    R.wait_seq = wait_seq;
+    R.intents = c->intents; R.pending_seq = c->algo == LVB_ALGO_SUBSENSE ? c->nb_seq : 0u;
+    const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, wait_seq ? 148 * 2 : 148 * 8);
     if(c->C == 1) refresh_model_kernel<1><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     else refresh_model_kernel<3><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
-    LAUNCHED();
-    refresh_done_kernel<<<1, 1, 0, c->stream>>>(c->ctl);
     LAUNCHED();
 }
 
 
+
 } // namespace
 
+/// mask stream, right behind the median kernel: the final mask (lastfg) of frame `seq` is complete
+__global__ void chain_done_kernel(FrameCtl* ctl, uint32_t seq) { ctl->chain_done = seq; }
 __global__ void refresh_start_kernel(FrameCtl* ctl, uint64_t seed, uint32_t N) {
     ctl->refresh_start = philox_draw(seed, ctl->refresh_epoch, 0, 0, DOM_REFRESH_START) % N;
 }
@@ -347,6 +390,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     REQUIRE(W <= 8192, "frame width above 8192 pixels is not supported");
     REQUIRE(step >= (size_t)W * C, "row step smaller than a row");
     CK(cudaSetDevice(c->device));
+    if(c->initialized) sync_streams(c);
     // ROI (BackgroundSubtractionUtils.cpp:82-99, validateROI :28-36)
     std::vector<uint8_t> r((size_t)W * H, 255);
     if(roi) {
@@ -382,6 +426,8 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         b.use_tma = make_image_tmap(&b.tmap, b.d_img, W, H, C, c->ipitch) ? 1 : 0;
         if(!c->s_in) { CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
                        { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->s_aux, cudaStreamNonBlocking, lo)); }
+                       { int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CK(cudaStreamCreateWithPriority(&c->s_post, cudaStreamNonBlocking, hi)); }
+                       for(cudaEvent_t* e : {&c->ev_scan, &c->ev_post, &c->ev_ds, &c->ev_mask}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
                        CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming)); }
         for(lvb_context::Slot& sl : c->slot) if(!sl.h2d_done) {
             CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
@@ -396,12 +442,13 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     c->last_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     c->tmp_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
     const size_t bp = (size_t)H * c->WW;
-    c->bits = dalloc<uint32_t>(c->stream, bp * 24);
+    c->bits = dalloc<uint32_t>(c->stream, bp * 27);
+    c->raw_alt = c->bits + bp * 24; c->blinks_alt = c->bits + bp * 25; c->lastfg_alt = c->bits + bp * 26;
     uint32_t** planes[] = {&c->roi_bits, &c->raw, &c->lastraw, &c->lastrawblink, &c->blinks, &c->tmpA, &c->pre, &c->reach, &c->comb,
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
     c->roi255 = c->bits + bp * 19; c->illum = c->bits + bp * 20; c->did = c->bits + bp * 21; c->dil = c->bits + bp * 22; c->gop_bits = c->bits + bp * 23; // PAWCS (intent planes: 14..18)
-    c->ghost_idx = 0;
+    c->ghost_idx = 0; c->sub_frame = 1; c->chain_seq = 0; c->post_pending = false;
     c->uf_rs = (W + 1) / 2 + 1;
     c->uf_parent = dalloc<uint32_t>(c->stream, (size_t)H * c->uf_rs + 1);
     c->uf_rankbase = dalloc<ushort>(c->stream, (size_t)H * c->WW);
@@ -447,6 +494,10 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         if(f.lr_scaling) REQUIRE(W % 8 == 0 && H % 8 == 0, "frame-level analysis needs frame sizes that are multiples of 8 (other sizes: not implemented yet)");
         c->maps = dalloc<float4>(c->stream, c->plane * 2);
         c->fin = dalloc<float2>(c->stream, c->plane);
+        c->fin_alt = dalloc<float2>(c->stream, c->plane);
+        c->hand = dalloc<uint2>(c->stream, c->plane);
+        c->last_color_alt = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
+        c->last_desc_alt = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
         c->dsLT = dalloc<float>(c->stream, (size_t)c->dsW * c->dsH * C);
         c->dsST = dalloc<float>(c->stream, (size_t)c->dsW * c->dsH * C);
         std::vector<float4> m(c->plane * 2);
@@ -468,6 +519,10 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     if(C == 1) init_frame_kernel<1><<<stage_grid(c), stage_block, 0, c->stream>>>(I, c->tmap_img);
     else init_frame_kernel<3><<<stage_grid(c), stage_block, 0, c->stream>>>(I, c->tmap_img);
     LAUNCHED();
+    if(c->last_color_alt) { // pixels outside the ROI keep their initial colour / descriptor in both planes
+        CK(cudaMemcpyAsync(c->last_color_alt, c->last_color, c->plane * c->col_bytes(), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->last_desc_alt, c->last_desc, c->plane * c->desc_bytes(), cudaMemcpyDeviceToDevice, c->stream));
+    }
     c->initialized = true;
     if(c->algo == LVB_ALGO_PAWCS) paw_launch_refresh(c, paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0), 1);
     else launch_refresh(c);
@@ -512,7 +567,7 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     PostArgs P{};
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv; P.dil = c->dil;
-    P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+    P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.fin_in = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
     pp_blink_close<<<wg, 256, 0, st>>>(P); LAUNCHED();
     {
         HoleArgs Hh{};
@@ -545,45 +600,41 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
 }
 
 /// enqueue one frame on the instance's stream; the frame is already in device memory at (img,pitch)
-void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUtensorMap& tmap, int use_tma, uint8_t* d_mask_out, double lr) {
-    if(c->algo == LVB_ALGO_PAWCS) { paw_enqueue_frame(c, img, pitch, tmap, use_tma, d_mask_out, lr); return; }
+/// `mask_ready` (optional) is recorded on whichever stream produces d_mask_out, right behind the kernel that writes it
+void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUtensorMap& tmap, int use_tma, uint8_t* d_mask_out, double lr, cudaEvent_t mask_ready = nullptr) {
+    if(c->algo == LVB_ALGO_PAWCS) { paw_enqueue_frame(c, img, pitch, tmap, use_tma, d_mask_out, lr); if(mask_ready) CK(cudaEventRecord(mask_ready, c->stream)); return; }
     const int W = c->W, H = c->H, C = c->C;
     cudaStream_t st = c->stream;
     const bool sub = c->algo == LVB_ALGO_SUBSENSE;
     SubArgs A{};
     A.W = W; A.H = H; A.Wp = c->Wp; A.WW = c->WW; A.N = c->P.n_samples; A.REQ = c->P.n_required; A.plane = c->plane;
-    A.img = img; A.ipitch = pitch; A.bg_color = c->bg_color; A.bg_desc = c->bg_desc; A.maps = c->maps; A.fin = c->fin;
-    A.last_color = c->last_color; A.last_desc = sub ? c->last_desc : c->tmp_desc; A.roi_bits = c->roi_bits; A.raw_bits = c->raw; A.unstable_bits = c->unstable;
+    A.img = img; A.ipitch = pitch; A.bg_color = c->bg_color; A.bg_desc = c->bg_desc; A.maps = c->maps; A.fin = c->fin; A.hand = c->hand;
+    A.last_color = sub ? c->last_color_alt : c->last_color; A.last_desc = sub ? c->last_desc_alt : c->tmp_desc;
+    A.prev_color = c->last_color; A.prev_desc = c->last_desc; A.pending_seq = sub ? c->nb_seq : 0u; A.roi_bits = c->roi_bits; A.raw_bits = sub ? c->raw_alt : c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
-    A.intent_bits = c->intent_bits; A.intents = c->intents; A.bitplane = (size_t)H * c->WW; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
+    A.intents = c->intents; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
     A.magic = c->magic; A.lr_magic = magic_of(A.lr_fixed); A.lr2_magic = magic_of(A.lr_fixed / 2u + 1u);
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane;
-    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = A.last_desc; B.intents = c->intents;
-    PostArgs P{};
-    P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
-    P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv;
-    P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = A.last_desc; B.intents = c->intents; // LOBSTER
     const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c), mg(c->Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
 
-    auto mark = [&](const char* n) { if(c->trace_on && c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); c->trace.push_back({n, e}); } };
-    mark("frame_start");
+    auto mark = [&](cudaStream_t on, const char* n) { if(c->trace_on && c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, on); c->trace.push_back({n, e}); } };
+    mark(st, "frame_start");
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
     if(sub) {
-        if(c->lut_small) { if(C == 1) subsense_phaseA<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
-        else { if(C == 1) subsense_phaseA<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_phaseA<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
-        LAUNCHED();
-        if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
-        mark("phaseA");
-        // phase B only touches the sample model: it runs on the auxiliary stream beside the mask post-processing chain
+        // Three streams per frame k (see subsense.cuh):
+        //   instance stream : scan(k) -> [chain(k-1) done, motion(k) done] -> feedback(k) + frame tail -> phase B(k) -> conditional refresh(k)
+        //   mask stream     : [scan(k) done] -> blink/close -> holes -> median (mask out) -> completion counter -> dilate/blink -> final EMAs
+        //   auxiliary stream: frame-level motion analysis (needs only the input frame)
+        cudaStream_t sp = c->s_post;
+        const uint32_t seq = ++c->chain_seq;
         CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->s_aux>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->s_aux>>>(B);
-        LAUNCHED();
-        {   // frame-level motion analysis only needs the input frame: also off the critical path
+        {
             DownsampleArgs D{};
             D.W = W; D.H = H; D.CH = C; D.dsW = c->dsW; D.dsH = c->dsH; D.img = img; D.ipitch = pitch; D.dsLT = c->dsLT; D.dsST = c->dsST; D.ctl = c->ctl;
             const int nds = c->dsW * c->dsH;
@@ -592,28 +643,51 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
                 LAUNCHED();
             }
         }
-        CK(cudaEventRecord(c->ev_join, c->s_aux));
-        c->ghost_idx ^= 1;
-        pp_blink_close<<<wg, 256, 0, st>>>(P); LAUNCHED(); mark("pp_blink_close");
+        CK(cudaEventRecord(c->ev_ds, c->s_aux));
+        if(c->lut_small) { if(C == 1) subsense_scan<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_scan<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        else { if(C == 1) subsense_scan<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_scan<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        LAUNCHED();
+        if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
+        mark(st, "scan");
+        CK(cudaEventRecord(c->ev_scan, st));
+        // ---- mask stream: chain of frame k, reading raw(k), writing blinks(k) / lastfg(k) / fin(k) into the spare buffers
+        CK(cudaStreamWaitEvent(sp, c->ev_scan, 0));
+        PostArgs P{};
+        P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw_alt; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks_alt;
+        P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg_alt; P.dilinv = c->dilinv;
+        P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin_alt; P.fin_in = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+        P.frame = c->sub_frame; P.avg_samples = c->P.n_samples_for_moving_avgs;
+        pp_blink_close<<<wg, 256, 0, sp>>>(P); LAUNCHED(); mark(sp, "  post: blink_close");
         {
             HoleArgs Hh{};
-            Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw; Hh.comb = c->comb;
+            Hh.W = W; Hh.H = H; Hh.WW = c->WW; Hh.RS = c->uf_rs; Hh.pre = c->pre; Hh.raw = c->raw_alt; Hh.comb = c->comb;
             Hh.parent = c->uf_parent; Hh.rankbase = c->uf_rankbase;
             const int rb = (H + 7) / 8;
-            pp_holes_init<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_init");
-            pp_holes_union<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_union");
-            pp_holes_combine<<<rb, 256, 0, st>>>(Hh); LAUNCHED(); mark("pp_holes_combine");
+            pp_holes_init<<<rb, 256, 0, sp>>>(Hh); LAUNCHED();
+            pp_holes_union<<<rb, 256, 0, sp>>>(Hh); LAUNCHED();
+            pp_holes_combine<<<rb, 256, 0, sp>>>(Hh); LAUNCHED(); mark(sp, "  post: holes");
         }
-        pp_median<<<mg, tb, 0, st>>>(c->comb, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED(); mark("pp_median");
-        pp_dilate_blink<<<wg, 256, 0, st>>>(P); LAUNCHED(); mark("pp_dilate_blink");
-        pp_final_ema<<<tg, tb, 0, st>>>(P); LAUNCHED(); mark("pp_final_ema");
+        pp_median<<<mg, tb, 0, sp>>>(c->comb, c->lastfg_alt, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED(); mark(sp, "  post: median");
+        chain_done_kernel<<<1, 1, 0, sp>>>(c->ctl, seq); LAUNCHED();
+        if(mask_ready) CK(cudaEventRecord(mask_ready, sp));
+        pp_dilate_blink<<<wg, 256, 0, sp>>>(P); LAUNCHED();
+        pp_final_ema<<<tg, tb, 0, sp>>>(P); LAUNCHED(); mark(sp, "  post: final_ema");
+        // ---- instance stream: feedback(k) needs chain(k-1) (blinks / lastfg / fin of the previous frame) and the motion sum of frame k
+        if(c->post_pending) CK(cudaStreamWaitEvent(st, c->ev_post, 0));
+        CK(cudaStreamWaitEvent(st, c->ev_ds, 0));
         TailArgs T{};
         T.ctl = c->ctl; T.lut = c->lut; T.rel = c->P.rel_lbsp_threshold; T.lbsp_off = c->P.lbsp_threshold_offset; T.min_color = c->P.color_dist_threshold;
         T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed;
-        CK(cudaStreamWaitEvent(st, c->ev_join, 0)); // the tail reads the motion sum, the conditional refresh rewrites the model: after the aux stream
-        mark("join_aux");
-        subsense_tail_kernel<<<1, 256, 0, st>>>(T); LAUNCHED(); mark("subsense_tail_kernel");
-        launch_refresh(c); mark("refresh");
+        if(C == 1) subsense_feedback<1><<<tg, tb, 0, st>>>(A, T); else subsense_feedback<3><<<tg, tb, 0, st>>>(A, T);
+        LAUNCHED(); mark(st, "feedback");
+        CK(cudaEventRecord(c->ev_post, sp)); c->post_pending = true; // recorded after feedback(k) is enqueued; covers the whole chain of frame k
+        // the neighbour writes queued by feedback(k) ("phase B") are applied by scan(k+1), or by whoever needs the model first
+        c->nb_seq = seq;
+        std::swap(c->last_color, c->last_color_alt); std::swap(c->last_desc, c->last_desc_alt);
+        c->ghost_idx ^= 1;
+        std::swap(c->raw, c->raw_alt); std::swap(c->blinks, c->blinks_alt); std::swap(c->lastfg, c->lastfg_alt); std::swap(c->fin, c->fin_alt);
+        c->sub_frame += 1;
+        launch_refresh(c, seq); mark(st, "refresh"); // reads lastfg(k) (only when the frame tail requested it: polls the completion counter first)
     } else { // LOBSTER
         if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
@@ -625,6 +699,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         pp_median<<<mg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
         lobster_tail_kernel<<<1, 1, 0, st>>>(c->ctl); LAUNCHED();
         CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        if(mask_ready) CK(cudaEventRecord(mask_ready, st));
     }
     if(c->collect_stats) ++c->stat_frames;
 }
@@ -654,8 +729,7 @@ void apply_async(lvb_context* c, const uint8_t* img, uint8_t* mask, double lr) {
     CK(cudaMemcpy2DAsync(sl.d_img, c->ipitch, src, row, row, c->H, cudaMemcpyHostToDevice, c->s_in));
     CK(cudaEventRecord(sl.h2d_done, c->s_in));
     CK(cudaStreamWaitEvent(c->stream, sl.h2d_done, 0));
-    enqueue_frame(c, sl.d_img, c->ipitch, sl.tmap, sl.use_tma, sl.d_mask, lr);
-    CK(cudaEventRecord(sl.compute_done, c->stream));
+    enqueue_frame(c, sl.d_img, c->ipitch, sl.tmap, sl.use_tma, sl.d_mask, lr, sl.compute_done);
     CK(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
     sl.direct = is_pinned(mask);
     CK(cudaMemcpyAsync(sl.direct ? mask : sl.h_mask, sl.d_mask, (size_t)c->W * c->H, cudaMemcpyDeviceToHost, c->s_out));
@@ -675,7 +749,7 @@ bool sync_next(lvb_context* c) {
 }
 void sync(lvb_context* c) {
     while(sync_next(c)) {}
-    CK(cudaStreamSynchronize(c->stream));
+    sync_streams(c);
 }
 
 // ---- state export / import in the reference's layout (tests + checkpointing) ----
@@ -727,7 +801,8 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
     REQUIRE(c->initialized, "algo must be initialized first");
     REQUIRE(bytes == state_bytes(c, n), "size mismatch for state buffer " + n);
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    sync_streams(c);
+    flush_pending(c);
     const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
     const size_t npx = (size_t)W * H;
     if(c->algo == LVB_ALGO_PAWCS) {
@@ -859,7 +934,8 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
     REQUIRE(c->initialized, "algo must be initialized first");
     REQUIRE(bytes == state_bytes(c, n), "size mismatch for state buffer " + n);
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
+    sync_streams(c);
+    flush_pending(c);
     const int W = c->W, H = c->H, C = c->C, Wp = c->Wp, WW = c->WW;
     const size_t npx = (size_t)W * H;
     if(c->algo == LVB_ALGO_PAWCS) {
@@ -939,6 +1015,7 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             f.t_lower = (float)d[7]; f.t_upper = (float)d[8]; f.last_nonzero_ratio = (float)d[9];
             const uint32_t avg = (uint32_t)c->P.n_samples_for_moving_avgs;
             f.aLT = 1.0f / (float)std::min(f.frame_idx, avg); f.aST = 1.0f / (float)std::min(f.frame_idx, avg / 4u);
+            c->sub_frame = f.frame_idx;
         }
         put_ctl(c, f);
         return;
@@ -988,8 +1065,10 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             if(C == 1) h[(size_t)y * Wp + x] = s[(size_t)y * W + x]; else h[((size_t)y * Wp + x) * 4 + k] = s[((size_t)y * W + x) * C + k];
         }
     };
-    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes(), 0); pack_col((const uint8_t*)in, h.data()); h2d(c->stream, c->last_color, h.data(), h.size()); return; }
-    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); h2d(c->stream, c->last_desc, h.data(), h.size() * 2); return; }
+    if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes(), 0); pack_col((const uint8_t*)in, h.data()); h2d(c->stream, c->last_color, h.data(), h.size());
+                           if(c->last_color_alt) h2d(c->stream, c->last_color_alt, h.data(), h.size()); return; }
+    if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); h2d(c->stream, c->last_desc, h.data(), h.size() * 2);
+                          if(c->last_desc_alt) h2d(c->stream, c->last_desc_alt, h.data(), h.size() * 2); return; }
     if(n == "bg_color") {
         std::vector<uint8_t> h(c->plane * c->col_bytes(), 0);
         for(int s = 0; s < c->P.n_samples; ++s) {
@@ -1012,6 +1091,8 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
 void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
     REQUIRE(c->initialized, "algo must be initialized first");
     CK(cudaSetDevice(c->device));
+    sync_streams(c);
+    flush_pending(c);
     const size_t n = (size_t)c->W * c->H * c->C;
     uint8_t* dc = nullptr; uint16_t* dd = nullptr;
     if(out_color) dc = dalloc<uint8_t>(c->stream, n, false); else dd = dalloc<uint16_t>(c->stream, n, false);
@@ -1080,7 +1161,10 @@ int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lv
     // high priority: while phase B occupies the auxiliary (low-priority) stream the small mask kernels get SM slots first
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+    // three priority levels per instance: mask stream (highest: its small kernels must slip in beside the big ones) > instance
+    // stream > auxiliary stream (lowest)
+    const int prio_mid = prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_hi;
+    cudaError_t e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_mid);
     if(e != cudaSuccess) { delete c; CK(e); }
     *out = c;
     LVB_CATCH
@@ -1089,9 +1173,13 @@ int lvb_destroy(lvb_handle h) {
     if(!h) return 0;
     cudaSetDevice(h->device);
     if(h->stream) { cudaStreamSynchronize(h->stream); }
+    if(h->s_post) cudaStreamSynchronize(h->s_post);
+    if(h->s_aux) cudaStreamSynchronize(h->s_aux);
     h->free_all();
     for(auto& sl : h->slot) { if(sl.h2d_done) cudaEventDestroy(sl.h2d_done); if(sl.compute_done) cudaEventDestroy(sl.compute_done); if(sl.d2h_done) cudaEventDestroy(sl.d2h_done); }
     if(h->s_aux) cudaStreamDestroy(h->s_aux);
+    if(h->s_post) cudaStreamDestroy(h->s_post);
+    for(cudaEvent_t e : {h->ev_scan, h->ev_post, h->ev_ds, h->ev_mask}) if(e) cudaEventDestroy(e);
     if(h->ev_fork) cudaEventDestroy(h->ev_fork);
     if(h->ev_join) cudaEventDestroy(h->ev_join);
     if(h->s_in) cudaStreamDestroy(h->s_in);
@@ -1153,6 +1241,13 @@ int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t*
         h->ext_ptr = d_img; h->ext_pitch = d_step;
     }
     enqueue_frame(h, d_img, d_step, h->tmap_ext, h->ext_tma, d_mask ? d_mask : h->d_mask, lr);
+    LVB_CATCH
+}
+int lvb_flush(lvb_handle h) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    CK(cudaSetDevice(h->device));
+    if(h->post_pending) CK(cudaStreamWaitEvent(h->stream, h->ev_post, 0));
     LVB_CATCH
 }
 int lvb_get_background_image(lvb_handle h, uint8_t* out) {
@@ -1256,16 +1351,18 @@ int lvb_set_profile(lvb_handle h, int enabled) {
 int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches) {
     LVB_TRY
     if(h && !h->trace.empty()) {
-        CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream));
+        CK(cudaSetDevice(h->device)); sync_streams(h);
+        // completion time of every marked kernel relative to the start of ITS frame (marks sit on three streams), averaged over frames
         std::vector<std::pair<std::string, std::pair<double, int>>> agg;
-        for(size_t k = 1; k < h->trace.size(); ++k) {
-            if(std::string(h->trace[k].first) == "frame_start") continue;
-            float ms = 0; cudaEventElapsedTime(&ms, h->trace[k - 1].second, h->trace[k].second);
+        size_t start = 0;
+        for(size_t k = 0; k < h->trace.size(); ++k) {
+            if(std::string(h->trace[k].first) == "frame_start") { start = k; continue; }
+            float ms = 0; cudaEventElapsedTime(&ms, h->trace[start].second, h->trace[k].second);
             bool found = false;
             for(auto& a : agg) if(a.first == h->trace[k].first) { a.second.first += ms; a.second.second++; found = true; }
             if(!found) agg.push_back({h->trace[k].first, {ms, 1}});
         }
-        for(auto& a : agg) fprintf(stderr, "[lvb trace] %-22s %8.1f us\n", a.first.c_str(), a.second.first / a.second.second * 1e3);
+        for(auto& a : agg) fprintf(stderr, "[lvb trace] done at +%8.1f us  %s\n", a.second.first / a.second.second * 1e3, a.first.c_str());
         for(auto& t : h->trace) cudaEventDestroy(t.second);
         h->trace.clear();
     }

@@ -14,9 +14,11 @@ struct PostArgs {
     uint32_t* tmpA; uint32_t* pre; uint32_t* reach; uint32_t* comb;
     uint32_t* lastfg; uint32_t* dilinv; uint32_t* dil; // dil: optional copy of the dilated mask (PAWCS refreshModel reads it)
     uchar* out_mask; size_t out_pitch;
-    float2* fin;
+    float2* fin;               // final-segmentation EMAs (written)
+    const float2* fin_in;      // ... read (== fin unless the caller ping-pongs the map)
     FrameCtl* ctl;
     int median_k;
+    uint32_t frame; int avg_samples; // frame != 0: the EMA factors are derived from the frame index instead of being read from ctl
 };
 
 template<int FILL>
@@ -296,10 +298,12 @@ __global__ void __launch_bounds__(256) pp_dilate_blink(const PostArgs A) {
 __global__ void __launch_bounds__(256) pp_final_ema(const PostArgs A) {
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if(x >= A.W || y >= A.H) return;
-    const float aLT = A.ctl->aLT, aST = A.ctl->aST;
+    // the frame tail advances ctl->aLT/aST; a caller that runs this kernel beside the tail passes the frame index instead
+    const float aLT = A.frame ? __fdiv_rn(1.0f, (float)min(A.frame, (uint32_t)A.avg_samples)) : A.ctl->aLT;
+    const float aST = A.frame ? __fdiv_rn(1.0f, (float)min(A.frame, (uint32_t)A.avg_samples / 4u)) : A.ctl->aST;
     const double v = ((A.lastfg[(size_t)y * A.WW + (x >> 5)] >> (x & 31)) & 1u) ? 255.0 : 0.0;
     const size_t pix = (size_t)y * A.Wp + x;
-    float2 f = A.fin[pix];
+    float2 f = A.fin_in[pix];
     f.x = (float)__dadd_rn(__dmul_rn((double)f.x, (double)__fsub_rn(1.0f, aLT)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)aLT)));
     f.y = (float)__dadd_rn(__dmul_rn((double)f.y, (double)__fsub_rn(1.0f, aST)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)aST)));
     A.fin[pix] = f;

@@ -39,7 +39,11 @@ struct FrameCtl {
     uint32_t flood_changed[4];   // 3 rotating convergence flags of pp_flood (+1 pad)
     uint32_t roi_count;
     unsigned long long stat_scanned, stat_writes, stat_fg; // optional instrumentation
-    uint32_t pad[8];
+    uint32_t blocks_done;      // ticket counter of the feedback kernel (its last CTA runs the frame tail)
+    uint32_t refresh_blocks;   // ticket counter of the conditional refresh kernel (its last CTA retires the request)
+    uint32_t chain_done;       // sequence number of the last frame whose final mask (lastfg) is complete; written on the mask stream
+    uint32_t nb_applied_seq;   // sequence number of the last frame whose queued neighbour writes are already in the model
+    uint32_t pad[4];
 };
 
 template<int CH> struct Pack;
@@ -57,8 +61,11 @@ struct SubArgs {
     const uchar* img; size_t ipitch;  // current frame, interleaved bytes
     void* bg_color; void* bg_desc;
     float4* maps;              // 2 float4 per pixel
-    float2* fin;
-    void* last_color; void* last_desc;
+    const float2* fin;         // final-segmentation EMAs of the previous frame
+    uint2* hand;               // scan -> feedback hand-off word
+    void* last_color; void* last_desc;          // this frame's colour / intra descriptors (written by the scan)
+    const void* prev_color; const void* prev_desc; // previous frame's (read by the scan: D_last and the pending neighbour writes)
+    uint32_t pending_seq;      // frame whose queued neighbour writes (intents[]) the scan has to apply first (0: none)
     const uint32_t* roi_bits;
     uint32_t* raw_bits; uint32_t* unstable_bits; const uint32_t* blinks_bits; const uint32_t* lastfg_bits;
     const uint32_t* ghost_prev; uint32_t* ghost_cur;

@@ -137,8 +137,9 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
         if(valid) {
             const uint32_t* ctx = wctx + src * X::WORDS;
             const size_t at = (size_t)smp * A.plane + ctx[X::PIX];
-            const Col bc = ((const Col*)A.bg_color)[at];
-            const Desc bd = ((const Desc*)A.bg_desc)[at];
+            // .cg: these samples may have just been rewritten by the lane that owns the pixel (pending neighbour writes)
+            const Col bc = __ldcg((const Col*)A.bg_color + at);
+            const Desc bd = __ldcg((const Desc*)A.bg_desc + at);
             Lookup16 L[CH];
             uint32_t cur[CH], intra[CH];
 #pragma unroll
@@ -187,9 +188,16 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
 struct CtlSlice { float aLT, aST, t_lower, t_upper; uint32_t frame, cooldown, use3x3, pad; };
 constexpr int GHOST_ROWS = TILE_H + 2 * HALO;
 
+// The reference's per-pixel loop (SuBSENSE.cpp:201-481) is split in two kernels so that the mask post-processing chain of
+// frame k (which only needs the raw mask) runs on a side stream beside the feedback step of frame k and the scan of frame
+// k+1, instead of sitting between two frames:
+//   scan     (A1): LBSP + sample-consensus scan -> raw mask, per-pixel hand-off word, last colour / descriptor
+//   feedback (A2): D_min / T / v / R maps, stochastic own-sample write, queued neighbour write, frame tail (last CTA)
+// Hand-off (uint2 per pixel): x = minSum | minDesc << 16 ; y = good | lastL1 << 16 | lastHd << 24.
+
 template<int CH, bool T7>
 __global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
-subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
+subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef ScanCtx<CH> X;
@@ -199,63 +207,84 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     __shared__ uchar s_order[TILE_H][32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uchar s_lut[256];
-    __shared__ uint32_t s_cnt[5];                 // nonzero | scanned | writes | fg | warps done
-    __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
-    __shared__ uint32_t s_magic[257];             // floor(2^32 / n): x % ceil(T(x)) without a hardware divide
-    __shared__ CtlSlice s_ctl;
+    __shared__ uint32_t s_cnt[5];                 // nonzero | scanned | - | fg | warps done
+    // neighbour writes queued by the previous frame's feedback kernel ("phase B", folded in here): intent words of the tile + 2-px
+    // halo, and per target pixel the mask of 5x5 window positions whose source aims at it (bit = (dy+2)*5 + k = 24 - offset index)
+    constexpr int IW = TILE_W + 2 * HALO, IH = TILE_H + 2 * HALO;
+    __shared__ ushort s_int[IH][IW + 2];
+    __shared__ uint32_t s_hits[TILE_H][TILE_W];
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
-    // small per-frame tables the feedback step needs: fetched here, next to the state loads, so that no dependent DRAM/L2 round
-    // trip is left after the scan
     for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
-    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
     if(tid < 5) s_cnt[tid] = 0;
-    if(tid < GHOST_ROWS * 3) {
-        const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
-        s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
-    }
-    if(tid == 64) {
-        const FrameCtl* ctl = A.ctl;
-        CtlSlice cs;
-        cs.aLT = ctl->aLT; cs.aST = ctl->aST; cs.t_lower = ctl->t_lower; cs.t_upper = ctl->t_upper;
-        cs.frame = ctl->frame_idx; cs.cooldown = ctl->cooldown; cs.use3x3 = ctl->use3x3; cs.pad = 0;
-        s_ctl = cs;
-    }
+    s_hits[threadIdx.y][threadIdx.x] = 0;
+    const bool pending = A.pending_seq != 0u && A.ctl->nb_applied_seq != A.pending_seq;
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const bool in_img = (x < A.W) && (y < A.H);
     const int wi = y * A.WW + (x >> 5);
     const uint32_t lane_bit = 1u << (x & 31);
-    uint32_t w_roi = 0, w_unst = 0, w_blink = 0, w_lastfg = 0;
-    if(y < A.H && (x >> 5) < A.WW) {
-        w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; w_blink = A.blinks_bits[wi]; w_lastfg = A.lastfg_bits[wi];
-    }
+    uint32_t w_roi = 0, w_unst = 0;
+    if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; }
     const bool active = in_img && (w_roi & lane_bit);
     const size_t pix = (size_t)y * A.Wp + x;
 
     // every global load that does not depend on the input tile is issued before waiting for the TMA copy; the first
     // REQ (=2) samples are always scanned, so they are fetched up front instead of one DRAM round trip each
-    float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
-    float2 fin = make_float2(0, 0);
+    float R = 0.f;
     Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
     Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
     const Col* bgc = (const Col*)A.bg_color + pix;
     const Desc* bgd = (const Desc*)A.bg_desc + pix;
     if(active) {
-        m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1];
-        fin = A.fin[pix];
-        lc = ((const Col*)A.last_color)[pix];
-        ld = ((const Desc*)A.last_desc)[pix];
+        R = ((const float*)A.maps)[pix * 8 + 1];
+        lc = ((const Col*)A.prev_color)[pix];
+        ld = ((const Desc*)A.prev_desc)[pix];
         pre_c0 = bgc[0]; pre_d0 = bgd[0];
         if(A.N > 1) { pre_c1 = bgc[A.plane]; pre_d1 = bgd[A.plane]; }
     }
+    if(pending) {
+        // scatter inside the CTA: every intent of the tile + halo marks its target pixel (smem atomics) instead of every target
+        // scanning its 25 possible sources
+        __syncthreads(); // s_hits cleared
+        for(int i = tid; i < IW * IH; i += TILE_W * TILE_H) {
+            const int r = i / IW, cc = i - r * IW;
+            const int gx = x0 - HALO + cc, gy = y0 - HALO + r;
+            const uint32_t it = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? (uint32_t)A.intents[(size_t)gy * A.Wp + gx] : NO_INTENT;
+            s_int[r][cc] = (ushort)it;
+            if(it != NO_INTENT) {
+                const int code = (int)(it >> 8), oy = code / 5, ox = code - oy * 5; // target = source + (ox-2, oy-2)
+                const int tx = cc - 2 * HALO + ox, ty = r - 2 * HALO + oy;           // target inside the 32 x TILE_H core?
+                if(tx >= 0 && tx < TILE_W && ty >= 0 && ty < TILE_H) atomicOr(&s_hits[ty][tx], 1u << (24 - code));
+            }
+        }
+    }
     stage_tile_wait(&s_bar, A.use_tma);
 
-    bool is_fg = false, unstable_new = false, ghost_new = false, has_intent = false, nonzero = false;
-    uint32_t writes = 0;
-    uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
+    // apply the pending neighbour writes aimed at this pixel, in raster order of their source (ascending bit index), before
+    // anything reads the model: own stores are visible to own loads, the two prefetched samples are patched in registers, and
+    // the cooperative scan tail (other lanes of this warp read this pixel's samples) runs behind a fence
+    if(pending && in_img) {
+        uint32_t hits = s_hits[threadIdx.y][threadIdx.x];
+        const Col* pcol = (const Col*)A.prev_color;
+        const Desc* pdes = (const Desc*)A.prev_desc;
+        while(hits) {
+            const int i = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int r = i / 5, k = i - r * 5;
+            const uint32_t slot = s_int[threadIdx.y + r][threadIdx.x + k] & 0xFFu;
+            const size_t q = (size_t)(y + r - 2) * A.Wp + (x - 2 + k);
+            const Col c_ = pcol[q]; const Desc d_ = pdes[q];
+            ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = c_;
+            ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = d_;
+            if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
+            if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
+        }
+    }
+
+    bool is_fg = false, nonzero = false;
     const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
     const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
     uint32_t cur[CH], intra[CH];
@@ -263,7 +292,6 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     Col cur_pack = Col(); Desc intra_pack = Desc();
 
     if(active) {
-        const float R = m0.y;
         const bool unstable_old = (w_unst & lane_bit) != 0;
         // thresholds (SuBSENSE.cpp:222-223 / :355-359)
         uint32_t thrC = (uint32_t)(__fsub_rn(__fmul_rn(R, (float)A.min_color), (float)(unstable_old ? 0 : A.min_color / 5)));
@@ -297,17 +325,14 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             ctx[X::THRC] = thrC; ctx[X::THRD] = thrD; ctx[X::PIX] = (uint32_t)pix;
         }
     }
+    // the fence sits here, ~600 instructions after the stores it covers, so it normally finds them already performed
+    if(pending) __threadfence_block();
     subsense_scan_tail<CH, T7>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
     const uint32_t scanned = s;
 
     if(active) {
-        const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
-        const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
-        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
-        const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
-        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
-
-        // D_last (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
+        is_fg = good < REQ;
+        // distance to the previous frame (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
         uint32_t lastL1 = 0, lastHd = 0;
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
@@ -316,6 +341,170 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             lastHd += __popc(desc_get(ld, c) ^ intra[c]);
         }
         if(CH != 1) lastL1 &= 0xFFu;
+        uint32_t pc = 0;
+#pragma unroll
+        for(int c = 0; c < CH; ++c) pc += __popc(intra[c]);
+        nonzero = pc >= (CH == 1 ? 2u : 4u);
+        A.hand[pix] = make_uint2(minSum | (minDesc << 16), good | (lastL1 << 16) | (lastHd << 24));
+        ((Col*)A.last_color)[pix] = cur_pack;
+        ((Desc*)A.last_desc)[pix] = intra_pack;
+    }
+
+    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
+    const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
+    if(y < A.H && (x >> 5) < A.WW && threadIdx.x == 0) {
+        A.raw_bits[wi] = b_raw;
+        atomicAdd(&s_cnt[0], __popc(b_nz));
+    }
+    if(A.collect_stats) {
+        uint32_t sc = scanned;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o);
+        if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[3], __popc(b_raw)); }
+    }
+    // no closing barrier: the last warp of the CTA to get here publishes the CTA's counters (the others retire at once
+    // instead of idling behind the slowest scan tail)
+    if(threadIdx.x == 0) {
+        __threadfence_block();
+        if(atomicAdd(&s_cnt[4], 1u) == (uint32_t)TILE_H - 1u) {
+            __threadfence_block();
+            const uint32_t nz = atomicAdd(&s_cnt[0], 0u);
+            if(nz) atomicAdd(&A.ctl->nonzero_count, nz);
+            if(A.collect_stats) {
+                atomicAdd(&A.ctl->stat_scanned, (unsigned long long)atomicAdd(&s_cnt[1], 0u));
+                atomicAdd(&A.ctl->stat_fg, (unsigned long long)atomicAdd(&s_cnt[3], 0u));
+            }
+        }
+    }
+}
+
+/// frame tail (SuBSENSE.cpp:555-611): LUT +-1 adaptation, frame-level reset / learning-rate caps, next-frame factors.
+/// Executed by one warp: the last one of the last CTA of the feedback kernel.
+struct TailArgs {
+    FrameCtl* ctl; uchar* lut;
+    float rel; int lbsp_off; int min_color; int avg_samples; int N; int dsW, dsH;
+    uint64_t seed;
+};
+__device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
+    FrameCtl* ctl = A.ctl;
+    int dir = 0;
+    if(lane == 0) {
+        const float ratio = __fdiv_rn((float)ctl->nonzero_count, (float)ctl->roi_count);
+        const float last = ctl->last_nonzero_ratio;
+        dir = (ratio < 0.1f && last < 0.1f) ? -1 : (ratio > 0.5f && last > 0.5f) ? 1 : 0;
+        ctl->last_nonzero_ratio = ratio;
+        ctl->nonzero_count = 0;
+        ctl->do_refresh = 0; ctl->set_T_one = 0;
+        if(ctl->lr_scaling) {
+            const float diff_ratio = __fdiv_rn((float)ctl->tot_color_diff, (float)(A.dsW * A.dsH));
+            const uint32_t thr = (uint32_t)A.min_color / 2u;
+            if(ctl->auto_reset) {
+                if(ctl->frames_since_reset > 1000u) ctl->auto_reset = 0;
+                else if(diff_ratio >= (float)thr && ctl->cooldown == 0) {
+                    ctl->frames_since_reset = 0;
+                    // refreshModel(0.1f): (size_t)(0.1f*N) slots starting at a random position
+                    ctl->do_refresh = 1; ctl->set_T_one = 1; ctl->refresh_force = 0;
+                    ctl->refresh_count = (uint32_t)__fmul_rn(0.1f, (float)A.N);
+                    const uint32_t epoch = ctl->refresh_epoch;
+                    ctl->refresh_start = philox_draw(A.seed, epoch, 0, 0, DOM_REFRESH_START) % (uint32_t)A.N;
+                    ctl->cooldown = (uint32_t)A.avg_samples / 4u;
+                } else ctl->frames_since_reset += 1;
+            } else if(diff_ratio >= (float)(thr * 2u)) {
+                ctl->frames_since_reset = 0;
+                ctl->auto_reset = 1;
+            }
+            if(diff_ratio >= (float)(thr / 2u)) {
+                const int sh = (int)__fdiv_rn(diff_ratio, 2.0f);
+                ctl->t_lower = (float)max(sh < 31 ? (2 >> sh) : 0, 1);
+                ctl->t_upper = (float)max(sh < 31 ? (256 >> sh) : 0, 1);
+            } else { ctl->t_lower = 2.0f; ctl->t_upper = 256.0f; }
+            if(ctl->cooldown > 0) ctl->cooldown -= 1;
+            ctl->tot_color_diff = 0;
+        }
+        // next frame
+        const uint32_t f = ctl->frame_idx + 1;
+        ctl->frame_idx = f;
+        ctl->aLT = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples));
+        ctl->aST = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples / 4u));
+        ctl->blocks_done = 0;
+    }
+    dir = __shfl_sync(0xFFFFFFFFu, dir, 0);
+    for(int t = lane; t < 256; t += 32) {
+        if(dir < 0) {
+            const float lo = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, ceilf(__fdiv_rn(__fmul_rn((float)t, A.rel), 4.0f)))), 0.f), 255.f);
+            if((float)A.lut[t] > lo) A.lut[t] -= 1;
+        } else if(dir > 0) {
+            const float hi = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, __fmul_rn(255.0f, A.rel))), 0.f), 255.f);
+            if((float)A.lut[t] < hi) A.lut[t] += 1;
+        }
+    }
+}
+
+template<int CH>
+__global__ void __launch_bounds__(256)
+subsense_feedback(const SubArgs A, const TailArgs TA) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    static_assert(TILE_W * TILE_H == 256, "the feedback kernel (and the frame tail it hosts) is written for 256-thread CTAs");
+    __shared__ uint32_t s_cnt[2];                 // writes | warps done
+    __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
+    __shared__ uint32_t s_magic[257];             // floor(2^32 / n): x % ceil(T(x)) without a hardware divide
+    __shared__ CtlSlice s_ctl;
+
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
+    if(tid < 2) s_cnt[tid] = 0;
+    if(tid < GHOST_ROWS * 3) {
+        const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
+        s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
+    }
+    if(tid == 64) {
+        const FrameCtl* ctl = A.ctl;
+        CtlSlice cs;
+        cs.aLT = ctl->aLT; cs.aST = ctl->aST; cs.t_lower = ctl->t_lower; cs.t_upper = ctl->t_upper;
+        cs.frame = ctl->frame_idx; cs.cooldown = ctl->cooldown; cs.use3x3 = ctl->use3x3; cs.pad = 0;
+        s_ctl = cs;
+    }
+
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    const bool in_img = (x < A.W) && (y < A.H);
+    const int wi = y * A.WW + (x >> 5);
+    const uint32_t lane_bit = 1u << (x & 31);
+    uint32_t w_roi = 0, w_blink = 0, w_lastfg = 0;
+    if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_blink = A.blinks_bits[wi]; w_lastfg = A.lastfg_bits[wi]; }
+    const bool active = in_img && (w_roi & lane_bit);
+    const size_t pix = (size_t)y * A.Wp + x;
+
+    float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
+    float2 fin = make_float2(0, 0);
+    uint2 hand = make_uint2(0, 0);
+    Col cur_pack = Col(); Desc intra_pack = Desc();
+    if(active) {
+        m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1];
+        fin = A.fin[pix];
+        hand = A.hand[pix];
+        cur_pack = ((const Col*)A.last_color)[pix];   // this frame's colour / intra descriptor (written by the scan kernel)
+        intra_pack = ((const Desc*)A.last_desc)[pix];
+    }
+    __syncthreads();
+
+    bool unstable_new = false, ghost_new = false, has_intent = false;
+    uint32_t writes = 0;
+    uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
+    const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
+    const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
+
+    if(active) {
+        const uint32_t minSum = hand.x & 0xFFFFu, minDesc = hand.x >> 16, good = hand.y & 0xFFFFu, lastL1 = (hand.y >> 16) & 0xFFu, lastHd = hand.y >> 24;
+        const bool is_fg = good < REQ;
+        const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
+        const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
+        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
+        const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
+        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
+
+        // D_last (:254-255 / :396-397)
         const float normLast = __fmul_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 0.5f); // x/2 == x*0.5 exactly
         Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
 
@@ -323,8 +512,7 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
         const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
         const float baseMin = __fmul_rn(__fadd_rn(__fdiv_rn((float)minSum, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange)), 0.5f);
-        if(good < REQ) { // foreground (:256-269 / :398-413)
-            is_fg = true;
+        if(is_fg) { // foreground (:256-269 / :398-413)
             const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
             DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
             DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(normMin, aST));
@@ -387,50 +575,44 @@ subsense_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             R = __fsub_rn(R, __fdiv_rn(0.01f, V));
             if(R < 1.0f) R = 1.0f;
         }
-        uint32_t pc = 0;
-#pragma unroll
-        for(int c = 0; c < CH; ++c) pc += __popc(intra[c]);
-        nonzero = pc >= (CH == 1 ? 2u : 4u);
         ghost_new = (rawST > 0.995f) && (Dlast < 0.010f);
 
         A.maps[pix * 2] = make_float4(T, R, V, Dlast);
         A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
-        ((Col*)A.last_color)[pix] = cur_pack;
-        ((Desc*)A.last_desc)[pix] = intra_pack;
     }
 
     // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
-    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
     const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
     const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
-    const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
     if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame: phase B scans the plane without a has-intent mask
-    if(y < A.H && (x >> 5) < A.WW) {
-        if(threadIdx.x == 0) {
-            A.raw_bits[wi] = b_raw; A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost;
-            atomicAdd(&s_cnt[0], __popc(b_nz));
-        }
-    }
+    if(y < A.H && (x >> 5) < A.WW && threadIdx.x == 0) { A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; }
     if(A.collect_stats) {
-        uint32_t sc = scanned, wr = writes + (has_intent ? 1u : 0u);
+        uint32_t wr = writes + (has_intent ? 1u : 0u);
 #pragma unroll
-        for(int o = 16; o > 0; o >>= 1) { sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o); wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o); }
-        if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[2], wr); atomicAdd(&s_cnt[3], __popc(b_raw)); }
+        for(int o = 16; o > 0; o >>= 1) wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
+        if(threadIdx.x == 0) atomicAdd(&s_cnt[0], wr);
     }
-    // no closing barrier: the last warp of the CTA to get here publishes the CTA's counters (the others retire at once
-    // instead of idling behind the slowest scan tail)
+    // frame tail: the last warp of the CTA to get here takes the CTA's ticket, and the last CTA of the grid runs the tail with
+    // that one warp (every other CTA has read its FrameCtl slice long before it took its ticket). No CTA-wide barrier: warps
+    // retire as they finish instead of idling through the ticket's round trip.
+    uint32_t last_warp = 0;
     if(threadIdx.x == 0) {
         __threadfence_block();
-        if(atomicAdd(&s_cnt[4], 1u) == (uint32_t)TILE_H - 1u) {
-            __threadfence_block();
-            const uint32_t nz = atomicAdd(&s_cnt[0], 0u);
-            if(nz) atomicAdd(&A.ctl->nonzero_count, nz);
-            if(A.collect_stats) {
-                atomicAdd(&A.ctl->stat_scanned, (unsigned long long)atomicAdd(&s_cnt[1], 0u));
-                atomicAdd(&A.ctl->stat_writes, (unsigned long long)atomicAdd(&s_cnt[2], 0u));
-                atomicAdd(&A.ctl->stat_fg, (unsigned long long)atomicAdd(&s_cnt[3], 0u));
-            }
-        }
+        last_warp = atomicAdd(&s_cnt[1], 1u) == (uint32_t)TILE_H - 1u;
+    }
+    last_warp = __shfl_sync(0xFFFFFFFFu, last_warp, 0);
+    if(!last_warp) return;
+    uint32_t last_cta = 0;
+    if(threadIdx.x == 0) {
+        const uint32_t wr = atomicAdd(&s_cnt[0], 0u);
+        if(A.collect_stats && wr) atomicAdd(&A.ctl->stat_writes, (unsigned long long)wr);
+        // no device-wide fence: the tail only reads counters accumulated with atomics (by this grid) or by earlier kernels,
+        // and what it rewrites in FrameCtl was read by every CTA before that CTA's first barrier
+        last_cta = atomicAdd(&A.ctl->blocks_done, 1u) == gridDim.x * gridDim.y - 1u;
+    }
+    last_cta = __shfl_sync(0xFFFFFFFFu, last_cta, 0);
+    if(last_cta) {
+        subsense_tail_warp(TA, (int)threadIdx.x);
     }
 }
 
@@ -446,6 +628,7 @@ struct PhaseBArgs {
     const void* last_color;    // == this frame's colour for every pixel that queued a write
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
     const ushort* intents;
+    const FrameCtl* ctl; uint32_t pending_seq; // pending_seq != 0: skip when FrameCtl::nb_applied_seq says these writes are already in the model
 };
 
 template<int CH>
@@ -454,6 +637,7 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     typedef typename Pack<CH>::Desc Desc;
     constexpr int TW = 32 + 4, TH = 8 + 4;
     __shared__ ushort s_int[TH][TW + 2]; // +2: row pitch of 19 words (odd) keeps the 5-row column walk conflict-free
+    if(A.pending_seq != 0u && A.ctl->nb_applied_seq == A.pending_seq) return;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     for(int i = tid; i < TW * TH; i += 256) {
@@ -464,17 +648,42 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     __syncthreads();
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
+    // pass 1: which of the 25 sources aim at this pixel (no global access); bit i = window position i = (dy+2)*5 + k
+    uint32_t hits = 0;
 #pragma unroll
     for(int dy = -2; dy <= 2; ++dy) {
 #pragma unroll
         for(int k = 0; k < 5; ++k) {
             const uint32_t it = s_int[threadIdx.y + 2 + dy][threadIdx.x + k];
-            if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) {
-                const size_t qpix = (size_t)(y + dy) * A.Wp + (x - 2 + k);
-                const size_t dst = (size_t)(it & 0xFFu) * A.plane + (size_t)y * A.Wp + x;
-                ((Col*)A.bg_color)[dst] = ((const Col*)A.last_color)[qpix];
-                ((Desc*)A.bg_desc)[dst] = ((const Desc*)A.last_desc)[qpix];
-            }
+            if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) hits |= 1u << ((dy + 2) * 5 + k);
+        }
+    }
+    // pass 2: apply them in raster order of the source (ascending bit index), two per round so that the source loads of both
+    // are in flight together. A warp runs as many rounds as its busiest lane needs (1-2), not one per window position.
+    const Col* lcol = (const Col*)A.last_color;
+    const Desc* ldes = (const Desc*)A.last_desc;
+    const size_t tpix = (size_t)y * A.Wp + x;
+    while(hits) {
+        const int i0 = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int i1 = hits ? __ffs(hits) - 1 : -1;
+        if(i1 >= 0) hits &= hits - 1;
+        const int r0 = i0 / 5, k0 = i0 - r0 * 5;
+        const uint32_t it0 = s_int[threadIdx.y + r0][threadIdx.x + k0];
+        const size_t q0 = (size_t)(y + r0 - 2) * A.Wp + (x - 2 + k0);
+        const Col c0 = lcol[q0]; const Desc d0 = ldes[q0];
+        Col c1 = Col(); Desc d1 = Desc(); uint32_t it1 = 0;
+        if(i1 >= 0) {
+            const int r1 = i1 / 5, k1 = i1 - r1 * 5;
+            it1 = s_int[threadIdx.y + r1][threadIdx.x + k1];
+            const size_t q1 = (size_t)(y + r1 - 2) * A.Wp + (x - 2 + k1);
+            c1 = lcol[q1]; d1 = ldes[q1];
+        }
+        const size_t dst0 = (size_t)(it0 & 0xFFu) * A.plane + tpix;
+        ((Col*)A.bg_color)[dst0] = c0; ((Desc*)A.bg_desc)[dst0] = d0;
+        if(i1 >= 0) {
+            const size_t dst1 = (size_t)(it1 & 0xFFu) * A.plane + tpix;
+            ((Col*)A.bg_color)[dst1] = c1; ((Desc*)A.bg_desc)[dst1] = d1;
         }
     }
 }
@@ -492,24 +701,49 @@ struct RefreshArgs {
     FrameCtl* ctl;
     uint64_t seed;
     int recompute_desc;        // LOBSTER: descriptor of the sampled pixel is recomputed from last_color
+    uint32_t wait_seq;         // != 0: a requested refresh first waits until ctl->chain_done reaches this frame (lastfg complete)
+    const ushort* intents; uint32_t pending_seq; // SuBSENSE: neighbour writes of this frame not yet in the model are applied first
 };
 
 template<int CH>
 __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
-    const FrameCtl* ctl = A.ctl;
+    FrameCtl* ctl = A.ctl;
     if(!ctl->do_refresh) return;
-    // launched every frame with a small grid (the request is decided on the device): a CTA walks 32x8 tiles grid-stride
+    // launched every frame with a small grid (the request is decided on the device): a CTA walks 32x8 tiles grid-stride.
+    // The request is rare (scene change); when it fires, the last-foreground mask of THIS frame is still being produced on the
+    // mask stream, so the few resident CTAs of this grid poll the completion counter before reading it.
+    if(A.wait_seq) {
+        if(threadIdx.x == 0 && threadIdx.y == 0) {
+            volatile uint32_t* flag = &ctl->chain_done;
+            while((int32_t)(*flag - A.wait_seq) < 0) __nanosleep(500);
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    const bool apply_nb = A.pending_seq != 0u && ctl->nb_applied_seq != A.pending_seq;
     const int tiles_x = A.Wp / 32, ntiles = tiles_x * ((A.H + 7) / 8);
     for(int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int x = (tile % tiles_x) * 32 + threadIdx.x, y = (tile / tiles_x) * 8 + threadIdx.y;
     if(x >= A.W || y >= A.H) continue;
     const size_t pix = (size_t)y * A.Wp + x;
+    if(apply_nb && x >= 2 && y >= 2 && x <= A.W - 3 && y <= A.H - 3) {
+        // the reference applies the frame's neighbour writes inside its pixel loop, i.e. before refreshModel: same rule as phase B
+        for(int dy = -2; dy <= 2; ++dy) for(int k = 0; k < 5; ++k) {
+            const size_t q = (size_t)(y + dy) * A.Wp + (x - 2 + k);
+            const uint32_t it = A.intents[q];
+            if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) {
+                const size_t dst = (size_t)(it & 0xFFu) * A.plane + pix;
+                ((Col*)A.bg_color)[dst] = ((const Col*)A.last_color)[q];
+                ((Desc*)A.bg_desc)[dst] = ((const Desc*)A.last_desc)[q];
+            }
+        }
+    }
     if(ctl->set_T_one && A.maps) A.maps[pix * 2].x = 1.0f;
     if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) continue;
     const bool force = ctl->refresh_force != 0;
-    if(!force && ((A.lastfg_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) continue;
+    if(!force && ((__ldcg(A.lastfg_bits + y * A.WW + (x >> 5)) >> (x & 31)) & 1u)) continue;
     const uint32_t N = (uint32_t)A.N, start = ctl->refresh_start, count = ctl->refresh_count, epoch = ctl->refresh_epoch;
     const uint32_t pixid = (uint32_t)(y * A.W + x);
     const Col* lc = (const Col*)A.last_color;
@@ -521,7 +755,7 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
         const uint32_t r = (rs & 3) == 0 ? rnd.x : (rs & 3) == 1 ? rnd.y : (rs & 3) == 2 ? rnd.z : rnd.w;
         int sx, sy;
         sample_pos_7x7(r, sx, sy, x, y, A.W, A.H);
-        if(!force && ((A.lastfg_bits[sy * A.WW + (sx >> 5)] >> (sx & 31)) & 1u)) continue;
+        if(!force && ((__ldcg(A.lastfg_bits + sy * A.WW + (sx >> 5)) >> (sx & 31)) & 1u)) continue;
         const size_t sp = (size_t)sy * A.Wp + sx;
         const Col col = lc[sp];
         Desc d;
@@ -550,6 +784,15 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
         ((Col*)A.bg_color)[(size_t)rs * A.plane + pix] = col;
         ((Desc*)A.bg_desc)[(size_t)rs * A.plane + pix] = d;
     }
+    }
+    // the last CTA to finish retires the request (every CTA has read it by then) and bumps the epoch it consumed
+    __syncthreads();
+    if(threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence();
+        if(atomicAdd(&ctl->refresh_blocks, 1u) == gridDim.x - 1u) {
+            ctl->refresh_epoch += 1; ctl->do_refresh = 0; ctl->set_T_one = 0; ctl->refresh_blocks = 0;
+            if(A.pending_seq) ctl->nb_applied_seq = A.pending_seq;
+        }
     }
 }
 
@@ -594,70 +837,6 @@ __global__ void __launch_bounds__(128) downsample_motion_kernel(const Downsample
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xFFFFFFFFu, diff, o);
     if((threadIdx.x & 31) == 0 && diff) atomicAdd(&A.ctl->tot_color_diff, diff);
-}
-
-/// frame tail (SuBSENSE.cpp:555-611): LUT +-1 adaptation, frame-level reset / learning-rate caps, next-frame factors.
-struct TailArgs {
-    FrameCtl* ctl; uchar* lut;
-    float rel; int lbsp_off; int min_color; int avg_samples; int N; int dsW, dsH;
-    uint64_t seed;
-};
-__global__ void __launch_bounds__(256) subsense_tail_kernel(const TailArgs A) {
-    FrameCtl* ctl = A.ctl;
-    __shared__ int s_dir;
-    const int t = threadIdx.x;
-    if(t == 0) {
-        const float ratio = __fdiv_rn((float)ctl->nonzero_count, (float)ctl->roi_count);
-        const float last = ctl->last_nonzero_ratio;
-        s_dir = (ratio < 0.1f && last < 0.1f) ? -1 : (ratio > 0.5f && last > 0.5f) ? 1 : 0;
-        ctl->last_nonzero_ratio = ratio;
-        ctl->nonzero_count = 0;
-        ctl->do_refresh = 0; ctl->set_T_one = 0;
-        if(ctl->lr_scaling) {
-            const float diff_ratio = __fdiv_rn((float)ctl->tot_color_diff, (float)(A.dsW * A.dsH));
-            const uint32_t thr = (uint32_t)A.min_color / 2u;
-            if(ctl->auto_reset) {
-                if(ctl->frames_since_reset > 1000u) ctl->auto_reset = 0;
-                else if(diff_ratio >= (float)thr && ctl->cooldown == 0) {
-                    ctl->frames_since_reset = 0;
-                    // refreshModel(0.1f): (size_t)(0.1f*N) slots starting at a random position
-                    ctl->do_refresh = 1; ctl->set_T_one = 1; ctl->refresh_force = 0;
-                    ctl->refresh_count = (uint32_t)__fmul_rn(0.1f, (float)A.N);
-                    const uint32_t epoch = ctl->refresh_epoch;
-                    ctl->refresh_start = philox_draw(A.seed, epoch, 0, 0, DOM_REFRESH_START) % (uint32_t)A.N;
-                    ctl->cooldown = (uint32_t)A.avg_samples / 4u;
-                } else ctl->frames_since_reset += 1;
-            } else if(diff_ratio >= (float)(thr * 2u)) {
-                ctl->frames_since_reset = 0;
-                ctl->auto_reset = 1;
-            }
-            if(diff_ratio >= (float)(thr / 2u)) {
-                const int sh = (int)__fdiv_rn(diff_ratio, 2.0f);
-                ctl->t_lower = (float)max(sh < 31 ? (2 >> sh) : 0, 1);
-                ctl->t_upper = (float)max(sh < 31 ? (256 >> sh) : 0, 1);
-            } else { ctl->t_lower = 2.0f; ctl->t_upper = 256.0f; }
-            if(ctl->cooldown > 0) ctl->cooldown -= 1;
-            ctl->tot_color_diff = 0;
-        }
-        // next frame
-        const uint32_t f = ctl->frame_idx + 1;
-        ctl->frame_idx = f;
-        ctl->aLT = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples));
-        ctl->aST = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples / 4u));
-    }
-    __syncthreads();
-    const int dir = s_dir;
-    if(dir < 0) {
-        const float lo = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, ceilf(__fdiv_rn(__fmul_rn((float)t, A.rel), 4.0f)))), 0.f), 255.f);
-        if((float)A.lut[t] > lo) A.lut[t] -= 1;
-    } else if(dir > 0) {
-        const float hi = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, __fmul_rn(255.0f, A.rel))), 0.f), 255.f);
-        if((float)A.lut[t] < hi) A.lut[t] += 1;
-    }
-}
-/// runs after the conditional refresh: bump the epoch it consumed and drop the request
-__global__ void refresh_done_kernel(FrameCtl* ctl) {
-    if(ctl->do_refresh) { ctl->refresh_epoch += 1; ctl->do_refresh = 0; ctl->set_T_one = 0; }
 }
 
 } // namespace lvb

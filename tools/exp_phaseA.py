@@ -32,6 +32,7 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(stream)
 for _ in range(100):
     step()
+sub.flush()
 e1.record(stream)
 torch.cuda.synchronize()
 frame_ms = e0.elapsed_time(e1) / 100
