@@ -99,7 +99,7 @@ struct lvb_context {
     uint8_t* d_mask = nullptr;
     uint8_t* h_img = nullptr; uint8_t* h_mask = nullptr; uint8_t* user_mask = nullptr;
     // model + maps
-    void* bg_color = nullptr; void* bg_desc = nullptr;
+    void* bg = nullptr;       // sample records [N][H][Wp] (Pack<C>::Rec: 16 bytes for 3 channels, 4 for 1)
     float4* maps = nullptr; float2* fin = nullptr;
     void* last_color = nullptr; void* last_desc = nullptr; void* tmp_desc = nullptr;
     // SuBSENSE: the scan of frame k+1 applies the neighbour writes queued by frame k, whose sources are frame k's colours and
@@ -152,12 +152,13 @@ struct lvb_context {
 
     size_t col_bytes() const { return C == 1 ? 1 : 4; }
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
+    size_t rec_bytes() const { return C == 1 ? 4 : 16; }
 
     void free_all() {
-        void* ptrs[] = {last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg_color, bg_desc, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
-        d_img = nullptr; d_mask = nullptr; bg_color = bg_desc = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
+        d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
         last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
@@ -215,7 +216,7 @@ void flush_pending(lvb_context* c) {
     if(c->algo != LVB_ALGO_SUBSENSE || !c->initialized || c->nb_seq == 0) return;
     PhaseBArgs B{};
     B.W = c->W; B.H = c->H; B.Wp = c->Wp; B.WW = c->WW; B.CH = c->C; B.plane = c->plane;
-    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents;
+    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents;
     B.ctl = c->ctl; B.pending_seq = c->nb_seq;
     const dim3 tg(c->Wp / 32, (c->H + 7) / 8), tb(32, 8);
     if(c->C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->stream>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->stream>>>(B);
@@ -228,7 +229,7 @@ void flush_pending(lvb_context* c) {
 void launch_refresh(lvb_context* c, uint32_t wait_seq = 0) {
     RefreshArgs R{};
     R.W = c->W; R.H = c->H; R.Wp = c->Wp; R.WW = c->WW; R.CH = c->C; R.N = c->P.n_samples; R.plane = c->plane;
-    R.bg_color = c->bg_color; R.bg_desc = c->bg_desc; R.last_color = c->last_color; R.last_desc = c->last_desc;
+    R.bg = c->bg; R.last_color = c->last_color; R.last_desc = c->last_desc;
     R.roi_bits = c->roi_bits; R.lastfg_bits = c->lastfg; R.maps = c->algo == LVB_ALGO_SUBSENSE ? c->maps : nullptr;
     R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
     const dim3 tgd = tile_grid(c);
@@ -435,8 +436,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         }
     }
     if(c->algo != LVB_ALGO_PAWCS) {
-        c->bg_color = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->col_bytes());
-        c->bg_desc = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->desc_bytes());
+        c->bg = dalloc<uint8_t>(c->stream, (size_t)N * c->plane * c->rec_bytes());
     }
     c->last_color = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
     c->last_desc = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
@@ -608,7 +608,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     const bool sub = c->algo == LVB_ALGO_SUBSENSE;
     SubArgs A{};
     A.W = W; A.H = H; A.Wp = c->Wp; A.WW = c->WW; A.N = c->P.n_samples; A.REQ = c->P.n_required; A.plane = c->plane;
-    A.img = img; A.ipitch = pitch; A.bg_color = c->bg_color; A.bg_desc = c->bg_desc; A.maps = c->maps; A.fin = c->fin; A.hand = c->hand;
+    A.img = img; A.ipitch = pitch; A.bg = c->bg; A.maps = c->maps; A.fin = c->fin; A.hand = c->hand;
     A.last_color = sub ? c->last_color_alt : c->last_color; A.last_desc = sub ? c->last_desc_alt : c->tmp_desc;
     A.prev_color = c->last_color; A.prev_desc = c->last_desc; A.pending_seq = sub ? c->nb_seq : 0u; A.roi_bits = c->roi_bits; A.raw_bits = sub ? c->raw_alt : c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
@@ -619,7 +619,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.magic = c->magic; A.lr_magic = magic_of(A.lr_fixed); A.lr2_magic = magic_of(A.lr_fixed / 2u + 1u);
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane;
-    B.bg_color = c->bg_color; B.bg_desc = c->bg_desc; B.last_color = c->last_color; B.last_desc = A.last_desc; B.intents = c->intents; // LOBSTER
+    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = A.last_desc; B.intents = c->intents; // LOBSTER
     const dim3 tg = tile_grid(c), tb(32, 8), wg = word_grid(c), mg(c->Wp / 32, (H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
 
     auto mark = [&](cudaStream_t on, const char* n) { if(c->trace_on && c->profile) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, on); c->trace.push_back({n, e}); } };
@@ -911,19 +911,17 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
     };
     if(n == "lastcolor") { std::vector<uint8_t> h(c->plane * c->col_bytes()); d2h(c->stream, h.data(), c->last_color, h.size()); unpack_col(h.data(), (uint8_t*)out); return; }
     if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2); d2h(c->stream, h.data(), c->last_desc, h.size() * 2); unpack_desc(h.data(), (uint16_t*)out); return; }
-    if(n == "bg_color") {
-        std::vector<uint8_t> h(c->plane * c->col_bytes());
+    if(n == "bg_color" || n == "bg_desc") { // one plane of sample records at a time: colour = bytes 0..C-1, descriptors = u16 at byte 4 (3ch) / 2 (1ch)
+        const size_t rb = c->rec_bytes(), doff = C == 1 ? 2 : 4;
+        std::vector<uint8_t> h(c->plane * rb);
         for(int s = 0; s < c->P.n_samples; ++s) {
-            d2h(c->stream, h.data(), (uint8_t*)c->bg_color + (size_t)s * h.size(), h.size());
-            unpack_col(h.data(), (uint8_t*)out + (size_t)s * npx * C);
-        }
-        return;
-    }
-    if(n == "bg_desc") {
-        std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2);
-        for(int s = 0; s < c->P.n_samples; ++s) {
-            d2h(c->stream, h.data(), (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.size() * 2);
-            unpack_desc(h.data(), (uint16_t*)out + (size_t)s * npx * C);
+            d2h(c->stream, h.data(), (uint8_t*)c->bg + (size_t)s * h.size(), h.size());
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k) {
+                const uint8_t* r = h.data() + ((size_t)y * Wp + x) * rb;
+                const size_t o = (size_t)s * npx * C + ((size_t)y * W + x) * C + k;
+                if(n == "bg_color") ((uint8_t*)out)[o] = r[k];
+                else { uint16_t v; std::memcpy(&v, r + doff + 2 * k, 2); ((uint16_t*)out)[o] = v; }
+            }
         }
         return;
     }
@@ -1069,19 +1067,18 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
                            if(c->last_color_alt) h2d(c->stream, c->last_color_alt, h.data(), h.size()); return; }
     if(n == "lastdesc") { std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0); pack_desc((const uint16_t*)in, h.data()); h2d(c->stream, c->last_desc, h.data(), h.size() * 2);
                           if(c->last_desc_alt) h2d(c->stream, c->last_desc_alt, h.data(), h.size() * 2); return; }
-    if(n == "bg_color") {
-        std::vector<uint8_t> h(c->plane * c->col_bytes(), 0);
+    if(n == "bg_color" || n == "bg_desc") { // read-modify-write of the record planes (the other half of each record is kept)
+        const size_t rb = c->rec_bytes(), doff = C == 1 ? 2 : 4;
+        std::vector<uint8_t> h(c->plane * rb);
         for(int s = 0; s < c->P.n_samples; ++s) {
-            pack_col((const uint8_t*)in + (size_t)s * npx * C, h.data());
-            h2d(c->stream, (uint8_t*)c->bg_color + (size_t)s * h.size(), h.data(), h.size());
-        }
-        return;
-    }
-    if(n == "bg_desc") {
-        std::vector<uint16_t> h(c->plane * c->desc_bytes() / 2, 0);
-        for(int s = 0; s < c->P.n_samples; ++s) {
-            pack_desc((const uint16_t*)in + (size_t)s * npx * C, h.data());
-            h2d(c->stream, (uint8_t*)c->bg_desc + (size_t)s * h.size() * 2, h.data(), h.size() * 2);
+            d2h(c->stream, h.data(), (uint8_t*)c->bg + (size_t)s * h.size(), h.size());
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int k = 0; k < C; ++k) {
+                uint8_t* r = h.data() + ((size_t)y * Wp + x) * rb;
+                const size_t o = (size_t)s * npx * C + ((size_t)y * W + x) * C + k;
+                if(n == "bg_color") r[k] = ((const uint8_t*)in)[o];
+                else { const uint16_t v = ((const uint16_t*)in)[o]; std::memcpy(r + doff + 2 * k, &v, 2); }
+            }
+            h2d(c->stream, (uint8_t*)c->bg + (size_t)s * h.size(), h.data(), h.size());
         }
         return;
     }
@@ -1100,8 +1097,8 @@ void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
         const PawArgs A = paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0);
         if(c->C == 1) pawcs_background_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1); else pawcs_background_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1);
     }
-    else if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
-    else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg_color, c->bg_desc, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
+    else if(c->C == 1) background_image_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
+    else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if(e == cudaSuccess) e = out_color ? cudaMemcpyAsync(out_color, dc, n, cudaMemcpyDeviceToHost, c->stream) : cudaMemcpyAsync(out_desc, dd, n * 2, cudaMemcpyDeviceToHost, c->stream);

@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(TILE_W * TILE_H)
 lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     constexpr int PITCH = tile_pitch(CH);
     __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
     __shared__ __align__(8) uint64_t s_bar;
@@ -49,11 +50,11 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         Lookup16 L[CH];
 #pragma unroll
         for(int c = 0; c < CH; ++c) L[c] = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
-        const Col* bgc = (const Col*)A.bg_color + pix;
-        const Desc* bgd = (const Desc*)A.bg_desc + pix;
+        const Rec* bgr = (const Rec*)A.bg + pix;
         uint32_t good = 0, s = 0;
         while(good < REQ && s < N) { // LOBSTER.cpp:481-495 / :533-553
-            const Col bc = bgc[(size_t)s * A.plane];
+            const Rec rec = bgr[(size_t)s * A.plane];
+            const Col bc = rec_col(rec);
             bool ok = true;
             uint32_t tc = 0;
 #pragma unroll
@@ -64,7 +65,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 tc += cd;
             }
             if(ok) {
-                const Desc bd = bgd[(size_t)s * A.plane];
+                const Desc bd = rec_desc(rec);
                 uint32_t td = 0;
 #pragma unroll
                 for(int c = 0; c < CH; ++c) {
@@ -94,8 +95,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 if constexpr (CH == 1) intra_pack = (ushort)intra[0]; else intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]);
                 if(own) {
                     const uint32_t slot = rnd.y % N;
-                    ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
-                    ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                    ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
                     ++writes;
                 }
                 if(nb) {
@@ -145,6 +145,7 @@ template<int CH>
 __global__ void __launch_bounds__(TILE_W * TILE_H) init_frame_kernel(const InitArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     constexpr int PITCH = tile_pitch(CH);
     __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
     __shared__ __align__(8) uint64_t s_bar;
@@ -173,10 +174,11 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) init_frame_kernel(const InitA
 /// getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649, LOBSTER.cpp:583-620):
 /// float mean accumulated sample by sample (x/N each), converted round-half-even with saturation
 template<int CH>
-__global__ void __launch_bounds__(256) background_image_kernel(const void* bg_color, const void* bg_desc, size_t plane, int N, int W, int H, int Wp,
+__global__ void __launch_bounds__(256) background_image_kernel(const void* bg, size_t plane, int N, int W, int H, int Wp,
                                                                 uchar* out_color, ushort* out_desc) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
     if(x >= W || y >= H) return;
     const size_t pix = (size_t)y * Wp + x, o = ((size_t)y * W + x) * CH;
@@ -185,11 +187,11 @@ __global__ void __launch_bounds__(256) background_image_kernel(const void* bg_co
     for(int c = 0; c < CH; ++c) acc[c] = 0.f;
     for(int s = 0; s < N; ++s) {
         if(out_color) {
-            const Col v = ((const Col*)bg_color)[(size_t)s * plane + pix];
+            const Col v = rec_col(((const Rec*)bg)[(size_t)s * plane + pix]);
 #pragma unroll
             for(int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], __fdiv_rn((float)col_get(v, c), (float)N));
         } else {
-            const Desc v = ((const Desc*)bg_desc)[(size_t)s * plane + pix];
+            const Desc v = rec_desc(((const Rec*)bg)[(size_t)s * plane + pix]);
 #pragma unroll
             for(int c = 0; c < CH; ++c) acc[c] = __fadd_rn(acc[c], __fdiv_rn((float)desc_get(v, c), (float)N));
         }

@@ -46,9 +46,18 @@ struct FrameCtl {
     uint32_t pad[4];
 };
 
+// One background sample = one naturally aligned record (colour + descriptors): 16 bytes for 3 channels, 4 bytes for 1.
+// A stochastic sample update is then ONE partial-sector write instead of two (scattered 32-byte read-modify-writes are what
+// the update kernels pay for in DRAM), and a lone sample fetched by the scan tail is one sector instead of two.
 template<int CH> struct Pack;
-template<> struct Pack<3> { typedef uint32_t Col; typedef uint2 Desc; };
-template<> struct Pack<1> { typedef uchar Col; typedef ushort Desc; };
+template<> struct Pack<3> { typedef uint32_t Col; typedef uint2 Desc; typedef uint4 Rec; };
+template<> struct Pack<1> { typedef uchar Col; typedef ushort Desc; typedef uint32_t Rec; };
+__device__ __forceinline__ uint4 rec_make(uint32_t c, uint2 d) { return make_uint4(c, d.x, d.y, 0u); }
+__device__ __forceinline__ uint32_t rec_make(uchar c, ushort d) { return (uint32_t)c | ((uint32_t)d << 16); }
+__device__ __forceinline__ uint32_t rec_col(const uint4& r) { return r.x; }
+__device__ __forceinline__ uint2 rec_desc(const uint4& r) { return make_uint2(r.y, r.z); }
+__device__ __forceinline__ uchar rec_col(const uint32_t& r) { return (uchar)(r & 0xFFu); }
+__device__ __forceinline__ ushort rec_desc(const uint32_t& r) { return (ushort)(r >> 16); }
 
 __device__ __forceinline__ uint32_t desc_get(const uint2& d, int c) { return c == 0 ? (d.x & 0xFFFFu) : c == 1 ? (d.x >> 16) : (d.y & 0xFFFFu); }
 __device__ __forceinline__ uint32_t desc_get(const ushort& d, int) { return d; }
@@ -59,7 +68,7 @@ struct SubArgs {
     int W, H, Wp, WW, N, REQ;
     size_t plane;              // H*Wp
     const uchar* img; size_t ipitch;  // current frame, interleaved bytes
-    void* bg_color; void* bg_desc;
+    void* bg;                  // sample records [N][H][Wp]
     float4* maps;              // 2 float4 per pixel
     const float2* fin;         // final-segmentation EMAs of the previous frame
     uint2* hand;               // scan -> feedback hand-off word

@@ -116,6 +116,7 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
                                                    uint32_t N, uint32_t REQ, uint32_t& good, uint32_t& s, uint32_t& minDesc, uint32_t& minSum) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     typedef ScanCtx<CH> X;
     const uint32_t FULL = 0xFFFFFFFFu, lane = threadIdx.x;
     uint32_t m = __ballot_sync(FULL, undecided);
@@ -138,8 +139,8 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
             const uint32_t* ctx = wctx + src * X::WORDS;
             const size_t at = (size_t)smp * A.plane + ctx[X::PIX];
             // .cg: these samples may have just been rewritten by the lane that owns the pixel (pending neighbour writes)
-            const Col bc = __ldcg((const Col*)A.bg_color + at);
-            const Desc bd = __ldcg((const Desc*)A.bg_desc + at);
+            const Rec rec = __ldcg((const Rec*)A.bg + at);
+            const Col bc = rec_col(rec); const Desc bd = rec_desc(rec);
             Lookup16 L[CH];
             uint32_t cur[CH], intra[CH];
 #pragma unroll
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
 subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     typedef ScanCtx<CH> X;
     constexpr int PITCH = tile_pitch(CH);
     __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
@@ -236,14 +238,13 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     float R = 0.f;
     Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
     Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
-    const Col* bgc = (const Col*)A.bg_color + pix;
-    const Desc* bgd = (const Desc*)A.bg_desc + pix;
+    const Rec* bgr = (const Rec*)A.bg + pix;
     if(active) {
         R = ((const float*)A.maps)[pix * 8 + 1];
         lc = ((const Col*)A.prev_color)[pix];
         ld = ((const Desc*)A.prev_desc)[pix];
-        pre_c0 = bgc[0]; pre_d0 = bgd[0];
-        if(A.N > 1) { pre_c1 = bgc[A.plane]; pre_d1 = bgd[A.plane]; }
+        { const Rec r0 = bgr[0]; pre_c0 = rec_col(r0); pre_d0 = rec_desc(r0); }
+        if(A.N > 1) { const Rec r1 = bgr[A.plane]; pre_c1 = rec_col(r1); pre_d1 = rec_desc(r1); }
     }
     if(pending) {
         // scatter inside the CTA: every intent of the tile + halo marks its target pixel (smem atomics) instead of every target
@@ -277,8 +278,7 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             const uint32_t slot = s_int[threadIdx.y + r][threadIdx.x + k] & 0xFFu;
             const size_t q = (size_t)(y + r - 2) * A.Wp + (x - 2 + k);
             const Col c_ = pcol[q]; const Desc d_ = pdes[q];
-            ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = c_;
-            ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = d_;
+            ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(c_, d_);
             if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
             if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
         }
@@ -445,6 +445,7 @@ __global__ void __launch_bounds__(256)
 subsense_feedback(const SubArgs A, const TailArgs TA) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     static_assert(TILE_W * TILE_H == 256, "the feedback kernel (and the frame tail it hosts) is written for 256-thread CTAs");
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
     __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
@@ -520,8 +521,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
             if(cooldown && (rnd.x % 2u) == 0) {
                 const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-                ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
-                ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
                 ++writes;
             }
         } else { // background (:270-301 / :414-450)
@@ -537,8 +537,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             const bool fastm = A.lr_fixed || tab;
             if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
                 const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-                ((Col*)A.bg_color)[(size_t)slot * A.plane + pix] = cur_pack;
-                ((Desc*)A.bg_desc)[(size_t)slot * A.plane + pix] = intra_pack;
+                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
                 ++writes;
             }
             const bool cur3 = use3x3 && !unstable_new;
@@ -624,7 +623,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
 struct PhaseBArgs {
     int W, H, Wp, WW, CH;
     size_t plane;
-    void* bg_color; void* bg_desc;
+    void* bg;
     const void* last_color;    // == this frame's colour for every pixel that queued a write
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
     const ushort* intents;
@@ -635,6 +634,7 @@ template<int CH>
 __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     constexpr int TW = 32 + 4, TH = 8 + 4;
     __shared__ ushort s_int[TH][TW + 2]; // +2: row pitch of 19 words (odd) keeps the 5-row column walk conflict-free
     if(A.pending_seq != 0u && A.ctl->nb_applied_seq == A.pending_seq) return;
@@ -680,10 +680,10 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
             c1 = lcol[q1]; d1 = ldes[q1];
         }
         const size_t dst0 = (size_t)(it0 & 0xFFu) * A.plane + tpix;
-        ((Col*)A.bg_color)[dst0] = c0; ((Desc*)A.bg_desc)[dst0] = d0;
+        ((Rec*)A.bg)[dst0] = rec_make(c0, d0);
         if(i1 >= 0) {
             const size_t dst1 = (size_t)(it1 & 0xFFu) * A.plane + tpix;
-            ((Col*)A.bg_color)[dst1] = c1; ((Desc*)A.bg_desc)[dst1] = d1;
+            ((Rec*)A.bg)[dst1] = rec_make(c1, d1);
         }
     }
 }
@@ -693,7 +693,7 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
 struct RefreshArgs {
     int W, H, Wp, WW, CH, N;
     size_t plane;
-    void* bg_color; void* bg_desc;
+    void* bg;
     const void* last_color; void* last_desc;
     const uint32_t* roi_bits; const uint32_t* lastfg_bits;
     float4* maps;
@@ -709,6 +709,7 @@ template<int CH>
 __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
     FrameCtl* ctl = A.ctl;
     if(!ctl->do_refresh) return;
     // launched every frame with a small grid (the request is decided on the device): a CTA walks 32x8 tiles grid-stride.
@@ -735,8 +736,7 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
             const uint32_t it = A.intents[q];
             if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) {
                 const size_t dst = (size_t)(it & 0xFFu) * A.plane + pix;
-                ((Col*)A.bg_color)[dst] = ((const Col*)A.last_color)[q];
-                ((Desc*)A.bg_desc)[dst] = ((const Desc*)A.last_desc)[q];
+                ((Rec*)A.bg)[dst] = rec_make(((const Col*)A.last_color)[q], ((const Desc*)A.last_desc)[q]);
             }
         }
     }
@@ -781,8 +781,7 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
             if constexpr (CH == 1) d = (ushort)dd[0]; else d = make_uint2(dd[0] | (dd[1] << 16), dd[2]);
             ((Desc*)A.last_desc)[sp] = d; // idempotent: a pure function of last_color
         } else d = ((const Desc*)A.last_desc)[sp];
-        ((Col*)A.bg_color)[(size_t)rs * A.plane + pix] = col;
-        ((Desc*)A.bg_desc)[(size_t)rs * A.plane + pix] = d;
+        ((Rec*)A.bg)[(size_t)rs * A.plane + pix] = rec_make(col, d);
     }
     }
     // the last CTA to finish retires the request (every CTA has read it by then) and bumps the epoch it consumed
