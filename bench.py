@@ -143,7 +143,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -211,24 +211,35 @@ def main():
     launches = lv.kernel_launch_count() - l0
     clocks = sampler.stop()
 
-    # dominant kernel (phase A): per-launch CUDA-event timing on its own stream + the algorithmic bytes it moved
+    # dominant kernels: per-launch CUDA-event timing on the instance stream + the algorithmic bytes they moved. The reference's
+    # per-pixel loop is two kernels here (scan: LBSP + sample consensus; feedback: maps + stochastic updates), so SURVEY.md §8(d)'s
+    # per-pixel figure B_alg = 131 + 9(s+u) is split between them: B_scan = 27 + 9 s + 9 u_nb, B_fb = 104 + 9 u_own.
     sub.set_profile(True)
     sub.set_collect_stats(True)
     nprof = max(20, min(args.steps, 100))
+    t_prof0 = torch.cuda.Event(enable_timing=True); t_prof1 = torch.cuda.Event(enable_timing=True)
+    t_prof0.record(stream)
     for _ in range(nprof):
         step_device()
+    sub.flush(); t_prof1.record(stream)
     torch.cuda.synchronize()
     pa_ms, pa_n = sub.get_profile()
+    fb_ms, fb_n = sub.get_profile_feedback()
     st = sub.stats()
     sub.set_profile(False)
     sub.set_collect_stats(False)
     roi_px = st["roi_px"] / max(st["frames"], 1)
     sbar = st["samples_scanned"] / max(st["roi_px"], 1)
     u = st["sample_writes"] / max(st["roi_px"], 1)
+    u_nb = u / 2.0                               # own-slot and neighbour writes are drawn with the same rate (1/LR each)
     b_alg = 131.0 + 9.0 * (sbar + u)            # B_alg = B_fixed(110+7C) + 3C*(s + u), C=3
+    b_scan = 27.0 + 9.0 * sbar + 9.0 * u_nb     # input 3 + raw 1 + lastColor RW 6 + lastDesc RW 12 + R 4 + unstable 1 ; samples read ; nb writes
+    b_fb = b_alg - b_scan
     hbm_peak, peak_src = peaks()
     pa_avg_ms = pa_ms / max(pa_n, 1)
-    achieved = roi_px * b_alg / (pa_avg_ms * 1e-3) / 1e9 if pa_avg_ms > 0 else 0.0
+    fb_avg_ms = fb_ms / max(fb_n, 1)
+    achieved = roi_px * b_scan / (pa_avg_ms * 1e-3) / 1e9 if pa_avg_ms > 0 else 0.0
+    fb_achieved = roi_px * b_fb / (fb_avg_ms * 1e-3) / 1e9 if fb_avg_ms > 0 else 0.0
 
     # end to end through the reference-facing C-ABI call with HOST buffers (pinned): every step uploads its frame and reads its
     # mask back inside the timed region. Headline: the asynchronous form (lvb_apply_async / lvb_sync_next: two frames in flight,
@@ -271,15 +282,20 @@ def main():
             "data": "synthetic",
             "config": {"workload": "SuBSENSE 1920x1080 RGB single stream per GPU (BASELINE.json configs[3])", "frame": [W, H, C],
                        "streams_per_gpu": 1, "fps_per_stream": args.steps / (ms_all * 1e-3), "boot_frames": BOOT_FRAMES,
-                       "l2": "per-frame working set (sample model 1.24 GB + maps) exceeds the 126 MB L2; no explicit flush"},
+                       "l2": "per-frame working set (sample model 1.66 GB + maps) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": W * H * C, "d2h_bytes_per_step": W * H, "steps": e2e_steps,
                     "api": "lvb_apply_async(host frame, host mask, lr) + lvb_sync_next: two frames in flight, pinned host buffers",
                     "synchronous_apply_value": W * H * e2e_steps * world / (sync_ms_all * 1e-3) / 1e6},
-            "roofline": {"bound": "hbm", "kernel": "subsense_phaseA<3>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "subsense_scan<3>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": pa_avg_ms,
-                         "launches_timed": int(pa_n), "alg_bytes_per_px": b_alg, "scan_depth": sbar, "sample_writes_per_px": u,
-                         "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / (ms_all / args.steps)},
+                         "launches_timed": int(pa_n), "alg_bytes_per_px": b_scan, "scan_depth": sbar, "sample_writes_per_px": u,
+                         "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / (ms_all / args.steps),
+                         "second_kernel": {"kernel": "subsense_feedback<3>", "avg_launch_ms": fb_avg_ms, "alg_bytes_per_px": b_fb,
+                                           "achieved": fb_achieved, "frac": fb_achieved / hbm_peak, "kernel_share_of_step": fb_avg_ms / (ms_all / args.steps)},
+                         "frame": {"alg_bytes_per_px": b_alg, "achieved": roi_px * b_alg / (ms_all / args.steps * 1e-3) / 1e9,
+                                   "frac": roi_px * b_alg / (ms_all / args.steps * 1e-3) / 1e9 / hbm_peak,
+                                   "note": "whole frame: SURVEY 8(d) B_alg x ROI px / ms_per_step (scan + feedback are on the critical path, the mask chain overlaps them)"}},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(frames)

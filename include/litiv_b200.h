@@ -105,9 +105,11 @@ int lvb_set_collect_stats(lvb_handle h, int enabled);
 int lvb_get_stats(lvb_handle h, uint64_t out[5]);
 /* number of kernels this library launched since the process started (bench.py's gpu_launches) */
 uint64_t lvb_kernel_launch_count(void);
-/* per-launch timing of the dominant kernel (phase A) with CUDA events on the instance's stream: enable, run frames, read+reset */
+/* per-launch timing of the dominant kernel (SuBSENSE: the scan kernel; LOBSTER / PAWCS: phase A) with CUDA events on the instance's stream: enable, run frames, read+reset */
 int lvb_set_profile(lvb_handle h, int enabled);
 int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches);
+/* same for the second-largest kernel of a SuBSENSE frame (the feedback kernel); zero launches for the other algorithms */
+int lvb_get_profile_feedback(lvb_handle h, double* ms_total, uint64_t* launches);
 /* page-locked host buffers: frames / masks living in them are copied straight to / from the device (no staging copy) */
 int lvb_host_alloc(void** out, size_t bytes);
 int lvb_host_free(void* p);

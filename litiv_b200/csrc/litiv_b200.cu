@@ -138,6 +138,7 @@ struct lvb_context {
     cudaStream_t s_aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // phase B runs beside the mask post-processing
     uint64_t n_submitted = 0, n_collected = 0;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
+    std::vector<cudaEvent_t> prof2_events; double prof2_ms = 0; uint64_t prof2_n = 0; // second-largest kernel (SuBSENSE feedback)
     bool direct_mask = false;
     // LVB_TRACE=1 (debugging aid): an event after every kernel of the main stream; lvb_get_profile prints the per-segment averages
     bool trace_on = getenv("LVB_TRACE") != nullptr; std::vector<std::pair<const char*, cudaEvent_t>> trace;
@@ -678,8 +679,11 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         TailArgs T{};
         T.ctl = c->ctl; T.lut = c->lut; T.rel = c->P.rel_lbsp_threshold; T.lbsp_off = c->P.lbsp_threshold_offset; T.min_color = c->P.color_dist_threshold;
         T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed;
+        cudaEvent_t fb0 = nullptr, fb1 = nullptr;
+        if(c->profile) { CK(cudaEventCreate(&fb0)); CK(cudaEventCreate(&fb1)); CK(cudaEventRecord(fb0, st)); }
         if(C == 1) subsense_feedback<1><<<tg, tb, 0, st>>>(A, T); else subsense_feedback<3><<<tg, tb, 0, st>>>(A, T);
         LAUNCHED(); mark(st, "feedback");
+        if(c->profile) { CK(cudaEventRecord(fb1, st)); c->prof2_events.push_back(fb0); c->prof2_events.push_back(fb1); }
         CK(cudaEventRecord(c->ev_post, sp)); c->post_pending = true; // recorded after feedback(k) is enqueued; covers the whole chain of frame k
         // the neighbour writes queued by feedback(k) ("phase B") are applied by scan(k+1), or by whoever needs the model first
         c->nb_seq = seq;
@@ -1374,6 +1378,21 @@ int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches) {
     h->prof_events.clear();
     *ms_total = h->prof_ms; *launches = h->prof_n;
     h->prof_ms = 0; h->prof_n = 0;
+    LVB_CATCH
+}
+int lvb_get_profile_feedback(lvb_handle h, double* ms_total, uint64_t* launches) {
+    LVB_TRY
+    REQUIRE(h && ms_total && launches, "null argument");
+    CK(cudaSetDevice(h->device));
+    sync_streams(h);
+    for(size_t i = 0; i + 1 < h->prof2_events.size(); i += 2) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, h->prof2_events[i], h->prof2_events[i + 1]));
+        h->prof2_ms += ms; ++h->prof2_n;
+        cudaEventDestroy(h->prof2_events[i]); cudaEventDestroy(h->prof2_events[i + 1]);
+    }
+    h->prof2_events.clear();
+    *ms_total = h->prof2_ms; *launches = h->prof2_n;
+    h->prof2_ms = 0; h->prof2_n = 0;
     LVB_CATCH
 }
 int lvb_host_alloc(void** out, size_t bytes) {
