@@ -124,6 +124,33 @@ def test_tier2_import_oracle_snapshot(lv, oracle):
     _compare_state(g, o, INT_STATE, FLT_STATE, "after import")
 
 
+@pytest.mark.parametrize("check_every_frame", [True, False])
+def test_subsense_scene_change_reset(lv, oracle, check_every_frame):
+    """frame-level reset (SuBSENSE.cpp:584-600): a sudden scene change makes the frame tail request refreshModel(0.1) on the
+    device. The conditional refresh then has to (1) wait for this frame's final mask, which is still being produced on the mask
+    stream, and (2) apply the frame's queued neighbour writes before it resamples. With check_every_frame=False nothing reads the
+    state between frames, so the kernels of consecutive frames really overlap (pipelined path); state is compared at the end."""
+    w, h, c = 320, 240, 3
+    seq_a, seq_b = SynthSequence(w, h, c, seed=21), SynthSequence(w, h, c, seed=22)
+    g, o = _mk(lv, oracle, "subsense", seed=5)
+    f0 = seq_a.frame(0)
+    g.initialize(f0)
+    o.initialize(f0)
+    epoch0 = o.state_get("scalars")[12]
+    masks_g, masks_o = [], []
+    for t in range(1, 96):
+        f = seq_a.frame(t) if t < 60 else (255 - seq_b.frame(t))   # hard cut at frame 60: the caps shrink, the reset fires around frame 79
+        lr = 1.0 if t <= 10 else 0.0
+        masks_g.append(g.apply(f, lr))
+        masks_o.append(o.apply(f, lr))
+        if check_every_frame:
+            _compare_state(g, o, INT_STATE, FLT_STATE, f"scene change, frame {t}")
+    assert o.state_get("scalars")[12] > epoch0, "the sequence did not trigger a model reset: the test does not test anything"
+    for t, (mg, mo) in enumerate(zip(masks_g, masks_o), 1):
+        assert np.array_equal(mg, mo), f"scene change, frame {t}: final masks differ in {(mg != mo).sum()} px"
+    _compare_state(g, o, INT_STATE, FLT_STATE, "scene change, end")
+
+
 @pytest.mark.parametrize("algo,w,h,c,n", [("subsense", 320, 240, 3, 130), ("lobster", 320, 240, 1, 80)])
 def test_tier3_sequence(lv, oracle, algo, w, h, c, n):
     """end-to-end masks over a longer sequence with the samples/changedet learning-rate protocol (main.cpp:56)"""
