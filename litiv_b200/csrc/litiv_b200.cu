@@ -123,6 +123,7 @@ struct lvb_context {
     uint8_t* lut = nullptr;
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
     uint32_t* magic = nullptr; // [257] floor(2^32 / n)
+    float* div_tab = nullptr;  // [colorRange + 1] i / colorRange, then [descRange + 1] i / descRange
     FrameCtl* ctl = nullptr;
     float* dsLT = nullptr; float* dsST = nullptr;
     std::vector<uint8_t> roi_host;
@@ -156,11 +157,11 @@ struct lvb_context {
     size_t rec_bytes() const { return C == 1 ? 4 : 16; }
 
     void free_all() {
-        void* ptrs[] = {last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -477,6 +478,14 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         for(uint32_t n = 2; n <= 256; ++n) mg[n] = (uint32_t)(0x100000000ull / n);
         c->magic = dalloc<uint32_t>(c->stream, 257, false);
         h2d(c->stream, c->magic, mg, sizeof(mg));
+        // i / colorRange, i / descRange (SuBSENSE.cpp:57-60: 255 / 16 for 1 channel, 765 / 48 for 3): float division on the host
+        // is the same IEEE round-to-nearest quotient as __fdiv_rn
+        const int cr = C == 1 ? 255 : 765, dr = C == 1 ? 16 : 48;
+        std::vector<float> dv((size_t)cr + 1 + dr + 1);
+        for(int i = 0; i <= cr; ++i) dv[i] = (float)i / (float)cr;
+        for(int i = 0; i <= dr; ++i) dv[(size_t)cr + 1 + i] = (float)i / (float)dr;
+        c->div_tab = dalloc<float>(c->stream, dv.size(), false);
+        h2d(c->stream, c->div_tab, dv.data(), dv.size() * sizeof(float));
     }
     FrameCtl f{};
     f.frame_idx = 1; f.aLT = 1.0f; f.aST = 1.0f; f.roi_count = (uint32_t)fin;
@@ -617,6 +626,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
+    A.div_color = c->div_tab; A.div_desc = c->div_tab + (C == 1 ? 256 : 766);
     A.magic = c->magic; A.lr_magic = magic_of(A.lr_fixed); A.lr2_magic = magic_of(A.lr_fixed / 2u + 1u);
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane;

@@ -87,6 +87,8 @@ struct SubArgs {
     int use_tma, collect_stats;
     uint32_t n_magic;          // floor(2^32 / N) for fast_mod
     const uint32_t* magic;     // [257] floor(2^32 / n) (n = 1: 0xFFFFFFFF), device table for x % ceil(T(x))
+    const float* div_color;    // [colorRange + 1] i / colorRange  (IEEE quotients tabulated on the host: the feedback step
+    const float* div_desc;     // [descRange + 1]  i / descRange    normalises four small integers per pixel)
     uint32_t lr_magic, lr2_magic; // magic numbers of lr_fixed and lr_fixed/2+1 when the rate is fixed
 };
 

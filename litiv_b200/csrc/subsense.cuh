@@ -440,8 +440,11 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
     }
 }
 
+#ifndef FEEDBACK_MIN_BLOCKS
+#define FEEDBACK_MIN_BLOCKS 5
+#endif
 template<int CH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FEEDBACK_MIN_BLOCKS)
 subsense_feedback(const SubArgs A, const TailArgs TA) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -449,12 +452,10 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     static_assert(TILE_W * TILE_H == 256, "the feedback kernel (and the frame tail it hosts) is written for 256-thread CTAs");
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
     __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
-    __shared__ uint32_t s_magic[257];             // floor(2^32 / n): x % ceil(T(x)) without a hardware divide
     __shared__ CtlSlice s_ctl;
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
     if(tid < 2) s_cnt[tid] = 0;
     if(tid < GHOST_ROWS * 3) {
         const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
@@ -506,13 +507,15 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // D_last (:254-255 / :396-397)
-        const float normLast = __fmul_rn(__fadd_rn(__fdiv_rn((float)lastL1, (float)colorRange), __fdiv_rn((float)lastHd, (float)descRange)), 0.5f); // x/2 == x*0.5 exactly
+        // i / colorRange and i / descRange come from 3 KB of host-tabulated IEEE quotients (read-only path, L1 resident) instead
+        // of four __fdiv_rn sequences per pixel
+        const float normLast = __fmul_rn(__fadd_rn(__ldg(A.div_color + lastL1), __ldg(A.div_desc + lastHd)), 0.5f); // x/2 == x*0.5 exactly
         Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
 
         const uint32_t pixid = (uint32_t)(y * A.W + x);
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
         const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
-        const float baseMin = __fmul_rn(__fadd_rn(__fdiv_rn((float)minSum, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange)), 0.5f);
+        const float baseMin = __fmul_rn(__fadd_rn(__ldg(A.div_color + min(minSum, colorRange)), __ldg(A.div_desc + min(minDesc, descRange))), 0.5f);
         if(is_fg) { // foreground (:256-269 / :398-413)
             const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
             DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
@@ -529,11 +532,11 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
             rawLT = __fmul_rn(rawLT, oneLT);
             rawST = __fmul_rn(rawST, oneST);
-            // x % LR, x % (LR/2+1): T(x) <= 256, so the magic numbers come from a table (a fixed rate has them in the arguments)
+            // x % LR, x % (LR/2+1): T(x) <= 256, so the magic numbers come from a 1 KB table (a fixed rate has them in the arguments)
             const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
             const uint32_t LR2 = LR / 2u + 1u;
             const bool tab = !A.lr_fixed && LR <= 256u;
-            const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
+            const uint32_t mg = A.lr_fixed ? A.lr_magic : __ldg(A.magic + (tab ? LR : 0u)), mg2 = A.lr_fixed ? A.lr2_magic : __ldg(A.magic + (tab ? LR2 : 0u));
             const bool fastm = A.lr_fixed || tab;
             if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
                 const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
