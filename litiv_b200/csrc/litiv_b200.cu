@@ -123,6 +123,7 @@ struct lvb_context {
     uint8_t* lut = nullptr;
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
     uint32_t* magic = nullptr; // [257] floor(2^32 / n)
+    float* r_plane = nullptr;  // compact R(x) plane read by the SuBSENSE scan kernel
     float* div_tab = nullptr;  // [colorRange + 1] i / colorRange, then [descRange + 1] i / descRange
     FrameCtl* ctl = nullptr;
     float* dsLT = nullptr; float* dsST = nullptr;
@@ -157,11 +158,11 @@ struct lvb_context {
     size_t rec_bytes() const { return C == 1 ? 4 : 16; }
 
     void free_all() {
-        void* ptrs[] = {div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -513,6 +514,9 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         std::vector<float4> m(c->plane * 2);
         for(size_t i = 0; i < c->plane; ++i) { m[i * 2] = make_float4(f.t_lower, 1.0f, 10.0f, 0.f); m[i * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
         h2d(c->stream, c->maps, m.data(), m.size() * sizeof(float4));
+        std::vector<float> r1(c->plane, 1.0f);
+        c->r_plane = dalloc<float>(c->stream, c->plane, false);
+        h2d(c->stream, c->r_plane, r1.data(), r1.size() * sizeof(float));
     }
     if(c->algo == LVB_ALGO_PAWCS) paw_initialize(c, f, orig);
     c->median_k = f.median_k;
@@ -626,7 +630,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
-    A.div_color = c->div_tab; A.div_desc = c->div_tab + (C == 1 ? 256 : 766);
+    A.r_plane = c->r_plane; A.div_color = c->div_tab; A.div_desc = c->div_tab + (C == 1 ? 256 : 766);
     A.magic = c->magic; A.lr_magic = magic_of(A.lr_fixed); A.lr2_magic = magic_of(A.lr_fixed / 2u + 1u);
     PhaseBArgs B{};
     B.W = W; B.H = H; B.Wp = c->Wp; B.WW = c->WW; B.CH = C; B.plane = c->plane;
@@ -1048,6 +1052,11 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
         const float* s = (const float*)in;
         for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) h[((size_t)y * Wp + x) * 8 + mi] = s[(size_t)y * W + x];
         h2d(c->stream, c->maps, h.data(), h.size() * 4);
+        if(mi == 1 && c->r_plane) { // the scan kernel reads R(x) from its compact copy
+            std::vector<float> rp(c->plane, 1.0f);
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) rp[(size_t)y * Wp + x] = s[(size_t)y * W + x];
+            h2d(c->stream, c->r_plane, rp.data(), rp.size() * 4);
+        }
         if(mi == 3 || mi == 7) { // ghost flag is derived state: rawST > 0.995 && Dlast < 0.01 inside the ROI
             std::vector<uint32_t> g((size_t)H * WW, 0);
             for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) {

@@ -70,6 +70,7 @@ struct SubArgs {
     const uchar* img; size_t ipitch;  // current frame, interleaved bytes
     void* bg;                  // sample records [N][H][Wp]
     float4* maps;              // 2 float4 per pixel
+    float* r_plane;            // compact copy of R(x) for the scan kernel (which would otherwise pull a 32-byte sector per pixel for 4 bytes)
     const float2* fin;         // final-segmentation EMAs of the previous frame
     uint2* hand;               // scan -> feedback hand-off word
     void* last_color; void* last_desc;          // this frame's colour / intra descriptors (written by the scan)

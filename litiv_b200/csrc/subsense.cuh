@@ -240,7 +240,7 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
     const Rec* bgr = (const Rec*)A.bg + pix;
     if(active) {
-        R = ((const float*)A.maps)[pix * 8 + 1];
+        R = A.r_plane[pix];
         lc = ((const Col*)A.prev_color)[pix];
         ld = ((const Desc*)A.prev_desc)[pix];
         { const Rec r0 = bgr[0]; pre_c0 = rec_col(r0); pre_d0 = rec_desc(r0); }
@@ -250,15 +250,24 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         // scatter inside the CTA: every intent of the tile + halo marks its target pixel (smem atomics) instead of every target
         // scanning its 25 possible sources
         __syncthreads(); // s_hits cleared
-        for(int i = tid; i < IW * IH; i += TILE_W * TILE_H) {
-            const int r = i / IW, cc = i - r * IW;
-            const int gx = x0 - HALO + cc, gy = y0 - HALO + r;
-            const uint32_t it = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? (uint32_t)A.intents[(size_t)gy * A.Wp + gx] : NO_INTENT;
-            s_int[r][cc] = (ushort)it;
-            if(it != NO_INTENT) {
-                const int code = (int)(it >> 8), oy = code / 5, ox = code - oy * 5; // target = source + (ox-2, oy-2)
-                const int tx = cc - 2 * HALO + ox, ty = r - 2 * HALO + oy;           // target inside the 32 x TILE_H core?
-                if(tx >= 0 && tx < TILE_W && ty >= 0 && ty < TILE_H) atomicOr(&s_hits[ty][tx], 1u << (24 - code));
+        // the tile row starts at x0-2 (even) and Wp is a multiple of 32: intents are fetched as aligned u32 pairs, one per thread
+        static_assert(IW % 2 == 0 && (IW / 2) * IH <= TILE_W * TILE_H, "one intent pair per thread");
+        if(tid < (IW / 2) * IH) {
+            const int r = tid / (IW / 2), cp = tid - r * (IW / 2);
+            const int gx = x0 - HALO + 2 * cp, gy = y0 - HALO + r;
+            uint32_t pair = NO_INTENT | (NO_INTENT << 16);
+            if(gy >= 0 && gy < A.H && gx >= 0 && gx < A.Wp) pair = *(const uint32_t*)(A.intents + (size_t)gy * A.Wp + gx);
+#pragma unroll
+            for(int e = 0; e < 2; ++e) {
+                const int cc = 2 * cp + e;
+                uint32_t it = e ? (pair >> 16) : (pair & 0xFFFFu);
+                if(gx + e >= A.W) it = NO_INTENT; // padding columns of the plane are never written
+                s_int[r][cc] = (ushort)it;
+                if(it != NO_INTENT) {
+                    const int code = (int)(it >> 8), oy = code / 5, ox = code - oy * 5; // target = source + (ox-2, oy-2)
+                    const int tx = cc - 2 * HALO + ox, ty = r - 2 * HALO + oy;           // target inside the 32 x TILE_H core?
+                    if(tx >= 0 && tx < TILE_W && ty >= 0 && ty < TILE_H) atomicOr(&s_hits[ty][tx], 1u << (24 - code));
+                }
             }
         }
     }
@@ -581,6 +590,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
 
         A.maps[pix * 2] = make_float4(T, R, V, Dlast);
         A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
+        A.r_plane[pix] = R;
     }
 
     // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
