@@ -29,6 +29,7 @@ W, H, C = 1920, 1080, 3
 BOOT_FRAMES = 60          # protocol frames before anything is timed (lr=1 for the first 50)
 N_UNIQUE = 24             # distinct synthetic frames kept resident and played ping-pong (continuous motion)
 METRIC = "subsense_1080p_mpx_per_s"
+SCAN_DRAM_BYTES_NCU = 436.6e6  # per subsense_scan launch at this workload (profiles/r01h_scan_feedback_ncu.md)
 
 
 def peaks():
@@ -288,7 +289,8 @@ def main():
                     "api": "lvb_apply_async(host frame, host mask, lr) + lvb_sync_next: two frames in flight, pinned host buffers",
                     "synchronous_apply_value": W * H * e2e_steps * world / (sync_ms_all * 1e-3) / 1e6},
             "roofline": {"bound": "hbm", "kernel": "subsense_scan<3>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "avg_launch_ms": pa_avg_ms,
+                         "frac": achieved / hbm_peak, "traffic": SCAN_DRAM_BYTES_NCU,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r01h_scan_feedback_ncu.md)", "peak_source": peak_src, "avg_launch_ms": pa_avg_ms,
                          "launches_timed": int(pa_n), "alg_bytes_per_px": b_scan, "scan_depth": sbar, "sample_writes_per_px": u,
                          "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / (ms_all / args.steps),
                          "second_kernel": {"kernel": "subsense_feedback<3>", "avg_launch_ms": fb_avg_ms, "alg_bytes_per_px": b_fb,

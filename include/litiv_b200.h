@@ -96,6 +96,17 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref_or_null, int width, 
  * 3 cv::floodFill((0,0),255)+bitwise_not ("holes": background not 4-connected to the border, needs src(0,0)==0) */
 int lvb_mask_op(int op, const uint8_t* src, uint8_t* dst, int width, int height, int param, int device);
 
+/* CDnet-style evaluation, the step right after apply() in the reference's loop: lv::BinClassif::accumulate(oClassif, oGT, oROI)
+ * (modules/datasets/src/metrics.cpp:21-61) computed on the device. counters[6] = TP, TN, FP, FN, SE, DC (BinClassif::CountersList,
+ * datasets/include/litiv/datasets/metrics.hpp:40-48) are ADDED to. gt: host W*H CDnet labels (0 negative, 50 shadow, 85 out of
+ * scope, 170 unknown, 255 positive) or null (every pixel is a don't-care); roi: host W*H or null (pixels equal to 0 are don't-care).
+ * lvb_binclassif_accumulate scores the instance's latest foreground mask where it lives (bit-packed in HBM: no mask read-back);
+ * lvb_binclassif scores a caller-provided host mask. lvb_binclassif_metrics = BinClassifMetrics (metrics.hpp:213-257):
+ * out[8] = recall, specificity, FPR, FNR, PBC, precision, F-measure, MCC. */
+int lvb_binclassif_accumulate(lvb_handle h, const uint8_t* gt_or_null, const uint8_t* roi_or_null, uint64_t counters[6]);
+int lvb_binclassif(const uint8_t* classif, const uint8_t* gt_or_null, const uint8_t* roi_or_null, int width, int height, uint64_t counters[6], int device);
+int lvb_binclassif_metrics(const uint64_t counters[6], double out[8]);
+
 /* parity / debug: named state buffers in the reference's layout (sample-major [N][H][W][C], maps [H][W]); see DESIGN.md */
 int lvb_state_size(lvb_handle h, const char* name, size_t* bytes);
 int lvb_state_get(lvb_handle h, const char* name, void* out, size_t bytes);

@@ -68,7 +68,10 @@ struct SubtractorBase {
     void apply(const ImageView& img, std::vector<uint8_t>& fgmask, double learningRate) { fgmask.resize((size_t)m_rows * m_cols); apply(img, fgmask.data(), learningRate); }
     /// asynchronous pair (the `apply_cuda` async mode sketched in apps/changedet/src/main.cpp:274-282)
     void apply_async(const ImageView& img, uint8_t* fgmask, double learningRate) { check(lvb_apply_async(m_h, img.data, fgmask, learningRate)); }
+    void sync_next() { check(lvb_sync_next(m_h)); }
     void sync() { check(lvb_sync(m_h)); }
+    /// order later work on the instance's CUDA stream behind the side-stream work of the frames enqueued so far
+    void flush() { check(lvb_flush(m_h)); }
     /// device-resident frame (what a cv::cuda::GpuMat overload binds to)
     void apply_device(const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask, double learningRate) { check(lvb_apply_device(m_h, d_img, d_step, d_fgmask, learningRate)); }
 
@@ -130,6 +133,51 @@ private:
         p.desc_dist_threshold = (int32_t)d; p.color_dist_threshold = (int32_t)c; p.n_samples = (int32_t)n; p.n_required = (int32_t)r;
         p.lbsp_threshold_offset = (int32_t)off; p.rel_lbsp_threshold = rel;
         return p;
+    }
+};
+
+/// BackgroundSubtractorPAWCS_<lv::CUDA> (ctor arguments and defaults: BackgroundSubtractorPAWCS.hpp:51-55)
+struct BackgroundSubtractorPAWCS : SubtractorBase {
+    explicit BackgroundSubtractorPAWCS(size_t nDescDistThresholdOffset = 2, size_t nMinColorDistThreshold = 20, size_t nMaxNbWords = 50,
+                                       size_t nSamplesForMovingAvgs = 100, float fRelLBSPThreshold = 0.333f, int device = 0, uint64_t seed = 0)
+        : SubtractorBase(LVB_ALGO_PAWCS, make(nDescDistThresholdOffset, nMinColorDistThreshold, nMaxNbWords, nSamplesForMovingAvgs, fRelLBSPThreshold), device, seed) {}
+    /// BackgroundSubtractorPAWCS::refreshModel(nBaseOccCount, fOccDecrFrac, bForceFGUpdate) (PAWCS.cpp:107-429)
+    void refreshModel(size_t nBaseOccCount, float fOccDecrFrac, bool bForceFGUpdate = false) { check(lvb_pawcs_refresh_model(m_h, (uint32_t)nBaseOccCount, fOccDecrFrac, bForceFGUpdate ? 1 : 0)); }
+private:
+    static lvb_params make(size_t d, size_t c, size_t n, size_t a, float rel) {
+        lvb_params p = defaults(LVB_ALGO_PAWCS);
+        p.desc_dist_threshold = (int32_t)d; p.color_dist_threshold = (int32_t)c; p.n_samples = (int32_t)n;
+        p.n_samples_for_moving_avgs = (int32_t)a; p.rel_lbsp_threshold = rel;
+        return p;
+    }
+};
+
+/// lv::BinClassif (datasets/include/litiv/datasets/metrics.hpp:32-67) with accumulate() on the device, and BinClassifMetrics (:213-257)
+struct BinClassif {
+    uint64_t nTP = 0, nTN = 0, nFP = 0, nFN = 0, nSE = 0, nDC = 0;
+    uint64_t total(bool bWithDontCare = false) const { return nTP + nTN + nFP + nFN + (bWithDontCare ? nDC : uint64_t(0)); }
+    /// scores the subtractor's latest foreground mask where it lives (no mask read-back)
+    void accumulate(const SubtractorBase& algo, const ImageView& gt, const ImageView& roi = ImageView()) {
+        uint64_t c[6] = {nTP, nTN, nFP, nFN, nSE, nDC};
+        check(lvb_binclassif_accumulate(algo.handle(), gt.empty() ? nullptr : gt.data, roi.empty() ? nullptr : roi.data, c));
+        nTP = c[0]; nTN = c[1]; nFP = c[2]; nFN = c[3]; nSE = c[4]; nDC = c[5];
+    }
+    void accumulate(const ImageView& classif, const ImageView& gt, const ImageView& roi = ImageView(), int device = 0) {
+        if(classif.empty() || classif.channels != 1 || !classif.isContinuous()) throw Exception("binary classifier results must be non-empty and of type 8UC1");
+        if((!gt.empty() && (gt.rows != classif.rows || gt.cols != classif.cols)) || (!roi.empty() && (roi.rows != classif.rows || roi.cols != classif.cols)))
+            throw Exception("all input mat sizes must match");
+        uint64_t c[6] = {nTP, nTN, nFP, nFN, nSE, nDC};
+        check(lvb_binclassif(classif.data, gt.empty() ? nullptr : gt.data, roi.empty() ? nullptr : roi.data, classif.cols, classif.rows, c, device));
+        nTP = c[0]; nTN = c[1]; nFP = c[2]; nFN = c[3]; nSE = c[4]; nDC = c[5];
+    }
+};
+struct BinClassifMetrics {
+    double dRecall, dSpecificity, dFPR, dFNR, dPBC, dPrecision, dFMeasure, dMCC;
+    explicit BinClassifMetrics(const BinClassif& m) {
+        const uint64_t c[6] = {m.nTP, m.nTN, m.nFP, m.nFN, m.nSE, m.nDC};
+        double o[8];
+        check(lvb_binclassif_metrics(c, o));
+        dRecall = o[0]; dSpecificity = o[1]; dFPR = o[2]; dFNR = o[3]; dPBC = o[4]; dPrecision = o[5]; dFMeasure = o[6]; dMCC = o[7];
     }
 };
 

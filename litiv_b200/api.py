@@ -24,6 +24,7 @@ EXPORTS = [
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
     "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback",
+    "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics",
 ]
 
 
@@ -61,6 +62,9 @@ def lib():
         L.lvb_sync.argtypes = [C.c_void_p]
         L.lvb_sync_next.argtypes = [C.c_void_p]
         L.lvb_flush.argtypes = [C.c_void_p]
+        L.lvb_binclassif_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvb_binclassif.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.lvb_binclassif_metrics.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_apply_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
         L.lvb_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]
         L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
@@ -385,3 +389,51 @@ class LBSP:
             rp = self.ref.ctypes.data
         _chk(lib().lvb_lbsp_compute(img.ctypes.data, rp, w, h, c, int(self.rel is not None), self.rel or 0.0, self.thr, out.ctypes.data, self.device))
         return out[..., 0] if c == 1 else out
+
+
+class BinClassif:
+    """lv::BinClassif (modules/datasets/include/litiv/datasets/metrics.hpp:32-67) with accumulate() on the device."""
+    NAMES = ("nTP", "nTN", "nFP", "nFN", "nSE", "nDC")   # BinClassif::CountersList order
+
+    def __init__(self, device=0):
+        self.counters = np.zeros(6, np.uint64)
+        self.device = device
+
+    def __getattr__(self, name):
+        if name in BinClassif.NAMES:
+            return int(self.counters[BinClassif.NAMES.index(name)])
+        raise AttributeError(name)
+
+    def total(self, bWithDontCare=False):
+        return int(self.counters[:4].sum()) + (int(self.counters[5]) if bWithDontCare else 0)
+
+    @staticmethod
+    def _mat(a, shape=None):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=np.uint8)
+        if a.ndim != 2 or (shape is not None and a.shape != shape):
+            raise LitivError("all input mat sizes must match")
+        return a
+
+    def accumulate(self, oClassif, oGT=None, oROI=None):
+        """oClassif: a host 8UC1 mask, or a background subtractor instance (its latest foreground mask is scored in HBM)"""
+        if isinstance(oClassif, _BackgroundSubtractor):
+            h, w, _ = oClassif.shape
+            gt, roi = self._mat(oGT, (h, w)), self._mat(oROI, (h, w))
+            _chk(lib().lvb_binclassif_accumulate(oClassif._h, gt.ctypes.data if gt is not None else None,
+                                                 roi.ctypes.data if roi is not None else None, self.counters.ctypes.data))
+            return self
+        m = self._mat(oClassif)
+        if m is None or m.size == 0:
+            raise LitivError("binary classifier results must be non-empty and of type 8UC1")
+        gt, roi = self._mat(oGT, m.shape), self._mat(oROI, m.shape)
+        _chk(lib().lvb_binclassif(m.ctypes.data, gt.ctypes.data if gt is not None else None, roi.ctypes.data if roi is not None else None,
+                                  m.shape[1], m.shape[0], self.counters.ctypes.data, self.device))
+        return self
+
+    def metrics(self):
+        """BinClassifMetrics (metrics.hpp:213-257)"""
+        out = np.zeros(8, np.float64)
+        _chk(lib().lvb_binclassif_metrics(self.counters.ctypes.data, out.ctypes.data))
+        return dict(zip(("dRecall", "dSpecificity", "dFPR", "dFNR", "dPBC", "dPrecision", "dFMeasure", "dMCC"), out.tolist()))

@@ -4,6 +4,7 @@
 #include "lobster.cuh"
 #include "postproc.cuh"
 #include "pawcs.cuh"
+#include "metrics.cuh"
 #include <string>
 #include <vector>
 #include <stdexcept>
@@ -1494,6 +1495,71 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
     } catch(...) { cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out); throw; }
     cudaFree(d_img); cudaFree(d_ref); cudaFree(d_out);
     (void)e;
+    LVB_CATCH
+}
+
+/// lv::BinClassif::accumulate (datasets/src/metrics.cpp:21-61) on the device; see csrc/metrics.cuh
+static void binclassif_run(cudaStream_t st, int W, int H, int WW, const uint8_t* d_classif, const uint32_t* d_bits, const uint8_t* gt, const uint8_t* roi,
+                           uint64_t counters[6]) {
+    REQUIRE(counters != nullptr, "null counters");
+    const size_t npx = (size_t)W * H;
+    if(!gt) { counters[BC_DC] += npx; return; } // metrics.cpp:26-29: no groundtruth -> every pixel is a don't-care
+    uint8_t* d_gt = dalloc<uint8_t>(st, npx, false), *d_roi = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    try {
+        d_cnt = dalloc<unsigned long long>(st, BC_COUNT);
+        CK(cudaMemcpyAsync(d_gt, gt, npx, cudaMemcpyHostToDevice, st));
+        if(roi) { d_roi = dalloc<uint8_t>(st, npx, false); CK(cudaMemcpyAsync(d_roi, roi, npx, cudaMemcpyHostToDevice, st)); }
+        BinClassifArgs A{};
+        A.W = W; A.H = H; A.WW = WW; A.classif = d_classif; A.cpitch = (size_t)W; A.classif_bits = d_bits; A.gt = d_gt; A.gpitch = (size_t)W;
+        A.roi = d_roi; A.rpitch = (size_t)W; A.counters = d_cnt;
+        binclassif_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, st>>>(A); LAUNCHED();
+        unsigned long long h[BC_COUNT];
+        d2h(st, h, d_cnt, sizeof(h));
+        for(int i = 0; i < BC_COUNT; ++i) counters[i] += h[i];
+    } catch(...) { cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt); throw; }
+    cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt);
+}
+int lvb_binclassif_accumulate(lvb_handle h, const uint8_t* gt, const uint8_t* roi, uint64_t counters[6]) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null handle");
+    REQUIRE(h->initialized, "algo & model must be initialized first");
+    CK(cudaSetDevice(h->device));
+    while(sync_next(h)) {}
+    sync_streams(h);
+    binclassif_run(h->stream, h->W, h->H, h->WW, nullptr, h->lastfg, gt, roi, counters);
+    LVB_CATCH
+}
+int lvb_binclassif(const uint8_t* classif, const uint8_t* gt, const uint8_t* roi, int W, int H, uint64_t counters[6], int device) {
+    LVB_TRY
+    REQUIRE(classif && W >= 1 && H >= 1, "binary classifier results must be non-empty and of type 8UC1");
+    REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const size_t npx = (size_t)W * H;
+    uint8_t* d_c = nullptr;
+    if(gt) { d_c = dalloc<uint8_t>((cudaStream_t)0, npx, false); CK(cudaMemcpy(d_c, classif, npx, cudaMemcpyHostToDevice)); }
+    try { binclassif_run((cudaStream_t)0, W, H, (W + 31) / 32, d_c, nullptr, gt, roi, counters); } catch(...) { cudaFree(d_c); throw; }
+    cudaFree(d_c);
+    LVB_CATCH
+}
+/// BinClassifMetrics (datasets/include/litiv/datasets/metrics.hpp:213-257): recall, specificity, FPR, FNR, PBC, precision, F-measure, MCC.
+/// Host arithmetic on six integers; no device involved.
+int lvb_binclassif_metrics(const uint64_t c[6], double out[8]) {
+    LVB_TRY
+    REQUIRE(c && out, "null argument");
+    const double TP = (double)c[BC_TP], TN = (double)c[BC_TN], FP = (double)c[BC_FP], FN = (double)c[BC_FN];
+    const uint64_t total = c[BC_TP] + c[BC_TN] + c[BC_FP] + c[BC_FN];
+    const double recall = (c[BC_TP] + c[BC_FN]) > 0 ? TP / (double)(c[BC_TP] + c[BC_FN]) : 0;
+    const double precision = (c[BC_TP] + c[BC_FP]) > 0 ? TP / (double)(c[BC_TP] + c[BC_FP]) : 0;
+    out[0] = recall;
+    out[1] = (c[BC_TN] + c[BC_FP]) > 0 ? TN / (double)(c[BC_TN] + c[BC_FP]) : 0;
+    out[2] = (c[BC_FP] + c[BC_TN]) > 0 ? FP / (double)(c[BC_FP] + c[BC_TN]) : 0;
+    out[3] = (c[BC_TP] + c[BC_FN]) > 0 ? FN / (double)(c[BC_TP] + c[BC_FN]) : 0;
+    out[4] = total > 0 ? 100.0 * (double)(c[BC_FN] + c[BC_FP]) / (double)total : 0;
+    out[5] = precision;
+    out[6] = (recall + precision) > 0 ? 2.0 * (recall * precision) / (recall + precision) : 0;
+    const bool ok = (c[BC_TP] + c[BC_FP]) > 0 && (c[BC_TP] + c[BC_FN]) > 0 && (c[BC_TN] + c[BC_FP]) > 0 && (c[BC_TN] + c[BC_FN]) > 0;
+    out[7] = ok ? ((TP * TN) - (double)(c[BC_FP] * c[BC_FN])) / std::sqrt((TP + FP) * (double)(c[BC_TP] + c[BC_FN]) * (double)(c[BC_TN] + c[BC_FP]) * (double)(c[BC_TN] + c[BC_FN])) : 0;
     LVB_CATCH
 }
 

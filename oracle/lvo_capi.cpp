@@ -220,6 +220,24 @@ int lvo_lbsp_compute(const uint8_t* img, const uint8_t* ref_or_null, int w, int 
     LVO_CATCH
 }
 
+// lv::BinClassif::accumulate(oClassif, oGT, oROI) -- modules/datasets/src/metrics.cpp:21-61; label values metrics.hpp:23-27.
+// counters = TP, TN, FP, FN, SE, DC (BinClassif::CountersList, metrics.hpp:40-48), added to.
+int lvo_binclassif(const uint8_t* classif, const uint8_t* gt_or_null, const uint8_t* roi_or_null, int w, int h, uint64_t counters[6]) {
+    LVO_TRY
+    if(!classif || w < 1 || h < 1) throw std::runtime_error("binary classifier results must be non-empty and of type 8UC1");
+    const size_t n = (size_t)w * h;
+    if(!gt_or_null) { counters[5] += n; return 0; }                       // :26-29
+    for(size_t i = 0; i < n; ++i) {
+        const uint8_t g = gt_or_null[i], in = classif[i];
+        if(g != 85 && g != 170 && (!roi_or_null || roi_or_null[i] != 0)) { // :37-39 (out of scope, unknown, ROI negative)
+            if(in == 255) { if(g == 255) ++counters[0]; else ++counters[2]; }   // TP / FP (:40-45)
+            else          { if(g == 255) ++counters[3]; else ++counters[1]; }   // FN / TN (:46-51)
+            if(g == 50 && in == 255) ++counters[4];                              // shadow error (:52-55)
+        } else ++counters[5];                                              // :57-58
+    }
+    LVO_CATCH
+}
+
 // --- helper entry points used by the "not gpu" tests to pin the helpers against the reference's known answers
 int lvo_glibc_rand_seq(unsigned seed, int n, int* out) { GlibcRand g(seed); for(int i = 0; i < n; ++i) out[i] = g.next(); return 0; }
 int lvo_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); return 0; }

@@ -179,3 +179,29 @@ def lbsp_compute(img, ref=None, rel=None, thr=0):
     _chk(lib().lvo_lbsp_compute(img.ctypes.data_as(C.POINTER(C.c_uint8)), rp, w, h, c, int(rel is not None),
                                 C.c_float(rel if rel is not None else 0.0), int(thr), out.ctypes.data_as(C.POINTER(C.c_uint16))))
     return out[..., 0] if c == 1 else out
+
+
+def binclassif(classif, gt=None, roi=None, counters=None):
+    """lv::BinClassif::accumulate (datasets/src/metrics.cpp:21-61); returns the six counters TP,TN,FP,FN,SE,DC (added to `counters`)"""
+    classif = np.ascontiguousarray(classif, dtype=np.uint8)
+    h, w = classif.shape
+    out = np.zeros(6, np.uint64) if counters is None else np.ascontiguousarray(counters, dtype=np.uint64).copy()
+    gp = rp = None
+    if gt is not None:
+        gt = np.ascontiguousarray(gt, dtype=np.uint8); gp = gt.ctypes.data_as(C.POINTER(C.c_uint8))
+    if roi is not None:
+        roi = np.ascontiguousarray(roi, dtype=np.uint8); rp = roi.ctypes.data_as(C.POINTER(C.c_uint8))
+    _chk(lib().lvo_binclassif(classif.ctypes.data_as(C.POINTER(C.c_uint8)), gp, rp, w, h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return out
+
+
+def binclassif_metrics(c):
+    """BinClassifMetrics (datasets/include/litiv/datasets/metrics.hpp:213-257), restated in Python floats (IEEE double)"""
+    TP, TN, FP, FN = (int(v) for v in c[:4])
+    rec = TP / (TP + FN) if TP + FN > 0 else 0.0
+    pre = TP / (TP + FP) if TP + FP > 0 else 0.0
+    ok = TP + FP > 0 and TP + FN > 0 and TN + FP > 0 and TN + FN > 0
+    return dict(dRecall=rec, dSpecificity=TN / (TN + FP) if TN + FP > 0 else 0.0, dFPR=FP / (FP + TN) if FP + TN > 0 else 0.0,
+                dFNR=FN / (TP + FN) if TP + FN > 0 else 0.0, dPBC=100.0 * (FN + FP) / (TP + TN + FP + FN) if TP + TN + FP + FN > 0 else 0.0,
+                dPrecision=pre, dFMeasure=2.0 * (rec * pre) / (rec + pre) if rec + pre > 0 else 0.0,
+                dMCC=((float(TP) * TN) - float(FP * FN)) / np.sqrt((float(TP) + FP) * (TP + FN) * (TN + FP) * (TN + FN)) if ok else 0.0)

@@ -9,5 +9,9 @@ int main() {
         s.apply(lvb::ImageView(img.data(), 48, 64, 3), mask, 1.0);
         std::printf("ran on GPU: %zu mask bytes\n", mask.size());
     } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
+    try { lvb::BackgroundSubtractorPAWCS p; p.refreshModel(1, 0.0f); } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
+    lvb::BinClassif bc; bc.nTP = 6; bc.nTN = 80; bc.nFP = 4; bc.nFN = 10;
+    const lvb::BinClassifMetrics m(bc);   // host arithmetic only
+    std::printf("F-measure %.6f total %llu\n", m.dFMeasure, (unsigned long long)bc.total());
     return 0;
 }
