@@ -29,6 +29,7 @@ W, H, C = 1920, 1080, 3
 BOOT_FRAMES = 60          # protocol frames before anything is timed (lr=1 for the first 50)
 N_UNIQUE = 24             # distinct synthetic frames kept resident and played ping-pong (continuous motion)
 METRIC = "subsense_1080p_mpx_per_s"
+WORKLOAD = "SuBSENSE 1920x1080 RGB single stream per GPU (BASELINE.json configs[3])"
 SCAN_DRAM_BYTES_NCU = 436.6e6  # per subsense_scan launch at this workload (profiles/r01h_scan_feedback_ncu.md)
 
 
@@ -134,7 +135,8 @@ def run_reference(args):
     val = W * H * nthreads * args.steps / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "SuBSENSE 1920x1080 RGB, one stream per host thread", "streams": nthreads, "frame": [W, H, C]},
+            "config": {"workload": WORKLOAD, "frame": [W, H, C], "cpu_streams": nthreads,
+                       "note": "same 1080p workload, one independent stream per host thread (the reference is single-threaded per stream)"},
             "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": nthreads, "kind": "port",
                              "sample": f"{args.steps} frames x {nthreads} independent 1080p streams, oracle reference-order mode (reference needs OpenCV C++: unbuildable here)"},
             "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -281,7 +283,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "SuBSENSE 1920x1080 RGB single stream per GPU (BASELINE.json configs[3])", "frame": [W, H, C],
+            "config": {"workload": WORKLOAD, "frame": [W, H, C],
                        "streams_per_gpu": 1, "fps_per_stream": args.steps / (ms_all * 1e-3), "boot_frames": BOOT_FRAMES,
                        "l2": "per-frame working set (sample model 1.66 GB + maps) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
