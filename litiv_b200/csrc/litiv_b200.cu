@@ -503,7 +503,6 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
             f.lr_scaling = 0; f.auto_reset = 0; f.use3x3 = 1; f.median_k = c->P.median_blur_kernel_size;
             f.t_lower = 4.0f; f.t_upper = 512.0f;
         }
-        if(f.lr_scaling) REQUIRE(W % 8 == 0 && H % 8 == 0, "frame-level analysis needs frame sizes that are multiples of 8 (other sizes: not implemented yet)");
         c->maps = dalloc<float4>(c->stream, c->plane * 2);
         c->fin = dalloc<float2>(c->stream, c->plane);
         c->fin_alt = dalloc<float2>(c->stream, c->plane);

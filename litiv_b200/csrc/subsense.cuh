@@ -815,6 +815,50 @@ struct DownsampleArgs {
     float* dsLT; float* dsST;
     FrameCtl* ctl;
 };
+/// one cell of OpenCV's general INTER_AREA table (imgproc resize.cpp computeResizeAreaTab) for destination index d: the source
+/// range [s_first, s_first + n) and the weights of its first / inner / last entries; evaluated in double then cast, as OpenCV does
+struct AreaCell { int s_first, n; float a_first, a_mid, a_last; bool has_first, has_last; };
+__device__ __forceinline__ AreaCell area_cell(int d, int ssize, double scale) {
+    const double fs1 = d * scale, fs2 = fs1 + scale, cell = fmin(scale, ssize - fs1);
+    int s1 = (int)ceil(fs1), s2 = (int)floor(fs2);
+    s2 = min(s2, ssize - 1); s1 = min(s1, s2);
+    AreaCell c;
+    c.has_first = (s1 - fs1) > 1e-3; c.has_last = (fs2 - s2) > 1e-3;
+    c.a_first = (float)((s1 - fs1) / cell); c.a_mid = (float)(1.0 / cell); c.a_last = (float)(fmin(fmin(fs2 - s2, 1.), cell) / cell);
+    c.s_first = c.has_first ? s1 - 1 : s1;
+    c.n = (s2 - s1) + (c.has_first ? 1 : 0) + (c.has_last ? 1 : 0);
+    return c;
+}
+__device__ __forceinline__ float area_weight(const AreaCell& c, int i) { // weight of the i-th table entry of the cell
+    if(c.has_first && i == 0) return c.a_first;
+    if(c.has_last && i == c.n - 1) return c.a_last;
+    return c.a_mid;
+}
+/// cv::resize(INTER_AREA) of one destination pixel for a non-integer shrink factor, with OpenCV's float accumulation order
+/// (ResizeArea_Invoker<uchar,float>: row buffer over the column table, then beta-weighted row sums)
+template<int CH>
+__device__ __forceinline__ void area_general_pixel(const uchar* img, size_t ipitch, int W, int H, int dsW, int dsH, int dx, int dy, float (&v)[CH]) {
+    const double scale_x = 1. / ((double)dsW / W), scale_y = 1. / ((double)dsH / H);
+    const AreaCell cx = area_cell(dx, W, scale_x), cy = area_cell(dy, H, scale_y);
+    float sum[CH];
+    for(int j = 0; j < cy.n; ++j) {
+        const uchar* row = img + (size_t)(cy.s_first + j) * ipitch;
+        float buf[CH];
+#pragma unroll
+        for(int c = 0; c < CH; ++c) buf[c] = 0.f;
+        for(int i = 0; i < cx.n; ++i) {
+            const float a = area_weight(cx, i);
+#pragma unroll
+            for(int c = 0; c < CH; ++c) buf[c] = __fadd_rn(buf[c], __fmul_rn((float)row[(size_t)(cx.s_first + i) * CH + c], a));
+        }
+        const float b = area_weight(cy, j);
+#pragma unroll
+        for(int c = 0; c < CH; ++c) sum[c] = j == 0 ? __fmul_rn(b, buf[c]) : __fadd_rn(sum[c], __fmul_rn(b, buf[c]));
+    }
+#pragma unroll
+    for(int c = 0; c < CH; ++c) v[c] = fminf(fmaxf(rintf(sum[c]), 0.f), 255.f);
+}
+
 template<int CH>
 __global__ void __launch_bounds__(128) downsample_motion_kernel(const DownsampleArgs A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -822,20 +866,25 @@ __global__ void __launch_bounds__(128) downsample_motion_kernel(const Downsample
     if(i < A.dsW * A.dsH && A.ctl->lr_scaling) {
         const int dx = i % A.dsW, dy = i / A.dsW;
         const float aLT = A.ctl->aLT, aST = A.ctl->aST;
-        uint32_t sum[CH];
+        float vv[CH];
+        if((A.W & 7) == 0 && (A.H & 7) == 0) { // OpenCV's integer-scale fast path: exact 8x8 mean
+            uint32_t sum[CH];
 #pragma unroll
-        for(int c = 0; c < CH; ++c) sum[c] = 0;
-        for(int r = 0; r < 8; ++r) {
-            const uchar* p = A.img + (size_t)(dy * 8 + r) * A.ipitch + (size_t)dx * 8 * CH;
+            for(int c = 0; c < CH; ++c) sum[c] = 0;
+            for(int r = 0; r < 8; ++r) {
+                const uchar* p = A.img + (size_t)(dy * 8 + r) * A.ipitch + (size_t)dx * 8 * CH;
 #pragma unroll
-            for(int b = 0; b < 8; ++b)
+                for(int b = 0; b < 8; ++b)
 #pragma unroll
-                for(int c = 0; c < CH; ++c) sum[c] += p[b * CH + c];
-        }
+                    for(int c = 0; c < CH; ++c) sum[c] += p[b * CH + c];
+            }
+#pragma unroll
+            for(int c = 0; c < CH; ++c) vv[c] = fminf(fmaxf(rintf(__fmul_rn((float)sum[c], 1.0f / 64)), 0.f), 255.f);
+        } else area_general_pixel<CH>(A.img, A.ipitch, A.W, A.H, A.dsW, A.dsH, dx, dy, vv);
         uint32_t best = 0;
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
-            const float v = fminf(fmaxf(rintf(__fmul_rn((float)sum[c], 1.0f / 64)), 0.f), 255.f);
+            const float v = vv[c];
             const size_t k = (size_t)i * CH + c;
             const float lt = __fadd_rn(__fmul_rn(v, aLT), __fmul_rn(A.dsLT[k], __fsub_rn(1.0f, aLT)));
             const float st = __fadd_rn(__fmul_rn(v, aST), __fmul_rn(A.dsST[k], __fsub_rn(1.0f, aST)));

@@ -254,6 +254,7 @@ int lvo_neighbor_pos(int five, int rnd, int ox, int oy, int border, int W, int H
 int lvo_morph_rect(const uint8_t* src, uint8_t* dst, int W, int H, int r, int dilate) { morph_rect(src, dst, W, H, r, dilate != 0); return 0; }
 int lvo_median_binary(const uint8_t* src, uint8_t* dst, int W, int H, int k) { median_binary(src, dst, W, H, k); return 0; }
 int lvo_floodfill_origin(uint8_t* img, int W, int H) { floodfill_from_origin(img, W, H); return 0; }
+int lvo_resize_area_general(const uint8_t* src, int W, int H, int C, int dw, int dh, uint8_t* dst) { resize_area_general(src, W, H, C, dw, dh, dst); return 0; }
 int lvo_resize_area_exact(const uint8_t* src, int W, int H, int C, int s, uint8_t* dst) { resize_area_exact(src, W, H, C, s, dst); return 0; }
 int lvo_lbsp_threshold(const uint8_t* vals, int ref, int t, int scalar) { return scalar ? lbsp_threshold_scalar(vals, (uchar)ref, (uchar)t) : lbsp_threshold(vals, (uchar)ref, (uchar)t); }
 int lvo_build_lut(int C, float rel, int off, uint8_t* lut) { build_lbsp_lut(C, rel, (size_t)off, lut); return 0; }

@@ -319,6 +319,44 @@ inline void resize_area_exact(const uchar* src, int W, int H, int C, int s, ucha
     }
 }
 
+/// cv::resize(INTER_AREA) u8 -> u8 for a non-integer shrink factor: OpenCV's general area path (imgproc resize.cpp:
+/// computeResizeAreaTab + ResizeArea_Invoker<uchar,float>), restated with its float accumulation order: per source row,
+/// buf[dx] += S[sx]*alpha over the column table; per destination row, sum = beta0*buf0 then += beta*buf; round-half-even +
+/// saturate at the end. OpenCV is not vendored by the reference; this restatement is pinned against cv2 4.13 in
+/// tests/test_oracle_cpu.py (bit-exact on CDnet's non-multiple-of-8 frame sizes).
+struct AreaTabEntry { int di, si; float alpha; };
+inline std::vector<AreaTabEntry> area_tab(int ssize, int dsize, double scale) {
+    std::vector<AreaTabEntry> tab;
+    for(int dx = 0; dx < dsize; ++dx) {
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = std::min(scale, ssize - fsx1);
+        int sx1 = (int)std::ceil(fsx1), sx2 = (int)std::floor(fsx2);
+        sx2 = std::min(sx2, ssize - 1); sx1 = std::min(sx1, sx2);
+        if(sx1 - fsx1 > 1e-3) tab.push_back({dx, sx1 - 1, (float)((sx1 - fsx1) / cell)});
+        for(int sx = sx1; sx < sx2; ++sx) tab.push_back({dx, sx, (float)(1.0 / cell)});
+        if(fsx2 - sx2 > 1e-3) tab.push_back({dx, sx2, (float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)});
+    }
+    return tab;
+}
+inline void resize_area_general(const uchar* src, int W, int H, int C, int dw, int dh, uchar* dst) {
+    const double scale_x = 1. / ((double)dw / W), scale_y = 1. / ((double)dh / H);
+    const std::vector<AreaTabEntry> xt = area_tab(W, dw, scale_x), yt = area_tab(H, dh, scale_y);
+    std::vector<float> buf((size_t)dw * C), sum((size_t)dw * C, 0.f);
+    int prev = -1;
+    auto flush = [&](int dy) { for(int i = 0; i < dw * C; ++i) dst[(size_t)dy * dw * C + i] = sat_u8(sum[i]); };
+    for(const AreaTabEntry& ye : yt) {
+        std::fill(buf.begin(), buf.end(), 0.f);
+        const uchar* S = src + (size_t)ye.si * W * C;
+        for(const AreaTabEntry& xe : xt)
+            for(int c = 0; c < C; ++c) buf[(size_t)xe.di * C + c] += (float)S[(size_t)xe.si * C + c] * xe.alpha;
+        if(ye.di != prev) {
+            if(prev >= 0) flush(prev);
+            for(int i = 0; i < dw * C; ++i) sum[i] = ye.alpha * buf[i];
+            prev = ye.di;
+        } else for(int i = 0; i < dw * C; ++i) sum[i] += ye.alpha * buf[i];
+    }
+    if(prev >= 0) flush(prev);
+}
+
 /// IIBackgroundSubtractor::initialize_common ROI handling (video/src/BackgroundSubtractionUtils.cpp:82-99)
 /// and validateROI (:28-36). Returns the final ROI ({0,128,255}); orig_count = countNonZero before validateROI.
 inline void build_roi(const uchar* roi_or_null, int W, int H, int border, std::vector<uchar>& roi, size_t& orig_count, size_t& final_count) {

@@ -415,8 +415,8 @@ struct SuBSENSE : BgsBase {
     }
 
     void resize_area(const uchar* img) {
-        if(W % 8 == 0 && H % 8 == 0) resize_area_exact(img, W, H, C, 8, ds_frame.data());
-        else throw std::runtime_error("frame sizes that are not multiples of 8 are not supported yet");
+        if(W % 8 == 0 && H % 8 == 0) resize_area_exact(img, W, H, C, 8, ds_frame.data());   // OpenCV's integer-scale fast path
+        else resize_area_general(img, W, H, C, dsW, dsH, ds_frame.data());
     }
 
     void apply(const uchar* img, uchar* fgmask, double lr) {

@@ -70,6 +70,8 @@ CASES = [
     ("subsense", 320, 240, 1, 8, None),
     ("subsense", 96, 72, 3, 8, None),       # "small" branch: no frame-level analysis, T in [4,512]
     ("subsense", 200, 150, 3, 6, "roi"),     # ragged width (not a multiple of 32) + user ROI
+    ("subsense", 330, 250, 3, 8, None),      # frame-level analysis on a size that is not a multiple of 8 (general INTER_AREA path)
+    ("subsense", 570, 340, 1, 6, None),      # CDnet twoPositionPTZCam size, 1 channel
     ("lobster", 320, 240, 1, 10, None),
     ("lobster", 320, 240, 3, 8, None),
     ("lobster", 75, 61, 1, 6, "roi"),

@@ -131,6 +131,14 @@ def test_mask_ops_match_cv2(oracle):
     ds = np.empty((8, 12, 3), np.uint8)
     L.lvo_resize_area_exact(img.ctypes.data_as(C.c_void_p), 96, 64, 3, 8, ds.ctypes.data_as(C.c_void_p))
     assert np.array_equal(ds, cv2.resize(img, (12, 8), interpolation=cv2.INTER_AREA))
+    # non-integer shrink factors (CDnet frame sizes that are not multiples of 8): OpenCV's general area path, bit-exact
+    for (w, h) in ((570, 340), (640, 364), (595, 245), (700, 450), (624, 420), (480, 295), (323, 243)):
+        for cn in (1, 3):
+            img = rng.randint(0, 256, (h, w, cn)).astype(np.uint8)
+            ds = np.empty((h // 8, w // 8, cn), np.uint8)
+            L.lvo_resize_area_general(img.ctypes.data_as(C.c_void_p), w, h, cn, w // 8, h // 8, ds.ctypes.data_as(C.c_void_p))
+            ref = cv2.resize(img if cn == 3 else img[..., 0], (w // 8, h // 8), interpolation=cv2.INTER_AREA).reshape(ds.shape)
+            assert np.array_equal(ds, ref), f"INTER_AREA {w}x{h}x{cn}: {(ds != ref).sum()} mismatches"
 
 
 def _fmeasure(m, gt):
