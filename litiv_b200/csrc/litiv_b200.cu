@@ -1220,7 +1220,10 @@ int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double lr) {
     LVB_TRY
     REQUIRE(h != nullptr, "null handle");
     apply_async(h, img, fgmask, lr);
-    sync(h);
+    // returns as soon as this frame's mask has landed in the caller's buffer: the feedback kernel and the rest of the mask chain
+    // keep running on the instance's streams while the caller fetches / uploads the next frame (anything that reads the model
+    // or the state waits for them)
+    while(sync_next(h)) {}
     LVB_CATCH
 }
 int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double lr) {
