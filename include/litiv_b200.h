@@ -63,6 +63,9 @@ int lvb_sync_next(lvb_handle h);
 int lvb_sync(lvb_handle h);
 /* n independent streams, one frame each (the lv::WorkerPool pattern of apps/changedet/src/main.cpp:148-154) */
 int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, double learning_rate);
+/* the same for device-resident frames (rows of d_step bytes; d_fgmasks or its entries may be null): enqueues one frame per
+ * instance from a small pool of host threads and returns without waiting (order later work with lvb_flush / lvb_sync) */
+int lvb_apply_batch_device(lvb_handle* hs, const uint8_t* const* d_imgs, size_t d_step, uint8_t* const* d_fgmasks, int n, double learning_rate);
 /* device-resident variant: d_img rows of d_step bytes, d_fgmask W*H bytes (or null), asynchronous on the instance's stream */
 int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);
 

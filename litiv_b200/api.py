@@ -24,7 +24,7 @@ EXPORTS = [
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
     "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback",
-    "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics",
+    "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics", "lvb_apply_batch_device",
 ]
 
 
@@ -66,6 +66,7 @@ def lib():
         L.lvb_binclassif.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.lvb_binclassif_metrics.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_apply_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.lvb_apply_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_double]
         L.lvb_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_double]
         L.lvb_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_get_background_descriptors_image.argtypes = [C.c_void_p, C.c_void_p]
@@ -348,6 +349,23 @@ def apply_batch(subtractors, imgs, learningRate):
     mp = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
     _chk(lib().lvb_apply_batch(hs, ip, mp, n, float(learningRate)))
     return masks
+
+
+class DeviceBatch:
+    """n independent streams fed with device-resident frames (lvb_apply_batch_device): the handle / pointer arrays are built once"""
+
+    def __init__(self, subtractors):
+        self.subs = list(subtractors)
+        self.n = len(self.subs)
+        self._hs = (C.c_void_p * self.n)(*[s._h for s in self.subs])
+        self._ip = (C.c_void_p * self.n)()
+        self._mp = (C.c_void_p * self.n)()
+
+    def apply(self, d_img_ptrs, d_step, d_mask_ptrs, learningRate):
+        for i in range(self.n):
+            self._ip[i] = d_img_ptrs[i]
+            self._mp[i] = d_mask_ptrs[i] if d_mask_ptrs is not None else None
+        _chk(lib().lvb_apply_batch_device(self._hs, self._ip, d_step, self._mp, self.n, float(learningRate)))
 
 
 class LBSP:

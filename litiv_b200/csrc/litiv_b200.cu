@@ -14,6 +14,10 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstdio>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 
 using namespace lvb;
 
@@ -770,6 +774,61 @@ void sync(lvb_context* c) {
     sync_streams(c);
 }
 
+// ---- host-side enqueue pool: a frame is 12 kernel launches + ~10 event operations, so with many small streams the enqueueing
+// thread is the bottleneck (BASELINE config #5: 64 VGA streams per GPU). The batch entry points spread the instances over a few
+// persistent worker threads (the lv::WorkerPool pattern of apps/changedet/src/main.cpp:148-154); instances are independent.
+class EnqueuePool {
+public:
+    EnqueuePool() {
+        const char* e = getenv("LVB_ENQUEUE_THREADS");
+        int n = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        n = std::max(1, std::min(n, 64));
+        for(int t = 1; t < n; ++t) workers_.emplace_back([this] { loop(); }); // the calling thread is worker 0
+    }
+    ~EnqueuePool() {
+        { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+        cv_.notify_all();
+        for(std::thread& t : workers_) t.join();
+    }
+    /// runs job(0..n-1), each index once, on the pool + the caller; rethrows the first failure
+    void run(int n, const std::function<void(int)>& job) {
+        if(n <= 0) return;
+        std::unique_lock<std::mutex> l(m_);
+        job_ = &job; n_ = n; next_ = 0; done_ = 0; err_.clear(); ++gen_;
+        l.unlock();
+        cv_.notify_all();
+        work();
+        l.lock();
+        cv_done_.wait(l, [this] { return done_ == n_; });
+        job_ = nullptr;
+        if(!err_.empty()) throw std::runtime_error(err_);
+    }
+private:
+    void work() {
+        while(true) {
+            int i;
+            { std::lock_guard<std::mutex> l(m_); if(!job_ || next_ >= n_) return; i = next_++; }
+            std::string err;
+            try { (*job_)(i); } catch(const std::exception& e) { err = e.what(); }
+            std::lock_guard<std::mutex> l(m_);
+            if(!err.empty() && err_.empty()) err_ = err;
+            if(++done_ == n_) cv_done_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        while(true) {
+            { std::unique_lock<std::mutex> l(m_); cv_.wait(l, [&] { return stop_ || gen_ != seen; }); if(stop_) return; seen = gen_; }
+            work();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_; std::condition_variable cv_, cv_done_;
+    const std::function<void(int)>* job_ = nullptr;
+    int n_ = 0, next_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false; std::string err_;
+};
+EnqueuePool& enqueue_pool() { static EnqueuePool p; return p; }
+
 // ---- state export / import in the reference's layout (tests + checkpointing) ----
 struct StateDesc { const char* name; int kind; };
 enum { K_BITS, K_MAPF, K_FIN, K_COLPLANE, K_DESCPLANE, K_BGCOL, K_BGDESC, K_LUT, K_DS, K_ROI, K_SCALARS };
@@ -1249,8 +1308,28 @@ int lvb_sync_next(lvb_handle h) {
 int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* masks, int n, double lr) {
     LVB_TRY
     REQUIRE(hs && imgs && masks && n >= 0, "bad batch arguments");
-    for(int i = 0; i < n; ++i) { REQUIRE(hs[i] != nullptr, "null handle in batch"); apply_async(hs[i], imgs[i], masks[i], lr); }
-    for(int i = 0; i < n; ++i) { CK(cudaSetDevice(hs[i]->device)); sync(hs[i]); }
+    for(int i = 0; i < n; ++i) REQUIRE(hs[i] != nullptr, "null handle in batch");
+    enqueue_pool().run(n, [&](int i) { apply_async(hs[i], imgs[i], masks[i], lr); });
+    for(int i = 0; i < n; ++i) { CK(cudaSetDevice(hs[i]->device)); while(sync_next(hs[i])) {} }
+    LVB_CATCH
+}
+int lvb_apply_batch_device(lvb_handle* hs, const uint8_t* const* d_imgs, size_t d_step, uint8_t* const* d_masks, int n, double lr) {
+    LVB_TRY
+    REQUIRE(hs && d_imgs && n >= 0, "bad batch arguments");
+    for(int i = 0; i < n; ++i) {
+        REQUIRE(hs[i] != nullptr, "null handle in batch");
+        check_apply(hs[i], d_imgs[i], lr);
+        REQUIRE(d_step >= (size_t)hs[i]->W * hs[i]->C, "row step smaller than a row");
+    }
+    enqueue_pool().run(n, [&](int i) {
+        lvb_context* h = hs[i];
+        CK(cudaSetDevice(h->device));
+        if(h->ext_ptr != d_imgs[i] || h->ext_pitch != d_step) {
+            h->ext_tma = make_image_tmap(&h->tmap_ext, d_imgs[i], h->W, h->H, h->C, d_step) ? 1 : 0;
+            h->ext_ptr = d_imgs[i]; h->ext_pitch = d_step;
+        }
+        enqueue_frame(h, d_imgs[i], d_step, h->tmap_ext, h->ext_tma, (d_masks && d_masks[i]) ? d_masks[i] : h->d_mask, lr);
+    });
     LVB_CATCH
 }
 int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_mask, double lr) {

@@ -224,6 +224,40 @@ def test_async_batch_and_device_paths(lv, oracle):
     assert np.array_equal(s.sync(), r.apply(f, 0.0))
 
 
+def test_batch_device_enqueue_pool(lv):
+    """lvb_apply_batch_device: many instances fed with device-resident frames from a pool of host threads; every stream must end
+    up in exactly the state of an instance driven alone through the host API"""
+    torch = pytest.importorskip("torch")
+    w, h, n = 160, 120, 12
+    seqs = [SynthSequence(w, h, 3, seed=40 + i) for i in range(n)]
+    subs = [lv.BackgroundSubtractorSuBSENSE(seed=i) for i in range(n)]
+    refs = [lv.BackgroundSubtractorSuBSENSE(seed=i) for i in range(n)]
+    for s, r, q in zip(subs, refs, seqs):
+        s.initialize(q.frame(0)); r.initialize(q.frame(0))
+    pitch = (w * 3 + 127) // 128 * 128
+    d_frames = torch.zeros((n, h, pitch), dtype=torch.uint8, device="cuda")
+    d_masks = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    batch = lv.DeviceBatch(subs)
+    want = None
+    for t in range(1, 9):
+        frames = [q.frame(t) for q in seqs]
+        for i, f in enumerate(frames):
+            d_frames[i, :, :w * 3] = torch.from_numpy(f.reshape(h, w * 3)).cuda()
+        torch.cuda.synchronize()
+        batch.apply([d_frames[i].data_ptr() for i in range(n)], pitch, [d_masks[i].data_ptr() for i in range(n)], 1.0 if t < 5 else 0.0)
+        want = [r.apply(f, 1.0 if t < 5 else 0.0) for r, f in zip(refs, frames)]
+        for s in subs:
+            s.sync()
+        got = d_masks.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], want[i]), f"stream {i}, frame {t}"
+    for s, r in zip(subs, refs):
+        for name in ("bg_color", "bg_desc", "R", "T", "lastfg"):
+            assert np.array_equal(s.state_get(name), r.state_get(name)), name
+    with pytest.raises(lv.LitivError):
+        batch.apply([0] * n, pitch, None, 1.0)   # null frame pointer
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_two_deep_pipeline_matches_synchronous_apply(lv, pinned):
     """lvb_apply_async keeps two frames in flight (upload of k+1 overlaps the kernels of k); masks come back in order and are

@@ -16,6 +16,7 @@ ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--size", default="640x480")
 ap.add_argument("--algo", default="subsense", choices=["subsense", "lobster", "pawcs"])
 ap.add_argument("--channels", type=int, default=3)
+ap.add_argument("--batch", action="store_true", help="enqueue through lvb_apply_batch_device (pool of host threads) instead of one call per stream")
 ap.add_argument("--unique", type=int, default=4, help="distinct sequences (streams share synthetic frames, each has its own model and seed)")
 args = ap.parse_args()
 W, H = (int(v) for v in args.size.split("x"))
@@ -40,9 +41,16 @@ for s in range(args.streams):
 def pp(i, n):
     k = i % (2 * (n - 1)); return k if k < n else 2 * (n - 1) - k
 
+batch = lv.DeviceBatch(subs) if args.batch else None
+mask_ptrs = [d_masks[s].data_ptr() for s in range(args.streams)]
+frame_ptrs = [[d_frames[s % args.unique, t].data_ptr() for s in range(args.streams)] for t in range(NF)]
+
 def round_(k):
     lr = 16.0 if args.algo == "lobster" else (1.0 if k <= 50 else 0.0)
     t = pp(k, NF)
+    if batch is not None:
+        batch.apply(frame_ptrs[t], pitch, mask_ptrs, lr)
+        return
     for s, b in enumerate(subs):
         b.apply_device(d_frames[s % args.unique, t].data_ptr(), pitch, d_masks[s].data_ptr(), lr)
 
@@ -63,4 +71,4 @@ px = W * H * args.streams * args.steps
 print(json.dumps({"metric": args.algo + "_multistream_mpx_per_s", "value": px / wall_s / 1e6, "unit": "Mpx/s", "streams": args.streams, "frame": [W, H, C],
                   "steps": args.steps, "fps_per_stream": args.steps / wall_s, "streams_x_fps": args.streams * args.steps / wall_s,
                   "ms_per_round": wall_s / args.steps * 1e3, "host_enqueue_ms_per_round": host_s / args.steps * 1e3,
-                  "gpu_launches": lv.kernel_launch_count() - l0, "timing": "wall clock around enqueue + device synchronize (work spans many CUDA streams)"}))
+                  "gpu_launches": lv.kernel_launch_count() - l0, "enqueue": "lvb_apply_batch_device" if args.batch else "lvb_apply_device per stream", "timing": "wall clock around enqueue + device synchronize (work spans many CUDA streams)"}))
