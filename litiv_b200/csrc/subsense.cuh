@@ -119,6 +119,7 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
     typedef typename Pack<CH>::Rec Rec;
     typedef ScanCtx<CH> X;
     const uint32_t FULL = 0xFFFFFFFFu, lane = threadIdx.x;
+    __syncwarp(); // the parked contexts (wctx) are read by other lanes
     uint32_t m = __ballot_sync(FULL, undecided);
     while(m) {
         const uint32_t k = __popc(m);
@@ -181,6 +182,7 @@ __device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* w
             minDesc = min(minDesc, rd); minSum = min(minSum, rs);
             undecided = good < REQ && s < N;
         }
+        __syncwarp(); // worder[] is rewritten by the next round
         m = __ballot_sync(FULL, undecided);
     }
 }
