@@ -153,6 +153,43 @@ def test_subsense_scene_change_reset(lv, oracle, check_every_frame):
     _compare_state(g, o, INT_STATE, FLT_STATE, "scene change, end")
 
 
+def test_subsense_host_operations_between_pipelined_frames(lv, oracle):
+    """SuBSENSE leaves the neighbour writes of the latest frame queued for the next frame's scan and runs its mask chain on a side
+    stream: host-side operations issued between frames (getBackgroundImage, refreshModel, state import, setAutomaticModelReset,
+    a second instance interleaved) must see / produce exactly the oracle's state. No state is read between most frames, so the
+    frames really are pipelined."""
+    w, h, c = 320, 240, 3
+    seq = SynthSequence(w, h, c, seed=33)
+    g, o = _mk(lv, oracle, "subsense", seed=9)
+    g2, o2 = _mk(lv, oracle, "subsense", seed=10)   # an unrelated instance interleaved on the same device
+    f0 = seq.frame(0)
+    for a in (g, o, g2, o2):
+        a.initialize(f0)
+    for t in range(1, 25):
+        f = seq.frame(t)
+        lr = 1.0 if t <= 6 else 0.0
+        mg, mo = g.apply(f, lr), o.apply(f, lr)
+        assert np.array_equal(mg, mo), f"frame {t}"
+        if t % 3 == 0:
+            assert np.array_equal(g2.apply(f, 0.0), o2.apply(f, 0.0))
+        if t == 5:
+            assert np.array_equal(g.getBackgroundImage(), o.get_background_image())          # flushes the queued neighbour writes
+        if t == 9:
+            g.refreshModel(0.5); o.refresh_model(0.5)                                        # host refresh with writes still queued
+        if t == 12:
+            g.setAutomaticModelReset(False); o.set_auto_model_reset(False)
+        if t == 15:
+            fg = o.state_get("lastfg").copy(); fg[::7] = 255
+            g.state_set("lastfg", fg); o.state_set("lastfg", fg)                             # import into the ping-pong planes
+            r = o.state_get("R").copy(); r[::5] += 0.25
+            g.state_set("R", r); o.state_set("R", r)                                         # also refreshes the compact R plane
+        if t == 18:
+            assert np.array_equal(g.getBackgroundDescriptorsImage(), o.get_background_descriptors_image())
+            g.refreshModel(1.0, True); o.refresh_model(1.0, True)
+    _compare_state(g, o, INT_STATE, FLT_STATE, "host operations, end")
+    _compare_state(g2, o2, INT_STATE, FLT_STATE, "interleaved instance, end")
+
+
 @pytest.mark.parametrize("algo,w,h,c,n", [("subsense", 320, 240, 3, 130), ("lobster", 320, 240, 1, 80)])
 def test_tier3_sequence(lv, oracle, algo, w, h, c, n):
     """end-to-end masks over a longer sequence with the samples/changedet learning-rate protocol (main.cpp:56)"""
