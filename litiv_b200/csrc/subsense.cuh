@@ -241,7 +241,7 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
     Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
     const Rec* bgr = (const Rec*)A.bg + pix;
-    if(active) {
+    if(in_img) { // not `active`: that would chain these loads behind the ROI word's round trip (the planes cover every pixel)
         R = A.r_plane[pix];
         lc = ((const Col*)A.prev_color)[pix];
         ld = ((const Desc*)A.prev_desc)[pix];
@@ -464,9 +464,18 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
     __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
     __shared__ CtlSlice s_ctl;
+    // small read-only tables behind data-dependent indices (T(x), the hand-off distances): staged in shared memory so that the
+    // look-ups cost a fixed ~25 cycles instead of an L1 miss in the middle of the dependency chain (L1 is streamed through by
+    // the feedback maps). [0,257): floor(2^32/n) ; then i/colorRange ; then i/descRange
+    constexpr int NCOL = (CH == 1 ? 255 : 765) + 1, NDES = (CH == 1 ? 16 : 48) + 1;
+    __shared__ uint32_t s_magic[257];
+    __shared__ float s_divc[NCOL], s_divd[NDES];
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
+    for(int i = tid; i < NCOL; i += TILE_W * TILE_H) s_divc[i] = A.div_color[i];
+    if(tid < NDES) s_divd[tid] = A.div_desc[tid];
     if(tid < 2) s_cnt[tid] = 0;
     if(tid < GHOST_ROWS * 3) {
         const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
@@ -493,7 +502,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     float2 fin = make_float2(0, 0);
     uint2 hand = make_uint2(0, 0);
     Col cur_pack = Col(); Desc intra_pack = Desc();
-    if(active) {
+    if(in_img) { // not `active`: that would chain these loads behind the ROI word's round trip (the planes cover every pixel)
         m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1];
         fin = A.fin[pix];
         hand = A.hand[pix];
@@ -518,15 +527,14 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // D_last (:254-255 / :396-397)
-        // i / colorRange and i / descRange come from 3 KB of host-tabulated IEEE quotients (read-only path, L1 resident) instead
-        // of four __fdiv_rn sequences per pixel
-        const float normLast = __fmul_rn(__fadd_rn(__ldg(A.div_color + lastL1), __ldg(A.div_desc + lastHd)), 0.5f); // x/2 == x*0.5 exactly
+        // i / colorRange and i / descRange come from 3 KB of host-tabulated IEEE quotients instead of four __fdiv_rn sequences per pixel
+        const float normLast = __fmul_rn(__fadd_rn(s_divc[min(lastL1, (uint32_t)NCOL - 1u)], s_divd[min(lastHd, (uint32_t)NDES - 1u)]), 0.5f); // x/2 == x*0.5 exactly
         Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
 
         const uint32_t pixid = (uint32_t)(y * A.W + x);
         const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
         const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
-        const float baseMin = __fmul_rn(__fadd_rn(__ldg(A.div_color + min(minSum, colorRange)), __ldg(A.div_desc + min(minDesc, descRange))), 0.5f);
+        const float baseMin = __fmul_rn(__fadd_rn(s_divc[min(minSum, colorRange)], s_divd[min(minDesc, descRange)]), 0.5f);
         if(is_fg) { // foreground (:256-269 / :398-413)
             const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
             DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
@@ -547,7 +555,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
             const uint32_t LR2 = LR / 2u + 1u;
             const bool tab = !A.lr_fixed && LR <= 256u;
-            const uint32_t mg = A.lr_fixed ? A.lr_magic : __ldg(A.magic + (tab ? LR : 0u)), mg2 = A.lr_fixed ? A.lr2_magic : __ldg(A.magic + (tab ? LR2 : 0u));
+            const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
             const bool fastm = A.lr_fixed || tab;
             if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
                 const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
