@@ -42,11 +42,44 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons DURING the timed region: NVML (a few hundred samples per second) when nvidia_ml_py is
+    importable, else the nvidia-smi query line of B200_PROFILING.md (a handful of samples)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")) and index < len(vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+            while not self._stop_evt.is_set():
+                try:
+                    sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.rows.append([str(sm), str(self.max_sm)] + ["Active" if r & b else "Not Active" for b, _ in bits])
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.004)
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._stop_evt.is_set():
             try:
@@ -63,9 +96,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_frames(seed, n):
