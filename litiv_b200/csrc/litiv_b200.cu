@@ -129,6 +129,7 @@ struct lvb_context {
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
     uint32_t* magic = nullptr; // [257] floor(2^32 / n)
     float* r_plane = nullptr;  // compact R(x) plane read by the SuBSENSE scan kernel
+    uint8_t* eval_gt = nullptr; uint8_t* eval_roi = nullptr; unsigned long long* eval_cnt = nullptr; // lvb_binclassif_accumulate scratch (W*H each)
     float* div_tab = nullptr;  // [colorRange + 1] i / colorRange, then [descRange + 1] i / descRange
     FrameCtl* ctl = nullptr;
     float* dsLT = nullptr; float* dsST = nullptr;
@@ -163,11 +164,11 @@ struct lvb_context {
     size_t rec_bytes() const { return C == 1 ? 4 : 16; }
 
     void free_all() {
-        void* ptrs[] = {r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -1581,46 +1582,52 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
 
 /// lv::BinClassif::accumulate (datasets/src/metrics.cpp:21-61) on the device; see csrc/metrics.cuh
 static void binclassif_run(cudaStream_t st, int W, int H, int WW, const uint8_t* d_classif, const uint32_t* d_bits, const uint8_t* gt, const uint8_t* roi,
-                           uint64_t counters[6]) {
-    REQUIRE(counters != nullptr, "null counters");
+                           uint64_t counters[6], uint8_t* d_gt, uint8_t* d_roi, unsigned long long* d_cnt) {
     const size_t npx = (size_t)W * H;
-    if(!gt) { counters[BC_DC] += npx; return; } // metrics.cpp:26-29: no groundtruth -> every pixel is a don't-care
-    uint8_t* d_gt = dalloc<uint8_t>(st, npx, false), *d_roi = nullptr;
-    unsigned long long* d_cnt = nullptr;
-    try {
-        d_cnt = dalloc<unsigned long long>(st, BC_COUNT);
-        CK(cudaMemcpyAsync(d_gt, gt, npx, cudaMemcpyHostToDevice, st));
-        if(roi) { d_roi = dalloc<uint8_t>(st, npx, false); CK(cudaMemcpyAsync(d_roi, roi, npx, cudaMemcpyHostToDevice, st)); }
-        BinClassifArgs A{};
-        A.W = W; A.H = H; A.WW = WW; A.classif = d_classif; A.cpitch = (size_t)W; A.classif_bits = d_bits; A.gt = d_gt; A.gpitch = (size_t)W;
-        A.roi = d_roi; A.rpitch = (size_t)W; A.counters = d_cnt;
-        binclassif_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, st>>>(A); LAUNCHED();
-        unsigned long long h[BC_COUNT];
-        d2h(st, h, d_cnt, sizeof(h));
-        for(int i = 0; i < BC_COUNT; ++i) counters[i] += h[i];
-    } catch(...) { cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt); throw; }
-    cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt);
+    CK(cudaMemsetAsync(d_cnt, 0, BC_COUNT * sizeof(unsigned long long), st));
+    CK(cudaMemcpyAsync(d_gt, gt, npx, cudaMemcpyHostToDevice, st));
+    if(roi) CK(cudaMemcpyAsync(d_roi, roi, npx, cudaMemcpyHostToDevice, st));
+    BinClassifArgs A{};
+    A.W = W; A.H = H; A.WW = WW; A.classif = d_classif; A.cpitch = (size_t)W; A.classif_bits = d_bits; A.gt = d_gt; A.gpitch = (size_t)W;
+    A.roi = roi ? d_roi : nullptr; A.rpitch = (size_t)W; A.counters = d_cnt;
+    binclassif_kernel<<<dim3((W + 31) / 32, (H + 7) / 8), dim3(32, 8), 0, st>>>(A); LAUNCHED();
+    unsigned long long h[BC_COUNT];
+    d2h(st, h, d_cnt, sizeof(h));
+    for(int i = 0; i < BC_COUNT; ++i) counters[i] += h[i];
 }
 int lvb_binclassif_accumulate(lvb_handle h, const uint8_t* gt, const uint8_t* roi, uint64_t counters[6]) {
     LVB_TRY
-    REQUIRE(h != nullptr, "null handle");
+    REQUIRE(h != nullptr && counters != nullptr, "null argument");
     REQUIRE(h->initialized, "algo & model must be initialized first");
     CK(cudaSetDevice(h->device));
+    const size_t npx = (size_t)h->W * h->H;
+    if(!gt) { counters[BC_DC] += npx; return 0; } // metrics.cpp:26-29: no groundtruth -> every pixel is a don't-care
     while(sync_next(h)) {}
-    sync_streams(h);
-    binclassif_run(h->stream, h->W, h->H, h->WW, nullptr, h->lastfg, gt, roi, counters);
+    if(h->s_post) CK(cudaStreamSynchronize(h->s_post));   // the final mask (lastfg) is written on the mask stream
+    if(!h->eval_gt) {   // scratch kept with the instance: scoring runs once per frame
+        h->eval_gt = dalloc<uint8_t>(h->stream, npx, false); h->eval_roi = dalloc<uint8_t>(h->stream, npx, false);
+        h->eval_cnt = dalloc<unsigned long long>(h->stream, BC_COUNT);
+    }
+    // SuBSENSE: on the (now idle) mask stream, beside the feedback kernel still running on the instance stream
+    binclassif_run(h->algo == LVB_ALGO_SUBSENSE && h->s_post ? h->s_post : h->stream, h->W, h->H, h->WW, nullptr, h->lastfg, gt, roi, counters,
+                   h->eval_gt, h->eval_roi, h->eval_cnt);
     LVB_CATCH
 }
 int lvb_binclassif(const uint8_t* classif, const uint8_t* gt, const uint8_t* roi, int W, int H, uint64_t counters[6], int device) {
     LVB_TRY
-    REQUIRE(classif && W >= 1 && H >= 1, "binary classifier results must be non-empty and of type 8UC1");
+    REQUIRE(classif && counters && W >= 1 && H >= 1, "binary classifier results must be non-empty and of type 8UC1");
     REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
-    CK(cudaSetDevice(device));
     const size_t npx = (size_t)W * H;
-    uint8_t* d_c = nullptr;
-    if(gt) { d_c = dalloc<uint8_t>((cudaStream_t)0, npx, false); CK(cudaMemcpy(d_c, classif, npx, cudaMemcpyHostToDevice)); }
-    try { binclassif_run((cudaStream_t)0, W, H, (W + 31) / 32, d_c, nullptr, gt, roi, counters); } catch(...) { cudaFree(d_c); throw; }
-    cudaFree(d_c);
+    if(!gt) { counters[BC_DC] += npx; return 0; }
+    CK(cudaSetDevice(device));
+    uint8_t* d_c = nullptr, *d_gt = nullptr, *d_roi = nullptr; unsigned long long* d_cnt = nullptr;
+    try {
+        d_c = dalloc<uint8_t>((cudaStream_t)0, npx, false); d_gt = dalloc<uint8_t>((cudaStream_t)0, npx, false);
+        d_roi = dalloc<uint8_t>((cudaStream_t)0, npx, false); d_cnt = dalloc<unsigned long long>((cudaStream_t)0, BC_COUNT);
+        CK(cudaMemcpy(d_c, classif, npx, cudaMemcpyHostToDevice));
+        binclassif_run((cudaStream_t)0, W, H, (W + 31) / 32, d_c, nullptr, gt, roi, counters, d_gt, d_roi, d_cnt);
+    } catch(...) { cudaFree(d_c); cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt); throw; }
+    cudaFree(d_c); cudaFree(d_gt); cudaFree(d_roi); cudaFree(d_cnt);
     LVB_CATCH
 }
 /// BinClassifMetrics (datasets/include/litiv/datasets/metrics.hpp:213-257): recall, specificity, FPR, FNR, PBC, precision, F-measure, MCC.
