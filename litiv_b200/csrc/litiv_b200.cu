@@ -233,18 +233,16 @@ void flush_pending(lvb_context* c) {
     mark_nb_applied_kernel<<<1, 1, 0, c->stream>>>(c->ctl, c->nb_seq); LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
 }
-/// conditional refreshModel on the instance stream. wait_seq != 0 (in-frame use): the grid is kept to two CTAs per SM because
-/// a fired request polls FrameCtl::chain_done while the mask stream still needs room to run.
-void launch_refresh(lvb_context* c, uint32_t wait_seq = 0) {
+/// conditional refreshModel on the instance stream (exits at once unless FrameCtl::do_refresh is set)
+void launch_refresh(lvb_context* c) {
     RefreshArgs R{};
     R.W = c->W; R.H = c->H; R.Wp = c->Wp; R.WW = c->WW; R.CH = c->C; R.N = c->P.n_samples; R.plane = c->plane;
     R.bg = c->bg; R.last_color = c->last_color; R.last_desc = c->last_desc;
     R.roi_bits = c->roi_bits; R.lastfg_bits = c->lastfg; R.maps = c->algo == LVB_ALGO_SUBSENSE ? c->maps : nullptr;
     R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
     const dim3 tgd = tile_grid(c);
-    R.wait_seq = wait_seq;
     R.intents = c->intents; R.pending_seq = c->algo == LVB_ALGO_SUBSENSE ? c->nb_seq : 0u;
-    const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, wait_seq ? 148 * 2 : 148 * 8);
+    const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, 148 * 8);
     if(c->C == 1) refresh_model_kernel<1><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     else refresh_model_kernel<3><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     LAUNCHED();
@@ -697,7 +695,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         CK(cudaStreamWaitEvent(st, c->ev_ds, 0));
         TailArgs T{};
         T.ctl = c->ctl; T.lut = c->lut; T.rel = c->P.rel_lbsp_threshold; T.lbsp_off = c->P.lbsp_threshold_offset; T.min_color = c->P.color_dist_threshold;
-        T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed;
+        T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed; T.wait_seq = seq;
         cudaEvent_t fb0 = nullptr, fb1 = nullptr;
         if(c->profile) { CK(cudaEventCreate(&fb0)); CK(cudaEventCreate(&fb1)); CK(cudaEventRecord(fb0, st)); }
         if(C == 1) subsense_feedback<1><<<tg, tb, 0, st>>>(A, T); else subsense_feedback<3><<<tg, tb, 0, st>>>(A, T);
@@ -710,7 +708,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         c->ghost_idx ^= 1;
         std::swap(c->raw, c->raw_alt); std::swap(c->blinks, c->blinks_alt); std::swap(c->lastfg, c->lastfg_alt); std::swap(c->fin, c->fin_alt);
         c->sub_frame += 1;
-        launch_refresh(c, seq); mark(st, "refresh"); // reads lastfg(k) (only when the frame tail requested it: polls the completion counter first)
+        launch_refresh(c); mark(st, "refresh"); // reads lastfg(k), only when the frame tail requested it (the tail waited for the mask)
     } else { // LOBSTER
         if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();

@@ -395,6 +395,7 @@ struct TailArgs {
     FrameCtl* ctl; uchar* lut;
     float rel; int lbsp_off; int min_color; int avg_samples; int N; int dsW, dsH;
     uint64_t seed;
+    uint32_t wait_seq;         // a requested reset holds this warp until FrameCtl::chain_done reaches this frame (see below)
 };
 __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
     FrameCtl* ctl = A.ctl;
@@ -438,6 +439,15 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
         ctl->aLT = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples));
         ctl->aST = __fdiv_rn(1.0f, (float)min(f, (uint32_t)A.avg_samples / 4u));
         ctl->blocks_done = 0;
+        // A requested reset (rare: scene change) resamples the model from pixels that are background in THIS frame's final mask,
+        // which the mask stream is still producing. This one warp (one resident CTA per instance, so any number of instances may
+        // wait at once without starving the mask kernels they wait for) holds the feedback kernel open until the mask is complete;
+        // the refresh kernel behind it in the stream then needs no synchronisation of its own.
+        if(ctl->do_refresh && A.wait_seq) {
+            volatile uint32_t* flag = &ctl->chain_done;
+            while((int32_t)(*flag - A.wait_seq) < 0) __nanosleep(500);
+            __threadfence();
+        }
     }
     dir = __shfl_sync(0xFFFFFFFFu, dir, 0);
     for(int t = lane; t < 256; t += 32) {
@@ -724,7 +734,6 @@ struct RefreshArgs {
     FrameCtl* ctl;
     uint64_t seed;
     int recompute_desc;        // LOBSTER: descriptor of the sampled pixel is recomputed from last_color
-    uint32_t wait_seq;         // != 0: a requested refresh first waits until ctl->chain_done reaches this frame (lastfg complete)
     const ushort* intents; uint32_t pending_seq; // SuBSENSE: neighbour writes of this frame not yet in the model are applied first
 };
 
@@ -735,17 +744,8 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
     typedef typename Pack<CH>::Rec Rec;
     FrameCtl* ctl = A.ctl;
     if(!ctl->do_refresh) return;
-    // launched every frame with a small grid (the request is decided on the device): a CTA walks 32x8 tiles grid-stride.
-    // The request is rare (scene change); when it fires, the last-foreground mask of THIS frame is still being produced on the
-    // mask stream, so the few resident CTAs of this grid poll the completion counter before reading it.
-    if(A.wait_seq) {
-        if(threadIdx.x == 0 && threadIdx.y == 0) {
-            volatile uint32_t* flag = &ctl->chain_done;
-            while((int32_t)(*flag - A.wait_seq) < 0) __nanosleep(500);
-            __threadfence();
-        }
-        __syncthreads();
-    }
+    // launched every frame (the request is decided on the device, by the frame tail): a CTA walks 32x8 tiles grid-stride. When a
+    // request fires, the tail has already waited for this frame's final mask (lastfg) before the feedback kernel ended.
     const bool apply_nb = A.pending_seq != 0u && ctl->nb_applied_seq != A.pending_seq;
     const int tiles_x = A.Wp / 32, ntiles = tiles_x * ((A.H + 7) / 8);
     for(int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
