@@ -275,20 +275,56 @@ void paw_launch_refresh(lvb_context* c, const PawArgs& A, uint32_t frame_off) {
     pawcs_refresh_done<<<1, 1, 0, c->stream>>>(A); LAUNCHED();
 }
 
+/// cv::resize(INTER_AREA) of a one-channel 8-bit image to (dw, dh), dw = W/8, dh = H/8: the exact 8x8 mean when both dimensions
+/// divide by 8 (OpenCV's integer-scale fast path), OpenCV's general area path otherwise (column / row tables of
+/// computeResizeAreaTab, float accumulation in ResizeArea_Invoker's order; same arithmetic as csrc/subsense.cuh area_general_pixel)
+void host_resize_area(const uint8_t* src, int W, int H, int dw, int dh, uint8_t* dst) {
+    auto sat = [](float v) { const long q = std::lrint((double)v); return (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q); };
+    if(W % 8 == 0 && H % 8 == 0) {
+        for(int y = 0; y < dh; ++y) for(int x = 0; x < dw; ++x) {
+            int sum = 0;
+            for(int dy = 0; dy < 8; ++dy) for(int dx = 0; dx < 8; ++dx) sum += src[(size_t)(y * 8 + dy) * W + x * 8 + dx];
+            dst[(size_t)y * dw + x] = sat((float)sum * (1.0f / 64));
+        }
+        return;
+    }
+    struct Cell { int first, n; float a_first, a_mid, a_last; bool hf, hl; };
+    auto cell = [](int d, int ssize, double scale) {
+        const double fs1 = d * scale, fs2 = fs1 + scale, cw = std::min(scale, ssize - fs1);
+        int s1 = (int)std::ceil(fs1), s2 = (int)std::floor(fs2);
+        s2 = std::min(s2, ssize - 1); s1 = std::min(s1, s2);
+        Cell c;
+        c.hf = (s1 - fs1) > 1e-3; c.hl = (fs2 - s2) > 1e-3;
+        c.a_first = (float)((s1 - fs1) / cw); c.a_mid = (float)(1.0 / cw); c.a_last = (float)(std::min(std::min(fs2 - s2, 1.), cw) / cw);
+        c.first = c.hf ? s1 - 1 : s1; c.n = (s2 - s1) + (c.hf ? 1 : 0) + (c.hl ? 1 : 0);
+        return c;
+    };
+    auto weight = [](const Cell& c, int i) { return (c.hf && i == 0) ? c.a_first : (c.hl && i == c.n - 1) ? c.a_last : c.a_mid; };
+    const double sx = 1. / ((double)dw / W), sy = 1. / ((double)dh / H);
+    for(int y = 0; y < dh; ++y) {
+        const Cell cy = cell(y, H, sy);
+        for(int x = 0; x < dw; ++x) {
+            const Cell cx = cell(x, W, sx);
+            float sum = 0.f;
+            for(int j = 0; j < cy.n; ++j) {
+                float buf = 0.f;
+                for(int i = 0; i < cx.n; ++i) { const float t = (float)src[(size_t)(cy.first + j) * W + cx.first + i] * weight(cx, i); buf = buf + t; }
+                const float t = weight(cy, j) * buf;
+                sum = j == 0 ? t : sum + t;
+            }
+            dst[(size_t)y * dw + x] = sat(sum);
+        }
+    }
+}
+
 /// PAWCS part of initialize (PAWCS.cpp:431-557); the common part (ROI, LUT, last colour / descriptor frames) is already done
 void paw_initialize(lvb_context* c, FrameCtl& f, size_t orig) {
     const int W = c->W, H = c->H, C = c->C;
-    REQUIRE(W % 8 == 0 && H % 8 == 0, "PAWCS: frame sizes that are not multiples of 8 are not supported yet");
     REQUIRE(c->P.n_samples / 2 > 0, "max local/global word counts must be positive");
     const size_t npx = (size_t)W * H, bp = (size_t)H * c->WW;
     c->dsW = W / 8; c->dsH = H / 8; c->gW = W / 2; c->gH = H / 2;
     std::vector<uint8_t> dsr((size_t)c->dsW * c->dsH);
-    for(int y = 0; y < c->dsH; ++y) for(int x = 0; x < c->dsW; ++x) { // cv::resize(ROI, INTER_AREA, 1/8) (:446)
-        int sum = 0;
-        for(int dy = 0; dy < 8; ++dy) for(int dx = 0; dx < 8; ++dx) sum += c->roi_host[(size_t)(y * 8 + dy) * W + x * 8 + dx];
-        const long q = std::lrint((double)((float)sum * (1.0f / 64)));
-        dsr[(size_t)y * c->dsW + x] = (uint8_t)(q < 0 ? 0 : q > 255 ? 255 : q);
-    }
+    host_resize_area(c->roi_host.data(), W, H, c->dsW, c->dsH, dsr.data()); // cv::resize(ROI, INTER_AREA, 1/8) (:446)
     const int maxG = c->P.n_samples / 2, qvga = 320 * 240, defk = c->P.median_blur_kernel_size;
     c->NW = c->P.n_samples;
     if(orig >= npx / 2 && (int)npx >= qvga) {

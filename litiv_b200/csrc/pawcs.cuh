@@ -587,20 +587,25 @@ __global__ void __launch_bounds__(128) pawcs_motion_kernel(const PawArgs A) {
     if(i < A.dsW * A.dsH) {
         const int dx = i % A.dsW, dy = i / A.dsW;
         const float aLT = A.ctl->aLT, aST = A.ctl->aST;
-        uint32_t sum[CH];
+        float vv[CH];
+        if((A.W & 7) == 0 && (A.H & 7) == 0) { // OpenCV's integer-scale fast path: exact 8x8 mean
+            uint32_t sum[CH];
 #pragma unroll
-        for(int c = 0; c < CH; ++c) sum[c] = 0;
-        for(int r = 0; r < 8; ++r) {
-            const uchar* p = A.img + (size_t)(dy * 8 + r) * A.ipitch + (size_t)dx * 8 * CH;
+            for(int c = 0; c < CH; ++c) sum[c] = 0;
+            for(int r = 0; r < 8; ++r) {
+                const uchar* p = A.img + (size_t)(dy * 8 + r) * A.ipitch + (size_t)dx * 8 * CH;
 #pragma unroll
-            for(int b = 0; b < 8; ++b)
+                for(int b = 0; b < 8; ++b)
 #pragma unroll
-                for(int c = 0; c < CH; ++c) sum[c] += p[b * CH + c];
-        }
+                    for(int c = 0; c < CH; ++c) sum[c] += p[b * CH + c];
+            }
+#pragma unroll
+            for(int c = 0; c < CH; ++c) vv[c] = fminf(fmaxf(rintf(__fmul_rn((float)sum[c], 1.0f / 64)), 0.f), 255.f);
+        } else area_general_pixel<CH>(A.img, A.ipitch, A.W, A.H, A.dsW, A.dsH, dx, dy, vv);
         float t = 0.0f;
 #pragma unroll
         for(int c = 0; c < CH; ++c) {
-            const float v = fminf(fmaxf(rintf(__fmul_rn((float)sum[c], 1.0f / 64)), 0.f), 255.f);
+            const float v = vv[c];
             const size_t k = (size_t)i * CH + c;
             const float lt = __fadd_rn(__fmul_rn(v, aLT), __fmul_rn(A.dsLT[k], __fsub_rn(1.0f, aLT)));
             const float st = __fadd_rn(__fmul_rn(v, aST), __fmul_rn(A.dsST[k], __fsub_rn(1.0f, aST)));
@@ -657,13 +662,16 @@ __global__ void __launch_bounds__(128) pawcs_model_dist_kernel(const PawArgs A) 
     if(i < A.dsW * A.dsH && A.ds_roi[i] == 255) {
         const int dx = i % A.dsW, dy = i / A.dsW;
         float bg[CH], lt[CH];
+        if((A.W & 7) == 0 && (A.H & 7) == 0) {
 #pragma unroll
-        for(int c = 0; c < CH; ++c) {
-            uint32_t s = 0;
-            for(int r = 0; r < 8; ++r) for(int b = 0; b < 8; ++b) s += A.bgimg[((size_t)(dy * 8 + r) * A.W + dx * 8 + b) * CH + c];
-            bg[c] = fminf(fmaxf(rintf(__fmul_rn((float)s, 1.0f / 64)), 0.f), 255.f);
-            lt[c] = A.dsLT[(size_t)i * CH + c];
-        }
+            for(int c = 0; c < CH; ++c) {
+                uint32_t s = 0;
+                for(int r = 0; r < 8; ++r) for(int b = 0; b < 8; ++b) s += A.bgimg[((size_t)(dy * 8 + r) * A.W + dx * 8 + b) * CH + c];
+                bg[c] = fminf(fmaxf(rintf(__fmul_rn((float)s, 1.0f / 64)), 0.f), 255.f);
+            }
+        } else area_general_pixel<CH>(A.bgimg, (size_t)A.W * CH, A.W, A.H, A.dsW, A.dsH, dx, dy, bg);
+#pragma unroll
+        for(int c = 0; c < CH; ++c) lt[c] = A.dsLT[(size_t)i * CH + c];
         float t = 0.0f;
 #pragma unroll
         for(int c = 0; c < CH; ++c) t = __fadd_rn(t, fabsf(__fsub_rn(lt[c], bg[c])));

@@ -187,17 +187,23 @@ struct PAWCS : BgsBase {
         if(C == 1) refresh_impl<1>(base_occ, decr_frac, force); else refresh_impl<3>(base_occ, decr_frac, force);
     }
 
+    /// cv::resize(src, dst, Size(W/8, H/8), 0, 0, INTER_AREA): OpenCV's integer-scale fast path when both dimensions divide by 8,
+    /// its general area path otherwise (lvo_common.hpp)
+    void ds_area(const uchar* src, int ch, uchar* dst) const {
+        if(W % 8 == 0 && H % 8 == 0) resize_area_exact(src, W, H, ch, 8, dst);
+        else resize_area_general(src, W, H, ch, dsW, dsH, dst);
+    }
+
     // ------------------------------------------------------------------------------------------
     // initialize (PAWCS.cpp:431-557)
     // ------------------------------------------------------------------------------------------
     void initialize(const uchar* img, int w, int h, int c, const uchar* roi_or_null) {
         if(P.n_samples <= 0 || P.n_samples / 2 <= 0) throw std::runtime_error("max local/global word counts must be positive");
-        if(w % 8 || h % 8) throw std::runtime_error("PAWCS: frame sizes that are not multiples of 8 are not supported yet");
         initialize_common(img, w, h, c, roi_or_null);
         moving_camera = false; auto_reset = true;
         dsW = W / 8; dsH = H / 8; gW = W / 2; gH = H / 2;
         ds_roi.assign((size_t)dsW * dsH, 0);
-        resize_area_exact(roi.data(), W, H, 1, 8, ds_roi.data());
+        ds_area(roi.data(), 1, ds_roi.data());
         last_nonflat_ratio = 0.0f;
         NW = P.n_samples;
         const int maxG = P.n_samples / 2, qvga = 320 * 240, defk = P.median_blur_kernel_size;
@@ -567,7 +573,7 @@ struct PAWCS : BgsBase {
         }
         last_nonflat_ratio = ratio;
         // frame-level analysis (:1474-1516)
-        resize_area_exact(img, W, H, C, 8, ds_frame.data());
+        ds_area(img, C, ds_frame.data());
         const float bLT = 1.0f - aLT, bST = 1.0f - aST;
         for(size_t i = 0; i < dsLT.size(); ++i) {
             const float sLT = (float)ds_frame[i] * aLT, dLT = dsLT[i] * bLT; dsLT[i] = sLT + dLT;
@@ -579,7 +585,7 @@ struct PAWCS : BgsBase {
             if((frame_idx % BOOTSTRAP_WIN) == 0) {
                 std::vector<uchar> bg(npx * C), dsbg((size_t)dsW * dsH * C);
                 get_background_image(bg.data());
-                resize_area_exact(bg.data(), W, H, C, 8, dsbg.data());
+                ds_area(bg.data(), C, dsbg.data());
                 std::vector<float> dsbgf(dsbg.begin(), dsbg.end());
                 const float ml1 = masked_l1(dsLT.data(), dsbgf.data(), ds_roi.data(), true) / (float)ds_roi_count;
                 const float mcd = C == 1 ? 0.0f : masked_cdist3(dsLT.data(), dsbgf.data(), ds_roi.data()) / (float)ds_roi_count;

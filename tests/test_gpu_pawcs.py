@@ -37,7 +37,8 @@ def _compare(g, o, tag, skip=()):
     assert np.allclose(sa[:13], sb[:13], rtol=1e-6), f"{tag}: scalars differ {sa[:13]} vs {sb[:13]}"
 
 
-@pytest.mark.parametrize("w,h,c,nframes,roi", [(160, 120, 3, 20, None), (160, 120, 1, 16, None), (320, 240, 3, 10, None), (96, 72, 3, 12, "roi")])
+@pytest.mark.parametrize("w,h,c,nframes,roi", [(160, 120, 3, 20, None), (160, 120, 1, 16, None), (320, 240, 3, 10, None), (96, 72, 3, 12, "roi"),
+                                                  (330, 250, 3, 8, None), (75, 61, 1, 10, "roi")])   # sizes that are not multiples of 8 (general INTER_AREA)
 def test_pawcs_state_parity(lv, oracle, w, h, c, nframes, roi):
     seq = SynthSequence(w, h, c, seed=13)
     roi_img = None
@@ -86,10 +87,12 @@ def test_pawcs_import_oracle_snapshot_and_refresh(lv, oracle):
     _compare(g, o, "frame after refresh")
 
 
-def test_pawcs_learning_rate_override_and_long_run(lv, oracle):
+@pytest.mark.parametrize("w,h", [(64, 48), (70, 51)])
+def test_pawcs_learning_rate_override_and_long_run(lv, oracle, w, h):
     """learning-rate override (incl. +inf), the end of the bootstrap window (frame 500: model check, maintenance recalc at
-    256/512) and a scene change that triggers the frame-level reset; masks compared every frame, full state at checkpoints"""
-    w, h, c = 64, 48, 3
+    256/512) and a scene change that triggers the frame-level reset; masks compared every frame, full state at checkpoints.
+    70x51: neither dimension divides by 8 nor by 2 (general INTER_AREA for the motion analysis, the ROI and the model check)"""
+    c = 3
     seq = SynthSequence(w, h, c, seed=21)
     g, o = _mk(lv, oracle, seed=9)
     f0 = seq.frame(0)
@@ -111,8 +114,8 @@ def test_pawcs_api_errors(lv):
     g = lv.BackgroundSubtractorPAWCS()
     with pytest.raises(lv.LitivError, match="initialized"):
         g.apply(np.zeros((48, 64, 3), np.uint8))
-    with pytest.raises(lv.LitivError, match="multiples of 8"):
-        g.initialize(np.zeros((50, 70, 3), np.uint8))
+    g.initialize(np.zeros((50, 70, 3), np.uint8))   # not a multiple of 8: general INTER_AREA path
+    assert g.apply(np.zeros((50, 70, 3), np.uint8)).shape == (50, 70)
     g.initialize(np.zeros((48, 64, 3), np.uint8))
     with pytest.raises(lv.LitivError, match="fraction"):
         g.refreshModel(1, 1.5)
