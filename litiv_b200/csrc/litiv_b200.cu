@@ -601,7 +601,8 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     const int recalc = (frame % (grate << 5)) == 0, update = (frame % grate) == 0, check_model = (frame % PAW_BOOTSTRAP) == 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
-    if(C == 1) pawcs_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
+    if(c->lut_small) { if(C == 1) pawcs_phaseA<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+    else { if(C == 1) pawcs_phaseA<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
     LAUNCHED();
     if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
     // phase B only touches the local dictionaries: auxiliary stream, beside the global-dictionary and mask kernels

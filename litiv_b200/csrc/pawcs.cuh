@@ -80,9 +80,15 @@ __device__ __forceinline__ uint32_t paw_color_dist(uint32_t cur, uint32_t bg, ui
     cd = 0;
     if(nonconst && nonnull) {
         const uint32_t cs = c0 * c0 + c1 * c1 + c2 * c2, bs = b0 * b0 + b1 * b1 + b2 * b2, mix = c0 * b0 + c1 * b1 + c2 * b2;
-        // floor(mix^2 / max(bs,1)) exactly: mix^2 < 2^36 so the correctly rounded double quotient never crosses an integer
-        const unsigned long long q = (unsigned long long)__double2ll_rd(__ddiv_rn((double)((unsigned long long)mix * mix), (double)max(bs, 1u)));
-        cd = (uint32_t)__fsqrt_rn((float)((unsigned long long)cs - q));
+        // floor(mix^2 / max(bs,1)) exactly, without a 64-bit or double division: q <= cs < 2^18 (Cauchy-Schwarz), so a single-
+        // precision estimate (relative error < 2^-21) is off by at most one; the 64-bit remainder fixes it
+        const unsigned long long m2 = (unsigned long long)mix * mix;
+        const uint32_t d = max(bs, 1u);
+        uint32_t q = (uint32_t)__fdividef(__fmul_rn((float)mix, (float)mix), (float)d);
+        long long r = (long long)m2 - (long long)((unsigned long long)q * d);
+        while(r < 0) { --q; r += d; }
+        while(r >= (long long)d) { ++q; r -= d; }
+        cd = (uint32_t)__fsqrt_rn((float)(cs - q));
     }
     return (l1 >> 1) + cd * 4u;
 }
@@ -122,7 +128,7 @@ __device__ __forceinline__ int paw_find_gword(const PawArgs& A, size_t pix, uint
     return -1;
 }
 
-template<int CH>
+template<int CH, bool T7>
 __global__ void __launch_bounds__(TILE_W * TILE_H, 3)
 pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
@@ -183,7 +189,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
             for(int c = 0; c < CH; ++c) {
                 L[c] = lbsp_lookup_window<CH>(Wn, c);
                 cur[c] = win_center<CH>(Wn, c);
-                intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+                intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
             }
         }
         Col cur_pack; Desc intra_pack;
@@ -221,7 +227,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
             for(int c = 0; c < CH; ++c) {
                 const uint32_t b = col_get(bc, c);
-                ehd += __popc(lbsp_threshold(L[c], b, s_lut[b]) ^ desc_get(bd, c));
+                ehd += __popc(lbsp_threshold<T7>(L[c], b, s_lut[b]) ^ desc_get(bd, c));
             }
             const uint32_t dd = (ihd + ehd) >> 1;
             if((!unst || flat || border) && mix <= thrC && l1 >= thrC / 2u && ihd <= thrD / 2u) { // illumination update (:1014-1030)
