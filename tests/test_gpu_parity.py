@@ -72,6 +72,11 @@ CASES = [
     ("subsense", 200, 150, 3, 6, "roi"),     # ragged width (not a multiple of 32) + user ROI
     ("subsense", 330, 250, 3, 8, None),      # frame-level analysis on a size that is not a multiple of 8 (general INTER_AREA path)
     ("subsense", 570, 340, 1, 6, None),      # CDnet twoPositionPTZCam size, 1 channel
+    ("subsense", 9, 7, 3, 6, None),          # smallest useful frames: the ROI left by the 2-px border is 5x3 / 27x1
+    ("subsense", 31, 5, 1, 5, None),
+    ("subsense", 4100, 6, 1, 4, None),       # very wide and flat: 129 tiles in x, one (partial) tile row
+    ("subsense", 37, 1030, 3, 3, None),      # narrow and tall: 129 tile rows, ragged width
+    ("lobster", 33, 5, 3, 6, None),
     ("lobster", 320, 240, 1, 10, None),
     ("lobster", 320, 240, 3, 8, None),
     ("lobster", 75, 61, 1, 6, "roi"),
