@@ -158,6 +158,39 @@ def test_subsense_scene_change_reset(lv, oracle, check_every_frame):
     _compare_state(g, o, INT_STATE, FLT_STATE, "scene change, end")
 
 
+@pytest.mark.parametrize("w,h", [(1920, 1080), (640, 480)])
+def test_pipelined_runs_are_deterministic(lv, w, h):
+    """race detector for the three-stream pipeline: the same sequence through two instances (one fed synchronously, one with two
+    frames in flight and nothing reading state in between) and a third run of the first must end in byte-identical state"""
+    seq = SynthSequence(w, h, 3, seed=77)
+    frames = [seq.frame(t) for t in range(7)]
+    order = [1, 2, 3, 4, 5, 6, 5, 4, 3, 2] * 12          # 120 frames of continuous motion
+
+    def run(mode):
+        g = lv.BackgroundSubtractorSuBSENSE(seed=3)
+        g.initialize(frames[0])
+        last = None
+        for i, k in enumerate(order):
+            lr = 1.0 if i < 30 else 0.0
+            if mode == "sync":
+                last = g.apply(frames[k], lr)
+            else:
+                g.apply_async(frames[k], lr)
+                if i > 0:
+                    last = g.sync_next()
+        if mode != "sync":
+            last = g.sync()
+        return last, {n: g.state_get(n) for n in ("bg_color", "bg_desc", "T", "R", "v", "DminLT", "rawST", "finLT", "lastfg", "blinks", "unstable", "lut", "scalars")}
+
+    m1, s1 = run("sync")
+    m2, s2 = run("async")
+    m3, s3 = run("sync")
+    assert np.array_equal(m1, m2) and np.array_equal(m1, m3)
+    for n in s1:
+        assert np.array_equal(s1[n], s2[n]), f"sync vs async: {n}"
+        assert np.array_equal(s1[n], s3[n]), f"run to run: {n}"
+
+
 def test_subsense_host_operations_between_pipelined_frames(lv, oracle):
     """SuBSENSE leaves the neighbour writes of the latest frame queued for the next frame's scan and runs its mask chain on a side
     stream: host-side operations issued between frames (getBackgroundImage, refreshModel, state import, setAutomaticModelReset,
