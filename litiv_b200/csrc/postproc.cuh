@@ -47,19 +47,7 @@ __device__ __forceinline__ uint32_t morph_word(const uint32_t* __restrict__ src,
     return acc & valid_mask(wi, WW, W);
 }
 
-/// P1 (blink bookkeeping, SuBSENSE.cpp:536-539) + first half of MORPH_CLOSE (dilate 3x3, :540)
-__global__ void __launch_bounds__(256) pp_blink_dilate(const PostArgs A) {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if(wi >= A.WW) return;
-    const size_t i = (size_t)y * A.WW + wi;
-    const uint32_t raw = A.raw[i];
-    const uint32_t cur_blink = raw ^ A.lastraw[i];
-    A.blinks[i] = cur_blink | A.lastrawblink[i];
-    A.lastrawblink[i] = cur_blink;
-    A.lastraw[i] = raw;
-    A.tmpA[i] = morph_word<1, true>(A.raw, y, wi, A.H, A.WW, A.W);
-}
-/// P1 + the whole MORPH_CLOSE in one launch: erode3x3(dilate3x3(raw)) needs raw rows y-2..y+2; the dilated rows are
+/// P1 (blink bookkeeping, SuBSENSE.cpp:536-539) + the whole MORPH_CLOSE (:540) in one launch: erode3x3(dilate3x3(raw)) needs raw rows y-2..y+2; the dilated rows are
 /// recomputed per word (a handful of bit operations each) instead of round-tripping through a plane and a launch boundary.
 __global__ void __launch_bounds__(256) pp_blink_close(const PostArgs A) {
     const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
@@ -89,15 +77,6 @@ __global__ void __launch_bounds__(256) pp_blink_close(const PostArgs A) {
     }
     A.pre[i] = acc & valid_mask(wi, A.WW, A.W);
 }
-/// second half of MORPH_CLOSE (erode 3x3)
-__global__ void __launch_bounds__(256) pp_erode_seed(const PostArgs A) {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if(wi >= A.WW) return;
-    const size_t i = (size_t)y * A.WW + wi;
-    const uint32_t pre = morph_word<1, false>(A.tmpA, y, wi, A.H, A.WW, A.W);
-    A.pre[i] = pre;
-}
-
 /// horizontal run fill of one 32-word chunk held one word per lane: returns the bits of m connected (towards higher
 /// bit index, across lanes) to a seed bit. Carry-propagation trick: adding the seeds to the run mask ripples through
 /// each run up to its end; the ripple across words is resolved with one ballot pair.
