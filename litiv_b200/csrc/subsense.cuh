@@ -253,9 +253,9 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         // scanning its 25 possible sources
         __syncthreads(); // s_hits cleared
         // the tile row starts at x0-2 (even) and Wp is a multiple of 32: intents are fetched as aligned u32 pairs, one per thread
-        static_assert(IW % 2 == 0 && (IW / 2) * IH <= TILE_W * TILE_H, "one intent pair per thread");
-        if(tid < (IW / 2) * IH) {
-            const int r = tid / (IW / 2), cp = tid - r * (IW / 2);
+        static_assert(IW % 2 == 0, "intent pairs");
+        for(int t = tid; t < (IW / 2) * IH; t += TILE_W * TILE_H) {
+            const int r = t / (IW / 2), cp = t - r * (IW / 2);
             const int gx = x0 - HALO + 2 * cp, gy = y0 - HALO + r;
             uint32_t pair = NO_INTENT | (NO_INTENT << 16);
             if(gy >= 0 && gy < A.H && gx >= 0 && gx < A.Wp) pair = *(const uint32_t*)(A.intents + (size_t)gy * A.Wp + gx);
@@ -470,9 +470,9 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
-    static_assert(TILE_W * TILE_H == 256, "the feedback kernel (and the frame tail it hosts) is written for 256-thread CTAs");
+    constexpr int FB_H = 8, FB_GHOST_ROWS = FB_H + 2 * HALO; // the feedback kernel keeps 32x8 tiles whatever the scan tile height is
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
-    __shared__ uint32_t s_ghost[GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
+    __shared__ uint32_t s_ghost[FB_GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
     __shared__ CtlSlice s_ctl;
     // small read-only tables behind data-dependent indices (T(x), the hand-off distances): staged in shared memory so that the
     // look-ups cost a fixed ~25 cycles instead of an L1 miss in the middle of the dependency chain (L1 is streamed through by
@@ -481,13 +481,13 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     __shared__ uint32_t s_magic[257];
     __shared__ float s_divc[NCOL], s_divd[NDES];
 
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * FB_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    for(int i = tid; i < 257; i += TILE_W * TILE_H) s_magic[i] = A.magic[i];
-    for(int i = tid; i < NCOL; i += TILE_W * TILE_H) s_divc[i] = A.div_color[i];
+    for(int i = tid; i < 257; i += TILE_W * FB_H) s_magic[i] = A.magic[i];
+    for(int i = tid; i < NCOL; i += TILE_W * FB_H) s_divc[i] = A.div_color[i];
     if(tid < NDES) s_divd[tid] = A.div_desc[tid];
     if(tid < 2) s_cnt[tid] = 0;
-    if(tid < GHOST_ROWS * 3) {
+    if(tid < FB_GHOST_ROWS * 3) {
         const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
         s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
     }
@@ -630,7 +630,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     uint32_t last_warp = 0;
     if(threadIdx.x == 0) {
         __threadfence_block();
-        last_warp = atomicAdd(&s_cnt[1], 1u) == (uint32_t)TILE_H - 1u;
+        last_warp = atomicAdd(&s_cnt[1], 1u) == (uint32_t)FB_H - 1u;
     }
     last_warp = __shfl_sync(0xFFFFFFFFu, last_warp, 0);
     if(!last_warp) return;
