@@ -111,6 +111,7 @@ struct lvb_context {
     // descriptors, while it writes frame k+1's: last_color/last_desc name the LATEST frame's planes, *_alt the spare ones
     void* last_color_alt = nullptr; void* last_desc_alt = nullptr;
     uint32_t nb_seq = 0;                // sequence number of the frame whose queued neighbour writes may still be pending (0: none)
+    uint32_t fin_pending = 0;           // SuBSENSE: frame index whose final mask is not folded into the final-segmentation EMAs yet (0: none)
     uint32_t* bits = nullptr; // all bit planes, one allocation
     uint32_t *roi_bits, *raw, *lastraw, *lastrawblink, *blinks, *tmpA, *pre, *reach, *comb, *lastfg, *dilinv, *unstable, *ghost[2], *intent_bits;
     int ghost_idx = 0;
@@ -168,7 +169,7 @@ struct lvb_context {
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
+        eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; fin_pending = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
@@ -222,7 +223,16 @@ __global__ void mark_nb_applied_kernel(FrameCtl* ctl, uint32_t seq) { ctl->nb_ap
 /// SuBSENSE leaves the neighbour writes of the latest frame queued for the next frame's scan; anything else that reads the sample
 /// model (state export, getBackgroundImage, a host-requested refreshModel) applies them first with the standalone kernel
 void flush_pending(lvb_context* c) {
-    if(c->algo != LVB_ALGO_SUBSENSE || !c->initialized || c->nb_seq == 0) return;
+    if(c->algo != LVB_ALGO_SUBSENSE || !c->initialized) return;
+    if(c->fin_pending) { // final-segmentation EMAs of the latest frame
+        PostArgs P{};
+        P.W = c->W; P.H = c->H; P.WW = c->WW; P.Wp = c->Wp; P.lastfg = c->lastfg; P.fin = c->fin; P.fin_in = c->fin; P.ctl = c->ctl;
+        P.frame = c->fin_pending; P.avg_samples = c->P.n_samples_for_moving_avgs;
+        pp_final_ema<<<dim3(c->Wp / 32, (c->H + 7) / 8), dim3(32, 8), 0, c->stream>>>(P); LAUNCHED();
+        CK(cudaStreamSynchronize(c->stream));
+        c->fin_pending = 0;
+    }
+    if(c->nb_seq == 0) return;
     PhaseBArgs B{};
     B.W = c->W; B.H = c->H; B.Wp = c->Wp; B.WW = c->WW; B.CH = c->C; B.plane = c->plane;
     B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents;
@@ -491,7 +501,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
                            &c->lastfg, &c->dilinv, &c->unstable, &c->ghost[0], &c->ghost[1], &c->intent_bits};
     for(int i = 0; i < 15; ++i) *planes[i] = c->bits + bp * i;
     c->roi255 = c->bits + bp * 19; c->illum = c->bits + bp * 20; c->did = c->bits + bp * 21; c->dil = c->bits + bp * 22; c->gop_bits = c->bits + bp * 23; // PAWCS (intent planes: 14..18)
-    c->ghost_idx = 0; c->sub_frame = 1; c->chain_seq = 0; c->post_pending = false;
+    c->ghost_idx = 0; c->sub_frame = 1; c->chain_seq = 0; c->post_pending = false; c->fin_pending = 0;
     c->uf_rs = (W + 1) / 2 + 1;
     c->uf_parent = dalloc<uint32_t>(c->stream, (size_t)H * c->uf_rs + 1);
     c->uf_rankbase = dalloc<ushort>(c->stream, (size_t)H * c->WW);
@@ -544,7 +554,6 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         }
         c->maps = dalloc<float4>(c->stream, c->plane * 2);
         c->fin = dalloc<float2>(c->stream, c->plane);
-        c->fin_alt = dalloc<float2>(c->stream, c->plane);
         c->hand = dalloc<uint2>(c->stream, c->plane);
         c->last_color_alt = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
         c->last_desc_alt = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
@@ -663,6 +672,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     SubArgs A{};
     A.W = W; A.H = H; A.Wp = c->Wp; A.WW = c->WW; A.N = c->P.n_samples; A.REQ = c->P.n_required; A.plane = c->plane;
     A.img = img; A.ipitch = pitch; A.bg = c->bg; A.maps = c->maps; A.fin = c->fin; A.hand = c->hand;
+    A.ema_frame = sub ? c->fin_pending : 0u; A.avg_samples = c->P.n_samples_for_moving_avgs;
     A.last_color = sub ? c->last_color_alt : c->last_color; A.last_desc = sub ? c->last_desc_alt : c->tmp_desc;
     A.prev_color = c->last_color; A.prev_desc = c->last_desc; A.pending_seq = sub ? c->nb_seq : 0u; A.roi_bits = c->roi_bits; A.raw_bits = sub ? c->raw_alt : c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
@@ -710,7 +720,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         PostArgs P{};
         P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw_alt; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks_alt;
         P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg_alt; P.dilinv = c->dilinv;
-        P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin_alt; P.fin_in = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+        P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.fin_in = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
         P.frame = c->sub_frame; P.avg_samples = c->P.n_samples_for_moving_avgs;
         pp_blink_close<<<wg, 256, 0, sp>>>(P); LAUNCHED(); mark(sp, "  post: blink_close");
         {
@@ -726,7 +736,9 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         chain_done_kernel<<<1, 1, 0, sp>>>(c->ctl, seq); LAUNCHED();
         if(mask_ready) CK(cudaEventRecord(mask_ready, sp));
         pp_dilate_blink<<<wg, 256, 0, sp>>>(P); LAUNCHED();
-        pp_final_ema<<<tg, tb, 0, sp>>>(P); LAUNCHED(); mark(sp, "  post: final_ema");
+        mark(sp, "  post: dilate_blink");
+        // the final-segmentation EMAs of this frame (:553-554) are folded in by the feedback kernel of the NEXT frame, which reads
+        // them anyway (flush_pending() does it for anything that needs them earlier)
         // ---- instance stream: feedback(k) needs chain(k-1) (blinks / lastfg / fin of the previous frame) and the motion sum of frame k
         if(c->post_pending) CK(cudaStreamWaitEvent(st, c->ev_post, 0));
         CK(cudaStreamWaitEvent(st, c->ev_ds, 0));
@@ -743,7 +755,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         c->nb_seq = seq;
         std::swap(c->last_color, c->last_color_alt); std::swap(c->last_desc, c->last_desc_alt);
         c->ghost_idx ^= 1;
-        std::swap(c->raw, c->raw_alt); std::swap(c->blinks, c->blinks_alt); std::swap(c->lastfg, c->lastfg_alt); std::swap(c->fin, c->fin_alt);
+        std::swap(c->raw, c->raw_alt); std::swap(c->blinks, c->blinks_alt); std::swap(c->lastfg, c->lastfg_alt);
+        c->fin_pending = c->sub_frame;
         c->sub_frame += 1;
         launch_refresh(c); mark(st, "refresh"); // reads lastfg(k), only when the frame tail requested it (the tail waited for the mask)
     } else { // LOBSTER

@@ -71,7 +71,9 @@ struct SubArgs {
     void* bg;                  // sample records [N][H][Wp]
     float4* maps;              // 2 float4 per pixel
     float* r_plane;            // compact copy of R(x) for the scan kernel (which would otherwise pull a 32-byte sector per pixel for 4 bytes)
-    const float2* fin;         // final-segmentation EMAs of the previous frame
+    float2* fin;               // final-segmentation EMAs (SuBSENSE.cpp:553-554). The feedback kernel of frame k+1 folds frame k's
+    uint32_t ema_frame;        // final mask into them before it uses them (ema_frame = k, 0: nothing pending) and stores them back
+    int avg_samples;
     uint2* hand;               // scan -> feedback hand-off word
     void* last_color; void* last_desc;          // this frame's colour / intra descriptors (written by the scan)
     const void* prev_color; const void* prev_desc; // previous frame's (read by the scan: D_last and the pending neighbour writes)

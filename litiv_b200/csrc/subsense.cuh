@@ -534,6 +534,14 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
         float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
         const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
+        if(A.ema_frame) { // final-segmentation EMAs of the previous frame (:553-554): cv::addWeighted accumulates in double, rounds once
+            const float eLT = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples));
+            const float eST = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples / 4u));
+            const double v = lastfg ? 255.0 : 0.0;
+            fin.x = (float)__dadd_rn(__dmul_rn((double)fin.x, (double)__fsub_rn(1.0f, eLT)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eLT)));
+            fin.y = (float)__dadd_rn(__dmul_rn((double)fin.y, (double)__fsub_rn(1.0f, eST)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eST)));
+            A.fin[pix] = fin;
+        }
         unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
         // D_last (:254-255 / :396-397)
