@@ -233,31 +233,35 @@ __global__ void __launch_bounds__(256) mask_morph_kernel(const uint32_t* __restr
 /// 32 x (8*MEDIAN_ROWS) tile and slides the window down it: the k-bit row popcounts enter and leave a running sum,
 /// so a pixel costs ~2 row evaluations instead of k. Writes the bit-packed result and the caller's byte mask.
 constexpr int MEDIAN_ROWS = 16;
+/// number of set pixels in the k-wide window centred on this lane's pixel, row yy (clamped: replicated border). The 32 lanes of
+/// a warp cover one mask word, so the three words the windows can touch are fetched (with the border rules) by lanes 0..2 only
+/// and broadcast; a lane's window is then one funnel shift away.
 __device__ __forceinline__ int median_row_count(const uint32_t* __restrict__ src, int yy, int wi, int xb, int r, uint32_t wmask, int H, int WW, int W) {
-    const uint32_t* row = src + (size_t)clampi(yy, 0, H - 1) * WW;
-    const uint32_t l = row_word<FILL_REPL>(row, wi - 1, WW, W), c = row_word<FILL_REPL>(row, wi, WW, W), rr = row_word<FILL_REPL>(row, wi + 1, WW, W);
-    const unsigned long long lo = ((unsigned long long)c << 32) | l, hi = ((unsigned long long)rr << 32) | c;
-    const uint32_t win = (xb >= r) ? (uint32_t)(hi >> (xb - r)) : (uint32_t)(lo >> (32 + xb - r));
+    const int lane = threadIdx.x;
+    uint32_t v = 0;
+    if(lane < 3) v = row_word<FILL_REPL>(src + (size_t)clampi(yy, 0, H - 1) * WW, wi - 1 + lane, WW, W);
+    const uint32_t l = __shfl_sync(0xFFFFFFFFu, v, 0), c = __shfl_sync(0xFFFFFFFFu, v, 1), rr = __shfl_sync(0xFFFFFFFFu, v, 2);
+    const uint32_t win = (xb >= r) ? __funnelshift_r(c, rr, xb - r) : __funnelshift_r(l, c, 32 + xb - r);
     return __popc(win & wmask);
 }
 __global__ void __launch_bounds__(256) pp_median(const uint32_t* __restrict__ src, uint32_t* dst, uchar* out_mask, size_t out_pitch,
                                                   int W, int H, int WW, int k) {
     const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * MEDIAN_ROWS;
     const int wi = x >> 5, xb = x & 31, r = k >> 1, half = (k * k) / 2;
-    const uint32_t wmask = (1u << k) - 1u;
+    const uint32_t wmask = k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u;
     const bool col_ok = x < W && wi < WW;
+    if(y0 >= H || wi >= WW) return; // warp-uniform: y0 and wi depend on threadIdx.y / blockIdx only
     int sum = 0;
-    if(col_ok && y0 < H)
-        for(int dy = -r; dy <= r; ++dy) sum += median_row_count(src, y0 + dy, wi, xb, r, wmask, H, WW, W);
+    for(int dy = -r; dy <= r; ++dy) sum += median_row_count(src, y0 + dy, wi, xb, r, wmask, H, WW, W);
 #pragma unroll 4
     for(int i = 0; i < MEDIAN_ROWS; ++i) {
         const int y = y0 + i;
-        if(y >= H) break; // warp-uniform: y depends on threadIdx.y only
-        if(i > 0 && col_ok) sum += median_row_count(src, y + r, wi, xb, r, wmask, H, WW, W) - median_row_count(src, y - r - 1, wi, xb, r, wmask, H, WW, W);
+        if(y >= H) break; // warp-uniform
+        if(i > 0) sum += median_row_count(src, y + r, wi, xb, r, wmask, H, WW, W) - median_row_count(src, y - r - 1, wi, xb, r, wmask, H, WW, W);
         const bool on = col_ok && sum > half;
         if(col_ok && out_mask) out_mask[(size_t)y * out_pitch + x] = on ? 255 : 0;
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, on);
-        if(threadIdx.x == 0 && wi < WW) dst[(size_t)y * WW + wi] = b;
+        if(threadIdx.x == 0) dst[(size_t)y * WW + wi] = b;
     }
 }
 
