@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(256, 3) pawcs_phaseB(const PawArgs A) {
     const uint32_t flatK = CH == 1 ? 2u : 4u;
     const size_t pix = (size_t)y * A.Wp + x;
     const float init_w = __fdiv_rn(1.0f, (float)woff);
+    // pass 1: which of the 25 possible sources aim at this pixel (bit = window position in raster order of the source)
+    uint32_t hits = 0;
 #pragma unroll
     for(int dy = -2; dy <= 2; ++dy) {
         const int qy = y + dy;
@@ -451,10 +453,20 @@ __global__ void __launch_bounds__(256, 3) pawcs_phaseB(const PawArgs A) {
         while(win) {
             const int k = __ffs(win) - 1;
             win &= win - 1;
+            if((int)(A.intents[(size_t)qy * A.Wp + (x - 2 + k)].x & 0xFFu) == (2 - dy) * 5 + (4 - k)) hits |= 1u << ((dy + 2) * 5 + k);
+        }
+    }
+    // pass 2: every lane pops ITS next hit, so the lanes of a warp walk their dictionaries together (as many rounds as the busiest
+    // lane has hits) instead of one round per window position with a handful of lanes each
+    {
+        while(hits) {
+            const int hi_ = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int r_ = hi_ / 5, k = hi_ - r_ * 5;
+            const int qy = y + r_ - 2;
             const int qx = x - 2 + k;
             const size_t qpix = (size_t)qy * A.Wp + qx;
             const uint4 rec = A.intents[qpix];
-            if((int)(rec.x & 0xFFu) != (2 - dy) * 5 + (4 - k)) continue;
             // source pixel (qx,qy) updates this pixel's dictionary with its own colour / descriptor / thresholds
             const uint32_t thrD = rec.x >> 8, thrC = rec.y, rate = rec.w;
             const float wthr = __uint_as_float(rec.z);
