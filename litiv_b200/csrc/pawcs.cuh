@@ -480,10 +480,15 @@ __global__ void __launch_bounds__(256, 3) pawcs_phaseB(const PawArgs A) {
             const bool traw = (A.raw_bits[y * A.WW + wi] >> xb) & 1u;
             const uint32_t src_id = (uint32_t)(qy * A.W + qx);
             float sum = 0.0f;
+            // software-pipelined: the colour / descriptor of word j+1 are fetched while word j is tested (the loads are harmless
+            // when the scan stops at j; a word rewritten by this very hit is never re-read by it)
+            Col nbc = ((const Col*)A.lw_color)[pix];
+            Desc nbd = ((const Desc*)A.lw_desc)[pix];
             for(int j = 0; j < A.NW && sum < wthr; ++j) {
                 const size_t at = (size_t)j * A.plane + pix;
-                const Col bc = ((const Col*)A.lw_color)[at];
-                const Desc bd = ((const Desc*)A.lw_desc)[at];
+                const Col bc = nbc;
+                const Desc bd = nbd;
+                if(j + 1 < A.NW) { nbc = ((const Col*)A.lw_color)[at + A.plane]; nbd = ((const Desc*)A.lw_desc)[at + A.plane]; }
                 uint32_t l1, cd;
                 const uint32_t mix = paw_color_dist<CH>(sc32, col_as_u32(bc), l1, cd);
                 const uint32_t hd = paw_hdist(sd, bd);
