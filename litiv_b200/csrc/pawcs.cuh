@@ -213,11 +213,21 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
         uint32_t minColor = colorRange, minDesc = descRange;
         int i = 0;
         uint32_t wf = f0, wl = l0, wo = o0;
-        for(; i < A.NW && sum < wthr; ++i) { // scan: one word per DRAM round trip (colour, descriptor and counters together)
+        // software-pipelined scan: word i+1 (colour, descriptor, counters) is fetched while word i is tested. A swap at step i
+        // exchanges positions i and i-1 only, so the prefetched word is still the one at position i+1.
+        Col nbc = ((const Col*)A.lw_color)[pix];
+        Desc nbd = ((const Desc*)A.lw_desc)[pix];
+        uint32_t nwf = f0, nwl = l0, nwo = o0;
+        for(; i < A.NW && sum < wthr; ++i) {
             const size_t at = (size_t)i * A.plane + pix;
-            const Col bc = ((const Col*)A.lw_color)[at];
-            const Desc bd = ((const Desc*)A.lw_desc)[at];
-            if(i > 0) { wf = A.lw_first[at]; wl = A.lw_last[at]; wo = A.lw_occ[at]; }
+            const Col bc = nbc;
+            const Desc bd = nbd;
+            wf = nwf; wl = nwl; wo = nwo;
+            if(i + 1 < A.NW) {
+                const size_t an = at + A.plane;
+                nbc = ((const Col*)A.lw_color)[an]; nbd = ((const Desc*)A.lw_desc)[an];
+                nwf = A.lw_first[an]; nwl = A.lw_last[an]; nwo = A.lw_occ[an];
+            }
             const float w = paw_weight(wf, wl, wo, frame, woff);
             ++scanned;
             uint32_t l1, cd;
