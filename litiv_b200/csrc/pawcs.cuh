@@ -115,14 +115,13 @@ __device__ __forceinline__ void paw_swap(const PawArgs& A, size_t pix, int i) {
 
 /// search the pixel's sorted global-word LUT (PAWCS.cpp:1073-1079 / :1119-1125); returns the identity or -1
 template<int CH>
-__device__ __forceinline__ int paw_find_gword(const PawArgs& A, size_t pix, uint32_t cur_pack, uint32_t bits, uint32_t thrC, uint32_t thrD) {
-    const GDict* gd = A.gd;
+__device__ __forceinline__ int paw_find_gword(const PawArgs& A, const uint32_t* s_gbits, const uint32_t* s_gcolor, size_t pix, uint32_t cur_pack, uint32_t bits, uint32_t thrC, uint32_t thrD) {
     for(int gi = 0; gi < A.NG; ++gi) {
         const int g = A.glut[(size_t)gi * A.plane + pix];
-        const uint32_t gb = gd->bits[g];
+        const uint32_t gb = s_gbits[g];
         if((bits > gb ? bits - gb : gb - bits) <= thrD / 4u) {
             uint32_t l1, cd;
-            if(paw_color_dist<CH>(cur_pack, gd->color[g], l1, cd) <= thrC) return g;
+            if(paw_color_dist<CH>(cur_pack, s_gcolor[g], l1, cd) <= thrC) return g;
         }
     }
     return -1;
@@ -138,11 +137,13 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uchar s_lut[256];
     __shared__ uint32_t s_cnt[4];
+    __shared__ uint32_t s_gbits[PAW_MAXG], s_gcolor[PAW_MAXG]; // frame-start snapshot of the global words' keys (read-only in this kernel)
 
     const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
     stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
     for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
+    for(int i = tid; i < PAW_MAXG; i += TILE_W * TILE_H) { s_gbits[i] = A.gd->bits[i]; s_gcolor[i] = A.gd->color[i]; }
     if(tid < 4) s_cnt[tid] = 0;
 
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
@@ -283,7 +284,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
             DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
             rawLT = __fmul_rn(rawLT, oneLT); rawST = __fmul_rn(rawST, oneST);
             if((rnd.x % rate) == 0u) {
-                const int g = paw_find_gword<CH>(A, pix, cur32, bits, thrC, thrD);
+                const int g = paw_find_gword<CH>(A, s_gbits, s_gcolor, pix, cur32, bits, thrC, thrD);
                 const uint32_t rep = rate >= 0x40000000u ? rnd.y : rnd.y % (rate * 2u);
                 if(g >= 0 || rep == 0u) {
                     A.gop_g[pix] = g >= 0 ? (uchar)g : (uchar)0xFE; A.gop_w[pix] = sum; has_gop = true;
@@ -296,7 +297,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
             DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(nmin, aST));
             rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT); rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
             if(flat || (rnd.x % rate) == 0u) {
-                const int g = paw_find_gword<CH>(A, pix, cur32, bits, thrC, thrD);
+                const int g = paw_find_gword<CH>(A, s_gbits, s_gcolor, pix, cur32, bits, thrC, thrD);
                 if(g < 0) seg = true;
                 else if(__fadd_rn(sum, __fdiv_rn(A.gmap[(size_t)g * A.gW * A.gH + cell], flat ? 2.0f : 4.0f)) < wthr) seg = true;
             } else seg = true;
