@@ -232,36 +232,42 @@ __global__ void __launch_bounds__(256) mask_morph_kernel(const uint32_t* __restr
 /// k x k majority (== cv::medianBlur on a binary mask, replicated borders). Each thread owns one column of a
 /// 32 x (8*MEDIAN_ROWS) tile and slides the window down it: the k-bit row popcounts enter and leave a running sum,
 /// so a pixel costs ~2 row evaluations instead of k. Writes the bit-packed result and the caller's byte mask.
-constexpr int MEDIAN_ROWS = 16;
-/// number of set pixels in the k-wide window centred on this lane's pixel, row yy (clamped: replicated border). The 32 lanes of
-/// a warp cover one mask word, so the three words the windows can touch are fetched (with the border rules) by lanes 0..2 only
-/// and broadcast; a lane's window is then one funnel shift away.
-__device__ __forceinline__ int median_row_count(const uint32_t* __restrict__ src, int yy, int wi, int xb, int r, uint32_t wmask, int H, int WW, int W) {
-    const int lane = threadIdx.x;
-    uint32_t v = 0;
-    if(lane < 3) v = row_word<FILL_REPL>(src + (size_t)clampi(yy, 0, H - 1) * WW, wi - 1 + lane, WW, W);
-    const uint32_t l = __shfl_sync(0xFFFFFFFFu, v, 0), c = __shfl_sync(0xFFFFFFFFu, v, 1), rr = __shfl_sync(0xFFFFFFFFu, v, 2);
-    const uint32_t win = (xb >= r) ? __funnelshift_r(c, rr, xb - r) : __funnelshift_r(l, c, 32 + xb - r);
-    return __popc(win & wmask);
-}
+constexpr int MEDIAN_ROWS = 16, MEDIAN_MAXR = 15, MEDIAN_STAGE = MEDIAN_ROWS + 2 * MEDIAN_MAXR; // k <= 31
+/// A warp owns one mask word (32 columns) x MEDIAN_ROWS rows. All the row words its windows can touch (rows y0-r .. y0+15+r,
+/// words wi-1..wi+1, with the replicated-border rules applied) are staged in shared memory by ONE round of loads, so the sliding
+/// sum runs without a dependent memory access per row; a lane's k-wide window is then one funnel shift away.
 __global__ void __launch_bounds__(256) pp_median(const uint32_t* __restrict__ src, uint32_t* dst, uchar* out_mask, size_t out_pitch,
                                                   int W, int H, int WW, int k) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y0 = (blockIdx.y * 8 + threadIdx.y) * MEDIAN_ROWS;
+    __shared__ uint32_t s_rows[8][MEDIAN_STAGE][3];
+    const int lane = threadIdx.x;
+    const int x = blockIdx.x * 32 + lane, y0 = (blockIdx.y * 8 + threadIdx.y) * MEDIAN_ROWS;
     const int wi = x >> 5, xb = x & 31, r = k >> 1, half = (k * k) / 2;
     const uint32_t wmask = k >= 32 ? 0xFFFFFFFFu : (1u << k) - 1u;
     const bool col_ok = x < W && wi < WW;
     if(y0 >= H || wi >= WW) return; // warp-uniform: y0 and wi depend on threadIdx.y / blockIdx only
+    uint32_t (*rows)[3] = s_rows[threadIdx.y];
+    const int nstage = MEDIAN_ROWS + 2 * r;  // staged row j <-> image row y0 - r + j (clamped: replicated border)
+    for(int t = lane; t < nstage * 3; t += 32) {
+        const int j = t / 3, w = t - j * 3;
+        rows[j][w] = row_word<FILL_REPL>(src + (size_t)clampi(y0 - r + j, 0, H - 1) * WW, wi - 1 + w, WW, W);
+    }
+    __syncwarp();
+    auto count = [&](int j) { // set pixels in this lane's window on staged row j
+        const uint32_t l = rows[j][0], c = rows[j][1], rr = rows[j][2];
+        const uint32_t win = (xb >= r) ? __funnelshift_r(c, rr, xb - r) : __funnelshift_r(l, c, 32 + xb - r);
+        return __popc(win & wmask);
+    };
     int sum = 0;
-    for(int dy = -r; dy <= r; ++dy) sum += median_row_count(src, y0 + dy, wi, xb, r, wmask, H, WW, W);
+    for(int j = 0; j <= 2 * r; ++j) sum += count(j);
 #pragma unroll 4
     for(int i = 0; i < MEDIAN_ROWS; ++i) {
         const int y = y0 + i;
         if(y >= H) break; // warp-uniform
-        if(i > 0) sum += median_row_count(src, y + r, wi, xb, r, wmask, H, WW, W) - median_row_count(src, y - r - 1, wi, xb, r, wmask, H, WW, W);
+        if(i > 0) sum += count(i + 2 * r) - count(i - 1);
         const bool on = col_ok && sum > half;
         if(col_ok && out_mask) out_mask[(size_t)y * out_pitch + x] = on ? 255 : 0;
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, on);
-        if(threadIdx.x == 0) dst[(size_t)y * WW + wi] = b;
+        if(lane == 0) dst[(size_t)y * WW + wi] = b;
     }
 }
 
