@@ -127,8 +127,11 @@ __device__ __forceinline__ int paw_find_gword(const PawArgs& A, const uint32_t* 
     return -1;
 }
 
+#ifndef PAW_MIN_BLOCKS
+#define PAW_MIN_BLOCKS 4   // 64 registers with some spills, 4 CTAs per SM: the kernel is latency bound (2 / 3 / 4 / 5 / 6 -> 2.90 / 2.63 / 2.52 / 2.67 / 2.58 ms)
+#endif
 template<int CH, bool T7>
-__global__ void __launch_bounds__(TILE_W * TILE_H, 3)
+__global__ void __launch_bounds__(TILE_W * TILE_H, PAW_MIN_BLOCKS)
 pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -439,8 +442,11 @@ __global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A) {
 }
 
 /// Phase B: queued neighbour-dictionary updates (PAWCS.cpp:1164-1247), gathered per TARGET pixel, raster order of the source
+#ifndef PAWB_MIN_BLOCKS
+#define PAWB_MIN_BLOCKS 5   // 3 / 4 / 5 / 6 / 8 CTAs per SM -> 2.52 / 2.46 / 2.41 / 2.46 / 2.52 ms per 1080p frame
+#endif
 template<int CH>
-__global__ void __launch_bounds__(256, 3) pawcs_phaseB(const PawArgs A) {
+__global__ void __launch_bounds__(256, PAWB_MIN_BLOCKS) pawcs_phaseB(const PawArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
