@@ -6,8 +6,11 @@
 
 namespace lvb {
 
+#ifndef LOB_MIN_BLOCKS
+#define LOB_MIN_BLOCKS 1
+#endif
 template<int CH>
-__global__ void __launch_bounds__(TILE_W * TILE_H)
+__global__ void __launch_bounds__(TILE_W * TILE_H, LOB_MIN_BLOCKS)
 lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
