@@ -747,7 +747,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed; T.wait_seq = seq;
         cudaEvent_t fb0 = nullptr, fb1 = nullptr;
         if(c->profile) { CK(cudaEventCreate(&fb0)); CK(cudaEventCreate(&fb1)); CK(cudaEventRecord(fb0, st)); }
-        if(C == 1) subsense_feedback<1><<<tg, tb, 0, st>>>(A, T); else subsense_feedback<3><<<tg, tb, 0, st>>>(A, T);
+        const dim3 fg(c->Wp / 32, (H + FB_H - 1) / FB_H), fb(32, FB_H);
+        if(C == 1) subsense_feedback<1><<<fg, fb, 0, st>>>(A, T); else subsense_feedback<3><<<fg, fb, 0, st>>>(A, T);
         LAUNCHED(); mark(st, "feedback");
         if(c->profile) { CK(cudaEventRecord(fb1, st)); c->prof2_events.push_back(fb0); c->prof2_events.push_back(fb1); }
         CK(cudaEventRecord(c->ev_post, sp)); c->post_pending = true; // recorded after feedback(k) is enqueued; covers the whole chain of frame k

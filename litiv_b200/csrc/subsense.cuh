@@ -464,13 +464,17 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
 #ifndef FEEDBACK_MIN_BLOCKS
 #define FEEDBACK_MIN_BLOCKS 5
 #endif
+#ifndef LVB_FB_H
+#define LVB_FB_H 8
+#endif
+constexpr int FB_H = LVB_FB_H; // tile height (warps per CTA) of the feedback kernel, independent of the scan tile
 template<int CH>
-__global__ void __launch_bounds__(256, FEEDBACK_MIN_BLOCKS)
+__global__ void __launch_bounds__(32 * FB_H, FEEDBACK_MIN_BLOCKS * 8 / FB_H)
 subsense_feedback(const SubArgs A, const TailArgs TA) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
-    constexpr int FB_H = 8, FB_GHOST_ROWS = FB_H + 2 * HALO; // the feedback kernel keeps 32x8 tiles whatever the scan tile height is
+    constexpr int FB_GHOST_ROWS = FB_H + 2 * HALO;
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
     __shared__ uint32_t s_ghost[FB_GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
     __shared__ CtlSlice s_ctl;
@@ -491,7 +495,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
         s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
     }
-    if(tid == 64) {
+    if(tid == 32 * FB_H - 1) {
         const FrameCtl* ctl = A.ctl;
         CtlSlice cs;
         cs.aLT = ctl->aLT; cs.aST = ctl->aST; cs.t_lower = ctl->t_lower; cs.t_upper = ctl->t_upper;
