@@ -299,6 +299,32 @@ def test_async_batch_and_device_paths(lv, oracle):
     assert np.array_equal(s.sync(), r.apply(f, 0.0))
 
 
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_cpp_drop_in_matches_python_path(lv, tmp_path, algo):
+    """the header-only C++ drop-in (include/litiv_b200.hpp: reference class and method names over the C ABI) produces the same
+    masks as the Python mirror on the same frames and seed"""
+    import subprocess
+    from litiv_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "shim_gpu"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp_shim_gpu.cpp"),
+                           "-L" + os.path.dirname(build.SO), "-llitiv_b200", "-Wl,-rpath," + os.path.dirname(build.SO), "-o", str(exe)])
+    w, h, c, n = 160, 120, 3, 12
+    seq = SynthSequence(w, h, c, seed=61)
+    frames = np.stack([seq.frame(t) for t in range(n)])
+    frames.tofile(tmp_path / "in.raw")
+    out = subprocess.run([str(exe), str(algo), str(w), str(h), str(c), str(n), str(tmp_path / "in.raw"), str(tmp_path / "out.raw")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ran on GPU" in out.stdout, out.stdout + out.stderr
+    got = np.fromfile(tmp_path / "out.raw", np.uint8).reshape(n - 1, h, w)
+    cls = [lv.BackgroundSubtractorLOBSTER, lv.BackgroundSubtractorSuBSENSE, lv.BackgroundSubtractorPAWCS][algo]
+    g = cls(seed=5)
+    g.initialize(frames[0])
+    for t in range(1, n):
+        lr = g.getDefaultLearningRate() if algo == 0 else (1.0 if t <= 5 else g.getDefaultLearningRate())
+        assert np.array_equal(g.apply(frames[t], lr), got[t - 1]), f"algo {algo}, frame {t}"
+
+
 def test_batch_device_enqueue_pool(lv):
     """lvb_apply_batch_device: many instances fed with device-resident frames from a pool of host threads; every stream must end
     up in exactly the state of an instance driven alone through the host API"""
