@@ -130,25 +130,37 @@ __device__ __forceinline__ void uf_union(uint32_t* P, uint32_t a, uint32_t b) {
     }
 }
 
-/// UF1: per row, number the background runs and make each its own root
+/// UF1: per row, number the background runs and make each its own root -- except the runs that touch the image border (every
+/// run of the first / last row, the run holding the first pixel, the run holding the last pixel): they start directly under node 0
+/// (parent[0] == 0 from the allocation; node 0 is never hooked under anything). In a sparse mask most runs span their row, so the
+/// vertical unions of UF2 then find equal roots at once instead of building row-to-row chains up to H long.
 __global__ void __launch_bounds__(256) pp_holes_init(const HoleArgs A) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if(y >= A.H) return;
-    if(y == 0 && lane == 0) A.parent[0] = 0;
+    const bool all_touch = (y == 0 || y == A.H - 1);
     const int nchunks = (A.WW + 31) >> 5;
     uint32_t base = 0;
+    bool first_bg = false, last_bg = false;
     for(int k = 0; k < nchunks; ++k) {
         const int wi = k * 32 + lane;
-        const uint32_t st = run_starts(bg_word(A.pre, y, wi, A.WW, A.W), bg_word(A.pre, y, wi - 1, A.WW, A.W));
+        const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
+        const uint32_t st = run_starts(m, bg_word(A.pre, y, wi - 1, A.WW, A.W));
         uint32_t cnt = __popc(st), incl = cnt;
 #pragma unroll
         for(int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if(lane >= o) incl += v; }
         const uint32_t excl = base + incl - cnt;
         if(wi < A.WW) {
             A.rankbase[(size_t)y * A.WW + wi] = (ushort)excl;
-            for(uint32_t r = 0; r < cnt; ++r) { const uint32_t id = 1u + (uint32_t)y * A.RS + excl + r; A.parent[id] = id; }
+            for(uint32_t r = 0; r < cnt; ++r) { const uint32_t id = 1u + (uint32_t)y * A.RS + excl + r; A.parent[id] = all_touch ? 0u : id; }
         }
+        first_bg |= __any_sync(0xFFFFFFFFu, wi == 0 && (m & 1u));
+        last_bg |= __any_sync(0xFFFFFFFFu, wi == A.WW - 1 && ((m >> ((A.W - 1) & 31)) & 1u));
         base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncwarp();
+    if(lane == 0 && !all_touch && base > 0u) {
+        if(first_bg) A.parent[1u + (uint32_t)y * A.RS] = 0u;                 // the run that starts at x = 0 is the row's first
+        if(last_bg) A.parent[1u + (uint32_t)y * A.RS + base - 1u] = 0u;      // the run that reaches x = W-1 is the row's last
     }
 }
 /// node id of the background run of row y that contains bit b of word wi
@@ -157,23 +169,18 @@ __device__ __forceinline__ uint32_t run_id(const HoleArgs& A, int y, int wi, int
     const uint32_t upto = b == 31 ? 0xFFFFFFFFu : ((2u << b) - 1u);
     return 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi] + __popc(st & upto) - 1u;
 }
-/// UF2: union vertically adjacent runs, and every run touching the image border with node 0
+/// UF2: union vertically adjacent runs (the border contacts were settled by UF1)
 __global__ void __launch_bounds__(256) pp_holes_union(const HoleArgs A) {
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if(y >= A.H) return;
-    for(int wi = lane; wi < A.WW; wi += 32) {
-        const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
-        if(y > 0) {
+    if(y > 0) {
+        for(int wi = lane; wi < A.WW; wi += 32) {
+            const uint32_t m = bg_word(A.pre, y, wi, A.WW, A.W);
             const uint32_t c = m & bg_word(A.pre, y - 1, wi, A.WW, A.W);
             const uint32_t cp = bg_word(A.pre, y, wi - 1, A.WW, A.W) & bg_word(A.pre, y - 1, wi - 1, A.WW, A.W);
             uint32_t cs = run_starts(c, cp);
             while(cs) { const int b = __ffs(cs) - 1; cs &= cs - 1; uf_union(A.parent, run_id(A, y - 1, wi, b), run_id(A, y, wi, b)); }
         }
-        uint32_t touch = 0;
-        if(y == 0 || y == A.H - 1) touch = run_starts(m, bg_word(A.pre, y, wi - 1, A.WW, A.W)) | (wi == 0 ? (m & 1u) : 0u);
-        if(wi == 0) touch |= m & 1u;
-        if(wi == A.WW - 1) touch |= m & (1u << ((A.W - 1) & 31));
-        while(touch) { const int b = __ffs(touch) - 1; touch &= touch - 1; uf_union(A.parent, run_id(A, y, wi, b), 0u); }
     }
 }
 /// UF3: runs whose root is the border node are "reached"; fill them from their start bits (carry trick), the rest of the
