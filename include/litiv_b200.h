@@ -130,6 +130,33 @@ int lvb_host_free(void* p);
 /* CUDA stream of the instance (cudaStream_t as void*) so callers can time on it with CUDA events */
 void* lvb_stream(lvb_handle h);
 
+/* ---- ViBe: BackgroundSubtractorViBe_1ch / _3ch, video/include/litiv/video/BackgroundSubtractorViBe.hpp:50-103,
+ * video/src/BackgroundSubtractorViBe.cpp. The reference classes derive from cv::BackgroundSubtractor directly (no ROI, no LBSP
+ * layer), hence their own handle type. model_channels = 1 (_1ch: 8UC1 frames only) or 3 (_3ch: 8UC3 frames, or 8UC1 frames expanded
+ * like cvtColor(GRAY2BGR), ViBe.cpp:121-124). Constructor defaults: threshold 20, N 20, required 2; apply() default learning rate 16
+ * and it must be > 0 (ViBe.hpp:41-47, ViBe.cpp:80). `seed` keys the Philox stream that replaces libc rand(). */
+typedef struct lvb_vibe_context* lvb_vibe_handle;
+int lvb_vibe_create(int model_channels, int color_dist_threshold, int n_samples, int n_required, int device, uint64_t seed, lvb_vibe_handle* out);
+int lvb_vibe_destroy(lvb_vibe_handle h);
+/* initialize(oInitImg) (ViBe.cpp:58-76, 115-138): rows of `step` bytes */
+int lvb_vibe_initialize(lvb_vibe_handle h, const uint8_t* img, int width, int height, int channels, size_t step);
+/* apply(image, fgmask, learningRate) (ViBe.cpp:78-110, 140-191): img continuous, fgmask W*H bytes, synchronous */
+int lvb_vibe_apply(lvb_vibe_handle h, const uint8_t* img, int channels, uint8_t* fgmask, double learning_rate);
+/* device-resident frame (rows of d_step bytes) and mask (W*H bytes, or null), asynchronous on the instance's stream */
+int lvb_vibe_apply_device(lvb_vibe_handle h, const uint8_t* d_img, int channels, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);
+int lvb_vibe_sync(lvb_vibe_handle h);
+/* getBackgroundImage (ViBe.cpp:32-49): W*H*model_channels bytes */
+int lvb_vibe_get_background_image(lvb_vibe_handle h, uint8_t* out);
+/* parity / checkpointing: the sample model in the reference's layout [N][H][W][C] (m_voBGImg); set != 0 imports it and sets the
+ * frame counter that indexes the Philox stream */
+int lvb_vibe_model(lvb_vibe_handle h, uint8_t* inout, size_t bytes, int set, uint32_t frame);
+/* instrumentation, as for the LBSP-based algorithms: out[0..4] = px, samples_scanned, sample_writes, fg_px, frames */
+int lvb_vibe_set_collect_stats(lvb_vibe_handle h, int enabled);
+int lvb_vibe_get_stats(lvb_vibe_handle h, uint64_t out[5]);
+int lvb_vibe_set_profile(lvb_vibe_handle h, int enabled);
+int lvb_vibe_get_profile(lvb_vibe_handle h, double* ms_total, uint64_t* launches);
+void* lvb_vibe_stream(lvb_vibe_handle h);
+
 #ifdef __cplusplus
 }
 #endif

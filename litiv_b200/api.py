@@ -25,6 +25,9 @@ EXPORTS = [
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
     "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback",
     "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics", "lvb_apply_batch_device",
+    "lvb_vibe_create", "lvb_vibe_destroy", "lvb_vibe_initialize", "lvb_vibe_apply", "lvb_vibe_apply_device", "lvb_vibe_sync",
+    "lvb_vibe_get_background_image", "lvb_vibe_model", "lvb_vibe_set_collect_stats", "lvb_vibe_get_stats", "lvb_vibe_set_profile",
+    "lvb_vibe_get_profile", "lvb_vibe_stream",
 ]
 
 
@@ -88,6 +91,20 @@ def lib():
         L.lvb_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
         L.lvb_host_free.argtypes = [C.c_void_p]
         L.lvb_mask_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.lvb_vibe_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        L.lvb_vibe_destroy.argtypes = [C.c_void_p]
+        L.lvb_vibe_initialize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t]
+        L.lvb_vibe_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double]
+        L.lvb_vibe_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_double]
+        L.lvb_vibe_sync.argtypes = [C.c_void_p]
+        L.lvb_vibe_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_vibe_model.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_uint32]
+        L.lvb_vibe_set_collect_stats.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_vibe_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_vibe_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_vibe_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvb_vibe_stream.restype = C.c_void_p
+        L.lvb_vibe_stream.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -319,6 +336,104 @@ class BackgroundSubtractorPAWCS(_BackgroundSubtractor):
 
 
 MASK_DILATE, MASK_ERODE, MASK_MEDIAN, MASK_HOLES = 0, 1, 2, 3
+
+
+class _BackgroundSubtractorViBe:
+    """BackgroundSubtractorViBe (video/include/litiv/video/BackgroundSubtractorViBe.hpp:50-77): initialize(img) / apply(img, lr=16) /
+    getBackgroundImage(); a plain cv::BackgroundSubtractor in the reference (no ROI, no LBSP layer)."""
+    MODEL_CHANNELS = None
+
+    def __init__(self, nColorDistThreshold=20, nBGSamples=20, nRequiredBGSamples=2, device=0, seed=0):
+        self._h = C.c_void_p()
+        self.N = nBGSamples
+        _chk(lib().lvb_vibe_create(self.MODEL_CHANNELS, nColorDistThreshold, nBGSamples, nRequiredBGSamples, device, seed, C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.lvb_vibe_destroy(h)
+            self._h = None
+
+    def _img(self, img, init=False):
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0:
+            raise LitivError("provided image must be non-empty, continuous, and of type 8UC1/8UC3")
+        if not init:
+            if self.shape is None:
+                raise LitivError("algo must be initialized first")
+            if img.shape[:2] != self.shape:
+                raise LitivError("input image size mismatch with initialization size")
+        return np.ascontiguousarray(img), (1 if img.ndim == 2 else img.shape[2])
+
+    def initialize(self, img):
+        img, c = self._img(img, init=True)
+        h, w = img.shape[:2]
+        _chk(lib().lvb_vibe_initialize(self._h, img.ctypes.data, w, h, c, w * c))
+        self.shape = (h, w)
+
+    def apply(self, img, learningRate=16.0, out=None):
+        img, c = self._img(img)
+        mask = np.empty(self.shape, np.uint8) if out is None else out
+        _chk(lib().lvb_vibe_apply(self._h, img.ctypes.data, c, mask.ctypes.data, float(learningRate)))
+        return mask
+
+    def apply_device(self, d_img_ptr, channels, d_step, d_mask_ptr=None, learningRate=16.0):
+        """device-resident frame (raw CUDA pointers); asynchronous on self.stream"""
+        _chk(lib().lvb_vibe_apply_device(self._h, d_img_ptr, channels, d_step, d_mask_ptr, float(learningRate)))
+
+    def sync(self):
+        _chk(lib().lvb_vibe_sync(self._h))
+
+    def getBackgroundImage(self):
+        if self.shape is None:
+            raise LitivError("algo must be initialized first")
+        out = np.empty(self.shape + (self.MODEL_CHANNELS,), np.uint8)
+        _chk(lib().lvb_vibe_get_background_image(self._h, out.ctypes.data))
+        return out[..., 0] if self.MODEL_CHANNELS == 1 else out
+
+    def getDefaultLearningRate(self):
+        return 16.0
+
+    @property
+    def stream(self):
+        return lib().lvb_vibe_stream(self._h)
+
+    def model(self):
+        """samples in the reference's layout [N][H][W][C] (m_voBGImg)"""
+        out = np.empty((self.N,) + self.shape + (self.MODEL_CHANNELS,), np.uint8)
+        _chk(lib().lvb_vibe_model(self._h, out.ctypes.data, out.nbytes, 0, 0))
+        return out
+
+    def set_model(self, arr, frame_idx):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        _chk(lib().lvb_vibe_model(self._h, arr.ctypes.data, arr.nbytes, 1, int(frame_idx)))
+
+    def set_collect_stats(self, enabled):
+        _chk(lib().lvb_vibe_set_collect_stats(self._h, int(enabled)))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        _chk(lib().lvb_vibe_get_stats(self._h, out))
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+    def set_profile(self, enabled):
+        _chk(lib().lvb_vibe_set_profile(self._h, int(enabled)))
+
+    def get_profile(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _chk(lib().lvb_vibe_get_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+class BackgroundSubtractorViBe_1ch(_BackgroundSubtractorViBe):
+    """video/include/litiv/video/BackgroundSubtractorViBe.hpp:80-90"""
+    MODEL_CHANNELS = 1
+
+
+class BackgroundSubtractorViBe_3ch(_BackgroundSubtractorViBe):
+    """video/include/litiv/video/BackgroundSubtractorViBe.hpp:93-103 (8UC3 frames, or 8UC1 frames expanded to BGR)"""
+    MODEL_CHANNELS = 3
 
 
 def mask_op(op, mask, param=0, device=0):

@@ -1701,3 +1701,5 @@ int lvb_binclassif_metrics(const uint64_t c[6], double out[8]) {
 }
 
 } // extern "C"
+
+#include "vibe_host.cuh"

@@ -6,6 +6,7 @@
 #ifdef LVO_WITH_PAWCS
 #include "lvo_pawcs.hpp"
 #endif
+#include "lvo_vibe.hpp"
 #include <map>
 #include <chrono>
 
@@ -269,6 +270,40 @@ double lvo_apply_sequence(void* hv, const uint8_t* frames, int n, size_t frame_b
         total += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
     return total;
+}
+
+// --- ViBe (video/src/BackgroundSubtractorViBe.cpp): separate handle type, the class is a plain cv::BackgroundSubtractor (no ROI)
+int lvo_vibe_create(int model_channels, int color_dist_threshold, int n_samples, int n_required, int mode, uint64_t seed, void** out) {
+    LVO_TRY
+    if(model_channels != 1 && model_channels != 3) throw std::runtime_error("ViBe model must have 1 or 3 channels");
+    if(n_samples <= 0 || n_required > n_samples) throw std::runtime_error("algo cannot require more sample matches than sample count in model");
+    ViBe* v = new ViBe();
+    v->model_channels = model_channels; v->color_dist_threshold = color_dist_threshold; v->n_samples = n_samples; v->n_required = n_required;
+    v->mode = (Mode)mode; v->seed = seed; v->grand.srand((unsigned)seed);
+    *out = v;
+    LVO_CATCH
+}
+int lvo_vibe_destroy(void* h) { delete (ViBe*)h; return 0; }
+int lvo_vibe_initialize(void* h, const uint8_t* img, int w, int hh, int c) { LVO_TRY ((ViBe*)h)->initialize(img, w, hh, c); LVO_CATCH }
+int lvo_vibe_apply(void* h, const uint8_t* img, int c, uint8_t* mask, double lr) { LVO_TRY ((ViBe*)h)->apply(img, c, mask, lr); LVO_CATCH }
+int lvo_vibe_get_background_image(void* h, uint8_t* out) { LVO_TRY ((ViBe*)h)->get_background_image(out); LVO_CATCH }
+/// model samples in the reference's layout [N][H][W][C]
+int lvo_vibe_model(void* h, uint8_t* inout, size_t bytes, int set) {
+    LVO_TRY
+    ViBe* v = (ViBe*)h;
+    if(bytes != v->bg.size()) throw std::runtime_error("size mismatch for the ViBe model");
+    if(set) std::memcpy(v->bg.data(), inout, bytes); else std::memcpy(inout, v->bg.data(), bytes);
+    LVO_CATCH
+}
+int lvo_vibe_set_frame(void* h, uint64_t frame_idx) { ((ViBe*)h)->frame_idx = (size_t)frame_idx; return 0; }
+int lvo_vibe_get_stats(void* h, uint64_t out[5]) {
+    const Stats& s = ((ViBe*)h)->stats;
+    out[0] = s.roi_px; out[1] = s.samples_scanned; out[2] = s.sample_writes; out[3] = s.fg_px; out[4] = s.frames;
+    return 0;
+}
+int lvo_vibe_match(int model_channels, int thr, const uint8_t* a, const uint8_t* b) {
+    ViBe v; v.model_channels = model_channels; v.color_dist_threshold = thr;
+    return v.matches(a, b) ? 1 : 0;
 }
 
 } // extern "C"

@@ -165,6 +165,66 @@ class Oracle:
         return np.array(list(out), dtype=np.uint64)
 
 
+class ViBeOracle:
+    """BackgroundSubtractorViBe_1ch / _3ch (video/src/BackgroundSubtractorViBe.cpp) over the CPU restatement (oracle/lvo_vibe.hpp)"""
+
+    def __init__(self, model_channels=3, color_dist_threshold=20, n_samples=20, n_required=2, mode=MODE_SNAPSHOT, seed=0):
+        self._h = C.c_void_p()
+        self.C, self.N = model_channels, n_samples
+        _chk(lib().lvo_vibe_create(model_channels, color_dist_threshold, n_samples, n_required, mode, C.c_uint64(seed), C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.lvo_vibe_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def _img(img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        return img, (1 if img.ndim == 2 else img.shape[2])
+
+    def initialize(self, img):
+        img, c = self._img(img)
+        h, w = img.shape[:2]
+        _chk(lib().lvo_vibe_initialize(self._h, img.ctypes.data_as(C.c_void_p), w, h, c))
+        self.shape = (h, w)
+
+    def apply(self, img, lr=16.0):
+        img, c = self._img(img)
+        assert img.shape[:2] == self.shape
+        mask = np.empty(self.shape, np.uint8)
+        _chk(lib().lvo_vibe_apply(self._h, img.ctypes.data_as(C.c_void_p), c, mask.ctypes.data_as(C.c_void_p), C.c_double(lr)))
+        return mask
+
+    def get_background_image(self):
+        out = np.empty(self.shape + (self.C,), np.uint8)
+        _chk(lib().lvo_vibe_get_background_image(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[..., 0] if self.C == 1 else out
+
+    def model(self):
+        """samples [N][H][W][C]"""
+        out = np.empty((self.N,) + self.shape + (self.C,), np.uint8)
+        _chk(lib().lvo_vibe_model(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes), 0))
+        return out
+
+    def set_model(self, arr, frame_idx=None):
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        _chk(lib().lvo_vibe_model(self._h, arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes), 1))
+        if frame_idx is not None:
+            lib().lvo_vibe_set_frame(self._h, C.c_uint64(frame_idx))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        lib().lvo_vibe_get_stats(self._h, out)
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+
+def vibe_match(model_channels, thr, a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return bool(lib().lvo_vibe_match(model_channels, thr, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+
 def lbsp_compute(img, ref=None, rel=None, thr=0):
     """LBSP::compute2 (dense). rel=None -> absolute threshold `thr`; else relative `rel` with offset `thr`."""
     img = np.ascontiguousarray(img, dtype=np.uint8)
