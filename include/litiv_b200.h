@@ -157,6 +157,31 @@ int lvb_vibe_set_profile(lvb_vibe_handle h, int enabled);
 int lvb_vibe_get_profile(lvb_vibe_handle h, double* ms_total, uint64_t* launches);
 void* lvb_vibe_stream(lvb_vibe_handle h);
 
+/* ---- PBAS: BackgroundSubtractorPBAS_1ch / _3ch, video/include/litiv/video/BackgroundSubtractorPBAS.hpp:88-147,
+ * video/src/BackgroundSubtractorPBAS.cpp (as shipped: self-diffusion on, R2 acceleration off, advanced morphology off). Same shape as the
+ * ViBe entry points. Constructor defaults: initial colour distance threshold 30, initial update rate 16, N 35, required 2
+ * (PBAS.hpp:47-54); apply()'s learning rate overrides T(x) when > 0 (default -1: use T(x)), PBAS.cpp:177, :411. */
+typedef struct lvb_pbas_context* lvb_pbas_handle;
+int lvb_pbas_create(int model_channels, int init_color_dist_threshold, float init_update_rate, int n_samples, int n_required, int device,
+                    uint64_t seed, lvb_pbas_handle* out);
+int lvb_pbas_destroy(lvb_pbas_handle h);
+/* initialize(oInitImg) (PBAS.cpp:60-110, 284-326) */
+int lvb_pbas_initialize(lvb_pbas_handle h, const uint8_t* img, int width, int height, int channels, size_t step);
+/* apply(image, fgmask, learningRateOverride) (PBAS.cpp:112-271, 328-496), synchronous */
+int lvb_pbas_apply(lvb_pbas_handle h, const uint8_t* img, int channels, uint8_t* fgmask, double learning_rate_override);
+int lvb_pbas_apply_device(lvb_pbas_handle h, const uint8_t* d_img, int channels, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate_override);
+int lvb_pbas_sync(lvb_pbas_handle h);
+/* getBackgroundImage (PBAS.cpp:37-54) */
+int lvb_pbas_get_background_image(lvb_pbas_handle h, uint8_t* out);
+/* parity / checkpointing: "bg_color" / "bg_grad" [N][H][W][C] u8, "R" / "T" / "meanmin" [H][W] f32, "scalars" 2 x f64 (frame counter,
+ * m_fFormerMeanGradDist); read-only "rawmask" [H][W] u8 and "lastgrad" [H][W][C] u8 */
+int lvb_pbas_state(lvb_pbas_handle h, const char* name, void* inout, size_t bytes, int set);
+int lvb_pbas_set_collect_stats(lvb_pbas_handle h, int enabled);
+int lvb_pbas_get_stats(lvb_pbas_handle h, uint64_t out[5]);
+int lvb_pbas_set_profile(lvb_pbas_handle h, int enabled);
+int lvb_pbas_get_profile(lvb_pbas_handle h, double* ms_total, uint64_t* launches);
+void* lvb_pbas_stream(lvb_pbas_handle h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,9 @@ EXPORTS = [
     "lvb_vibe_create", "lvb_vibe_destroy", "lvb_vibe_initialize", "lvb_vibe_apply", "lvb_vibe_apply_device", "lvb_vibe_sync",
     "lvb_vibe_get_background_image", "lvb_vibe_model", "lvb_vibe_set_collect_stats", "lvb_vibe_get_stats", "lvb_vibe_set_profile",
     "lvb_vibe_get_profile", "lvb_vibe_stream",
+    "lvb_pbas_create", "lvb_pbas_destroy", "lvb_pbas_initialize", "lvb_pbas_apply", "lvb_pbas_apply_device", "lvb_pbas_sync",
+    "lvb_pbas_get_background_image", "lvb_pbas_state", "lvb_pbas_set_collect_stats", "lvb_pbas_get_stats", "lvb_pbas_set_profile",
+    "lvb_pbas_get_profile", "lvb_pbas_stream",
 ]
 
 
@@ -105,6 +108,20 @@ def lib():
         L.lvb_vibe_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_vibe_stream.restype = C.c_void_p
         L.lvb_vibe_stream.argtypes = [C.c_void_p]
+        L.lvb_pbas_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
+        L.lvb_pbas_destroy.argtypes = [C.c_void_p]
+        L.lvb_pbas_initialize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t]
+        L.lvb_pbas_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_double]
+        L.lvb_pbas_apply_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_double]
+        L.lvb_pbas_sync.argtypes = [C.c_void_p]
+        L.lvb_pbas_get_background_image.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_pbas_state.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.lvb_pbas_set_collect_stats.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_pbas_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_pbas_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.lvb_pbas_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvb_pbas_stream.restype = C.c_void_p
+        L.lvb_pbas_stream.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -433,6 +450,104 @@ class BackgroundSubtractorViBe_1ch(_BackgroundSubtractorViBe):
 
 class BackgroundSubtractorViBe_3ch(_BackgroundSubtractorViBe):
     """video/include/litiv/video/BackgroundSubtractorViBe.hpp:93-103 (8UC3 frames, or 8UC1 frames expanded to BGR)"""
+    MODEL_CHANNELS = 3
+
+
+PBAS_STATE = {"bg_color": np.uint8, "bg_grad": np.uint8, "R": np.float32, "T": np.float32, "meanmin": np.float32, "rawmask": np.uint8,
+              "lastgrad": np.uint8, "scalars": np.float64}
+
+
+class _BackgroundSubtractorPBAS(_BackgroundSubtractorViBe):
+    """BackgroundSubtractorPBAS (video/include/litiv/video/BackgroundSubtractorPBAS.hpp:88-121): initialize(img) /
+    apply(img, learningRateOverride=-1) / getBackgroundImage()."""
+
+    def __init__(self, nInitColorDistThreshold=30, fInitUpdateRate=16.0, nBGSamples=35, nRequiredBGSamples=2, device=0, seed=0):
+        self._h = C.c_void_p()
+        self.N = nBGSamples
+        _chk(lib().lvb_pbas_create(self.MODEL_CHANNELS, nInitColorDistThreshold, fInitUpdateRate, nBGSamples, nRequiredBGSamples, device,
+                                   seed, C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and _LIB is not None:
+            _LIB.lvb_pbas_destroy(h)
+            self._h = None
+
+    def initialize(self, img):
+        img, c = self._img(img, init=True)
+        h, w = img.shape[:2]
+        _chk(lib().lvb_pbas_initialize(self._h, img.ctypes.data, w, h, c, w * c))
+        self.shape = (h, w)
+
+    def apply(self, img, learningRateOverride=-1.0, out=None):
+        img, c = self._img(img)
+        mask = np.empty(self.shape, np.uint8) if out is None else out
+        _chk(lib().lvb_pbas_apply(self._h, img.ctypes.data, c, mask.ctypes.data, float(learningRateOverride)))
+        return mask
+
+    def apply_device(self, d_img_ptr, channels, d_step, d_mask_ptr=None, learningRateOverride=-1.0):
+        _chk(lib().lvb_pbas_apply_device(self._h, d_img_ptr, channels, d_step, d_mask_ptr, float(learningRateOverride)))
+
+    def sync(self):
+        _chk(lib().lvb_pbas_sync(self._h))
+
+    def getBackgroundImage(self):
+        if self.shape is None:
+            raise LitivError("algo must be initialized first")
+        out = np.empty(self.shape + (self.MODEL_CHANNELS,), np.uint8)
+        _chk(lib().lvb_pbas_get_background_image(self._h, out.ctypes.data))
+        return out[..., 0] if self.MODEL_CHANNELS == 1 else out
+
+    def getDefaultLearningRate(self):
+        return -1.0
+
+    @property
+    def stream(self):
+        return lib().lvb_pbas_stream(self._h)
+
+    def _shape_of(self, name):
+        if name in ("bg_color", "bg_grad"):
+            return (self.N,) + self.shape + (self.MODEL_CHANNELS,)
+        if name == "lastgrad":
+            return self.shape + (self.MODEL_CHANNELS,)
+        return (2,) if name == "scalars" else self.shape
+
+    def state_get(self, name):
+        out = np.empty(self._shape_of(name), PBAS_STATE[name])
+        _chk(lib().lvb_pbas_state(self._h, name.encode(), out.ctypes.data, out.nbytes, 0))
+        return out
+
+    def state_set(self, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=PBAS_STATE[name])
+        _chk(lib().lvb_pbas_state(self._h, name.encode(), arr.ctypes.data, arr.nbytes, 1))
+
+    model = set_model = None
+
+    def set_collect_stats(self, enabled):
+        _chk(lib().lvb_pbas_set_collect_stats(self._h, int(enabled)))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        _chk(lib().lvb_pbas_get_stats(self._h, out))
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+    def set_profile(self, enabled):
+        _chk(lib().lvb_pbas_set_profile(self._h, int(enabled)))
+
+    def get_profile(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _chk(lib().lvb_pbas_get_profile(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+class BackgroundSubtractorPBAS_1ch(_BackgroundSubtractorPBAS):
+    """video/include/litiv/video/BackgroundSubtractorPBAS.hpp:124-134"""
+    MODEL_CHANNELS = 1
+
+
+class BackgroundSubtractorPBAS_3ch(_BackgroundSubtractorPBAS):
+    """video/include/litiv/video/BackgroundSubtractorPBAS.hpp:137-147 (8UC3 frames, or 8UC1 frames expanded to BGR)"""
     MODEL_CHANNELS = 3
 
 

@@ -1703,3 +1703,4 @@ int lvb_binclassif_metrics(const uint64_t c[6], double out[8]) {
 } // extern "C"
 
 #include "vibe_host.cuh"
+#include "pbas_host.cuh"

@@ -7,6 +7,7 @@
 #include "lvo_pawcs.hpp"
 #endif
 #include "lvo_vibe.hpp"
+#include "lvo_pbas.hpp"
 #include <map>
 #include <chrono>
 
@@ -305,5 +306,50 @@ int lvo_vibe_match(int model_channels, int thr, const uint8_t* a, const uint8_t*
     ViBe v; v.model_channels = model_channels; v.color_dist_threshold = thr;
     return v.matches(a, b) ? 1 : 0;
 }
+
+// --- PBAS (video/src/BackgroundSubtractorPBAS.cpp): separate handle type, like ViBe
+int lvo_pbas_create(int model_channels, int color_dist_threshold, float update_rate, int n_samples, int n_required, int mode, uint64_t seed, void** out) {
+    LVO_TRY
+    if(model_channels != 1 && model_channels != 3) throw std::runtime_error("PBAS model must have 1 or 3 channels");
+    if(n_samples <= 0 || n_required > n_samples) throw std::runtime_error("algo cannot require more sample matches than sample count in model");
+    if(!(update_rate > 0 && update_rate <= 255)) throw std::runtime_error("default update rate must be in ]0,255]");
+    PBAS* v = new PBAS();
+    v->model_channels = model_channels; v->color_dist_threshold = color_dist_threshold; v->default_update_rate = update_rate;
+    v->n_samples = n_samples; v->n_required = n_required;
+    v->mode = (Mode)mode; v->seed = seed; v->grand.srand((unsigned)seed);
+    *out = v;
+    LVO_CATCH
+}
+int lvo_pbas_destroy(void* h) { delete (PBAS*)h; return 0; }
+int lvo_pbas_initialize(void* h, const uint8_t* img, int w, int hh, int c) { LVO_TRY ((PBAS*)h)->initialize(img, w, hh, c); LVO_CATCH }
+int lvo_pbas_apply(void* h, const uint8_t* img, int c, uint8_t* mask, double lr) { LVO_TRY ((PBAS*)h)->apply(img, c, mask, lr); LVO_CATCH }
+int lvo_pbas_get_background_image(void* h, uint8_t* out) { LVO_TRY ((PBAS*)h)->get_background_image(out); LVO_CATCH }
+/// named state: bg_color / bg_grad [N][H][W][C] u8, R / T / meanmin [H][W] f32, rawmask / lastgrad u8, scalars = {frame_idx, former_mean_grad_dist} f64
+int lvo_pbas_state(void* h, const char* name, void* inout, size_t bytes, int set) {
+    LVO_TRY
+    PBAS* v = (PBAS*)h;
+    const std::string n(name);
+    void* ptr = nullptr; size_t sz = 0;
+    double sc[2] = {(double)v->frame_idx, (double)v->former_mean_grad_dist};
+    if(n == "bg_color") { ptr = v->bg_color.data(); sz = v->bg_color.size(); }
+    else if(n == "bg_grad") { ptr = v->bg_grad.data(); sz = v->bg_grad.size(); }
+    else if(n == "R") { ptr = v->R.data(); sz = v->R.size() * 4; }
+    else if(n == "T") { ptr = v->T.data(); sz = v->T.size() * 4; }
+    else if(n == "meanmin") { ptr = v->meanmin.data(); sz = v->meanmin.size() * 4; }
+    else if(n == "rawmask") { ptr = v->raw_mask.data(); sz = v->raw_mask.size(); }
+    else if(n == "lastgrad") { ptr = v->last_grad.data(); sz = v->last_grad.size(); }
+    else if(n == "scalars") { ptr = sc; sz = sizeof(sc); }
+    else throw std::runtime_error("unknown state buffer: " + n);
+    if(bytes != sz) throw std::runtime_error("size mismatch for state buffer " + n);
+    if(set) { std::memcpy(ptr, inout, sz); if(n == "scalars") { v->frame_idx = (size_t)sc[0]; v->former_mean_grad_dist = (float)sc[1]; } }
+    else std::memcpy(inout, ptr, sz);
+    LVO_CATCH
+}
+int lvo_pbas_get_stats(void* h, uint64_t out[5]) {
+    const Stats& s = ((PBAS*)h)->stats;
+    out[0] = s.roi_px; out[1] = s.samples_scanned; out[2] = s.sample_writes; out[3] = s.fg_px; out[4] = s.frames;
+    return 0;
+}
+int lvo_pbas_gradient_image(const uint8_t* img, int w, int h, int c, uint8_t* out) { LVO_TRY pbas_gradient_image(img, w, h, c, out); LVO_CATCH }
 
 } // extern "C"

@@ -220,6 +220,74 @@ class ViBeOracle:
         return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
 
 
+PBAS_STATE = {"bg_color": np.uint8, "bg_grad": np.uint8, "R": np.float32, "T": np.float32, "meanmin": np.float32, "rawmask": np.uint8,
+              "lastgrad": np.uint8, "scalars": np.float64}
+
+
+class PBASOracle:
+    """BackgroundSubtractorPBAS_1ch / _3ch (video/src/BackgroundSubtractorPBAS.cpp) over the CPU restatement (oracle/lvo_pbas.hpp)"""
+
+    def __init__(self, model_channels=3, color_dist_threshold=30, update_rate=16.0, n_samples=35, n_required=2, mode=MODE_SNAPSHOT, seed=0):
+        self._h = C.c_void_p()
+        self.C, self.N = model_channels, n_samples
+        _chk(lib().lvo_pbas_create(model_channels, color_dist_threshold, C.c_float(update_rate), n_samples, n_required, mode,
+                                   C.c_uint64(seed), C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.lvo_pbas_destroy(self._h)
+            self._h = None
+
+    def initialize(self, img):
+        img, c = ViBeOracle._img(img)
+        h, w = img.shape[:2]
+        _chk(lib().lvo_pbas_initialize(self._h, img.ctypes.data_as(C.c_void_p), w, h, c))
+        self.shape = (h, w)
+
+    def apply(self, img, lr=-1.0):
+        img, c = ViBeOracle._img(img)
+        assert img.shape[:2] == self.shape
+        mask = np.empty(self.shape, np.uint8)
+        _chk(lib().lvo_pbas_apply(self._h, img.ctypes.data_as(C.c_void_p), c, mask.ctypes.data_as(C.c_void_p), C.c_double(lr)))
+        return mask
+
+    def get_background_image(self):
+        out = np.empty(self.shape + (self.C,), np.uint8)
+        _chk(lib().lvo_pbas_get_background_image(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[..., 0] if self.C == 1 else out
+
+    def _shape_of(self, name):
+        if name in ("bg_color", "bg_grad"):
+            return (self.N,) + self.shape + (self.C,)
+        if name == "lastgrad":
+            return self.shape + (self.C,)
+        return (2,) if name == "scalars" else self.shape
+
+    def state_get(self, name):
+        out = np.empty(self._shape_of(name), PBAS_STATE[name])
+        _chk(lib().lvo_pbas_state(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes), 0))
+        return out
+
+    def state_set(self, name, arr):
+        arr = np.ascontiguousarray(arr, dtype=PBAS_STATE[name])
+        _chk(lib().lvo_pbas_state(self._h, name.encode(), arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.nbytes), 1))
+
+    def stats(self):
+        out = (C.c_uint64 * 5)()
+        lib().lvo_pbas_get_stats(self._h, out)
+        return dict(roi_px=out[0], samples_scanned=out[1], sample_writes=out[2], fg_px=out[3], frames=out[4])
+
+
+def pbas_gradient_image(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    _chk(lib().lvo_pbas_gradient_image(img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def vibe_match(model_channels, thr, a, b):
     a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
     return bool(lib().lvo_vibe_match(model_channels, thr, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
