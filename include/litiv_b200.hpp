@@ -152,6 +152,96 @@ private:
     }
 };
 
+/// BackgroundSubtractorViBe_1ch / _3ch (video/include/litiv/video/BackgroundSubtractorViBe.hpp:50-103): plain cv::BackgroundSubtractor
+/// in the reference (no ROI): initialize(img), apply(img, fgmask, learningRate = 16), getBackgroundImage
+template<int MODEL_CHANNELS>
+#ifdef LITIV_B200_WITH_OPENCV
+struct BackgroundSubtractorViBe_ : public cv::BackgroundSubtractor {
+#else
+struct BackgroundSubtractorViBe_ {
+#endif
+    explicit BackgroundSubtractorViBe_(size_t nColorDistThreshold = 20, size_t nBGSamples = 20, size_t nRequiredBGSamples = 2, int device = 0, uint64_t seed = 0) {
+        check(lvb_vibe_create(MODEL_CHANNELS, (int)nColorDistThreshold, (int)nBGSamples, (int)nRequiredBGSamples, device, seed, &m_h));
+    }
+    virtual ~BackgroundSubtractorViBe_() { if(m_h) lvb_vibe_destroy(m_h); }
+    BackgroundSubtractorViBe_(const BackgroundSubtractorViBe_&) = delete;
+    BackgroundSubtractorViBe_& operator=(const BackgroundSubtractorViBe_&) = delete;
+    virtual void initialize(const ImageView& img) {
+        if(img.empty()) throw Exception("provided image for initialization must be non-empty and continuous");
+        check(lvb_vibe_initialize(m_h, img.data, img.cols, img.rows, img.channels, img.step));
+        m_rows = img.rows; m_cols = img.cols;
+    }
+    virtual void apply(const ImageView& img, uint8_t* fgmask, double learningRate = 16.0) {
+        if(img.rows != m_rows || img.cols != m_cols) throw Exception(m_rows ? "input image size mismatch with initialization size" : "algo must be initialized first");
+        if(!img.isContinuous()) throw Exception("input image data must be continuous");
+        check(lvb_vibe_apply(m_h, img.data, img.channels, fgmask, learningRate));
+    }
+    void apply(const ImageView& img, std::vector<uint8_t>& fgmask, double learningRate = 16.0) { fgmask.resize((size_t)m_rows * m_cols); apply(img, fgmask.data(), learningRate); }
+    void apply_device(const uint8_t* d_img, int channels, size_t d_step, uint8_t* d_fgmask, double learningRate = 16.0) { check(lvb_vibe_apply_device(m_h, d_img, channels, d_step, d_fgmask, learningRate)); }
+    void sync() { check(lvb_vibe_sync(m_h)); }
+    /// out: rows*cols*MODEL_CHANNELS bytes
+    void getBackgroundImage(uint8_t* out) const { check(lvb_vibe_get_background_image(m_h, out)); }
+#ifdef LITIV_B200_WITH_OPENCV
+    void apply(cv::InputArray image, cv::OutputArray fgmask, double learningRate = 16.0) override {
+        const cv::Mat img = image.getMat();
+        fgmask.create(img.size(), CV_8UC1);
+        cv::Mat m = fgmask.getMat();
+        apply(ImageView(img), m.data, learningRate);
+    }
+    void getBackgroundImage(cv::OutputArray out) const override { out.create(m_rows, m_cols, CV_8UC(MODEL_CHANNELS)); getBackgroundImage(out.getMat().data); }
+#endif
+    lvb_vibe_handle handle() const { return m_h; }
+protected:
+    lvb_vibe_handle m_h = nullptr; int m_rows = 0, m_cols = 0;
+};
+typedef BackgroundSubtractorViBe_<1> BackgroundSubtractorViBe_1ch;
+typedef BackgroundSubtractorViBe_<3> BackgroundSubtractorViBe_3ch;
+
+/// BackgroundSubtractorPBAS_1ch / _3ch (video/include/litiv/video/BackgroundSubtractorPBAS.hpp:88-147): initialize(img),
+/// apply(img, fgmask, learningRateOverride = -1), getBackgroundImage
+template<int MODEL_CHANNELS>
+#ifdef LITIV_B200_WITH_OPENCV
+struct BackgroundSubtractorPBAS_ : public cv::BackgroundSubtractor {
+#else
+struct BackgroundSubtractorPBAS_ {
+#endif
+    explicit BackgroundSubtractorPBAS_(size_t nInitColorDistThreshold = 30, float fInitUpdateRate = 16.0f, size_t nBGSamples = 35, size_t nRequiredBGSamples = 2,
+                                       int device = 0, uint64_t seed = 0) {
+        check(lvb_pbas_create(MODEL_CHANNELS, (int)nInitColorDistThreshold, fInitUpdateRate, (int)nBGSamples, (int)nRequiredBGSamples, device, seed, &m_h));
+    }
+    virtual ~BackgroundSubtractorPBAS_() { if(m_h) lvb_pbas_destroy(m_h); }
+    BackgroundSubtractorPBAS_(const BackgroundSubtractorPBAS_&) = delete;
+    BackgroundSubtractorPBAS_& operator=(const BackgroundSubtractorPBAS_&) = delete;
+    virtual void initialize(const ImageView& img) {
+        if(img.empty()) throw Exception("provided image for initialization must be non-empty and continuous");
+        check(lvb_pbas_initialize(m_h, img.data, img.cols, img.rows, img.channels, img.step));
+        m_rows = img.rows; m_cols = img.cols;
+    }
+    virtual void apply(const ImageView& img, uint8_t* fgmask, double learningRateOverride = -1.0) {
+        if(img.rows != m_rows || img.cols != m_cols) throw Exception(m_rows ? "input image size mismatch with initialization size" : "algo must be initialized first");
+        if(!img.isContinuous()) throw Exception("input image data must be continuous");
+        check(lvb_pbas_apply(m_h, img.data, img.channels, fgmask, learningRateOverride));
+    }
+    void apply(const ImageView& img, std::vector<uint8_t>& fgmask, double learningRateOverride = -1.0) { fgmask.resize((size_t)m_rows * m_cols); apply(img, fgmask.data(), learningRateOverride); }
+    void apply_device(const uint8_t* d_img, int channels, size_t d_step, uint8_t* d_fgmask, double learningRateOverride = -1.0) { check(lvb_pbas_apply_device(m_h, d_img, channels, d_step, d_fgmask, learningRateOverride)); }
+    void sync() { check(lvb_pbas_sync(m_h)); }
+    void getBackgroundImage(uint8_t* out) const { check(lvb_pbas_get_background_image(m_h, out)); }
+#ifdef LITIV_B200_WITH_OPENCV
+    void apply(cv::InputArray image, cv::OutputArray fgmask, double learningRateOverride = -1.0) override {
+        const cv::Mat img = image.getMat();
+        fgmask.create(img.size(), CV_8UC1);
+        cv::Mat m = fgmask.getMat();
+        apply(ImageView(img), m.data, learningRateOverride);
+    }
+    void getBackgroundImage(cv::OutputArray out) const override { out.create(m_rows, m_cols, CV_8UC(MODEL_CHANNELS)); getBackgroundImage(out.getMat().data); }
+#endif
+    lvb_pbas_handle handle() const { return m_h; }
+protected:
+    lvb_pbas_handle m_h = nullptr; int m_rows = 0, m_cols = 0;
+};
+typedef BackgroundSubtractorPBAS_<1> BackgroundSubtractorPBAS_1ch;
+typedef BackgroundSubtractorPBAS_<3> BackgroundSubtractorPBAS_3ch;
+
 /// lv::BinClassif (datasets/include/litiv/datasets/metrics.hpp:32-67) with accumulate() on the device, and BinClassifMetrics (:213-257)
 struct BinClassif {
     uint64_t nTP = 0, nTN = 0, nFP = 0, nFN = 0, nSE = 0, nDC = 0;

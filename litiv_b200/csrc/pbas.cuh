@@ -49,8 +49,9 @@ __device__ __forceinline__ uint32_t pbas_tile_gradient(const uchar* img, size_t 
                                                        uint32_t (*s_in)[PB_IN_W], uint32_t (*s_bl)[PB_BL_W + 2], uint32_t& cur_out) {
     const int tid = threadIdx.y * 32 + threadIdx.x;
     // 1. input tile + 2-px halo, border pixels mirrored (reflect 101): every entry is a real pixel
-    for(int i = tid; i < PB_IN_W * PB_IN_H; i += 256) {
-        const int r = i / PB_IN_W, c = i - r * PB_IN_W;
+    for(int i = tid; i < 64 * PB_IN_H; i += 256) { // 64 slots per row, the last 28 idle: no division
+        const int r = i >> 6, c = i & 63;
+        if(c >= PB_IN_W) continue;
         const int gx = reflect101(min(x0 - 2 + c, W + 1), W), gy = reflect101(min(y0 - 2 + r, H + 1), H);
         s_in[r][c] = (uint32_t)vibe_load_pixel<CH>(img, ipitch, in_ch, gx, gy);
     }
@@ -58,32 +59,29 @@ __device__ __forceinline__ uint32_t pbas_tile_gradient(const uchar* img, size_t 
     cur_out = s_in[threadIdx.y + 2][threadIdx.x + 2];
     // 2. blurred tile + 1-px halo: [1 2 1]x[1 2 1] / 16, round half up (OpenCV's fixed-point GaussianBlur for 8-bit images).
     //    Positions outside the image take the blurred value of the mirrored position (the Scharr pass mirrors the BLURRED image).
-    for(int i = tid; i < PB_BL_W * PB_BL_H; i += 256) {
-        const int r = i / PB_BL_W, c = i - r * PB_BL_W;
+    for(int i = tid; i < 64 * PB_BL_H; i += 256) {
+        const int r = i >> 6, c = i & 63;
         const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        if(gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
-        uint32_t acc[CH];
-#pragma unroll
-        for(int k = 0; k < CH; ++k) acc[k] = 8u;
+        if(c >= PB_BL_W || gx < 0 || gx >= W || gy < 0 || gy >= H) continue;
+        // channels 0 / 2 and channel 1 in the 16-bit lanes of two words: a weighted sum is at most 16 * 255
+        uint32_t acc02 = 0x00080008u, acc1 = 0x00000008u;
 #pragma unroll
         for(int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for(int dx = 0; dx < 3; ++dx) {
                 const uint32_t v = s_in[r + dy][c + dx];
                 const uint32_t w = (dy == 1 ? 2u : 1u) * (dx == 1 ? 2u : 1u);
-#pragma unroll
-                for(int k = 0; k < CH; ++k) acc[k] += w * ((v >> (8 * k)) & 0xFFu);
+                acc02 += w * (v & 0x00FF00FFu);
+                if(CH == 3) acc1 += w * ((v >> 8) & 0xFFu);
             }
-        uint32_t o = 0;
-#pragma unroll
-        for(int k = 0; k < CH; ++k) o |= (acc[k] >> 4) << (8 * k);
+        const uint32_t o = ((acc02 >> 4) & 0x00FF00FFu) | (((acc1 >> 4) & 0xFFu) << 8);
         s_bl[r][c] = o;
     }
     __syncthreads();
-    for(int i = tid; i < PB_BL_W * PB_BL_H; i += 256) {
-        const int r = i / PB_BL_W, c = i - r * PB_BL_W;
+    for(int i = tid; i < 64 * PB_BL_H; i += 256) {
+        const int r = i >> 6, c = i & 63;
         const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        if(gx >= 0 && gx < W && gy >= 0 && gy < H) continue;
+        if(c >= PB_BL_W || (gx >= 0 && gx < W && gy >= 0 && gy < H)) continue;
         if(gx < -1 || gx > W || gy < -1 || gy > H) continue;          // never read by a pixel of the image
         const int mx = reflect101(gx, W) - (x0 - 1), my = reflect101(gy, H) - (y0 - 1);
         if(mx >= 0 && mx < PB_BL_W && my >= 0 && my < PB_BL_H) s_bl[r][c] = s_bl[my][mx];
@@ -96,14 +94,21 @@ __device__ __forceinline__ uint32_t pbas_tile_gradient(const uchar* img, size_t 
     const uint32_t a00 = s_bl[r - 1][c - 1], a01 = s_bl[r - 1][c], a02 = s_bl[r - 1][c + 1];
     const uint32_t a10 = s_bl[r][c - 1], a12 = s_bl[r][c + 1];
     const uint32_t a20 = s_bl[r + 1][c - 1], a21 = s_bl[r + 1][c], a22 = s_bl[r + 1][c + 1];
-    uint32_t g = 0;
-#pragma unroll
-    for(int k = 0; k < CH; ++k) {
-        auto B = [&](uint32_t v) { return (int)((v >> (8 * k)) & 0xFFu); };
-        const int gx = 3 * (B(a02) - B(a00)) + 10 * (B(a12) - B(a10)) + 3 * (B(a22) - B(a20));
-        const int gy = 3 * (B(a20) - B(a00)) + 10 * (B(a21) - B(a01)) + 3 * (B(a22) - B(a02));
-        const uint32_t t = (uint32_t)min(abs(gx), 255) + (uint32_t)min(abs(gy), 255);
-        g |= ((t >> 1) + ((t & 1u) & ((t >> 1) & 1u))) << (8 * k);
+    // positive and negative halves of each Scharr sum in 16-bit lanes (each at most 16 * 255), then per-lane |P - M|
+    auto lanes02 = [](uint32_t v) { return v & 0x00FF00FFu; };
+    auto lane1 = [](uint32_t v) { return (v >> 8) & 0xFFu; };
+    auto mag = [](uint32_t px, uint32_t mx, uint32_t py, uint32_t my) { // one 16-bit lane each
+        const uint32_t t = min((uint32_t)abs((int)px - (int)mx), 255u) + min((uint32_t)abs((int)py - (int)my), 255u);
+        return (t >> 1) + ((t & 1u) & ((t >> 1) & 1u));
+    };
+    const uint32_t xp = 3u * lanes02(a02) + 10u * lanes02(a12) + 3u * lanes02(a22), xm = 3u * lanes02(a00) + 10u * lanes02(a10) + 3u * lanes02(a20);
+    const uint32_t yp = 3u * lanes02(a20) + 10u * lanes02(a21) + 3u * lanes02(a22), ym = 3u * lanes02(a00) + 10u * lanes02(a01) + 3u * lanes02(a02);
+    uint32_t g = mag(xp & 0xFFFFu, xm & 0xFFFFu, yp & 0xFFFFu, ym & 0xFFFFu);
+    if(CH == 3) {
+        g |= mag(xp >> 16, xm >> 16, yp >> 16, ym >> 16) << 16;
+        const uint32_t xp1 = 3u * lane1(a02) + 10u * lane1(a12) + 3u * lane1(a22), xm1 = 3u * lane1(a00) + 10u * lane1(a10) + 3u * lane1(a20);
+        const uint32_t yp1 = 3u * lane1(a20) + 10u * lane1(a21) + 3u * lane1(a22), ym1 = 3u * lane1(a00) + 10u * lane1(a01) + 3u * lane1(a02);
+        g |= mag(xp1, xm1, yp1, ym1) << 8;
     }
     return g;
 }
@@ -279,9 +284,7 @@ __global__ void __launch_bounds__(256) pbas_phaseB(const PbasArgs A) {
 #pragma unroll
         for(int dx = -1; dx <= 1; ++dx) {
             const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-            if(it == VIBE_NO_INTENT) continue;
-            const int code = (int)(it >> 8), cy = code / 3 - 1, cx = code - (code / 3) * 3 - 1;
-            if(cx == -dx && cy == -dy) {
+            if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) { // the source at (dx, dy) aims at this pixel ("none" has code 0xFF)
                 if(!loaded) {
                     const uint32_t c = (uint32_t)vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x, y);
                     const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.grad)[pix] : ((const uint32_t*)A.grad)[pix];

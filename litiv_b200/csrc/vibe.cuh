@@ -17,7 +17,7 @@ constexpr uint32_t VIBE_NO_INTENT = 0xFFFFu; // valid intents are (code 0..8) <<
 struct VibeArgs {
     int W, H, Wp;
     int N, REQ;
-    uint32_t thr;              // 1 channel: nColorDistThreshold (L1 < thr) ; 3 channels: nColorDistThreshold*3 (L2 < thr)
+    uint32_t thr;              // 1 channel: nColorDistThreshold (L1 < thr) ; 3 channels: (nColorDistThreshold*3)^2 (squared L2 < thr)
     const uchar* img; size_t ipitch; int in_ch; // in_ch == 1 with a 3-channel model: cvtColor(GRAY2BGR) on the fly (ViBe.cpp:121-124)
     void* bg; size_t plane;    // plane = H*Wp samples
     ushort* intents;           // [H][Wp]
@@ -43,7 +43,9 @@ __device__ __forceinline__ typename VibeCol<CH>::T vibe_load_pixel(const uchar* 
 }
 
 /// ViBe.cpp:93 (L1dist < thr) / :167-171 (L2dist < thr*3). lv::L2dist<3,uchar> accumulates the squares in uint16 (utils/math.hpp:
-/// 391-397, L2sqrdist :301-306): the sum wraps mod 65536 before the float square root.
+/// 391-397, L2sqrdist :301-306): the sum wraps mod 65536 before the float square root. For an integer n < 2^16 and an integer
+/// T <= 765, (float)sqrt(n) < T  <=>  n < T^2 (sqrt is correctly rounded and T - sqrt(T^2 - 1) > 6e-4 >> ulp(T)/2), so the kernel
+/// compares integers; the oracle keeps the float form.
 template<int CH>
 __device__ __forceinline__ bool vibe_match(typename VibeCol<CH>::T cur, typename VibeCol<CH>::T b, uint32_t thr) {
     if constexpr (CH == 1) return (uint32_t)abs((int)cur - (int)b) < thr;
@@ -51,7 +53,7 @@ __device__ __forceinline__ bool vibe_match(typename VibeCol<CH>::T cur, typename
         const uint32_t ad = __vabsdiffu4(cur, b);
         const uint32_t d0 = ad & 0xFFu, d1 = (ad >> 8) & 0xFFu, d2 = (ad >> 16) & 0xFFu;
         const uint32_t acc = (d0 * d0 + d1 * d1 + d2 * d2) & 0xFFFFu;
-        return __fsqrt_rn((float)acc) < (float)thr;
+        return acc < thr;
     }
 }
 
@@ -140,9 +142,9 @@ __global__ void __launch_bounds__(256) vibe_phaseB(const VibeArgs A) {
 #pragma unroll
         for(int dx = -1; dx <= 1; ++dx) { // raster order of the source (x+dx, y+dy)
             const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-            if(it == VIBE_NO_INTENT) continue;
-            const int code = (int)(it >> 8), cy = code / 3 - 1, cx = code - (code / 3) * 3 - 1; // source -> target offset
-            if(cx == -dx && cy == -dy)
+            // the source at (dx, dy) aims at this pixel iff its clamped offset is (-dx, -dy): code (1 - dy) * 3 + (1 - dx); the
+            // "none" word has code 0xFF
+            if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx)))
                 ((Col*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x + dx, y + dy);
         }
 }

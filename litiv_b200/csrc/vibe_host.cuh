@@ -32,7 +32,7 @@ namespace {
 VibeArgs vibe_args(lvb_vibe_context* c, const uint8_t* d_img, size_t pitch, int in_ch, uint8_t* d_mask, double lr) {
     VibeArgs A{};
     A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.N = c->N; A.REQ = c->REQ;
-    A.thr = (uint32_t)(c->MC == 1 ? c->thr : c->thr * 3);
+    A.thr = (uint32_t)(c->MC == 1 ? c->thr : (c->thr * 3) * (c->thr * 3)); // threshold <= 255: (3*thr)^2 < 2^20
     A.img = d_img; A.ipitch = pitch; A.in_ch = in_ch;
     A.bg = c->bg; A.plane = c->plane; A.intents = c->intents; A.mask = d_mask; A.mpitch = (size_t)c->W;
     A.frame = c->frame; A.seed = c->seed; A.lr = lr_to_fixed(lr);

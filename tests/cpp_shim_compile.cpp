@@ -10,6 +10,13 @@ int main() {
         std::printf("ran on GPU: %zu mask bytes\n", mask.size());
     } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
     try { lvb::BackgroundSubtractorPAWCS p; p.refreshModel(1, 0.0f); } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
+    try {
+        lvb::BackgroundSubtractorViBe_3ch v; lvb::BackgroundSubtractorPBAS_1ch b;   // throw without a device
+        std::vector<uint8_t> img(64 * 48 * 3, 7), mask;
+        v.initialize(lvb::ImageView(img.data(), 48, 64, 3)); v.apply(lvb::ImageView(img.data(), 48, 64, 3), mask);
+        b.initialize(lvb::ImageView(img.data(), 48, 64, 1)); b.apply(lvb::ImageView(img.data(), 48, 64, 1), mask);
+        std::printf("ViBe / PBAS ran on GPU\n");
+    } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
     lvb::BinClassif bc; bc.nTP = 6; bc.nTN = 80; bc.nFP = 4; bc.nFN = 10;
     const lvb::BinClassifMetrics m(bc);   // host arithmetic only
     std::printf("F-measure %.6f total %llu\n", m.dFMeasure, (unsigned long long)bc.total());

@@ -299,7 +299,7 @@ def test_async_batch_and_device_paths(lv, oracle):
     assert np.array_equal(s.sync(), r.apply(f, 0.0))
 
 
-@pytest.mark.parametrize("algo", [0, 1, 2])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
 def test_cpp_drop_in_matches_python_path(lv, tmp_path, algo):
     """the header-only C++ drop-in (include/litiv_b200.hpp: reference class and method names over the C ABI) produces the same
     masks as the Python mirror on the same frames and seed"""
@@ -317,11 +317,12 @@ def test_cpp_drop_in_matches_python_path(lv, tmp_path, algo):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ran on GPU" in out.stdout, out.stdout + out.stderr
     got = np.fromfile(tmp_path / "out.raw", np.uint8).reshape(n - 1, h, w)
-    cls = [lv.BackgroundSubtractorLOBSTER, lv.BackgroundSubtractorSuBSENSE, lv.BackgroundSubtractorPAWCS][algo]
+    cls = [lv.BackgroundSubtractorLOBSTER, lv.BackgroundSubtractorSuBSENSE, lv.BackgroundSubtractorPAWCS, lv.BackgroundSubtractorViBe_3ch,
+           lv.BackgroundSubtractorPBAS_3ch][algo]
     g = cls(seed=5)
     g.initialize(frames[0])
     for t in range(1, n):
-        lr = g.getDefaultLearningRate() if algo == 0 else (1.0 if t <= 5 else g.getDefaultLearningRate())
+        lr = g.getDefaultLearningRate() if algo in (0, 3, 4) else (1.0 if t <= 5 else g.getDefaultLearningRate())
         assert np.array_equal(g.apply(frames[t], lr), got[t - 1]), f"algo {algo}, frame {t}"
 
 
