@@ -77,12 +77,22 @@ __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeAr
         uint32_t good = 0, s = 0;
         if(good < REQ && s < N) { good += vibe_match<CH>(cur, v0, A.thr) ? 1u : 0u; ++s; }
         if(good < REQ && s < N) { good += vibe_match<CH>(cur, v1, A.thr) ? 1u : 0u; ++s; }
-        while(good < REQ && s < N) { // undecided: two samples in flight per round trip
+        // undecided after two samples (~10 % of the pixels): one more pair, then eight samples in flight per DRAM round trip. A
+        // foreground pixel scans all N, and its warp (and CTA slot) waits for it: the deeper batches cut that tail's latency 4x.
+        if(good < REQ && s < N) {
             const bool two = s + 1u < N;
             v0 = bgr[(size_t)s * A.plane];
             if(two) v1 = bgr[(size_t)(s + 1u) * A.plane];
             good += vibe_match<CH>(cur, v0, A.thr) ? 1u : 0u; ++s;
             if(good < REQ && two) { good += vibe_match<CH>(cur, v1, A.thr) ? 1u : 0u; ++s; }
+        }
+        while(good < REQ && s < N) {
+            Col v[8];
+            const uint32_t s0 = s;
+#pragma unroll
+            for(uint32_t j = 0; j < 8u; ++j) if(s0 + j < N) v[j] = bgr[(size_t)(s0 + j) * A.plane];
+#pragma unroll
+            for(uint32_t j = 0; j < 8u; ++j) if(good < REQ && s0 + j < N) { good += vibe_match<CH>(cur, v[j], A.thr) ? 1u : 0u; ++s; }
         }
         scanned = s;
         uint32_t intent = VIBE_NO_INTENT;
