@@ -50,15 +50,14 @@ template<int CH>
 __device__ __forceinline__ bool vibe_match(typename VibeCol<CH>::T cur, typename VibeCol<CH>::T b, uint32_t thr) {
     if constexpr (CH == 1) return (uint32_t)abs((int)cur - (int)b) < thr;
     else {
-        const uint32_t ad = __vabsdiffu4(cur, b);
-        const uint32_t d0 = ad & 0xFFu, d1 = (ad >> 8) & 0xFFu, d2 = (ad >> 16) & 0xFFu;
-        const uint32_t acc = (d0 * d0 + d1 * d1 + d2 * d2) & 0xFFFFu;
+        const uint32_t ad = __vabsdiffu4(cur, b);           // the packed values keep byte 3 zero
+        const uint32_t acc = __dp4a(ad, ad, 0u) & 0xFFFFu;  // d0^2 + d1^2 + d2^2 in one IDP.4A
         return acc < thr;
     }
 }
 
 #ifndef VIBE_MIN_BLOCKS
-#define VIBE_MIN_BLOCKS 6
+#define VIBE_MIN_BLOCKS 8
 #endif
 template<int CH>
 __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeArgs A) {
