@@ -3,9 +3,11 @@
 //
 // Model: [N][H][Wp] of one packed colour per sample (3 channels: B | G<<8 | R<<16 in a u32; 1 channel: one byte), sample-major so
 // that a warp reads 128 (32) contiguous bytes per sample row. No ROI, no border, no descriptors, no post-processing: a frame is
-//   phase A (1 thread / pixel): scan -> mask byte; own-slot write at once; neighbour write queued as an intent word
-//   phase B (1 thread / pixel): every pixel gathers the intents of its 3x3 neighbourhood aimed at it, in raster order of the source
-//                               (last writer wins), and copies the SOURCE pixel's colour of this frame into the drawn slot.
+//   ONE kernel (1 thread / pixel): the neighbour writes queued by the PREVIOUS frame are applied first (every pixel gathers the
+//   intents of its 3x3 neighbourhood aimed at it from a shared-memory tile, in raster order of the source = last writer wins, and
+//   copies the source's colour of that frame into the drawn slot); then scan -> mask byte; own-slot write at once; this frame's
+//   neighbour write queued as an intent word + the pixel's colour. Anything that needs the model between frames (export,
+//   getBackgroundImage) applies the pending writes with the standalone vibe_phaseB.
 // HBM bound by construction: ~(C + 1 + 2 + 2) + s*Cpacked bytes per pixel for s scanned samples and a handful of instructions each.
 #pragma once
 #include "common.cuh"
@@ -20,7 +22,9 @@ struct VibeArgs {
     uint32_t thr;              // 1 channel: nColorDistThreshold (L1 < thr) ; 3 channels: (nColorDistThreshold*3)^2 (squared L2 < thr)
     const uchar* img; size_t ipitch; int in_ch; // in_ch == 1 with a 3-channel model: cvtColor(GRAY2BGR) on the fly (ViBe.cpp:121-124)
     void* bg; size_t plane;    // plane = H*Wp samples
-    ushort* intents;           // [H][Wp]
+    ushort* intents;           // [H][Wp] intent words this frame writes
+    void* nbcol;               // [H][Wp] colour of the pixels that queued a neighbour write this frame (written only there)
+    const ushort* prev_intents; const void* prev_nbcol; // previous frame's planes, still to be applied (null: nothing pending)
     uchar* mask; size_t mpitch;
     uint32_t frame; uint64_t seed; uint32_t lr; // lr = ceil(learningRate), 0xFFFFFFFF for +inf
     uint32_t lr_magic, n_magic;  // floor(2^32 / lr), floor(2^32 / N) for fast_mod / fast_div
@@ -56,23 +60,61 @@ __device__ __forceinline__ bool vibe_match(typename VibeCol<CH>::T cur, typename
     }
 }
 
+/// intent words of a 32x8 tile + 1-px halo -> shared memory ("none" outside the image); ends with a barrier
+__device__ __forceinline__ void vibe_stage_intents(const ushort* intents, int W, int H, int Wp, int x0, int y0, ushort (*s_int)[36]) {
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    auto fetch = [&](int r, int c) {
+        const int gx = x0 - 1 + c, gy = y0 - 1 + r;
+        s_int[r][c] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? intents[(size_t)gy * Wp + gx] : (ushort)VIBE_NO_INTENT;
+    };
+    fetch(threadIdx.y + 1, threadIdx.x + 1);                          // core: one coalesced row per warp
+    if(tid < 68) fetch(tid < 34 ? 0 : 9, tid < 34 ? tid : tid - 34);  // top / bottom halo rows
+    else if(tid < 84) fetch(1 + ((tid - 68) & 7), tid < 76 ? 0 : 33); // left / right halo columns
+    __syncthreads();
+}
+
 #ifndef VIBE_MIN_BLOCKS
 #define VIBE_MIN_BLOCKS 8
 #endif
 template<int CH>
 __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeArgs A) {
     typedef typename VibeCol<CH>::T Col;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    __shared__ ushort s_int[10][36];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     const bool in_img = x < A.W && y < A.H;
+    const bool pending = A.prev_intents != nullptr;
     uint32_t scanned = 0, writes = 0;
     bool is_fg = false;
+    const size_t pix = (size_t)y * A.Wp + x;
+    const Col* bgr = (const Col*)A.bg + pix;
+    const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
+    // the first two samples are (almost) always scanned: both are in flight before anything else happens
+    Col v0 = Col(), v1 = Col(), cur = Col();
     if(in_img) {
-        const size_t pix = (size_t)y * A.Wp + x;
-        const Col* bgr = (const Col*)A.bg + pix;
-        const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
-        // the first two samples are (almost) always scanned: both fetched before the frame pixel arrives
-        Col v0 = bgr[0], v1 = N > 1u ? bgr[A.plane] : Col();
-        const Col cur = vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x, y);
+        v0 = bgr[0];
+        if(N > 1u) v1 = bgr[A.plane];
+        cur = vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x, y);
+    }
+    if(pending) { // previous frame's intent tile + 1-px halo
+        vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
+        if(in_img) {
+#pragma unroll
+            for(int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for(int dx = -1; dx <= 1; ++dx) { // raster order of the source (x+dx, y+dy)
+                    const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
+                    if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) { // see vibe_phaseB
+                        const Col c = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
+                        const uint32_t slot = it & 0xFFu;
+                        ((Col*)A.bg)[(size_t)slot * A.plane + pix] = c; // later loads of this thread see it (same thread, same address)
+                        if(slot == 0u) v0 = c;
+                        if(slot == 1u) v1 = c;
+                    }
+                }
+        }
+    }
+    if(in_img) {
         uint32_t good = 0, s = 0;
         if(good < REQ && s < N) { good += vibe_match<CH>(cur, v0, A.thr) ? 1u : 0u; ++s; }
         if(good < REQ && s < N) { good += vibe_match<CH>(cur, v1, A.thr) ? 1u : 0u; ++s; }
@@ -107,6 +149,7 @@ __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeAr
                 neighbor_offset(true, rnd.w, dx, dy);
                 const int nx = clampi(x + dx, 0, A.W - 1), ny = clampi(y + dy, 0, A.H - 1); // border 0 (getNeighborPosition_3x3(...,0,size))
                 intent = (uint32_t)(((ny - y + 1) * 3 + (nx - x + 1)) << 8) | fast_mod(fast_div(rnd.y, N, A.n_magic), N, A.n_magic); // one Philox block per pixel
+                ((Col*)A.nbcol)[pix] = cur;
                 ++writes;
             }
         }
@@ -128,21 +171,14 @@ __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeAr
 }
 
 /// queued neighbour writes (ViBe.cpp:104-107 / :184-187), gathered per TARGET pixel so that colliding writes resolve in raster
-/// order of their source without atomics. The intent tile + 1-px halo is staged in shared memory (one coalesced pass).
+/// order of their source without atomics. Standalone form of the gather at the top of vibe_phaseA, for whoever needs the model
+/// before the next frame arrives. Reads A.prev_intents / A.prev_nbcol.
 template<int CH>
 __global__ void __launch_bounds__(256) vibe_phaseB(const VibeArgs A) {
     typedef typename VibeCol<CH>::T Col;
     __shared__ ushort s_int[10][36];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    auto fetch = [&](int r, int c) { // tile coordinates incl. the 1-px halo -> intent word (none outside the image)
-        const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        s_int[r][c] = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? A.intents[(size_t)gy * A.Wp + gx] : (ushort)VIBE_NO_INTENT;
-    };
-    fetch(threadIdx.y + 1, threadIdx.x + 1);                       // core: one coalesced row per warp
-    if(tid < 68) fetch(tid < 34 ? 0 : 9, tid < 34 ? tid : tid - 34); // top / bottom halo rows
-    else if(tid < 84) fetch(1 + ((tid - 68) & 7), tid < 76 ? 0 : 33);  // left / right halo columns
-    __syncthreads();
+    vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x >= A.W || y >= A.H) return;
     const size_t pix = (size_t)y * A.Wp + x;
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(256) vibe_phaseB(const VibeArgs A) {
             // the source at (dx, dy) aims at this pixel iff its clamped offset is (-dx, -dy): code (1 - dy) * 3 + (1 - dx); the
             // "none" word has code 0xFF
             if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx)))
-                ((Col*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x + dx, y + dy);
+                ((Col*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
         }
 }
 

@@ -14,15 +14,19 @@ struct lvb_vibe_context {
     uint32_t frame = 0;                 // frames applied since initialize (Philox counter word 0; the first apply is frame 1)
     cudaStream_t stream = nullptr;
     uint8_t *d_img = nullptr, *d_mask = nullptr, *h_img = nullptr, *h_mask = nullptr;
-    void* bg = nullptr; ushort* intents = nullptr;
+    void* bg = nullptr;
+    // neighbour writes queued by frame k are applied by the scan of frame k+1: planes [k & 1] are written, [(k & 1) ^ 1] read
+    ushort* intents[2] = {nullptr, nullptr}; void* nbcol[2] = {nullptr, nullptr};
+    bool nb_pending = false;           // the planes of the latest frame still hold unapplied writes
     unsigned long long* d_stats = nullptr; int collect_stats = 0; uint64_t stat_frames = 0;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
 
     void free_all() {
-        for(void* p : {(void*)d_img, (void*)d_mask, bg, (void*)intents, (void*)d_stats}) if(p) cudaFree(p);
+        for(void* p : {(void*)d_img, (void*)d_mask, bg, (void*)intents[0], (void*)intents[1], nbcol[0], nbcol[1], (void*)d_stats}) if(p) cudaFree(p);
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
-        d_img = d_mask = h_img = h_mask = nullptr; bg = nullptr; intents = nullptr; d_stats = nullptr;
+        d_img = d_mask = h_img = h_mask = nullptr; bg = nullptr; intents[0] = intents[1] = nullptr; nbcol[0] = nbcol[1] = nullptr; d_stats = nullptr;
+        nb_pending = false;
         initialized = false;
     }
 };
@@ -34,7 +38,10 @@ VibeArgs vibe_args(lvb_vibe_context* c, const uint8_t* d_img, size_t pitch, int 
     A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.N = c->N; A.REQ = c->REQ;
     A.thr = (uint32_t)(c->MC == 1 ? c->thr : (c->thr * 3) * (c->thr * 3)); // threshold <= 255: (3*thr)^2 < 2^20
     A.img = d_img; A.ipitch = pitch; A.in_ch = in_ch;
-    A.bg = c->bg; A.plane = c->plane; A.intents = c->intents; A.mask = d_mask; A.mpitch = (size_t)c->W;
+    A.bg = c->bg; A.plane = c->plane; A.mask = d_mask; A.mpitch = (size_t)c->W;
+    const int cur = (int)(c->frame & 1u); // planes written by frame c->frame
+    A.intents = c->intents[cur]; A.nbcol = c->nbcol[cur];
+    A.prev_intents = c->nb_pending ? c->intents[cur ^ 1] : nullptr; A.prev_nbcol = c->nbcol[cur ^ 1];
     A.frame = c->frame; A.seed = c->seed; A.lr = lr_to_fixed(lr);
     A.lr_magic = magic_of(A.lr); A.n_magic = magic_of((uint32_t)c->N);
     A.stats = c->collect_stats ? c->d_stats : nullptr;
@@ -57,9 +64,19 @@ void vibe_enqueue(lvb_vibe_context* c, const uint8_t* d_img, size_t pitch, int i
     if(c->MC == 1) vibe_phaseA<1><<<g, b, 0, c->stream>>>(A); else vibe_phaseA<3><<<g, b, 0, c->stream>>>(A);
     LAUNCHED();
     if(c->profile) { CK(cudaEventRecord(e1, c->stream)); c->prof_events.push_back(e0); c->prof_events.push_back(e1); }
-    if(c->MC == 1) vibe_phaseB<1><<<g, b, 0, c->stream>>>(A); else vibe_phaseB<3><<<g, b, 0, c->stream>>>(A);
-    LAUNCHED();
+    c->nb_pending = true; // this frame's neighbour writes wait for the next frame's scan (or vibe_flush_pending)
     if(c->collect_stats) ++c->stat_frames;
+}
+
+/// apply the neighbour writes the latest frame queued (model export, getBackgroundImage, model import)
+void vibe_flush_pending(lvb_vibe_context* c) {
+    if(!c->nb_pending) return;
+    VibeArgs A = vibe_args(c, c->d_img, c->ipitch, c->MC, c->d_mask, 1.0);
+    const int last = (int)(c->frame & 1u); // planes the latest frame wrote
+    A.prev_intents = c->intents[last]; A.prev_nbcol = c->nbcol[last];
+    if(c->MC == 1) vibe_phaseB<1><<<vibe_grid(c), dim3(32, 8), 0, c->stream>>>(A); else vibe_phaseB<3><<<vibe_grid(c), dim3(32, 8), 0, c->stream>>>(A);
+    LAUNCHED();
+    c->nb_pending = false;
 }
 
 } // namespace
@@ -112,7 +129,7 @@ int lvb_vibe_initialize(lvb_vibe_handle h, const uint8_t* img, int W, int H, int
     CK(cudaMallocHost((void**)&h->h_img, (size_t)W * H * h->MC));
     CK(cudaMallocHost((void**)&h->h_mask, (size_t)W * H));
     h->bg = dalloc<uint8_t>(h->stream, (size_t)h->N * h->plane * (h->MC == 1 ? 1 : 4));
-    h->intents = dalloc<ushort>(h->stream, h->plane);
+    for(int i = 0; i < 2; ++i) { h->intents[i] = dalloc<ushort>(h->stream, h->plane); h->nbcol[i] = dalloc<uint8_t>(h->stream, h->plane * (h->MC == 1 ? 1 : 4)); }
     h->d_stats = dalloc<unsigned long long>(h->stream, 3);
     h->frame = 0; h->stat_frames = 0;
     CK(cudaMemcpy2DAsync(h->d_img, h->ipitch, img, step, (size_t)W * channels, H, cudaMemcpyHostToDevice, h->stream));
@@ -168,6 +185,7 @@ int lvb_vibe_get_background_image(lvb_vibe_handle h, uint8_t* out) {
     REQUIRE(out != nullptr, "null output");
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->W * h->H * h->MC;
+    vibe_flush_pending(h);
     uint8_t* d = dalloc<uint8_t>(h->stream, n, false);
     const VibeArgs A = vibe_args(h, h->d_img, h->ipitch, h->MC, h->d_mask, 1.0);
     if(h->MC == 1) vibe_background_kernel<1><<<vibe_grid(h), dim3(32, 8), 0, h->stream>>>(A, d); else vibe_background_kernel<3><<<vibe_grid(h), dim3(32, 8), 0, h->stream>>>(A, d);
@@ -188,6 +206,7 @@ int lvb_vibe_model(lvb_vibe_handle h, uint8_t* inout, size_t bytes, int set, uin
     const size_t n = (size_t)h->N * h->W * h->H * h->MC;
     REQUIRE(inout != nullptr && bytes == n, "size mismatch for the ViBe model");
     CK(cudaSetDevice(h->device));
+    if(set) h->nb_pending = false; else vibe_flush_pending(h); // an imported model is a complete one: queued writes are dropped
     uint8_t* d = dalloc<uint8_t>(h->stream, n, false);
     cudaError_t e = cudaSuccess;
     if(set) e = cudaMemcpyAsync(d, inout, n, cudaMemcpyHostToDevice, h->stream);
