@@ -100,3 +100,36 @@ def test_full_hd_device_resident_path_matches_oracle(lv, oracle):
         assert np.array_equal(d_mask.cpu().numpy(), o.apply(f, 16.0)), t
     assert np.array_equal(g.model(), o.model())
     assert np.array_equal(g.getBackgroundImage(), o.get_background_image())
+
+
+def test_cpu_restatement_timed_beside_the_gpu(lv, oracle, capsys):
+    """the reference-order CPU restatement on one host core beside the CUDA path on the same 1080p RGB frames (a reported baseline,
+    printed with -s; the only assertion is that the GPU path is not the slower one)"""
+    import json
+    import time
+    seq = SynthSequence(1920, 1080, 3, seed=4100)
+    frames = [seq.frame(t) for t in range(5)]
+    o = oracle.ViBeOracle(3, mode=oracle.MODE_REFERENCE, seed=1)
+    o.initialize(frames[0])
+    t0 = time.perf_counter()
+    for f in frames[1:]:
+        o.apply(f, 16.0)
+    cpu_s = (time.perf_counter() - t0) / 4
+    g = lv.BackgroundSubtractorViBe_3ch(seed=1)
+    g.initialize(frames[0])
+    hf = [lv.pinned_empty(frames[0].shape) for _ in frames]
+    for a, b in zip(hf, frames):
+        a[...] = b
+    hm = lv.pinned_empty((1080, 1920))
+    for k in range(10):
+        g.apply(hf[k % 5], 16.0, out=hm)
+    t0 = time.perf_counter()
+    for k in range(40):
+        g.apply(hf[k % 5], 16.0, out=hm)
+    gpu_s = (time.perf_counter() - t0) / 40
+    line = {"algo": "vibe", "frame": [1920, 1080, 3], "cpu_baseline": {"value": 1920 * 1080 / cpu_s / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
+            "sample": "4 frames, oracle reference-order mode"}, "gpu_end_to_end": {"value": 1920 * 1080 / gpu_s / 1e6, "unit": "Mpx/s",
+            "api": "synchronous apply, host frame -> host mask, pinned buffers"}}
+    with capsys.disabled():
+        print("\n" + json.dumps(line))
+    assert gpu_s < cpu_s

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """ViBe throughput on one GPU: device-resident frames, CUDA events on the instance's stream, the scan kernel
-timed per launch through lvb_vibe_set_profile, the oracle (reference order, one core) on a few frames beside it. One JSON line.
+timed per launch through lvb_vibe_set_profile. One JSON line. (The CPU restatement is timed beside the GPU by
+tests/test_gpu_vibe.py::test_cpu_restatement_timed_beside_the_gpu: only tests/ and bench.py may execute oracle/.)
 usage: python tools/bench_vibe.py [--size 1920x1080] [--channels 3] [--steps 300]"""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +14,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", default="1920x1080")
 ap.add_argument("--channels", type=int, default=3)
 ap.add_argument("--steps", type=int, default=300)
-ap.add_argument("--cpu-frames", type=int, default=6)
 args = ap.parse_args()
 W, H = (int(v) for v in args.size.split("x"))
 C, NF = args.channels, 12
@@ -72,13 +72,6 @@ sample_b = C
 b_alg = C + 1 + sample_b * (depth + writes)
 peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else {}
 peak = float(peaks.get("hbm_gbs", 0) or 0) or 6459.0
-from oracle import oracle as O
-o = O.ViBeOracle(C, mode=O.MODE_REFERENCE, seed=1)
-o.initialize(host[0])
-t0 = time.perf_counter()
-for t in range(1, 1 + args.cpu_frames):
-    o.apply(host[t % NF], 16.0)
-cpu_s = (time.perf_counter() - t0) / args.cpu_frames
 scan_ms = pms / max(pn, 1)
 print(json.dumps({
     "metric": "vibe_mpx_per_s", "value": W * H / ms / 1e3, "unit": "Mpx/s", "ms_per_frame": ms, "fps": 1e3 / ms, "frame": [W, H, C],
@@ -86,5 +79,4 @@ print(json.dumps({
     "scan_depth": depth, "sample_writes_per_px": writes, "alg_bytes_per_px": b_alg,
     "roofline": {"bound": "hbm", "kernel": "vibe_phaseA", "avg_launch_ms": scan_ms, "achieved": W * H * b_alg / (scan_ms * 1e-3) / 1e9, "peak": peak,
                  "unit": "GB/s", "frac": W * H * b_alg / (scan_ms * 1e-3) / 1e9 / peak, "kernel_share_of_step": scan_ms / ms},
-    "cpu_baseline": {"value": W * H / cpu_s / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port", "sample": f"{args.cpu_frames} frames, oracle reference-order mode"},
 }))
