@@ -8,7 +8,9 @@
 //            |.| -> average are evaluated there (the reference's five full-frame OpenCV passes, PBAS.cpp:125-134); scan; R/T/mean
 //            feedback; own-slot write; neighbour intent; raw mask bits by ballot; frame sums of gradient distance / bad samples
 //            (CTA-reduced, one 64-bit atomic each; the last CTA folds them into next frame's m_fFormerMeanGradDist)
-//   phase B  queued "self-diffusion" writes: a pixel whose 3x3 neighbourhood aimed at it stores ITS OWN colour / gradient (:190-191)
+//            The queued "self-diffusion" writes of the PREVIOUS frame are applied first (a pixel whose 3x3 neighbourhood aimed at it
+//            stores ITS OWN colour / gradient of that frame, :190-191), as in vibe_phaseA.
+//   phase B  the same gather, standalone, for whoever needs the model between frames (state export, getBackgroundImage)
 //   pp_median (postproc.cuh) 9x9 on the bit-packed raw mask -> output mask bytes (:269 / :494)
 #pragma once
 #include "vibe.cuh"
@@ -24,8 +26,10 @@ struct PbasArgs {
     const uchar* img; size_t ipitch; int in_ch;
     void* bg; size_t plane;
     float *R, *T, *meanmin;    // [H][Wp]
-    void* grad;                // [H][Wp] packed gradient of the current frame (u32 / u8)
+    void* grad;                // [H][Wp] packed gradient of the current frame (u32 / u8), written for every pixel
+    void* col;                 // [H][Wp] packed colour of the current frame (what a self-diffusion write of this frame stores)
     ushort* intents;
+    const ushort* prev_intents; const void* prev_col; const void* prev_grad; // previous frame's planes, still to be applied (null: none)
     uint32_t* raw_bits;        // [H][WW]
     PbasCtl* ctl;
     uint32_t frame; uint64_t seed; uint32_t lr_override; // 0: use ceil(T(x))
@@ -158,6 +162,31 @@ __global__ void __launch_bounds__(256, PBAS_MIN_BLOCKS) pbas_phaseA(const PbasAr
         v0 = bgr[0];
         if(N > 1u) v1 = bgr[A.plane];
     }
+    if(A.prev_intents != nullptr) { // neighbour writes queued by the previous frame (see vibe_phaseA)
+        __shared__ ushort s_int[10][36];
+        vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
+        if(in_img) {
+            bool loaded = false;
+            Rec own = Rec();
+#pragma unroll
+            for(int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for(int dx = -1; dx <= 1; ++dx) {
+                    const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
+                    if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) {
+                        if(!loaded) {
+                            const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
+                            const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
+                            own = pbas_rec<CH>(c, g); loaded = true;
+                        }
+                        const uint32_t slot = it & 0xFFu;
+                        ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = own;
+                        if(slot == 0u) v0 = own;
+                        if(slot == 1u) v1 = own;
+                    }
+                }
+        }
+    }
     uint32_t cur;
     const uint32_t cg = pbas_tile_gradient<CH>(A.img, A.ipitch, A.in_ch, A.W, A.H, x0, y0, s_in, s_bl, cur);
 
@@ -224,7 +253,8 @@ __global__ void __launch_bounds__(256, PBAS_MIN_BLOCKS) pbas_phaseA(const PbasAr
         else if(R > 0.6f) R = __fmul_rn(R, 0.95f);
         A.R[pix] = R; A.T[pix] = T; A.meanmin[pix] = mm;
         A.intents[pix] = (ushort)intent;
-        if constexpr (CH == 1) ((uchar*)A.grad)[pix] = (uchar)cg; else ((uint32_t*)A.grad)[pix] = cg;
+        if constexpr (CH == 1) { ((uchar*)A.grad)[pix] = (uchar)cg; ((uchar*)A.col)[pix] = (uchar)cur; }
+        else { ((uint32_t*)A.grad)[pix] = cg; ((uint32_t*)A.col)[pix] = cur; }
     }
     const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
     if(threadIdx.x == 0 && y < A.H && (x >> 5) < A.WW) A.raw_bits[y * A.WW + (x >> 5)] = b_raw;
@@ -257,22 +287,14 @@ __global__ void __launch_bounds__(256, PBAS_MIN_BLOCKS) pbas_phaseA(const PbasAr
 }
 
 /// queued neighbour writes with BGSPBAS_USE_SELF_DIFFUSION (PBAS.cpp:186-191 / :420-425): the TARGET stores its own colour and
-/// gradient of this frame in the drawn slot, so colliding writes are idempotent and only "did a neighbour aim at me, with which
-/// slot" matters.
+/// gradient of that frame in the drawn slot, so colliding writes are idempotent and only "did a neighbour aim at me, with which
+/// slot" matters. Standalone form of the gather at the top of pbas_phaseA; reads A.prev_intents / prev_col / prev_grad.
 template<int CH>
 __global__ void __launch_bounds__(256) pbas_phaseB(const PbasArgs A) {
     typedef typename PbasRec<CH>::T Rec;
     __shared__ ushort s_int[10][36];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    auto fetch = [&](int r, int c) {
-        const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        s_int[r][c] = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? A.intents[(size_t)gy * A.Wp + gx] : (ushort)VIBE_NO_INTENT;
-    };
-    fetch(threadIdx.y + 1, threadIdx.x + 1);
-    if(tid < 68) fetch(tid < 34 ? 0 : 9, tid < 34 ? tid : tid - 34);
-    else if(tid < 84) fetch(1 + ((tid - 68) & 7), tid < 76 ? 0 : 33);
-    __syncthreads();
+    vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x >= A.W || y >= A.H) return;
     const size_t pix = (size_t)y * A.Wp + x;
@@ -285,8 +307,8 @@ __global__ void __launch_bounds__(256) pbas_phaseB(const PbasArgs A) {
             const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
             if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) { // the source at (dx, dy) aims at this pixel ("none" has code 0xFF)
                 if(!loaded) {
-                    const uint32_t c = (uint32_t)vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x, y);
-                    const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.grad)[pix] : ((const uint32_t*)A.grad)[pix];
+                    const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
+                    const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
                     own = pbas_rec<CH>(c, g); loaded = true;
                 }
                 ((Rec*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = own;

@@ -14,7 +14,10 @@ struct lvb_pbas_context {
     uint32_t frame = 0;
     cudaStream_t stream = nullptr;
     uint8_t *d_img = nullptr, *d_mask = nullptr, *h_img = nullptr, *h_mask = nullptr;
-    void *bg = nullptr, *grad = nullptr; ushort* intents = nullptr;
+    void* bg = nullptr;
+    // planes written by frame k: [k & 1]; the scan of frame k+1 applies the neighbour writes they describe
+    void *grad[2] = {nullptr, nullptr}, *col[2] = {nullptr, nullptr}; ushort* intents[2] = {nullptr, nullptr};
+    bool nb_pending = false;
     float *R = nullptr, *T = nullptr, *meanmin = nullptr;
     uint32_t *raw_bits = nullptr, *fg_bits = nullptr, *magic = nullptr;
     PbasCtl* ctl = nullptr;
@@ -24,11 +27,12 @@ struct lvb_pbas_context {
     size_t rec_bytes() const { return MC == 1 ? 2 : 8; }
     size_t grad_bytes() const { return MC == 1 ? 1 : 4; }
     void free_all() {
-        for(void* p : {(void*)d_img, (void*)d_mask, bg, grad, (void*)intents, (void*)R, (void*)T, (void*)meanmin, (void*)raw_bits, (void*)fg_bits,
+        for(void* p : {(void*)d_img, (void*)d_mask, bg, grad[0], grad[1], col[0], col[1], (void*)intents[0], (void*)intents[1], (void*)R, (void*)T, (void*)meanmin, (void*)raw_bits, (void*)fg_bits,
                        (void*)magic, (void*)ctl, (void*)d_stats}) if(p) cudaFree(p);
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
-        d_img = d_mask = h_img = h_mask = nullptr; bg = grad = nullptr; intents = nullptr; R = T = meanmin = nullptr;
+        d_img = d_mask = h_img = h_mask = nullptr; bg = nullptr; grad[0] = grad[1] = col[0] = col[1] = nullptr; intents[0] = intents[1] = nullptr;
+        R = T = meanmin = nullptr; nb_pending = false;
         raw_bits = fg_bits = magic = nullptr; ctl = nullptr; d_stats = nullptr;
         initialized = false;
     }
@@ -40,7 +44,10 @@ PbasArgs pbas_args(lvb_pbas_context* c, const uint8_t* d_img, size_t pitch, int 
     PbasArgs A{};
     A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.WW = c->WW; A.N = c->N; A.REQ = c->REQ; A.thr0 = (float)c->thr;
     A.img = d_img; A.ipitch = pitch; A.in_ch = in_ch;
-    A.bg = c->bg; A.plane = c->plane; A.R = c->R; A.T = c->T; A.meanmin = c->meanmin; A.grad = c->grad; A.intents = c->intents;
+    A.bg = c->bg; A.plane = c->plane; A.R = c->R; A.T = c->T; A.meanmin = c->meanmin;
+    const int cur = (int)(c->frame & 1u);
+    A.grad = c->grad[cur]; A.col = c->col[cur]; A.intents = c->intents[cur];
+    A.prev_intents = c->nb_pending ? c->intents[cur ^ 1] : nullptr; A.prev_col = c->col[cur ^ 1]; A.prev_grad = c->grad[cur ^ 1];
     A.raw_bits = c->raw_bits; A.ctl = c->ctl;
     A.frame = c->frame; A.seed = c->seed; A.lr_override = lr_to_fixed(lr);
     A.n_magic = magic_of((uint32_t)c->N); A.magic = c->magic;
@@ -64,12 +71,22 @@ void pbas_enqueue(lvb_pbas_context* c, const uint8_t* d_img, size_t pitch, int i
     if(c->MC == 1) pbas_phaseA<1><<<g, b, 0, c->stream>>>(A); else pbas_phaseA<3><<<g, b, 0, c->stream>>>(A);
     LAUNCHED();
     if(c->profile) { CK(cudaEventRecord(e1, c->stream)); c->prof_events.push_back(e0); c->prof_events.push_back(e1); }
-    if(c->MC == 1) pbas_phaseB<1><<<g, b, 0, c->stream>>>(A); else pbas_phaseB<3><<<g, b, 0, c->stream>>>(A);
-    LAUNCHED();
+    c->nb_pending = true; // this frame's self-diffusion writes wait for the next frame's scan (or pbas_flush_pending)
     const dim3 mg(c->Wp / 32, (c->H + 8 * MEDIAN_ROWS - 1) / (8 * MEDIAN_ROWS));
     pp_median<<<mg, b, 0, c->stream>>>(c->raw_bits, c->fg_bits, d_mask, (size_t)c->W, c->W, c->H, c->WW, 9); // PBAS.cpp:269 / :494
     LAUNCHED();
     if(c->collect_stats) ++c->stat_frames;
+}
+
+/// apply the neighbour writes the latest frame queued (state export, getBackgroundImage)
+void pbas_flush_pending(lvb_pbas_context* c) {
+    if(!c->nb_pending) return;
+    PbasArgs A = pbas_args(c, c->d_img, c->ipitch, c->MC, 0.0);
+    const int last = (int)(c->frame & 1u);
+    A.prev_intents = c->intents[last]; A.prev_col = c->col[last]; A.prev_grad = c->grad[last];
+    if(c->MC == 1) pbas_phaseB<1><<<pbas_grid(c), dim3(32, 8), 0, c->stream>>>(A); else pbas_phaseB<3><<<pbas_grid(c), dim3(32, 8), 0, c->stream>>>(A);
+    LAUNCHED();
+    c->nb_pending = false;
 }
 
 } // namespace
@@ -126,8 +143,10 @@ int lvb_pbas_initialize(lvb_pbas_handle h, const uint8_t* img, int W, int H, int
     CK(cudaMallocHost((void**)&h->h_img, (size_t)W * H * h->MC));
     CK(cudaMallocHost((void**)&h->h_mask, (size_t)W * H));
     h->bg = dalloc<uint8_t>(st, (size_t)h->N * h->plane * h->rec_bytes());
-    h->grad = dalloc<uint8_t>(st, h->plane * h->grad_bytes());
-    h->intents = dalloc<ushort>(st, h->plane);
+    for(int i = 0; i < 2; ++i) {
+        h->grad[i] = dalloc<uint8_t>(st, h->plane * h->grad_bytes()); h->col[i] = dalloc<uint8_t>(st, h->plane * h->grad_bytes());
+        h->intents[i] = dalloc<ushort>(st, h->plane);
+    }
     h->R = dalloc<float>(st, h->plane); h->T = dalloc<float>(st, h->plane); h->meanmin = dalloc<float>(st, h->plane);
     h->raw_bits = dalloc<uint32_t>(st, (size_t)H * h->WW); h->fg_bits = dalloc<uint32_t>(st, (size_t)H * h->WW);
     h->d_stats = dalloc<unsigned long long>(st, 3);
@@ -198,6 +217,7 @@ int lvb_pbas_get_background_image(lvb_pbas_handle h, uint8_t* out) {
     REQUIRE(out != nullptr, "null output");
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)h->W * h->H * h->MC;
+    pbas_flush_pending(h);
     uint8_t* d = dalloc<uint8_t>(h->stream, n, false);
     const PbasArgs A = pbas_args(h, h->d_img, h->ipitch, h->MC, 0.0);
     if(h->MC == 1) pbas_background_kernel<1><<<pbas_grid(h), dim3(32, 8), 0, h->stream>>>(A, d); else pbas_background_kernel<3><<<pbas_grid(h), dim3(32, 8), 0, h->stream>>>(A, d);
@@ -219,6 +239,7 @@ int lvb_pbas_state(lvb_pbas_handle h, const char* name, void* inout, size_t byte
     REQUIRE(name && inout, "null argument");
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    pbas_flush_pending(h); // the model buffers below are complete ones
     CK(cudaStreamSynchronize(st));
     const std::string n(name);
     const size_t npx = (size_t)h->W * h->H;
@@ -253,7 +274,7 @@ int lvb_pbas_state(lvb_pbas_handle h, const char* name, void* inout, size_t byte
     } else if(n == "lastgrad") {
         REQUIRE(bytes == npx * h->MC && !set, "lastgrad is read-only, W*H*C bytes");
         std::vector<uint8_t> g(h->plane * h->grad_bytes());
-        d2h(st, g.data(), h->grad, g.size());
+        d2h(st, g.data(), h->grad[h->frame & 1u], g.size());
         uint8_t* o = (uint8_t*)inout;
         for(int y = 0; y < h->H; ++y) for(int x = 0; x < h->W; ++x) for(int c = 0; c < h->MC; ++c)
             o[((size_t)y * h->W + x) * h->MC + c] = g[((size_t)y * h->Wp + x) * h->grad_bytes() + c];
@@ -262,7 +283,11 @@ int lvb_pbas_state(lvb_pbas_handle h, const char* name, void* inout, size_t byte
         PbasCtl c0{};
         d2h(st, &c0, h->ctl, sizeof(c0));
         double* d = (double*)inout;
-        if(set) { h->frame = (uint32_t)d[0]; c0.former = (float)d[1]; h2d(st, h->ctl, &c0, sizeof(c0)); }
+        if(set) {
+            const uint32_t f = (uint32_t)d[0];
+            if((f ^ h->frame) & 1u) { std::swap(h->grad[0], h->grad[1]); std::swap(h->col[0], h->col[1]); std::swap(h->intents[0], h->intents[1]); } // "latest" planes stay latest
+            h->frame = f; c0.former = (float)d[1]; h2d(st, h->ctl, &c0, sizeof(c0));
+        }
         else { d[0] = (double)h->frame; d[1] = (double)c0.former; }
     } else REQUIRE(false, "unknown state buffer: " + n);
     LVB_CATCH
