@@ -46,6 +46,10 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.BackgroundSubtractorSuBSENSE()
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
+        lv.BackgroundSubtractorViBe_3ch()
+    with pytest.raises(lv.LitivError, match="no CPU fallback"):
+        lv.BackgroundSubtractorPBAS_1ch()
+    with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.LBSP(20).compute2(np.zeros((16, 16), np.uint8))
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.mask_op(lv.MASK_DILATE, np.zeros((16, 16), np.uint8), 1)

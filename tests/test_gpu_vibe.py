@@ -133,3 +133,24 @@ def test_cpu_restatement_timed_beside_the_gpu(lv, oracle, capsys):
     with capsys.disabled():
         print("\n" + json.dumps(line))
     assert gpu_s < cpu_s
+
+
+def test_interleaved_instances_are_independent(lv, oracle):
+    """several ViBe / PBAS instances fed in turn (one CUDA stream and one Philox key each, no shared rand()) end in exactly the state
+    of the same instance driven alone; the reference's instances perturb each other through libc rand()"""
+    seqs = [SynthSequence(96, 64, 3, seed=50 + i) for i in range(3)]
+    mk = [lambda s: lv.BackgroundSubtractorViBe_3ch(seed=s), lambda s: lv.BackgroundSubtractorPBAS_3ch(seed=s)]
+    for make in mk:
+        together = [make(i) for i in range(3)]
+        for g, q in zip(together, seqs):
+            g.initialize(q.frame(0))
+        masks = [[] for _ in range(3)]
+        for t in range(1, 12):
+            for i, (g, q) in enumerate(zip(together, seqs)):
+                masks[i].append(g.apply(q.frame(t)))
+        for i, q in enumerate(seqs):
+            alone = make(i)
+            alone.initialize(q.frame(0))
+            for t in range(1, 12):
+                assert np.array_equal(alone.apply(q.frame(t)), masks[i][t - 1]), (i, t)
+            assert np.array_equal(alone.getBackgroundImage(), together[i].getBackgroundImage())
