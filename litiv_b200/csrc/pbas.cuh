@@ -164,27 +164,20 @@ __global__ void __launch_bounds__(256, PBAS_MIN_BLOCKS) pbas_phaseA(const PbasAr
     }
     if(A.prev_intents != nullptr) { // neighbour writes queued by the previous frame (see vibe_phaseA)
         __shared__ ushort s_int[10][36];
-        vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
-        if(in_img) {
-            bool loaded = false;
-            Rec own = Rec();
-#pragma unroll
-            for(int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for(int dx = -1; dx <= 1; ++dx) {
-                    const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-                    if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) {
-                        if(!loaded) {
-                            const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
-                            const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
-                            own = pbas_rec<CH>(c, g); loaded = true;
-                        }
-                        const uint32_t slot = it & 0xFFu;
-                        ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = own;
-                        if(slot == 0u) v0 = own;
-                        if(slot == 1u) v1 = own;
-                    }
-                }
+        __shared__ uint32_t s_hits[8][32];
+        uint32_t hits = vibe_stage_hits(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int, s_hits);
+        if(in_img && hits) { // self-diffusion: every hit stores this pixel's own colour / gradient of the previous frame
+            const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
+            const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
+            const Rec own = pbas_rec<CH>(c, g);
+            while(hits) {
+                const int i = __ffs(hits) - 1, dy = i / 3 - 1, dx = i - (i / 3) * 3 - 1;
+                hits &= hits - 1u;
+                const uint32_t slot = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx] & 0xFFu;
+                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = own;
+                if(slot == 0u) v0 = own;
+                if(slot == 1u) v1 = own;
+            }
         }
     }
     uint32_t cur;
@@ -293,27 +286,20 @@ template<int CH>
 __global__ void __launch_bounds__(256) pbas_phaseB(const PbasArgs A) {
     typedef typename PbasRec<CH>::T Rec;
     __shared__ ushort s_int[10][36];
+    __shared__ uint32_t s_hits[8][32];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
+    uint32_t hits = vibe_stage_hits(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int, s_hits);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if(x >= A.W || y >= A.H) return;
+    if(x >= A.W || y >= A.H || !hits) return;
     const size_t pix = (size_t)y * A.Wp + x;
-    bool loaded = false;
-    Rec own = Rec();
-#pragma unroll
-    for(int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for(int dx = -1; dx <= 1; ++dx) {
-            const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-            if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) { // the source at (dx, dy) aims at this pixel ("none" has code 0xFF)
-                if(!loaded) {
-                    const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
-                    const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
-                    own = pbas_rec<CH>(c, g); loaded = true;
-                }
-                ((Rec*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = own;
-            }
-        }
+    const uint32_t c = CH == 1 ? (uint32_t)((const uchar*)A.prev_col)[pix] : ((const uint32_t*)A.prev_col)[pix];
+    const uint32_t g = CH == 1 ? (uint32_t)((const uchar*)A.prev_grad)[pix] : ((const uint32_t*)A.prev_grad)[pix];
+    const Rec own = pbas_rec<CH>(c, g);
+    while(hits) {
+        const int i = __ffs(hits) - 1, dy = i / 3 - 1, dx = i - (i / 3) * 3 - 1;
+        hits &= hits - 1u;
+        ((Rec*)A.bg)[(size_t)(s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx] & 0xFFu) * A.plane + pix] = own;
+    }
 }
 
 /// gradient image alone (initialize: PBAS.cpp:80-89 / :301-310)

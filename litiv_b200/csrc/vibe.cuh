@@ -60,17 +60,30 @@ __device__ __forceinline__ bool vibe_match(typename VibeCol<CH>::T cur, typename
     }
 }
 
-/// intent words of a 32x8 tile + 1-px halo -> shared memory ("none" outside the image); ends with a barrier
-__device__ __forceinline__ void vibe_stage_intents(const ushort* intents, int W, int H, int Wp, int x0, int y0, ushort (*s_int)[36]) {
+/// Stages the intent words of a 32x8 tile + 1-px halo in shared memory ("none" outside the image) and returns, for the calling
+/// thread's pixel, the mask of 3x3 neighbourhood positions whose pixel aims at it: bit (dy+1)*3 + (dx+1) for the source at
+/// (x+dx, y+dy), so ascending bits = raster order of the sources. Scatter inside the CTA: the ~6 % of entries that carry an intent
+/// mark their target with a shared-memory atomicOr, instead of every pixel testing its nine neighbours. Two barriers.
+__device__ __forceinline__ uint32_t vibe_stage_hits(const ushort* intents, int W, int H, int Wp, int x0, int y0, ushort (*s_int)[36],
+                                                    uint32_t (*s_hits)[32]) {
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    auto fetch = [&](int r, int c) {
+    s_hits[threadIdx.y][threadIdx.x] = 0u;
+    __syncthreads();
+    auto fetch = [&](int r, int c) { // tile coordinates incl. the halo
         const int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        s_int[r][c] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? intents[(size_t)gy * Wp + gx] : (ushort)VIBE_NO_INTENT;
+        const uint32_t it = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? (uint32_t)intents[(size_t)gy * Wp + gx] : VIBE_NO_INTENT;
+        s_int[r][c] = (ushort)it;
+        if(it != VIBE_NO_INTENT) {
+            const int code = (int)(it >> 8), oy = code / 3 - 1, ox = code - (code / 3) * 3 - 1; // source -> target offset (clamped)
+            const int tr = r - 1 + oy, tc = c - 1 + ox;                                         // target inside the 32x8 core?
+            if(tr >= 0 && tr < 8 && tc >= 0 && tc < 32) atomicOr(&s_hits[tr][tc], 1u << ((1 - oy) * 3 + (1 - ox)));
+        }
     };
     fetch(threadIdx.y + 1, threadIdx.x + 1);                          // core: one coalesced row per warp
     if(tid < 68) fetch(tid < 34 ? 0 : 9, tid < 34 ? tid : tid - 34);  // top / bottom halo rows
     else if(tid < 84) fetch(1 + ((tid - 68) & 7), tid < 76 ? 0 : 33); // left / right halo columns
     __syncthreads();
+    return s_hits[threadIdx.y][threadIdx.x];
 }
 
 #ifndef VIBE_MIN_BLOCKS
@@ -96,22 +109,18 @@ __global__ void __launch_bounds__(256, VIBE_MIN_BLOCKS) vibe_phaseA(const VibeAr
         if(N > 1u) v1 = bgr[A.plane];
         cur = vibe_load_pixel<CH>(A.img, A.ipitch, A.in_ch, x, y);
     }
-    if(pending) { // previous frame's intent tile + 1-px halo
-        vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
-        if(in_img) {
-#pragma unroll
-            for(int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                for(int dx = -1; dx <= 1; ++dx) { // raster order of the source (x+dx, y+dy)
-                    const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-                    if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx))) { // see vibe_phaseB
-                        const Col c = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
-                        const uint32_t slot = it & 0xFFu;
-                        ((Col*)A.bg)[(size_t)slot * A.plane + pix] = c; // later loads of this thread see it (same thread, same address)
-                        if(slot == 0u) v0 = c;
-                        if(slot == 1u) v1 = c;
-                    }
-                }
+    if(pending) { // neighbour writes queued by the previous frame, in raster order of their source (last writer wins)
+        __shared__ uint32_t s_hits[8][32];
+        uint32_t hits = vibe_stage_hits(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int, s_hits);
+        if(!in_img) hits = 0u;
+        while(hits) {
+            const int i = __ffs(hits) - 1, dy = i / 3 - 1, dx = i - (i / 3) * 3 - 1;
+            hits &= hits - 1u;
+            const uint32_t slot = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx] & 0xFFu;
+            const Col c = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
+            ((Col*)A.bg)[(size_t)slot * A.plane + pix] = c; // later loads of this thread see it (same thread, same address)
+            if(slot == 0u) v0 = c;
+            if(slot == 1u) v1 = c;
         }
     }
     if(in_img) {
@@ -177,21 +186,18 @@ template<int CH>
 __global__ void __launch_bounds__(256) vibe_phaseB(const VibeArgs A) {
     typedef typename VibeCol<CH>::T Col;
     __shared__ ushort s_int[10][36];
+    __shared__ uint32_t s_hits[8][32];
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    vibe_stage_intents(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int);
+    uint32_t hits = vibe_stage_hits(A.prev_intents, A.W, A.H, A.Wp, x0, y0, s_int, s_hits);
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x >= A.W || y >= A.H) return;
     const size_t pix = (size_t)y * A.Wp + x;
-#pragma unroll
-    for(int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-        for(int dx = -1; dx <= 1; ++dx) { // raster order of the source (x+dx, y+dy)
-            const uint32_t it = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx];
-            // the source at (dx, dy) aims at this pixel iff its clamped offset is (-dx, -dy): code (1 - dy) * 3 + (1 - dx); the
-            // "none" word has code 0xFF
-            if((it >> 8) == (uint32_t)((1 - dy) * 3 + (1 - dx)))
-                ((Col*)A.bg)[(size_t)(it & 0xFFu) * A.plane + pix] = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
-        }
+    while(hits) { // ascending bits = raster order of the sources
+        const int i = __ffs(hits) - 1, dy = i / 3 - 1, dx = i - (i / 3) * 3 - 1;
+        hits &= hits - 1u;
+        const uint32_t slot = s_int[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx] & 0xFFu;
+        ((Col*)A.bg)[(size_t)slot * A.plane + pix] = ((const Col*)A.prev_nbcol)[(size_t)(y + dy) * A.Wp + (x + dx)];
+    }
 }
 
 /// initialize (ViBe.cpp:58-76 / :115-138): sample s of pixel p = the init image at a 7x7-Gaussian-distributed neighbour (border 0)
