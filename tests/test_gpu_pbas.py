@@ -64,6 +64,10 @@ def test_non_default_parameters_gray_frames_and_errors(lv, oracle):
         f = seq.frame(t) if t % 2 else np.repeat(seq.frame(t)[..., None], 3, axis=2)
         assert np.array_equal(g.apply(f), o.apply(f)), t
     _compare(g, o, "gray into 3ch")
+    for t, lr in enumerate((1000.0, float("inf"), 257.0, 2.0), start=14):   # overrides beyond the in-kernel modulo table, and "never"
+        f = seq.frame(t)
+        assert np.array_equal(g.apply(f, lr), o.apply(f, lr)), (t, lr)
+    _compare(g, o, "large learning-rate overrides")
     with pytest.raises(lv.LitivError):
         lv.BackgroundSubtractorPBAS_1ch().initialize(np.zeros((8, 8, 3), np.uint8))
     with pytest.raises(lv.LitivError, match="initialized"):

@@ -56,6 +56,10 @@ def test_gray_frames_into_the_3ch_model(lv, oracle):
         f = seq.frame(t) if t % 2 else np.repeat(seq.frame(t)[..., None], 3, axis=2)   # 8UC1 and 8UC3 frames may alternate
         assert np.array_equal(g.apply(f), o.apply(f))
     assert np.array_equal(g.model(), o.model())
+    for t, lr in enumerate((1000.0, float("inf"), 1.0, 0.5), start=10):   # large, "never", and fractional (ceil -> 1) learning rates
+        f = seq.frame(t)
+        assert np.array_equal(g.apply(f, lr), o.apply(f, lr)), (t, lr)
+    assert np.array_equal(g.model(), o.model())
     with pytest.raises(lv.LitivError):
         lv.BackgroundSubtractorViBe_1ch().initialize(np.zeros((8, 8, 3), np.uint8))
 
