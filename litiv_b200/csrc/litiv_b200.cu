@@ -764,13 +764,17 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
-        CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
-        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->s_aux>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->s_aux>>>(B);
+        B.bump_frame = &c->ctl->frame_idx; // the frame counter (Philox index) advances in phase B: no tail kernel
+        // small frames are launch bound (BASELINE config #2, 320x240: 36 us of driver calls per frame with the fork / join below), so they
+        // run phase B and the median back to back on the instance stream; large frames overlap the two on the auxiliary stream
+        const bool serial = (size_t)W * H <= (size_t)640 * 480;
+        cudaStream_t sb = serial ? st : c->s_aux;
+        if(!serial) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); }
+        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, sb>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, sb>>>(B);
         LAUNCHED();
-        CK(cudaEventRecord(c->ev_join, c->s_aux));
+        if(!serial) CK(cudaEventRecord(c->ev_join, c->s_aux));
         pp_median<<<mg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();
-        lobster_tail_kernel<<<1, 1, 0, st>>>(c->ctl); LAUNCHED();
-        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+        if(!serial) CK(cudaStreamWaitEvent(st, c->ev_join, 0));
         if(mask_ready) CK(cudaEventRecord(mask_ready, st));
     }
     if(c->collect_stats) ++c->stat_frames;

@@ -133,7 +133,6 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         }
     }
 }
-__global__ void lobster_tail_kernel(FrameCtl* ctl) { ctl->frame_idx += 1; }
 
 /// initialisation (BackgroundSubtractionUtils.cpp:117-154 + BackgroundSubtractorLBSP.cpp:21-65):
 /// last_color = init image inside the ROI, last_desc = intra LBSP for ROI pixels strictly inside the 2-px border + 1 (Q4)

@@ -673,6 +673,7 @@ struct PhaseBArgs {
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
     const ushort* intents;
     const FrameCtl* ctl; uint32_t pending_seq; // pending_seq != 0: skip when FrameCtl::nb_applied_seq says these writes are already in the model
+    uint32_t* bump_frame;      // LOBSTER: FrameCtl::frame_idx, advanced by one thread here (the frame's pixel pass is over; saves a launch)
 };
 
 template<int CH>
@@ -691,6 +692,7 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
         s_int[r][cc] = (gx >= 0 && gx < A.W && gy >= 0 && gy < A.H) ? A.intents[(size_t)gy * A.Wp + gx] : (ushort)NO_INTENT;
     }
     __syncthreads();
+    if(A.bump_frame && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) *A.bump_frame += 1u;
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
     // pass 1: which of the 25 sources aim at this pixel (no global access); bit i = window position i = (dy+2)*5 + k
