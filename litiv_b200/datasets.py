@@ -164,7 +164,13 @@ def analyze(seq, algo, evaluate=True, output_dir=None, precache=True, init_frame
     pre = DataPrecacher(seq, with_gt=evaluate) if precache else None
     get = (lambda i: pre.get(i)) if pre else (lambda i: (seq.getInput(i), seq.getGT(i) if evaluate else None))
     first, _ = get(0)
-    algo.initialize(np.array(first, copy=True), seq.roi)
+    # ViBe / PBAS are plain cv::BackgroundSubtractor classes in the reference: initialize(img) without a ROI, synchronous apply, and
+    # their masks are scored from the host copy (with the sequence ROI, as the evaluator does for every algorithm)
+    lbsp_family = isinstance(algo, api._BackgroundSubtractor)
+    if lbsp_family:
+        algo.initialize(np.array(first, copy=True), seq.roi)
+    else:
+        algo.initialize(np.array(first, copy=True))
     counters = api.BinClassif(device=getattr(algo, "device", 0))
     masks = []
     if output_dir:
@@ -177,10 +183,10 @@ def analyze(seq, algo, evaluate=True, output_dir=None, precache=True, init_frame
     for idx in range(n):
         img, gt = get(idx)
         lr = 1.0 if idx <= init_frames else default_lr          # main.cpp:393
-        if evaluate or need_mask:
+        if evaluate or need_mask or not lbsp_family:
             mask = algo.apply(img, lr)
             if evaluate:
-                counters.accumulate(algo, gt, seq.roi)           # oBatch.push -> evaluator (BinClassif::accumulate with the GT ROI)
+                counters.accumulate(algo if lbsp_family else mask, gt, seq.roi)   # oBatch.push -> evaluator (BinClassif::accumulate with the GT ROI)
             if output_dir:
                 cv2.imwrite(os.path.join(output_dir, seq.getOutputName(idx) + ".png"), mask)
             if keep_masks:

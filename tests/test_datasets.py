@@ -63,3 +63,24 @@ def test_analyze_matches_oracle_loop(lv, oracle, tmp_path, precache):
     # throughput mode: no evaluation, no masks kept, two frames in flight
     fast = D.analyze(seq, lv.BackgroundSubtractorSuBSENSE(seed=4), evaluate=False, precache=precache)
     assert fast["frames"] == 24 and fast["metrics"] is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["vibe", "pbas"])
+def test_analyze_runs_vibe_and_pbas(lv, oracle, tmp_path, name):
+    """the same loop for the two plain cv::BackgroundSubtractor classes (no ROI at initialize; masks scored from the host copy)"""
+    D = _datasets()
+    d = D.write_synthetic_cdnet(str(tmp_path), "highway", 320, 240, 16, seed=6)
+    seq = D.CDnetSequence(d)
+    if name == "vibe":
+        g, o = lv.BackgroundSubtractorViBe_3ch(seed=4), oracle.ViBeOracle(3, mode=oracle.MODE_SNAPSHOT, seed=4)
+    else:
+        g, o = lv.BackgroundSubtractorPBAS_3ch(seed=4), oracle.PBASOracle(3, mode=oracle.MODE_SNAPSHOT, seed=4)
+    out = D.analyze(seq, g, evaluate=True, init_frames=5, keep_masks=True)
+    o.initialize(seq.getInput(0))
+    want = np.zeros(6, np.uint64)
+    for i in range(len(seq)):
+        m = o.apply(seq.getInput(i), 1.0 if i <= 5 else g.getDefaultLearningRate())
+        assert np.array_equal(out["masks"][i], m), f"frame {i}"
+        want = oracle.binclassif(m, seq.getGT(i), seq.roi, counters=want)
+    assert np.array_equal(out["counters"], want)

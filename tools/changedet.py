@@ -12,7 +12,7 @@ from litiv_b200 import datasets as D
 ap = argparse.ArgumentParser()
 ap.add_argument("--root")
 ap.add_argument("--synthetic", help="WxH:frames")
-ap.add_argument("--algo", default="subsense", choices=["subsense", "lobster", "pawcs"])
+ap.add_argument("--algo", default="subsense", choices=["subsense", "lobster", "pawcs", "vibe", "pbas"])
 ap.add_argument("--no-eval", action="store_true", help="throughput mode: no scoring, two frames in flight")
 ap.add_argument("--no-precache", action="store_true")
 ap.add_argument("--save", help="directory for bin%%06d.png masks")
@@ -23,7 +23,8 @@ if args.synthetic:
     w, h = (int(v) for v in size.split("x"))
     root = tempfile.mkdtemp(prefix="cdnet_synth_")
     D.write_synthetic_cdnet(root, "synthetic", w, h, int(n), seed=7)
-cls = {"subsense": lv.BackgroundSubtractorSuBSENSE, "lobster": lv.BackgroundSubtractorLOBSTER, "pawcs": lv.BackgroundSubtractorPAWCS}[args.algo]
+cls = {"subsense": lv.BackgroundSubtractorSuBSENSE, "lobster": lv.BackgroundSubtractorLOBSTER, "pawcs": lv.BackgroundSubtractorPAWCS,
+       "vibe": lv.BackgroundSubtractorViBe_3ch, "pbas": lv.BackgroundSubtractorPBAS_3ch}[args.algo]
 for cat in sorted(os.listdir(root)):
     cdir = os.path.join(root, cat)
     if not os.path.isdir(cdir):
