@@ -94,6 +94,11 @@ double lvb_default_learning_rate(int algo);
 int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref_or_null, int width, int height, int channels,
                      int use_rel, float rel, int thr, uint16_t* out, int device);
 
+/* LBSP::computeDescriptor_gradient<C, nAbsOffset = 20, nRelShift = 2> evaluated densely (features2d/include/litiv/features2d/LBSP.hpp:
+ * 235-256; the per-pixel primitive of the LBSP edge detector, imgproc/src/EdgeDetectorLBSP.cpp:253). out: [H][W][4] bytes = gradX (int8),
+ * gradY (int8), gradient magnitude (0..16), 0 -- the layout of the detector's gradient map (:196); the 2-px border is (0,0,0,0). */
+int lvb_lbsp_gradient(const uint8_t* img, int width, int height, int channels, uint8_t* out, int device);
+
 /* the bit-packed mask operators that replace the reference's OpenCV calls (SuBSENSE.cpp:536-554), standalone on byte masks:
  * op 0 cv::dilate / 1 cv::erode with a (2*param+1)^2 rect (param 1 or 3) ; 2 cv::medianBlur(param) on a binary mask ;
  * 3 cv::floodFill((0,0),255)+bitwise_not ("holes": background not 4-connected to the border, needs src(0,0)==0) */

@@ -30,7 +30,7 @@ EXPORTS = [
     "lvb_vibe_get_profile", "lvb_vibe_stream",
     "lvb_pbas_create", "lvb_pbas_destroy", "lvb_pbas_initialize", "lvb_pbas_apply", "lvb_pbas_apply_device", "lvb_pbas_sync",
     "lvb_pbas_get_background_image", "lvb_pbas_state", "lvb_pbas_set_collect_stats", "lvb_pbas_get_stats", "lvb_pbas_set_profile",
-    "lvb_pbas_get_profile", "lvb_pbas_stream",
+    "lvb_pbas_get_profile", "lvb_pbas_stream", "lvb_lbsp_gradient",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
         L.lvb_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_lbsp_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
         L.lvb_default_params.argtypes = [C.c_int, C.c_void_p]
+        L.lvb_lbsp_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.lvb_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_get_profile_feedback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -596,6 +597,17 @@ class DeviceBatch:
             self._ip[i] = d_img_ptrs[i]
             self._mp[i] = d_mask_ptrs[i] if d_mask_ptrs is not None else None
         _chk(lib().lvb_apply_batch_device(self._hs, self._ip, d_step, self._mp, self.n, float(learningRate)))
+
+
+def lbsp_gradient(img, device=0):
+    """dense LBSP::computeDescriptor_gradient (features2d LBSP.hpp:235-256): [H][W][4] u8 = gradX (int8), gradY (int8), magnitude, 0"""
+    img = np.ascontiguousarray(img)
+    if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0:
+        raise LitivError("input image must be non-empty, continuous, and of type 8UC1/8UC3")
+    h, w = img.shape[:2]
+    out = np.empty((h, w, 4), np.uint8)
+    _chk(lib().lvb_lbsp_gradient(img.ctypes.data, w, h, 1 if img.ndim == 2 else img.shape[2], out.ctypes.data, device))
+    return out
 
 
 class LBSP:

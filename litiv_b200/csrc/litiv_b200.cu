@@ -1633,6 +1633,31 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
     LVB_CATCH
 }
 
+int lvb_lbsp_gradient(const uint8_t* img, int W, int H, int C, uint8_t* out, int device) {
+    LVB_TRY
+    REQUIRE(img && out && (C == 1 || C == 3), "input image must be non-empty, continuous, and of type 8UC1/8UC3");
+    REQUIRE(W >= 5 && H >= 5, "input image size is too small to compute descriptors with current patch size");
+    REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
+    CK(cudaSetDevice(device));
+    const size_t pitch = ((size_t)W * C + 127) / 128 * 128, npx = (size_t)W * H;
+    uint8_t* d_img = dalloc<uint8_t>((cudaStream_t)0, pitch * H);
+    uchar4* d_out = nullptr;
+    try {
+        d_out = dalloc<uchar4>((cudaStream_t)0, npx, false);
+        CK(cudaMemcpy2D(d_img, pitch, img, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice));
+        CUtensorMap tmap;
+        LbspGradArgs A{};
+        A.W = W; A.H = H; A.img = d_img; A.ipitch = pitch; A.out = d_out;
+        A.use_tma = make_image_tmap(&tmap, d_img, W, H, C, pitch) ? 1 : 0;
+        const dim3 g((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H), b(TILE_W, TILE_H);
+        if(C == 1) lbsp_gradient_kernel<1><<<g, b>>>(A, tmap); else lbsp_gradient_kernel<3><<<g, b>>>(A, tmap);
+        LAUNCHED();
+        d2h((cudaStream_t)0, out, d_out, npx * 4);
+    } catch(...) { cudaFree(d_img); cudaFree(d_out); throw; }
+    cudaFree(d_img); cudaFree(d_out);
+    LVB_CATCH
+}
+
 /// lv::BinClassif::accumulate (datasets/src/metrics.cpp:21-61) on the device; see csrc/metrics.cuh
 static void binclassif_run(cudaStream_t st, int W, int H, int WW, const uint8_t* d_classif, const uint32_t* d_bits, const uint8_t* gt, const uint8_t* roi,
                            uint64_t counters[6], uint8_t* d_gt, uint8_t* d_roi, unsigned long long* d_cnt) {

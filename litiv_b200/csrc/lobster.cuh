@@ -236,4 +236,40 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_dense_kernel(const LbspA
     }
 }
 
+/// dense LBSP gradient map (LBSP::computeDescriptor_gradient<C, 20, 2>, features2d/include/litiv/features2d/LBSP.hpp:235-256, the
+/// per-pixel primitive of imgproc/src/EdgeDetectorLBSP.cpp:253): 4 bytes per pixel = gradX (int8), gradY (int8), magnitude, 0.
+/// Pixels within the 2-px border get (0,0,0,0), the value the edge detector's all-equal border lookup yields (:84-100).
+struct LbspGradArgs { int W, H; const uchar* img; size_t ipitch; uchar4* out; int use_tma; };
+template<int CH>
+__global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_gradient_kernel(const LbspGradArgs A, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int PITCH = tile_pitch(CH);
+    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    stage_tile<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if(x >= A.W || y >= A.H) return;
+    uchar4 o = make_uchar4(0, 0, 0, 0);
+    if(x >= 2 && y >= 2 && x < A.W - 2 && y < A.H - 2) {
+        const int sx = threadIdx.x + HALO, sy = threadIdx.y + HALO;
+        uint32_t best = 0; int best_mag = -1;
+#pragma unroll
+        for(int k = 0; k < CH; ++k) {
+            const int c = k == 0 ? CH - 1 : k - 1; // the reference starts from the last channel and replaces on strictly greater
+            const uint32_t ref = s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
+            const Lookup16 L = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
+            const uint32_t d = lbsp_threshold(L, ref, ((ref >> 2) + 20u) >> 1);
+            const int m = __popc(d);
+            if(best_mag < m) { best_mag = m; best = d; }
+        }
+        constexpr uint32_t XP = (1u<<0)|(1u<<4)|(1u<<7)|(1u<<9)|(1u<<12)|(1u<<15), XN = (1u<<1)|(1u<<5)|(1u<<6)|(1u<<11)|(1u<<13)|(1u<<14);
+        constexpr uint32_t YP = (1u<<3)|(1u<<4)|(1u<<6)|(1u<<8)|(1u<<13)|(1u<<15), YN = (1u<<2)|(1u<<5)|(1u<<7)|(1u<<10)|(1u<<12)|(1u<<14); // LBSP.hpp:288-291
+        o.x = (uchar)(signed char)(__popc(best & XP) - __popc(best & XN));
+        o.y = (uchar)(signed char)(__popc(best & YP) - __popc(best & YN));
+        o.z = (uchar)best_mag;
+    }
+    A.out[(size_t)y * A.W + x] = o;
+}
+
 } // namespace lvb

@@ -172,9 +172,41 @@ inline ushort lbsp_threshold(const uchar vals[16], uchar ref, uchar t) {
 #endif
 }
 
-/// features2d/src/LBSP.cpp:102-152 (lbsp_computeImpl, dense; abs or rel threshold; optional ref image)
+/// LBSP::computeDescriptor_gradient<nChannels, nAbsOffset=20, nRelShift=2> (features2d/include/litiv/features2d/LBSP.hpp:235-256):
+/// per channel the pattern is thresholded with t = ((ref >> 2) + 20) / 2; the channel with the largest popcount wins (the scan starts
+/// from the LAST channel and replaces on strictly greater); gradX / gradY = popcount differences over the masks of LBSP.hpp:288-291.
+static const ushort LBSP_GRADX_POS = (1<<0)|(1<<4)|(1<<7)|(1<<9)|(1<<12)|(1<<15), LBSP_GRADX_NEG = (1<<1)|(1<<5)|(1<<6)|(1<<11)|(1<<13)|(1<<14);
+static const ushort LBSP_GRADY_POS = (1<<3)|(1<<4)|(1<<6)|(1<<8)|(1<<13)|(1<<15), LBSP_GRADY_NEG = (1<<2)|(1<<5)|(1<<7)|(1<<10)|(1<<12)|(1<<14);
+inline void lbsp_gradient_point(const uchar* img, int W, int C, int x, int y, signed char& gx, signed char& gy, uchar& mag) {
+    ushort best = 0; int best_mag = -1;
+    for(int k = 0; k < C; ++k) {
+        const int c = k == 0 ? C - 1 : k - 1; // channel order of the reference: last, then 0 .. C-2
+        uchar vals[16];
+        lbsp_lookup(img, W, C, x, y, c, vals);
+        const uchar ref = img[((size_t)y * W + x) * C + c];
+        const ushort d = lbsp_threshold(vals, ref, (uchar)((((int)ref >> 2) + 20) / 2));
+        const int m = __builtin_popcount((unsigned)d);
+        if(best_mag < m) { best_mag = m; best = d; }
+    }
+    mag = (uchar)best_mag;
+    gx = (signed char)(__builtin_popcount((unsigned)(best & LBSP_GRADX_POS)) - __builtin_popcount((unsigned)(best & LBSP_GRADX_NEG)));
+    gy = (signed char)(__builtin_popcount((unsigned)(best & LBSP_GRADY_POS)) - __builtin_popcount((unsigned)(best & LBSP_GRADY_NEG)));
+}
+/// dense map in the layout of EdgeDetectorLBSP's gradient map (imgproc/src/EdgeDetectorLBSP.cpp:196: 4 bytes per pixel = gradX, gradY,
+/// magnitude, 0); pixels within the 2-px border have the all-equal lookup of :84-100, i.e. a zero pattern: (0, 0, 0, 0)
+inline void lbsp_gradient_dense(const uchar* img, int W, int H, int C, uchar* out) {
+    std::memset(out, 0, (size_t)W * H * 4);
+    for(int y = 2; y < H - 2; ++y) for(int x = 2; x < W - 2; ++x) {
+        signed char gx, gy; uchar mag;
+        lbsp_gradient_point(img, W, C, x, y, gx, gy, mag);
+        uchar* o = out + ((size_t)y * W + x) * 4;
+        o[0] = (uchar)gx; o[1] = (uchar)gy; o[2] = mag;
+    }
+}
+
 /// The 2-px border of the output is left untouched (the reference never writes it); we keep whatever
 /// the caller put there (tests pre-fill zeros).
+/// features2d/src/LBSP.cpp:102-152 (lbsp_computeImpl, dense; abs or rel threshold; optional ref image)
 inline void lbsp_compute_dense(const uchar* img, const uchar* ref_or_null, int W, int H, int C,
                                bool use_rel, float rel, size_t thr, ushort* out) {
     const uchar* ref = ref_or_null ? ref_or_null : img;

@@ -309,6 +309,16 @@ def lbsp_compute(img, ref=None, rel=None, thr=0):
     return out[..., 0] if c == 1 else out
 
 
+def lbsp_gradient(img):
+    """dense LBSP::computeDescriptor_gradient map: [H][W][4] u8 = gradX (int8), gradY (int8), magnitude, 0"""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape[:2]
+    c = 1 if img.ndim == 2 else img.shape[2]
+    out = np.zeros((h, w, 4), np.uint8)
+    _chk(lib().lvo_lbsp_gradient(img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def binclassif(classif, gt=None, roi=None, counters=None):
     """lv::BinClassif::accumulate (datasets/src/metrics.cpp:21-61); returns the six counters TP,TN,FP,FN,SE,DC (added to `counters`)"""
     classif = np.ascontiguousarray(classif, dtype=np.uint8)

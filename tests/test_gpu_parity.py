@@ -46,6 +46,21 @@ def test_lbsp_matches_oracle(lv, oracle, shape, mode):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("shape", [(37, 53, 3), (64, 64, 1), (5, 5, 3), (9, 130, 1), (240, 320, 3), (1080, 1920, 3)])
+def test_lbsp_gradient_matches_oracle(lv, oracle, shape):
+    """dense LBSP::computeDescriptor_gradient (the per-pixel primitive of EdgeDetectorLBSP): bit-exact gradX / gradY / magnitude"""
+    rng = np.random.RandomState(hash(shape) & 0xFFFF)
+    img = rng.randint(0, 256, shape).astype(np.uint8)
+    if shape[2] == 1:
+        img = img[..., 0]
+    got, want = lv.lbsp_gradient(img), oracle.lbsp_gradient(img)
+    assert np.array_equal(got, want)
+    smooth = np.ascontiguousarray(np.clip(np.cumsum(np.cumsum(rng.randint(-3, 4, shape), axis=0), axis=1) + 128, 0, 255).astype(np.uint8))
+    if shape[2] == 1:
+        smooth = smooth[..., 0]
+    assert np.array_equal(lv.lbsp_gradient(smooth), oracle.lbsp_gradient(smooth))
+
+
 def _mk(lv, oracle, algo, seed, **kw):
     if algo == "subsense":
         return lv.BackgroundSubtractorSuBSENSE(seed=seed, **kw), oracle.Oracle(oracle.ALGO_SUBSENSE, mode=oracle.MODE_SNAPSHOT, seed=seed)

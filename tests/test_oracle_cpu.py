@@ -193,3 +193,20 @@ def test_oracle_determinism_and_api_errors(oracle):
     # small frame -> "small" branch of SuBSENSE.cpp:121-128
     sc = a.state_get("scalars")
     assert sc[4] == 0 and sc[7] == 4.0 and sc[8] == 512.0 and sc[6] == 9
+
+
+def test_lbsp_gradient_known_answers(oracle):
+    """LBSP::computeDescriptor_gradient (features2d LBSP.hpp:235-256) on patterns whose answer follows from the masks of :288-291"""
+    O = oracle
+    flat = np.full((9, 9), 100, np.uint8)
+    assert not O.lbsp_gradient(flat).any()                       # no neighbour differs by more than t = ((100 >> 2) + 20) / 2 = 22
+    step = flat.copy(); step[:, 5:] = 200                        # vertical edge right of the centre column
+    g = O.lbsp_gradient(step)[4, 4]
+    # neighbours with dx > 0 differ (bits 1, 5, 6 at dx = +2; 11, 13, 14 at dx = +1): six bits, all in the GradX_Neg mask
+    assert g[2] == 6 and np.int8(g[0]) == -6 and np.int8(g[1]) == 0
+    g = O.lbsp_gradient(np.ascontiguousarray(step.T))[4, 4]      # horizontal edge below the centre row: dy > 0 bits = GradY_Pos
+    assert g[2] == 6 and np.int8(g[0]) == 0 and np.int8(g[1]) == 6
+    # three channels: the channel with the most differing neighbours wins; ties keep the LAST channel
+    rgb = np.stack([flat, step, flat], axis=2)
+    assert np.array_equal(O.lbsp_gradient(rgb)[4, 4], O.lbsp_gradient(step)[4, 4])
+    assert not O.lbsp_gradient(rgb)[:2].any() and not O.lbsp_gradient(rgb)[:, -2:].any()   # 2-px border: zero pattern
