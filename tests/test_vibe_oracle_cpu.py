@@ -93,3 +93,13 @@ def test_background_image_is_float_mean_round_half_even(oracle):
     for s in range(m.shape[0]):
         acc = acc + m[s] / np.float32(m.shape[0])
     assert np.array_equal(v.get_background_image(), np.clip(np.rint(acc), 0, 255).astype(np.uint8))
+
+
+def test_integer_form_of_the_l2_test_is_exact():
+    """the kernel evaluates `(float)sqrt(n) < T` (ViBe.cpp:171 through lv::L2dist) as `n < T*T`: exhaustive over every uint16 sum and every
+    threshold the API accepts (T = 3 * nColorDistThreshold <= 765)"""
+    n = np.arange(65536, dtype=np.float32)
+    r = np.sqrt(n)                                   # correctly rounded float32 square root, as std::sqrt(float)
+    ni = np.arange(65536, dtype=np.int64)
+    for T in range(0, 766):
+        assert np.array_equal(r < np.float32(T), ni < T * T), T
