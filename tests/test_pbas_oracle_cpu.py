@@ -21,25 +21,30 @@ def test_gradient_image_matches_cv2(oracle, shape):
 
 @pytest.mark.parametrize("ch", [1, 3])
 def test_snapshot_mode_within_seed_noise_of_reference_order(oracle, ch):
+    """tier 3: per-pixel disagreement and F-measure against the synthetic ground truth stay within the seed-to-seed spread of the
+    reference order"""
     O = oracle
     seq = SynthSequence(160, 120, ch, seed=12)
-    frames = [seq.frame(t) for t in range(70)]
+    frames = [seq.frame(t, with_gt=True) for t in range(70)]
 
     def run(mode, seed):
         v = O.PBASOracle(ch, mode=mode, seed=seed)
-        v.initialize(frames[0])
-        return np.stack([v.apply(f) for f in frames[1:]])[25:], v
+        v.initialize(frames[0][0])
+        return np.stack([v.apply(f) for f, _ in frames[1:]])[25:], v
 
+    gts = np.stack([g for _, g in frames[1:]])[25:]
+    fm = lambda m: 2 * ((m > 0) & gts).sum() / max(2 * ((m > 0) & gts).sum() + ((m > 0) & ~gts).sum() + ((m == 0) & gts).sum(), 1)
     refs = [run(O.MODE_REFERENCE, s)[0] for s in (1, 2, 3)]
     snaps = [run(O.MODE_SNAPSHOT, s) for s in (1, 2)]
     noise = max((refs[i] != refs[j]).mean() for i in range(3) for j in range(i + 1, 3))
     gap = max((s != r).mean() for s, _ in snaps for r in refs)
     assert gap <= 1.5 * noise + 0.002, (gap, noise)
+    f_ref, f_snap = [fm(r) for r in refs], [fm(s) for s, _ in snaps]
+    assert abs(np.mean(f_snap) - np.mean(f_ref)) <= (max(f_ref) - min(f_ref)) + 0.02, (f_snap, f_ref)
     v = snaps[0][1]
     R, T, mm = v.state_get("R"), v.state_get("T"), v.state_get("meanmin")
     assert R.min() >= 0.6 * 0.95 - 1e-6 and R.max() <= 99 * 1.05 and T.min() >= 2.0 and T.max() <= 200.0 and mm.min() >= 0 and mm.max() <= 1.0
     assert v.state_get("scalars")[1] >= 20.0   # m_fFormerMeanGradDist floor (PBAS.cpp:224)
-
 
 def test_self_diffusion_writes_the_neighbours_own_pixel(oracle):
     """BGSPBAS_USE_SELF_DIFFUSION (PBAS.cpp:190-191): every model sample of a pixel is one of that pixel's own past colours or an
