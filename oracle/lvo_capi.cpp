@@ -8,6 +8,7 @@
 #endif
 #include "lvo_vibe.hpp"
 #include "lvo_pbas.hpp"
+#include "lvo_edge_lbsp.hpp"
 #include <map>
 #include <chrono>
 
@@ -277,6 +278,28 @@ int lvo_lbsp_gradient(const uint8_t* img, int w, int h, int c, uint8_t* out) {
     LVO_TRY
     if(!img || (c != 1 && c != 3) || w < 5 || h < 5) throw std::runtime_error("input image must be non-empty, 8UC1/8UC3 and at least 5x5");
     lbsp_gradient_dense(img, w, h, c, out);
+    LVO_CATCH
+}
+
+// --- EdgeDetectorLBSP (imgproc/src/EdgeDetectorLBSP.cpp): oracle only so far (SURVEY 8f rank 4 groundwork)
+int lvo_edge_create(int levels, double hyst_low_factor, void** out) {
+    LVO_TRY
+    if(levels < 1) throw std::runtime_error("number of pyramid levels must be positive");
+    if(!(hyst_low_factor > 0 && hyst_low_factor < 1)) throw std::runtime_error("lower hysteresis threshold factor must be between 0 and 1");
+    EdgeDetectorLBSP* e = new EdgeDetectorLBSP();
+    e->n_levels = levels; e->hyst_low_factor = hyst_low_factor;
+    *out = e;
+    LVO_CATCH
+}
+int lvo_edge_destroy(void* h) { delete (EdgeDetectorLBSP*)h; return 0; }
+int lvo_edge_apply_threshold(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out, double thr) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply_threshold(img, w, hh, c, out, thr); LVO_CATCH }
+int lvo_edge_apply(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply(img, w, hh, c, out); LVO_CATCH }
+/// gradient map of the latest pass without its padding: [H][W][4] = gradX, gradY, magnitude (min over the scales), pad
+int lvo_edge_gradient_map(void* h, int w, int hh, uint8_t* out) {
+    LVO_TRY
+    EdgeDetectorLBSP* e = (EdgeDetectorLBSP*)h;
+    if(e->grad.size() != (size_t)(w + 4) * (hh + 4) * 4) throw std::runtime_error("no pass of that size has run");
+    for(int r = 0; r < hh; ++r) std::memcpy(out + (size_t)r * w * 4, e->grad.data() + ((size_t)(r + 2) * (w + 4) + 2) * 4, (size_t)w * 4);
     LVO_CATCH
 }
 

@@ -288,6 +288,40 @@ def pbas_gradient_image(img):
     return out
 
 
+class EdgeDetectorLBSPOracle:
+    """EdgeDetectorLBSP (imgproc/src/EdgeDetectorLBSP.cpp) over the CPU restatement (oracle/lvo_edge_lbsp.hpp); like the reference
+    object it keeps its gradient / mask buffers between calls"""
+
+    def __init__(self, levels=3, hyst_low_factor=0.5):
+        self._h = C.c_void_p()
+        _chk(lib().lvo_edge_create(levels, C.c_double(hyst_low_factor), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.lvo_edge_destroy(self._h)
+            self._h = None
+
+    def apply_threshold(self, img, thr=0.5):
+        img, c = ViBeOracle._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().lvo_edge_apply_threshold(self._h, img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p), C.c_double(thr)))
+        return out
+
+    def apply(self, img):
+        img, c = ViBeOracle._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().lvo_edge_apply(self._h, img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def gradient_map(self, shape):
+        h, w = shape[:2]
+        out = np.empty((h, w, 4), np.uint8)
+        _chk(lib().lvo_edge_gradient_map(self._h, w, h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
 def vibe_match(model_channels, thr, a, b):
     a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
     return bool(lib().lvo_vibe_match(model_channels, thr, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))

@@ -1,0 +1,72 @@
+"""CPU tests of the EdgeDetectorLBSP oracle (oracle/lvo_edge_lbsp.hpp; SURVEY 8f rank 4 groundwork: no CUDA counterpart yet).
+The reference has no test or golden vector for the detector (parity unpinned); these tests pin the restatement's documented properties,
+including the three observable quirks of the source listed in DESIGN.md (row shift, unwritten mask rows, little-endian initial value)."""
+import numpy as np
+import pytest
+
+from litiv_b200.synth import SynthSequence
+
+
+def _square(n=64, lo=60, hi=200, a=20, b=44):
+    img = np.full((n, n), lo, np.uint8)
+    img[a:b, a:b] = hi
+    return img
+
+
+def test_flat_image_has_no_edges_and_square_has_a_closed_outline(oracle):
+    O = oracle
+    assert not O.EdgeDetectorLBSPOracle().apply_threshold(np.full((48, 64, 3), 90, np.uint8)).any()
+    m = O.EdgeDetectorLBSPOracle(levels=1).apply_threshold(_square(), 0.3)
+    assert set(np.unique(m)) == {0, 255}
+    ys, xs = np.nonzero(m)
+    assert xs.min() in (18, 19, 20) and xs.max() in (43, 44, 45)        # columns: around the square's sides
+    # rows: the non-maximum-suppression loop writes gradient row r+2 into mask row r (EdgeDetectorLBSP.cpp:263, 270-272)
+    assert ys.min() in (16, 17, 18) and ys.max() in (41, 42, 43)
+    assert not m[30, 25:40].any()                                       # nothing inside the square
+
+
+def test_gradient_map_keeps_the_little_endian_initial_value_quirk(oracle):
+    """(CHAR_MAX<<24)|(CHAR_MAX<<16)|(UCHAR_MAX<<8) stored as uint32 -> per-pixel bytes (gradX, gradY, mag, pad) = (0, -1, 127, 127):
+    with the min-|.| combination gradX stays 0 and |gradY| <= 1; the magnitude is the minimum over the scales"""
+    O = oracle
+    f = SynthSequence(160, 120, 3, seed=3).frame(10)
+    e1 = O.EdgeDetectorLBSPOracle(levels=1)
+    e1.apply_threshold(f)
+    g = e1.gradient_map(f.shape)
+    own = O.lbsp_gradient(f)
+    assert not g[..., 0].any() and np.abs(g[..., 1].view(np.int8)).max() <= 1
+    assert np.array_equal(g[..., 2], own[..., 2])                       # one scale: min(own, 127) = own
+    gy_own = own[..., 1].view(np.int8).astype(int)
+    want_gy = np.where(np.abs(gy_own) <= 1, gy_own, -1)                 # std::min(new, -1, |a| < |b|)
+    assert np.array_equal(g[..., 1].view(np.int8).astype(int), want_gy)
+    e3 = O.EdgeDetectorLBSPOracle(levels=3)
+    e3.apply_threshold(f)
+    assert (e3.gradient_map(f.shape)[..., 2] <= g[..., 2]).all()        # more scales can only lower the magnitude
+
+
+def test_thresholds_are_monotone_and_confidence_map_counts_them(oracle):
+    O = oracle
+    f = SynthSequence(128, 96, 1, seed=8).frame(12)
+    masks = [O.EdgeDetectorLBSPOracle().apply_threshold(f, t / 16.0) > 0 for t in range(16)]   # fresh objects
+    for a, b in zip(masks[:-1], masks[1:]):
+        assert not (b & ~a).any()                                       # a higher threshold never adds an edge pixel
+    assert masks[2].any() and masks[2].sum() > masks[10].sum()
+    conf = O.EdgeDetectorLBSPOracle().apply(f)                          # apply(): sixteen passes on ONE object, 16 per hit, saturated
+    assert set(np.unique(conf)) <= set(list(range(0, 256, 16)) + [255])
+    assert (conf > 0).any() and conf.max() <= 255
+    assert np.array_equal(O.EdgeDetectorLBSPOracle().apply_threshold(f, -1.0), O.EdgeDetectorLBSPOracle().apply_threshold(f, 0.5))   # default
+
+
+def test_repeatable_on_one_object_and_errors(oracle):
+    O = oracle
+    f = SynthSequence(96, 80, 3, seed=1).frame(7)
+    e = O.EdgeDetectorLBSPOracle()
+    a = e.apply_threshold(f, 0.4)
+    assert np.array_equal(a, e.apply_threshold(f, 0.4))                 # the buffers persist between calls, the same input reproduces
+    assert np.array_equal(a, O.EdgeDetectorLBSPOracle().apply_threshold(f, 0.4))
+    with pytest.raises(O.OracleError, match="too small"):
+        O.EdgeDetectorLBSPOracle(levels=3).apply_threshold(np.zeros((12, 40), np.uint8))       # 12 -> 6 -> 3 rows
+    with pytest.raises(O.OracleError):
+        O.EdgeDetectorLBSPOracle(levels=0)
+    with pytest.raises(O.OracleError):
+        O.EdgeDetectorLBSPOracle(hyst_low_factor=1.0)
