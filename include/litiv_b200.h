@@ -187,6 +187,22 @@ int lvb_pbas_set_profile(lvb_pbas_handle h, int enabled);
 int lvb_pbas_get_profile(lvb_pbas_handle h, double* ms_total, uint64_t* launches);
 void* lvb_pbas_stream(lvb_pbas_handle h);
 
+/* EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83; imgproc/src/EdgeDetectorLBSP.cpp:26-433): the LBSP
+ * multi-scale edge detector. create = the constructor (nLevels = 3, dHystLowThrshFactor = 0.5; same argument checks, :31-32).
+ * apply_threshold (:391-410): edges[H][W] = 255 on edge pixels for one detection threshold in [0,1] (outside: the default 0.5).
+ * apply (:412-433): confidence[H][W] = 16 x the number of thresholds 0/16 .. 15/16 that mark the pixel. img: host, continuous,
+ * 8UC1 or 8UC3. Like the reference object the detector keeps its maps between calls (the two mask rows its suppression loop never
+ * writes are carried from call to call); get_gradient_map: [H][W][4] = gradX, gradY, magnitude (min over the scales), pad of the
+ * latest call. flood_sweeps: relaxation sweeps the hysteresis of the latest call needed (diagnostic). */
+typedef struct lvb_edge_context* lvb_edge_handle;
+int lvb_edge_create(int levels, double hyst_low_factor, int device, lvb_edge_handle* out);
+int lvb_edge_destroy(lvb_edge_handle h);
+double lvb_edge_default_threshold(void);
+int lvb_edge_apply_threshold(lvb_edge_handle h, const uint8_t* img, int width, int height, int channels, uint8_t* edges, double threshold);
+int lvb_edge_apply(lvb_edge_handle h, const uint8_t* img, int width, int height, int channels, uint8_t* confidence);
+int lvb_edge_get_gradient_map(lvb_edge_handle h, uint8_t* out);
+uint64_t lvb_edge_flood_sweeps(lvb_edge_handle h);
+
 #ifdef __cplusplus
 }
 #endif

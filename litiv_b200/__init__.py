@@ -3,5 +3,5 @@ LBSP descriptors + SuBSENSE / LOBSTER / PAWCS apply(), behind the reference's IB
 from .api import (ALGO_LOBSTER, ALGO_PAWCS, ALGO_SUBSENSE, LBSP, BinClassif, DeviceBatch, BackgroundSubtractorLOBSTER,  # noqa: F401
                   BackgroundSubtractorPAWCS, BackgroundSubtractorSuBSENSE, BackgroundSubtractorViBe_1ch, BackgroundSubtractorViBe_3ch,
                   BackgroundSubtractorPBAS_1ch, BackgroundSubtractorPBAS_3ch, LitivError, Params, apply_batch, default_params, device_count,
-                  kernel_launch_count, lbsp_gradient, lib, lib_path, mask_op, pinned_empty,
+                  kernel_launch_count, lbsp_gradient, EdgeDetectorLBSP, lib, lib_path, mask_op, pinned_empty,
                   MASK_DILATE, MASK_ERODE, MASK_MEDIAN, MASK_HOLES)

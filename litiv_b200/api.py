@@ -31,6 +31,8 @@ EXPORTS = [
     "lvb_pbas_create", "lvb_pbas_destroy", "lvb_pbas_initialize", "lvb_pbas_apply", "lvb_pbas_apply_device", "lvb_pbas_sync",
     "lvb_pbas_get_background_image", "lvb_pbas_state", "lvb_pbas_set_collect_stats", "lvb_pbas_get_stats", "lvb_pbas_set_profile",
     "lvb_pbas_get_profile", "lvb_pbas_stream", "lvb_lbsp_gradient",
+    "lvb_edge_create", "lvb_edge_destroy", "lvb_edge_default_threshold", "lvb_edge_apply_threshold", "lvb_edge_apply",
+    "lvb_edge_get_gradient_map", "lvb_edge_flood_sweeps",
 ]
 
 
@@ -89,6 +91,14 @@ def lib():
         L.lvb_lbsp_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_int]
         L.lvb_default_params.argtypes = [C.c_int, C.c_void_p]
         L.lvb_lbsp_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.lvb_edge_create.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p]
+        L.lvb_edge_destroy.argtypes = [C.c_void_p]
+        L.lvb_edge_default_threshold.restype = C.c_double
+        L.lvb_edge_apply_threshold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double]
+        L.lvb_edge_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.lvb_edge_get_gradient_map.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_edge_flood_sweeps.argtypes = [C.c_void_p]
+        L.lvb_edge_flood_sweeps.restype = C.c_uint64
         L.lvb_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_get_profile_feedback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -608,6 +618,57 @@ def lbsp_gradient(img, device=0):
     out = np.empty((h, w, 4), np.uint8)
     _chk(lib().lvb_lbsp_gradient(img.ctypes.data, w, h, 1 if img.ndim == 2 else img.shape[2], out.ctypes.data, device))
     return out
+
+
+class EdgeDetectorLBSP:
+    """EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83): apply_threshold(img, thr) -> 0 / 255 edge mask,
+    apply(img) -> confidence map (16 per threshold that marks the pixel). Keeps its maps between calls like the reference object."""
+
+    def __init__(self, nLevels=3, dHystLowThrshFactor=0.5, device=0):
+        self._h = C.c_void_p()
+        _chk(lib().lvb_edge_create(int(nLevels), float(dHystLowThrshFactor), device, C.byref(self._h)))
+        self._shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.lvb_edge_destroy(self._h)
+            self._h = None
+
+    def getDefaultThreshold(self):
+        return lib().lvb_edge_default_threshold()
+
+    @staticmethod
+    def _img(img):
+        img = np.ascontiguousarray(img)
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0 or (img.ndim == 3 and img.shape[2] not in (1, 3)):
+            raise LitivError("input image must be non-empty and continuous, 8UC1 or 8UC3")
+        return img, (1 if img.ndim == 2 else img.shape[2])
+
+    def apply_threshold(self, img, dDetThreshold=0.5):
+        img, c = self._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().lvb_edge_apply_threshold(self._h, img.ctypes.data, w, h, c, out.ctypes.data, float(dDetThreshold)))
+        self._shape = (h, w)
+        return out
+
+    def apply(self, img):
+        img, c = self._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().lvb_edge_apply(self._h, img.ctypes.data, w, h, c, out.ctypes.data))
+        self._shape = (h, w)
+        return out
+
+    def gradient_map(self):
+        if self._shape is None:
+            raise LitivError("no pass has run yet")
+        out = np.empty(self._shape + (4,), np.uint8)
+        _chk(lib().lvb_edge_get_gradient_map(self._h, out.ctypes.data))
+        return out
+
+    def flood_sweeps(self):
+        return int(lib().lvb_edge_flood_sweeps(self._h))
 
 
 class LBSP:

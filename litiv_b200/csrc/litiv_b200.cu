@@ -1733,3 +1733,4 @@ int lvb_binclassif_metrics(const uint64_t c[6], double out[8]) {
 
 #include "vibe_host.cuh"
 #include "pbas_host.cuh"
+#include "edge_host.cuh"

@@ -1,0 +1,77 @@
+"""The order-free restatement the edge-detector kernels use (litiv_b200/csrc/edge_px.cuh: per-level maps instead of one shared map,
+suppression as a pure function of the maps, hysteresis as relaxation sweeps) against the sequential oracle (oracle/lvo_edge_lbsp.hpp),
+on the CPU: tests/edge_emul.cpp compiles the kernels' own per-pixel bodies with g++ and drives them with plain loops. What this does
+NOT cover is the launch code (grids, indexing, the shared-memory flood): that is tests/test_zz_gpu_edge.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from litiv_b200.synth import SynthSequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("edge_emul") / "edge_emul.so")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", cuda_inc, "-o", so, os.path.join(HERE, "edge_emul.cpp")])
+    L = C.CDLL(so)
+    L.emul_create.restype = C.c_void_p
+    L.emul_create.argtypes = [C.c_int, C.c_double]
+    L.emul_destroy.argtypes = [C.c_void_p]
+    L.emul_apply_threshold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double]
+    L.emul_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.emul_gradient_map.argtypes = [C.c_void_p, C.c_void_p]
+    return L
+
+
+def _frame(seq, t, ch):
+    f = np.ascontiguousarray(seq.frame(t))
+    return np.ascontiguousarray(f[..., 0]) if ch == 1 and f.ndim == 3 else f
+
+
+@pytest.mark.parametrize("size", [(96, 72), (97, 73), (96, 73), (97, 72), (43, 41)])
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("levels", [1, 2, 3])
+def test_kernel_bodies_equal_the_sequential_oracle(oracle, emul, size, ch, levels):
+    w, h = size
+    seq = SynthSequence(w, h, ch, seed=w + h + ch)
+    o, e = oracle.EdgeDetectorLBSPOracle(levels=levels), emul.emul_create(levels, 0.5)
+    try:
+        for t, thr in [(3, 0.5), (5, 0.25), (7, 0.75), (9, 0.0), (11, 0.9), (12, -1.0)]:   # one object, a sequence of calls (the maps persist)
+            f = _frame(seq, t, ch)
+            want = o.apply_threshold(f, thr)
+            got, grad = np.empty((h, w), np.uint8), np.empty((h, w, 4), np.uint8)
+            emul.emul_apply_threshold(e, f.ctypes.data, w, h, ch, got.ctypes.data, thr)
+            emul.emul_gradient_map(e, grad.ctypes.data)
+            assert np.array_equal(grad, o.gradient_map(f.shape)), (t, thr)
+            assert np.array_equal(got, want), (t, thr, int((got != want).sum()))
+        f = _frame(seq, 14, ch)
+        got = np.empty((h, w), np.uint8)
+        emul.emul_apply(e, f.ctypes.data, w, h, ch, got.ctypes.data)
+        want = o.apply(f)
+        assert np.array_equal(got, want) and want.any()
+    finally:
+        emul.emul_destroy(e)
+
+
+def test_blocky_noise_with_many_edges(oracle, emul):
+    rng = np.random.default_rng(5)
+    for (w, h), ch, levels in [((64, 49), 3, 3), ((65, 48), 1, 2), ((51, 51), 3, 1)]:
+        o, e = oracle.EdgeDetectorLBSPOracle(levels=levels), emul.emul_create(levels, 0.5)
+        for thr in (0.5, 0.2, 0.05, 0.8, 0.0):
+            base = rng.integers(0, 256, (h // 4 + 2, w // 4 + 2, ch), dtype=np.uint8)
+            f = np.kron(base, np.ones((4, 4, 1), np.uint8))[:h, :w]
+            f = np.ascontiguousarray((f.astype(int) + rng.integers(-8, 9, f.shape)).clip(0, 255).astype(np.uint8))
+            f = np.ascontiguousarray(f[..., 0]) if ch == 1 else f
+            want, got = o.apply_threshold(f, thr), np.empty((h, w), np.uint8)
+            emul.emul_apply_threshold(e, f.ctypes.data, w, h, ch, got.ctypes.data, thr)
+            assert np.array_equal(got, want) and want.any()
+            # gradient rows H-2, H-1 lie in the LBSP border (magnitude 0, never a maximum): mask rows H-4, H-3 are always "no edge", which
+            # walls the two rows the suppression loop never writes off from every seed -- they stay empty whatever the call history
+            assert not want[-4:].any()
+        emul.emul_destroy(e)

@@ -1,0 +1,52 @@
+"""GPU parity of the LBSP edge detector (lvb_edge_*, litiv_b200/csrc/edge.cuh) against the CPU oracle, through the
+C ABI. The file sorts last on purpose: these kernels were written after the round's GPU budget was spent, so they have compiled for
+sm_100a and their per-pixel bodies are checked on the CPU (tests/test_edge_emul_cpu.py), but the launch code has not run on a device
+yet. Until a run on a B200 is on record the cases are marked xfail(strict=False): a pass shows up as XPASS, a failure does not hide
+the verified suites before it. Remove the marker after the first green run."""
+import numpy as np
+import pytest
+
+from litiv_b200.synth import SynthSequence
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="edge-detector launch code not yet run on a GPU (round-1 GPU budget spent before it was written)")]
+
+
+def _frame(seq, t, ch):
+    f = np.ascontiguousarray(seq.frame(t))
+    return np.ascontiguousarray(f[..., 0]) if ch == 1 and f.ndim == 3 else f
+
+
+@pytest.mark.parametrize("size", [(96, 72), (97, 73), (320, 240), (641, 479)])
+@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("levels", [1, 3])
+def test_edge_masks_and_gradient_map_match_oracle(lv, oracle, size, ch, levels):
+    w, h = size
+    seq = SynthSequence(w, h, ch, seed=w + h + ch)
+    o, e = oracle.EdgeDetectorLBSPOracle(levels=levels), lv.EdgeDetectorLBSP(levels)
+    for t, thr in [(3, 0.5), (5, 0.25), (7, 0.75), (9, 0.0), (12, -1.0)]:
+        f = _frame(seq, t, ch)
+        want, got = o.apply_threshold(f, thr), e.apply_threshold(f, thr)
+        assert np.array_equal(e.gradient_map(), o.gradient_map(f.shape)), (t, thr)
+        assert np.array_equal(got, want), (t, thr, int((got != want).sum()))
+    f = _frame(seq, 14, ch)
+    want = o.apply(f)
+    assert np.array_equal(e.apply(f), want) and want.any()
+
+
+def test_edge_1080p_and_size_change(lv, oracle):
+    e, o = lv.EdgeDetectorLBSP(), oracle.EdgeDetectorLBSPOracle()
+    f = SynthSequence(1920, 1080, 3, seed=4).frame(20)
+    assert np.array_equal(e.apply_threshold(f), o.apply_threshold(f))
+    assert e.flood_sweeps() >= 4
+    small = SynthSequence(160, 120, 3, seed=4).frame(20)
+    assert np.array_equal(e.apply_threshold(small, 0.3), oracle.EdgeDetectorLBSPOracle().apply_threshold(small, 0.3))
+
+
+def test_edge_argument_checks(lv):
+    with pytest.raises(lv.LitivError):
+        lv.EdgeDetectorLBSP(0)
+    with pytest.raises(lv.LitivError):
+        lv.EdgeDetectorLBSP(3, 1.0)
+    with pytest.raises(lv.LitivError):
+        lv.EdgeDetectorLBSP(3).apply_threshold(np.zeros((16, 16), np.uint8))   # 16 -> 8 -> 4: smaller than the LBSP patch
