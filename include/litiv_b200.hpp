@@ -291,4 +291,40 @@ private:
     bool m_abs; float m_rel; int m_thr, m_dev; ImageView m_ref;
 };
 
+/// EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83): same constructor defaults and method names; masks are
+/// caller-owned rows*cols bytes. Like the reference object, the detector keeps its maps between calls and is not thread-safe.
+struct EdgeDetectorLBSP {
+    explicit EdgeDetectorLBSP(size_t nLevels = 3, double dHystLowThrshFactor = 0.5, int device = 0) { check(lvb_edge_create((int)nLevels, dHystLowThrshFactor, device, &m_h)); }
+    ~EdgeDetectorLBSP() { lvb_edge_destroy(m_h); }
+    EdgeDetectorLBSP(const EdgeDetectorLBSP&) = delete;
+    EdgeDetectorLBSP& operator=(const EdgeDetectorLBSP&) = delete;
+    double getDefaultThreshold() const { return lvb_edge_default_threshold(); }
+    void apply_threshold(const ImageView& img, uint8_t* oEdgeMask, double dDetThreshold = 8.0 / 16.0) {
+        checkInput(img);
+        check(lvb_edge_apply_threshold(m_h, img.data, img.cols, img.rows, img.channels, oEdgeMask, dDetThreshold));
+    }
+    void apply(const ImageView& img, uint8_t* oEdgeMask) {
+        checkInput(img);
+        check(lvb_edge_apply(m_h, img.data, img.cols, img.rows, img.channels, oEdgeMask));
+    }
+#ifdef LITIV_B200_WITH_OPENCV
+    void apply_threshold(cv::InputArray oInputImage, cv::OutputArray oEdgeMask, double dDetThreshold = 8.0 / 16.0) {
+        const cv::Mat m = oInputImage.getMat();
+        oEdgeMask.create(m.size(), CV_8UC1);
+        apply_threshold(ImageView(m), oEdgeMask.getMat().data, dDetThreshold);
+    }
+    void apply(cv::InputArray oInputImage, cv::OutputArray oEdgeMask) {
+        const cv::Mat m = oInputImage.getMat();
+        oEdgeMask.create(m.size(), CV_8UC1);
+        apply(ImageView(m), oEdgeMask.getMat().data);
+    }
+#endif
+    lvb_edge_handle handle() const { return m_h; }
+private:
+    static void checkInput(const ImageView& img) {
+        if(img.empty() || !img.isContinuous() || (img.channels != 1 && img.channels != 3)) throw Exception("input image must be non-empty and continuous, 8UC1 or 8UC3");
+    }
+    lvb_edge_handle m_h = nullptr;
+};
+
 } // namespace lvb

@@ -281,7 +281,7 @@ int lvo_lbsp_gradient(const uint8_t* img, int w, int h, int c, uint8_t* out) {
     LVO_CATCH
 }
 
-// --- EdgeDetectorLBSP (imgproc/src/EdgeDetectorLBSP.cpp): oracle only so far (SURVEY 8f rank 4 groundwork)
+// --- EdgeDetectorLBSP (imgproc/src/EdgeDetectorLBSP.cpp): the checker of lvb_edge_* 
 int lvo_edge_create(int levels, double hyst_low_factor, void** out) {
     LVO_TRY
     if(levels < 1) throw std::runtime_error("number of pyramid levels must be positive");

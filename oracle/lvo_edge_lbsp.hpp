@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see lvo_common.hpp header).
 // CPU restatement of EdgeDetectorLBSP (reference imgproc/src/EdgeDetectorLBSP.cpp:26-417, imgproc/include/litiv/imgproc/
 // EdgeDetectorLBSP.hpp; compile-time switches as shipped: USE_5x5_NON_MAX_SUPP 1, USE_MIN_GRAD_ORIENT 1, USE_3_AXIS_ORIENT 1; Gaussian
-// sigma 0, i.e. no pre-blur). SURVEY §8f rank 4 groundwork: there is no CUDA counterpart yet, only the per-pixel
+// sigma 0, i.e. no pre-blur). SURVEY §8f rank 4: the checker of lvb_edge_*  and of the per-pixel
 // primitive (lvb_lbsp_gradient). Parity unpinned: the reference has no test or golden vector for the detector.
 //
 // The restatement keeps the reference's OBSERVABLE behaviour, including three things that look unintended:

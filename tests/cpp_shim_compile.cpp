@@ -17,6 +17,12 @@ int main() {
         b.initialize(lvb::ImageView(img.data(), 48, 64, 1)); b.apply(lvb::ImageView(img.data(), 48, 64, 1), mask);
         std::printf("ViBe / PBAS ran on GPU\n");
     } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
+    try {
+        lvb::EdgeDetectorLBSP e;                        // throws without a device
+        std::vector<uint8_t> img(64 * 48 * 3, 7), edges(64 * 48);
+        e.apply_threshold(lvb::ImageView(img.data(), 48, 64, 3), edges.data(), e.getDefaultThreshold());
+        std::printf("EdgeDetectorLBSP ran on GPU\n");
+    } catch(const lvb::Exception& e) { std::printf("lvb::Exception: %s\n", e.what()); }
     lvb::BinClassif bc; bc.nTP = 6; bc.nTN = 80; bc.nFP = 4; bc.nFN = 10;
     const lvb::BinClassifMetrics m(bc);   // host arithmetic only
     std::printf("F-measure %.6f total %llu\n", m.dFMeasure, (unsigned long long)bc.total());
