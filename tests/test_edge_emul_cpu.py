@@ -1,7 +1,7 @@
 """The order-free restatement the edge-detector kernels use (litiv_b200/csrc/edge_px.cuh: per-level maps instead of one shared map,
 suppression as a pure function of the maps, hysteresis as relaxation sweeps) against the sequential oracle (oracle/lvo_edge_lbsp.hpp),
-on the CPU: tests/edge_emul.cpp compiles the kernels' own per-pixel bodies with g++ and drives them with plain loops. What this does
-NOT cover is the launch code (grids, indexing, the shared-memory flood): that is tests/test_zz_gpu_edge.py."""
+on the CPU: tests/edge_emul.cpp compiles the kernels' own per-pixel bodies with g++ and drives them with plain loops. The launch code
+(grids, indexing, the shared-memory flood) is covered by tests/test_gpu_edge.py."""
 import ctypes as C
 import os
 import subprocess

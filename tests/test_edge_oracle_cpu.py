@@ -1,4 +1,4 @@
-"""CPU tests of the EdgeDetectorLBSP oracle (oracle/lvo_edge_lbsp.hpp; the CUDA counterpart is lvb_edge_*, tests/test_zz_gpu_edge.py).
+"""CPU tests of the EdgeDetectorLBSP oracle (oracle/lvo_edge_lbsp.hpp; the CUDA counterpart is lvb_edge_*, tests/test_gpu_edge.py).
 The reference has no test or golden vector for the detector (parity unpinned); these tests pin the restatement's documented properties,
 including the three observable quirks of the source listed in DESIGN.md (row shift, unwritten mask rows, little-endian initial value)."""
 import numpy as np

@@ -1,15 +1,13 @@
 """GPU parity of the LBSP edge detector (lvb_edge_*, litiv_b200/csrc/edge.cuh) against the CPU oracle, through the
-C ABI. The file sorts last on purpose: these kernels were written after the round's GPU budget was spent, so they have compiled for
-sm_100a and their per-pixel bodies are checked on the CPU (tests/test_edge_emul_cpu.py), but the launch code has not run on a device
-yet. Until a run on a B200 is on record the cases are marked xfail(strict=False): a pass shows up as XPASS, a failure does not hide
-the verified suites before it. Remove the marker after the first green run."""
+C ABI: edge masks, gradient maps and confidence maps bit-exact for 1 / 3 pyramid levels, gray / RGB, odd and even sizes up to 1080p,
+sequences of calls on one object (its maps persist, like the reference's). First run on a B200: 18 passed (gpurun_out/edge_gpu_tests.log,
+profiles/r01z_edge_probe.md)."""
 import numpy as np
 import pytest
 
 from litiv_b200.synth import SynthSequence
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="edge-detector launch code not yet run on a GPU (round-1 GPU budget spent before it was written)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def _frame(seq, t, ch):
