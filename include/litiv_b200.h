@@ -202,6 +202,9 @@ int lvb_edge_apply_threshold(lvb_edge_handle h, const uint8_t* img, int width, i
 int lvb_edge_apply(lvb_edge_handle h, const uint8_t* img, int width, int height, int channels, uint8_t* confidence);
 int lvb_edge_get_gradient_map(lvb_edge_handle h, uint8_t* out);
 uint64_t lvb_edge_flood_sweeps(lvb_edge_handle h);
+/* device-resident variant (frame already in HBM, row pitch d_step; d_edges_or_null: W*H device bytes) and the detector's CUDA stream */
+int lvb_edge_apply_threshold_device(lvb_edge_handle h, const uint8_t* d_img, int width, int height, int channels, size_t d_step, uint8_t* d_edges_or_null, double threshold);
+void* lvb_edge_stream(lvb_edge_handle h);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ EXPORTS = [
     "lvb_pbas_get_background_image", "lvb_pbas_state", "lvb_pbas_set_collect_stats", "lvb_pbas_get_stats", "lvb_pbas_set_profile",
     "lvb_pbas_get_profile", "lvb_pbas_stream", "lvb_lbsp_gradient",
     "lvb_edge_create", "lvb_edge_destroy", "lvb_edge_default_threshold", "lvb_edge_apply_threshold", "lvb_edge_apply",
-    "lvb_edge_get_gradient_map", "lvb_edge_flood_sweeps",
+    "lvb_edge_get_gradient_map", "lvb_edge_flood_sweeps", "lvb_edge_apply_threshold_device", "lvb_edge_stream",
 ]
 
 
@@ -99,6 +99,9 @@ def lib():
         L.lvb_edge_get_gradient_map.argtypes = [C.c_void_p, C.c_void_p]
         L.lvb_edge_flood_sweeps.argtypes = [C.c_void_p]
         L.lvb_edge_flood_sweeps.restype = C.c_uint64
+        L.lvb_edge_apply_threshold_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_double]
+        L.lvb_edge_stream.argtypes = [C.c_void_p]
+        L.lvb_edge_stream.restype = C.c_void_p
         L.lvb_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_get_profile_feedback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -669,6 +672,15 @@ class EdgeDetectorLBSP:
 
     def flood_sweeps(self):
         return int(lib().lvb_edge_flood_sweeps(self._h))
+
+    def apply_threshold_device(self, d_img_ptr, w, h, channels, d_step, d_edges_ptr=None, dDetThreshold=0.5):
+        """frame already in device memory (raw pointers, row pitch d_step bytes); returns when the mask is complete"""
+        _chk(lib().lvb_edge_apply_threshold_device(self._h, d_img_ptr, w, h, channels, d_step, d_edges_ptr, float(dDetThreshold)))
+        self._shape = (h, w)
+
+    @property
+    def stream(self):
+        return lib().lvb_edge_stream(self._h)
 
 
 class LBSP:

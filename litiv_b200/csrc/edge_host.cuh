@@ -30,7 +30,7 @@ struct lvb_edge_context {
 
 namespace {
 
-void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C) {
+void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, size_t src_step = 0, cudaMemcpyKind kind = cudaMemcpyHostToDevice) {
     REQUIRE(src && (C == 1 || C == 3), "input image must be non-empty and continuous, 8UC1 or 8UC3");   // EdgeDetectorLBSP.cpp:392-393
     std::vector<int> Wl(1, W), Hl(1, H);
     for(int l = 1; l < c->levels; ++l) { Wl.push_back((Wl.back() + 1) / 2); Hl.push_back((Hl.back() + 1) / 2); }
@@ -52,7 +52,7 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C) 
         c->flag = dalloc<int>(c->stream, 1);
     }
     cudaStream_t st = c->stream;
-    CK(cudaMemcpy2DAsync(c->img[0], c->pitch[0], src, (size_t)W * C, (size_t)W * C, H, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(c->img[0], c->pitch[0], src, src_step ? src_step : (size_t)W * C, (size_t)W * C, H, kind, st));
     const dim3 b(32, 8);
     for(int l = 0; l + 1 < c->levels; ++l) {   // apply_internal_lookup: the pyramid
         const dim3 g((Wl[l + 1] * C + 31) / 32, (Hl[l + 1] + 7) / 8);
@@ -167,5 +167,23 @@ int lvb_edge_get_gradient_map(lvb_edge_handle h, uint8_t* out) {
 }
 
 uint64_t lvb_edge_flood_sweeps(lvb_edge_handle h) { return h ? h->flood_sweeps : 0; }
+
+/* the same pass on a frame that already lives in device memory (row pitch d_step bytes); d_edges_or_null: W*H device bytes. The call
+ * returns when the result is complete (the hysteresis loop reads a convergence flag back). Written at the end of round 1 and NOT yet
+ * run on a device: tools/bench_edge.py is its first user. */
+int lvb_edge_apply_threshold_device(lvb_edge_handle h, const uint8_t* d_img, int W, int H, int C, size_t d_step, uint8_t* d_edges_or_null, double threshold) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null argument");
+    REQUIRE(d_step >= (size_t)W * C, "row pitch smaller than a row");
+    if(threshold < 0 || threshold > 1) threshold = lvb_edge_default_threshold();
+    h->flood_sweeps = 0;
+    edge_prepare(h, d_img, W, H, C, d_step, cudaMemcpyDeviceToDevice);
+    edge_pass(h, (unsigned)(uint8_t)(threshold * 16), 0);
+    if(d_edges_or_null) CK(cudaMemcpyAsync(d_edges_or_null, h->out, (size_t)W * H, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    LVB_CATCH
+}
+void* lvb_edge_stream(lvb_edge_handle h) { return h ? (void*)h->stream : nullptr; }
+
 
 } // extern "C"
