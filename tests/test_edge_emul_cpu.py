@@ -75,3 +75,24 @@ def test_blocky_noise_with_many_edges(oracle, emul):
             # walls the two rows the suppression loop never writes off from every seed -- they stay empty whatever the call history
             assert not want[-4:].any()
         emul.emul_destroy(e)
+
+
+def test_random_small_images_levels_and_hysteresis_factors(oracle, emul):
+    """edge cases of the domain: the smallest legal sizes per level count (5, 9, 17, 33 px), four levels, hysteresis factors near 0 and 1,
+    every threshold of the 0..16 scale, random content (many short edges, seeds next to image borders)"""
+    rng = np.random.default_rng(11)
+    cases = [((5, 5), 1), ((6, 5), 1), ((9, 9), 2), ((10, 9), 2), ((17, 17), 3), ((18, 19), 3), ((33, 35), 4), ((40, 33), 4), ((31, 47), 2)]
+    for (w, h), levels in cases:
+        for ch in (1, 3):
+            for hyst in (0.5, 0.05, 0.95):
+                o, e = oracle.EdgeDetectorLBSPOracle(levels=levels, hyst_low_factor=hyst), emul.emul_create(levels, hyst)
+                for k in range(17):
+                    f = rng.integers(0, 256, (h, w, ch), dtype=np.uint8)
+                    f[h // 3:, w // 2:] //= 4                                   # one large-scale structure besides the noise
+                    f = np.ascontiguousarray(f[..., 0]) if ch == 1 else np.ascontiguousarray(f)
+                    want, got = o.apply_threshold(f, k / 16.0), np.empty((h, w), np.uint8)
+                    emul.emul_apply_threshold(e, f.ctypes.data, w, h, ch, got.ctypes.data, k / 16.0)
+                    assert np.array_equal(got, want), (w, h, levels, ch, hyst, k)
+                emul.emul_destroy(e)
+    with pytest.raises(RuntimeError):
+        oracle.EdgeDetectorLBSPOracle(levels=3).apply_threshold(np.zeros((16, 16), np.uint8))   # 16 -> 8 -> 4 < the 5x5 patch
