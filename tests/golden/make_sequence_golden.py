@@ -78,6 +78,43 @@ def run_cases():
     return res
 
 
+def oracle_factories():
+    from oracle import oracle as O
+    return {"subsense": lambda ch: O.Oracle(O.ALGO_SUBSENSE, mode=O.MODE_SNAPSHOT, seed=3),
+            "lobster": lambda ch: O.Oracle(O.ALGO_LOBSTER, mode=O.MODE_SNAPSHOT, seed=3),
+            "pawcs": lambda ch: O.Oracle(O.ALGO_PAWCS, mode=O.MODE_SNAPSHOT, seed=3),
+            "vibe": lambda ch: O.ViBeOracle(ch, mode=O.MODE_SNAPSHOT, seed=3),
+            "pbas": lambda ch: O.PBASOracle(ch, mode=O.MODE_SNAPSHOT, seed=3),
+            "edge": lambda: O.EdgeDetectorLBSPOracle(), "lbsp_gradient": O.lbsp_gradient}
+
+
+def run_mask_cases(make):
+    """the protocol of run_cases() for ANY implementation with the reference's method names (make: kind -> factory, see
+    oracle_factories): name -> (SHA-256 of all masks, last mask, SHA-256 of the LBSP gradient map for the edge cases, else None).
+    tests/test_gpu_parity.py::test_gpu_reproduces_the_committed_sequence_fixtures runs it with the CUDA classes."""
+    res = {}
+    for name, kind, ch, lr_boot, lr in [("subsense_3ch", "subsense", 3, 1.0, 0.0), ("subsense_1ch", "subsense", 1, 1.0, 0.0), ("lobster_1ch", "lobster", 1, 16.0, 16.0),
+                                        ("lobster_3ch", "lobster", 3, 16.0, 16.0), ("pawcs_3ch", "pawcs", 3, 1.0, 0.0)]:
+        a, fr = make[kind](ch), frames(ch, 100 + ch)
+        a.initialize(fr[0])
+        masks = [a.apply(f, lr_boot if t <= 5 else lr).copy() for t, f in enumerate(fr[1:], start=1)]
+        res[name] = (sha(*masks), masks[-1], None)
+    for ch in (1, 3):
+        fr = frames(ch, 100 + ch)
+        v = make["vibe"](ch)
+        v.initialize(fr[0])
+        masks = [v.apply(f, 16.0).copy() for f in fr[1:]]
+        res[f"vibe_{ch}ch"] = (sha(*masks), masks[-1], None)
+        p = make["pbas"](ch)
+        p.initialize(fr[0])
+        masks = [p.apply(f).copy() for f in fr[1:]]
+        res[f"pbas_{ch}ch"] = (sha(*masks), masks[-1], None)
+        e = make["edge"]()
+        edges = [e.apply_threshold(fr[5], t / 16.0).copy() for t in (4, 8, 12)] + [make["edge"]().apply(fr[5])]
+        res[f"edge_lbsp_{ch}ch"] = (sha(*edges), edges[1], sha(make["lbsp_gradient"](fr[5])))
+    return res
+
+
 if __name__ == "__main__":
     res = run_cases()
     out = {}
