@@ -39,7 +39,7 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
     if(W != c->W || H != c->H || C != c->C) {
         CK(cudaStreamSynchronize(c->stream));
         c->free_all();
-        c->W = W; c->H = H; c->C = C; c->Wl = Wl; c->Hl = Hl;
+        c->Wl = Wl; c->Hl = Hl;
         c->tmap.resize(c->levels); c->use_tma.assign(c->levels, 0);
         for(int l = 0; l < c->levels; ++l) {
             c->pitch.push_back(((size_t)Wl[l] * C + 127) / 128 * 128);
@@ -50,6 +50,7 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
         c->mask = dalloc<uint8_t>(c->stream, (size_t)W * H);   // zero = "may belong to an edge", the fresh vector of the reference
         c->out = dalloc<uint8_t>(c->stream, (size_t)W * H);
         c->flag = dalloc<int>(c->stream, 1);
+        c->W = W; c->H = H; c->C = C;   // last: a failed allocation leaves W == 0, so the next call starts over instead of using half a set of maps
     }
     cudaStream_t st = c->stream;
     CK(cudaMemcpy2DAsync(c->img[0], c->pitch[0], src, src_step ? src_step : (size_t)W * C, (size_t)W * C, H, kind, st));
