@@ -53,6 +53,10 @@ def test_no_cpu_fallback_without_device():
         lv.LBSP(20).compute2(np.zeros((16, 16), np.uint8))
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.mask_op(lv.MASK_DILATE, np.zeros((16, 16), np.uint8), 1)
+    with pytest.raises(lv.LitivError, match="no CPU fallback"):
+        lv.EdgeDetectorLBSP()
+    with pytest.raises(lv.LitivError, match="no CPU fallback"):
+        lv.lbsp_gradient(np.zeros((16, 16), np.uint8))
 
 
 def test_product_package_never_imports_oracle():
