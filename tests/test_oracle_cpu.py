@@ -210,3 +210,27 @@ def test_lbsp_gradient_known_answers(oracle):
     rgb = np.stack([flat, step, flat], axis=2)
     assert np.array_equal(O.lbsp_gradient(rgb)[4, 4], O.lbsp_gradient(step)[4, 4])
     assert not O.lbsp_gradient(rgb)[:2].any() and not O.lbsp_gradient(rgb)[:, -2:].any()   # 2-px border: zero pattern
+
+
+def test_cdist_l1dist_full_known_answer_lists_of_the_reference(oracle):
+    """every uchar-applicable known answer of modules/utils/test/math.cpp: cdist<2> (:782-795, the same list again for std::array at
+    :799-812), the cdist range / self-distance properties of :764-781 on random arrays for 2, 3 and 4 channels, and the L1dist<3> array
+    cases of :349-353 / :357-361"""
+    L = oracle.lib()
+    L.lvo_cdist2.restype = L.lvo_cdist3.restype = L.lvo_cdist4.restype = C.c_uint64
+    u8 = lambda *v: np.array(v, np.uint8).ctypes.data_as(C.c_void_p)
+    cd2 = [((0, 0), (0, 0), 0), ((1, 0), (0, 0), 1), ((255, 0), (0, 0), 255), ((0, 0), (1, 0), 0), ((0, 0), (255, 0), 0), ((1, 0), (0, 1), 1),
+           ((0, 1), (1, 0), 1), ((255, 0), (0, 255), 255), ((0, 255), (255, 0), 255), ((255, 0), (0, 1), 255), ((1, 1), (1, 1), 0),
+           ((255, 255), (255, 255), 0), ((1, 1), (255, 255), 0), ((255, 255), (1, 1), 0)]
+    for a, b, want in cd2:
+        assert L.lvo_cdist2(u8(*a), u8(*b)) == want, (a, b)
+    assert L.lvo_l1dist3_u8(u8(1, 2, 3), u8(0, 0, 0)) == 6
+    rng = np.random.default_rng(17)
+    for hi in (2, 256):                                               # genarray(0,1) and genarray(0,255)
+        v = rng.integers(0, hi, 20004, dtype=np.uint8)
+        for i in range(0, 10000, 7):
+            a, b = v[i:i + 4].copy(), v[i + 10000:i + 10004].copy()
+            for c, f in ((2, L.lvo_cdist2), (3, L.lvo_cdist3), (4, L.lvo_cdist4)):
+                d = f(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+                assert 0 <= d <= (hi - 1) * c, (a, b, c, d)
+                assert f(a.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p)) == 0
