@@ -234,3 +234,19 @@ def test_cdist_l1dist_full_known_answer_lists_of_the_reference(oracle):
                 d = f(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
                 assert 0 <= d <= (hi - 1) * c, (a, b, c, d)
                 assert f(a.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p)) == 0
+
+
+def test_clamp_and_neighbour_known_answers_of_the_reference(oracle):
+    """modules/utils/test/opencv.cpp:369-388 (clampImageCoords at 640x480 with borders 0 and 5, reached through the neighbour walk) and
+    :415-429 (10 000 draws of the 8-neighbour pattern stay within +-1 of the origin and never return it)"""
+    L = oracle.lib()
+    xy = (C.c_int * 2)()
+    L.lvo_neighbor_pos(0, 5, 0, 0, 0, 640, 480, xy); assert (xy[0], xy[1]) == (0, 0)          # (-1,-1) clamped, border 0
+    L.lvo_neighbor_pos(0, 5, 0, 0, 5, 640, 480, xy); assert (xy[0], xy[1]) == (5, 5)          # border 5
+    L.lvo_neighbor_pos(0, 2, 639, 479, 0, 640, 480, xy); assert (xy[0], xy[1]) == (639, 479)  # (+1,+1) from the last pixel
+    L.lvo_neighbor_pos(0, 2, 639, 479, 5, 640, 480, xy); assert (xy[0], xy[1]) == (634, 474)
+    L.lvo_neighbor_pos(0, 4, 320, 240, 5, 640, 480, xy); assert (xy[0], xy[1]) == (321, 240)  # interior: untouched by the clamp
+    rng = np.random.default_rng(23)
+    for r in rng.integers(0, 2 ** 31 - 1, 10000):
+        L.lvo_neighbor_pos(0, int(r), 320, 240, 0, 640, 480, xy)
+        assert 319 <= xy[0] <= 321 and 239 <= xy[1] <= 241 and (xy[0], xy[1]) != (320, 240)
