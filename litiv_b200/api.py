@@ -702,11 +702,22 @@ class LBSP:
     def windowSize(self):
         return (5, 5)
 
-    def borderSize(self):
+    def borderSize(self, nDim=0):
+        """LBSP::borderSize (features2d/src/LBSP.cpp: only dimensions 0 and 1 exist; features2d/test/lbsp.cpp:13-14)"""
+        if nDim not in (0, 1):
+            raise LitivError("border size is only defined for 2 dimensions")
         return 2
 
     def descriptorSize(self):
         return 2
+
+    def descriptorType(self):
+        """CV_16U == CV_16UC1 (features2d/test/lbsp.cpp:16-17)"""
+        return 2
+
+    def defaultNorm(self):
+        """cv::NORM_HAMMING (features2d/test/lbsp.cpp:18)"""
+        return 6
 
     def compute2(self, img):
         img = np.ascontiguousarray(img)

@@ -116,3 +116,20 @@ def test_stream_sharding_gloo_world2(tmp_path):
                           "--master-port", "29533", str(script)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_lbsp_api_invariants_of_the_reference():
+    """modules/features2d/test/lbsp.cpp:4-19 (regression_constr, regression_default_params) on the Python mirror; no device involved"""
+    import litiv_b200 as lv
+    with pytest.raises(lv.LitivError):
+        lv.LBSP(-0.5)
+    e = lv.LBSP(20)
+    assert e.windowSize() == (5, 5) and e.windowSize()[0] // 2 == e.borderSize() == e.borderSize(1)
+    with pytest.raises(lv.LitivError):
+        e.borderSize(2)
+    assert e.descriptorSize() == 2
+    try:
+        import cv2
+        assert e.descriptorType() == cv2.CV_16U == cv2.CV_16UC1 and e.defaultNorm() == cv2.NORM_HAMMING
+    except ImportError:
+        assert e.descriptorType() == 2 and e.defaultNorm() == 6
