@@ -278,8 +278,12 @@ struct LBSP {
         if(fRelThreshold < 0) throw Exception("relative LBSP threshold must be non-negative");
     }
     static constexpr int PATCH_SIZE = 5, DESC_SIZE = 2, DESC_SIZE_BITS = 16;
-    int borderSize() const { return PATCH_SIZE / 2; }
+    /// only two dimensions exist (features2d/test/lbsp.cpp:13-14: borderSize(2) throws)
+    int borderSize(int nDim = 0) const { if(nDim < 0 || nDim > 1) throw Exception("border size is only defined for 2 dimensions"); return PATCH_SIZE / 2; }
+    int windowSize() const { return PATCH_SIZE; }   // square window: width == height == 5
     int descriptorSize() const { return DESC_SIZE; }
+    int descriptorType() const { return 2; }         // CV_16U
+    int defaultNorm() const { return 6; }            // cv::NORM_HAMMING
     void setReference(const ImageView& ref) { m_ref = ref; }
     /// out: rows*cols*channels uint16; the 2-px border is left untouched like the reference's oDesc.create()
     void compute2(const ImageView& img, uint16_t* out) const {

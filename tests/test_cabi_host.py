@@ -86,6 +86,7 @@ def test_cpp_shim_compiles_and_reports_errors(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0
     assert "no CPU fallback" in out.stdout or "ran on GPU" in out.stdout
+    assert "LBSP invariants ok" in out.stdout, out.stdout
 
 
 SHARD_SCRIPT = r'''
