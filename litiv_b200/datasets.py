@@ -239,3 +239,54 @@ def write_synthetic_cdnet(root, name, width, height, nframes, seed=1, category="
         gt[roi == 0] = 85
         cv2.imwrite(os.path.join(d, "groundtruth", "gt%06d.png" % (t + 1)), gt)
     return d
+
+
+# --- lv::write / lv::read, MatArchive_BINARY (modules/utils/src/opencv.cpp:514-531, 608-625): the archive format of the reference's
+# descriptor dumps (modules/features2d/test/data/test_lbsp.bin is one): int32 cv type, uint64 element size, uint64 element count,
+# int32 dims, int32 size[dims], raw row-major data; little-endian, no padding. Host-side I/O next to the path.
+_CV_DEPTHS = [np.uint8, np.int8, np.uint16, np.int16, np.int32, np.float32, np.float64]   # CV_8U .. CV_64F = 0 .. 6
+
+
+def write_mat_binary(path, arr, channels_last=None):
+    """writes `arr` as the reference's lv::write(path, mat, lv::MatArchive_BINARY) would write the equivalent cv::Mat. A 3-d array whose
+    last axis has at most 4 entries is taken as rows x cols x channels (what cv2 hands out); pass channels_last=False to store a
+    genuinely 3-dimensional single-channel Mat instead."""
+    import struct
+    arr = np.ascontiguousarray(arr)
+    try:
+        depth = [np.dtype(d) for d in _CV_DEPTHS].index(arr.dtype)
+    except ValueError:
+        raise ValueError(f"dtype {arr.dtype} has no cv::Mat depth") from None
+    if channels_last is None:
+        channels_last = arr.ndim == 3 and arr.shape[2] <= 4
+    if arr.ndim < 2:
+        arr = arr.reshape(-1, 1) if arr.ndim == 1 else arr.reshape(1, 1)     # cv::Mat has at least two dimensions
+    cn = arr.shape[-1] if channels_last else 1
+    sizes = arr.shape[:-1] if channels_last else arr.shape
+    if not 1 <= cn <= 512:
+        raise ValueError("cv::Mat supports 1..512 channels")
+    total = int(np.prod(sizes, dtype=np.int64))
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iQQi", depth + ((cn - 1) << 3), arr.dtype.itemsize * cn, total, len(sizes)))
+        f.write(struct.pack("<%di" % len(sizes), *sizes))
+        f.write(arr.tobytes())
+
+
+def read_mat_binary(path):
+    """lv::read(path, lv::MatArchive_BINARY): returns the array (rows x cols [x channels] for 2-d Mats, dims... [x channels] otherwise)"""
+    import struct
+    raw = open(path, "rb").read()
+    if len(raw) < 24:
+        raise ValueError("binary archive read failed")
+    mtype, esz, total, dims = struct.unpack("<iQQi", raw[:24])
+    if dims < 1 or dims > 32 or len(raw) < 24 + 4 * dims:
+        raise ValueError("binary archive read failed")
+    sizes = struct.unpack("<%di" % dims, raw[24:24 + 4 * dims])
+    depth, cn = mtype & 7, (mtype >> 3) + 1
+    if depth >= len(_CV_DEPTHS):
+        raise ValueError("unsupported cv::Mat depth in archive")
+    dt = np.dtype(_CV_DEPTHS[depth])
+    if esz != dt.itemsize * cn or total != int(np.prod(sizes, dtype=np.int64)) or len(raw) < 24 + 4 * dims + esz * total:
+        raise ValueError("binary archive read failed")
+    data = np.frombuffer(raw, dt, count=total * cn, offset=24 + 4 * dims)
+    return data.reshape(tuple(sizes) + ((cn,) if cn > 1 else ())).copy()

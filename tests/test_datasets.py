@@ -84,3 +84,37 @@ def test_analyze_runs_vibe_and_pbas(lv, oracle, tmp_path, name):
         assert np.array_equal(out["masks"][i], m), f"frame {i}"
         want = oracle.binclassif(m, seq.getGT(i), seq.roi, counters=want)
     assert np.array_equal(out["counters"], want)
+
+
+def test_mat_binary_archive_round_trip_and_reference_file(tmp_path):
+    """lv::write / lv::read MatArchive_BINARY (modules/utils/src/opencv.cpp:514-531, 608-625): the round trip of
+    modules/utils/test/opencv.cpp:659-669 for every cv depth, the byte layout of a known header, and -- in the build container, where the
+    reference tree exists -- the reference's own archive modules/features2d/test/data/test_lbsp.bin against the committed fixture"""
+    import struct
+    from litiv_b200.datasets import read_mat_binary, write_mat_binary
+    rng = np.random.default_rng(3)
+    for dt in (np.uint8, np.int8, np.uint16, np.int16, np.int32, np.float32, np.float64):
+        for shape in ((rng.integers(100, 200), rng.integers(100, 200)), (17, 9, 3), (5, 4, 1), (1, 1)):
+            a = (rng.uniform(-200, 200, shape)).astype(dt)
+            p = str(tmp_path / "m.bin")
+            write_mat_binary(p, a)
+            b = read_mat_binary(p)
+            want = a[..., 0] if a.ndim == 3 and a.shape[2] == 1 else a
+            assert b.dtype == a.dtype and np.array_equal(b, want)
+    p = str(tmp_path / "h.bin")
+    write_mat_binary(p, np.arange(65 * 65 * 3, dtype=np.uint16).reshape(65, 65, 3))
+    raw = open(p, "rb").read()
+    assert struct.unpack("<iQQiii", raw[:32]) == (18, 6, 65 * 65, 2, 65, 65) and len(raw) == 32 + 65 * 65 * 6   # CV_16UC3 == 18
+    vol = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    write_mat_binary(p, vol, channels_last=False)                                                              # a 3-d single-channel Mat
+    assert struct.unpack("<iQQi", open(p, "rb").read()[:24]) == (5, 4, 24, 3) and np.array_equal(read_mat_binary(p), vol)
+    with pytest.raises(ValueError):
+        open(p, "wb").write(b"\\x00" * 10)
+        read_mat_binary(p)
+    ref = "/root/reference/modules/features2d/test/data/test_lbsp.bin"
+    if os.path.exists(ref):
+        gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lbsp_golden.npz"))["desc"]
+        got = read_mat_binary(ref)
+        assert got.dtype == np.uint16 and np.array_equal(got, gold)
+        write_mat_binary(p, gold)
+        assert open(p, "rb").read() == open(ref, "rb").read()      # byte-identical to what the reference wrote
