@@ -7,7 +7,9 @@
 // The restatement keeps the reference's OBSERVABLE behaviour, including three things that look unintended:
 //   * the non-maximum-suppression loop classifies gradient row r+2 into mask row r (:263, :270-272), so the output is shifted up by two rows;
 //   * mask rows H and H+1 of the padded map are never written by that loop: they keep what the object's previous call left there
-//     (zero = "may belong to an edge" on a fresh object) and the hysteresis may flood them; they are the source of output rows H-2, H-1;
+//     (zero = "may belong to an edge" on a fresh object) and are the source of output rows H-2, H-1. In practice they stay empty: the
+//     two mask rows above them hold the classes of gradient rows H-2, H-1, which lie in the LBSP border (magnitude 0, never a maximum),
+//     so no seed can reach them (asserted in tests/test_edge_emul_cpu.py);
 //   * the gradient map is initialised with the uint32 (CHAR_MAX<<24)|(CHAR_MAX<<16)|(UCHAR_MAX<<8) (:205), stored little-endian: per pixel
 //     (gradX, gradY, magnitude, pad) = (0, -1, 127, 127), so the min-|.| combination keeps gradX == 0 and |gradY| <= 1 at every scale.
 // Like the reference object, the gradient and mask buffers persist between calls.
