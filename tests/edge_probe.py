@@ -1,4 +1,4 @@
-"""One-shot GPU probe of the edge detector against the oracle (a few sizes, printed mismatch counts); the full suite is tests/test_gpu_edge.py."""
+"""TEST INFRASTRUCTURE (it executes the oracle, so it lives under tests/): one-shot GPU probe of the edge detector against the oracle (a few sizes, printed mismatch counts and wall-clock times); the full suite is tests/test_gpu_edge.py."""
 import os
 import sys
 import time
