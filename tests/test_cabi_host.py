@@ -67,6 +67,10 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(txt), f"{f} references the oracle"
+    imp = re.compile(r"^\s*(import\s+oracle|from\s+oracle)", re.M)   # tools/ may name the oracle in prose, but never import or run it
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            assert not imp.search(open(os.path.join(ROOT, "tools", f)).read()), f"tools/{f} imports the oracle"
 
 
 def test_synth_sequence_is_deterministic():
