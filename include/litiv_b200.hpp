@@ -298,7 +298,11 @@ private:
 /// EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83): same constructor defaults and method names; masks are
 /// caller-owned rows*cols bytes. Like the reference object, the detector keeps its maps between calls and is not thread-safe.
 struct EdgeDetectorLBSP {
-    explicit EdgeDetectorLBSP(size_t nLevels = 3, double dHystLowThrshFactor = 0.5, int device = 0) { check(lvb_edge_create((int)nLevels, dHystLowThrshFactor, device, &m_h)); }
+    /// bNormalizeOutput (EdgeDetectorLBSP.cpp:431-432, default false in the reference) is not supported: normalise the confidence map yourself
+    explicit EdgeDetectorLBSP(size_t nLevels = 3, double dHystLowThrshFactor = 0.5, bool bNormalizeOutput = false, int device = 0) {
+        if(bNormalizeOutput) throw Exception("bNormalizeOutput=true is not supported (min-max normalisation of the confidence map is left to the caller)");
+        check(lvb_edge_create((int)nLevels, dHystLowThrshFactor, device, &m_h));
+    }
     ~EdgeDetectorLBSP() { lvb_edge_destroy(m_h); }
     EdgeDetectorLBSP(const EdgeDetectorLBSP&) = delete;
     EdgeDetectorLBSP& operator=(const EdgeDetectorLBSP&) = delete;

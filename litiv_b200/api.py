@@ -627,8 +627,10 @@ class EdgeDetectorLBSP:
     """EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83): apply_threshold(img, thr) -> 0 / 255 edge mask,
     apply(img) -> confidence map (16 per threshold that marks the pixel). Keeps its maps between calls like the reference object."""
 
-    def __init__(self, nLevels=3, dHystLowThrshFactor=0.5, device=0):
+    def __init__(self, nLevels=3, dHystLowThrshFactor=0.5, bNormalizeOutput=False, device=0):
         self._h = C.c_void_p()
+        if bNormalizeOutput:   # EdgeDetectorLBSP.cpp:431-432 (cv::normalize of the confidence map); the reference's default is false
+            raise LitivError("bNormalizeOutput=true is not supported (min-max normalisation of the confidence map is left to the caller)")
         _chk(lib().lvb_edge_create(int(nLevels), float(dHystLowThrshFactor), device, C.byref(self._h)))
         self._shape = None
 
