@@ -1,8 +1,10 @@
 // litiv_b200 — kernels of the LBSP edge detector (reference imgproc/src/EdgeDetectorLBSP.cpp:47-433). The per-pixel
 // bodies live in edge_px.cuh (shared with the CPU emulation of the tests); the per-level LBSP gradient is lbsp_gradient_kernel of
-// lobster.cuh (TMA-staged tile + 5x5 halo). All maps are HBM-resident per detector object; one pass over a WxH image moves about
-// C (input) + 4/3*(C + 4 + 4) (pyramid, per-level gradient, combined map) + 4*25/.. (suppression window, L1/L2 hits) + 2 (mask) bytes
-// per pixel: the detector is bound by launch latency at CDnet sizes and by HBM at 1080p.
+// lobster.cuh (TMA-staged tile + 5x5 halo). All maps are HBM-resident per detector object. Algorithmic bytes of one apply_threshold
+// call per full-resolution pixel, three levels (sizes 1 + 1/4 + 1/16 = 1.31): image read C and 4-byte map written, re-read and rewritten by
+// the combination (C + 13 per level pixel, + C for writing the two coarser images), the suppression's map read 4 and mask write 1 (its 5x5
+// window is served by L1 / L2), one mask read per flood sweep, mask read + result write 2: about 33 B/px for RGB with four sweeps
+// (tools/bench_edge.py). The detector is launch bound at CDnet sizes (16 launches and one flag read-back per call).
 #pragma once
 #include "edge_px.cuh"
 
