@@ -137,6 +137,7 @@ struct lvb_context {
     std::vector<uint8_t> roi_host;
     size_t orig_roi_count = 0, roi_count = 0;
     int collect_stats = 0, median_k = 9;
+    int sm_count = 148;       // persistent kernels size their grids as sm_count x resident CTAs per SM
     uint64_t stat_frames = 0;
     bool pending = false;
     // two-deep host pipeline (lvb_apply_async): slot k%2 = {device frame, device mask, pinned staging}; uploads on s_in, masks back on s_out
@@ -747,7 +748,9 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         T.avg_samples = c->P.n_samples_for_moving_avgs; T.N = c->P.n_samples; T.dsW = c->dsW; T.dsH = c->dsH; T.seed = c->seed; T.wait_seq = seq;
         cudaEvent_t fb0 = nullptr, fb1 = nullptr;
         if(c->profile) { CK(cudaEventCreate(&fb0)); CK(cudaEventCreate(&fb1)); CK(cudaEventRecord(fb0, st)); }
-        const dim3 fg(c->Wp / 32, (H + FB_H - 1) / FB_H), fb(32, FB_H);
+        // persistent: sm_count x FB_CTAS_PER_SM CTAs walk the 32x8 tiles (one tile each when the frame has fewer tiles than that)
+        const int fb_tiles = (c->Wp / 32) * ((H + FB_H - 1) / FB_H);
+        const dim3 fg((unsigned)std::min(fb_tiles, c->sm_count * FB_CTAS_PER_SM)), fb(32, FB_H);
         if(C == 1) subsense_feedback<1><<<fg, fb, 0, st>>>(A, T); else subsense_feedback<3><<<fg, fb, 0, st>>>(A, T);
         LAUNCHED(); mark(st, "feedback");
         if(c->profile) { CK(cudaEventRecord(fb1, st)); c->prof2_events.push_back(fb0); c->prof2_events.push_back(fb1); }
@@ -1272,6 +1275,19 @@ int lvb_default_params(int algo, lvb_params* out) {
 }
 double lvb_default_learning_rate(int algo) { return algo == LVB_ALGO_LOBSTER ? 16.0 : 0.0; }
 
+/// per-device settings applied before the first instance is created on a device.
+/// L2 fetch granularity: the scan tail, the stochastic sample writes (read-modify-write of a 32-byte sector) and the queued
+/// neighbour writes touch lone 32-byte sectors; the default 64-byte fetch granularity doubles their DRAM traffic.
+static void device_tuning_once(int device) {
+    static std::mutex mu; static std::vector<int> done;
+    std::lock_guard<std::mutex> lk(mu);
+    if(std::find(done.begin(), done.end(), device) != done.end()) return;
+    done.push_back(device);
+    size_t gran = 32;
+    if(const char* e = getenv("LVB_L2_FETCH")) gran = (size_t)atoi(e);
+    if(gran == 32 || gran == 64 || gran == 128) { if(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) (void)cudaGetLastError(); }
+}
+
 int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lvb_handle* out) {
     LVB_TRY
     REQUIRE(out != nullptr, "null output handle");
@@ -1287,8 +1303,10 @@ int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lv
     REQUIRE(ndev > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
     REQUIRE(device >= 0 && device < ndev, "invalid CUDA device id");
     CK(cudaSetDevice(device));
+    device_tuning_once(device);
     lvb_context* c = new lvb_context();
     c->algo = algo; c->device = device; c->seed = seed;
+    if(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count <= 0) { (void)cudaGetLastError(); c->sm_count = 148; }
     static_assert(sizeof(Params) == sizeof(lvb_params), "params mirror out of sync");
     std::memcpy(&c->P, &p, sizeof(p));
     // high priority: while phase B occupies the auxiliary (low-priority) stream the small mask kernels get SM slots first

@@ -289,7 +289,9 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             const uint32_t slot = s_int[threadIdx.y + r][threadIdx.x + k] & 0xFFu;
             const size_t q = (size_t)(y + r - 2) * A.Wp + (x - 2 + k);
             const Col c_ = pcol[q]; const Desc d_ = pdes[q];
+#ifndef LVB_EXP_NO_NB_WRITE
             ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(c_, d_);
+#endif
             if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
             if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
         }
@@ -338,7 +340,9 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     }
     // the fence sits here, ~600 instructions after the stores it covers, so it normally finds them already performed
     if(pending) __threadfence_block();
+#ifndef LVB_EXP_NO_TAIL
     subsense_scan_tail<CH, T7>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
+#endif
     const uint32_t scanned = s;
 
     if(active) {
@@ -464,19 +468,30 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
 #ifndef FEEDBACK_MIN_BLOCKS
 #define FEEDBACK_MIN_BLOCKS 5
 #endif
-#ifndef LVB_FB_H
-#define LVB_FB_H 8
-#endif
-constexpr int FB_H = LVB_FB_H; // tile height (warps per CTA) of the feedback kernel, independent of the scan tile
+constexpr int FB_H = 8;                       // tile height (warps per CTA) of the feedback kernel
+constexpr int FB_CTAS_PER_SM = FEEDBACK_MIN_BLOCKS;
+
+/// one 32x8 tile of per-pixel state staged in shared memory by cp.async, one block per warp row (so a warp only ever reads what
+/// its own lanes copied: the tile loop needs __syncwarp, never __syncthreads)
+template<int CH> struct FbStage {
+    float4 maps[FB_H][64];                    // (T,R,v,Dlast | DminLT,DminST,rawLT,rawST) x 32 px
+    float2 fin[FB_H][32];
+    uint2 hand[FB_H][32];
+    typename Pack<CH>::Col col[FB_H][32];     // this frame's colour / intra descriptors (written by the scan kernel)
+    typename Pack<CH>::Desc desc[FB_H][32];
+    uint32_t words[FB_H][20];                 // roi | blinks | lastfg | - | previous frame's ghost bits: rows y-2..y+2 x words wi-1..wi+1 | -
+};
+
+/// Persistent: a CTA walks 32x8 tiles with stride gridDim.x. The state of tile i+1 is copied global -> shared (cp.async, no
+/// registers held) while tile i is computed, so the ~1 us DRAM round trip that used to open every CTA's life is hidden behind
+/// the previous tile's arithmetic, and the small division / modulo tables are staged once per CTA instead of once per tile.
 template<int CH>
-__global__ void __launch_bounds__(32 * FB_H, FEEDBACK_MIN_BLOCKS * 8 / FB_H)
+__global__ void __launch_bounds__(32 * FB_H, FEEDBACK_MIN_BLOCKS)
 subsense_feedback(const SubArgs A, const TailArgs TA) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
-    constexpr int FB_GHOST_ROWS = FB_H + 2 * HALO;
     __shared__ uint32_t s_cnt[2];                 // writes | warps done
-    __shared__ uint32_t s_ghost[FB_GHOST_ROWS][3];   // previous frame's ghost bits around the tile (rows y0-2.., words wi-1..wi+1)
     __shared__ CtlSlice s_ctl;
     // small read-only tables behind data-dependent indices (T(x), the hand-off distances): staged in shared memory so that the
     // look-ups cost a fixed ~25 cycles instead of an L1 miss in the middle of the dependency chain (L1 is streamed through by
@@ -484,17 +499,43 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     constexpr int NCOL = (CH == 1 ? 255 : 765) + 1, NDES = (CH == 1 ? 16 : 48) + 1;
     __shared__ uint32_t s_magic[257];
     __shared__ float s_divc[NCOL], s_divd[NDES];
+    __shared__ __align__(16) FbStage<CH> s_stage[2];
+    static_assert(sizeof(FbStage<CH>) % 16 == 0, "stage alignment");
 
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * FB_H;
-    const int tid = threadIdx.y * TILE_W + threadIdx.x;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int tid = warp * TILE_W + lane;
+    const int tiles_x = A.Wp / TILE_W, ntiles = tiles_x * ((A.H + FB_H - 1) / FB_H);
+
+    auto prefetch = [&](int tile, FbStage<CH>& S) {
+        const int ty = tile / tiles_x, x0 = (tile - ty * tiles_x) * TILE_W, y = ty * FB_H + warp;
+        if(y < A.H) { // whole 32-px row segments: the planes are Wp (a multiple of 32) wide, padding columns are never used
+            const size_t rowpix = (size_t)y * A.Wp + x0;
+            const char* g_maps = (const char*)(A.maps + rowpix * 2);
+            cp_async16((char*)&S.maps[warp][0] + 16 * lane, g_maps + 16 * lane);
+            cp_async16((char*)&S.maps[warp][0] + 16 * (lane + 32), g_maps + 16 * (lane + 32));
+            if(lane < 16) cp_async16((char*)&S.fin[warp][0] + 16 * lane, (const char*)(A.fin + rowpix) + 16 * lane);
+            else cp_async16((char*)&S.hand[warp][0] + 16 * (lane - 16), (const char*)(A.hand + rowpix) + 16 * (lane - 16));
+            constexpr int NC = 32 * (int)sizeof(Col) / 16, ND = 32 * (int)sizeof(Desc) / 16;
+            static_assert(NC <= 8 && ND <= 16, "row segment chunks");
+            if(lane < NC) cp_async16((char*)&S.col[warp][0] + 16 * lane, (const char*)((const Col*)A.last_color + rowpix) + 16 * lane);
+            else if(lane >= 8 && lane < 8 + ND) cp_async16((char*)&S.desc[warp][0] + 16 * (lane - 8), (const char*)((const Desc*)A.last_desc + rowpix) + 16 * (lane - 8));
+            if(lane < 18) {
+                const int wx = x0 >> 5;
+                const uint32_t* src = A.roi_bits; bool ok = true; int gy = y, gw = wx;
+                if(lane == 1) src = A.blinks_bits; else if(lane == 2) src = A.lastfg_bits;
+                else if(lane >= 3) { src = A.ghost_prev; gy = y - HALO + (lane - 3) / 3; gw = wx - 1 + (lane - 3) % 3; ok = gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW; }
+                cp_async4_zfill(&S.words[warp][lane < 3 ? lane : lane + 1], ok ? src + (size_t)gy * A.WW + gw : src, ok);
+            }
+        }
+    };
+
+    int tile = blockIdx.x;
+    if(tile < ntiles) prefetch(tile, s_stage[0]);
+    cp_async_commit();
     for(int i = tid; i < 257; i += TILE_W * FB_H) s_magic[i] = A.magic[i];
     for(int i = tid; i < NCOL; i += TILE_W * FB_H) s_divc[i] = A.div_color[i];
     if(tid < NDES) s_divd[tid] = A.div_desc[tid];
     if(tid < 2) s_cnt[tid] = 0;
-    if(tid < FB_GHOST_ROWS * 3) {
-        const int gy = y0 - HALO + tid / 3, gw = (x0 >> 5) - 1 + tid % 3;
-        s_ghost[tid / 3][tid % 3] = (gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW) ? A.ghost_prev[gy * A.WW + gw] : 0u;
-    }
     if(tid == 32 * FB_H - 1) {
         const FrameCtl* ctl = A.ctl;
         CtlSlice cs;
@@ -502,161 +543,177 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         cs.frame = ctl->frame_idx; cs.cooldown = ctl->cooldown; cs.use3x3 = ctl->use3x3; cs.pad = 0;
         s_ctl = cs;
     }
-
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool in_img = (x < A.W) && (y < A.H);
-    const int wi = y * A.WW + (x >> 5);
-    const uint32_t lane_bit = 1u << (x & 31);
-    uint32_t w_roi = 0, w_blink = 0, w_lastfg = 0;
-    if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_blink = A.blinks_bits[wi]; w_lastfg = A.lastfg_bits[wi]; }
-    const bool active = in_img && (w_roi & lane_bit);
-    const size_t pix = (size_t)y * A.Wp + x;
-
-    float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
-    float2 fin = make_float2(0, 0);
-    uint2 hand = make_uint2(0, 0);
-    Col cur_pack = Col(); Desc intra_pack = Desc();
-    if(in_img) { // not `active`: that would chain these loads behind the ROI word's round trip (the planes cover every pixel)
-        m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1];
-        fin = A.fin[pix];
-        hand = A.hand[pix];
-        cur_pack = ((const Col*)A.last_color)[pix];   // this frame's colour / intra descriptor (written by the scan kernel)
-        intra_pack = ((const Desc*)A.last_desc)[pix];
-    }
-    __syncthreads();
-
-    bool unstable_new = false, ghost_new = false, has_intent = false;
-    uint32_t writes = 0;
-    uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
+    __syncthreads(); // the only CTA-wide barrier: tables + FrameCtl slice
     const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
     const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
+    const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
+    const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
+    uint32_t writes_acc = 0;
 
-    if(active) {
-        const uint32_t minSum = hand.x & 0xFFFFu, minDesc = hand.x >> 16, good = hand.y & 0xFFFFu, lastL1 = (hand.y >> 16) & 0xFFu, lastHd = hand.y >> 24;
-        const bool is_fg = good < REQ;
-        const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
-        const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
-        float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
-        const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
-        if(A.ema_frame) { // final-segmentation EMAs of the previous frame (:553-554): cv::addWeighted accumulates in double, rounds once
-            const float eLT = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples));
-            const float eST = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples / 4u));
-            const double v = lastfg ? 255.0 : 0.0;
-            fin.x = (float)__dadd_rn(__dmul_rn((double)fin.x, (double)__fsub_rn(1.0f, eLT)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eLT)));
-            fin.y = (float)__dadd_rn(__dmul_rn((double)fin.y, (double)__fsub_rn(1.0f, eST)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eST)));
-            A.fin[pix] = fin;
-        }
-        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
+    for(int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const FbStage<CH>& S = s_stage[it & 1];
+        const int next = tile + (int)gridDim.x;
+        if(next < ntiles) prefetch(next, s_stage[(it + 1) & 1]);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed has landed: this tile's state is in shared memory
+        __syncwarp();        // ... and visible to the other lanes of the warp (row segments are copied cooperatively)
 
-        // D_last (:254-255 / :396-397)
-        // i / colorRange and i / descRange come from 3 KB of host-tabulated IEEE quotients instead of four __fdiv_rn sequences per pixel
-        const float normLast = __fmul_rn(__fadd_rn(s_divc[min(lastL1, (uint32_t)NCOL - 1u)], s_divd[min(lastHd, (uint32_t)NDES - 1u)]), 0.5f); // x/2 == x*0.5 exactly
-        Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
+        const int ty = tile / tiles_x, x0 = (tile - ty * tiles_x) * TILE_W;
+        const int x = x0 + lane, y = ty * FB_H + warp;
+        const bool in_img = (x < A.W) && (y < A.H);
+        const int wi = y * A.WW + (x >> 5);
+        const uint32_t lane_bit = 1u << lane;
+        uint32_t w_roi = 0, w_blink = 0, w_lastfg = 0;
+        if(y < A.H) { w_roi = S.words[warp][0]; w_blink = S.words[warp][1]; w_lastfg = S.words[warp][2]; }
+        const bool active = in_img && (w_roi & lane_bit);
+        const size_t pix = (size_t)y * A.Wp + x;
 
-        const uint32_t pixid = (uint32_t)(y * A.W + x);
-        const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
-        const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
-        const float baseMin = __fmul_rn(__fadd_rn(s_divc[min(minSum, colorRange)], s_divd[min(minDesc, descRange)]), 0.5f);
-        if(is_fg) { // foreground (:256-269 / :398-413)
-            const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
-            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
-            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(normMin, aST));
-            rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT);
-            rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
-            if(cooldown && (rnd.x % 2u) == 0) {
-                const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
-                ++writes;
+        bool unstable_new = false, ghost_new = false, has_intent = false;
+        uint32_t writes = 0;
+        uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
+
+        if(active) {
+            const float4 m0 = S.maps[warp][2 * lane], m1 = S.maps[warp][2 * lane + 1];
+            float2 fin = S.fin[warp][lane];
+            const uint2 hand = S.hand[warp][lane];
+            const Col cur_pack = S.col[warp][lane];
+            const Desc intra_pack = S.desc[warp][lane];
+            const uint32_t minSum = hand.x & 0xFFFFu, minDesc = hand.x >> 16, good = hand.y & 0xFFFFu, lastL1 = (hand.y >> 16) & 0xFFu, lastHd = hand.y >> 24;
+            const bool is_fg = good < REQ;
+            float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
+            const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
+            if(A.ema_frame) { // final-segmentation EMAs of the previous frame (:553-554): cv::addWeighted accumulates in double, rounds once
+                const float eLT = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples));
+                const float eST = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples / 4u));
+                const double v = lastfg ? 255.0 : 0.0;
+                fin.x = (float)__dadd_rn(__dmul_rn((double)fin.x, (double)__fsub_rn(1.0f, eLT)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eLT)));
+                fin.y = (float)__dadd_rn(__dmul_rn((double)fin.y, (double)__fsub_rn(1.0f, eST)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eST)));
+                A.fin[pix] = fin;
             }
-        } else { // background (:270-301 / :414-450)
-            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(baseMin, aLT));
-            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
-            rawLT = __fmul_rn(rawLT, oneLT);
-            rawST = __fmul_rn(rawST, oneST);
-            // x % LR, x % (LR/2+1): T(x) <= 256, so the magic numbers come from a 1 KB table (a fixed rate has them in the arguments)
-            const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
-            const uint32_t LR2 = LR / 2u + 1u;
-            const bool tab = !A.lr_fixed && LR <= 256u;
-            const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
-            const bool fastm = A.lr_fixed || tab;
-            if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
-                const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
-                ++writes;
-            }
-            const bool cur3 = use3x3 && !unstable_new;
-            int dx, dy;
-            neighbor_offset(cur3, rnd.z, dx, dy);
-            const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
-            const bool nb_ghost = (s_ghost[ny - y0 + HALO][(nx >> 5) - (x0 >> 5) + 1] >> (nx & 31)) & 1u;
-            const uint32_t n_rand = rnd.w;
-            const uint32_t nbLR = cur3 ? LR : LR2;
-            if((fastm ? fast_mod(n_rand, nbLR, cur3 ? mg : mg2) : n_rand % nbLR) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
-                const uint32_t slot = fast_mod(fast_div(rnd.y, N, A.n_magic), N, A.n_magic); // (d1 / N) % N: one Philox block serves the whole pixel
-                // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
-                intent = (((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot;
-                has_intent = true;
-            }
-        }
-        // T(x) (:302-311 / :451-460)
-        const float dmin = fminf(DminLT, DminST), dmax = fmaxf(DminLT, DminST);
-        if(lastfg || (dmin < 0.1f && is_fg)) {
-            if(T < t_upper) T = __fadd_rn(T, __fdiv_rn(0.5f, __fmul_rn(dmax, V)));
-        } else if(T > t_lower)
-            T = __fsub_rn(T, __fdiv_rn(__fmul_rn(0.25f, V), dmax));
-        if(T < t_lower) T = t_lower; else if(T > t_upper) T = t_upper;
-        // v(x) (:312-318 / :461-467)
-        if(dmax > 0.1f && blink) V = __fadd_rn(V, 1.0f);
-        else if(V > 0.1f) {
-            V = __fsub_rn(V, lastfg ? (0.1f / 4) : unstable_new ? (0.1f / 2) : 0.1f);
-            if(V < 0.1f) V = 0.1f;
-        }
-        // R(x) (:319-325 / :468-474); std::pow(float,int) evaluates in double (Q7): the square is exact in fp64
-        const double rr = (double)__fadd_rn(1.0f, __fmul_rn(dmin, 2.0f));
-        if((double)R < __dmul_rn(rr, rr)) R = __fadd_rn(R, __fmul_rn(0.01f, __fsub_rn(V, 0.1f)));
-        else {
-            R = __fsub_rn(R, __fdiv_rn(0.01f, V));
-            if(R < 1.0f) R = 1.0f;
-        }
-        ghost_new = (rawST > 0.995f) && (Dlast < 0.010f);
+            unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
 
-        A.maps[pix * 2] = make_float4(T, R, V, Dlast);
-        A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
-        A.r_plane[pix] = R;
+            // D_last (:254-255 / :396-397)
+            // i / colorRange and i / descRange come from 3 KB of host-tabulated IEEE quotients instead of four __fdiv_rn sequences per pixel
+            const float normLast = __fmul_rn(__fadd_rn(s_divc[min(lastL1, (uint32_t)NCOL - 1u)], s_divd[min(lastHd, (uint32_t)NDES - 1u)]), 0.5f); // x/2 == x*0.5 exactly
+            Dlast = __fadd_rn(__fmul_rn(Dlast, __fsub_rn(1.0f, aST)), __fmul_rn(normLast, aST));
+
+            const uint32_t pixid = (uint32_t)(y * A.W + x);
+#ifndef LVB_EXP_NO_PHILOX
+            const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_APPLY);
+#else
+            const uint4 rnd = make_uint4((pixid * 2654435761u + frame) >> 1, (pixid * 40503u + frame * 7u) >> 1, (pixid ^ (frame * 97u)) >> 1, (pixid * 2246822519u + frame) >> 1);
+#endif
+            const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
+            const float baseMin = __fmul_rn(__fadd_rn(s_divc[min(minSum, colorRange)], s_divd[min(minDesc, descRange)]), 0.5f);
+            if(is_fg) { // foreground (:256-269 / :398-413)
+                const float normMin = fminf(1.0f, __fadd_rn(baseMin, __fdiv_rn((float)(REQ - good), (float)REQ)));
+                DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(normMin, aLT));
+                DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(normMin, aST));
+                rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT);
+                rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
+                if(cooldown && (rnd.x % 2u) == 0) {
+                    const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
+#ifndef LVB_EXP_NO_OWN_WRITE
+                    ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
+#endif
+                    ++writes;
+                }
+            } else { // background (:270-301 / :414-450)
+                DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(baseMin, aLT));
+                DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
+                rawLT = __fmul_rn(rawLT, oneLT);
+                rawST = __fmul_rn(rawST, oneST);
+                // x % LR, x % (LR/2+1): T(x) <= 256, so the magic numbers come from a 1 KB table (a fixed rate has them in the arguments)
+                const uint32_t LR = A.lr_fixed ? A.lr_fixed : (uint32_t)ceilf(T);
+                const uint32_t LR2 = LR / 2u + 1u;
+                const bool tab = !A.lr_fixed && LR <= 256u;
+                const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
+                const bool fastm = A.lr_fixed || tab;
+                if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
+                    const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
+#ifndef LVB_EXP_NO_OWN_WRITE
+                    ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
+#else
+                    if(slot == 77u) A.r_plane[pix] = 0.f;
+#endif
+                    ++writes;
+                }
+                const bool cur3 = use3x3 && !unstable_new;
+                int dx, dy;
+                neighbor_offset(cur3, rnd.z, dx, dy);
+                const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
+                const bool nb_ghost = (S.words[warp][4 + (ny - y + HALO) * 3 + (nx >> 5) - (x0 >> 5) + 1] >> (nx & 31)) & 1u;
+                const uint32_t n_rand = rnd.w;
+                const uint32_t nbLR = cur3 ? LR : LR2;
+                if((fastm ? fast_mod(n_rand, nbLR, cur3 ? mg : mg2) : n_rand % nbLR) == 0 || (nb_ghost && (n_rand % (uint32_t)t_lower) == 0)) {
+                    const uint32_t slot = fast_mod(fast_div(rnd.y, N, A.n_magic), N, A.n_magic); // (d1 / N) % N: one Philox block serves the whole pixel
+                    // intent = (clamped relative target offset index) << 8 | slot ; offset index = (ty-y+2)*5 + (tx-x+2)
+                    intent = (((ny - y + 2) * 5 + (nx - x + 2)) << 8) | slot;
+                    has_intent = true;
+                }
+            }
+            // T(x) (:302-311 / :451-460)
+            const float dmin = fminf(DminLT, DminST), dmax = fmaxf(DminLT, DminST);
+            if(lastfg || (dmin < 0.1f && is_fg)) {
+                if(T < t_upper) T = __fadd_rn(T, __fdiv_rn(0.5f, __fmul_rn(dmax, V)));
+            } else if(T > t_lower)
+                T = __fsub_rn(T, __fdiv_rn(__fmul_rn(0.25f, V), dmax));
+            if(T < t_lower) T = t_lower; else if(T > t_upper) T = t_upper;
+            // v(x) (:312-318 / :461-467)
+            if(dmax > 0.1f && blink) V = __fadd_rn(V, 1.0f);
+            else if(V > 0.1f) {
+                V = __fsub_rn(V, lastfg ? (0.1f / 4) : unstable_new ? (0.1f / 2) : 0.1f);
+                if(V < 0.1f) V = 0.1f;
+            }
+            // R(x) (:319-325 / :468-474); std::pow(float,int) evaluates in double (Q7): the square is exact in fp64
+            const double rr = (double)__fadd_rn(1.0f, __fmul_rn(dmin, 2.0f));
+            if((double)R < __dmul_rn(rr, rr)) R = __fadd_rn(R, __fmul_rn(0.01f, __fsub_rn(V, 0.1f)));
+            else {
+                R = __fsub_rn(R, __fdiv_rn(0.01f, V));
+                if(R < 1.0f) R = 1.0f;
+            }
+            ghost_new = (rawST > 0.995f) && (Dlast < 0.010f);
+
+            A.maps[pix * 2] = make_float4(T, R, V, Dlast);
+            A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
+            A.r_plane[pix] = R;
+        }
+
+        // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
+        const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
+        const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
+        if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame: phase B scans the plane without a has-intent mask
+        if(y < A.H && (x >> 5) < A.WW && lane == 0) { A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; }
+        if(A.collect_stats) writes_acc += writes + (has_intent ? 1u : 0u);
+        __syncwarp(); // every lane is done with this stage before the warp refills it (two iterations from now)
     }
-
-    // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
-    const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
-    const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
-    if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame: phase B scans the plane without a has-intent mask
-    if(y < A.H && (x >> 5) < A.WW && threadIdx.x == 0) { A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; }
+    cp_async_wait<0>();
     if(A.collect_stats) {
-        uint32_t wr = writes + (has_intent ? 1u : 0u);
 #pragma unroll
-        for(int o = 16; o > 0; o >>= 1) wr += __shfl_xor_sync(0xFFFFFFFFu, wr, o);
-        if(threadIdx.x == 0) atomicAdd(&s_cnt[0], wr);
+        for(int o = 16; o > 0; o >>= 1) writes_acc += __shfl_xor_sync(0xFFFFFFFFu, writes_acc, o);
+        if(lane == 0) atomicAdd(&s_cnt[0], writes_acc);
     }
     // frame tail: the last warp of the CTA to get here takes the CTA's ticket, and the last CTA of the grid runs the tail with
     // that one warp (every other CTA has read its FrameCtl slice long before it took its ticket). No CTA-wide barrier: warps
     // retire as they finish instead of idling through the ticket's round trip.
     uint32_t last_warp = 0;
-    if(threadIdx.x == 0) {
+    if(lane == 0) {
         __threadfence_block();
         last_warp = atomicAdd(&s_cnt[1], 1u) == (uint32_t)FB_H - 1u;
     }
     last_warp = __shfl_sync(0xFFFFFFFFu, last_warp, 0);
     if(!last_warp) return;
     uint32_t last_cta = 0;
-    if(threadIdx.x == 0) {
+    if(lane == 0) {
         const uint32_t wr = atomicAdd(&s_cnt[0], 0u);
         if(A.collect_stats && wr) atomicAdd(&A.ctl->stat_writes, (unsigned long long)wr);
         // no device-wide fence: the tail only reads counters accumulated with atomics (by this grid) or by earlier kernels,
         // and what it rewrites in FrameCtl was read by every CTA before that CTA's first barrier
-        last_cta = atomicAdd(&A.ctl->blocks_done, 1u) == gridDim.x * gridDim.y - 1u;
+        last_cta = atomicAdd(&A.ctl->blocks_done, 1u) == gridDim.x - 1u;
     }
     last_cta = __shfl_sync(0xFFFFFFFFu, last_cta, 0);
     if(last_cta) {
-        subsense_tail_warp(TA, (int)threadIdx.x);
+        subsense_tail_warp(TA, lane);
     }
 }
 

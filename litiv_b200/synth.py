@@ -6,7 +6,9 @@ import numpy as np
 
 
 class SynthSequence:
-    def __init__(self, width, height, channels=3, seed=1, n_objects=5, noise=3):
+    def __init__(self, width, height, channels=3, seed=1, n_objects=5, noise=3, fg_area=None):
+        """fg_area: None keeps the historical object sizes (half-size 3-7 % of min(W,H): ~2 % of a 16:9 frame is foreground);
+        a fraction (SURVEY 8(d) specifies 5-10 %) sizes the objects so that together they cover about that share of the frame."""
         self.w, self.h, self.c, self.seed, self.noise = width, height, channels, seed, noise
         rng = np.random.RandomState(seed)
         yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
@@ -26,6 +28,10 @@ class SynthSequence:
         for _ in range(n_objects):
             kind = rng.randint(0, 2)
             size = rng.uniform(0.03, 0.07) * min(width, height)
+            if fg_area is not None:
+                # rectangle of half-size s covers (2s+1)^2, disc of radius s covers pi s^2; shares of 0.6-1.4 x the mean per object
+                a = fg_area * width * height / n_objects * (size / (0.05 * min(width, height)))
+                size = (np.sqrt(a) - 1) / 2 if kind == 0 else np.sqrt(a / np.pi)
             pos = rng.uniform([0, 0], [width, height])
             vel = rng.uniform(1.0, 3.0, 2) * rng.choice([-1, 1], 2)
             col = rng.randint(0, 256, channels).astype(np.float32)
