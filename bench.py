@@ -261,6 +261,7 @@ def main():
     torch.cuda.synchronize()
     pa_ms, pa_n = sub.get_profile()
     fb_ms, fb_n = sub.get_profile_feedback()
+    tp_ms, tp_n = sub.get_profile_tail()
     st = sub.stats()
     sub.set_profile(False)
     sub.set_collect_stats(False)
@@ -328,6 +329,7 @@ def main():
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r01h_scan_feedback_ncu.md)", "peak_source": peak_src, "avg_launch_ms": pa_avg_ms,
                          "launches_timed": int(pa_n), "alg_bytes_per_px": b_scan, "scan_depth": sbar, "sample_writes_per_px": u,
                          "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / (ms_all / args.steps),
+                         "tail_passes_avg_ms": tp_ms / max(tp_n, 1),
                          "second_kernel": {"kernel": "subsense_feedback<3>", "avg_launch_ms": fb_avg_ms, "alg_bytes_per_px": b_fb,
                                            "achieved": fb_achieved, "frac": fb_achieved / hbm_peak, "kernel_share_of_step": fb_avg_ms / (ms_all / args.steps)},
                          "frame": {"alg_bytes_per_px": b_alg, "achieved": roi_px * b_alg / (ms_all / args.steps * 1e-3) / 1e9,

@@ -129,6 +129,8 @@ int lvb_set_profile(lvb_handle h, int enabled);
 int lvb_get_profile(lvb_handle h, double* ms_total, uint64_t* launches);
 /* same for the second-largest kernel of a SuBSENSE frame (the feedback kernel); zero launches for the other algorithms */
 int lvb_get_profile_feedback(lvb_handle h, double* ms_total, uint64_t* launches);
+/* same for the two tail passes of the SuBSENSE scan (pixels needing more than two samples), timed together */
+int lvb_get_profile_tail(lvb_handle h, double* ms_total, uint64_t* launches);
 /* page-locked host buffers: frames / masks living in them are copied straight to / from the device (no staging copy) */
 int lvb_host_alloc(void** out, size_t bytes);
 int lvb_host_free(void* p);

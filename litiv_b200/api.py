@@ -23,7 +23,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback", "lvb_get_profile_tail",
     "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics", "lvb_apply_batch_device",
     "lvb_vibe_create", "lvb_vibe_destroy", "lvb_vibe_initialize", "lvb_vibe_apply", "lvb_vibe_apply_device", "lvb_vibe_sync",
     "lvb_vibe_get_background_image", "lvb_vibe_model", "lvb_vibe_set_collect_stats", "lvb_vibe_get_stats", "lvb_vibe_set_profile",
@@ -105,6 +105,7 @@ def lib():
         L.lvb_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.lvb_get_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_get_profile_feedback.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lvb_get_profile_tail.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.lvb_host_alloc.argtypes = [C.c_void_p, C.c_size_t]
         L.lvb_host_free.argtypes = [C.c_void_p]
         L.lvb_mask_op.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -315,6 +316,11 @@ class _BackgroundSubtractor:
     def get_profile_feedback(self):
         ms, n = C.c_double(), C.c_uint64()
         _chk(lib().lvb_get_profile_feedback(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def get_profile_tail(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _chk(lib().lvb_get_profile_tail(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
     def set_collect_stats(self, enabled):

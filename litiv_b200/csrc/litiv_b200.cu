@@ -126,6 +126,8 @@ struct lvb_context {
     uint32_t sub_frame = 1;             // host mirror of FrameCtl::frame_idx (SuBSENSE; the final-mask EMA factors derive from it)
     uint32_t chain_seq = 0;             // frames enqueued (sequence number written to FrameCtl::chain_done by the mask stream)
     ushort* intents = nullptr;
+    uint8_t* own_slot = nullptr;        // SuBSENSE: queued own-sample writes (slot per pixel, 0xFF none), applied by the next scan
+    uint32_t* wl_ctx = nullptr; uint32_t* wl2_idx = nullptr; uint32_t wl_cap = 0;   // SuBSENSE scan work-list (subsense.cuh: WlCtx)
     uint8_t* lut = nullptr;
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
     uint32_t* magic = nullptr; // [257] floor(2^32 / n)
@@ -149,6 +151,7 @@ struct lvb_context {
     uint64_t n_submitted = 0, n_collected = 0;
     bool profile = false; std::vector<cudaEvent_t> prof_events; double prof_ms = 0; uint64_t prof_n = 0;
     std::vector<cudaEvent_t> prof2_events; double prof2_ms = 0; uint64_t prof2_n = 0; // second-largest kernel (SuBSENSE feedback)
+    std::vector<cudaEvent_t> prof3_events; double prof3_ms = 0; uint64_t prof3_n = 0; // SuBSENSE scan tail passes
     bool direct_mask = false;
     // LVB_TRACE=1 (debugging aid): an event after every kernel of the main stream; lvb_get_profile prints the per-segment averages
     bool trace_on = getenv("LVB_TRACE") != nullptr; std::vector<std::pair<const char*, cudaEvent_t>> trace;
@@ -166,10 +169,11 @@ struct lvb_context {
     size_t rec_bytes() const { return C == 1 ? 4 : 16; }
 
     void free_all() {
-        void* ptrs[] = {eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {own_slot, wl_ctx, wl2_idx, eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
+        own_slot = nullptr; wl_ctx = nullptr; wl2_idx = nullptr; wl_cap = 0;
         eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; fin_pending = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
@@ -236,7 +240,7 @@ void flush_pending(lvb_context* c) {
     if(c->nb_seq == 0) return;
     PhaseBArgs B{};
     B.W = c->W; B.H = c->H; B.Wp = c->Wp; B.WW = c->WW; B.CH = c->C; B.plane = c->plane;
-    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents;
+    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents; B.own_slot = c->own_slot;
     B.ctl = c->ctl; B.pending_seq = c->nb_seq;
     const dim3 tg(c->Wp / 32, (c->H + 7) / 8), tb(32, 8);
     if(c->C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->stream>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->stream>>>(B);
@@ -253,6 +257,7 @@ void launch_refresh(lvb_context* c) {
     R.lut = c->lut; R.ctl = c->ctl; R.seed = c->seed; R.recompute_desc = c->algo == LVB_ALGO_LOBSTER;
     const dim3 tgd = tile_grid(c);
     R.intents = c->intents; R.pending_seq = c->algo == LVB_ALGO_SUBSENSE ? c->nb_seq : 0u;
+    R.own_slot = c->algo == LVB_ALGO_SUBSENSE ? c->own_slot : nullptr;
     const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, 148 * 8);
     if(c->C == 1) refresh_model_kernel<1><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     else refresh_model_kernel<3><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
@@ -556,6 +561,11 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         c->maps = dalloc<float4>(c->stream, c->plane * 2);
         c->fin = dalloc<float2>(c->stream, c->plane);
         c->hand = dalloc<uint2>(c->stream, c->plane);
+        c->own_slot = dalloc<uint8_t>(c->stream, c->plane, false);
+        CK(cudaMemsetAsync(c->own_slot, 0xFF, c->plane, c->stream));
+        c->wl_cap = (uint32_t)c->plane;   // every pixel may be undecided after two samples (first frames after a scene change)
+        c->wl_ctx = dalloc<uint32_t>(c->stream, (size_t)(C == 1 ? WlCtx<1>::FIELDS : WlCtx<3>::FIELDS) * c->wl_cap, false);
+        c->wl2_idx = dalloc<uint32_t>(c->stream, c->wl_cap, false);
         c->last_color_alt = dalloc<uint8_t>(c->stream, c->plane * c->col_bytes());
         c->last_desc_alt = dalloc<uint8_t>(c->stream, c->plane * c->desc_bytes());
         c->dsLT = dalloc<float>(c->stream, (size_t)c->dsW * c->dsH * C);
@@ -678,6 +688,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.prev_color = c->last_color; A.prev_desc = c->last_desc; A.pending_seq = sub ? c->nb_seq : 0u; A.roi_bits = c->roi_bits; A.raw_bits = sub ? c->raw_alt : c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
     A.intents = c->intents; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
+    A.wl_ctx = c->wl_ctx; A.wl_cap = c->wl_cap; A.wl2_idx = c->wl2_idx; A.own_slot = c->own_slot;
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
@@ -715,6 +726,26 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         mark(st, "scan");
+        {   // tail passes over the work-list of pixels the scan kernel left undecided (entry per lane; grid sized to the SM count)
+            TailPassArgs TP{};
+            TP.Wp = c->Wp; TP.WW = c->WW; TP.N = c->P.n_samples; TP.REQ = c->P.n_required; TP.plane = c->plane; TP.bg = c->bg;
+            TP.wl_ctx = c->wl_ctx; TP.wl_cap = c->wl_cap; TP.hand = c->hand; TP.raw_bits = c->raw_alt; TP.lut = c->lut; TP.ctl = c->ctl;
+            TP.collect_stats = c->collect_stats;
+            cudaEvent_t tp0 = nullptr, tp1 = nullptr;
+            if(c->profile) { CK(cudaEventCreate(&tp0)); CK(cudaEventCreate(&tp1)); CK(cudaEventRecord(tp0, st)); }
+            const int npx = W * H;
+            const int g1 = std::max(1, std::min(c->sm_count * 8, (npx / 4 + 127) / 128)), g2 = std::max(1, std::min(c->sm_count * 8, (npx / 16 + 127) / 128));
+            TP.in_idx = nullptr; TP.in_count = &c->ctl->wl_count; TP.out_idx = c->wl2_idx; TP.out_count = &c->ctl->wl2_count; TP.s_limit = TAIL_PASS1_LIMIT;
+            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 3><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 3><<<g1, 128, 0, st>>>(TP); }
+            else { if(C == 1) subsense_tail_pass<1, false, 3><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 3><<<g1, 128, 0, st>>>(TP); }
+            LAUNCHED();
+            TP.in_idx = c->wl2_idx; TP.in_count = &c->ctl->wl2_count; TP.out_idx = nullptr; TP.out_count = nullptr; TP.s_limit = 0xFFFFFFFFu;
+            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 4><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 4><<<g2, 128, 0, st>>>(TP); }
+            else { if(C == 1) subsense_tail_pass<1, false, 4><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 4><<<g2, 128, 0, st>>>(TP); }
+            LAUNCHED();
+            if(c->profile) { CK(cudaEventRecord(tp1, st)); c->prof3_events.push_back(tp0); c->prof3_events.push_back(tp1); }
+            mark(st, "scan tail passes");
+        }
         CK(cudaEventRecord(c->ev_scan, st));
         // ---- mask stream: chain of frame k, reading raw(k), writing blinks(k) / lastfg(k) / fin(k) into the spare buffers
         CK(cudaStreamWaitEvent(sp, c->ev_scan, 0));
@@ -1566,6 +1597,21 @@ int lvb_get_profile_feedback(lvb_handle h, double* ms_total, uint64_t* launches)
     h->prof2_events.clear();
     *ms_total = h->prof2_ms; *launches = h->prof2_n;
     h->prof2_ms = 0; h->prof2_n = 0;
+    LVB_CATCH
+}
+int lvb_get_profile_tail(lvb_handle h, double* ms_total, uint64_t* launches) {
+    LVB_TRY
+    REQUIRE(h && ms_total && launches, "null argument");
+    CK(cudaSetDevice(h->device));
+    sync_streams(h);
+    for(size_t i = 0; i + 1 < h->prof3_events.size(); i += 2) {
+        float ms = 0; CK(cudaEventElapsedTime(&ms, h->prof3_events[i], h->prof3_events[i + 1]));
+        h->prof3_ms += ms; ++h->prof3_n;
+        cudaEventDestroy(h->prof3_events[i]); cudaEventDestroy(h->prof3_events[i + 1]);
+    }
+    h->prof3_events.clear();
+    *ms_total = h->prof3_ms; *launches = h->prof3_n;
+    h->prof3_ms = 0; h->prof3_n = 0;
     LVB_CATCH
 }
 int lvb_host_alloc(void** out, size_t bytes) {

@@ -43,7 +43,9 @@ struct FrameCtl {
     uint32_t refresh_blocks;   // ticket counter of the conditional refresh kernel (its last CTA retires the request)
     uint32_t chain_done;       // sequence number of the last frame whose final mask (lastfg) is complete; written on the mask stream
     uint32_t nb_applied_seq;   // sequence number of the last frame whose queued neighbour writes are already in the model
-    uint32_t pad[4];
+    uint32_t wl_count;         // SuBSENSE scan work-list: pixels still undecided after the two prefetched samples (reset by the frame tail)
+    uint32_t wl2_count;        // ... and those still undecided after the first tail pass
+    uint32_t pad[2];
 };
 
 // One background sample = one naturally aligned record (colour + descriptors): 16 bytes for 3 channels, 4 bytes for 1.
@@ -93,6 +95,10 @@ struct SubArgs {
     const float* div_color;    // [colorRange + 1] i / colorRange  (IEEE quotients tabulated on the host: the feedback step
     const float* div_desc;     // [descRange + 1]  i / descRange    normalises four small integers per pixel)
     uint32_t lr_magic, lr2_magic; // magic numbers of lr_fixed and lr_fixed/2+1 when the rate is fixed
+    // scan work-list (see subsense.cuh): contexts of the pixels the scan kernel could not decide with the two prefetched samples,
+    // structure-of-arrays [WlCtx<CH>::FIELDS][wl_cap] u32, and the indices of the entries that survive the first tail pass
+    uint32_t* wl_ctx; uint32_t wl_cap; uint32_t* wl2_idx;
+    uchar* own_slot;           // [H][Wp] own-sample write queued by the feedback kernel (slot, 0xFF: none); applied by the next scan
 };
 
 } // namespace lvb

@@ -100,92 +100,20 @@ __device__ __forceinline__ bool subsense_test_sample(const Lookup16 (&L)[CH], co
     return ok;
 }
 
-/// per-pixel scan context parked in shared memory by the pixels that are still undecided after the first two samples
-/// (words): 4*CH neighbour words | packed colour | intra descriptors (CH==3: 2 words) | thrC | thrD | pixel offset
-template<int CH> struct ScanCtx {
-    static constexpr int CUR = 4 * CH, INTRA = CUR + 1, THRC = INTRA + (CH == 3 ? 2 : 1), THRD = THRC + 1, PIX = THRD + 1;
-    static constexpr int WORDS = (PIX + 1 + 3) / 4 * 4;
+/// Work-list entry of a pixel that is still undecided after the two prefetched samples. The scan kernel appends it (warp-aggregated
+/// atomic on FrameCtl::wl_count) and moves on: the rest of the pixel's scan runs in subsense_tail_pass, spread over the whole chip,
+/// instead of holding the 32x8 tile's CTA through a chain of dependent DRAM round trips. Only ~17 % of the pixels get here (3 or more
+/// samples), ~2-6 % are foreground and scan all N. Structure of arrays [FIELDS][wl_cap] u32: consecutive entries are written by
+/// consecutive lanes of one warp.
+template<int CH> struct WlCtx {
+    static constexpr int LOOK = 0;                      // 4*CH words: the 16 LBSP neighbours of every channel
+    static constexpr int CUR = 4 * CH;                  // packed colour
+    static constexpr int INTRA = CUR + 1;               // intra descriptors (CH==3: 2 words)
+    static constexpr int THRC = INTRA + (CH == 3 ? 2 : 1), THRD = THRC + 1, PIX = THRD + 1;
+    static constexpr int STATE = PIX + 1;               // minSum (10 bits) | minDesc << 10 (6) | good << 16 (8) | scanned << 24 (8)
+    static constexpr int FIELDS = STATE + 1;
 };
-
-/// Tail of the scan, executed by the whole warp. Only ~15 % of the pixels need a third sample and ~0.2 % (foreground) need all
-/// N, so a per-lane loop runs at 1-5 active lanes for up to N-2 dependent DRAM round trips. Instead the k undecided pixels
-/// of the warp share its 32 lanes: each round tests 32/k' samples (k' = k rounded up to a power of two) of every undecided
-/// pixel at once, then ballots + a segmented min-reduction reproduce the sequential "stop at the REQ-th match" rule exactly.
-template<int CH, bool T7>
-__device__ __forceinline__ void subsense_scan_tail(const SubArgs& A, uint32_t* wctx, uchar* worder, const uchar* s_lut, bool undecided,
-                                                   uint32_t N, uint32_t REQ, uint32_t& good, uint32_t& s, uint32_t& minDesc, uint32_t& minSum) {
-    typedef typename Pack<CH>::Col Col;
-    typedef typename Pack<CH>::Desc Desc;
-    typedef typename Pack<CH>::Rec Rec;
-    typedef ScanCtx<CH> X;
-    const uint32_t FULL = 0xFFFFFFFFu, lane = threadIdx.x;
-    __syncwarp(); // the parked contexts (wctx) are read by other lanes
-    uint32_t m = __ballot_sync(FULL, undecided);
-    while(m) {
-        const uint32_t k = __popc(m);
-        const uint32_t lg = k <= 1u ? 0u : 32u - (uint32_t)__clz(k - 1u); // log2(k')
-        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-        if(undecided) worder[rank] = (uchar)lane;
-        __syncwarp();
-        const uint32_t slot = lane & ((1u << lg) - 1u), off = lane >> lg;
-        const bool has = slot < k;
-        const uint32_t src = has ? worder[slot] : 0u;
-        const uint32_t st = __shfl_sync(FULL, s | (good << 16), src);
-        const uint32_t s_src = st & 0xFFFFu, good_src = st >> 16;
-        const uint32_t smp = s_src + off;
-        const bool valid = has && smp < N;
-        bool ok = false;
-        uint32_t td = 0xFFFFFFFFu, ts = 0xFFFFFFFFu;
-        if(valid) {
-            const uint32_t* ctx = wctx + src * X::WORDS;
-            const size_t at = (size_t)smp * A.plane + ctx[X::PIX];
-            // .cg: these samples may have just been rewritten by the lane that owns the pixel (pending neighbour writes)
-            const Rec rec = __ldcg((const Rec*)A.bg + at);
-            const Col bc = rec_col(rec); const Desc bd = rec_desc(rec);
-            Lookup16 L[CH];
-            uint32_t cur[CH], intra[CH];
-#pragma unroll
-            for(int c = 0; c < CH; ++c) {
-                const uint4 v = *(const uint4*)(ctx + 4 * c);
-                L[c].w[0] = v.x; L[c].w[1] = v.y; L[c].w[2] = v.z; L[c].w[3] = v.w;
-                cur[c] = (ctx[X::CUR] >> (8 * c)) & 0xFFu;
-            }
-            if constexpr (CH == 1) intra[0] = ctx[X::INTRA];
-            else { intra[0] = ctx[X::INTRA] & 0xFFFFu; intra[1] = ctx[X::INTRA] >> 16; intra[2] = ctx[X::INTRA + 1]; }
-            uint32_t d_, s_;
-            ok = subsense_test_sample<CH, T7>(L, cur, intra, bc, bd, ctx[X::THRC], ctx[X::THRD], s_lut, d_, s_);
-            if(ok) { td = d_; ts = s_; }
-        }
-        const uint32_t okmask = __ballot_sync(FULL, ok);
-        const uint32_t gpat = lg == 0u ? 0xFFFFFFFFu : lg == 1u ? 0x55555555u : lg == 2u ? 0x11111111u : lg == 3u ? 0x01010101u : lg == 4u ? 0x00010001u : 1u;
-        const uint32_t gok = okmask & (gpat << slot);   // matches of my pixel, ordered by sample
-        const uint32_t need = REQ - good_src;           // >= 1 for every undecided pixel
-        uint32_t t = gok;
-        for(uint32_t i = 1; i < need && t; ++i) t &= t - 1u; // drop the need-1 first matches
-        const bool has_exit = t != 0u;
-        const uint32_t e = has_exit ? (uint32_t)__ffs(t) - 1u : 31u; // lane of the match that ends the scan
-        const uint32_t ngood = has_exit ? need : (uint32_t)__popc(gok);
-        const uint32_t left = N - min(s_src, N);
-        const uint32_t nscan = has_exit ? (e >> lg) + 1u : min(32u >> lg, left);
-        if(!(ok && lane <= e)) { td = 0xFFFFFFFFu; ts = 0xFFFFFFFFu; } // matches past the exit were never scanned
-#pragma unroll
-        for(uint32_t o = 1; o < 32u; o <<= 1) {
-            if(o >= (1u << lg)) { // warp-uniform
-                td = min(td, __shfl_xor_sync(FULL, td, o)); ts = min(ts, __shfl_xor_sync(FULL, ts, o));
-            }
-        }
-        // the pixel of rank r was served by the lanes of slot r; lane r holds its reduced result
-        const uint32_t pk = __shfl_sync(FULL, ngood | (nscan << 16), rank);
-        const uint32_t rd = __shfl_sync(FULL, td, rank), rs = __shfl_sync(FULL, ts, rank);
-        if(undecided) {
-            good += pk & 0xFFFFu; s += pk >> 16;
-            minDesc = min(minDesc, rd); minSum = min(minSum, rs);
-            undecided = good < REQ && s < N;
-        }
-        __syncwarp(); // worder[] is rewritten by the next round
-        m = __ballot_sync(FULL, undecided);
-    }
-}
+__device__ __forceinline__ uint32_t wl_state_pack(uint32_t minSum, uint32_t minDesc, uint32_t good, uint32_t s) { return minSum | (minDesc << 10) | (good << 16) | (s << 24); }
 
 /// slice of FrameCtl staged in shared memory by the prologue (the feedback step reads it long after the state loads)
 struct CtlSlice { float aLT, aST, t_lower, t_upper; uint32_t frame, cooldown, use3x3, pad; };
@@ -204,11 +132,9 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
-    typedef ScanCtx<CH> X;
+    typedef WlCtx<CH> X;
     constexpr int PITCH = tile_pitch(CH);
     __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
-    __shared__ __align__(16) uint32_t s_ctx[TILE_H][32 * X::WORDS];
-    __shared__ uchar s_order[TILE_H][32];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uchar s_lut[256];
     __shared__ uint32_t s_cnt[5];                 // nonzero | scanned | - | fg | warps done
@@ -240,9 +166,11 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     float R = 0.f;
     Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
     Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
+    uint32_t own = 0xFFu; // own-sample write queued by the previous frame's feedback kernel (slot; 0xFF: none)
     const Rec* bgr = (const Rec*)A.bg + pix;
     if(in_img) { // not `active`: that would chain these loads behind the ROI word's round trip (the planes cover every pixel)
         R = A.r_plane[pix];
+        if(pending) own = A.own_slot[pix];
         lc = ((const Col*)A.prev_color)[pix];
         ld = ((const Desc*)A.prev_desc)[pix];
         { const Rec r0 = bgr[0]; pre_c0 = rec_col(r0); pre_d0 = rec_desc(r0); }
@@ -279,6 +207,17 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     // anything reads the model: own stores are visible to own loads, the two prefetched samples are patched in registers, and
     // the cooperative scan tail (other lanes of this warp read this pixel's samples) runs behind a fence
     if(pending && in_img) {
+        // the pixel's own stochastic update of the previous frame first (the reference writes it inside its pixel loop, the queued
+        // neighbour writes come after the loop and override it): the record is the previous frame's colour / descriptors of this
+        // very pixel, which the scan holds anyway. Doing the scattered store here, where it overlaps ~1000 instructions of
+        // arithmetic, costs nothing measurable; at the end of the feedback kernel it cost 27 us per 1080p frame.
+        if(own != 0xFFu) {
+#ifndef LVB_EXP_NO_OWN_WRITE
+            ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(lc, ld);
+#endif
+            if(own == 0u) { pre_c0 = lc; pre_d0 = ld; }
+            if(own == 1u) { pre_c1 = lc; pre_d1 = ld; }
+        }
         uint32_t hits = s_hits[threadIdx.y][threadIdx.x];
         const Col* pcol = (const Col*)A.prev_color;
         const Desc* pdes = (const Desc*)A.prev_desc;
@@ -303,6 +242,8 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     uint32_t cur[CH], intra[CH];
     uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
     Col cur_pack = Col(); Desc intra_pack = Desc();
+    Lookup16 Lk[CH];
+    uint32_t thrC_ = 0, thrD_ = 0;
 
     if(active) {
         const bool unstable_old = (w_unst & lane_bit) != 0;
@@ -312,7 +253,7 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
 
         const int sy = threadIdx.y + HALO;
-        Lookup16 L[CH];
+        Lookup16 (&L)[CH] = Lk;
         {
             const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
 #pragma unroll
@@ -329,24 +270,35 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
         uint32_t d_, s_;
         if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
         if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
-        if(good < REQ && s < N) { // still undecided: park the scan context for the warp-cooperative tail
-            uint32_t* ctx = &s_ctx[threadIdx.y][threadIdx.x * X::WORDS];
+        thrC_ = thrC; thrD_ = thrD;
+    }
+    // still undecided after the two prefetched samples: hand the pixel to the tail passes (work-list append, one atomic per warp)
+    {
+        const bool undecided = active && good < REQ && s < N;
+        const uint32_t um = __ballot_sync(0xFFFFFFFFu, undecided);
+        if(um) {
+            uint32_t base = 0;
+            if(threadIdx.x == 0) base = atomicAdd(&A.ctl->wl_count, (uint32_t)__popc(um));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if(undecided) {
+                const uint32_t e = base + (uint32_t)__popc(um & ((1u << threadIdx.x) - 1u));
+                uint32_t* w = A.wl_ctx + e;
+                const size_t cap = A.wl_cap;
 #pragma unroll
-            for(int c = 0; c < CH; ++c) *(uint4*)(ctx + 4 * c) = make_uint4(L[c].w[0], L[c].w[1], L[c].w[2], L[c].w[3]);
-            if constexpr (CH == 1) { ctx[X::CUR] = cur[0]; ctx[X::INTRA] = intra[0]; }
-            else { ctx[X::CUR] = cur_pack; ctx[X::INTRA] = intra_pack.x; ctx[X::INTRA + 1] = intra_pack.y; }
-            ctx[X::THRC] = thrC; ctx[X::THRD] = thrD; ctx[X::PIX] = (uint32_t)pix;
+                for(int c = 0; c < CH; ++c)
+#pragma unroll
+                    for(int q = 0; q < 4; ++q) w[(size_t)(X::LOOK + 4 * c + q) * cap] = Lk[c].w[q];
+                if constexpr (CH == 1) { w[(size_t)X::CUR * cap] = cur[0]; w[(size_t)X::INTRA * cap] = intra[0]; }
+                else { w[(size_t)X::CUR * cap] = cur_pack; w[(size_t)X::INTRA * cap] = intra_pack.x; w[(size_t)(X::INTRA + 1) * cap] = intra_pack.y; }
+                w[(size_t)X::THRC * cap] = thrC_; w[(size_t)X::THRD * cap] = thrD_; w[(size_t)X::PIX * cap] = (uint32_t)pix;
+                w[(size_t)X::STATE * cap] = wl_state_pack(minSum, minDesc, good, s);
+            }
         }
     }
-    // the fence sits here, ~600 instructions after the stores it covers, so it normally finds them already performed
-    if(pending) __threadfence_block();
-#ifndef LVB_EXP_NO_TAIL
-    subsense_scan_tail<CH, T7>(A, &s_ctx[threadIdx.y][0], &s_order[threadIdx.y][0], s_lut, active && good < REQ && s < N, N, REQ, good, s, minDesc, minSum);
-#endif
     const uint32_t scanned = s;
 
     if(active) {
-        is_fg = good < REQ;
+        is_fg = good < REQ && s >= N; // an undecided pixel (s < N) is classified by the tail passes, which set its raw bit
         // distance to the previous frame (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
         uint32_t lastL1 = 0, lastHd = 0;
 #pragma unroll
@@ -393,6 +345,118 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     }
 }
 
+/// Tail passes of the sample-consensus scan (SuBSENSE.cpp:229-253 / :367-395 past the second sample): one work-list entry per
+/// LANE, scanned sequentially exactly like the reference's loop ("while good < REQ and s < N"), with the sample records of a batch
+/// of B consecutive samples in flight together. Pass 1 takes every entry up to sample `s_limit` (8: more than 98 % of the
+/// background pixels are decided by then); the survivors (foreground, which scans all N, and a few deep background pixels) go on
+/// list 2 by index and are finished by pass 2, where almost every lane runs the full N samples, so warps stay converged.
+/// A decided entry completes the scan kernel's outputs: min distances + match count in the hand-off word, raw bit if foreground.
+#ifndef LVB_TAIL_PASS1_LIMIT
+#define LVB_TAIL_PASS1_LIMIT 8
+#endif
+constexpr uint32_t TAIL_PASS1_LIMIT = LVB_TAIL_PASS1_LIMIT; // pass 1 scans samples 2 .. LIMIT-1
+struct TailPassArgs {
+    int Wp, WW, N, REQ;
+    size_t plane;
+    const void* bg;
+    const uint32_t* wl_ctx; uint32_t wl_cap;
+    const uint32_t* in_idx;     // nullptr: entries 0..count-1 of the work-list; else the entries named by this index list
+    const uint32_t* in_count;
+    uint32_t* out_idx; uint32_t* out_count;   // survivors (nullptr: none expected, s_limit >= N)
+    uint32_t s_limit;
+    uint2* hand; uint32_t* raw_bits;
+    const uchar* lut;
+    FrameCtl* ctl; int collect_stats;
+};
+template<int CH, bool T7, int B>
+__global__ void __launch_bounds__(128) subsense_tail_pass(const TailPassArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
+    typedef WlCtx<CH> X;
+    __shared__ uchar s_lut[256];
+    for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
+    __syncthreads();
+    const uint32_t count = *A.in_count;
+    const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ, s_end = min(N, A.s_limit);
+    const size_t cap = A.wl_cap;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t scanned_acc = 0, fg_acc = 0;
+    // whole warps stay in the loop together (the survivor append is a warp-level ballot)
+    const uint32_t nthreads = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
+    for(uint32_t e0 = first - lane; e0 < count; e0 += nthreads) {
+        const uint32_t e = e0 + lane;
+        const bool have = e < count;
+        bool survivor = false;
+        uint32_t idx = 0;
+        if(have) {
+            idx = A.in_idx ? A.in_idx[e] : e;
+            const uint32_t* w = A.wl_ctx + idx;
+            Lookup16 L[CH];
+            uint32_t cur[CH], intra[CH];
+#pragma unroll
+            for(int c = 0; c < CH; ++c)
+#pragma unroll
+                for(int q = 0; q < 4; ++q) L[c].w[q] = w[(size_t)(X::LOOK + 4 * c + q) * cap];
+            const uint32_t cp = w[(size_t)X::CUR * cap];
+            if constexpr (CH == 1) { cur[0] = cp; intra[0] = w[(size_t)X::INTRA * cap]; }
+            else {
+                const uint32_t i0 = w[(size_t)X::INTRA * cap], i1 = w[(size_t)(X::INTRA + 1) * cap];
+#pragma unroll
+                for(int c = 0; c < CH; ++c) cur[c] = (cp >> (8 * c)) & 0xFFu;
+                intra[0] = i0 & 0xFFFFu; intra[1] = i0 >> 16; intra[2] = i1;
+            }
+            const uint32_t thrC = w[(size_t)X::THRC * cap], thrD = w[(size_t)X::THRD * cap], pix = w[(size_t)X::PIX * cap];
+            const uint32_t st = w[(size_t)X::STATE * cap];
+            uint32_t minSum = st & 0x3FFu, minDesc = (st >> 10) & 0x3Fu, good = (st >> 16) & 0xFFu, s = st >> 24;
+            const uint32_t s0 = s;
+            const Rec* bgp = (const Rec*)A.bg + pix;
+            while(good < REQ && s < s_end) {
+                Rec r[B];
+#pragma unroll
+                for(int j = 0; j < B; ++j) if(s + j < s_end) r[j] = bgp[(size_t)(s + j) * A.plane];
+#pragma unroll
+                for(int j = 0; j < B; ++j) {
+                    if(good < REQ && s < s_end) {
+                        uint32_t d_, s_;
+                        if(subsense_test_sample<CH, T7>(L, cur, intra, rec_col(r[j]), rec_desc(r[j]), thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; }
+                        ++s;
+                    }
+                }
+            }
+            scanned_acc += s - s0;
+            if(good < REQ && s < N) { // not decided within this pass
+                survivor = true;
+                const_cast<uint32_t*>(A.wl_ctx)[(size_t)X::STATE * cap + idx] = wl_state_pack(minSum, minDesc, good, s);
+            } else {
+                uint2* h = A.hand + pix;
+                h->x = minSum | (minDesc << 16);
+                *(ushort*)&h->y = (ushort)good; // low half of (good | lastL1 << 16 | lastHd << 24)
+                if(good < REQ) {
+                    const uint32_t px = pix % (uint32_t)A.Wp, py = pix / (uint32_t)A.Wp;
+                    atomicOr(A.raw_bits + (size_t)py * A.WW + (px >> 5), 1u << (px & 31u));
+                    ++fg_acc;
+                }
+            }
+        }
+        const uint32_t sm = __ballot_sync(0xFFFFFFFFu, survivor);
+        if(sm && A.out_idx) {
+            uint32_t base = 0;
+            if(lane == 0) base = atomicAdd(A.out_count, (uint32_t)__popc(sm));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if(survivor) A.out_idx[base + (uint32_t)__popc(sm & ((1u << lane) - 1u))] = idx;
+        }
+    }
+    if(A.collect_stats) {
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { scanned_acc += __shfl_xor_sync(0xFFFFFFFFu, scanned_acc, o); fg_acc += __shfl_xor_sync(0xFFFFFFFFu, fg_acc, o); }
+        if(lane == 0) {
+            if(scanned_acc) atomicAdd(&A.ctl->stat_scanned, (unsigned long long)scanned_acc);
+            if(fg_acc) atomicAdd(&A.ctl->stat_fg, (unsigned long long)fg_acc);
+        }
+    }
+}
+
 /// frame tail (SuBSENSE.cpp:555-611): LUT +-1 adaptation, frame-level reset / learning-rate caps, next-frame factors.
 /// Executed by one warp: the last one of the last CTA of the feedback kernel.
 struct TailArgs {
@@ -410,6 +474,7 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
         dir = (ratio < 0.1f && last < 0.1f) ? -1 : (ratio > 0.5f && last > 0.5f) ? 1 : 0;
         ctl->last_nonzero_ratio = ratio;
         ctl->nonzero_count = 0;
+        ctl->wl_count = 0; ctl->wl2_count = 0; // the scan work-lists of this frame were consumed by the tail passes long ago
         ctl->do_refresh = 0; ctl->set_T_one = 0;
         if(ctl->lr_scaling) {
             const float diff_ratio = __fdiv_rn((float)ctl->tot_color_diff, (float)(A.dsW * A.dsH));
@@ -477,11 +542,11 @@ template<int CH> struct FbStage {
     float4 maps[FB_H][64];                    // (T,R,v,Dlast | DminLT,DminST,rawLT,rawST) x 32 px
     float2 fin[FB_H][32];
     uint2 hand[FB_H][32];
-    typename Pack<CH>::Col col[FB_H][32];     // this frame's colour / intra descriptors (written by the scan kernel)
-    typename Pack<CH>::Desc desc[FB_H][32];
     uint32_t words[FB_H][20];                 // roi | blinks | lastfg | - | previous frame's ghost bits: rows y-2..y+2 x words wi-1..wi+1 | -
 };
 
+/// The kernel does not touch the sample model: the pixel's own stochastic update is QUEUED (own_slot plane, like the neighbour
+/// write in the intents plane) and stored by the next frame's scan kernel, which holds the record anyway.
 /// Persistent: a CTA walks 32x8 tiles with stride gridDim.x. The state of tile i+1 is copied global -> shared (cp.async, no
 /// registers held) while tile i is computed, so the ~1 us DRAM round trip that used to open every CTA's life is hidden behind
 /// the previous tile's arithmetic, and the small division / modulo tables are staged once per CTA instead of once per tile.
@@ -515,10 +580,6 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             cp_async16((char*)&S.maps[warp][0] + 16 * (lane + 32), g_maps + 16 * (lane + 32));
             if(lane < 16) cp_async16((char*)&S.fin[warp][0] + 16 * lane, (const char*)(A.fin + rowpix) + 16 * lane);
             else cp_async16((char*)&S.hand[warp][0] + 16 * (lane - 16), (const char*)(A.hand + rowpix) + 16 * (lane - 16));
-            constexpr int NC = 32 * (int)sizeof(Col) / 16, ND = 32 * (int)sizeof(Desc) / 16;
-            static_assert(NC <= 8 && ND <= 16, "row segment chunks");
-            if(lane < NC) cp_async16((char*)&S.col[warp][0] + 16 * lane, (const char*)((const Col*)A.last_color + rowpix) + 16 * lane);
-            else if(lane >= 8 && lane < 8 + ND) cp_async16((char*)&S.desc[warp][0] + 16 * (lane - 8), (const char*)((const Desc*)A.last_desc + rowpix) + 16 * (lane - 8));
             if(lane < 18) {
                 const int wx = x0 >> 5;
                 const uint32_t* src = A.roi_bits; bool ok = true; int gy = y, gw = wx;
@@ -571,13 +632,12 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         bool unstable_new = false, ghost_new = false, has_intent = false;
         uint32_t writes = 0;
         uint32_t intent = NO_INTENT; // queued neighbour write: (clamped relative target offset index) << 8 | slot
+        uint32_t own = 0xFFu;        // queued own-sample write: slot (the next scan stores this frame's colour / descriptors there)
 
         if(active) {
             const float4 m0 = S.maps[warp][2 * lane], m1 = S.maps[warp][2 * lane + 1];
             float2 fin = S.fin[warp][lane];
             const uint2 hand = S.hand[warp][lane];
-            const Col cur_pack = S.col[warp][lane];
-            const Desc intra_pack = S.desc[warp][lane];
             const uint32_t minSum = hand.x & 0xFFFFu, minDesc = hand.x >> 16, good = hand.y & 0xFFFFu, lastL1 = (hand.y >> 16) & 0xFFu, lastHd = hand.y >> 24;
             const bool is_fg = good < REQ;
             float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
@@ -612,10 +672,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
                 rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT);
                 rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
                 if(cooldown && (rnd.x % 2u) == 0) {
-                    const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-#ifndef LVB_EXP_NO_OWN_WRITE
-                    ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
-#endif
+                    own = fast_mod(rnd.y, N, A.n_magic);
                     ++writes;
                 }
             } else { // background (:270-301 / :414-450)
@@ -630,12 +687,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
                 const uint32_t mg = A.lr_fixed ? A.lr_magic : s_magic[tab ? LR : 0u], mg2 = A.lr_fixed ? A.lr2_magic : s_magic[tab ? LR2 : 0u];
                 const bool fastm = A.lr_fixed || tab;
                 if((fastm ? fast_mod(rnd.x, LR, mg) : rnd.x % LR) == 0) {
-                    const uint32_t slot = fast_mod(rnd.y, N, A.n_magic);
-#ifndef LVB_EXP_NO_OWN_WRITE
-                    ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(cur_pack, intra_pack);
-#else
-                    if(slot == 77u) A.r_plane[pix] = 0.f;
-#endif
+                    own = fast_mod(rnd.y, N, A.n_magic);
                     ++writes;
                 }
                 const bool cur3 = use3x3 && !unstable_new;
@@ -682,7 +734,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         // warp-level packing of the per-pixel flags: one 32-bit mask word per warp row
         const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
         const uint32_t b_ghost = __ballot_sync(0xFFFFFFFFu, ghost_new);
-        if(in_img) A.intents[pix] = (ushort)intent; // every pixel, every frame: phase B scans the plane without a has-intent mask
+        if(in_img) { A.intents[pix] = (ushort)intent; A.own_slot[pix] = (uchar)own; } // every pixel, every frame: consumers scan the planes without a has-intent mask
         if(y < A.H && (x >> 5) < A.WW && lane == 0) { A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; }
         if(A.collect_stats) writes_acc += writes + (has_intent ? 1u : 0u);
         __syncwarp(); // every lane is done with this stage before the warp refills it (two iterations from now)
@@ -729,6 +781,7 @@ struct PhaseBArgs {
     const void* last_color;    // == this frame's colour for every pixel that queued a write
     const void* last_desc;     // == this frame's intra descriptors for every pixel that queued a write
     const ushort* intents;
+    const uchar* own_slot;     // SuBSENSE: queued own-sample writes (applied before the neighbour writes, which override them); LOBSTER: nullptr
     const FrameCtl* ctl; uint32_t pending_seq; // pending_seq != 0: skip when FrameCtl::nb_applied_seq says these writes are already in the model
     uint32_t* bump_frame;      // LOBSTER: FrameCtl::frame_idx, advanced by one thread here (the frame's pixel pass is over; saves a launch)
 };
@@ -751,6 +804,11 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     __syncthreads();
     if(A.bump_frame && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) *A.bump_frame += 1u;
     const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if(A.own_slot && x < A.W && y < A.H) { // the pixel's own queued update first
+        const size_t p = (size_t)y * A.Wp + x;
+        const uint32_t own = A.own_slot[p];
+        if(own != 0xFFu) ((Rec*)A.bg)[(size_t)own * A.plane + p] = rec_make(((const Col*)A.last_color)[p], ((const Desc*)A.last_desc)[p]);
+    }
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
     // pass 1: which of the 25 sources aim at this pixel (no global access); bit i = window position i = (dy+2)*5 + k
     uint32_t hits = 0;
@@ -806,6 +864,7 @@ struct RefreshArgs {
     uint64_t seed;
     int recompute_desc;        // LOBSTER: descriptor of the sampled pixel is recomputed from last_color
     const ushort* intents; uint32_t pending_seq; // SuBSENSE: neighbour writes of this frame not yet in the model are applied first
+    const uchar* own_slot;     // SuBSENSE: ... and before them the queued own-sample writes
 };
 
 template<int CH>
@@ -823,6 +882,10 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
     const int x = (tile % tiles_x) * 32 + threadIdx.x, y = (tile / tiles_x) * 8 + threadIdx.y;
     if(x >= A.W || y >= A.H) continue;
     const size_t pix = (size_t)y * A.Wp + x;
+    if(apply_nb && A.own_slot) {
+        const uint32_t own = A.own_slot[pix];
+        if(own != 0xFFu) ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(((const Col*)A.last_color)[pix], ((const Desc*)A.last_desc)[pix]);
+    }
     if(apply_nb && x >= 2 && y >= 2 && x <= A.W - 3 && y <= A.H - 3) {
         // the reference applies the frame's neighbour writes inside its pixel loop, i.e. before refreshModel: same rule as phase B
         for(int dy = -2; dy <= 2; ++dy) for(int k = 0; k < 5; ++k) {

@@ -24,7 +24,7 @@ else
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
-    print('frame_ms=%.4f scan_ms=%.4f fb_ms=%.4f e2e=%.0f frame_frac=%.3f' % (d['ms_per_step'], r['avg_launch_ms'], r['second_kernel']['avg_launch_ms'], d['e2e']['value'], r['frame']['frac']))
+    print('frame_ms=%.4f scan_ms=%.4f tail_ms=%.4f fb_ms=%.4f e2e=%.0f sync=%.0f frame_frac=%.3f sbar=%.2f' % (d['ms_per_step'], r['avg_launch_ms'], r.get('tail_passes_avg_ms', 0), r['second_kernel']['avg_launch_ms'], d['e2e']['value'], d['e2e']['synchronous_apply_value'], r['frame']['frac'], r['scan_depth']))
 except Exception as e: print('FAILED', e)
 ")"
   done
