@@ -733,15 +733,16 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
             TP.collect_stats = c->collect_stats;
             cudaEvent_t tp0 = nullptr, tp1 = nullptr;
             if(c->profile) { CK(cudaEventCreate(&tp0)); CK(cudaEventCreate(&tp1)); CK(cudaEventRecord(tp0, st)); }
+            // persistent grids (warps pull chunks of 32 entries): resident CTAs per SM x SM count, capped by the frame size
             const int npx = W * H;
-            const int g1 = std::max(1, std::min(c->sm_count * 8, (npx / 4 + 127) / 128)), g2 = std::max(1, std::min(c->sm_count * 8, (npx / 16 + 127) / 128));
-            TP.in_idx = nullptr; TP.in_count = &c->ctl->wl_count; TP.out_idx = c->wl2_idx; TP.out_count = &c->ctl->wl2_count; TP.s_limit = TAIL_PASS1_LIMIT;
-            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 3><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 3><<<g1, 128, 0, st>>>(TP); }
-            else { if(C == 1) subsense_tail_pass<1, false, 3><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 3><<<g1, 128, 0, st>>>(TP); }
+            const int g1 = std::max(1, std::min(c->sm_count * TAIL1_MINB, (npx / 4 + 127) / 128)), g2 = std::max(1, std::min(c->sm_count * TAIL2_MINB, (npx / 8 + 127) / 128));
+            TP.in_idx = nullptr; TP.in_count = &c->ctl->wl_count; TP.cursor = &c->ctl->wl_cursor; TP.out_idx = c->wl2_idx; TP.out_count = &c->ctl->wl2_count; TP.s_limit = TAIL_PASS1_LIMIT;
+            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
+            else { if(C == 1) subsense_tail_pass<1, false, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
             LAUNCHED();
-            TP.in_idx = c->wl2_idx; TP.in_count = &c->ctl->wl2_count; TP.out_idx = nullptr; TP.out_count = nullptr; TP.s_limit = 0xFFFFFFFFu;
-            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 4><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 4><<<g2, 128, 0, st>>>(TP); }
-            else { if(C == 1) subsense_tail_pass<1, false, 4><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 4><<<g2, 128, 0, st>>>(TP); }
+            TP.in_idx = c->wl2_idx; TP.in_count = &c->ctl->wl2_count; TP.cursor = &c->ctl->wl2_cursor; TP.out_idx = nullptr; TP.out_count = nullptr; TP.s_limit = 0xFFFFFFFFu;
+            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); }
+            else { if(C == 1) subsense_tail_pass<1, false, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); }
             LAUNCHED();
             if(c->profile) { CK(cudaEventRecord(tp1, st)); c->prof3_events.push_back(tp0); c->prof3_events.push_back(tp1); }
             mark(st, "scan tail passes");

@@ -45,7 +45,7 @@ struct FrameCtl {
     uint32_t nb_applied_seq;   // sequence number of the last frame whose queued neighbour writes are already in the model
     uint32_t wl_count;         // SuBSENSE scan work-list: pixels still undecided after the two prefetched samples (reset by the frame tail)
     uint32_t wl2_count;        // ... and those still undecided after the first tail pass
-    uint32_t pad[2];
+    uint32_t wl_cursor, wl2_cursor;   // chunk cursors of the two tail passes (warps pull 32 entries at a time)
 };
 
 // One background sample = one naturally aligned record (colour + descriptors): 16 bytes for 3 channels, 4 bytes for 1.

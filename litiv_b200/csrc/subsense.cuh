@@ -111,7 +111,8 @@ template<int CH> struct WlCtx {
     static constexpr int INTRA = CUR + 1;               // intra descriptors (CH==3: 2 words)
     static constexpr int THRC = INTRA + (CH == 3 ? 2 : 1), THRD = THRC + 1, PIX = THRD + 1;
     static constexpr int STATE = PIX + 1;               // minSum (10 bits) | minDesc << 10 (6) | good << 16 (8) | scanned << 24 (8)
-    static constexpr int FIELDS = STATE + 1;
+    static constexpr int FIELDS = (STATE + 1 + 3) / 4 * 4;   // array of structures, entries padded to 16 bytes: a warp's appends are one contiguous run of full sectors
+    static constexpr int VEC = FIELDS / 4;
 };
 __device__ __forceinline__ uint32_t wl_state_pack(uint32_t minSum, uint32_t minDesc, uint32_t good, uint32_t s) { return minSum | (minDesc << 10) | (good << 16) | (s << 24); }
 
@@ -282,16 +283,20 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if(undecided) {
                 const uint32_t e = base + (uint32_t)__popc(um & ((1u << threadIdx.x) - 1u));
-                uint32_t* w = A.wl_ctx + e;
-                const size_t cap = A.wl_cap;
+                uint32_t f[X::FIELDS];
+#pragma unroll
+                for(int i = 0; i < X::FIELDS; ++i) f[i] = 0u;
 #pragma unroll
                 for(int c = 0; c < CH; ++c)
 #pragma unroll
-                    for(int q = 0; q < 4; ++q) w[(size_t)(X::LOOK + 4 * c + q) * cap] = Lk[c].w[q];
-                if constexpr (CH == 1) { w[(size_t)X::CUR * cap] = cur[0]; w[(size_t)X::INTRA * cap] = intra[0]; }
-                else { w[(size_t)X::CUR * cap] = cur_pack; w[(size_t)X::INTRA * cap] = intra_pack.x; w[(size_t)(X::INTRA + 1) * cap] = intra_pack.y; }
-                w[(size_t)X::THRC * cap] = thrC_; w[(size_t)X::THRD * cap] = thrD_; w[(size_t)X::PIX * cap] = (uint32_t)pix;
-                w[(size_t)X::STATE * cap] = wl_state_pack(minSum, minDesc, good, s);
+                    for(int q = 0; q < 4; ++q) f[X::LOOK + 4 * c + q] = Lk[c].w[q];
+                if constexpr (CH == 1) { f[X::CUR] = cur[0]; f[X::INTRA] = intra[0]; }
+                else { f[X::CUR] = cur_pack; f[X::INTRA] = intra_pack.x; f[X::INTRA + 1] = intra_pack.y; }
+                f[X::THRC] = thrC_; f[X::THRD] = thrD_; f[X::PIX] = (uint32_t)pix;
+                f[X::STATE] = wl_state_pack(minSum, minDesc, good, s);
+                uint4* w = (uint4*)(A.wl_ctx + (size_t)e * X::FIELDS);
+#pragma unroll
+                for(int v = 0; v < X::VEC; ++v) w[v] = make_uint4(f[4 * v], f[4 * v + 1], f[4 * v + 2], f[4 * v + 3]);
             }
         }
     }
@@ -355,79 +360,126 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 #define LVB_TAIL_PASS1_LIMIT 8
 #endif
 constexpr uint32_t TAIL_PASS1_LIMIT = LVB_TAIL_PASS1_LIMIT; // pass 1 scans samples 2 .. LIMIT-1
+#ifndef LVB_TAIL1_MINB
+#define LVB_TAIL1_MINB 7
+#endif
+#ifndef LVB_TAIL2_MINB
+#define LVB_TAIL2_MINB 4
+#endif
+#ifndef LVB_TAIL2_B
+#define LVB_TAIL2_B 8
+#endif
+constexpr int TAIL1_MINB = LVB_TAIL1_MINB, TAIL2_MINB = LVB_TAIL2_MINB, TAIL2_B = LVB_TAIL2_B; // resident CTAs per SM (launch bounds) of the two passes; pass-2 stage depth
 struct TailPassArgs {
     int Wp, WW, N, REQ;
     size_t plane;
     const void* bg;
-    const uint32_t* wl_ctx; uint32_t wl_cap;
+    uint32_t* wl_ctx; uint32_t wl_cap;
     const uint32_t* in_idx;     // nullptr: entries 0..count-1 of the work-list; else the entries named by this index list
     const uint32_t* in_count;
+    uint32_t* cursor;           // work distribution: every warp pulls chunks of 32 entries (FrameCtl::wl_cursor / wl2_cursor)
     uint32_t* out_idx; uint32_t* out_count;   // survivors (nullptr: none expected, s_limit >= N)
     uint32_t s_limit;
     uint2* hand; uint32_t* raw_bits;
     const uchar* lut;
     FrameCtl* ctl; int collect_stats;
 };
-template<int CH, bool T7, int B>
-__global__ void __launch_bounds__(128) subsense_tail_pass(const TailPassArgs A) {
+/// STREAM = false (pass 1): the B records of a batch are loaded into registers. STREAM = true (pass 2, where nearly every entry scans
+/// all N samples): the records stream through a per-lane double buffer in shared memory filled by cp.async, batch j+1 in flight while
+/// batch j is tested, so the ~40 dependent DRAM round trips of a foreground pixel collapse into one pipeline.
+template<int CH, bool T7, int B, int MINB, bool STREAM>
+__global__ void __launch_bounds__(128, MINB) subsense_tail_pass(const TailPassArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
     typedef WlCtx<CH> X;
     __shared__ uchar s_lut[256];
+    __shared__ __align__(16) Rec s_rec[STREAM ? 2 : 1][STREAM ? B : 1][STREAM ? 128 : 1];
     for(int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = A.lut[i];
     __syncthreads();
     const uint32_t count = *A.in_count;
     const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ, s_end = min(N, A.s_limit);
-    const size_t cap = A.wl_cap;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, tid = threadIdx.x;
     uint32_t scanned_acc = 0, fg_acc = 0;
-    // whole warps stay in the loop together (the survivor append is a warp-level ballot)
-    const uint32_t nthreads = gridDim.x * blockDim.x, first = blockIdx.x * blockDim.x + threadIdx.x;
-    for(uint32_t e0 = first - lane; e0 < count; e0 += nthreads) {
+    for(;;) {
+        uint32_t e0 = 0;
+        if(lane == 0) e0 = atomicAdd(A.cursor, 32u);
+        e0 = __shfl_sync(0xFFFFFFFFu, e0, 0);
+        if(e0 >= count) break;
         const uint32_t e = e0 + lane;
         const bool have = e < count;
         bool survivor = false;
         uint32_t idx = 0;
         if(have) {
             idx = A.in_idx ? A.in_idx[e] : e;
-            const uint32_t* w = A.wl_ctx + idx;
+            uint32_t* w = A.wl_ctx + (size_t)idx * X::FIELDS;
+            uint32_t f[X::FIELDS];
+#pragma unroll
+            for(int v = 0; v < X::VEC; ++v) { const uint4 t = ((const uint4*)w)[v]; f[4 * v] = t.x; f[4 * v + 1] = t.y; f[4 * v + 2] = t.z; f[4 * v + 3] = t.w; }
             Lookup16 L[CH];
             uint32_t cur[CH], intra[CH];
 #pragma unroll
             for(int c = 0; c < CH; ++c)
 #pragma unroll
-                for(int q = 0; q < 4; ++q) L[c].w[q] = w[(size_t)(X::LOOK + 4 * c + q) * cap];
-            const uint32_t cp = w[(size_t)X::CUR * cap];
-            if constexpr (CH == 1) { cur[0] = cp; intra[0] = w[(size_t)X::INTRA * cap]; }
+                for(int q = 0; q < 4; ++q) L[c].w[q] = f[X::LOOK + 4 * c + q];
+            const uint32_t cp = f[X::CUR];
+            if constexpr (CH == 1) { cur[0] = cp; intra[0] = f[X::INTRA]; }
             else {
-                const uint32_t i0 = w[(size_t)X::INTRA * cap], i1 = w[(size_t)(X::INTRA + 1) * cap];
 #pragma unroll
                 for(int c = 0; c < CH; ++c) cur[c] = (cp >> (8 * c)) & 0xFFu;
-                intra[0] = i0 & 0xFFFFu; intra[1] = i0 >> 16; intra[2] = i1;
+                intra[0] = f[X::INTRA] & 0xFFFFu; intra[1] = f[X::INTRA] >> 16; intra[2] = f[X::INTRA + 1];
             }
-            const uint32_t thrC = w[(size_t)X::THRC * cap], thrD = w[(size_t)X::THRD * cap], pix = w[(size_t)X::PIX * cap];
-            const uint32_t st = w[(size_t)X::STATE * cap];
+            const uint32_t thrC = f[X::THRC], thrD = f[X::THRD], pix = f[X::PIX];
+            const uint32_t st = f[X::STATE];
             uint32_t minSum = st & 0x3FFu, minDesc = (st >> 10) & 0x3Fu, good = (st >> 16) & 0xFFu, s = st >> 24;
             const uint32_t s0 = s;
             const Rec* bgp = (const Rec*)A.bg + pix;
-            while(good < REQ && s < s_end) {
-                Rec r[B];
+            if constexpr (STREAM) {
+                auto issue = [&](int stage, uint32_t from) {
 #pragma unroll
-                for(int j = 0; j < B; ++j) if(s + j < s_end) r[j] = bgp[(size_t)(s + j) * A.plane];
+                    for(int j = 0; j < B; ++j)
+                        if(from + j < s_end) {
+                            if constexpr (sizeof(Rec) == 16) cp_async16(&s_rec[stage][j][tid], bgp + (size_t)(from + j) * A.plane);
+                            else cp_async4_zfill(&s_rec[stage][j][tid], bgp + (size_t)(from + j) * A.plane, true);
+                        }
+                    cp_async_commit();
+                };
+                int stage = 0;
+                issue(0, s);
+                while(good < REQ && s < s_end) {
+                    issue(stage ^ 1, s + B);   // next batch in flight while this one is tested
+                    cp_async_wait<1>();        // this batch has landed (every lane reads only what it copied itself)
 #pragma unroll
-                for(int j = 0; j < B; ++j) {
-                    if(good < REQ && s < s_end) {
-                        uint32_t d_, s_;
-                        if(subsense_test_sample<CH, T7>(L, cur, intra, rec_col(r[j]), rec_desc(r[j]), thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; }
-                        ++s;
+                    for(int j = 0; j < B; ++j) {
+                        if(good < REQ && s < s_end) {
+                            const Rec r = s_rec[stage][j][tid];
+                            uint32_t d_, s_;
+                            if(subsense_test_sample<CH, T7>(L, cur, intra, rec_col(r), rec_desc(r), thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; }
+                            ++s;
+                        }
+                    }
+                    stage ^= 1;
+                }
+                cp_async_wait<0>();            // nothing of this entry may land in the buffers once the next entry uses them
+            } else {
+                while(good < REQ && s < s_end) {
+                    Rec r[B];
+#pragma unroll
+                    for(int j = 0; j < B; ++j) if(s + j < s_end) r[j] = bgp[(size_t)(s + j) * A.plane];
+#pragma unroll
+                    for(int j = 0; j < B; ++j) {
+                        if(good < REQ && s < s_end) {
+                            uint32_t d_, s_;
+                            if(subsense_test_sample<CH, T7>(L, cur, intra, rec_col(r[j]), rec_desc(r[j]), thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; }
+                            ++s;
+                        }
                     }
                 }
             }
             scanned_acc += s - s0;
             if(good < REQ && s < N) { // not decided within this pass
                 survivor = true;
-                const_cast<uint32_t*>(A.wl_ctx)[(size_t)X::STATE * cap + idx] = wl_state_pack(minSum, minDesc, good, s);
+                w[X::STATE] = wl_state_pack(minSum, minDesc, good, s);
             } else {
                 uint2* h = A.hand + pix;
                 h->x = minSum | (minDesc << 16);
@@ -474,7 +526,7 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
         dir = (ratio < 0.1f && last < 0.1f) ? -1 : (ratio > 0.5f && last > 0.5f) ? 1 : 0;
         ctl->last_nonzero_ratio = ratio;
         ctl->nonzero_count = 0;
-        ctl->wl_count = 0; ctl->wl2_count = 0; // the scan work-lists of this frame were consumed by the tail passes long ago
+        ctl->wl_count = 0; ctl->wl2_count = 0; ctl->wl_cursor = 0; ctl->wl2_cursor = 0; // this frame's scan work-lists are consumed
         ctl->do_refresh = 0; ctl->set_T_one = 0;
         if(ctl->lr_scaling) {
             const float diff_ratio = __fdiv_rn((float)ctl->tot_color_diff, (float)(A.dsW * A.dsH));
@@ -571,8 +623,14 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     const int tid = warp * TILE_W + lane;
     const int tiles_x = A.Wp / TILE_W, ntiles = tiles_x * ((A.H + FB_H - 1) / FB_H);
 
-    auto prefetch = [&](int tile, FbStage<CH>& S) {
-        const int ty = tile / tiles_x, x0 = (tile - ty * tiles_x) * TILE_W, y = ty * FB_H + warp;
+    // tile coordinates advance incrementally (no integer division per tile): (tx, ty) += (step_x, step_y) with a carry
+    const int step_y = (int)gridDim.x / tiles_x, step_x = (int)gridDim.x - step_y * tiles_x;
+    auto advance = [&](int& tx, int& ty) { tx += step_x; ty += step_y; if(tx >= tiles_x) { tx -= tiles_x; ++ty; } };
+    // which flag word this lane stages for its warp: roi | blinks | lastfg | previous frame's ghost bits (rows y-2..y+2, words wi-1..wi+1)
+    const uint32_t* w_src = lane == 0 ? A.roi_bits : lane == 1 ? A.blinks_bits : lane == 2 ? A.lastfg_bits : A.ghost_prev;
+    const int w_dy = lane >= 3 ? (lane - 3) / 3 - HALO : 0, w_dx = lane >= 3 ? (lane - 3) % 3 - 1 : 0, w_slot = lane < 3 ? lane : lane + 1;
+    auto prefetch = [&](int tx, int ty, FbStage<CH>& S) {
+        const int x0 = tx * TILE_W, y = ty * FB_H + warp;
         if(y < A.H) { // whole 32-px row segments: the planes are Wp (a multiple of 32) wide, padding columns are never used
             const size_t rowpix = (size_t)y * A.Wp + x0;
             const char* g_maps = (const char*)(A.maps + rowpix * 2);
@@ -581,17 +639,16 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             if(lane < 16) cp_async16((char*)&S.fin[warp][0] + 16 * lane, (const char*)(A.fin + rowpix) + 16 * lane);
             else cp_async16((char*)&S.hand[warp][0] + 16 * (lane - 16), (const char*)(A.hand + rowpix) + 16 * (lane - 16));
             if(lane < 18) {
-                const int wx = x0 >> 5;
-                const uint32_t* src = A.roi_bits; bool ok = true; int gy = y, gw = wx;
-                if(lane == 1) src = A.blinks_bits; else if(lane == 2) src = A.lastfg_bits;
-                else if(lane >= 3) { src = A.ghost_prev; gy = y - HALO + (lane - 3) / 3; gw = wx - 1 + (lane - 3) % 3; ok = gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW; }
-                cp_async4_zfill(&S.words[warp][lane < 3 ? lane : lane + 1], ok ? src + (size_t)gy * A.WW + gw : src, ok);
+                const int gy = y + w_dy, gw = tx + w_dx;
+                const bool ok = gy >= 0 && gy < A.H && gw >= 0 && gw < A.WW;
+                cp_async4_zfill(&S.words[warp][w_slot], ok ? w_src + (size_t)gy * A.WW + gw : w_src, ok);
             }
         }
     };
 
     int tile = blockIdx.x;
-    if(tile < ntiles) prefetch(tile, s_stage[0]);
+    int tx = tile % tiles_x, ty = tile / tiles_x;
+    if(tile < ntiles) prefetch(tx, ty, s_stage[0]);
     cp_async_commit();
     for(int i = tid; i < 257; i += TILE_W * FB_H) s_magic[i] = A.magic[i];
     for(int i = tid; i < NCOL; i += TILE_W * FB_H) s_divc[i] = A.div_color[i];
@@ -610,16 +667,22 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
     const float aLT = s_ctl.aLT, aST = s_ctl.aST, t_lower = s_ctl.t_lower, t_upper = s_ctl.t_upper;
     const uint32_t frame = s_ctl.frame, cooldown = s_ctl.cooldown, use3x3 = s_ctl.use3x3;
     uint32_t writes_acc = 0;
+    // factors of the folded final-mask EMAs, uniform over the frame: (1 - e) and 255 * ((1/255) * e), each rounded as in the per-pixel form
+    const float eLT = __fdiv_rn(1.0f, (float)min(max(A.ema_frame, 1u), (uint32_t)A.avg_samples)), eST = __fdiv_rn(1.0f, (float)min(max(A.ema_frame, 1u), (uint32_t)A.avg_samples / 4u));
+    const double ema_a1 = (double)__fsub_rn(1.0f, eLT), ema_a2 = (double)__fsub_rn(1.0f, eST);
+    const double ema_b1 = __dmul_rn(255.0, __dmul_rn(1.0 / 255, (double)eLT)), ema_b2 = __dmul_rn(255.0, __dmul_rn(1.0 / 255, (double)eST));
 
     for(int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
         const FbStage<CH>& S = s_stage[it & 1];
         const int next = tile + (int)gridDim.x;
-        if(next < ntiles) prefetch(next, s_stage[(it + 1) & 1]);
+        int ntx = tx, nty = ty;
+        advance(ntx, nty);
+        if(next < ntiles) prefetch(ntx, nty, s_stage[(it + 1) & 1]);
         cp_async_commit();
         cp_async_wait<1>();  // everything but the group just committed has landed: this tile's state is in shared memory
         __syncwarp();        // ... and visible to the other lanes of the warp (row segments are copied cooperatively)
 
-        const int ty = tile / tiles_x, x0 = (tile - ty * tiles_x) * TILE_W;
+        const int x0 = tx * TILE_W;
         const int x = x0 + lane, y = ty * FB_H + warp;
         const bool in_img = (x < A.W) && (y < A.H);
         const int wi = y * A.WW + (x >> 5);
@@ -643,11 +706,8 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
             float T = m0.x, R = m0.y, V = m0.z, Dlast = m0.w, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
             const bool blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
             if(A.ema_frame) { // final-segmentation EMAs of the previous frame (:553-554): cv::addWeighted accumulates in double, rounds once
-                const float eLT = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples));
-                const float eST = __fdiv_rn(1.0f, (float)min(A.ema_frame, (uint32_t)A.avg_samples / 4u));
-                const double v = lastfg ? 255.0 : 0.0;
-                fin.x = (float)__dadd_rn(__dmul_rn((double)fin.x, (double)__fsub_rn(1.0f, eLT)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eLT)));
-                fin.y = (float)__dadd_rn(__dmul_rn((double)fin.y, (double)__fsub_rn(1.0f, eST)), __dmul_rn(v, __dmul_rn(1.0 / 255, (double)eST)));
+                fin.x = (float)__dadd_rn(__dmul_rn((double)fin.x, ema_a1), lastfg ? ema_b1 : 0.0);
+                fin.y = (float)__dadd_rn(__dmul_rn((double)fin.y, ema_a2), lastfg ? ema_b2 : 0.0);
                 A.fin[pix] = fin;
             }
             unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
@@ -738,6 +798,7 @@ subsense_feedback(const SubArgs A, const TailArgs TA) {
         if(y < A.H && (x >> 5) < A.WW && lane == 0) { A.unstable_bits[wi] = b_unst; A.ghost_cur[wi] = b_ghost; }
         if(A.collect_stats) writes_acc += writes + (has_intent ? 1u : 0u);
         __syncwarp(); // every lane is done with this stage before the warp refills it (two iterations from now)
+        tx = ntx; ty = nty;
     }
     cp_async_wait<0>();
     if(A.collect_stats) {
