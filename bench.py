@@ -3,13 +3,21 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one apply() of the hot path on one 1920x1080 RGB frame of a synthetic CDnet-shaped sequence
-(BASELINE.json configs[3]).  `value` is measured with the frames already resident in HBM (lvb_apply_device), `e2e`
-through the reference-facing call (apply(img, fgmask, lr) with HOST buffers in pinned memory: H2D copy of the frame
-and D2H copy of the mask inside the timed region).  The timed region starts after the reference's own warm-up
-protocol (samples/changedet/src/main.cpp:56: learning-rate override 1 for the first frames, then T(x)).
-`--impl reference` times the CPU restatement of the reference (oracle/, reference-order mode: the reference itself
-needs OpenCV C++ and cannot be built in this image) on the host cores, one stream per thread.
+A "step" is one apply() of the hot path on one 1920x1080 RGB frame of a synthetic CDnet-shaped sequence (BASELINE.json configs[3],
+SURVEY.md 8(d): textured background, 10 % flickering region, moving objects covering 5-10 % of the frame, +-3 noise). The timed
+region starts after the reference's own warm-up protocol (samples/changedet/src/main.cpp:56: learning-rate override 1 up to frame
+50, then T(x)); frames 1..60 are never timed, on either arm.
+
+  value   frames already resident in HBM (lvb_apply_device), CUDA events on the instance's stream. The block of K steps is repeated
+          REPEATS times back to back; `value` comes from the MEDIAN block (max over ranks per block), all blocks are summarised.
+  e2e     the same metric through the reference-facing C ABI with HOST buffers (pinned): every step uploads its frame and reads its
+          mask back inside the timed region. Headline form: lvb_apply_stream (C loop over lvb_apply_async / lvb_sync_next, two frames
+          in flight); the strictly synchronous apply(img, fgmask, lr) is reported next to it.
+  roofline  dominant kernel (subsense_scan) timed per launch with CUDA events; algorithmic bytes from SURVEY 8(d) with the scan depth
+          and write rate measured on the device; DRAM traffic from the committed ncu capture (profiles/r02_kernels.json).
+  cpu_baseline / --impl reference   the reference's OWN sources (oracle/_ref: compiled unmodified against oracle/cvcompat), same
+          frames, same learning rates, same frame indices as the GPU arm (bootstrap frames untimed).
+  streams64_vga   BASELINE configs[4]: 64 independent 640x480 RGB streams per GPU, aggregate streams x fps.
 """
 import argparse
 import json
@@ -26,11 +34,14 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA initialises (see litiv_b200/api.py)
 
 W, H, C = 1920, 1080, 3
-BOOT_FRAMES = 60          # protocol frames before anything is timed (lr=1 for the first 50)
-N_UNIQUE = 24             # distinct synthetic frames kept resident and played ping-pong (continuous motion)
+BOOT_FRAMES = 60          # protocol frames before anything is timed (lr = 1 for the first 50)
+N_UNIQUE = 160            # distinct synthetic frames kept resident (1 GB) and played ping-pong: continuous motion whose period (318 frames) is far
+                          # longer than the life of a background sample, so moving objects are not absorbed by the model through repetition
+FG_AREA = 0.09            # objects sized to cover ~9 % of the frame before overlap / wrap-around (measured ground truth: ~7 %)
+REPEATS = 21              # timed blocks of K steps; the median block is reported
 METRIC = "subsense_1080p_mpx_per_s"
 WORKLOAD = "SuBSENSE 1920x1080 RGB single stream per GPU (BASELINE.json configs[3])"
-SCAN_DRAM_BYTES_NCU = 436.6e6  # per subsense_scan launch at this workload (profiles/r01h_scan_feedback_ncu.md)
+KERNEL_PROFILE = os.path.join(ROOT, "profiles", "r02_kernels.json")   # dram bytes per launch from the committed ncu --set full capture
 
 
 def peaks():
@@ -39,6 +50,16 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed capture of this build, or None"""
+    try:
+        d = json.load(open(KERNEL_PROFILE))
+        k = d["kernels"][kernel]
+        return float(k["dram_bytes_read"]) + float(k["dram_bytes_write"]), d.get("source", KERNEL_PROFILE)
+    except Exception:
+        return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -101,9 +122,28 @@ class ClockSampler(threading.Thread):
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
-def make_frames(seed, n):
+def pin_to_gpu_numa_node(local):
+    """bind this rank's threads (and therefore its pinned buffers, first touch) to the CPUs NVML reports as local to its GPU"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        phys = int(vis.split(",")[local]) if vis and all(v.strip().isdigit() for v in vis.split(",")) and local < len(vis.split(",")) else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return sorted(os.sched_getaffinity(0))
+
+
+def make_frames(seed, n, w=W, h=H):
     from litiv_b200.synth import SynthSequence
-    seq = SynthSequence(W, H, C, seed=seed)
+    seq = SynthSequence(w, h, C, seed=seed, fg_area=FG_AREA)
     return seq, [seq.frame(t) for t in range(n)]
 
 
@@ -118,102 +158,201 @@ def lr_for(t):
     return 1.0 if t <= 50 else 0.0
 
 
-def cpu_baseline(frames, seconds_budget=20.0):
-    """bounded sample of the same workload on ONE host core (the reference is single-threaded per stream)"""
+# --------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own sources (oracle/_ref), or the oracle port when that library is missing
+# --------------------------------------------------------------------------------------------------------------------
+def _cpu_engine():
+    from oracle import ref as R
+    if R.available():
+        try:
+            R.lib()
+            return "reference", lambda seed: R.Reference(1, seed=seed)
+        except Exception:
+            pass
     from oracle import oracle as O
-    o = O.Oracle(O.ALGO_SUBSENSE, mode=O.MODE_REFERENCE, seed=0)
-    o.initialize(frames[0])
-    n_done, t_in = 0, 0.0
-    t0 = time.time()
-    while time.time() - t0 < seconds_budget and n_done < 16:
-        k = n_done + 1
-        t, _ = o.apply_sequence(frames[pingpong(k, len(frames))][None], [lr_for(k)])
+    O.lib()
+    return "port", lambda seed: O.Oracle(O.ALGO_SUBSENSE, mode=O.MODE_REFERENCE, seed=seed)
+
+
+def _cpu_worker(seed, n_unique, first_timed, n_timed, start_evt, out_q):
+    """one 1080p stream on one host core: bootstrap frames untimed, then the SAME frame indices / learning rates the GPU arm times"""
+    kind, make = _cpu_engine()
+    _, frames = make_frames(4, n_unique)
+    algo = make(seed)
+    algo.initialize(frames[0])
+    for k in range(1, first_timed):
+        algo.apply(frames[pingpong(k, n_unique)], lr_for(k))
+    out_q.put(("ready", seed))
+    start_evt.wait()
+    t0 = time.perf_counter()
+    t_in = 0.0
+    for k in range(first_timed, first_timed + n_timed):
+        t, _ = algo.apply_sequence(frames[pingpong(k, n_unique)][None], [lr_for(k)])
         t_in += t
-        n_done += 1
-    return {"value": W * H * n_done / t_in / 1e6, "unit": "Mpx/s", "cores": 1, "kind": "port",
-            "sample": f"first {n_done} frames (lr=1 bootstrap phase) of the same 1080p sequence, oracle reference-order mode, 1 thread"}
+    out_q.put(("done", seed, time.perf_counter() - t0, t_in, kind))
+
+
+def run_cpu(n_streams, n_timed, first_timed=BOOT_FRAMES + 1, n_unique=None):
+    """n_streams independent 1080p streams, one PROCESS each (the reference's global rand() is per process: this is one lv::WorkerPool
+    thread per sequence without the lock contention of a shared rand()). Returns (Mpx/s over the timed phase, kind, wall seconds)."""
+    import multiprocessing as mp
+    if n_unique is None:
+        n_unique = min(N_UNIQUE, first_timed + n_timed)   # the frames the GPU arm plays at these indices (no wrap-around before N_UNIQUE)
+    ctx = mp.get_context("spawn")   # the GPU arm calls this after CUDA / NCCL are up: no fork of a process that holds a CUDA context
+    start_evt, q = ctx.Event(), ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(i, n_unique, first_timed, n_timed, start_evt, q)) for i in range(n_streams)]
+    [p.start() for p in procs]
+
+    def get():
+        while True:
+            try:
+                return q.get(timeout=5)
+            except Exception:
+                if any(p.exitcode not in (None, 0) for p in procs):
+                    [p.terminate() for p in procs]
+                    raise RuntimeError("a CPU-arm worker process died")
+    for _ in range(n_streams):
+        assert get()[0] == "ready"
+    t0 = time.perf_counter()
+    start_evt.set()
+    res = [get() for _ in range(n_streams)]
+    wall = time.perf_counter() - t0
+    [p.join() for p in procs]
+    kind = res[0][4]
+    return W * H * n_timed * n_streams / wall / 1e6, kind, wall
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement on the host cores, one 1080p stream per thread (lv::WorkerPool model)"""
+    """--impl reference: the reference's own CPU implementation on the host cores, one 1080p stream per core (the threading model of
+    apps/changedet/src/main.cpp:148-154), every stream through the bootstrap protocol first"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as O
-    O.lib()
-    ncores = os.cpu_count() or 1
-    nthreads = max(1, min(ncores, 16))
-    seq, frames = make_frames(4, 8)
-    oracles = []
-    for i in range(nthreads):
-        o = O.Oracle(O.ALGO_SUBSENSE, mode=O.MODE_REFERENCE, seed=i)
-        o.initialize(frames[0])
-        oracles.append(o)
-    counter = [0]
-
-    def step():
-        counter[0] += 1
-        k = counter[0]
-        f = frames[pingpong(k, len(frames))][None]
-        ths = [threading.Thread(target=o.apply_sequence, args=(f, [lr_for(k)])) for o in oracles]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.time()
-    for _ in range(args.steps):
-        step()
-    dt = time.time() - t0
-    val = W * H * nthreads * args.steps / dt / 1e6
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frame": [W, H, C], "cpu_streams": nthreads,
-                       "note": "same 1080p workload, one independent stream per host thread (the reference is single-threaded per stream)"},
-            "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": nthreads, "kind": "port",
-                             "sample": f"{args.steps} frames x {nthreads} independent 1080p streams, oracle reference-order mode (reference needs OpenCV C++: unbuildable here)"},
+    ncores = len(os.sched_getaffinity(0))
+    steps = max(1, min(args.steps, 40))   # a 1080p frame costs the reference ~0.3 s per core: bounded so that the run ends within minutes
+    val, kind, wall = run_cpu(ncores, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Mpx/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": wall / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame": [W, H, C], "cpu_streams": ncores, "boot_frames": BOOT_FRAMES, "fg_area_target": FG_AREA,
+                       "note": "same 1080p workload, same frame indices and learning rates as the GPU arm (60 bootstrap frames untimed), one "
+                               "independent stream per host core in its own process (the reference is single-threaded per stream)"},
+            "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": ncores, "kind": kind,
+                             "sample": f"frames {BOOT_FRAMES + 1}..{BOOT_FRAMES + steps} x {ncores} independent 1080p streams; "
+                                       + ("oracle/_ref = the reference's own sources compiled unmodified against oracle/cvcompat" if kind == "reference"
+                                          else "oracle reference-order port (oracle/_ref missing)")},
             "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------------------
+def bench_streams64(lv, torch, dev, local, rank, world, barrier, all_max):
+    """BASELINE configs[4]: 64 independent 640x480 RGB SuBSENSE streams on this GPU through lvb_apply_batch_device (device-resident)
+    and lvb_apply_batch (host frames in, host masks out); aggregate streams x fps over all ranks"""
+    w, h, ns, n_unique, rounds = 640, 480, 64, 48, 120
+    seqs = [make_frames(5000 + 100 * rank + i, n_unique, w, h)[1] for i in range(4)]     # 4 distinct sequences shared by the 64 streams
+    subs = [lv.BackgroundSubtractorSuBSENSE(device=local, seed=1000 * rank + i) for i in range(ns)]
+    pitch = (w * C + 127) // 128 * 128
+    d_frames = torch.zeros((4, n_unique, h, pitch), dtype=torch.uint8, device=dev)
+    for s in range(4):
+        for i, f in enumerate(seqs[s]):
+            d_frames[s, i, :, :w * C] = torch.from_numpy(f.reshape(h, w * C)).to(dev)
+    d_masks = torch.zeros((ns, h, w), dtype=torch.uint8, device=dev)
+    for i, s in enumerate(subs):
+        s.initialize(seqs[i % 4][0])
+    batch = lv.DeviceBatch(subs)
+    mp = [d_masks[i].data_ptr() for i in range(ns)]
+    k = [0]
+
+    def round_device():
+        k[0] += 1
+        j = pingpong(k[0], n_unique)
+        batch.apply([d_frames[i % 4, j].data_ptr() for i in range(ns)], pitch, mp, lr_for(k[0]))
+
+    for _ in range(BOOT_FRAMES + 5):
+        round_device()
+    for s in subs:
+        s.sync()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        round_device()
+    for s in subs:
+        s.sync()
+    torch.cuda.synchronize()
+    dev_s = time.perf_counter() - t0
+    # host frames in / host masks out
+    h_frames = [[lv.pinned_empty((h, w, C)) for _ in range(n_unique)] for _ in range(4)]
+    for s in range(4):
+        for i in range(n_unique):
+            h_frames[s][i][...] = seqs[s][i]
+    e2e_rounds = 40
+    barrier()
+    t0 = time.perf_counter()
+    for r in range(e2e_rounds):
+        j = pingpong(r, n_unique)
+        lv.apply_batch(subs, [h_frames[i % 4][j] for i in range(ns)], 0.0)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    dev_ms, e2e_ms = all_max([dev_s * 1e3, e2e_s * 1e3])
+    out = {"workload": "SuBSENSE 640x480 RGB, 64 independent streams per GPU (BASELINE.json configs[4])", "streams_per_gpu": ns,
+           "streams_x_fps": ns * rounds * world / (dev_ms * 1e-3), "mpx_per_s": ns * rounds * world * w * h / (dev_ms * 1e-3) / 1e6, "rounds": rounds,
+           "api": "lvb_apply_batch_device (device-resident frames, enqueue pool)",
+           "e2e_streams_x_fps": ns * e2e_rounds * world / (e2e_ms * 1e-3), "e2e_api": "lvb_apply_batch (host frames in, host masks out, pinned)",
+           "timing": "wall clock around enqueue + synchronize, max over ranks"}
+    del batch, subs
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streams64", action="store_true")
+    ap.add_argument("--repeats", type=int, default=REPEATS)
     args = ap.parse_args()
     if args.impl == "reference":
-        args.steps = min(args.steps, 12)
-        args.warmup = min(args.warmup, 2)
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
-
-    import torch
-    import litiv_b200 as lv
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpus = pin_to_gpu_numa_node(local)
+
+    import torch
+    import litiv_b200 as lv
+
     if not torch.cuda.is_available() or lv.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: litiv_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_max(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     seq, frames = make_frames(4 + 1000 * rank, N_UNIQUE)
-    dev = torch.device("cuda", local)
+    gt_share = float(np.mean([seq.frame(t, with_gt=True)[1].mean() for t in (5, 11, 17, 23)]))
     pitch = (W * C + 127) // 128 * 128
     d_frames = torch.zeros((N_UNIQUE, H, pitch), dtype=torch.uint8, device=dev)
     for i, f in enumerate(frames):
         d_frames[i, :, :W * C] = torch.from_numpy(f.reshape(H, W * C)).to(dev)
+    frames = frames[:32]     # the host copies are only needed for initialize() and the end-to-end legs
     d_mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
 
     sub = lv.BackgroundSubtractorSuBSENSE(device=local, seed=rank)
@@ -224,8 +363,7 @@ def main():
     def step_device():
         frame_no[0] += 1
         k = frame_no[0]
-        i = pingpong(k, N_UNIQUE)
-        sub.apply_device(d_frames[i].data_ptr(), pitch, d_mask.data_ptr(), lr_for(k))
+        sub.apply_device(d_frames[pingpong(k, N_UNIQUE)].data_ptr(), pitch, d_mask.data_ptr(), lr_for(k))
 
     for _ in range(BOOT_FRAMES):
         step_device()
@@ -235,29 +373,28 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     l0 = lv.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    R = max(1, args.repeats)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
     barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    sub.flush()          # the mask chain of the last frames runs on a side stream: order e1 behind it
-    e1.record(stream)
+    evs[0].record(stream)
+    for r in range(R):
+        for _ in range(args.steps):
+            step_device()
+        if r == R - 1:
+            sub.flush()      # the mask chain of the last frames runs on a side stream: order the closing event behind it
+        evs[r + 1].record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    launches = lv.kernel_launch_count() - l0
+    block_ms = [evs[r].elapsed_time(evs[r + 1]) for r in range(R)]
+    launches = (lv.kernel_launch_count() - l0) // R
     clocks = sampler.stop()
 
-    # dominant kernels: per-launch CUDA-event timing on the instance stream + the algorithmic bytes they moved. The reference's
-    # per-pixel loop is two kernels here (scan: LBSP + sample consensus; feedback: maps + stochastic updates), so SURVEY.md §8(d)'s
-    # per-pixel figure B_alg = 131 + 9(s+u) is split between them: B_scan = 27 + 9 s + 9 u_nb, B_fb = 104 + 9 u_own.
+    # dominant kernels: per-launch CUDA-event timing on the instance stream + the algorithmic bytes they moved
     sub.set_profile(True)
     sub.set_collect_stats(True)
     nprof = max(20, min(args.steps, 100))
-    t_prof0 = torch.cuda.Event(enable_timing=True); t_prof1 = torch.cuda.Event(enable_timing=True)
-    t_prof0.record(stream)
     for _ in range(nprof):
         step_device()
-    sub.flush(); t_prof1.record(stream)
+    sub.flush()
     torch.cuda.synchronize()
     pa_ms, pa_n = sub.get_profile()
     fb_ms, fb_n = sub.get_profile_feedback()
@@ -268,76 +405,98 @@ def main():
     roi_px = st["roi_px"] / max(st["frames"], 1)
     sbar = st["samples_scanned"] / max(st["roi_px"], 1)
     u = st["sample_writes"] / max(st["roi_px"], 1)
-    u_nb = u / 2.0                               # own-slot and neighbour writes are drawn with the same rate (1/LR each)
-    b_alg = 131.0 + 9.0 * (sbar + u)            # B_alg = B_fixed(110+7C) + 3C*(s + u), C=3
-    b_scan = 27.0 + 9.0 * sbar + 9.0 * u_nb     # input 3 + raw 1 + lastColor RW 6 + lastDesc RW 12 + R 4 + unstable 1 ; samples read ; nb writes
-    b_fb = b_alg - b_scan
+    fg_share = st["fg_px"] / max(st["roi_px"], 1)
+    # B_alg = B_fixed(110 + 7C) + 3C (s + u), C = 3. Split over the kernels that move the bytes: the scan
+    # kernel reads input 3 + R 4 + unstable 1, reads + writes lastColor 6 + lastDesc 12, writes raw 1, reads the first two samples of every
+    # pixel and stores every queued sample write (own + neighbour); the tail passes read the samples past the second; the rest is feedback
+    b_alg = 131.0 + 9.0 * (sbar + u)
+    b_scan = 27.0 + 9.0 * min(sbar, 2.0) + 9.0 * u
+    b_tail = 9.0 * max(sbar - 2.0, 0.0)
+    b_fb = b_alg - b_scan - b_tail
     hbm_peak, peak_src = peaks()
-    pa_avg_ms = pa_ms / max(pa_n, 1)
-    fb_avg_ms = fb_ms / max(fb_n, 1)
-    achieved = roi_px * b_scan / (pa_avg_ms * 1e-3) / 1e9 if pa_avg_ms > 0 else 0.0
-    fb_achieved = roi_px * b_fb / (fb_avg_ms * 1e-3) / 1e9 if fb_avg_ms > 0 else 0.0
+    pa_avg_ms, fb_avg_ms, tp_avg_ms = pa_ms / max(pa_n, 1), fb_ms / max(fb_n, 1), tp_ms / max(tp_n, 1)
 
-    # end to end through the reference-facing C-ABI call with HOST buffers (pinned): every step uploads its frame and reads its
-    # mask back inside the timed region. Headline: the asynchronous form (lvb_apply_async / lvb_sync_next: two frames in flight,
-    # the upload of frame k+1 overlaps the kernels of frame k - the `apply_cuda` async mode the reference's apps/changedet expects);
-    # the strictly synchronous apply(img, fgmask, lr) is timed too and reported next to it.
-    h_frames = [lv.pinned_empty((H, W, C)) for _ in range(4)]
-    for hf, f in zip(h_frames, frames[:4]):
+    def gbs(b, ms):
+        return roi_px * b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    achieved, fb_achieved, tp_achieved = gbs(b_scan, pa_avg_ms), gbs(b_fb, fb_avg_ms), gbs(b_tail, tp_avg_ms)
+
+    # end to end through the reference-facing C-ABI with HOST buffers (pinned): every step uploads its frame and reads its mask back
+    # inside the timed region
+    NH = 32
+    h_frames = [lv.pinned_empty((H, W, C)) for _ in range(NH)]
+    for hf, f in zip(h_frames, frames[:NH]):
         hf[...] = f
     h_masks = [lv.pinned_empty((H, W)) for _ in range(2)]
     e2e_steps = max(10, min(args.steps, 100))
+    e2e_rep = max(1, min(R, 7))
     for j in range(3):
-        sub.apply(h_frames[j % 4], 0.0, out=h_masks[0])
-    barrier()
-    t0 = time.perf_counter()
-    for j in range(e2e_steps):
-        sub.apply(h_frames[pingpong(j, 4)], 0.0, out=h_masks[0])
-    torch.cuda.synchronize()
-    sync_s = time.perf_counter() - t0
-    barrier()
-    t0 = time.perf_counter()
-    sub.apply_async(h_frames[0], 0.0, out=h_masks[0])
-    for j in range(1, e2e_steps):
-        sub.apply_async(h_frames[pingpong(j, 4)], 0.0, out=h_masks[j % 2])
-        sub.sync_next()
-    sub.sync_next()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+        sub.apply(h_frames[j % NH], 0.0, out=h_masks[0])
+    sync_blocks, e2e_blocks = [], []
+    for _ in range(e2e_rep):
+        barrier()
+        t0 = time.perf_counter()
+        for j in range(e2e_steps):
+            sub.apply(h_frames[pingpong(j, NH)], 0.0, out=h_masks[0])
+        torch.cuda.synchronize()
+        sync_blocks.append((time.perf_counter() - t0) * 1e3)
+    fr = [h_frames[pingpong(j, NH)] for j in range(e2e_steps)]
+    outs = [h_masks[j % 2] for j in range(e2e_steps)]
+    lrs = [0.0] * e2e_steps
+    for _ in range(e2e_rep):
+        barrier()
+        t0 = time.perf_counter()
+        sub.apply_stream(fr, lrs, outs)
+        torch.cuda.synchronize()
+        e2e_blocks.append((time.perf_counter() - t0) * 1e3)
 
-    t_max = torch.tensor([ms, e2e_s * 1e3, sync_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    ms_all, e2e_ms_all, sync_ms_all = float(t_max[0]), float(t_max[1]), float(t_max[2])
+    red = all_max(block_ms + sync_blocks + e2e_blocks)
+    block_all, sync_all, e2e_all = red[:R], red[R:R + e2e_rep], red[R + e2e_rep:]
+    ms_blk, sync_ms, e2e_ms = float(np.median(block_all)), float(np.median(sync_all)), float(np.median(e2e_all))
+
+    s64 = None
+    if not args.no_streams64:
+        del sub
+        s64 = bench_streams64(lv, torch, dev, local, rank, world, barrier, all_max)
 
     if rank == 0:
-        value = W * H * args.steps * world / (ms_all * 1e-3) / 1e6
-        e2e_val = W * H * e2e_steps * world / (e2e_ms_all * 1e-3) / 1e6
+        ms_step = ms_blk / args.steps
+        value = W * H * world / (ms_step * 1e-3) / 1e6
+        e2e_val = W * H * e2e_steps * world / (e2e_ms * 1e-3) / 1e6
+        traffic, traffic_src = ncu_traffic("subsense_scan")
         line = {
             "metric": METRIC, "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frame": [W, H, C],
-                       "streams_per_gpu": 1, "fps_per_stream": args.steps / (ms_all * 1e-3), "boot_frames": BOOT_FRAMES,
+            "config": {"workload": WORKLOAD, "frame": [W, H, C], "streams_per_gpu": 1, "fps_per_stream": 1e3 / ms_step, "boot_frames": BOOT_FRAMES,
+                       "fg_area_target": FG_AREA, "ground_truth_fg_share": gt_share, "classified_fg_share": fg_share,
+                       "timed_blocks": R, "block_ms_median": ms_blk, "block_ms_min": min(block_all), "block_ms_max": max(block_all),
+                       "timing": f"{R} back-to-back blocks of {args.steps} steps, CUDA events on the instance stream, per-block max over ranks, median block reported",
+                       "cpu_affinity": [cpus[0], cpus[-1], len(cpus)] if cpus else None,
                        "l2": "per-frame working set (sample model 1.66 GB + maps) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": W * H * C, "d2h_bytes_per_step": W * H, "steps": e2e_steps,
-                    "api": "lvb_apply_async(host frame, host mask, lr) + lvb_sync_next: two frames in flight, pinned host buffers",
-                    "synchronous_apply_value": W * H * e2e_steps * world / (sync_ms_all * 1e-3) / 1e6},
+            "e2e": {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": W * H * C, "d2h_bytes_per_step": W * H, "steps": e2e_steps, "blocks": e2e_rep,
+                    "api": "lvb_apply_stream(host frames, host masks, lrs): C loop over lvb_apply_async + lvb_sync_next, two frames in flight, pinned host buffers",
+                    "synchronous_apply_value": W * H * e2e_steps * world / (sync_ms * 1e-3) / 1e6,
+                    "synchronous_api": "lvb_apply(host frame, host mask, lr), one frame at a time"},
             "roofline": {"bound": "hbm", "kernel": "subsense_scan<3>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": SCAN_DRAM_BYTES_NCU,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r01h_scan_feedback_ncu.md)", "peak_source": peak_src, "avg_launch_ms": pa_avg_ms,
-                         "launches_timed": int(pa_n), "alg_bytes_per_px": b_scan, "scan_depth": sbar, "sample_writes_per_px": u,
-                         "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / (ms_all / args.steps),
-                         "tail_passes_avg_ms": tp_ms / max(tp_n, 1),
-                         "second_kernel": {"kernel": "subsense_feedback<3>", "avg_launch_ms": fb_avg_ms, "alg_bytes_per_px": b_fb,
-                                           "achieved": fb_achieved, "frac": fb_achieved / hbm_peak, "kernel_share_of_step": fb_avg_ms / (ms_all / args.steps)},
-                         "frame": {"alg_bytes_per_px": b_alg, "achieved": roi_px * b_alg / (ms_all / args.steps * 1e-3) / 1e9,
-                                   "frac": roi_px * b_alg / (ms_all / args.steps * 1e-3) / 1e9 / hbm_peak,
-                                   "note": "whole frame: SURVEY 8(d) B_alg x ROI px / ms_per_step (scan + feedback are on the critical path, the mask chain overlaps them)"}},
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "avg_launch_ms": pa_avg_ms, "launches_timed": int(pa_n), "alg_bytes_per_px": b_scan, "scan_depth": sbar,
+                         "sample_writes_per_px": u, "roi_px": roi_px, "kernel_share_of_step": pa_avg_ms / ms_step,
+                         "other_kernels": [
+                             {"kernel": "subsense_tail_pass (two passes)", "avg_launch_ms": tp_avg_ms, "alg_bytes_per_px": b_tail, "achieved": tp_achieved,
+                              "frac": tp_achieved / hbm_peak, "kernel_share_of_step": tp_avg_ms / ms_step},
+                             {"kernel": "subsense_feedback<3>", "avg_launch_ms": fb_avg_ms, "alg_bytes_per_px": b_fb, "achieved": fb_achieved,
+                              "frac": fb_achieved / hbm_peak, "kernel_share_of_step": fb_avg_ms / ms_step}],
+                         "frame": {"alg_bytes_per_px": b_alg, "achieved": gbs(b_alg, ms_step), "frac": gbs(b_alg, ms_step) / hbm_peak,
+                                   "note": "whole frame: SURVEY 8(d) B_alg x ROI px / ms_per_step (scan + tail passes + feedback are on the critical path, the mask chain overlaps them)"}},
         }
+        if s64 is not None:
+            line["streams64_vga"] = s64
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(frames)
+            v, kind, wall = run_cpu(1, 12)
+            line["cpu_baseline"] = {"value": v, "unit": "Mpx/s", "cores": 1, "kind": kind,
+                                    "sample": f"frames {BOOT_FRAMES + 1}..{BOOT_FRAMES + 12} of the same 1080p sequence (60 bootstrap frames untimed), one stream on one core; "
+                                              + ("oracle/_ref = the reference's own sources compiled unmodified" if kind == "reference" else "oracle reference-order port")}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

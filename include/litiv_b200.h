@@ -61,10 +61,14 @@ int lvb_apply(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning
 int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double learning_rate);
 int lvb_sync_next(lvb_handle h);
 int lvb_sync(lvb_handle h);
+/* one stream, n consecutive frames: lvb_apply_async / lvb_sync_next driven from a C loop (two frames in flight, masks delivered in order
+ * into fgmasks[i]); returns when the last mask has landed. The sequence loop of samples/changedet/src/main.cpp:33-74 in one call. */
+int lvb_apply_stream(lvb_handle h, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, const double* learning_rates);
 /* n independent streams, one frame each (the lv::WorkerPool pattern of apps/changedet/src/main.cpp:148-154) */
 int lvb_apply_batch(lvb_handle* hs, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, double learning_rate);
 /* the same for device-resident frames (rows of d_step bytes; d_fgmasks or its entries may be null): enqueues one frame per
- * instance from a small pool of host threads and returns without waiting (order later work with lvb_flush / lvb_sync) */
+ * instance from a small pool of host threads and returns without waiting (order later work with lvb_flush / lvb_sync).
+ * Both batch calls may be issued from several host threads at once (e.g. one per GPU): batches are serialised inside. */
 int lvb_apply_batch_device(lvb_handle* hs, const uint8_t* const* d_imgs, size_t d_step, uint8_t* const* d_fgmasks, int n, double learning_rate);
 /* device-resident variant: d_img rows of d_step bytes, d_fgmask W*H bytes (or null), asynchronous on the instance's stream */
 int lvb_apply_device(lvb_handle h, const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask_or_null, double learning_rate);

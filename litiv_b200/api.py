@@ -23,7 +23,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback", "lvb_get_profile_tail",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback", "lvb_get_profile_tail", "lvb_apply_stream",
     "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics", "lvb_apply_batch_device",
     "lvb_vibe_create", "lvb_vibe_destroy", "lvb_vibe_initialize", "lvb_vibe_apply", "lvb_vibe_apply_device", "lvb_vibe_sync",
     "lvb_vibe_get_background_image", "lvb_vibe_model", "lvb_vibe_set_collect_stats", "lvb_vibe_get_stats", "lvb_vibe_set_profile",
@@ -67,6 +67,7 @@ def lib():
         L.lvb_initialize.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
         L.lvb_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_apply_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        L.lvb_apply_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.lvb_sync.argtypes = [C.c_void_p]
         L.lvb_sync_next.argtypes = [C.c_void_p]
         L.lvb_flush.argtypes = [C.c_void_p]
@@ -218,18 +219,38 @@ class _BackgroundSubtractor:
             raise LitivError("input image type/size mismatch with initialization type/size")
         return np.ascontiguousarray(img)
 
+    def _check_out(self, out):
+        """caller-supplied mask buffer: the C ABI writes W*H bytes through the raw pointer, so it has to be exactly that"""
+        if out is None:
+            return np.empty(self.shape[:2], np.uint8)
+        if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != tuple(self.shape[:2]) or not out.flags.c_contiguous or not out.flags.writeable:
+            raise LitivError("output mask must be a writeable C-contiguous uint8 array of the frame size")
+        return out
+
     def apply(self, img, learningRate=None, out=None):
         img = self._check_img(img)
         lr = self.getDefaultLearningRate() if learningRate is None else learningRate
-        mask = np.empty(self.shape[:2], np.uint8) if out is None else out
+        mask = self._check_out(out)
         _chk(lib().lvb_apply(self._h, img.ctypes.data, mask.ctypes.data, float(lr)))
         return mask
+
+    def apply_stream(self, frames, learningRates, outs=None):
+        """n consecutive frames of one stream through lvb_apply_stream (C loop over lvb_apply_async / lvb_sync_next, two frames in
+        flight); returns the list of masks"""
+        imgs = [self._check_img(f) for f in frames]
+        masks = [self._check_out(None if outs is None else outs[i]) for i in range(len(imgs))]
+        n = len(imgs)
+        ip = (C.c_void_p * n)(*[f.ctypes.data for f in imgs])
+        mp = (C.c_void_p * n)(*[m.ctypes.data for m in masks])
+        lrs = (C.c_double * n)(*[float(x) for x in learningRates])
+        _chk(lib().lvb_apply_stream(self._h, ip, mp, n, lrs))
+        return masks
 
     def apply_async(self, img, learningRate=None, out=None):
         """enqueue one frame (up to two may be in flight); collect the masks in order with sync_next() / sync()"""
         img = self._check_img(img)
         lr = self.getDefaultLearningRate() if learningRate is None else learningRate
-        mask = np.empty(self.shape[:2], np.uint8) if out is None else out
+        mask = self._check_out(out)
         _chk(lib().lvb_apply_async(self._h, img.ctypes.data, mask.ctypes.data, float(lr)))
         self._inflight.append((mask, img))   # keeps the buffers alive until collected
 
@@ -283,7 +304,11 @@ class _BackgroundSubtractor:
         return out
 
     def setROI(self, roi):
-        roi = np.ascontiguousarray(roi, dtype=np.uint8)
+        if self.shape is None:
+            raise LitivError("algo & model must be initialized first")
+        roi = np.ascontiguousarray(roi)
+        if roi.dtype != np.uint8 or roi.shape != tuple(self.shape[:2]):
+            raise LitivError("provided ROI mat size must be equal to the init frame size, and its type must be 8UC1")
         _chk(lib().lvb_set_roi(self._h, roi.ctypes.data))
 
     def refreshModel(self, fSamplesRefreshFrac, bForceFGUpdate=False):

@@ -144,7 +144,7 @@ struct lvb_context {
     bool pending = false;
     // two-deep host pipeline (lvb_apply_async): slot k%2 = {device frame, device mask, pinned staging}; uploads on s_in, masks back on s_out
     struct Slot { uint8_t* d_img = nullptr; uint8_t* d_mask = nullptr; uint8_t* h_img = nullptr; uint8_t* h_mask = nullptr; CUtensorMap tmap; int use_tma = 0;
-                  cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr; uint8_t* user_mask = nullptr; bool direct = false, busy = false; };
+                  cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr, in_consumed = nullptr; uint8_t* user_mask = nullptr; bool direct = false, busy = false, used = false; };
     Slot slot[2];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaStream_t s_aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; // phase B runs beside the mask post-processing
@@ -443,6 +443,7 @@ void request_refresh(lvb_context* c, float frac, bool force) {
     CK(cudaStreamSynchronize(c->stream));
 }
 
+void sync(lvb_context* c);
 void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size_t step, const uint8_t* roi) {
     REQUIRE(img && W > 0 && H > 0 && (C == 1 || C == 3 || C == 4), "provided image for initialization must be non-empty, continuous, and of type 8UC1/3/4");
     REQUIRE(C != 4, "8UC4 input is accepted by the reference's initialize() but its apply() has no 4-channel path; use 8UC1 or 8UC3");
@@ -450,7 +451,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     REQUIRE(W <= 8192, "frame width above 8192 pixels is not supported");
     REQUIRE(step >= (size_t)W * C, "row step smaller than a row");
     CK(cudaSetDevice(c->device));
-    if(c->initialized) sync_streams(c);
+    if(c->initialized) sync(c);   // frames still in flight (lvb_apply_async) are collected, their masks delivered, before the buffers go
     // ROI (BackgroundSubtractionUtils.cpp:82-99, validateROI :28-36)
     std::vector<uint8_t> r((size_t)W * H, 255);
     if(roi) {
@@ -481,6 +482,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
     {   // pipeline slots: slot 0 aliases the buffers above, slot 1 gets its own
         lvb_context::Slot& a = c->slot[0]; lvb_context::Slot& b = c->slot[1];
         a.d_img = c->d_img; a.d_mask = c->d_mask; a.h_img = c->h_img; a.h_mask = c->h_mask; a.tmap = c->tmap_img; a.use_tma = c->use_tma;
+        a.used = b.used = false;
         b.d_img = dalloc<uint8_t>(c->stream, c->ipitch * H); b.d_mask = dalloc<uint8_t>(c->stream, (size_t)W * H);
         CK(cudaMallocHost((void**)&b.h_img, (size_t)W * H * C)); CK(cudaMallocHost((void**)&b.h_mask, (size_t)W * H));
         b.use_tma = make_image_tmap(&b.tmap, b.d_img, W, H, C, c->ipitch) ? 1 : 0;
@@ -492,6 +494,7 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         for(lvb_context::Slot& sl : c->slot) if(!sl.h2d_done) {
             CK(cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.in_consumed, cudaEventDisableTiming));
         }
     }
     if(c->algo != LVB_ALGO_PAWCS) {
@@ -836,11 +839,15 @@ void apply_async(lvb_context* c, const uint8_t* img, uint8_t* mask, double lr) {
     const size_t row = (size_t)c->W * c->C;
     const uint8_t* src = img;
     if(!is_pinned(img)) { std::memcpy(sl.h_img, img, row * c->H); src = sl.h_img; } // pageable -> pinned staging
-    // upload on s_in (overlaps the previous frame's kernels), kernels on the instance stream, mask back on s_out
+    // upload on s_in (overlaps the previous frame's kernels), kernels on the instance stream, mask back on s_out.
+    // The slot's device frame may still be read by the frame that used it two submissions ago (its motion-analysis kernel runs on the
+    // lowest-priority stream and is only awaited by that frame's feedback kernel, not by its mask): wait for "input consumed"
+    if(sl.used) CK(cudaStreamWaitEvent(c->s_in, sl.in_consumed, 0));
     CK(cudaMemcpy2DAsync(sl.d_img, c->ipitch, src, row, row, c->H, cudaMemcpyHostToDevice, c->s_in));
     CK(cudaEventRecord(sl.h2d_done, c->s_in));
     CK(cudaStreamWaitEvent(c->stream, sl.h2d_done, 0));
     enqueue_frame(c, sl.d_img, c->ipitch, sl.tmap, sl.use_tma, sl.d_mask, lr, sl.compute_done);
+    CK(cudaEventRecord(sl.in_consumed, c->stream)); sl.used = true; // behind every kernel of this frame that reads the input (the stream waited for the side streams' readers)
     CK(cudaStreamWaitEvent(c->s_out, sl.compute_done, 0));
     sl.direct = is_pinned(mask);
     CK(cudaMemcpyAsync(sl.direct ? mask : sl.h_mask, sl.d_mask, (size_t)c->W * c->H, cudaMemcpyDeviceToHost, c->s_out));
@@ -882,6 +889,9 @@ public:
     /// runs job(0..n-1), each index once, on the pool + the caller; rethrows the first failure
     void run(int n, const std::function<void(int)>& job) {
         if(n <= 0) return;
+        // one batch at a time: concurrent callers (e.g. one host thread per GPU) queue up here instead of overwriting each other's
+        // job descriptor while it is still being worked on
+        std::lock_guard<std::mutex> batch(run_mutex_);
         std::unique_lock<std::mutex> l(m_);
         job_ = &job; n_ = n; next_ = 0; done_ = 0; err_.clear(); ++gen_;
         l.unlock();
@@ -912,7 +922,7 @@ private:
         }
     }
     std::vector<std::thread> workers_;
-    std::mutex m_; std::condition_variable cv_, cv_done_;
+    std::mutex m_, run_mutex_; std::condition_variable cv_, cv_done_;
     const std::function<void(int)>* job_ = nullptr;
     int n_ = 0, next_ = 0, done_ = 0; uint64_t gen_ = 0; bool stop_ = false; std::string err_;
 };
@@ -1328,7 +1338,8 @@ int lvb_create(int algo, const lvb_params* params, int device, uint64_t seed, lv
     if(params) p = *params; else lvb_default_params(algo, &p);
     REQUIRE(p.n_samples > 0 && p.n_required <= p.n_samples, "algo cannot require more sample matches than sample count in model");
     REQUIRE(p.n_samples <= 255, "at most 255 samples per pixel are supported");
-    REQUIRE(p.color_dist_threshold > 0 || p.desc_dist_threshold > 0, "distance thresholds must be positive values");
+    REQUIRE(p.color_dist_threshold > 0 && p.desc_dist_threshold > 0, "distance thresholds must be positive values");
+    REQUIRE(algo == LVB_ALGO_PAWCS ? p.n_required >= 0 : p.n_required >= 1, "the number of required sample matches must be positive");
     REQUIRE(p.rel_lbsp_threshold >= 0, "relative threshold for LBSP features must be non-negative");
     REQUIRE(p.n_samples_for_moving_avgs >= 4, "moving average window must be >= 4");
     int ndev = lvb_device_count();
@@ -1359,7 +1370,7 @@ int lvb_destroy(lvb_handle h) {
     if(h->s_post) cudaStreamSynchronize(h->s_post);
     if(h->s_aux) cudaStreamSynchronize(h->s_aux);
     h->free_all();
-    for(auto& sl : h->slot) { if(sl.h2d_done) cudaEventDestroy(sl.h2d_done); if(sl.compute_done) cudaEventDestroy(sl.compute_done); if(sl.d2h_done) cudaEventDestroy(sl.d2h_done); }
+    for(auto& sl : h->slot) { if(sl.in_consumed) cudaEventDestroy(sl.in_consumed); if(sl.h2d_done) cudaEventDestroy(sl.h2d_done); if(sl.compute_done) cudaEventDestroy(sl.compute_done); if(sl.d2h_done) cudaEventDestroy(sl.d2h_done); }
     if(h->s_aux) cudaStreamDestroy(h->s_aux);
     if(h->s_post) cudaStreamDestroy(h->s_post);
     for(cudaEvent_t e : {h->ev_scan, h->ev_post, h->ev_ds, h->ev_mask}) if(e) cudaEventDestroy(e);
@@ -1393,6 +1404,17 @@ int lvb_apply_async(lvb_handle h, const uint8_t* img, uint8_t* fgmask, double lr
     LVB_TRY
     REQUIRE(h != nullptr, "null handle");
     apply_async(h, img, fgmask, lr);
+    LVB_CATCH
+}
+int lvb_apply_stream(lvb_handle h, const uint8_t* const* imgs, uint8_t* const* fgmasks, int n, const double* lrs) {
+    LVB_TRY
+    REQUIRE(h != nullptr && imgs && fgmasks && lrs && n >= 0, "bad stream arguments");
+    CK(cudaSetDevice(h->device));
+    for(int i = 0; i < n; ++i) {
+        apply_async(h, imgs[i], fgmasks[i], lrs[i]);   // upload of frame i overlaps the kernels of frame i-1
+        if(i > 0) REQUIRE(sync_next(h), "no frame in flight");
+    }
+    if(n > 0) REQUIRE(sync_next(h), "no frame in flight");
     LVB_CATCH
 }
 int lvb_sync(lvb_handle h) {
