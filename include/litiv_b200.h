@@ -82,6 +82,11 @@ int lvb_flush(lvb_handle h);
 /* getBackgroundImage / getBackgroundDescriptorsImage (SuBSENSE.cpp:614-649; LOBSTER.cpp:583-620; PAWCS.cpp:1525-1594) */
 int lvb_get_background_image(lvb_handle h, uint8_t* out);
 int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out);
+/* the same into DEVICE memory (W*H*C bytes, continuous): the display path of apps/changedet/src/main.cpp:304-307 passes a cv::cuda::GpuMat */
+int lvb_get_background_image_device(lvb_handle h, uint8_t* d_out);
+/* IIBackgroundSubtractor::validateROI (BackgroundSubtractionUtils.hpp:38, .cpp:28-36): clears every ROI pixel closer than `border` to the frame
+ * edge, in place (border = 2 = LBSP::PATCH_SIZE/2 for the three LBSP-based subtractors: BackgroundSubtractorLBSP.hpp, m_nROIBorderSize) */
+int lvb_validate_roi(uint8_t* roi, int width, int height, int border);
 /* refreshModel(fSamplesRefreshFrac, bForceFGUpdate) (SuBSENSE.cpp:80-105; LOBSTER.cpp:410-441) */
 int lvb_refresh_model(lvb_handle h, float frac, int force_fg);
 /* BackgroundSubtractorPAWCS::refreshModel(nBaseOccCount, fOccDecrFrac, bForceFGUpdate) (PAWCS.cpp:107-429) */

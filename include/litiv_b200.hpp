@@ -67,7 +67,12 @@ struct SubtractorBase {
     void apply(const ImageView& img, uint8_t* fgmask) { apply(img, fgmask, getDefaultLearningRate()); }
     void apply(const ImageView& img, std::vector<uint8_t>& fgmask, double learningRate) { fgmask.resize((size_t)m_rows * m_cols); apply(img, fgmask.data(), learningRate); }
     /// asynchronous pair (the `apply_cuda` async mode sketched in apps/changedet/src/main.cpp:274-282)
-    void apply_async(const ImageView& img, uint8_t* fgmask, double learningRate) { check(lvb_apply_async(m_h, img.data, fgmask, learningRate)); }
+    void apply_async(const ImageView& img, uint8_t* fgmask, double learningRate) {
+        if(img.rows != m_rows || img.cols != m_cols || img.channels != m_channels) throw Exception(m_rows ? "input image type/size mismatch with initialization type/size" : "algo & model must be initialized first");
+        if(!img.isContinuous()) throw Exception("input image data must be continuous");
+        if(!fgmask) throw Exception("output mask must be provided");
+        check(lvb_apply_async(m_h, img.data, fgmask, learningRate));
+    }
     void sync_next() { check(lvb_sync_next(m_h)); }
     void sync() { check(lvb_sync(m_h)); }
     /// order later work on the instance's CUDA stream behind the side-stream work of the frames enqueued so far
@@ -76,10 +81,21 @@ struct SubtractorBase {
     void apply_device(const uint8_t* d_img, size_t d_step, uint8_t* d_fgmask, double learningRate) { check(lvb_apply_device(m_h, d_img, d_step, d_fgmask, learningRate)); }
 
     virtual void getBackgroundImage(uint8_t* out) const { check(lvb_get_background_image(m_h, out)); }
+    /// getBackgroundImage into device memory (rows*cols*channels bytes): what the cv::cuda::GpuMat overload of apps/changedet/src/main.cpp:304-307 binds to
+    void getBackgroundImageDevice(uint8_t* d_out) const { check(lvb_get_background_image_device(m_h, d_out)); }
     virtual void getBackgroundDescriptorsImage(uint16_t* out) const { check(lvb_get_background_descriptors_image(m_h, out)); }
     virtual double getDefaultLearningRate() const { return lvb_default_learning_rate(m_algo); }
     virtual void setAutomaticModelReset(bool b) { check(lvb_set_auto_model_reset(m_h, b ? 1 : 0)); }
-    virtual void setROI(const ImageView& roi) { check(lvb_set_roi(m_h, roi.data)); }
+    /// IIBackgroundSubtractor::validateROI (BackgroundSubtractionUtils.cpp:28-36): clears the LBSP border (2 px) of a writable ROI in place
+    virtual void validateROI(uint8_t* roi, int rows, int cols) const {
+        if(!roi || rows <= 0 || cols <= 0) throw Exception("provided ROI must be non-empty and of type 8UC1");
+        check(lvb_validate_roi(roi, cols, rows, 2));
+    }
+    virtual void setROI(const ImageView& roi) {
+        if(roi.empty() || roi.channels != 1 || !roi.isContinuous()) throw Exception("provided ROI must be non-empty and of type 8UC1");
+        if(m_rows && (roi.rows != m_rows || roi.cols != m_cols)) throw Exception("provided ROI mat size must be equal to the init frame size, and its type must be 8UC1");
+        check(lvb_set_roi(m_h, roi.data));
+    }
     virtual std::vector<uint8_t> getROICopy() const { std::vector<uint8_t> r((size_t)m_rows * m_cols); check(lvb_get_roi(m_h, r.data())); return r; }
     void refreshModel(float fSamplesRefreshFrac, bool bForceFGUpdate = false) { check(lvb_refresh_model(m_h, fSamplesRefreshFrac, bForceFGUpdate ? 1 : 0)); }
     lvb_handle handle() const { return m_h; }
@@ -98,6 +114,12 @@ struct SubtractorBase {
         cv::Mat m = out.getMat();
         getBackgroundImage(m.data);
     }
+    void validateROI(cv::Mat& roi) const {
+        if(roi.empty() || roi.type() != CV_8UC1 || !roi.isContinuous()) throw Exception("provided ROI must be non-empty and of type 8UC1");
+        validateROI(roi.data, roi.rows, roi.cols);
+    }
+    void setROI(cv::Mat& roi) { validateROI(roi); setROI(ImageView(roi)); }
+    cv::Mat getROICopyMat() const { std::vector<uint8_t> r = getROICopy(); cv::Mat m(m_rows, m_cols, CV_8UC1); std::memcpy(m.data, r.data(), r.size()); return m; }
 #endif
 protected:
     SubtractorBase(int algo, const lvb_params& p, int device, uint64_t seed) : m_algo(algo) { check(lvb_create(algo, &p, device, seed, &m_h)); }

@@ -23,7 +23,7 @@ EXPORTS = [
     "lvb_get_background_descriptors_image", "lvb_refresh_model", "lvb_set_auto_model_reset", "lvb_get_roi", "lvb_set_roi",
     "lvb_default_learning_rate", "lvb_lbsp_compute", "lvb_state_size", "lvb_state_get", "lvb_state_set",
     "lvb_set_collect_stats", "lvb_get_stats", "lvb_kernel_launch_count", "lvb_stream", "lvb_set_profile", "lvb_get_profile",
-    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback", "lvb_get_profile_tail", "lvb_apply_stream",
+    "lvb_host_alloc", "lvb_host_free", "lvb_mask_op", "lvb_pawcs_refresh_model", "lvb_sync_next", "lvb_flush", "lvb_get_profile_feedback", "lvb_get_profile_tail", "lvb_apply_stream", "lvb_get_background_image_device", "lvb_validate_roi",
     "lvb_binclassif_accumulate", "lvb_binclassif", "lvb_binclassif_metrics", "lvb_apply_batch_device",
     "lvb_vibe_create", "lvb_vibe_destroy", "lvb_vibe_initialize", "lvb_vibe_apply", "lvb_vibe_apply_device", "lvb_vibe_sync",
     "lvb_vibe_get_background_image", "lvb_vibe_model", "lvb_vibe_set_collect_stats", "lvb_vibe_get_stats", "lvb_vibe_set_profile",
@@ -68,6 +68,8 @@ def lib():
         L.lvb_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_apply_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         L.lvb_apply_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.lvb_get_background_image_device.argtypes = [C.c_void_p, C.c_void_p]
+        L.lvb_validate_roi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.lvb_sync.argtypes = [C.c_void_p]
         L.lvb_sync_next.argtypes = [C.c_void_p]
         L.lvb_flush.argtypes = [C.c_void_p]
@@ -302,6 +304,17 @@ class _BackgroundSubtractor:
         out = np.empty((h, w), np.uint8)
         _chk(lib().lvb_get_roi(self._h, out.ctypes.data))
         return out
+
+    def validateROI(self, roi):
+        """IIBackgroundSubtractor::validateROI: clears the 2-px border of the (uint8, HxW) ROI in place and returns it"""
+        if not isinstance(roi, np.ndarray) or roi.dtype != np.uint8 or roi.ndim != 2 or roi.size == 0 or not roi.flags.c_contiguous or not roi.flags.writeable:
+            raise LitivError("provided ROI must be non-empty and of type 8UC1")
+        _chk(lib().lvb_validate_roi(roi.ctypes.data, roi.shape[1], roi.shape[0], 2))
+        return roi
+
+    def getBackgroundImageDevice(self, d_out_ptr):
+        """getBackgroundImage into device memory (raw CUDA pointer to W*H*C bytes), the cv::cuda::GpuMat form of the reference's display path"""
+        _chk(lib().lvb_get_background_image_device(self._h, d_out_ptr))
 
     def setROI(self, roi):
         if self.shape is None:

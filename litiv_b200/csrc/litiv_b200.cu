@@ -1266,7 +1266,7 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
     throw std::runtime_error("unknown state buffer: " + n);
 }
 
-void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
+void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc, bool out_on_device = false) {
     REQUIRE(c->initialized, "algo must be initialized first");
     CK(cudaSetDevice(c->device));
     sync_streams(c);
@@ -1274,6 +1274,7 @@ void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
     const size_t n = (size_t)c->W * c->H * c->C;
     uint8_t* dc = nullptr; uint16_t* dd = nullptr;
     if(out_color) dc = dalloc<uint8_t>(c->stream, n, false); else dd = dalloc<uint16_t>(c->stream, n, false);
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if(c->algo == LVB_ALGO_PAWCS) {
         const PawArgs A = paw_args(c, c->d_img, c->ipitch, c->use_tma, 0.0);
         if(c->C == 1) pawcs_background_kernel<1><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1); else pawcs_background_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(A, dc, dd, 1);
@@ -1282,7 +1283,7 @@ void get_bg_image(lvb_context* c, uint8_t* out_color, uint16_t* out_desc) {
     else background_image_kernel<3><<<tile_grid(c), dim3(32, 8), 0, c->stream>>>(c->bg, c->plane, c->P.n_samples, c->W, c->H, c->Wp, dc, dd);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
-    if(e == cudaSuccess) e = out_color ? cudaMemcpyAsync(out_color, dc, n, cudaMemcpyDeviceToHost, c->stream) : cudaMemcpyAsync(out_desc, dd, n * 2, cudaMemcpyDeviceToHost, c->stream);
+    if(e == cudaSuccess) e = out_color ? cudaMemcpyAsync(out_color, dc, n, kind, c->stream) : cudaMemcpyAsync(out_desc, dd, n * 2, kind, c->stream);
     if(e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(dc); cudaFree(dd);
     CK(e);
@@ -1422,6 +1423,11 @@ int lvb_sync(lvb_handle h) {
     REQUIRE(h != nullptr, "null handle");
     CK(cudaSetDevice(h->device));
     sync(h);
+    if(h->initialized && h->algo == LVB_ALGO_SUBSENSE) { // a model reset that gave up waiting for its final mask is an error, not a silent skip
+        FrameCtl f; get_ctl(h, f);
+        if(f.spin_timeout) { const uint32_t seq = f.spin_timeout; f.spin_timeout = 0; put_ctl(h, f);
+            throw std::runtime_error("the mask chain of frame " + std::to_string(seq) + " did not complete within the wait bound of the frame-level model reset (streams not progressing concurrently?); the reset was skipped"); }
+    }
     LVB_CATCH
 }
 int lvb_sync_next(lvb_handle h) {
@@ -1482,6 +1488,23 @@ int lvb_get_background_image(lvb_handle h, uint8_t* out) {
     LVB_TRY
     REQUIRE(h && out, "null argument");
     get_bg_image(h, out, nullptr);
+    LVB_CATCH
+}
+int lvb_get_background_image_device(lvb_handle h, uint8_t* d_out) {
+    LVB_TRY
+    REQUIRE(h && d_out, "null argument");
+    cudaPointerAttributes at;
+    REQUIRE(cudaPointerGetAttributes(&at, d_out) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged), "output must be a device pointer");
+    get_bg_image(h, d_out, nullptr, true);
+    LVB_CATCH
+}
+int lvb_validate_roi(uint8_t* roi, int width, int height, int border) {
+    LVB_TRY
+    // IIBackgroundSubtractor::validateROI (BackgroundSubtractionUtils.cpp:28-36): everything within `border` pixels of the frame edge is cleared
+    REQUIRE(roi != nullptr && width > 0 && height > 0, "provided ROI must be non-empty and of type 8UC1");
+    REQUIRE(border >= 0, "border size must be non-negative");
+    for(int y = 0; y < height; ++y) for(int x = 0; x < width; ++x)
+        if(x < border || y < border || x >= width - border || y >= height - border) roi[(size_t)y * width + x] = 0;
     LVB_CATCH
 }
 int lvb_get_background_descriptors_image(lvb_handle h, uint16_t* out) {

@@ -46,6 +46,8 @@ struct FrameCtl {
     uint32_t wl_count;         // SuBSENSE scan work-list: pixels still undecided after the two prefetched samples (reset by the frame tail)
     uint32_t wl2_count;        // ... and those still undecided after the first tail pass
     uint32_t wl_cursor, wl2_cursor;   // chunk cursors of the two tail passes (warps pull 32 entries at a time)
+    uint32_t spin_timeout;     // != 0: sequence number of a frame whose model reset gave up waiting for its final mask (see subsense_tail_warp)
+    uint32_t pad2[3];
 };
 
 // One background sample = one naturally aligned record (colour + descriptors): 16 bytes for 3 channels, 4 bytes for 1.

@@ -511,6 +511,9 @@ __global__ void __launch_bounds__(128, MINB) subsense_tail_pass(const TailPassAr
 
 /// frame tail (SuBSENSE.cpp:555-611): LUT +-1 adaptation, frame-level reset / learning-rate caps, next-frame factors.
 /// Executed by one warp: the last one of the last CTA of the feedback kernel.
+#ifndef LVB_SPIN_LIMIT
+#define LVB_SPIN_LIMIT 4000000u   // x 500 ns: the frame tail waits at most ~2 s for the frame's final mask before it drops a model reset
+#endif
 struct TailArgs {
     FrameCtl* ctl; uchar* lut;
     float rel; int lbsp_off; int min_color; int avg_samples; int N; int dsW, dsH;
@@ -564,9 +567,15 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
         // which the mask stream is still producing. This one warp (one resident CTA per instance, so any number of instances may
         // wait at once without starving the mask kernels they wait for) holds the feedback kernel open until the mask is complete;
         // the refresh kernel behind it in the stream then needs no synchronisation of its own.
+        // The wait is bounded (~2 s): it relies on the mask stream making progress beside this kernel, which holds whenever the mask
+        // chain was enqueued first (it always is, so even CUDA_LAUNCH_BLOCKING=1 finds the flag set), but is not a CUDA guarantee
+        // (time-sliced contexts). On a timeout the request is dropped and FrameCtl::spin_timeout names the frame: the host reports it
+        // as an error at its next synchronisation point instead of the device hanging.
         if(ctl->do_refresh && A.wait_seq) {
             volatile uint32_t* flag = &ctl->chain_done;
-            while((int32_t)(*flag - A.wait_seq) < 0) __nanosleep(500);
+            uint32_t spins = 0;
+            while((int32_t)(*flag - A.wait_seq) < 0 && spins < LVB_SPIN_LIMIT) { __nanosleep(500); ++spins; }
+            if((int32_t)(*flag - A.wait_seq) < 0) { ctl->do_refresh = 0; ctl->set_T_one = 0; ctl->spin_timeout = A.wait_seq; }
             __threadfence();
         }
     }

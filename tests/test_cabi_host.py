@@ -95,6 +95,20 @@ def test_cpp_shim_compiles_and_reports_errors(tmp_path):
     assert "LBSP invariants ok" in out.stdout, out.stdout
 
 
+def test_cpp_shim_opencv_branch_compiles(tmp_path):
+    """the LITIV_B200_WITH_OPENCV branch (classes derived from cv::BackgroundSubtractor, cv::Mat / InputArray / OutputArray signatures, validateROI,
+    setROI(cv::Mat&)) compiles and links; OpenCV C++ is absent from this image, so oracle/cvcompat stands in for its declarations"""
+    from litiv_b200 import build
+    exe = tmp_path / "shim_cv"
+    subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "cvcompat"),
+                           os.path.join(ROOT, "tests", "cpp_shim_opencv_compile.cpp"), os.path.join(ROOT, "oracle", "cvcompat", "cvcompat.cpp"),
+                           "-L" + os.path.dirname(build.SO), "-llitiv_b200", "-Wl,-rpath," + os.path.dirname(build.SO), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "no CPU fallback" in out.stdout or "ran on GPU" in out.stdout
+    assert "validateROI keeps 35 of 99" in out.stdout, out.stdout   # (11-4) x (9-4) inner pixels survive
+
+
 SHARD_SCRIPT = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
