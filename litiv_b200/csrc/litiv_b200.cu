@@ -59,6 +59,20 @@ bool make_image_tmap(CUtensorMap* map, const void* ptr, int W, int H, int C, siz
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+/// tensor map over a per-pixel plane [rows][width] of `esz`-byte elements (esz 1, 2, 4 or 8), box = box_w x box_h elements
+bool make_plane_tmap(CUtensorMap* map, const void* ptr, int esz, size_t width, size_t rows, int box_w, int box_h) {
+    std::memset(map, 0, sizeof(*map));
+    EncodeTiledFn fn = get_encode_fn();
+    if(!fn || ((uintptr_t)ptr & 15) || ((width * esz) & 15) || ((size_t)box_w * esz & 15) || box_w > 256 || box_h > 256) return false;
+    const CUtensorMapDataType dt = esz == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+    const cuuint64_t gdim[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)(width * esz)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // All device work of an instance goes to ITS stream (created non-blocking): the legacy default stream is never used,
 // because a pageable cudaMemcpy may return before its DMA has landed and a non-blocking stream would not wait for it.
 template<typename T> T* dalloc(cudaStream_t st, size_t n, bool zero = true) {
@@ -126,6 +140,8 @@ struct lvb_context {
     uint32_t sub_frame = 1;             // host mirror of FrameCtl::frame_idx (SuBSENSE; the final-mask EMA factors derive from it)
     uint32_t chain_seq = 0;             // frames enqueued (sequence number written to FrameCtl::chain_done by the mask stream)
     ushort* intents = nullptr;
+    ScanMaps scan_maps[2];              // SuBSENSE scan kernel: TMA maps of its per-pixel planes; [i] reads colour / descriptor plane pair i as "previous frame"
+    int scan_maps_idx = 0;              // which pair is the latest frame's (follows the last_color / last_color_alt swap)
     uint8_t* own_slot = nullptr;        // SuBSENSE: queued own-sample writes (slot per pixel, 0xFF none), applied by the next scan
     uint32_t* wl_ctx = nullptr; uint32_t* wl2_idx = nullptr; uint32_t wl_cap = 0;   // SuBSENSE scan work-list (subsense.cuh: WlCtx)
     uint8_t* lut = nullptr;
@@ -579,6 +595,24 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         std::vector<float> r1(c->plane, 1.0f);
         c->r_plane = dalloc<float>(c->stream, c->plane, false);
         h2d(c->stream, c->r_plane, r1.data(), r1.size() * sizeof(float));
+        {   // TMA maps of the planes the scan kernel stages (subsense.cuh: ScanTile). Pair i describes colour / descriptor planes i as "previous frame".
+            const int rec = (int)c->rec_bytes(), bge = rec >= 8 ? 8 : 4, IH = TILE_H + 2 * HALO;
+            const int bw_col = C == 1 ? ScanTile<1>::BW_COL : ScanTile<3>::BW_COL, bw_desc = C == 1 ? ScanTile<1>::BW_DESC : ScanTile<3>::BW_DESC;
+            const int bw_int = C == 1 ? ScanTile<1>::BW_INT : ScanTile<3>::BW_INT;
+            void* cols[2] = {c->last_color, c->last_color_alt}; void* descs[2] = {c->last_desc, c->last_desc_alt};
+            bool ok = true;
+            for(int i = 0; i < 2; ++i) {
+                ScanMaps& M = c->scan_maps[i];
+                ok = ok && make_plane_tmap(&M.pcol, cols[i], (int)c->col_bytes(), c->Wp, H, bw_col, IH);
+                ok = ok && make_plane_tmap(&M.pdesc, descs[i], (int)c->desc_bytes(), c->Wp, H, bw_desc, IH);
+                ok = ok && make_plane_tmap(&M.intents, c->intents, 2, c->Wp, H, bw_int, IH);
+                ok = ok && make_plane_tmap(&M.own, c->own_slot, 1, c->Wp, H, TILE_W, TILE_H);
+                ok = ok && make_plane_tmap(&M.rpl, c->r_plane, 4, c->Wp, H, TILE_W, TILE_H);
+                ok = ok && make_plane_tmap(&M.bg, c->bg, bge, (size_t)c->Wp * (rec / bge), (size_t)N * H, TILE_W * (rec / bge), TILE_H);
+            }
+            REQUIRE(ok, "cuTensorMapEncodeTiled failed for the SuBSENSE scan planes (driver without TMA support?)");
+            c->scan_maps_idx = 0;
+        }
     }
     if(c->algo == LVB_ALGO_PAWCS) paw_initialize(c, f, orig);
     c->median_k = f.median_k;
@@ -724,8 +758,14 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
             }
         }
         CK(cudaEventRecord(c->ev_ds, c->s_aux));
-        if(c->lut_small) { if(C == 1) subsense_scan<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_scan<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
-        else { if(C == 1) subsense_scan<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else subsense_scan<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        const ScanMaps& SM = c->scan_maps[c->scan_maps_idx];   // "previous frame" = the latest colour / descriptor planes
+        // multi-tile CTAs: every CTA walks ~3-4 tiles with the next tile's TMA boxes in flight. The grid is 4x what fits on the chip at once
+        // (measured, 1080p: 4 / 8 / 16 / 32 / 55 CTAs per SM -> 134 / 117 / 113 / 117 / 129 us; one tile per CTA: 127 us): a fully persistent
+        // grid loses to the tail effect of its static tile assignment, the oversubscribed one lets the hardware scheduler balance it
+        static const int scan_ctas = getenv("LVB_SCAN_CTAS") ? atoi(getenv("LVB_SCAN_CTAS")) : SCAN_GRID_CTAS_PER_SM;
+        const dim3 sg((unsigned)std::min<int>((int)(stage_grid(c).x * stage_grid(c).y), c->sm_count * scan_ctas));
+        if(c->lut_small) { if(C == 1) subsense_scan<1, true><<<sg, stage_block, 0, st>>>(A, tmap, SM); else subsense_scan<3, true><<<sg, stage_block, 0, st>>>(A, tmap, SM); }
+        else { if(C == 1) subsense_scan<1, false><<<sg, stage_block, 0, st>>>(A, tmap, SM); else subsense_scan<3, false><<<sg, stage_block, 0, st>>>(A, tmap, SM); }
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         mark(st, "scan");
@@ -792,7 +832,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         CK(cudaEventRecord(c->ev_post, sp)); c->post_pending = true; // recorded after feedback(k) is enqueued; covers the whole chain of frame k
         // the neighbour writes queued by feedback(k) ("phase B") are applied by scan(k+1), or by whoever needs the model first
         c->nb_seq = seq;
-        std::swap(c->last_color, c->last_color_alt); std::swap(c->last_desc, c->last_desc_alt);
+        std::swap(c->last_color, c->last_color_alt); std::swap(c->last_desc, c->last_desc_alt); c->scan_maps_idx ^= 1;
         c->ghost_idx ^= 1;
         std::swap(c->raw, c->raw_alt); std::swap(c->blinks, c->blinks_alt); std::swap(c->lastfg, c->lastfg_alt);
         c->fin_pending = c->sub_frame;

@@ -18,6 +18,10 @@ constexpr int TILE_W = 32, TILE_H = LVB_TILE_H, HALO = 2; // tile of the TMA-sta
 #define PHASEA_MIN_BLOCKS 4
 #endif
 constexpr int TILE_ROWS = TILE_H + 2 * HALO;
+#ifndef LVB_SCAN_GRID_CTAS
+#define LVB_SCAN_GRID_CTAS 16
+#endif
+constexpr int SCAN_GRID_CTAS_PER_SM = LVB_SCAN_GRID_CTAS; // grid of the multi-tile scan kernel, in CTAs per SM (4 are resident)
 constexpr uint32_t NO_INTENT = 0xFFFFu; // intents[] entry of a pixel that queued no neighbour write (valid codes are <= 0x18FF)
 // TMA boxes must start on a 16-byte boundary of the image row: the box starts TILE_SHIFT bytes before the halo's first
 // byte ((32k-2)*ch mod 16 is the same for every tile) and is TILE_SHIFT bytes wider.
@@ -127,159 +131,260 @@ constexpr int GHOST_ROWS = TILE_H + 2 * HALO;
 //   feedback (A2): D_min / T / v / R maps, stochastic own-sample write, queued neighbour write, frame tail (last CTA)
 // Hand-off (uint2 per pixel): x = minSum | minDesc << 16 ; y = good | lastL1 << 16 | lastHd << 24.
 
+/// Tensor maps of the per-pixel planes the scan kernel stages with TMA besides the input tile (built once per instance; the
+/// colour / descriptor planes are ping-ponged between frames, so there is a map per plane and the host passes the pair in use)
+struct ScanMaps { CUtensorMap pcol, pdesc, intents, own, rpl, bg; };
+/// shared-memory layout of one scan tile: every operand is its own TMA box (128-byte aligned start, rows of a 16-byte multiple)
+template<int CH> struct ScanTile {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    typedef typename Pack<CH>::Rec Rec;
+    static constexpr int IW = TILE_W + 2 * HALO, IH = TILE_H + 2 * HALO;                  // 36 x 12: tile + 2-px halo
+    // a TMA box has to START on a 16-byte boundary of the plane row (and span a 16-byte multiple): the halo'd boxes begin LP_x >= HALO
+    // elements left of the tile (x0 is a multiple of 32) and are BW_x elements wide; pixel x0 - HALO + k sits at column k + LP_x - HALO
+    static constexpr int lpad(int esz) { return esz >= 16 ? HALO : (HALO + 16 / esz - 1) / (16 / esz) * (16 / esz); }
+    static constexpr int bwid(int esz) { return esz >= 16 ? IW : (lpad(esz) + TILE_W + HALO + 16 / esz - 1) / (16 / esz) * (16 / esz); }
+    static constexpr int LP_COL = lpad(sizeof(Col)), LP_DESC = lpad(sizeof(Desc)), LP_INT = lpad(2);
+    static constexpr int BW_COL = bwid(sizeof(Col)), BW_DESC = bwid(sizeof(Desc)), BW_INT = bwid(2);
+    static constexpr int SH_COL = LP_COL - HALO, SH_DESC = LP_DESC - HALO, SH_INT = LP_INT - HALO;   // column shift of halo index k
+    static constexpr int BG_ELEM = sizeof(Rec) >= 8 ? 8 : 4;                              // the sample planes are described as u64 / u32 elements (a TMA box row holds <= 256 elements)
+    static constexpr int a128(int v) { return (v + 127) / 128 * 128; }
+    static constexpr int O_IMG = 0;
+    static constexpr int O_PCOL = a128(O_IMG + tile_pitch(CH) * TILE_ROWS);
+    static constexpr int O_PDESC = a128(O_PCOL + BW_COL * IH * (int)sizeof(Col));
+    static constexpr int O_INT = a128(O_PDESC + BW_DESC * IH * (int)sizeof(Desc));
+    static constexpr int O_OWN = a128(O_INT + BW_INT * IH * 2);
+    static constexpr int O_R = a128(O_OWN + TILE_W * TILE_H);
+    static constexpr int O_SMP = a128(O_R + TILE_W * TILE_H * 4);
+    static constexpr int BYTES = O_SMP + 2 * TILE_W * TILE_H * (int)sizeof(Rec);
+    static constexpr uint32_t TX_PLANES = (uint32_t)(BW_COL * IH * sizeof(Col) + BW_DESC * IH * sizeof(Desc) + TILE_W * TILE_H * 4 + 2 * TILE_W * TILE_H * sizeof(Rec));
+    static constexpr uint32_t TX_PENDING = (uint32_t)(BW_INT * IH * 2 + TILE_W * TILE_H);
+};
+
+/// Scan kernel: one thread per pixel of a 32x8 tile. EVERYTHING the tile reads (input tile + halo, previous colour / descriptor
+/// tiles + halo, R(x), the first two sample records of every pixel, and - when neighbour / own-sample writes of the previous frame are
+/// pending - the intent tile + halo and the own-slot tile) is staged by one elected thread with cp.async.bulk.tensor (TMA) behind a
+/// single mbarrier: no thread issues a global load in the prologue, and the queued sample writes find their source records in shared memory.
 template<int CH, bool T7>
 __global__ void __launch_bounds__(TILE_W * TILE_H, PHASEA_MIN_BLOCKS)
-subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
+subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ScanMaps M) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     typedef typename Pack<CH>::Rec Rec;
     typedef WlCtx<CH> X;
+    typedef ScanTile<CH> ST;
     constexpr int PITCH = tile_pitch(CH);
-    __shared__ __align__(128) uchar s_tile[PITCH * TILE_ROWS];
-    __shared__ __align__(8) uint64_t s_bar;
+    constexpr int IW = ST::IW, IH = ST::IH;
+    // PERSISTENT: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; the boxes of tile i+1 are in flight (second buffer, second
+    // mbarrier) while tile i is computed, so only the first tile of a CTA waits for DRAM
+    __shared__ __align__(128) uchar s_bufs[2][ST::BYTES];
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uchar s_lut[256];
     __shared__ uint32_t s_cnt[5];                 // nonzero | scanned | - | fg | warps done
-    // neighbour writes queued by the previous frame's feedback kernel ("phase B", folded in here): intent words of the tile + 2-px
-    // halo, and per target pixel the mask of 5x5 window positions whose source aims at it (bit = (dy+2)*5 + k = 24 - offset index)
-    constexpr int IW = TILE_W + 2 * HALO, IH = TILE_H + 2 * HALO;
-    __shared__ ushort s_int[IH][IW + 2];
-    __shared__ uint32_t s_hits[TILE_H][TILE_W];
+    // per target pixel: mask of the 5x5 window positions whose source aims a queued neighbour write at it (bit = (dy+2)*5 + k = 24 - offset index)
+    __shared__ uint32_t s_hits2[2][TILE_H][TILE_W];
 
-    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
     const int tid = threadIdx.y * TILE_W + threadIdx.x;
-    stage_tile_begin<CH>(s_tile, &s_bar, &tmap, A.use_tma, A.img, A.ipitch, A.W, A.H, x0, y0);
+    const int tiles_x = A.Wp / TILE_W, ntiles = tiles_x * ((A.H + TILE_H - 1) / TILE_H);
+    const int step_y = (int)gridDim.x / tiles_x, step_x = (int)gridDim.x - step_y * tiles_x;
+    auto issue = [&](int tx, int ty, int b) { // thread 0 only
+        uchar* buf = s_bufs[b];
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+        mbar_expect_tx(&s_bar[b], (A.use_tma ? (uint32_t)(PITCH * TILE_ROWS) : 0u) + ST::TX_PLANES + ST::TX_PENDING);
+        if(A.use_tma) tma_load_2d(buf + ST::O_IMG, &tmap, (x0 - HALO) * CH - tile_shift(CH), y0 - HALO, &s_bar[b]);
+        tma_load_2d(buf + ST::O_SMP, &M.bg, x0 * (int)(sizeof(Rec) / ST::BG_ELEM), y0, &s_bar[b]);                                  // sample 0
+        tma_load_2d(buf + ST::O_SMP + TILE_W * TILE_H * sizeof(Rec), &M.bg, x0 * (int)(sizeof(Rec) / ST::BG_ELEM), A.H + y0, &s_bar[b]);   // sample 1 (plane rows H..2H-1)
+        tma_load_2d(buf + ST::O_PCOL, &M.pcol, x0 - ST::LP_COL, y0 - HALO, &s_bar[b]);
+        tma_load_2d(buf + ST::O_PDESC, &M.pdesc, x0 - ST::LP_DESC, y0 - HALO, &s_bar[b]);
+        tma_load_2d(buf + ST::O_R, &M.rpl, x0, y0, &s_bar[b]);
+        tma_load_2d(buf + ST::O_INT, &M.intents, x0 - ST::LP_INT, y0 - HALO, &s_bar[b]);   // (staged even when nothing is pending: 1.2 KB, and the
+        tma_load_2d(buf + ST::O_OWN, &M.own, x0, y0, &s_bar[b]);                            //  `pending` flag's own load stays off the critical path)
+    };
+    int tile = blockIdx.x;
+    int tx = tile % tiles_x, ty = tile / tiles_x;
+    if(tid == 0) {
+        mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+        if(tile < ntiles) issue(tx, ty, 0);
+    }
     for(int i = tid; i < 256; i += TILE_W * TILE_H) s_lut[i] = A.lut[i];
     if(tid < 5) s_cnt[tid] = 0;
-    s_hits[threadIdx.y][threadIdx.x] = 0;
+    s_hits2[0][threadIdx.y][threadIdx.x] = 0;
     const bool pending = A.pending_seq != 0u && A.ctl->nb_applied_seq != A.pending_seq;
-
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    const bool in_img = (x < A.W) && (y < A.H);
-    const int wi = y * A.WW + (x >> 5);
-    const uint32_t lane_bit = 1u << (x & 31);
-    uint32_t w_roi = 0, w_unst = 0;
-    if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; }
-    const bool active = in_img && (w_roi & lane_bit);
-    const size_t pix = (size_t)y * A.Wp + x;
-
-    // every global load that does not depend on the input tile is issued before waiting for the TMA copy; the first
-    // REQ (=2) samples are always scanned, so they are fetched up front instead of one DRAM round trip each
-    float R = 0.f;
-    Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
-    Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
-    uint32_t own = 0xFFu; // own-sample write queued by the previous frame's feedback kernel (slot; 0xFF: none)
-    const Rec* bgr = (const Rec*)A.bg + pix;
-    if(in_img) { // not `active`: that would chain these loads behind the ROI word's round trip (the planes cover every pixel)
-        R = A.r_plane[pix];
-        if(pending) own = A.own_slot[pix];
-        lc = ((const Col*)A.prev_color)[pix];
-        ld = ((const Desc*)A.prev_desc)[pix];
-        { const Rec r0 = bgr[0]; pre_c0 = rec_col(r0); pre_d0 = rec_desc(r0); }
-        if(A.N > 1) { const Rec r1 = bgr[A.plane]; pre_c1 = rec_col(r1); pre_d1 = rec_desc(r1); }
-    }
-    if(pending) {
-        // scatter inside the CTA: every intent of the tile + halo marks its target pixel (smem atomics) instead of every target
-        // scanning its 25 possible sources
-        __syncthreads(); // s_hits cleared
-        // the tile row starts at x0-2 (even) and Wp is a multiple of 32: intents are fetched as aligned u32 pairs, one per thread
-        static_assert(IW % 2 == 0, "intent pairs");
-        for(int t = tid; t < (IW / 2) * IH; t += TILE_W * TILE_H) {
-            const int r = t / (IW / 2), cp = t - r * (IW / 2);
-            const int gx = x0 - HALO + 2 * cp, gy = y0 - HALO + r;
-            uint32_t pair = NO_INTENT | (NO_INTENT << 16);
-            if(gy >= 0 && gy < A.H && gx >= 0 && gx < A.Wp) pair = *(const uint32_t*)(A.intents + (size_t)gy * A.Wp + gx);
-#pragma unroll
-            for(int e = 0; e < 2; ++e) {
-                const int cc = 2 * cp + e;
-                uint32_t it = e ? (pair >> 16) : (pair & 0xFFFFu);
-                if(gx + e >= A.W) it = NO_INTENT; // padding columns of the plane are never written
-                s_int[r][cc] = (ushort)it;
-                if(it != NO_INTENT) {
-                    const int code = (int)(it >> 8), oy = code / 5, ox = code - oy * 5; // target = source + (ox-2, oy-2)
-                    const int tx = cc - 2 * HALO + ox, ty = r - 2 * HALO + oy;           // target inside the 32 x TILE_H core?
-                    if(tx >= 0 && tx < TILE_W && ty >= 0 && ty < TILE_H) atomicOr(&s_hits[ty][tx], 1u << (24 - code));
-                }
-            }
-        }
-    }
-    stage_tile_wait(&s_bar, A.use_tma);
-
-    // apply the pending neighbour writes aimed at this pixel, in raster order of their source (ascending bit index), before
-    // anything reads the model: own stores are visible to own loads, the two prefetched samples are patched in registers, and
-    // the cooperative scan tail (other lanes of this warp read this pixel's samples) runs behind a fence
-    if(pending && in_img) {
-        // the pixel's own stochastic update of the previous frame first (the reference writes it inside its pixel loop, the queued
-        // neighbour writes come after the loop and override it): the record is the previous frame's colour / descriptors of this
-        // very pixel, which the scan holds anyway. Doing the scattered store here, where it overlaps ~1000 instructions of
-        // arithmetic, costs nothing measurable; at the end of the feedback kernel it cost 27 us per 1080p frame.
-        if(own != 0xFFu) {
-#ifndef LVB_EXP_NO_OWN_WRITE
-            ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(lc, ld);
-#endif
-            if(own == 0u) { pre_c0 = lc; pre_d0 = ld; }
-            if(own == 1u) { pre_c1 = lc; pre_d1 = ld; }
-        }
-        uint32_t hits = s_hits[threadIdx.y][threadIdx.x];
-        const Col* pcol = (const Col*)A.prev_color;
-        const Desc* pdes = (const Desc*)A.prev_desc;
-        while(hits) {
-            const int i = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const int r = i / 5, k = i - r * 5;
-            const uint32_t slot = s_int[threadIdx.y + r][threadIdx.x + k] & 0xFFu;
-            const size_t q = (size_t)(y + r - 2) * A.Wp + (x - 2 + k);
-            const Col c_ = pcol[q]; const Desc d_ = pdes[q];
-#ifndef LVB_EXP_NO_NB_WRITE
-            ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(c_, d_);
-#endif
-            if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
-            if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
-        }
-    }
-
-    bool is_fg = false, nonzero = false;
     const uint32_t N = (uint32_t)A.N, REQ = (uint32_t)A.REQ;
     const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
-    uint32_t cur[CH], intra[CH];
-    uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
-    Col cur_pack = Col(); Desc intra_pack = Desc();
-    Lookup16 Lk[CH];
-    uint32_t thrC_ = 0, thrD_ = 0;
+    uint32_t nz_acc = 0, sc_acc = 0, fg_acc = 0;
+    __syncthreads();          // mbarriers initialised, tables staged, first hit plane cleared
 
-    if(active) {
-        const bool unstable_old = (w_unst & lane_bit) != 0;
-        // thresholds (SuBSENSE.cpp:222-223 / :355-359)
-        uint32_t thrC = (uint32_t)(__fsub_rn(__fmul_rn(R, (float)A.min_color), (float)(unstable_old ? 0 : A.min_color / 5)));
-        if(CH == 1) thrC >>= 1;
-        const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
+    for(int it = 0; tile < ntiles; ++it, tile += (int)gridDim.x) {
+        const int b = it & 1;
+        uchar* s_buf = s_bufs[b];
+        uchar* s_tile = s_buf + ST::O_IMG;
+        const Col (*s_pcol)[ST::BW_COL] = (const Col (*)[ST::BW_COL])(s_buf + ST::O_PCOL);
+        const Desc (*s_pdesc)[ST::BW_DESC] = (const Desc (*)[ST::BW_DESC])(s_buf + ST::O_PDESC);
+        const ushort (*s_int)[ST::BW_INT] = (const ushort (*)[ST::BW_INT])(s_buf + ST::O_INT);
+        const uchar (*s_own)[TILE_W] = (const uchar (*)[TILE_W])(s_buf + ST::O_OWN);
+        const float (*s_R)[TILE_W] = (const float (*)[TILE_W])(s_buf + ST::O_R);
+        const Rec (*s_smp)[TILE_H][TILE_W] = (const Rec (*)[TILE_H][TILE_W])(s_buf + ST::O_SMP);
+        uint32_t (*s_hits)[TILE_W] = s_hits2[b];
+        const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+        // next tile: its boxes go to the other buffer, which every thread finished reading before the barrier that closed the previous tile
+        int ntx = tx + step_x, nty = ty + step_y;
+        if(ntx >= tiles_x) { ntx -= tiles_x; ++nty; }
+        if(tid == 0 && tile + (int)gridDim.x < ntiles) issue(ntx, nty, b ^ 1);
+        if(!A.use_tma) { // frame pitch not TMA-compatible: cooperative byte copy of the input tile only
+            const int rowbytes = (TILE_W + 2 * HALO) * CH;
+            for(int i = tid; i < rowbytes * TILE_ROWS; i += TILE_W * TILE_H) {
+                const int r = i / rowbytes, bb = i - r * rowbytes;
+                const int gy = y0 - HALO + r, gb = (x0 - HALO) * CH + bb;
+                uchar v = 0;
+                if(gy >= 0 && gy < A.H && gb >= 0 && gb < A.W * CH) v = A.img[(size_t)gy * A.ipitch + gb];
+                s_tile[r * PITCH + tile_shift(CH) + bb] = v;
+            }
+            __syncthreads();
+        }
 
-        const int sy = threadIdx.y + HALO;
-        Lookup16 (&L)[CH] = Lk;
-        {
-            const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
+        const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+        const bool in_img = (x < A.W) && (y < A.H);
+        const int wi = y * A.WW + (x >> 5);
+        const uint32_t lane_bit = 1u << (x & 31);
+        uint32_t w_roi = 0, w_unst = 0;
+        if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; }
+        const bool active = in_img && (w_roi & lane_bit);
+        const size_t pix = (size_t)y * A.Wp + x;
+
+        mbar_wait(&s_bar[b], (uint32_t)((it >> 1) & 1));     // every TMA box of this tile has landed (async proxy -> visible after the phase flips)
+
+        if(pending) {
+            // scatter inside the CTA: every intent of the tile + halo marks its target pixel (smem atomics) instead of every target
+            // scanning its 25 possible sources. Out-of-image entries of the box are zero-filled by TMA: they are skipped by position.
+            static_assert(IW % 2 == 0, "intent pairs");
+            for(int t = tid; t < (IW / 2) * IH; t += TILE_W * TILE_H) {
+                const int r = t / (IW / 2), cp = t - r * (IW / 2);
+                const int gx = x0 - HALO + 2 * cp, gy = y0 - HALO + r;
+                if(gy < 0 || gy >= A.H) continue;
+                const uint32_t pair = *(const uint32_t*)&s_int[r][2 * cp + ST::SH_INT];
 #pragma unroll
-            for(int c = 0; c < CH; ++c) {
-                L[c] = lbsp_lookup_window<CH>(Wn, c);
-                cur[c] = win_center<CH>(Wn, c);
-                intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
+                for(int e = 0; e < 2; ++e) {
+                    const int cc = 2 * cp + e;
+                    const uint32_t itw = e ? (pair >> 16) : (pair & 0xFFFFu);
+                    if(gx + e < 0 || gx + e >= A.W || itw == NO_INTENT) continue; // padding columns of the plane are never written
+                    const int code = (int)(itw >> 8), oy = code / 5, ox = code - oy * 5; // target = source + (ox-2, oy-2)
+                    const int ttx = cc - 2 * HALO + ox, tty = r - 2 * HALO + oy;         // target inside the 32 x TILE_H core?
+                    if(ttx >= 0 && ttx < TILE_W && tty >= 0 && tty < TILE_H) atomicOr(&s_hits[tty][ttx], 1u << (24 - code));
+                }
+            }
+            __syncthreads();
+        }
+
+        float R = 0.f;
+        Col lc = Col(), pre_c0 = Col(), pre_c1 = Col();
+        Desc ld = Desc(), pre_d0 = Desc(), pre_d1 = Desc();
+        if(in_img) {
+            R = s_R[threadIdx.y][threadIdx.x];
+            lc = s_pcol[threadIdx.y + HALO][threadIdx.x + HALO + ST::SH_COL];
+            ld = s_pdesc[threadIdx.y + HALO][threadIdx.x + HALO + ST::SH_DESC];
+            { const Rec r0 = s_smp[0][threadIdx.y][threadIdx.x]; pre_c0 = rec_col(r0); pre_d0 = rec_desc(r0); }
+            if(A.N > 1) { const Rec r1 = s_smp[1][threadIdx.y][threadIdx.x]; pre_c1 = rec_col(r1); pre_d1 = rec_desc(r1); }
+        }
+        // apply the pending sample writes aimed at this pixel before anything reads the model: own stores are visible to own loads and
+        // the two staged samples are patched in registers
+        if(pending && in_img) {
+            // the pixel's own stochastic update of the previous frame first (the reference writes it inside its pixel loop, the queued
+            // neighbour writes come after the loop and override it): the record is the previous frame's colour / descriptors of this
+            // very pixel, which the scan holds anyway. Doing the scattered store here, where it overlaps ~1000 instructions of
+            // arithmetic, costs nothing measurable; at the end of the feedback kernel it cost 27 us per 1080p frame.
+            const uint32_t own = s_own[threadIdx.y][threadIdx.x];
+            if(own != 0xFFu) {
+#ifndef LVB_EXP_NO_OWN_WRITE
+                ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(lc, ld);
+#endif
+                if(own == 0u) { pre_c0 = lc; pre_d0 = ld; }
+                if(own == 1u) { pre_c1 = lc; pre_d1 = ld; }
+            }
+            // neighbour writes in raster order of their source (ascending bit index): the source's record comes from the staged tiles
+            uint32_t hits = s_hits[threadIdx.y][threadIdx.x];
+            while(hits) {
+                const int i = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int r = i / 5, k = i - r * 5;
+                const uint32_t slot = s_int[threadIdx.y + r][threadIdx.x + k + ST::SH_INT] & 0xFFu;
+                const Col c_ = s_pcol[threadIdx.y + r][threadIdx.x + k + ST::SH_COL]; const Desc d_ = s_pdesc[threadIdx.y + r][threadIdx.x + k + ST::SH_DESC];
+#ifndef LVB_EXP_NO_NB_WRITE
+                ((Rec*)A.bg)[(size_t)slot * A.plane + pix] = rec_make(c_, d_);
+#endif
+                if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
+                if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
             }
         }
-        if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
-        else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
+        s_hits2[b ^ 1][threadIdx.y][threadIdx.x] = 0; // the other hit plane, for the next tile (last read before the barrier that closed the previous tile)
 
-        // samples 0 and 1 were prefetched
-        uint32_t d_, s_;
-        if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
-        if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
-        thrC_ = thrC; thrD_ = thrD;
-    }
-    // still undecided after the two prefetched samples: hand the pixel to the tail passes (work-list append, one atomic per warp)
-    {
+        bool is_fg = false, nonzero = false;
+        uint32_t cur[CH], intra[CH];
+        uint32_t good = 0, s = 0, minDesc = descRange, minSum = colorRange;
+        Col cur_pack = Col(); Desc intra_pack = Desc();
+        Lookup16 Lk[CH];
+        uint32_t thrC_ = 0, thrD_ = 0;
+
+        if(active) {
+            const bool unstable_old = (w_unst & lane_bit) != 0;
+            // thresholds (SuBSENSE.cpp:222-223 / :355-359)
+            uint32_t thrC = (uint32_t)(__fsub_rn(__fmul_rn(R, (float)A.min_color), (float)(unstable_old ? 0 : A.min_color / 5)));
+            if(CH == 1) thrC >>= 1;
+            const uint32_t thrD = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unstable_old ? (uint32_t)A.desc_off : 0u);
+
+            const int sy = threadIdx.y + HALO;
+            Lookup16 (&L)[CH] = Lk;
+            {
+                const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
+#pragma unroll
+                for(int c = 0; c < CH; ++c) {
+                    L[c] = lbsp_lookup_window<CH>(Wn, c);
+                    cur[c] = win_center<CH>(Wn, c);
+                    intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
+                }
+            }
+            if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
+            else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
+
+            // samples 0 and 1 were staged with the tile
+            uint32_t d_, s_;
+            if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+            if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c1, pre_d1, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
+            thrC_ = thrC; thrD_ = thrD;
+        }
+        // still undecided after the two staged samples: the pixel goes to the tail passes. One atomic per warp reserves the work-list
+        // entries; it is issued HERE and its result used after the epilogue's stores, so the round trip overlaps them.
         const bool undecided = active && good < REQ && s < N;
         const uint32_t um = __ballot_sync(0xFFFFFFFFu, undecided);
-        if(um) {
-            uint32_t base = 0;
-            if(threadIdx.x == 0) base = atomicAdd(&A.ctl->wl_count, (uint32_t)__popc(um));
+        uint32_t base = 0;
+        if(um && threadIdx.x == 0) base = atomicAdd(&A.ctl->wl_count, (uint32_t)__popc(um));
+
+        if(active) {
+            is_fg = good < REQ && s >= N; // an undecided pixel (s < N) is classified by the tail passes, which set its raw bit
+            // distance to the previous frame (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
+            uint32_t lastL1 = 0, lastHd = 0;
+#pragma unroll
+            for(int c = 0; c < CH; ++c) {
+                const uint32_t bb = col_get(lc, c);
+                lastL1 += cur[c] > bb ? cur[c] - bb : bb - cur[c];
+                lastHd += __popc(desc_get(ld, c) ^ intra[c]);
+            }
+            if(CH != 1) lastL1 &= 0xFFu;
+            uint32_t pc = 0;
+#pragma unroll
+            for(int c = 0; c < CH; ++c) pc += __popc(intra[c]);
+            nonzero = pc >= (CH == 1 ? 2u : 4u);
+            A.hand[pix] = make_uint2(minSum | (minDesc << 16), good | (lastL1 << 16) | (lastHd << 24));
+            ((Col*)A.last_color)[pix] = cur_pack;
+            ((Desc*)A.last_desc)[pix] = intra_pack;
+        }
+        const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
+        const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
+        if(y < A.H && (x >> 5) < A.WW && threadIdx.x == 0) A.raw_bits[wi] = b_raw;
+        nz_acc += __popc(b_nz); fg_acc += __popc(b_raw); sc_acc += s;   // (nz / fg: identical on every lane; lane 0 publishes them)
+
+        if(um) { // work-list append
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if(undecided) {
                 const uint32_t e = base + (uint32_t)__popc(um & ((1u << threadIdx.x) - 1u));
@@ -299,44 +404,18 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
                 for(int v = 0; v < X::VEC; ++v) w[v] = make_uint4(f[4 * v], f[4 * v + 1], f[4 * v + 2], f[4 * v + 3]);
             }
         }
-    }
-    const uint32_t scanned = s;
-
-    if(active) {
-        is_fg = good < REQ && s >= N; // an undecided pixel (s < N) is classified by the tail passes, which set its raw bit
-        // distance to the previous frame (:254-255 / :396-397); the 3-channel L1 wraps in uint8 (quirk Q1)
-        uint32_t lastL1 = 0, lastHd = 0;
-#pragma unroll
-        for(int c = 0; c < CH; ++c) {
-            const uint32_t b = col_get(lc, c);
-            lastL1 += cur[c] > b ? cur[c] - b : b - cur[c];
-            lastHd += __popc(desc_get(ld, c) ^ intra[c]);
-        }
-        if(CH != 1) lastL1 &= 0xFFu;
-        uint32_t pc = 0;
-#pragma unroll
-        for(int c = 0; c < CH; ++c) pc += __popc(intra[c]);
-        nonzero = pc >= (CH == 1 ? 2u : 4u);
-        A.hand[pix] = make_uint2(minSum | (minDesc << 16), good | (lastL1 << 16) | (lastHd << 24));
-        ((Col*)A.last_color)[pix] = cur_pack;
-        ((Desc*)A.last_desc)[pix] = intra_pack;
+        tx = ntx; ty = nty;
+        __syncthreads(); // every thread is done with this tile's buffer and hit plane: they are refilled two / one iterations from now
     }
 
-    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, is_fg);
-    const uint32_t b_nz = __ballot_sync(0xFFFFFFFFu, nonzero);
-    if(y < A.H && (x >> 5) < A.WW && threadIdx.x == 0) {
-        A.raw_bits[wi] = b_raw;
-        atomicAdd(&s_cnt[0], __popc(b_nz));
-    }
     if(A.collect_stats) {
-        uint32_t sc = scanned;
 #pragma unroll
-        for(int o = 16; o > 0; o >>= 1) sc += __shfl_xor_sync(0xFFFFFFFFu, sc, o);
-        if(threadIdx.x == 0) { atomicAdd(&s_cnt[1], sc); atomicAdd(&s_cnt[3], __popc(b_raw)); }
+        for(int o = 16; o > 0; o >>= 1) sc_acc += __shfl_xor_sync(0xFFFFFFFFu, sc_acc, o);
     }
-    // no closing barrier: the last warp of the CTA to get here publishes the CTA's counters (the others retire at once
-    // instead of idling behind the slowest scan tail)
+    // the last warp of the CTA to get here publishes the CTA's counters (the loop's closing barrier keeps the warps within one tile of each other)
     if(threadIdx.x == 0) {
+        atomicAdd(&s_cnt[0], nz_acc);
+        if(A.collect_stats) { atomicAdd(&s_cnt[1], sc_acc); atomicAdd(&s_cnt[3], fg_acc); }
         __threadfence_block();
         if(atomicAdd(&s_cnt[4], 1u) == (uint32_t)TILE_H - 1u) {
             __threadfence_block();

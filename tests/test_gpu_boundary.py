@@ -25,7 +25,7 @@ def test_validate_roi_and_set_roi(lv, oracle):
     assert np.array_equal(v[2:-2, 2:-2], roi[2:-2, 2:-2])
     g.initialize(seq.frame(0), roi)
     got = g.getROICopy()
-    assert np.array_equal(got > 0, v > 0)
+    assert np.array_equal(got == 255, v == 255)   # (the final ROI also carries the 128-valued ring the reference adds around ROI borders)
     for t in range(1, 5):
         g.apply(seq.frame(t), 1.0)
     roi2 = np.full((h, w), 255, np.uint8)

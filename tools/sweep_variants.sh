@@ -19,12 +19,12 @@ else
     if [[ "$v" == *@* ]]; then envs=$(echo "${v#*@}" | tr ',' ' '); fi
     so=litiv_b200/liblitiv_b200.so
     [ "$name" != base ] && so=exp_build/lib_$name.so
-    out=$(env $envs LVB_SO=$PWD/$so python bench.py --steps 60 --warmup 5 --no-cpu-baseline 2>&1 | tail -1)
+    out=$(env $envs LVB_SO=$PWD/$so python bench.py --steps 40 --warmup 5 --repeats 5 --no-cpu-baseline --no-streams64 2>&1 | tail -1)
     echo "$v $(echo "$out" | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); r=d['roofline']
-    print('frame_ms=%.4f scan_ms=%.4f tail_ms=%.4f fb_ms=%.4f e2e=%.0f sync=%.0f frame_frac=%.3f sbar=%.2f' % (d['ms_per_step'], r['avg_launch_ms'], r.get('tail_passes_avg_ms', 0), r['second_kernel']['avg_launch_ms'], d['e2e']['value'], d['e2e']['synchronous_apply_value'], r['frame']['frac'], r['scan_depth']))
+    print('frame_ms=%.4f scan_ms=%.4f tail_ms=%.4f fb_ms=%.4f e2e=%.0f sync=%.0f frame_frac=%.3f sbar=%.2f' % (d['ms_per_step'], r['avg_launch_ms'], r['other_kernels'][0]['avg_launch_ms'], r['other_kernels'][1]['avg_launch_ms'], d['e2e']['value'], d['e2e']['synchronous_apply_value'], r['frame']['frac'], r['scan_depth']))
 except Exception as e: print('FAILED', e)
 ")"
   done
