@@ -780,8 +780,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
             const int npx = W * H;
             const int g1 = std::max(1, std::min(c->sm_count * TAIL1_MINB, (npx / 4 + 127) / 128)), g2 = std::max(1, std::min(c->sm_count * TAIL2_MINB, (npx / 8 + 127) / 128));
             TP.in_idx = nullptr; TP.in_count = &c->ctl->wl_count; TP.cursor = &c->ctl->wl_cursor; TP.out_idx = c->wl2_idx; TP.out_count = &c->ctl->wl2_count; TP.s_limit = TAIL_PASS1_LIMIT;
-            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
-            else { if(C == 1) subsense_tail_pass<1, false, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, 3, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
+            if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
+            else { if(C == 1) subsense_tail_pass<1, false, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
             LAUNCHED();
             TP.in_idx = c->wl2_idx; TP.in_count = &c->ctl->wl2_count; TP.cursor = &c->ctl->wl2_cursor; TP.out_idx = nullptr; TP.out_count = nullptr; TP.s_limit = 0xFFFFFFFFu;
             if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); }
@@ -825,7 +825,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         if(c->profile) { CK(cudaEventCreate(&fb0)); CK(cudaEventCreate(&fb1)); CK(cudaEventRecord(fb0, st)); }
         // persistent: sm_count x FB_CTAS_PER_SM CTAs walk the 32x8 tiles (one tile each when the frame has fewer tiles than that)
         const int fb_tiles = (c->Wp / 32) * ((H + FB_H - 1) / FB_H);
-        const dim3 fg((unsigned)std::min(fb_tiles, c->sm_count * FB_CTAS_PER_SM)), fb(32, FB_H);
+        static const int fb_ctas = getenv("LVB_FB_CTAS") ? atoi(getenv("LVB_FB_CTAS")) : FB_GRID_CTAS_PER_SM;
+        const dim3 fg((unsigned)std::min(fb_tiles, c->sm_count * fb_ctas)), fb(32, FB_H);
         if(C == 1) subsense_feedback<1><<<fg, fb, 0, st>>>(A, T); else subsense_feedback<3><<<fg, fb, 0, st>>>(A, T);
         LAUNCHED(); mark(st, "feedback");
         if(c->profile) { CK(cudaEventRecord(fb1, st)); c->prof2_events.push_back(fb0); c->prof2_events.push_back(fb1); }

@@ -442,6 +442,10 @@ constexpr uint32_t TAIL_PASS1_LIMIT = LVB_TAIL_PASS1_LIMIT; // pass 1 scans samp
 #ifndef LVB_TAIL1_MINB
 #define LVB_TAIL1_MINB 7
 #endif
+#ifndef LVB_TAIL1_B
+#define LVB_TAIL1_B 3
+#endif
+constexpr int TAIL1_B = LVB_TAIL1_B;   // pass 1: sample records per batch (in registers)
 #ifndef LVB_TAIL2_MINB
 #define LVB_TAIL2_MINB 4
 #endif
@@ -675,6 +679,10 @@ __device__ __noinline__ void subsense_tail_warp(const TailArgs& A, int lane) {
 #endif
 constexpr int FB_H = 8;                       // tile height (warps per CTA) of the feedback kernel
 constexpr int FB_CTAS_PER_SM = FEEDBACK_MIN_BLOCKS;
+#ifndef LVB_FB_GRID_CTAS
+#define LVB_FB_GRID_CTAS FEEDBACK_MIN_BLOCKS
+#endif
+constexpr int FB_GRID_CTAS_PER_SM = LVB_FB_GRID_CTAS;   // grid of the multi-tile feedback kernel, in CTAs per SM
 
 /// one 32x8 tile of per-pixel state staged in shared memory by cp.async, one block per warp row (so a warp only ever reads what
 /// its own lanes copied: the tile loop needs __syncwarp, never __syncthreads)
