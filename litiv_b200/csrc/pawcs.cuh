@@ -127,6 +127,9 @@ __device__ __forceinline__ int paw_find_gword(const PawArgs& A, const uint32_t* 
     return -1;
 }
 
+#ifndef PAW_CHUNK
+#define PAW_CHUNK 8   // words of the bubble pass whose counters are in flight together
+#endif
 #ifndef PAW_MIN_BLOCKS
 #define PAW_MIN_BLOCKS 4   // 64 registers with some spills, 4 CTAs per SM: the kernel is latency bound (2 / 3 / 4 / 5 / 6 -> 2.90 / 2.63 / 2.52 / 2.67 / 2.58 ms)
 #endif
@@ -261,7 +264,7 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
         }
         // the bubble pass continues over the rest of the dictionary (:1054-1065): only the counters are needed, CHUNK words
         // in flight at once (a swap exchanges positions i and i-1 in memory; words already in registers are at positions > i)
-        constexpr int CHUNK = 8;
+        constexpr int CHUNK = PAW_CHUNK;
         for(; i < A.NW; i += CHUNK) {
             uint32_t cf[CHUNK], cl[CHUNK], co[CHUNK];
 #pragma unroll
