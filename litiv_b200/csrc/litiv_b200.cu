@@ -174,7 +174,7 @@ struct lvb_context {
     // PAWCS
     int NW = 0, NG = 0, gW = 0, gH = 0;
     uint32_t paw_frame = 1;   // host mirror of FrameCtl::frame_idx (decides which frames run maintenance / the 500-frame check)
-    uint32_t *lw_first = nullptr, *lw_last = nullptr, *lw_occ = nullptr; void *lw_color = nullptr, *lw_desc = nullptr;
+    uint2* lw_key = nullptr; uint32_t* lw_first = nullptr; void *lw_color = nullptr, *lw_desc = nullptr;   // key = (occurrences, first + last), pawcs.cuh
     uint8_t* glut = nullptr; float *gmap = nullptr, *gmap_tmp = nullptr; GDict* gd = nullptr;
     uint32_t *roi255 = nullptr, *illum = nullptr, *did = nullptr, *dil = nullptr, *gop_bits = nullptr;
     uint4* paw_intents = nullptr; float* gop_w = nullptr; uint8_t* gop_g = nullptr; uint8_t* ds_roi = nullptr; uint8_t* bgimg = nullptr;
@@ -186,12 +186,12 @@ struct lvb_context {
 
     void free_all() {
         void* ptrs[] = {own_slot, wl_ctx, wl2_idx, eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
-                        lw_first, lw_last, lw_occ, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
+                        lw_first, lw_key, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
         own_slot = nullptr; wl_ctx = nullptr; wl2_idx = nullptr; wl_cap = 0;
         eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; fin_pending = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
-        lw_first = lw_last = lw_occ = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
+        lw_first = nullptr; lw_key = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
@@ -303,8 +303,7 @@ void paw_launch_refresh(lvb_context* c, const PawArgs& A, uint32_t frame_off) {
     LAUNCHED();
     if(c->C == 1) pawcs_refresh_global<1><<<1, 1024, 0, c->stream>>>(A, frame_off); else pawcs_refresh_global<3><<<1, 1024, 0, c->stream>>>(A, frame_off);
     LAUNCHED();
-    pawcs_glut_bubble<<<tg, tb, 0, c->stream>>>(A, 1); LAUNCHED();
-    pawcs_refresh_done<<<1, 1, 0, c->stream>>>(A); LAUNCHED();
+    pawcs_glut_bubble<<<tg, tb, 0, c->stream>>>(A, 1); LAUNCHED(); // its last CTA closes the request (epoch, refresh_req)
 }
 
 /// cv::resize(INTER_AREA) of a one-channel 8-bit image to (dw, dh), dw = W/8, dh = H/8: the exact 8x8 mean when both dimensions
@@ -374,23 +373,27 @@ void paw_initialize(lvb_context* c, FrameCtl& f, size_t orig) {
     if(c->median_k < 1) c->median_k = 1;
     if(C == 1) { c->NW = std::max(c->NW / 2, 1); c->NG = std::max(c->NG / 2, 1); }
     REQUIRE(c->NG <= PAW_MAXG, "too many global words");
+    REQUIRE(c->NW <= PAW_SPLIT_MAX_NW, "PAWCS: at most 56 local words per pixel are supported (the reference's default is 50)");
     c->ds_roi_count = 0; for(uint8_t v : dsr) c->ds_roi_count += v != 0;
     REQUIRE(c->ds_roi_count > 0, "downsampled ROI is empty");
     f.median_k = c->median_k; f.auto_reset = 1;
     const int NW = c->NW, NG = c->NG;
     cudaStream_t st = c->stream;
     c->lw_first = dalloc<uint32_t>(st, (size_t)NW * c->plane, false);
-    c->lw_last = dalloc<uint32_t>(st, (size_t)NW * c->plane);
-    c->lw_occ = dalloc<uint32_t>(st, (size_t)NW * c->plane);
+    c->lw_key = dalloc<uint2>(st, (size_t)NW * c->plane, false);
     c->lw_color = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->col_bytes());
     c->lw_desc = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->desc_bytes());
-    { std::vector<uint32_t> ones((size_t)NW * c->plane, 1u); h2d(st, c->lw_first, ones.data(), ones.size() * 4); } // (first=1,last=0): word not created yet
+    { std::vector<uint32_t> ones((size_t)NW * c->plane, 1u); h2d(st, c->lw_first, ones.data(), ones.size() * 4);   // (first=1,last=0,occ=0): word not created yet
+      std::vector<uint2> keys((size_t)NW * c->plane, make_uint2(0u, 1u)); h2d(st, c->lw_key, keys.data(), keys.size() * 8); }
     c->gmap = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
     c->gmap_tmp = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
     c->gd = dalloc<GDict>(st, 1);
     { std::vector<uint8_t> l((size_t)NG * c->plane); for(int i = 0; i < NG; ++i) std::fill(l.begin() + (size_t)i * c->plane, l.begin() + (size_t)(i + 1) * c->plane, (uint8_t)i);
       c->glut = dalloc<uint8_t>(st, l.size(), false); h2d(st, c->glut, l.data(), l.size()); }
     c->paw_intents = dalloc<uint4>(st, c->plane, false);
+    c->hand = dalloc<uint2>(st, c->plane);                 // split phase A: matched-word mask + flags per pixel
+    c->wl2_idx = dalloc<uint32_t>(st, c->plane, false);    // work-list of the pixels whose scan goes past PAW_K words
+    c->wl_ctx = dalloc<uint32_t>(st, c->plane * 2, false); // phase B work-list: (target pixel, remaining hits)
     c->gop_w = dalloc<float>(st, c->plane, false);
     c->gop_g = dalloc<uint8_t>(st, c->plane, false);
     c->ds_roi = dalloc<uint8_t>(st, dsr.size(), false); h2d(st, c->ds_roi, dsr.data(), dsr.size());
@@ -418,13 +421,14 @@ PawArgs paw_args(lvb_context* c, const uint8_t* img, size_t pitch, int use_tma, 
     PawArgs A{};
     A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.WW = c->WW; A.NW = c->NW; A.NG = c->NG; A.gW = c->gW; A.gH = c->gH; A.plane = c->plane;
     A.img = img; A.ipitch = pitch;
-    A.lw_first = c->lw_first; A.lw_last = c->lw_last; A.lw_occ = c->lw_occ; A.lw_color = c->lw_color; A.lw_desc = c->lw_desc;
+    A.lw_first = c->lw_first; A.lw_key = c->lw_key; A.lw_color = c->lw_color; A.lw_desc = c->lw_desc;
     A.glut = c->glut; A.gmap = c->gmap; A.gmap_tmp = c->gmap_tmp; A.gd = c->gd;
     A.maps = c->maps; A.fin = c->fin; A.last_color = c->last_color; A.last_desc = c->last_desc;
     A.roi_bits = c->roi_bits; A.roi255_bits = c->roi255; A.raw_bits = c->raw; A.unstable_bits = c->unstable; A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg;
     A.illum_bits = c->illum; A.did_bits = c->did; A.dil_bits = c->dil; A.dilinv_bits = c->dilinv;
     A.intent_bits = c->intent_bits; A.intents = c->paw_intents; A.bitplane = (size_t)c->H * c->WW;
     A.gop_bits = c->gop_bits; A.gop_w = c->gop_w; A.gop_g = c->gop_g;
+    A.hand = c->hand; A.wl = c->wl2_idx; A.wlB = (uint2*)c->wl_ctx;
     A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed; A.lr_fixed = lr_to_fixed(lr);
     A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold; A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.rel = c->P.rel_lbsp_threshold; A.lbsp_off = c->P.lbsp_threshold_offset; A.avg_samples = c->P.n_samples_for_moving_avgs;
@@ -658,27 +662,41 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     const int recalc = (frame % (grate << 5)) == 0, update = (frame % grate) == 0, check_model = (frame % PAW_BOOTSTRAP) == 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if(c->profile) { CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventRecord(ev0, st)); }
-    if(c->lut_small) { if(C == 1) pawcs_phaseA<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
-    else { if(C == 1) pawcs_phaseA<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_phaseA<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
-    LAUNCHED();
+    // instance stream : scan -> scan tail (work-list pixels, incl. their bubble pass) -> global dictionary -> mask chain -> ...
+    // auxiliary stream: bubble pass of the other pixels (beside the scan tail) -> phase B (needs both) -> phase B tail
+    {
+        const int tail_grid = c->sm_count * 8;
+        if(c->lut_small) { if(C == 1) pawcs_scan<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_scan<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        else { if(C == 1) pawcs_scan<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_scan<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        LAUNCHED();
+        CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+        if(C == 1) pawcs_bubble<1><<<tg, tb, 0, c->s_aux>>>(A); else pawcs_bubble<3><<<tg, tb, 0, c->s_aux>>>(A);
+        LAUNCHED();
+        if(c->lut_small) { if(C == 1) pawcs_scan_tail<1, true><<<tail_grid, PAW_TAIL_THREADS, 0, st>>>(A); else pawcs_scan_tail<3, true><<<tail_grid, PAW_TAIL_THREADS, 0, st>>>(A); }
+        else { if(C == 1) pawcs_scan_tail<1, false><<<tail_grid, PAW_TAIL_THREADS, 0, st>>>(A); else pawcs_scan_tail<3, false><<<tail_grid, PAW_TAIL_THREADS, 0, st>>>(A); }
+        LAUNCHED();
+        CK(cudaEventRecord(c->ev_scan, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_scan, 0));
+    }
     if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
-    // phase B only touches the local dictionaries: auxiliary stream, beside the global-dictionary and mask kernels
-    CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
     if(C == 1) pawcs_phaseB<1><<<tg, tb, 0, c->s_aux>>>(A); else pawcs_phaseB<3><<<tg, tb, 0, c->s_aux>>>(A);
     LAUNCHED();
+    if(C == 1) pawcs_phaseB_tail<1><<<c->sm_count * 8, PAW_TAIL_THREADS, 0, c->s_aux>>>(A); else pawcs_phaseB_tail<3><<<c->sm_count * 8, PAW_TAIL_THREADS, 0, c->s_aux>>>(A);
+    LAUNCHED();
     CK(cudaEventRecord(c->ev_join, c->s_aux));
-    pawcs_illum_kernel<<<wg, 256, 0, st>>>(A); LAUNCHED();
-    if(C == 1) pawcs_gword_replace<1><<<1, 1024, 0, st>>>(A); else pawcs_gword_replace<3><<<1, 1024, 0, st>>>(A);
+    if(C == 1) pawcs_gword_replace<1><<<16, 1024, 0, st>>>(A); else pawcs_gword_replace<3><<<16, 1024, 0, st>>>(A);
     LAUNCHED();
     pawcs_gword_apply<<<dim3((c->gW + 31) / 32, (c->gH + 7) / 8), 256, 0, st>>>(A); LAUNCHED();
-    pawcs_gword_finish<<<1, 128, 0, st>>>(A); LAUNCHED();
-    if(recalc || update) { pawcs_gword_maintain<<<c->NG, 1024, 0, st>>>(A, recalc, update); LAUNCHED(); }
-    pawcs_gdict_bubble<<<1, 1, 0, st>>>(A); LAUNCHED();
+    pawcs_gword_finish<<<1, 128, 0, st>>>(A, !(recalc || update)); LAUNCHED();
+    if(recalc || update) {
+        pawcs_gword_maintain<<<c->NG, 1024, 0, st>>>(A, recalc, update); LAUNCHED();
+        pawcs_gdict_bubble<<<1, 1, 0, st>>>(A); LAUNCHED();
+    }
     if(update) { pawcs_glut_bubble<<<tg, tb, 0, st>>>(A, 0); LAUNCHED(); }
     PostArgs P{};
     P.W = W; P.H = H; P.WW = c->WW; P.Wp = c->Wp; P.raw = c->raw; P.lastraw = c->lastraw; P.lastrawblink = c->lastrawblink; P.blinks = c->blinks;
     P.tmpA = c->tmpA; P.pre = c->pre; P.reach = c->reach; P.comb = c->comb; P.lastfg = c->lastfg; P.dilinv = c->dilinv; P.dil = c->dil;
     P.out_mask = d_mask_out; P.out_pitch = (size_t)W; P.fin = c->fin; P.fin_in = c->fin; P.ctl = c->ctl; P.median_k = c->median_k;
+    P.did = c->did; P.roi255 = c->roi255; P.roi = c->roi_bits; P.illum = c->illum; // + next frame's illumination mask
     pp_blink_close<<<wg, 256, 0, st>>>(P); LAUNCHED();
     {
         HoleArgs Hh{};
@@ -702,9 +720,11 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
         if(C == 1) pawcs_model_dist_kernel<1><<<(nds + 127) / 128, 128, 0, st>>>(A); else pawcs_model_dist_kernel<3><<<(nds + 127) / 128, 128, 0, st>>>(A);
         LAUNCHED();
     }
-    pawcs_tail1_kernel<<<1, 256, 0, st>>>(A, check_model); LAUNCHED();
-    if(check_model) paw_launch_refresh(c, A, 0);      // moving-camera mode switch (:1486-1499)
-    pawcs_tail2_kernel<<<1, 1, 0, st>>>(A); LAUNCHED();
+    pawcs_tail1_kernel<<<1, 256, 0, st>>>(A, check_model, !check_model); LAUNCHED();
+    if(check_model) {
+        paw_launch_refresh(c, A, 0);                  // moving-camera mode switch (:1486-1499)
+        pawcs_tail2_kernel<<<1, 1, 0, st>>>(A); LAUNCHED();
+    }
     paw_launch_refresh(c, A, 1);                      // frame-level model reset (:1503-1510)
     c->paw_frame = frame + 1;
     if(c->collect_stats) ++c->stat_frames;
@@ -1033,14 +1053,14 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
             return;
         }
         if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
-            std::vector<uint32_t> h(nw * c->plane), fi, la;
-            d2h(c->stream, h.data(), n == "lw_first" ? c->lw_first : n == "lw_last" ? c->lw_last : c->lw_occ, h.size() * 4);
-            if(n == "lw_first") { la.resize(h.size()); d2h(c->stream, la.data(), c->lw_last, la.size() * 4); }
+            std::vector<uint32_t> fi(nw * c->plane); std::vector<uint2> ke(nw * c->plane); // device layout: first, key = (occ, first + last)
+            d2h(c->stream, fi.data(), c->lw_first, fi.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
             uint32_t* o = (uint32_t*)out;
             for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) {
                 const size_t at = i * c->plane + (size_t)y * Wp + x;
-                uint32_t v = h[at];
-                if(n == "lw_first" && v == 1u && la[at] == 0u) v = 0; // "not created" marker (non-ROI pixels)
+                const uint32_t last = ke[at].y - fi[at];
+                uint32_t v = n == "lw_first" ? fi[at] : n == "lw_last" ? last : ke[at].x;
+                if(n == "lw_first" && v == 1u && last == 0u) v = 0; // "not created" marker (non-ROI pixels)
                 o[((size_t)y * W + x) * nw + i] = v;
             }
             return;
@@ -1171,12 +1191,17 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             return;
         }
         if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
-            uint32_t* dst = n == "lw_first" ? c->lw_first : n == "lw_last" ? c->lw_last : c->lw_occ;
-            std::vector<uint32_t> h(nw * c->plane);
-            d2h(c->stream, h.data(), dst, h.size() * 4);
+            std::vector<uint32_t> fi(nw * c->plane); std::vector<uint2> ke(nw * c->plane); // device layout: first, key = (occ, first + last)
+            d2h(c->stream, fi.data(), c->lw_first, fi.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
             const uint32_t* sI = (const uint32_t*)in;
-            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) h[i * c->plane + (size_t)y * Wp + x] = sI[((size_t)y * W + x) * nw + i];
-            h2d(c->stream, dst, h.data(), h.size() * 4);
+            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) {
+                const size_t at = i * c->plane + (size_t)y * Wp + x;
+                const uint32_t v = sI[((size_t)y * W + x) * nw + i], last = ke[at].y - fi[at];
+                if(n == "lw_first") { fi[at] = v; ke[at].y = v + last; }
+                else if(n == "lw_last") ke[at].y = fi[at] + v;
+                else ke[at].x = v;
+            }
+            h2d(c->stream, c->lw_first, fi.data(), fi.size() * 4); h2d(c->stream, c->lw_key, ke.data(), ke.size() * 8);
             return;
         }
         if(n == "lw_color") {

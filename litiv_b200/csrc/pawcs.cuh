@@ -10,10 +10,12 @@
 //       -> motion analysis + frame tail (LUT adaptation, reset / moving-camera logic on the device) -> conditional refresh.
 // The deterministic parallel semantics ("snapshot" semantics) are specified in DESIGN.md section 2.
 //
-// HBM layout (per stream; Wp = W rounded up to 32): local words are five sample-major SoA planes [NW][H][Wp]
-// (first u32, last u32, occurrences u32, colour u32 B,G,R,0, descriptors uint2): every frame every pixel re-weights all
-// NW words (12 B each, three coalesced 128-byte requests per warp and word), colour/descriptor are touched only while
-// the weight sum is below its threshold. Global words: GDict (small arrays) + occupancy maps [NG][H/2][W/2] f32 +
+// HBM layout (per stream; Wp = W rounded up to 32): local words are four sample-major SoA planes [NW][H][Wp]:
+// key uint2 (occurrences, first + last mod 2^32), first u32, colour u32 B,G,R,0, descriptors uint2. The weight of a word,
+// occ / ((last - first) + 2 (frame - last) + offset) = occ / (2 frame + offset - (first + last)), only needs the key, and every
+// frame every pixel re-weights all NW words: 8 B per word in one 64-bit load instead of three 32-bit planes. `first` is touched
+// only when a word is matched (last = frame  =>  key.y = first + frame), created or moved; colour / descriptor only while the
+// weight sum is below its threshold. State export / import converts to and from (first, last, occurrences). Global words: GDict (small arrays) + occupancy maps [NG][H/2][W/2] f32 +
 // per-pixel sort LUT [NG][H][Wp] u8.
 #pragma once
 #include "subsense.cuh"
@@ -39,13 +41,15 @@ struct GDict { // global dictionary (indexed by word identity) + the PAWCS frame
     long long motion_acc, model_l1_acc, model_cd_acc;
     uint32_t refresh_req, refresh_base_occ, refresh_force, set_T_one; float refresh_decr;
     uint32_t ds_roi_count, nST, tail_gate;
+    uint32_t wlB_count;                // phase B work-list (reset by the frame tail)
+    uint32_t refresh_ticket;           // CTAs of the conditional refresh's last kernel that are done
 };
 
 struct PawArgs {
     int W, H, Wp, WW, NW, NG, gW, gH;
     size_t plane;
     const uchar* img; size_t ipitch;
-    uint32_t* lw_first; uint32_t* lw_last; uint32_t* lw_occ; void* lw_color; void* lw_desc;
+    uint2* lw_key; uint32_t* lw_first; void* lw_color; void* lw_desc;   // key = (occurrences, first + last)
     uchar* glut; float* gmap; float* gmap_tmp; GDict* gd;
     float4* maps; float2* fin; void* last_color; void* last_desc;
     const uint32_t* roi_bits; const uint32_t* roi255_bits;
@@ -53,6 +57,8 @@ struct PawArgs {
     uint32_t* illum_bits; uint32_t* did_bits; const uint32_t* dil_bits; const uint32_t* dilinv_bits;
     uint32_t* intent_bits; uint4* intents; size_t bitplane;
     uint32_t* gop_bits; float* gop_w; uchar* gop_g;
+    uint2* hand; uint32_t* wl;   // phase A: scan -> bubble hand-off, work-list of the pixels whose scan goes past PAW_K words
+    uint2* wlB;                  // phase B: (target pixel, remaining hits) of the targets whose current hit walks past PAWB_K words
     uchar* lut; FrameCtl* ctl;
     uint64_t seed; uint32_t lr_fixed; int min_color, desc_off;
     int use_tma, collect_stats;
@@ -60,37 +66,61 @@ struct PawArgs {
     const uchar* ds_roi; float* dsLT; float* dsST; uchar* bgimg; // frame-level analysis
 };
 
-__device__ __forceinline__ float paw_weight(uint32_t first, uint32_t last, uint32_t occ, uint32_t frame, uint32_t off) { // PAWCS.cpp:1596-1598
-    return __fdiv_rn((float)occ, (float)((last - first) + (frame - last) * 2u + off));
-}
+/// PAWCS.cpp:1596-1598: occ / ((last - first) + (frame - last) * 2 + offset), all uint32 (wrapping) = occ / (K - (first + last)), K = 2 frame + offset
+__device__ __forceinline__ uint32_t paw_wk(uint32_t frame, uint32_t off) { return frame * 2u + off; }
+__device__ __forceinline__ float paw_weight(const uint2 key, uint32_t K) { return __fdiv_rn((float)key.x, (float)(K - key.y)); }
 __device__ __forceinline__ uint32_t paw_hdist(const uint2& a, const uint2& b) { return __popc(a.x ^ b.x) + __popc((a.y ^ b.y) & 0xFFFFu); }
 __device__ __forceinline__ uint32_t paw_hdist(const ushort& a, const ushort& b) { return __popc((uint32_t)(a ^ b)); }
 __device__ __forceinline__ uint32_t paw_bits(const uint2& a) { return __popc(a.x) + __popc(a.y & 0xFFFFu); }
 __device__ __forceinline__ uint32_t paw_bits(const ushort& a) { return __popc((uint32_t)a); }
 
-/// colour distances of math.hpp: L1dist (u8-wrapping for 3 channels, Q1), cdist :474-496, cmixdist :596-605
+/// colour distances of math.hpp: L1dist (u8-wrapping for 3 channels, Q1), cdist :474-496, cmixdist :596-605.
+/// Split in two so that callers can stop after the cheap part: cmixdist = (L1 >> 1) + 4 cdist (3 channels) can only be within a
+/// threshold if L1 >> 1 is.
 template<int CH>
-__device__ __forceinline__ uint32_t paw_color_dist(uint32_t cur, uint32_t bg, uint32_t& l1, uint32_t& cd) {
-    if(CH == 1) { const uint32_t a = cur & 0xFFu, b = bg & 0xFFu; l1 = a > b ? a - b : b - a; cd = 0; return l1; }
+__device__ __forceinline__ uint32_t paw_l1(uint32_t cur, uint32_t bg) {
+    if(CH == 1) { const uint32_t a = cur & 0xFFu, b = bg & 0xFFu; return a > b ? a - b : b - a; }
+    return __vsadu4(cur & 0x00FFFFFFu, bg & 0x00FFFFFFu) & 0xFFu; // sum of the three byte differences, wrapped like the reference's uchar accumulator
+}
+/// floor(sqrt(n)) for n < 2^24: == (uint32_t)sqrtf((float)n) of the reference (a correctly rounded root of an integer below 2^24 never
+/// rounds up to the next integer), from the approximate root and one correction step
+__device__ __forceinline__ uint32_t paw_isqrt(uint32_t n) {
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"((float)n));
+    uint32_t r = (uint32_t)s;
+    if(r * r > n) --r; else if((r + 1u) * (r + 1u) <= n) ++r;
+    return r;
+}
+__device__ __forceinline__ uint32_t paw_cdist3(uint32_t cur, uint32_t bg) { // math.hpp:474-496 for uchar triplets
     const uint32_t c0 = cur & 0xFFu, c1 = (cur >> 8) & 0xFFu, c2 = (cur >> 16) & 0xFFu;
     const uint32_t b0 = bg & 0xFFu, b1 = (bg >> 8) & 0xFFu, b2 = (bg >> 16) & 0xFFu;
-    l1 = (__usad(c0, b0, 0u) + __usad(c1, b1, 0u) + __usad(c2, b2, 0u)) & 0xFFu;
     const bool nonconst = (c1 != c0) || (b1 != b0) || (c2 != c1) || (b2 != b1);
-    const bool nonnull = (c0 != b0) || (c1 != b1) || (c2 != b2);
-    cd = 0;
-    if(nonconst && nonnull) {
-        const uint32_t cs = c0 * c0 + c1 * c1 + c2 * c2, bs = b0 * b0 + b1 * b1 + b2 * b2, mix = c0 * b0 + c1 * b1 + c2 * b2;
-        // floor(mix^2 / max(bs,1)) exactly, without a 64-bit or double division: q <= cs < 2^18 (Cauchy-Schwarz), so a single-
-        // precision estimate (relative error < 2^-21) is off by at most one; the 64-bit remainder fixes it
-        const unsigned long long m2 = (unsigned long long)mix * mix;
-        const uint32_t d = max(bs, 1u);
-        uint32_t q = (uint32_t)__fdividef(__fmul_rn((float)mix, (float)mix), (float)d);
-        long long r = (long long)m2 - (long long)((unsigned long long)q * d);
-        while(r < 0) { --q; r += d; }
-        while(r >= (long long)d) { ++q; r -= d; }
-        cd = (uint32_t)__fsqrt_rn((float)(cs - q));
-    }
+    const bool nonnull = ((cur ^ bg) & 0x00FFFFFFu) != 0u;
+    if(!(nonconst && nonnull)) return 0u;
+    const uint32_t cs = c0 * c0 + c1 * c1 + c2 * c2, bs = b0 * b0 + b1 * b1 + b2 * b2, mix = c0 * b0 + c1 * b1 + c2 * b2;
+    // floor(mix^2 / max(bs,1)) exactly, without a 64-bit or double division: q <= cs < 2^18 (Cauchy-Schwarz), so a single-
+    // precision estimate (relative error < 2^-21) is off by at most one; the remainder (|r| < 2^19, so 32-bit wrapping arithmetic
+    // holds it exactly although mix^2 does not fit) fixes it
+    const uint32_t d = max(bs, 1u);
+    uint32_t q = (uint32_t)__fdividef(__fmul_rn((float)mix, (float)mix), (float)d);
+    const int r = (int)(mix * mix - q * d);
+    if(r < 0) --q; else if(r >= (int)d) ++q;
+    return paw_isqrt(cs - q);
+}
+template<int CH>
+__device__ __forceinline__ uint32_t paw_color_dist(uint32_t cur, uint32_t bg, uint32_t& l1, uint32_t& cd) {
+    l1 = paw_l1<CH>(cur, bg);
+    if(CH == 1) { cd = 0; return l1; }
+    cd = paw_cdist3(cur, bg);
     return (l1 >> 1) + cd * 4u;
+}
+/// cmixdist(cur, bg) <= thr, the expensive part only when the cheap part allows it
+template<int CH>
+__device__ __forceinline__ bool paw_color_within(uint32_t cur, uint32_t bg, uint32_t thr) {
+    const uint32_t l1 = paw_l1<CH>(cur, bg);
+    if(CH == 1) return l1 <= thr;
+    if((l1 >> 1) > thr) return false;
+    return (l1 >> 1) + paw_cdist3(cur, bg) * 4u <= thr;
 }
 
 template<int CH> struct PawPlanes {
@@ -100,42 +130,218 @@ template<int CH> struct PawPlanes {
 __device__ __forceinline__ uint32_t col_as_u32(const uint32_t& v) { return v; }
 __device__ __forceinline__ uint32_t col_as_u32(const uchar& v) { return v; }
 
-/// exchange dictionary positions i and i-1 of one pixel (all five planes)
+/// exchange dictionary positions i and i-1 of one pixel (all four planes)
 template<int CH>
 __device__ __forceinline__ void paw_swap(const PawArgs& A, size_t pix, int i) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     const size_t a = (size_t)i * A.plane + pix, b = a - A.plane;
-    const uint32_t f = A.lw_first[a], l = A.lw_last[a], o = A.lw_occ[a];
+    const uint2 k = A.lw_key[a]; const uint32_t f = A.lw_first[a];
     const Col c = ((Col*)A.lw_color)[a]; const Desc d = ((Desc*)A.lw_desc)[a];
-    A.lw_first[a] = A.lw_first[b]; A.lw_last[a] = A.lw_last[b]; A.lw_occ[a] = A.lw_occ[b];
+    A.lw_key[a] = A.lw_key[b]; A.lw_first[a] = A.lw_first[b];
     ((Col*)A.lw_color)[a] = ((Col*)A.lw_color)[b]; ((Desc*)A.lw_desc)[a] = ((Desc*)A.lw_desc)[b];
-    A.lw_first[b] = f; A.lw_last[b] = l; A.lw_occ[b] = o; ((Col*)A.lw_color)[b] = c; ((Desc*)A.lw_desc)[b] = d;
+    A.lw_key[b] = k; A.lw_first[b] = f; ((Col*)A.lw_color)[b] = c; ((Desc*)A.lw_desc)[b] = d;
 }
 
-/// search the pixel's sorted global-word LUT (PAWCS.cpp:1073-1079 / :1119-1125); returns the identity or -1
+/// search the pixel's sorted global-word LUT (PAWCS.cpp:1073-1079 / :1119-1125); returns the identity or -1.
+/// Stage 1 (no dependent loads, all NG LUT bytes in flight): the cheap tests of every position (descriptor bit count, L1 part of the
+/// colour distance) give a candidate mask; stage 2 runs the colour-distortion part on the candidates in LUT order.
+#ifndef PAW_GFIND
+#define PAW_GFIND 4
+#endif
 template<int CH>
 __device__ __forceinline__ int paw_find_gword(const PawArgs& A, const uint32_t* s_gbits, const uint32_t* s_gcolor, size_t pix, uint32_t cur_pack, uint32_t bits, uint32_t thrC, uint32_t thrD) {
-    for(int gi = 0; gi < A.NG; ++gi) {
-        const int g = A.glut[(size_t)gi * A.plane + pix];
-        const uint32_t gb = s_gbits[g];
-        if((bits > gb ? bits - gb : gb - bits) <= thrD / 4u) {
-            uint32_t l1, cd;
-            if(paw_color_dist<CH>(cur_pack, s_gcolor[g], l1, cd) <= thrC) return g;
+    for(int g0 = 0; g0 < A.NG; g0 += PAW_GFIND) {
+        uint32_t gv[PAW_GFIND];
+#pragma unroll
+        for(int k = 0; k < PAW_GFIND; ++k) gv[k] = g0 + k < A.NG ? (uint32_t)A.glut[(size_t)(g0 + k) * A.plane + pix] : 0u;
+        uint32_t cand = 0;
+#pragma unroll
+        for(int k = 0; k < PAW_GFIND; ++k) {
+            const uint32_t gb = s_gbits[gv[k]];
+            const uint32_t l1 = paw_l1<CH>(cur_pack, s_gcolor[gv[k]]);
+            const bool ok = g0 + k < A.NG && (bits > gb ? bits - gb : gb - bits) <= thrD / 4u && (CH == 1 ? l1 : (l1 >> 1)) <= thrC;
+            cand |= ok ? (1u << k) : 0u;
+        }
+        while(cand) {
+            const int k = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            uint32_t g = gv[0];
+#pragma unroll
+            for(int j = 1; j < PAW_GFIND; ++j) g = k == j ? gv[j] : g;
+            if(CH == 1) return (int)g;
+            if((paw_l1<CH>(cur_pack, s_gcolor[g]) >> 1) + paw_cdist3(cur_pack, s_gcolor[g]) * 4u <= thrC) return (int)g;
         }
     }
     return -1;
 }
 
-#ifndef PAW_CHUNK
-#define PAW_CHUNK 8   // words of the bubble pass whose counters are in flight together
-#endif
-#ifndef PAW_MIN_BLOCKS
-#define PAW_MIN_BLOCKS 4   // 64 registers with some spills, 4 CTAs per SM: the kernel is latency bound (2 / 3 / 4 / 5 / 6 -> 2.90 / 2.63 / 2.52 / 2.67 / 2.58 ms)
+// ------------------------------------------------------------------------------------------------------------
+// Phase A = scan -> scan tail -> bubble (NW <= PAW_SPLIT_MAX_NW: the hand-off word holds one bit per word).
+//
+// The reference interleaves, per pixel, the word scan ("while the weight sum is below its threshold") with one bubble-sort pass
+// over ALL words (PAWCS.cpp:1002-1065). Step i of that pass looks at position i, which still holds the frame-start word i
+// (a swap at step i-1 exchanges positions i-1 and i-2 only), and compares the PRE-update weight of word i with the pre-update
+// weight of the word carried from below. So the permutation is a pure function of the frame-start counters, and the scan can
+// run without swaps if the words it matched are recorded:
+//   pawcs_scan       tile kernel: LBSP + the first PAW_K words (their colour / descriptor / counters are in flight before the
+//                    input tile lands). A pixel that ends its scan within them (> 95 %) is classified and gets its feedback step
+//                    here; the others (foreground scans all NW words) go to a work-list and NOTHING of theirs is written yet.
+//   pawcs_scan_tail  one work-list pixel per lane, the same per-pixel code from word 0 with no depth limit.
+//   pawcs_bubble     every pixel, uniform: all NW counters (in flight in chunks), weights, the carry chain of the bubble pass
+//                    with the carried word kept in registers (a run of k swaps = k + 1 word moves instead of 2k), the counter
+//                    updates of the matched words (hand-off mask), the new word over the last one (:1142-1153).
+// Hand-off per pixel (uint2): matched-word mask bits 0..55, flags in the top byte.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PAW_K = 4;
+constexpr int PAW_SPLIT_MAX_NW = 56;
+constexpr uint32_t PAW_H_OCC = 1u << 24, PAW_H_NEW = 1u << 25, PAW_H_FLAT = 1u << 26, PAW_H_SKIP = 1u << 27; // hand.y: mask bits 32..55 in bits 0..23; SKIP: pawcs_scan_tail owns the pixel
+
+template<int CH> struct PawPix {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    Lookup16 L[CH];
+    Col cur_pack; Desc intra_pack;
+    uint32_t cur32, bits, thrC, thrD, rate, pixid, frame, woff, wk;   // wk = 2 frame + weight offset (paw_wk)
+    float wthr;
+    bool unst, flat, border, lastfg, blink, boot, moving;
+    size_t pix;
+};
+struct PawScan { float sum; uint32_t minColor, minDesc, illum_cur, mlo, mhi, scanned; bool did; };
+struct PawMaps { float T, R, V, DminLT, DminST, rawLT, rawST, finLT, finST; };
+struct PawBits { bool seg, unstable_new, has_intent, has_gop; int intent_row; uint32_t hand_y; };
+
+/// thresholds, update rate and the scan's weight threshold of one pixel (:967-994); key0 = frame-start key of word 0
+template<int CH, bool T7>
+__device__ __forceinline__ void paw_pix_setup(const PawArgs& A, const uchar* s_lut, PawPix<CH>& P, const uint32_t (&cur)[CH], const PawMaps& M,
+                                              const uint2 key0) {
+    const FrameCtl* ctl = A.ctl; const GDict* gd = A.gd;
+    P.frame = ctl->frame_idx; P.woff = gd->weight_offset; P.boot = gd->boot != 0; P.moving = gd->moving_camera != 0;
+    P.wk = paw_wk(P.frame, P.woff);
+    uint32_t intra[CH];
+#pragma unroll
+    for(int c = 0; c < CH; ++c) intra[c] = lbsp_threshold<T7>(P.L[c], cur[c], s_lut[cur[c]]);
+    if constexpr (CH == 1) { P.cur_pack = (uchar)cur[0]; P.intra_pack = (ushort)intra[0]; }
+    else { P.cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); P.intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
+    P.cur32 = col_as_u32(P.cur_pack);
+    P.bits = paw_bits(P.intra_pack);
+    P.flat = P.bits < (CH == 1 ? 2u : 4u);
+    P.rate = A.lr_fixed ? A.lr_fixed : (P.flat ? (uint32_t)ceilf(__fadd_rn(M.T, 1.0f)) / 2u : (uint32_t)ceilf(M.T)); // :987-989
+    const uint32_t cbase = (uint32_t)__fmul_rn(__fsqrt_rn(M.R), (float)A.min_color);
+    P.thrC = CH == 1 ? cbase / 2u : cbase * 3u;
+    const uint32_t dbase = (1u << (uint32_t)floorf(__fadd_rn(M.R, 0.5f))) + (uint32_t)A.desc_off + (P.unst ? (uint32_t)A.desc_off : 0u);
+    P.thrD = CH == 1 ? dbase : dbase * 3u;
+    P.wthr = __fdiv_rn(paw_weight(key0, P.wk), __fmul_rn(M.R, 2.0f)); // :967-968
+}
+
+/// one step of the word scan (:1002-1043) without the swap and without the counter updates (pawcs_bubble applies them)
+template<int CH, bool T7, bool DEFER>
+__device__ __forceinline__ void paw_test_word(const PawArgs& A, const uchar* s_lut, const PawPix<CH>& P, PawScan& S, int i,
+                                              const typename Pack<CH>::Col bc, const typename Pack<CH>::Desc bd, const uint2 key, uint32_t& deferred) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    ++S.scanned;
+    const uint32_t l1 = paw_l1<CH>(P.cur32, col_as_u32(bc));
+    if((CH == 1 ? l1 : (l1 >> 1)) > P.thrC) return; // neither the illumination update nor a match is possible
+    const uint32_t mix = CH == 1 ? l1 : (l1 >> 1) + paw_cdist3(P.cur32, col_as_u32(bc)) * 4u;
+    if(mix > P.thrC) return;
+    const uint32_t ihd = paw_hdist(P.intra_pack, bd);
+    if((!P.unst || P.flat || P.border) && l1 >= P.thrC / 2u && ihd <= P.thrD / 2u) { // illumination update (:1014-1030)
+        const uint32_t mod = S.illum_cur ? (P.rate / 2u + 1u) : P.rate;
+        if((philox_draw(A.seed, P.frame, P.pixid, 4u + (uint32_t)i, DOM_PAWCS_A) % mod) == 0u) {
+            if(DEFER) deferred |= 1u << i;
+            else { const size_t at = (size_t)i * A.plane + P.pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
+            S.did = true; S.illum_cur = 2u;
+        }
+    }
+    uint32_t ehd = 0;
+#pragma unroll
+    for(int c = 0; c < CH; ++c) {
+        const uint32_t b = col_get(bc, c);
+        ehd += __popc(lbsp_threshold<T7>(P.L[c], b, s_lut[b]) ^ desc_get(bd, c));
+    }
+    const uint32_t dd = (ihd + ehd) >> 1;
+    if(dd <= P.thrD) {
+        S.sum = __fadd_rn(S.sum, paw_weight(key, P.wk));
+        if(i < 32) S.mlo |= 1u << i; else S.mhi |= 1u << (i - 32);
+        S.minColor = min(S.minColor, mix); S.minDesc = min(S.minDesc, dd);
+    }
+}
+
+/// classification, global-word look-up, queued neighbour update, feedback (:1070-1269) and the hand-off word of a pixel whose scan ended
+template<int CH, bool GPRE = false, bool WRITE_HAND = true>
+__device__ __forceinline__ PawBits paw_finish(const PawArgs& A, const uint32_t* s_gbits, const uint32_t* s_gcolor, const PawPix<CH>& P, const PawScan& S,
+                                              PawMaps M, int x, int y, int g_pre = -1) {
+    const float aLT = A.ctl->aLT, aST = A.ctl->aST;
+    const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u;
+    PawBits B; B.seg = false; B.has_intent = false; B.has_gop = false; B.intent_row = 0; B.hand_y = 0;
+    bool new_word = false;
+    const float sum = S.sum, wthr = P.wthr;
+    const uint32_t rate = P.rate;
+    const uint4 rnd = philox_block(A.seed, P.frame, P.pixid, 0, DOM_PAWCS_A);
+    const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
+    const float baseMin = fmaxf(__fdiv_rn((float)S.minColor, (float)colorRange), __fdiv_rn((float)S.minDesc, (float)descRange));
+    const size_t cell = (size_t)(y >> 1) * A.gW + (x >> 1);
+    if(sum >= wthr || P.border) { // background (:1070-1106)
+        M.DminLT = __fadd_rn(__fmul_rn(M.DminLT, oneLT), __fmul_rn(baseMin, aLT));
+        M.DminST = __fadd_rn(__fmul_rn(M.DminST, oneST), __fmul_rn(baseMin, aST));
+        M.rawLT = __fmul_rn(M.rawLT, oneLT); M.rawST = __fmul_rn(M.rawST, oneST);
+        if((rnd.x % rate) == 0u) {
+            const int g = GPRE ? g_pre : paw_find_gword<CH>(A, s_gbits, s_gcolor, P.pix, P.cur32, P.bits, P.thrC, P.thrD);
+            const uint32_t rep = rate >= 0x40000000u ? rnd.y : rnd.y % (rate * 2u);
+            if(g >= 0 || rep == 0u) {
+                A.gop_g[P.pix] = g >= 0 ? (uchar)g : (uchar)0xFE; A.gop_w[P.pix] = sum; B.has_gop = true;
+                if(g < 0) atomicMin(&A.gd->rep_winner, P.pixid);
+            }
+        }
+    } else { // foreground (:1107-1155)
+        const float nmin = fmaxf(baseMin, __fdiv_rn(__fsub_rn(wthr, sum), wthr));
+        M.DminLT = __fadd_rn(__fmul_rn(M.DminLT, oneLT), __fmul_rn(nmin, aLT));
+        M.DminST = __fadd_rn(__fmul_rn(M.DminST, oneST), __fmul_rn(nmin, aST));
+        M.rawLT = __fadd_rn(__fmul_rn(M.rawLT, oneLT), aLT); M.rawST = __fadd_rn(__fmul_rn(M.rawST, oneST), aST);
+        if(P.flat || (rnd.x % rate) == 0u) {
+            const int g = GPRE ? g_pre : paw_find_gword<CH>(A, s_gbits, s_gcolor, P.pix, P.cur32, P.bits, P.thrC, P.thrD);
+            if(g < 0) B.seg = true;
+            else if(__fadd_rn(sum, __fdiv_rn(A.gmap[(size_t)g * A.gW * A.gH + cell], P.flat ? 2.0f : 4.0f)) < wthr) B.seg = true;
+        } else B.seg = true;
+        new_word = sum < __fdiv_rn(1.0f, (float)P.woff); // new local word over the last one (:1142-1153): written by pawcs_bubble
+    }
+    // neighbour dictionary update, queued (:1164-1247)
+    if((!B.seg && (rnd.z % rate) == 0u) || P.border || P.moving) {
+        int dx, dy;
+        neighbor_offset(!(P.flat || P.border || P.moving), rnd.w, dx, dy);
+        const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
+        if((A.roi_bits[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u) {
+            A.intents[P.pix] = make_uint4((uint32_t)((ny - y + 2) * 5 + (nx - x + 2)) | (P.thrD << 8), P.thrC, __float_as_uint(wthr), rate);
+            B.has_intent = true; B.intent_row = ny - y + 2;
+        }
+    }
+    // feedback (:1252-1269)
+    B.unstable_new = (M.R > 3.0f) || (__fsub_rn(M.rawLT, M.finLT) > 0.1f) || (__fsub_rn(M.rawST, M.finST) > 0.1f);
+    const float dmin = fminf(M.DminLT, M.DminST), dmax = fmaxf(M.DminLT, M.DminST);
+    if(P.lastfg || (dmin < 0.1f && B.seg)) M.T = fminf(__fadd_rn(M.T, __fdiv_rn(0.5f, __fmul_rn(dmax, M.V))), 256.0f);
+    else M.T = fmaxf(__fsub_rn(M.T, __fdiv_rn(__fmul_rn(0.25f, M.V), dmax)), 1.0f);
+    if(dmax > 0.1f && P.blink) M.V = __fadd_rn(M.V, P.boot ? 2.0f : 1.0f);
+    else M.V = fmaxf(__fsub_rn(M.V, __fmul_rn(0.1f, (P.boot || P.flat) ? 2.0f : P.lastfg ? 0.5f : 1.0f)), 0.1f);
+    const double rr = (double)__fadd_rn(1.0f, __fmul_rn(dmin, 2.0f));
+    if((double)M.R < __dmul_rn(rr, rr)) M.R = __fadd_rn(M.R, __fmul_rn(0.01f, __fsub_rn(M.V, 0.1f)));
+    else M.R = fmaxf(__fsub_rn(M.R, __fdiv_rn(0.01f, M.V)), 1.0f);
+
+    A.maps[P.pix * 2] = make_float4(M.T, M.R, M.V, 0.0f);
+    A.maps[P.pix * 2 + 1] = make_float4(M.DminLT, M.DminST, M.rawLT, M.rawST);
+    ((typename Pack<CH>::Col*)A.last_color)[P.pix] = P.cur_pack;
+    ((typename Pack<CH>::Desc*)A.last_desc)[P.pix] = P.intra_pack;
+    B.hand_y = S.mhi | ((!P.lastfg || P.moving) ? PAW_H_OCC : 0u) | (new_word ? PAW_H_NEW : 0u) | (P.flat ? PAW_H_FLAT : 0u);
+    if(WRITE_HAND) A.hand[P.pix] = make_uint2(S.mlo, B.hand_y);
+    return B;
+}
+
+#ifndef PAWS_MIN_BLOCKS
+#define PAWS_MIN_BLOCKS 4
 #endif
 template<int CH, bool T7>
-__global__ void __launch_bounds__(TILE_W * TILE_H, PAW_MIN_BLOCKS)
-pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(TILE_W * TILE_H, PAWS_MIN_BLOCKS)
+pawcs_scan(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     constexpr int PITCH = tile_pitch(CH);
@@ -166,189 +372,74 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     const size_t pix = (size_t)y * A.Wp + x;
     float4 m0 = make_float4(0, 0, 0, 0), m1 = m0;
     float2 fin = make_float2(0, 0);
-    uint32_t f0 = 0, l0 = 0, o0 = 0;
+    // the first PAW_K words of the pixel, in flight before the tile lands
+    Col bc[PAW_K]; Desc bd[PAW_K]; uint2 wkey[PAW_K];
+#pragma unroll
+    for(int k = 0; k < PAW_K; ++k) { bc[k] = Col(); bd[k] = Desc(); wkey[k] = make_uint2(0, 0); }
     if(active) {
+#pragma unroll
+        for(int k = 0; k < PAW_K; ++k)
+            if(k < A.NW) {
+                const size_t at = (size_t)k * A.plane + pix;
+                wkey[k] = A.lw_key[at];
+                bc[k] = ((const Col*)A.lw_color)[at]; bd[k] = ((const Desc*)A.lw_desc)[at];
+            }
         m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1]; fin = A.fin[pix];
-        f0 = A.lw_first[pix]; l0 = A.lw_last[pix]; o0 = A.lw_occ[pix];
     }
     stage_tile_wait(&s_bar, A.use_tma);
 
-    bool seg = false, unstable_new = false, did = false, has_intent = false, has_gop = false, flat = false;
+    bool finished = false, did = false, flat = false, unst_old = false;
+    PawBits B; B.seg = false; B.unstable_new = false; B.has_intent = false; B.has_gop = false; B.intent_row = 0; B.hand_y = 0;
     uint32_t scanned = 0;
-    int intent_row = 0;
     if(active) {
-        const FrameCtl* ctl = A.ctl; const GDict* gd = A.gd;
-        const float aLT = ctl->aLT, aST = ctl->aST;
-        const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown;
-        const uint32_t woff = gd->weight_offset; const bool boot = gd->boot != 0, moving = gd->moving_camera != 0;
-        const uint32_t colorRange = CH == 1 ? 255u : 765u, descRange = CH == 1 ? 16u : 48u, flatK = CH == 1 ? 2u : 4u;
-        float T = m0.x, R = m0.y, V = m0.z, DminLT = m1.x, DminST = m1.y, rawLT = m1.z, rawST = m1.w;
-        const bool unst = (w_unst & lane_bit) != 0, blink = (w_blink & lane_bit) != 0, lastfg = (w_lastfg & lane_bit) != 0;
-        const bool border = !(w_roi255 & lane_bit);
-        uint32_t illum_cur = (w_illum & lane_bit) ? 1u : 0u;
-
-        const int sy = threadIdx.y + HALO;
-        Lookup16 L[CH];
-        uint32_t cur[CH], intra[CH];
+        PawPix<CH> P;
+        P.pix = pix; P.pixid = (uint32_t)(y * A.W + x);
+        P.unst = (w_unst & lane_bit) != 0; P.blink = (w_blink & lane_bit) != 0; P.lastfg = (w_lastfg & lane_bit) != 0;
+        P.border = !(w_roi255 & lane_bit);
+        unst_old = P.unst;
+        PawMaps M; M.T = m0.x; M.R = m0.y; M.V = m0.z; M.DminLT = m1.x; M.DminST = m1.y; M.rawLT = m1.z; M.rawST = m1.w; M.finLT = fin.x; M.finST = fin.y;
+        uint32_t cur[CH];
         {
-            const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, sy, tile_shift(CH) + (int)threadIdx.x * CH);
+            const Window5<CH> Wn = lbsp_window_smem<CH>(s_tile, PITCH, threadIdx.y + HALO, tile_shift(CH) + (int)threadIdx.x * CH);
 #pragma unroll
-            for(int c = 0; c < CH; ++c) {
-                L[c] = lbsp_lookup_window<CH>(Wn, c);
-                cur[c] = win_center<CH>(Wn, c);
-                intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
-            }
+            for(int c = 0; c < CH; ++c) { P.L[c] = lbsp_lookup_window<CH>(Wn, c); cur[c] = win_center<CH>(Wn, c); }
         }
-        Col cur_pack; Desc intra_pack;
-        if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
-        else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
-        const uint32_t cur32 = col_as_u32(cur_pack);
-        const uint32_t bits = paw_bits(intra_pack);
-        flat = bits < flatK;
-        const uint32_t occ_incr = (1u + cooldown) << ((flat || boot) ? 1 : 0);
-        const uint32_t rate = A.lr_fixed ? A.lr_fixed : (flat ? (uint32_t)ceilf(__fadd_rn(T, 1.0f)) / 2u : (uint32_t)ceilf(T)); // :987-989
-        // thresholds (:993-994)
-        const uint32_t cbase = (uint32_t)__fmul_rn(__fsqrt_rn(R), (float)A.min_color);
-        const uint32_t thrC = CH == 1 ? cbase / 2u : cbase * 3u;
-        const uint32_t dbase = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unst ? (uint32_t)A.desc_off : 0u);
-        const uint32_t thrD = CH == 1 ? dbase : dbase * 3u;
-        const float wthr = __fdiv_rn(paw_weight(f0, l0, o0, frame, woff), __fmul_rn(R, 2.0f)); // :967-968
-        const uint32_t pixid = (uint32_t)(y * A.W + x);
-
-        // local dictionary: scan while the weight sum is below its threshold (:1002-1053), bubble pass over all words (:1044-1065)
-        float sum = 0.0f, last_w = FLT_MAX;
-        uint32_t minColor = colorRange, minDesc = descRange;
-        int i = 0;
-        uint32_t wf = f0, wl = l0, wo = o0;
-        // software-pipelined scan: word i+1 (colour, descriptor, counters) is fetched while word i is tested. A swap at step i
-        // exchanges positions i and i-1 only, so the prefetched word is still the one at position i+1.
-        Col nbc = ((const Col*)A.lw_color)[pix];
-        Desc nbd = ((const Desc*)A.lw_desc)[pix];
-        uint32_t nwf = f0, nwl = l0, nwo = o0;
-        for(; i < A.NW && sum < wthr; ++i) {
-            const size_t at = (size_t)i * A.plane + pix;
-            const Col bc = nbc;
-            const Desc bd = nbd;
-            wf = nwf; wl = nwl; wo = nwo;
-            if(i + 1 < A.NW) {
-                const size_t an = at + A.plane;
-                nbc = ((const Col*)A.lw_color)[an]; nbd = ((const Desc*)A.lw_desc)[an];
-                nwf = A.lw_first[an]; nwl = A.lw_last[an]; nwo = A.lw_occ[an];
-            }
-            const float w = paw_weight(wf, wl, wo, frame, woff);
-            ++scanned;
-            uint32_t l1, cd;
-            const uint32_t mix = paw_color_dist<CH>(cur32, col_as_u32(bc), l1, cd);
-            const uint32_t ihd = paw_hdist(intra_pack, bd);
-            uint32_t ehd = 0;
+        paw_pix_setup<CH, T7>(A, s_lut, P, cur, M, wkey[0]);
+        flat = P.flat;
+        PawScan S; S.sum = 0.0f; S.minColor = CH == 1 ? 255u : 765u; S.minDesc = CH == 1 ? 16u : 48u;
+        S.illum_cur = (w_illum & lane_bit) ? 1u : 0u; S.mlo = 0; S.mhi = 0; S.scanned = 0; S.did = false;
+        uint32_t deferred = 0;
 #pragma unroll
-            for(int c = 0; c < CH; ++c) {
-                const uint32_t b = col_get(bc, c);
-                ehd += __popc(lbsp_threshold<T7>(L[c], b, s_lut[b]) ^ desc_get(bd, c));
-            }
-            const uint32_t dd = (ihd + ehd) >> 1;
-            if((!unst || flat || border) && mix <= thrC && l1 >= thrC / 2u && ihd <= thrD / 2u) { // illumination update (:1014-1030)
-                const uint32_t mod = illum_cur ? (rate / 2u + 1u) : rate;
-                if((philox_draw(A.seed, frame, pixid, 4u + (uint32_t)i, DOM_PAWCS_A) % mod) == 0u) {
-                    ((Col*)A.lw_color)[at] = cur_pack; ((Desc*)A.lw_desc)[at] = intra_pack;
-                    did = true; illum_cur = 2u;
-                }
-            }
-            if(dd <= thrD && mix <= thrC) {
-                sum = __fadd_rn(sum, w);
-                A.lw_last[at] = frame;
-                if((!lastfg || moving) && w < 1.0f) A.lw_occ[at] = wo + occ_incr;
-                minColor = min(minColor, mix); minDesc = min(minDesc, dd);
-            }
-            if(w > last_w) paw_swap<CH>(A, pix, i); else last_w = w;
-        }
-        // the bubble pass continues over the rest of the dictionary (:1054-1065): only the counters are needed, CHUNK words
-        // in flight at once (a swap exchanges positions i and i-1 in memory; words already in registers are at positions > i)
-        constexpr int CHUNK = PAW_CHUNK;
-        for(; i < A.NW; i += CHUNK) {
-            uint32_t cf[CHUNK], cl[CHUNK], co[CHUNK];
+        for(int k = 0; k < PAW_K; ++k)
+            if(k < A.NW && S.sum < P.wthr) paw_test_word<CH, T7, true>(A, s_lut, P, S, k, bc[k], bd[k], wkey[k], deferred);
+        finished = !(PAW_K < A.NW && S.sum < P.wthr);
+        if(finished) {
 #pragma unroll
-            for(int k = 0; k < CHUNK; ++k) {
-                if(i + k < A.NW) { const size_t at = (size_t)(i + k) * A.plane + pix; cf[k] = A.lw_first[at]; cl[k] = A.lw_last[at]; co[k] = A.lw_occ[at]; }
-                else { cf[k] = 0; cl[k] = 0; co[k] = 0; }
-            }
-#pragma unroll
-            for(int k = 0; k < CHUNK; ++k) {
-                if(i + k < A.NW) {
-                    const float w = paw_weight(cf[k], cl[k], co[k], frame, woff);
-                    if(w > last_w) paw_swap<CH>(A, pix, i + k); else last_w = w;
-                }
-            }
+            for(int k = 0; k < PAW_K; ++k)
+                if((deferred >> k) & 1u) { const size_t at = (size_t)k * A.plane + pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
+            B = paw_finish<CH>(A, s_gbits, s_gcolor, P, S, M, x, y);
+            did = S.did; scanned = S.scanned;
         }
-
-        const uint4 rnd = philox_block(A.seed, frame, pixid, 0, DOM_PAWCS_A);
-        const float oneLT = __fsub_rn(1.0f, aLT), oneST = __fsub_rn(1.0f, aST);
-        const float baseMin = fmaxf(__fdiv_rn((float)minColor, (float)colorRange), __fdiv_rn((float)minDesc, (float)descRange));
-        const size_t cell = (size_t)(y >> 1) * A.gW + (x >> 1);
-        if(sum >= wthr || border) { // background (:1070-1106)
-            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(baseMin, aLT));
-            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(baseMin, aST));
-            rawLT = __fmul_rn(rawLT, oneLT); rawST = __fmul_rn(rawST, oneST);
-            if((rnd.x % rate) == 0u) {
-                const int g = paw_find_gword<CH>(A, s_gbits, s_gcolor, pix, cur32, bits, thrC, thrD);
-                const uint32_t rep = rate >= 0x40000000u ? rnd.y : rnd.y % (rate * 2u);
-                if(g >= 0 || rep == 0u) {
-                    A.gop_g[pix] = g >= 0 ? (uchar)g : (uchar)0xFE; A.gop_w[pix] = sum; has_gop = true;
-                    if(g < 0) atomicMin(&A.gd->rep_winner, pixid);
-                }
-            }
-        } else { // foreground (:1107-1155)
-            const float nmin = fmaxf(baseMin, __fdiv_rn(__fsub_rn(wthr, sum), wthr));
-            DminLT = __fadd_rn(__fmul_rn(DminLT, oneLT), __fmul_rn(nmin, aLT));
-            DminST = __fadd_rn(__fmul_rn(DminST, oneST), __fmul_rn(nmin, aST));
-            rawLT = __fadd_rn(__fmul_rn(rawLT, oneLT), aLT); rawST = __fadd_rn(__fmul_rn(rawST, oneST), aST);
-            if(flat || (rnd.x % rate) == 0u) {
-                const int g = paw_find_gword<CH>(A, s_gbits, s_gcolor, pix, cur32, bits, thrC, thrD);
-                if(g < 0) seg = true;
-                else if(__fadd_rn(sum, __fdiv_rn(A.gmap[(size_t)g * A.gW * A.gH + cell], flat ? 2.0f : 4.0f)) < wthr) seg = true;
-            } else seg = true;
-            if(sum < __fdiv_rn(1.0f, (float)woff)) { // new local word over the last one (:1142-1153)
-                const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
-                ((Col*)A.lw_color)[at] = cur_pack; ((Desc*)A.lw_desc)[at] = intra_pack;
-                A.lw_occ[at] = occ_incr; A.lw_first[at] = frame; A.lw_last[at] = frame;
-            }
-        }
-        // neighbour dictionary update, queued (:1164-1247)
-        if((!seg && (rnd.z % rate) == 0u) || border || moving) {
-            int dx, dy;
-            neighbor_offset(!(flat || border || moving), rnd.w, dx, dy);
-            const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
-            if((A.roi_bits[ny * A.WW + (nx >> 5)] >> (nx & 31)) & 1u) {
-                A.intents[pix] = make_uint4((uint32_t)((ny - y + 2) * 5 + (nx - x + 2)) | (thrD << 8), thrC, __float_as_uint(wthr), rate);
-                has_intent = true; intent_row = ny - y + 2;
-            }
-        }
-        // feedback (:1252-1269)
-        unstable_new = (R > 3.0f) || (__fsub_rn(rawLT, fin.x) > 0.1f) || (__fsub_rn(rawST, fin.y) > 0.1f);
-        const float dmin = fminf(DminLT, DminST), dmax = fmaxf(DminLT, DminST);
-        if(lastfg || (dmin < 0.1f && seg)) T = fminf(__fadd_rn(T, __fdiv_rn(0.5f, __fmul_rn(dmax, V))), 256.0f);
-        else T = fmaxf(__fsub_rn(T, __fdiv_rn(__fmul_rn(0.25f, V), dmax)), 1.0f);
-        if(dmax > 0.1f && blink) V = __fadd_rn(V, boot ? 2.0f : 1.0f);
-        else V = fmaxf(__fsub_rn(V, __fmul_rn(0.1f, (boot || flat) ? 2.0f : lastfg ? 0.5f : 1.0f)), 0.1f);
-        const double rr = (double)__fadd_rn(1.0f, __fmul_rn(dmin, 2.0f));
-        if((double)R < __dmul_rn(rr, rr)) R = __fadd_rn(R, __fmul_rn(0.01f, __fsub_rn(V, 0.1f)));
-        else R = fmaxf(__fsub_rn(R, __fdiv_rn(0.01f, V)), 1.0f);
-
-        A.maps[pix * 2] = make_float4(T, R, V, 0.0f);
-        A.maps[pix * 2 + 1] = make_float4(DminLT, DminST, rawLT, rawST);
-        ((Col*)A.last_color)[pix] = cur_pack;
-        ((Desc*)A.last_desc)[pix] = intra_pack;
     }
-
-    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, seg);
-    const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, unstable_new);
+    // pixels whose scan goes on: work-list (one atomic per warp)
+    {
+        const uint32_t um = __ballot_sync(0xFFFFFFFFu, active && !finished);
+        if(um) {
+            uint32_t base = 0;
+            if(threadIdx.x == 0) base = atomicAdd(&A.ctl->wl_count, (uint32_t)__popc(um));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if(active && !finished) { A.wl[base + __popc(um & (lane_bit - 1u))] = (uint32_t)pix; A.hand[pix] = make_uint2(0u, PAW_H_SKIP); }
+        }
+    }
+    const uint32_t b_raw = __ballot_sync(0xFFFFFFFFu, B.seg);
+    const uint32_t b_unst = __ballot_sync(0xFFFFFFFFu, finished ? B.unstable_new : unst_old); // an unfinished pixel keeps its old bit for the tail kernel
     const uint32_t b_did = __ballot_sync(0xFFFFFFFFu, did);
-    const uint32_t b_gop = __ballot_sync(0xFFFFFFFFu, has_gop);
+    const uint32_t b_gop = __ballot_sync(0xFFFFFFFFu, B.has_gop);
     const uint32_t b_flat = __ballot_sync(0xFFFFFFFFu, flat);
     uint32_t b_int = 0;
 #pragma unroll
     for(int d = 0; d < 5; ++d) {
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, has_intent && intent_row == d);
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, B.has_intent && B.intent_row == d);
         if((int)threadIdx.x == d) b_int = b;
     }
     if(in_words) {
@@ -374,17 +465,294 @@ pawcs_phaseA(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
     }
 }
 
-/// illumination mask of the next frame: new[p] = did[p+1] ? (roi[p]==255) : did[p]  (snapshot semantics)
-__global__ void __launch_bounds__(256) pawcs_illum_kernel(const PawArgs A) {
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if(wi >= A.WW) return;
-    const size_t i = (size_t)y * A.WW + wi;
-    const uint32_t d = A.did_bits[i], nxt = wi + 1 < A.WW ? A.did_bits[i + 1] : 0u;
-    const uint32_t dn = (d >> 1) | (nxt << 31); // bit x = did[x+1]
-    A.illum_bits[i] = ((dn & A.roi255_bits[i]) | (~dn & d)) & A.roi_bits[i];
+/// the pixels pawcs_scan could not finish (foreground scans all NW words): one pixel per WARP, nothing of theirs was written yet.
+/// Lane j tests word 32 r + j (colour / descriptor distances, weight, the draw of its illumination update); the sequential part of
+/// the reference's loop (weight sum in word order until it reaches the threshold, illumination updates whose modulus depends on
+/// the earlier ones) is replayed over the ballots of the words that matter; the global-word look-up is one word per lane too.
+constexpr int PAW_TAIL_THREADS = 128;
+#ifndef PAWT_MIN_BLOCKS
+#define PAWT_MIN_BLOCKS 8
+#endif
+template<int CH, bool T7>
+__global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_tail(const PawArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    __shared__ uchar s_lut[256];
+    __shared__ uint32_t s_gbits[PAW_MAXG], s_gcolor[PAW_MAXG];
+    constexpr uint32_t WPB = PAW_TAIL_THREADS / 32;
+    const uint32_t n = A.ctl->wl_count;
+    if(blockIdx.x * WPB >= n) return;
+    for(int i = threadIdx.x; i < 256; i += PAW_TAIL_THREADS) s_lut[i] = A.lut[i];
+    for(int i = threadIdx.x; i < PAW_MAXG; i += PAW_TAIL_THREADS) { s_gbits[i] = A.gd->bits[i]; s_gcolor[i] = A.gd->color[i]; }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long scanned_acc = 0, fg_acc = 0;
+    for(uint32_t e = blockIdx.x * WPB + (threadIdx.x >> 5); e < n; e += gridDim.x * WPB) {
+        const size_t pix = A.wl[e];
+        const int y = (int)(pix / (size_t)A.Wp), x = (int)(pix - (size_t)y * A.Wp);
+        const int wi = y * A.WW + (x >> 5);
+        const uint32_t lane_bit = 1u << (x & 31);
+        PawPix<CH> P;
+        P.pix = pix; P.pixid = (uint32_t)(y * A.W + x);
+        P.unst = (A.unstable_bits[wi] & lane_bit) != 0; P.blink = (A.blinks_bits[wi] & lane_bit) != 0; P.lastfg = (A.lastfg_bits[wi] & lane_bit) != 0;
+        P.border = !(A.roi255_bits[wi] & lane_bit);
+        const float4 m0 = A.maps[pix * 2], m1 = A.maps[pix * 2 + 1]; const float2 fin = A.fin[pix];
+        PawMaps M; M.T = m0.x; M.R = m0.y; M.V = m0.z; M.DminLT = m1.x; M.DminST = m1.y; M.rawLT = m1.z; M.rawST = m1.w; M.finLT = fin.x; M.finST = fin.y;
+        uint32_t cur[CH];
+#pragma unroll
+        for(int c = 0; c < CH; ++c) { P.L[c] = lbsp_lookup_smem<CH>(A.img, (int)A.ipitch, x, y, c); cur[c] = A.img[(size_t)y * A.ipitch + (size_t)x * CH + c]; }
+        paw_pix_setup<CH, T7>(A, s_lut, P, cur, M, A.lw_key[pix]);
+        PawScan S; S.sum = 0.0f; S.minColor = CH == 1 ? 255u : 765u; S.minDesc = CH == 1 ? 16u : 48u;
+        S.illum_cur = (A.illum_bits[wi] & lane_bit) ? 1u : 0u; S.mlo = 0; S.mhi = 0; S.scanned = 0; S.did = false;
+        for(int base = 0; base < A.NW && S.sum < P.wthr; base += 32) { // (warp-uniform condition)
+            const int i = base + (int)lane;
+            bool match = false, cand = false;
+            float w = 0.0f; uint32_t mix = 0, dd = 0, drw = 0;
+            if(i < A.NW) {
+                const size_t at = (size_t)i * A.plane + pix;
+                const Col bc = ((const Col*)A.lw_color)[at]; const Desc bd = ((const Desc*)A.lw_desc)[at];
+                w = paw_weight(A.lw_key[at], P.wk);
+                const uint32_t l1 = paw_l1<CH>(P.cur32, col_as_u32(bc));
+                if((CH == 1 ? l1 : (l1 >> 1)) <= P.thrC) {
+                    mix = CH == 1 ? l1 : (l1 >> 1) + paw_cdist3(P.cur32, col_as_u32(bc)) * 4u;
+                    if(mix <= P.thrC) {
+                        const uint32_t ihd = paw_hdist(P.intra_pack, bd);
+                        uint32_t ehd = 0;
+#pragma unroll
+                        for(int c = 0; c < CH; ++c) {
+                            const uint32_t b = col_get(bc, c);
+                            ehd += __popc(lbsp_threshold<T7>(P.L[c], b, s_lut[b]) ^ desc_get(bd, c));
+                        }
+                        dd = (ihd + ehd) >> 1;
+                        cand = (!P.unst || P.flat || P.border) && l1 >= P.thrC / 2u && ihd <= P.thrD / 2u; // :1014-1030
+                        match = dd <= P.thrD;
+                    }
+                }
+                if(cand) drw = philox_draw(A.seed, P.frame, P.pixid, 4u + (uint32_t)i, DOM_PAWCS_A);
+            }
+            const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match), cm = __ballot_sync(0xFFFFFFFFu, cand);
+            uint32_t evm = mm | cm, done = 0;
+            bool stop = false;
+            while(evm && !stop) { // the reference's loop order over the words that do something
+                const int j = __ffs(evm) - 1;
+                evm &= evm - 1u;
+                if((cm >> j) & 1u) {
+                    const uint32_t mod = S.illum_cur ? (P.rate / 2u + 1u) : P.rate;
+                    if((__shfl_sync(0xFFFFFFFFu, drw, j) % mod) == 0u) { done |= 1u << j; S.did = true; S.illum_cur = 2u; }
+                }
+                if((mm >> j) & 1u) {
+                    S.sum = __fadd_rn(S.sum, __shfl_sync(0xFFFFFFFFu, w, j));
+                    if(base == 0) S.mlo |= 1u << j; else S.mhi |= 1u << j;
+                    S.minColor = min(S.minColor, __shfl_sync(0xFFFFFFFFu, mix, j)); S.minDesc = min(S.minDesc, __shfl_sync(0xFFFFFFFFu, dd, j));
+                    if(!(S.sum < P.wthr)) { stop = true; S.scanned = (uint32_t)(base + j + 1); }
+                }
+            }
+            if(!stop) S.scanned = (uint32_t)min(base + 32, A.NW);
+            if((done >> lane) & 1u) { const size_t at = (size_t)i * A.plane + pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
+        }
+        // global-word look-up (:1073-1079 / :1119-1125), one LUT position per lane, first hit in LUT order
+        int g = -1;
+        for(int gb0 = 0; gb0 < A.NG && g < 0; gb0 += 32) {
+            const int gi = gb0 + (int)lane;
+            bool hit = false; int gv = 0;
+            if(gi < A.NG) {
+                gv = A.glut[(size_t)gi * A.plane + pix];
+                const uint32_t gb = s_gbits[gv];
+                if((P.bits > gb ? P.bits - gb : gb - P.bits) <= P.thrD / 4u) hit = paw_color_within<CH>(P.cur32, s_gcolor[gv], P.thrC);
+            }
+            const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+            if(hm) g = __shfl_sync(0xFFFFFFFFu, gv, __ffs(hm) - 1);
+        }
+        uint32_t hand_y = 0;
+        if(lane == 0) {
+            const PawBits B = paw_finish<CH, true, false>(A, s_gbits, s_gcolor, P, S, M, x, y, g);
+            hand_y = B.hand_y;
+            if(B.seg) atomicOr(&A.raw_bits[wi], lane_bit);
+            if(B.unstable_new != P.unst) atomicXor(&A.unstable_bits[wi], lane_bit);
+            if(S.did) atomicOr(&A.did_bits[wi], lane_bit);
+            if(B.has_gop) atomicOr(&A.gop_bits[wi], lane_bit);
+            if(B.has_intent) atomicOr(&A.intent_bits[(size_t)B.intent_row * A.bitplane + wi], lane_bit);
+            scanned_acc += S.scanned; fg_acc += B.seg ? 1u : 0u;
+        }
+        // the pixel's bubble pass (what pawcs_bubble does for the other pixels, which runs beside this kernel): lane j holds words j
+        // and j + 32; weights by the reference's division, the carry chain replayed over shuffles, then every word that moves or
+        // was matched is loaded by its lane, and stored at its final position once all lanes have loaded
+        {
+            hand_y = __shfl_sync(0xFFFFFFFFu, hand_y, 0);
+            const unsigned long long matched = ((unsigned long long)(hand_y & 0x00FFFFFFu) << 32) | S.mlo;
+            const bool occ_en = (hand_y & PAW_H_OCC) != 0;
+            const uint32_t occ_incr = (1u + A.ctl->cooldown) << ((P.flat || P.boot) ? 1 : 0);
+            uint2 key[2]; float w[2];
+#pragma unroll
+            for(int t = 0; t < 2; ++t) {
+                const int j = (int)lane + 32 * t;
+                key[t] = j < A.NW ? A.lw_key[(size_t)j * A.plane + pix] : make_uint2(0u, 0u);
+                w[t] = j < A.NW ? paw_weight(key[t], P.wk) : 0.0f;
+            }
+            unsigned long long swaps = 0ull;
+            float last_w = FLT_MAX;
+            for(int i = 0; i < A.NW; ++i) { // :1044-1052 (warp-uniform)
+                const float wi = __shfl_sync(0xFFFFFFFFu, i < 32 ? w[0] : w[1], i & 31);
+                if(wi > last_w) swaps |= 1ull << i; else last_w = wi;
+            }
+            bool moved[2], upd[2]; size_t dst[2]; uint32_t first[2]; Col mc[2]; Desc md[2];
+#pragma unroll
+            for(int t = 0; t < 2; ++t) {
+                const int j = (int)lane + 32 * t;
+                moved[t] = false; upd[t] = false; dst[t] = 0; first[t] = 0; mc[t] = Col(); md[t] = Desc();
+                if(j < A.NW) {
+                    const size_t at = (size_t)j * A.plane + pix;
+                    const bool down = (swaps >> j) & 1ull;
+                    const int pos = down ? j - 1 : j + (__ffsll((long long)~(swaps >> (j + 1))) - 1); // carried up through the run of swaps that follows
+                    moved[t] = pos != j; upd[t] = (matched >> j) & 1ull;
+                    dst[t] = (size_t)pos * A.plane + pix;
+                    if(moved[t] || upd[t]) first[t] = A.lw_first[at];
+                    if(upd[t]) key[t] = make_uint2((occ_en && w[t] < 1.0f) ? key[t].x + occ_incr : key[t].x, first[t] + P.frame); // :1035-1038
+                    if(moved[t]) { mc[t] = ((const Col*)A.lw_color)[at]; md[t] = ((const Desc*)A.lw_desc)[at]; }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for(int t = 0; t < 2; ++t) {
+                if(moved[t]) { A.lw_key[dst[t]] = key[t]; A.lw_first[dst[t]] = first[t]; ((Col*)A.lw_color)[dst[t]] = mc[t]; ((Desc*)A.lw_desc)[dst[t]] = md[t]; }
+                else if(upd[t]) A.lw_key[dst[t]] = key[t];
+            }
+            __syncwarp();
+            if((hand_y & PAW_H_NEW) && lane == 0) { // new local word over the last one (:1142-1153)
+                const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
+                ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack;
+                A.lw_key[at] = make_uint2(occ_incr, P.frame * 2u); A.lw_first[at] = P.frame;
+            }
+        }
+    }
+    if(A.collect_stats && lane == 0) {
+        if(scanned_acc) atomicAdd(&A.ctl->stat_scanned, scanned_acc);
+        if(fg_acc) atomicAdd(&A.ctl->stat_fg, fg_acc);
+    }
+}
+
+/// bubble pass over all words of every pixel + counter updates of the matched words + the new word (see the block comment above).
+/// Two steps per pixel: (1) uniform, no stores: all NW keys (PAWU_CHUNK 64-bit loads in flight) and the carry chain
+/// "if(w_i > carried) swap" of the reference, which yields the swap mask s (bit i: word i moves down to i-1);
+/// (2) sparse: only the words that move (s | s >> 1: a run of k swaps rotates k + 1 words, the carried one in registers) or were
+/// matched by the scan (hand-off mask: last = frame, occurrences += incr) are read again (L1 / L2 hits) and stored.
+///
+/// Step (1) compares the FLOAT quotients fl(o_i / d_i) > fl(o_c / d_c) without dividing: for operands below 2^24 (exact in float)
+/// rounding is monotone, so o_i d_c <= o_c d_i (64-bit products) means "no swap", and a relative gap above 2^-22 means the rounded
+/// quotients differ too ("swap"); the sliver in between (near ties) takes the two IEEE divisions. A pixel with a counter >= 2^24 or a
+/// zero denominator anywhere redoes step (1) with the divisions (paw_swaps_by_division).
+#ifndef PAWU_CHUNK
+#define PAWU_CHUNK 10
+#endif
+#ifndef PAWU_MIN_BLOCKS
+#define PAWU_MIN_BLOCKS 5
+#endif
+__device__ __noinline__ unsigned long long paw_swaps_by_division(const uint2* pk, size_t plane, int NW, uint32_t K) {
+    unsigned long long swaps = 0ull;
+    float last_w = FLT_MAX;
+    for(int i = 0; i < NW; ++i) {
+        const float w = paw_weight(pk[(size_t)i * plane], K);
+        if(w > last_w) swaps |= 1ull << i; else last_w = w; // :1044-1052
+    }
+    return swaps;
+}
+template<int CH>
+__global__ void __launch_bounds__(256, PAWU_MIN_BLOCKS) pawcs_bubble(const PawArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(x >= A.W || y >= A.H) return;
+    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
+    const size_t pix = (size_t)y * A.Wp + x;
+    const uint2 hand = A.hand[pix];
+    if(hand.y & PAW_H_SKIP) return; // pawcs_scan_tail does the bubble pass of its pixels itself
+    const FrameCtl* ctl = A.ctl; const GDict* gd = A.gd;
+    const uint32_t frame = ctl->frame_idx, K = paw_wk(frame, gd->weight_offset);
+    constexpr int CHUNK = PAWU_CHUNK;
+    unsigned long long swaps = 0ull;
+    {
+        uint32_t oc = 0xFFFFFFFFu, dc = 1u, unsafe = 0u; // carried word; the initial value never lets word 0 swap
+        const uint2* pk = A.lw_key + pix;
+        int i0 = 0;
+        for(; i0 + CHUNK <= A.NW; i0 += CHUNK) {
+            uint2 key[CHUNK];
+#pragma unroll
+            for(int k = 0; k < CHUNK; ++k) key[k] = pk[(size_t)k * A.plane];
+            uint32_t sw = 0;
+#pragma unroll
+            for(int k = 0; k < CHUNK; ++k) {
+                const uint32_t oi = key[k].x, di = K - key[k].y;
+                unsafe |= oi | (di - 1u);
+                const unsigned long long a = (unsigned long long)oi * dc, b = (unsigned long long)oc * di;
+                bool s = a > b;
+                if(s && !((a - b) > (b >> 22))) s = __fdiv_rn((float)oi, (float)di) > __fdiv_rn((float)oc, (float)dc); // near tie
+                sw |= s ? (1u << k) : 0u;
+                oc = s ? oc : oi; dc = s ? dc : di;
+            }
+            swaps |= (unsigned long long)sw << i0;
+            pk += (size_t)CHUNK * A.plane;
+        }
+        for(; i0 < A.NW; ++i0) { // NW not a multiple of the chunk
+            const uint2 key = *pk;
+            const uint32_t oi = key.x, di = K - key.y;
+            unsafe |= oi | (di - 1u);
+            const unsigned long long a = (unsigned long long)oi * dc, b = (unsigned long long)oc * di;
+            bool s = a > b;
+            if(s && !((a - b) > (b >> 22))) s = __fdiv_rn((float)oi, (float)di) > __fdiv_rn((float)oc, (float)dc);
+            swaps |= s ? (1ull << i0) : 0ull;
+            oc = s ? oc : oi; dc = s ? dc : di;
+            pk += A.plane;
+        }
+        if(unsafe >> 24) swaps = paw_swaps_by_division(A.lw_key + pix, A.plane, A.NW, K);
+    }
+    const bool occ_en = (hand.y & PAW_H_OCC) != 0;
+    const uint32_t occ_incr = (1u + ctl->cooldown) << (((hand.y & PAW_H_FLAT) || gd->boot) ? 1 : 0);
+    const unsigned long long matched = ((unsigned long long)(hand.y & 0x00FFFFFFu) << 32) | hand.x;
+    unsigned long long ev = matched | swaps | (swaps >> 1);
+    uint2 ckey = make_uint2(0, 0); uint32_t cfirst = 0; Col ccol = Col(); Desc cdesc = Desc(); // the carried word of the current run
+    // events in word order; the next event's word is fetched while the current one is stored (an event at i writes positions i-1
+    // and i only, the next one reads a position > i)
+    struct Ev { int i; uint2 key; uint32_t first; Col col; Desc desc; };
+    auto fetch = [&](Ev& e) {
+        e.i = __ffsll((long long)ev) - 1;
+        if(e.i < 0) return;
+        ev &= ev - 1ull;
+        const size_t at = (size_t)e.i * A.plane + pix;
+        e.key = A.lw_key[at]; e.first = A.lw_first[at];
+        if((swaps >> e.i) & 3ull) { e.col = ((const Col*)A.lw_color)[at]; e.desc = ((const Desc*)A.lw_desc)[at]; } // moves (down, or carried up)
+    };
+    Ev cur, nxt;
+    cur.col = Col(); cur.desc = Desc(); nxt.col = Col(); nxt.desc = Desc();
+    fetch(cur);
+    while(cur.i >= 0) {
+        fetch(nxt);
+        const int i = cur.i;
+        const size_t at = (size_t)i * A.plane + pix;
+        uint2 key = cur.key;
+        const bool down = (swaps >> i) & 1ull, next_down = (swaps >> (i + 1)) & 1ull;
+        if((matched >> i) & 1ull) { // :1035-1038: last = frame, occurrences += incr while the (old) weight is below 1
+            const float w = paw_weight(key, K);
+            key = make_uint2((occ_en && w < 1.0f) ? key.x + occ_incr : key.x, cur.first + frame);
+        }
+        if(down) { // word i -> position i-1; the run ends here if word i+1 stays
+            const size_t ab = at - A.plane;
+            ((Col*)A.lw_color)[ab] = cur.col; ((Desc*)A.lw_desc)[ab] = cur.desc;
+            A.lw_key[ab] = key; A.lw_first[ab] = cur.first;
+            if(!next_down) { A.lw_key[at] = ckey; A.lw_first[at] = cfirst; ((Col*)A.lw_color)[at] = ccol; ((Desc*)A.lw_desc)[at] = cdesc; }
+        } else if(next_down) { // word i is carried up through the run that starts at i+1
+            ckey = key; cfirst = cur.first; ccol = cur.col; cdesc = cur.desc;
+        } else A.lw_key[at] = key; // matched, stays where it is
+        cur = nxt;
+    }
+    if(hand.y & PAW_H_NEW) { // new local word over the last one (:1142-1153)
+        const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
+        ((Col*)A.lw_color)[at] = ((const Col*)A.last_color)[pix]; ((Desc*)A.lw_desc)[at] = ((const Desc*)A.last_desc)[pix];
+        A.lw_key[at] = make_uint2(occ_incr, frame * 2u); A.lw_first[at] = frame;
+    }
 }
 
 /// global dictionary, step 1: the first pixel (raster order) that asked for it replaces the last word of the dictionary
+/// (gridDim.x CTAs zero the word's occupancy map, thread 0 of CTA 0 rewrites the word; nobody reads what it writes in this kernel)
 template<int CH>
 __global__ void __launch_bounds__(1024) pawcs_gword_replace(const PawArgs A) {
     GDict* gd = A.gd;
@@ -392,8 +760,8 @@ __global__ void __launch_bounds__(1024) pawcs_gword_replace(const PawArgs A) {
     if(win == 0xFFFFFFFFu) return;
     const int g = gd->dict[A.NG - 1];
     float* m = A.gmap + (size_t)g * A.gW * A.gH;
-    for(int i = threadIdx.x; i < A.gW * A.gH; i += blockDim.x) m[i] = 0.0f;
-    if(threadIdx.x == 0) {
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.gW * A.gH; i += gridDim.x * blockDim.x) m[i] = 0.0f;
+    if(threadIdx.x == 0 && blockIdx.x == 0) {
         const int x = (int)(win % (uint32_t)A.W), y = (int)(win / (uint32_t)A.W);
         const size_t pix = (size_t)y * A.Wp + x;
         if constexpr (CH == 1) {
@@ -434,7 +802,12 @@ __global__ void __launch_bounds__(256) pawcs_gword_apply(const PawArgs A) {
     for(int i = threadIdx.x; i < A.NG; i += blockDim.x) if(s_acc[i]) atomicAdd(&gd->acc[i], s_acc[i]);
 }
 /// step 3 (1 CTA): fold the fixed-point increments into the float weights
-__global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A) {
+__device__ __forceinline__ void paw_gdict_bubble_pass(const PawArgs& A) { // :1316-1317
+    GDict* gd = A.gd;
+    for(int i = 1; i < A.NG; ++i)
+        if(gd->weight[gd->dict[i]] > gd->weight[gd->dict[i - 1]]) { const int t = gd->dict[i]; gd->dict[i] = gd->dict[i - 1]; gd->dict[i - 1] = t; }
+}
+__global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A, int then_bubble) {
     GDict* gd = A.gd;
     const int g = threadIdx.x;
     if(g < A.NG) {
@@ -442,101 +815,191 @@ __global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A) {
         if(a) { gd->weight[g] = (float)((double)gd->weight[g] + (double)(long long)a / 4294967296.0); gd->acc[g] = 0ull; }
     }
     if(g == 0) gd->rep_winner = 0xFFFFFFFFu;
+    if(then_bubble) { // no maintenance this frame: the dictionary bubble pass (:1316-1317) follows at once
+        __syncthreads();
+        if(g == 0) paw_gdict_bubble_pass(A);
+    }
 }
 
-/// Phase B: queued neighbour-dictionary updates (PAWCS.cpp:1164-1247), gathered per TARGET pixel, raster order of the source
+/// Phase B: queued neighbour-dictionary updates (PAWCS.cpp:1164-1247), gathered per TARGET pixel, raster order of the source.
+/// pawcs_phaseB: one target per thread. The sources of the tile + 2-px halo mark their targets in shared memory (bit = position of
+/// the source in the target's 5x5 window, ascending = raster order), every target pops its hits in order. A hit walks the target's
+/// dictionary while its weight sum is below the source's threshold; here only the first PAWB_K words (in flight together), with
+/// the word updates held back until the walk is known to end within them. A target whose current hit needs more words is pushed to
+/// a list with its remaining hits and finished by pawcs_phaseB_tail: one target per WARP, one word per lane, the sequential part
+/// (weight sum in word order) replayed over the ballot of the credited words.
 #ifndef PAWB_MIN_BLOCKS
-#define PAWB_MIN_BLOCKS 5   // 3 / 4 / 5 / 6 / 8 CTAs per SM -> 2.52 / 2.46 / 2.41 / 2.46 / 2.52 ms per 1080p frame
+#define PAWB_MIN_BLOCKS 5
 #endif
+#ifndef PAWB_KW
+#define PAWB_KW 3
+#endif
+constexpr int PAWB_K = PAWB_KW;
+template<int CH> struct PawHit {
+    typename Pack<CH>::Col sc; typename Pack<CH>::Desc sd, td;
+    uint32_t sc32, thrC, thrD, rate, src_id, occ_incr;
+    float wthr;
+    bool sflat, tflat, traw;
+};
+/// the source pixel (qx,qy) updates the dictionary of target (x,y) with its own colour / descriptor / thresholds
+template<int CH>
+__device__ __forceinline__ void paw_hit_load(const PawArgs& A, PawHit<CH>& Hh, int x, int y, int qx, int qy, uint32_t cooldown, bool boot) {
+    typedef typename Pack<CH>::Desc Desc;
+    const uint32_t flatK = CH == 1 ? 2u : 4u;
+    const size_t qpix = (size_t)qy * A.Wp + qx, pix = (size_t)y * A.Wp + x;
+    const uint4 rec = A.intents[qpix];
+    Hh.thrD = rec.x >> 8; Hh.thrC = rec.y; Hh.rate = rec.w; Hh.wthr = __uint_as_float(rec.z);
+    const uchar* src = A.img + (size_t)qy * A.ipitch + (size_t)qx * CH;
+    if constexpr (CH == 1) { Hh.sc = src[0]; Hh.sc32 = src[0]; } else { Hh.sc = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16); Hh.sc32 = Hh.sc; }
+    Hh.sd = ((const Desc*)A.last_desc)[qpix];   // == the source's intra descriptor of this frame
+    Hh.td = ((const Desc*)A.last_desc)[pix];    // target's intra descriptor of this frame
+    Hh.sflat = paw_bits(Hh.sd) < flatK; Hh.tflat = paw_bits(Hh.td) < flatK;
+    Hh.occ_incr = (1u + cooldown) << ((Hh.sflat || boot) ? 1 : 0);
+    Hh.traw = (A.raw_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u;
+    Hh.src_id = (uint32_t)(qy * A.W + qx);
+}
+/// one word of a hit's walk (:1180-1230): bit 0 credit, bit 1 take the source's descriptor, bit 2 take the source's colour
+template<int CH>
+__device__ __forceinline__ uint32_t paw_hit_word(const PawArgs& A, const PawHit<CH>& Hh, int j, typename Pack<CH>::Col bc, typename Pack<CH>::Desc bd, uint32_t frame, bool boot) {
+    uint32_t l1, cd;
+    const uint32_t mix = paw_color_dist<CH>(Hh.sc32, col_as_u32(bc), l1, cd);
+    const uint32_t hd = paw_hdist(Hh.sd, bd);
+    if(mix <= Hh.thrC && hd <= Hh.thrD) return 1u;
+    if(!Hh.traw && Hh.sflat && (boot || (philox_draw(A.seed, frame, Hh.src_id, (uint32_t)j, DOM_PAWCS_B) % Hh.rate) == 0u)) {
+        const uint32_t lhd = paw_hdist(Hh.sd, Hh.td);
+        if(mix <= Hh.thrC && lhd <= Hh.thrD / 2u) return 3u;
+        if(CH != 1 && Hh.tflat && lhd + hd <= Hh.thrD && cd <= Hh.thrC / 4u) return 5u;
+    }
+    return 0u;
+}
+/// counter / colour / descriptor updates of a credited word (Q8: the 1-channel path of the reference updates a by-value copy, PAWCS.cpp:838)
+template<int CH>
+__device__ __forceinline__ void paw_hit_commit(const PawArgs& A, const PawHit<CH>& Hh, size_t at, uint32_t flags, uint2 key, float w, typename Pack<CH>::Desc bd, uint32_t frame) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    if(CH == 1) return;
+    const uint32_t incr = paw_bits(bd) < (CH == 1 ? 2u : 4u) ? Hh.occ_incr * 2u : Hh.occ_incr;
+    A.lw_key[at] = make_uint2(w < 1.0f ? key.x + incr : key.x, A.lw_first[at] + frame); // last = frame
+    if(flags & 2u) ((Desc*)A.lw_desc)[at] = Hh.sd;
+    if(flags & 4u) ((Col*)A.lw_color)[at] = Hh.sc;
+}
+template<int CH>
+__device__ __forceinline__ void paw_hit_new_word(const PawArgs& A, const PawHit<CH>& Hh, size_t pix, uint32_t frame) {
+    const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
+    ((typename Pack<CH>::Col*)A.lw_color)[at] = Hh.sc; ((typename Pack<CH>::Desc*)A.lw_desc)[at] = Hh.sd;
+    A.lw_key[at] = make_uint2(Hh.occ_incr, frame * 2u); A.lw_first[at] = frame;
+}
+
 template<int CH>
 __global__ void __launch_bounds__(256, PAWB_MIN_BLOCKS) pawcs_phaseB(const PawArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    __shared__ uint32_t s_hits[8][32];
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    s_hits[threadIdx.y][threadIdx.x] = 0u;
+    __syncthreads();
+    // pass 1: every source of the tile + halo marks its target (bit = window position of the source, raster order)
+    for(int sidx = tid; sidx < 36 * 12; sidx += 256) {
+        const int sy = y0 - 2 + sidx / 36, sx = x0 - 2 + sidx % 36;
+        if(sx < 0 || sy < 0 || sx >= A.W || sy >= A.H) continue;
+        const uint32_t code = A.intents[(size_t)sy * A.Wp + sx].x & 0xFFu;
+        if(code >= 25u) continue;
+        const int row = (int)code / 5, col = (int)code - row * 5;
+        if(!((A.intent_bits[(size_t)row * A.bitplane + (size_t)sy * A.WW + (sx >> 5)] >> (sx & 31)) & 1u)) continue; // no intent this frame
+        const int tx = sx + col - 2 - x0, ty = sy + row - 2 - y0;
+        if(tx < 0 || ty < 0 || tx >= 32 || ty >= 8) continue;
+        atomicOr(&s_hits[ty][tx], 1u << ((4 - row) * 5 + (4 - col)));
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return;
-    const int wi = x >> 5, xb = x & 31;
+    uint32_t hits = s_hits[threadIdx.y][threadIdx.x];
+    if(!hits) return;
     const FrameCtl* ctl = A.ctl; const GDict* gd = A.gd;
-    const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, woff = gd->weight_offset;
+    const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, woff = gd->weight_offset, wk = paw_wk(frame, woff);
     const bool boot = gd->boot != 0;
-    const uint32_t flatK = CH == 1 ? 2u : 4u;
     const size_t pix = (size_t)y * A.Wp + x;
     const float init_w = __fdiv_rn(1.0f, (float)woff);
-    // pass 1: which of the 25 possible sources aim at this pixel (bit = window position in raster order of the source)
-    uint32_t hits = 0;
+    // pass 2: every lane pops ITS next hit
+    while(hits) {
+        const int hi_ = __ffs(hits) - 1;
+        const int r_ = hi_ / 5, k = hi_ - r_ * 5;
+        PawHit<CH> Hh;
+        paw_hit_load<CH>(A, Hh, x, y, x - 2 + k, y + r_ - 2, cooldown, boot);
+        Col bc[PAWB_K]; Desc bd[PAWB_K]; uint2 key[PAWB_K];
 #pragma unroll
-    for(int dy = -2; dy <= 2; ++dy) {
-        const int qy = y + dy;
-        const uint32_t* row = A.intent_bits + (size_t)(2 - dy) * A.bitplane + (size_t)qy * A.WW;
-        const uint32_t left = wi > 0 ? row[wi - 1] : 0u, cur = row[wi], right = wi + 1 < A.WW ? row[wi + 1] : 0u;
-        const unsigned long long lo = ((unsigned long long)cur << 32) | left, hi = ((unsigned long long)right << 32) | cur;
-        uint32_t win = (xb >= 2) ? (uint32_t)(hi >> (xb - 2)) & 31u : (uint32_t)(lo >> (30 + xb)) & 31u;
-        while(win) {
-            const int k = __ffs(win) - 1;
-            win &= win - 1;
-            if((int)(A.intents[(size_t)qy * A.Wp + (x - 2 + k)].x & 0xFFu) == (2 - dy) * 5 + (4 - k)) hits |= 1u << ((dy + 2) * 5 + k);
+        for(int j = 0; j < PAWB_K; ++j) {
+            if(j < A.NW) { const size_t at = (size_t)j * A.plane + pix; bc[j] = ((const Col*)A.lw_color)[at]; bd[j] = ((const Desc*)A.lw_desc)[at]; key[j] = A.lw_key[at]; }
+            else { bc[j] = Col(); bd[j] = Desc(); key[j] = make_uint2(0, 0); }
         }
+        float sum = 0.0f, w[PAWB_K]; uint32_t fl[PAWB_K];
+#pragma unroll
+        for(int j = 0; j < PAWB_K; ++j) {
+            fl[j] = 0u; w[j] = 0.0f;
+            if(j < A.NW && sum < Hh.wthr) {
+                fl[j] = paw_hit_word<CH>(A, Hh, j, bc[j], bd[j], frame, boot);
+                if(fl[j] & 1u) { w[j] = paw_weight(key[j], wk); sum = __fadd_rn(sum, w[j]); }
+            }
+        }
+        if(PAWB_K < A.NW && sum < Hh.wthr) { // the walk goes on: this hit and the later ones of this target go to the tail kernel
+            const uint32_t e = atomicAdd(&A.gd->wlB_count, 1u);
+            A.wlB[e] = make_uint2((uint32_t)pix, hits);
+            break;
+        }
+#pragma unroll
+        for(int j = 0; j < PAWB_K; ++j)
+            if(fl[j] & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl[j], key[j], w[j], bd[j], frame);
+        if(sum < init_w) paw_hit_new_word<CH>(A, Hh, pix, frame);
+        hits &= hits - 1u;
     }
-    // pass 2: every lane pops ITS next hit, so the lanes of a warp walk their dictionaries together (as many rounds as the busiest
-    // lane has hits) instead of one round per window position with a handful of lanes each
-    {
-        while(hits) {
+}
+
+template<int CH>
+__global__ void __launch_bounds__(PAW_TAIL_THREADS) pawcs_phaseB_tail(const PawArgs A) {
+    typedef typename Pack<CH>::Col Col;
+    typedef typename Pack<CH>::Desc Desc;
+    constexpr uint32_t WPB = PAW_TAIL_THREADS / 32;
+    const uint32_t n = A.gd->wlB_count;
+    const uint32_t lane = threadIdx.x & 31u;
+    const FrameCtl* ctl = A.ctl; const GDict* gd = A.gd;
+    const uint32_t frame = ctl->frame_idx, cooldown = ctl->cooldown, woff = gd->weight_offset, wk = paw_wk(frame, woff);
+    const bool boot = gd->boot != 0;
+    const float init_w = __fdiv_rn(1.0f, (float)woff);
+    for(uint32_t e = blockIdx.x * WPB + (threadIdx.x >> 5); e < n; e += gridDim.x * WPB) {
+        const uint2 ent = A.wlB[e];
+        const size_t pix = ent.x;
+        const int y = (int)(pix / (size_t)A.Wp), x = (int)(pix - (size_t)y * A.Wp);
+        uint32_t hits = ent.y;
+        while(hits) { // (warp-uniform)
             const int hi_ = __ffs(hits) - 1;
-            hits &= hits - 1;
+            hits &= hits - 1u;
             const int r_ = hi_ / 5, k = hi_ - r_ * 5;
-            const int qy = y + r_ - 2;
-            const int qx = x - 2 + k;
-            const size_t qpix = (size_t)qy * A.Wp + qx;
-            const uint4 rec = A.intents[qpix];
-            // source pixel (qx,qy) updates this pixel's dictionary with its own colour / descriptor / thresholds
-            const uint32_t thrD = rec.x >> 8, thrC = rec.y, rate = rec.w;
-            const float wthr = __uint_as_float(rec.z);
-            const uchar* src = A.img + (size_t)qy * A.ipitch + (size_t)qx * CH;
-            Col sc; uint32_t sc32;
-            if constexpr (CH == 1) { sc = src[0]; sc32 = src[0]; } else { sc = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16); sc32 = sc; }
-            const Desc sd = ((const Desc*)A.last_desc)[qpix];   // == the source's intra descriptor of this frame
-            const Desc td = ((const Desc*)A.last_desc)[pix];    // target's intra descriptor of this frame
-            const bool sflat = paw_bits(sd) < flatK;
-            const uint32_t occ_incr = (1u + cooldown) << ((sflat || boot) ? 1 : 0);
-            const bool traw = (A.raw_bits[y * A.WW + wi] >> xb) & 1u;
-            const uint32_t src_id = (uint32_t)(qy * A.W + qx);
+            PawHit<CH> Hh;
+            paw_hit_load<CH>(A, Hh, x, y, x - 2 + k, y + r_ - 2, cooldown, boot);
             float sum = 0.0f;
-            // software-pipelined: the colour / descriptor of word j+1 are fetched while word j is tested (the loads are harmless
-            // when the scan stops at j; a word rewritten by this very hit is never re-read by it)
-            Col nbc = ((const Col*)A.lw_color)[pix];
-            Desc nbd = ((const Desc*)A.lw_desc)[pix];
-            for(int j = 0; j < A.NW && sum < wthr; ++j) {
-                const size_t at = (size_t)j * A.plane + pix;
-                const Col bc = nbc;
-                const Desc bd = nbd;
-                if(j + 1 < A.NW) { nbc = ((const Col*)A.lw_color)[at + A.plane]; nbd = ((const Desc*)A.lw_desc)[at + A.plane]; }
-                uint32_t l1, cd;
-                const uint32_t mix = paw_color_dist<CH>(sc32, col_as_u32(bc), l1, cd);
-                const uint32_t hd = paw_hdist(sd, bd);
-                const uint32_t incr = paw_bits(bd) < flatK ? occ_incr * 2u : occ_incr;
-                bool credit = false, set_desc = false, set_col = false;
-                if(mix <= thrC && hd <= thrD) credit = true;
-                else if(!traw && sflat && (boot || (philox_draw(A.seed, frame, src_id, (uint32_t)j, DOM_PAWCS_B) % rate) == 0u)) {
-                    const uint32_t lhd = paw_hdist(sd, td);
-                    if(mix <= thrC && lhd <= thrD / 2u) { credit = true; set_desc = true; }
-                    else if(CH != 1 && paw_bits(td) < flatK && lhd + hd <= thrD && cd <= thrC / 4u) { credit = true; set_col = true; }
+            bool stop = false;
+            for(int base = 0; base < A.NW && !stop; base += 32) {
+                const int j = base + (int)lane;
+                uint32_t fl = 0u; float w = 0.0f; uint2 key = make_uint2(0, 0); Desc bd = Desc();
+                if(j < A.NW) {
+                    const size_t at = (size_t)j * A.plane + pix;
+                    bd = ((const Desc*)A.lw_desc)[at];
+                    fl = paw_hit_word<CH>(A, Hh, j, ((const Col*)A.lw_color)[at], bd, frame, boot);
+                    if(fl & 1u) { key = A.lw_key[at]; w = paw_weight(key, wk); }
                 }
-                if(credit) {
-                    const uint32_t wf = A.lw_first[at], wl = A.lw_last[at], wo = A.lw_occ[at];
-                    const float w = paw_weight(wf, wl, wo, frame, woff);
-                    sum = __fadd_rn(sum, w);
-                    if(CH != 1) { // Q8: the 1-channel path of the reference updates a by-value copy (PAWCS.cpp:838)
-                        A.lw_last[at] = frame;
-                        if(w < 1.0f) A.lw_occ[at] = wo + incr;
-                        if(set_desc) ((Desc*)A.lw_desc)[at] = sd;
-                        if(set_col) ((Col*)A.lw_color)[at] = sc;
-                    }
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, fl & 1u), upto = 0u;
+                while(m && !stop) { // the credited words in word order, until the weight sum reaches the source's threshold
+                    const int jj = __ffs(m) - 1;
+                    m &= m - 1u;
+                    sum = __fadd_rn(sum, __shfl_sync(0xFFFFFFFFu, w, jj));
+                    upto |= 1u << jj;
+                    if(!(sum < Hh.wthr)) stop = true;
                 }
+                if((upto >> lane) & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl, key, w, bd, frame);
             }
-            if(sum < init_w) {
-                const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
-                ((Col*)A.lw_color)[at] = sc; ((Desc*)A.lw_desc)[at] = sd;
-                A.lw_occ[at] = occ_incr; A.lw_first[at] = frame; A.lw_last[at] = frame;
-            }
+            if(sum < init_w && lane == 0) paw_hit_new_word<CH>(A, Hh, pix, frame);
+            __syncwarp();
         }
     }
 }
@@ -597,25 +1060,32 @@ __global__ void __launch_bounds__(1024) pawcs_gword_maintain(const PawArgs A, in
         for(int i = threadIdx.x; i < n; i += blockDim.x) m[i] = tmp[i];
     }
 }
-__global__ void pawcs_gdict_bubble(const PawArgs A) { // :1316-1317
-    GDict* gd = A.gd;
-    for(int i = 1; i < A.NG; ++i)
-        if(gd->weight[gd->dict[i]] > gd->weight[gd->dict[i - 1]]) { const int t = gd->dict[i]; gd->dict[i] = gd->dict[i - 1]; gd->dict[i - 1] = t; }
-}
-/// one bubble pass over the per-pixel global-word LUT (:1319-1334 / :411-428); `only_if_refresh`: runs only when a refresh just happened
+__global__ void pawcs_gdict_bubble(const PawArgs A) { paw_gdict_bubble_pass(A); }
+/// one bubble pass over the per-pixel global-word LUT (:1319-1334 / :411-428); `only_if_refresh`: last kernel of a conditional refresh:
+/// runs only when a refresh just happened, and the last CTA to finish then bumps the epoch the refresh kernels consumed and clears the request
 __global__ void __launch_bounds__(256) pawcs_glut_bubble(const PawArgs A, int only_if_refresh) {
     if(only_if_refresh && !A.gd->refresh_req) return;
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if(x >= A.W || y >= A.H) return;
-    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) return;
-    const size_t pix = (size_t)y * A.Wp + x, cell = (size_t)(y >> 1) * A.gW + (x >> 1), msz = (size_t)A.gW * A.gH;
-    uint32_t prev = A.glut[pix];
-    float last = A.gmap[(size_t)prev * msz + cell];
-    for(int i = 1; i < A.NG; ++i) {
-        const uint32_t g = A.glut[(size_t)i * A.plane + pix];
-        const float w = A.gmap[(size_t)g * msz + cell];
-        if(w > last) { A.glut[(size_t)i * A.plane + pix] = (uchar)prev; A.glut[(size_t)(i - 1) * A.plane + pix] = (uchar)g; }
-        else { last = w; prev = g; }
+    if(x < A.W && y < A.H && ((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) {
+        const size_t pix = (size_t)y * A.Wp + x, cell = (size_t)(y >> 1) * A.gW + (x >> 1), msz = (size_t)A.gW * A.gH;
+        uint32_t prev = A.glut[pix];
+        float last = A.gmap[(size_t)prev * msz + cell];
+        for(int i = 1; i < A.NG; ++i) {
+            const uint32_t g = A.glut[(size_t)i * A.plane + pix];
+            const float w = A.gmap[(size_t)g * msz + cell];
+            if(w > last) { A.glut[(size_t)i * A.plane + pix] = (uchar)prev; A.glut[(size_t)(i - 1) * A.plane + pix] = (uchar)g; }
+            else { last = w; prev = g; }
+        }
+    }
+    if(only_if_refresh) {
+        __syncthreads();
+        if(threadIdx.x == 0 && threadIdx.y == 0) {
+            __threadfence();
+            if(atomicAdd(&A.gd->refresh_ticket, 1u) == gridDim.x * gridDim.y - 1u) {
+                A.gd->refresh_ticket = 0u;
+                A.ctl->refresh_epoch += 1; A.gd->refresh_req = PAW_REQ_NONE; A.gd->set_T_one = 0;
+            }
+        }
     }
 }
 
@@ -677,12 +1147,13 @@ __global__ void __launch_bounds__(256) pawcs_background_kernel(const PawArgs A, 
     }
     const size_t pix = (size_t)y * A.Wp + x;
     const uint32_t frame = A.ctl->frame_idx - frame_off, woff = A.gd->weight_offset; // m_nFrameIdx: frame_off 0 inside a frame, 1 between frames
+    const uint32_t wk = paw_wk(frame, woff);
     float tw = 0.0f, tc[CH], td[CH];
 #pragma unroll
     for(int c = 0; c < CH; ++c) { tc[c] = 0.0f; td[c] = 0.0f; }
     for(int i = 0; i < A.NW; ++i) {
         const size_t at = (size_t)i * A.plane + pix;
-        const float w = paw_weight(A.lw_first[at], A.lw_last[at], A.lw_occ[at], frame, woff);
+        const float w = paw_weight(A.lw_key[at], wk);
         if(out_color) { const Col bc = ((const Col*)A.lw_color)[at];
 #pragma unroll
             for(int c = 0; c < CH; ++c) tc[c] = __fadd_rn(tc[c], __fmul_rn((float)col_get(bc, c), w)); }
@@ -743,7 +1214,8 @@ __global__ void __launch_bounds__(128) pawcs_model_dist_kernel(const PawArgs A) 
 
 /// tail, part 1 (1 CTA, 256 threads): LUT adaptation (:1462-1473), auto-reset enable, moving-camera decision (:1479-1500).
 /// `check_model`: this frame is a multiple of the bootstrap window and the model distances were accumulated.
-__global__ void __launch_bounds__(256) pawcs_tail1_kernel(const PawArgs A, int check_model) {
+__device__ __forceinline__ void paw_tail2(const PawArgs& A);
+__global__ void __launch_bounds__(256) pawcs_tail1_kernel(const PawArgs A, int check_model, int then_tail2) {
     FrameCtl* ctl = A.ctl; GDict* gd = A.gd;
     __shared__ int s_dir;
     const int t = threadIdx.x;
@@ -778,9 +1250,11 @@ __global__ void __launch_bounds__(256) pawcs_tail1_kernel(const PawArgs A, int c
         const float hi = fminf(fmaxf(rintf(__fadd_rn((float)A.lbsp_off, __fmul_rn(255.0f, A.rel))), 0.f), 255.f);
         if((float)A.lut[t] < hi) A.lut[t] += 1;
     }
+    if(then_tail2 && t == 0) paw_tail2(A);
 }
-/// tail, part 2 (1 thread): reset logic (:1501-1515), next-frame factors
-__global__ void pawcs_tail2_kernel(const PawArgs A) {
+/// tail, part 2 (1 thread): reset logic (:1501-1515), next-frame factors; follows part 1 in the same launch (`then_tail2`) unless the
+/// 500-frame model check may put a refresh between the two
+__device__ __forceinline__ void paw_tail2(const PawArgs& A) {
     FrameCtl* ctl = A.ctl; GDict* gd = A.gd;
     gd->refresh_req = PAW_REQ_NONE;
     const float l1ratio = __fdiv_rn((float)((double)gd->motion_acc / 65536.0), (float)gd->ds_roi_count);
@@ -795,6 +1269,7 @@ __global__ void pawcs_tail2_kernel(const PawArgs A) {
         } else if(!gd->boot) ctl->frames_since_reset += 1;
     }
     if(ctl->cooldown > 0) ctl->cooldown -= 1;
+    ctl->wl_count = 0; gd->wlB_count = 0; // this frame's work-lists are consumed
     // next frame
     const uint32_t f = ctl->frame_idx + 1;
     ctl->frame_idx = f;
@@ -805,6 +1280,7 @@ __global__ void pawcs_tail2_kernel(const PawArgs A) {
     ctl->aLT = __fdiv_rn(1.0f, (float)min(f, nLT));
     ctl->aST = __fdiv_rn(1.0f, (float)min(f, nST));
 }
+__global__ void pawcs_tail2_kernel(const PawArgs A) { paw_tail2(A); }
 
 // ------------------------------------------------------------------------------------------------------------
 // refreshModel (PAWCS.cpp:107-429); runs only when gd->refresh_req is set (the tail decides on the device)
@@ -835,10 +1311,11 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
     const uint32_t thrD = CH == 1 ? dbase : dbase * 3u;
     const int NW = A.NW;
     // occurrence == 0 && last == 0 && first == 1 marks a word that does not exist yet (initialisation only)
-    auto valid = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return !(A.lw_first[at] == 1u && A.lw_last[at] == 0u); };
-    auto weight = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return paw_weight(A.lw_first[at], A.lw_last[at], A.lw_occ[at], frame, woff); };
+    auto valid = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return !(A.lw_first[at] == 1u && A.lw_key[at].y == 1u); }; // first == 1 && last == 0
+    const uint32_t wk = paw_wk(frame, woff);
+    auto weight = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return paw_weight(A.lw_key[at], wk); };
     if(decr > 0.0f)
-        for(int i = 0; i < NW; ++i) { const size_t at = (size_t)i * A.plane + pix; if(valid(i)) { const uint32_t o = A.lw_occ[at]; A.lw_occ[at] = o - (uint32_t)__fmul_rn(decr, (float)o); } }
+        for(int i = 0; i < NW; ++i) { const size_t at = (size_t)i * A.plane + pix; if(valid(i)) { const uint32_t o = A.lw_key[at].x; A.lw_key[at].x = o - (uint32_t)__fmul_rn(decr, (float)o); } }
     uint32_t site = 0;
     uint4 rnd = make_uint4(0, 0, 0, 0);
     auto draw = [&]() { if((site & 3u) == 0u) rnd = philox_block(A.seed, epoch, pixid, site >> 2, DOM_REFRESH);
@@ -856,14 +1333,14 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
             const size_t at = (size_t)i * A.plane + pix;
             uint32_t l1, cd;
             if(paw_color_dist<CH>(col_as_u32(scol), col_as_u32(((const Col*)A.lw_color)[at]), l1, cd) <= thrC && paw_hdist(sdesc, ((const Desc*)A.lw_desc)[at]) <= thrD) {
-                A.lw_occ[at] += 1u; A.lw_last[at] = frame; break;
+                A.lw_key[at] = make_uint2(A.lw_key[at].x + 1u, A.lw_first[at] + frame); break; // last = frame
             }
         }
         if(i == NW) {
             i = NW - 1;
             const size_t at = (size_t)i * A.plane + pix;
             ((Col*)A.lw_color)[at] = scol; ((Desc*)A.lw_desc)[at] = sdesc;
-            A.lw_occ[at] = base_occ; A.lw_first[at] = frame; A.lw_last[at] = frame;
+            A.lw_key[at] = make_uint2(base_occ, frame * 2u); A.lw_first[at] = frame;
         }
         while(i > 0 && (!valid(i - 1) || weight(i) > weight(i - 1))) { paw_swap<CH>(A, pix, i); --i; }
     }
@@ -879,8 +1356,8 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
         else ((Col*)A.lw_color)[at] = (uint32_t)min(max((int)(rc & 0xFFu) + off, 0), 255) | ((uint32_t)min(max((int)((rc >> 8) & 0xFFu) + off, 0), 255) << 8)
                                     | ((uint32_t)min(max((int)((rc >> 16) & 0xFFu) + off, 0), 255) << 16);
         ((Desc*)A.lw_desc)[at] = ((const Desc*)A.lw_desc)[ar];
-        const uint32_t o = (uint32_t)__fmul_rn((float)A.lw_occ[ar], __fdiv_rn((float)(NW - i), (float)NW));
-        A.lw_occ[at] = max(o, 1u); A.lw_first[at] = frame; A.lw_last[at] = frame;
+        const uint32_t o = (uint32_t)__fmul_rn((float)A.lw_key[ar].x, __fdiv_rn((float)(NW - i), (float)NW));
+        A.lw_key[at] = make_uint2(max(o, 1u), frame * 2u); A.lw_first[at] = frame;
     }
 }
 /// global resampling (:342-408): sequential by nature (<= ~4*NG pixels); thread 0 decides, the CTA zeroes maps
@@ -937,7 +1414,7 @@ __global__ void __launch_bounds__(1024) pawcs_refresh_global(const PawArgs A, ui
             __syncthreads();
             if(threadIdx.x == 0) {
                 const int g = gd->dict[i];
-                const float bw = paw_weight(A.lw_first[pix], A.lw_last[pix], A.lw_occ[pix], frame, woff);
+                const float bw = paw_weight(A.lw_key[pix], paw_wk(frame, woff));
                 float* cw = A.gmap + (size_t)g * msz + (size_t)(y >> 1) * A.gW + (x >> 1);
                 if(*cw < bw) { gd->weight[g] = __fadd_rn(gd->weight[g], bw); *cw = __fadd_rn(*cw, bw); }
                 while(i > 0 && (gd->dict[i - 1] < 0 || gd->weight[gd->dict[i]] > gd->weight[gd->dict[i - 1]])) { const int t = gd->dict[i]; gd->dict[i] = gd->dict[i - 1]; gd->dict[i - 1] = t; --i; }
@@ -956,9 +1433,4 @@ __global__ void __launch_bounds__(1024) pawcs_refresh_global(const PawArgs A, ui
         __syncthreads();
     }
 }
-/// runs after the conditional refresh kernels: bump the epoch they consumed
-__global__ void pawcs_refresh_done(const PawArgs A) {
-    if(A.gd->refresh_req) { A.ctl->refresh_epoch += 1; A.gd->refresh_req = PAW_REQ_NONE; A.gd->set_T_one = 0; }
-}
-
 } // namespace lvb

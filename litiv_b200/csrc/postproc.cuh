@@ -19,6 +19,9 @@ struct PostArgs {
     FrameCtl* ctl;
     int median_k;
     uint32_t frame; int avg_samples; // frame != 0: the EMA factors are derived from the frame index instead of being read from ctl
+    // PAWCS only (null otherwise): the illumination mask of the next frame, new[p] = did[p+1] ? (roi[p]==255) : did[p] (snapshot semantics,
+    // DESIGN.md section 2), is computed by pp_blink_close, which runs over the same word grid
+    const uint32_t* did; const uint32_t* roi255; const uint32_t* roi; uint32_t* illum;
 };
 
 template<int FILL>
@@ -76,6 +79,11 @@ __global__ void __launch_bounds__(256) pp_blink_close(const PostArgs A) {
         acc &= hmorph<1, false>(d[0], d[1], d[2]);
     }
     A.pre[i] = acc & valid_mask(wi, A.WW, A.W);
+    if(A.illum) {
+        const uint32_t d = A.did[i], nxt = wi + 1 < A.WW ? A.did[i + 1] : 0u;
+        const uint32_t dn = (d >> 1) | (nxt << 31); // bit x = did[x+1]
+        A.illum[i] = ((dn & A.roi255[i]) | (~dn & d)) & A.roi[i];
+    }
 }
 /// horizontal run fill of one 32-word chunk held one word per lane: returns the bits of m connected (towards higher
 /// bit index, across lanes) to a seed bit. Carry-propagation trick: adding the seeds to the run mask ripples through

@@ -110,7 +110,36 @@ def test_pawcs_learning_rate_override_and_long_run(lv, oracle, w, h):
     assert o.state_get("scalars")[12] >= 2, "the scene change was expected to trigger a model reset in the oracle"
 
 
+def test_pawcs_large_counters_take_the_division_path(lv, oracle):
+    """the bubble-pass kernel compares word weights by exact 64-bit cross-multiplication while every counter is below 2^24
+    (exact in float) and redoes a pixel with the reference's float divisions otherwise, near ties included: occurrence counts
+    around 2^24..2^26 (rounded by the int -> float conversion) and equal-ratio words must sort exactly like the oracle"""
+    w, h, c = 96, 72, 3
+    seq = SynthSequence(w, h, c, seed=17)
+    g, o = _mk(lv, oracle, seed=11)
+    f0 = seq.frame(0)
+    g.initialize(f0); o.initialize(f0)
+    for t in range(1, 8):
+        o.apply(seq.frame(t), 0.0)
+    occ = o.state_get("lw_occ").copy().reshape(h, w, -1)
+    rng = np.random.default_rng(3)
+    big = rng.integers(1 << 24, 1 << 26, size=occ.shape, dtype=np.int64).astype(np.uint32)
+    occ[:, : w // 3] = big[:, : w // 3]                               # >= 2^24: float conversion rounds, division path
+    occ[:, w // 3: 2 * w // 3] = ((occ[:, w // 3: 2 * w // 3].astype(np.int64) + 1) * 4099).astype(np.uint32)   # large products, many near ties
+    o.state_set("lw_occ", occ.ravel())
+    for n in INT_STATE + FLT_STATE + ["scalars"]:
+        if n != "rawmask":
+            g.state_set(n, o.state_get(n))
+    for t in range(8, 20):
+        f = seq.frame(t)
+        mg, mo = g.apply(f, 0.0), o.apply(f, 0.0)
+        _compare(g, o, f"large counters, frame {t}")
+        assert np.array_equal(mg, mo)
+
+
 def test_pawcs_api_errors(lv):
+    with pytest.raises(lv.LitivError, match="56 local words"):
+        lv.BackgroundSubtractorPAWCS(nMaxNbWords=60).initialize(np.zeros((48, 64, 3), np.uint8))
     g = lv.BackgroundSubtractorPAWCS()
     with pytest.raises(lv.LitivError, match="initialized"):
         g.apply(np.zeros((48, 64, 3), np.uint8))
