@@ -665,7 +665,7 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     // instance stream : scan -> scan tail (work-list pixels, incl. their bubble pass) -> global dictionary -> mask chain -> ...
     // auxiliary stream: bubble pass of the other pixels (beside the scan tail) -> phase B (needs both) -> phase B tail
     {
-        const int tail_grid = c->sm_count * 8;
+        const int tail_grid = c->sm_count * PAWT_MIN_BLOCKS;
         if(c->lut_small) { if(C == 1) pawcs_scan<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_scan<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
         else { if(C == 1) pawcs_scan<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else pawcs_scan<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
         LAUNCHED();
@@ -680,7 +680,7 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
     if(C == 1) pawcs_phaseB<1><<<tg, tb, 0, c->s_aux>>>(A); else pawcs_phaseB<3><<<tg, tb, 0, c->s_aux>>>(A);
     LAUNCHED();
-    if(C == 1) pawcs_phaseB_tail<1><<<c->sm_count * 8, PAW_TAIL_THREADS, 0, c->s_aux>>>(A); else pawcs_phaseB_tail<3><<<c->sm_count * 8, PAW_TAIL_THREADS, 0, c->s_aux>>>(A);
+    if(C == 1) pawcs_phaseB_tail<1><<<c->sm_count * PAWBT_MIN_BLOCKS, PAW_TAIL_THREADS, 0, c->s_aux>>>(A); else pawcs_phaseB_tail<3><<<c->sm_count * PAWBT_MIN_BLOCKS, PAW_TAIL_THREADS, 0, c->s_aux>>>(A);
     LAUNCHED();
     CK(cudaEventRecord(c->ev_join, c->s_aux));
     if(C == 1) pawcs_gword_replace<1><<<16, 1024, 0, st>>>(A); else pawcs_gword_replace<3><<<16, 1024, 0, st>>>(A);

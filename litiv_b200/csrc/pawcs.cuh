@@ -471,7 +471,7 @@ pawcs_scan(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
 /// the earlier ones) is replayed over the ballots of the words that matter; the global-word look-up is one word per lane too.
 constexpr int PAW_TAIL_THREADS = 128;
 #ifndef PAWT_MIN_BLOCKS
-#define PAWT_MIN_BLOCKS 8
+#define PAWT_MIN_BLOCKS 5
 #endif
 template<int CH, bool T7>
 __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_tail(const PawArgs A) {
@@ -501,67 +501,100 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
         uint32_t cur[CH];
 #pragma unroll
         for(int c = 0; c < CH; ++c) { P.L[c] = lbsp_lookup_smem<CH>(A.img, (int)A.ipitch, x, y, c); cur[c] = A.img[(size_t)y * A.ipitch + (size_t)x * CH + c]; }
-        paw_pix_setup<CH, T7>(A, s_lut, P, cur, M, A.lw_key[pix]);
+        // lane j holds words j and j + 32. All keys at once (the bubble pass below needs every weight); colour / descriptor round by
+        // round: a word costs a 32-byte sector per plane here (one pixel per warp), and most pixels of the list stop within the first round
+        Col bc[2]; Desc bd[2]; uint2 key[2]; float w[2]; bool have_cd[2];
+#pragma unroll
+        for(int t = 0; t < 2; ++t) {
+            const int j = (int)lane + 32 * t;
+            bc[t] = Col(); bd[t] = Desc(); have_cd[t] = false;
+            key[t] = j < A.NW ? A.lw_key[(size_t)j * A.plane + pix] : make_uint2(0u, 0u);
+        }
+        const uint32_t gv_lane = (int)lane < A.NG ? (uint32_t)A.glut[(size_t)lane * A.plane + pix] : 0u; // global-word LUT, position = lane
+        paw_pix_setup<CH, T7>(A, s_lut, P, cur, M, make_uint2(__shfl_sync(0xFFFFFFFFu, key[0].x, 0), __shfl_sync(0xFFFFFFFFu, key[0].y, 0)));
         PawScan S; S.sum = 0.0f; S.minColor = CH == 1 ? 255u : 765u; S.minDesc = CH == 1 ? 16u : 48u;
         S.illum_cur = (A.illum_bits[wi] & lane_bit) ? 1u : 0u; S.mlo = 0; S.mhi = 0; S.scanned = 0; S.did = false;
-        for(int base = 0; base < A.NW && S.sum < P.wthr; base += 32) { // (warp-uniform condition)
-            const int i = base + (int)lane;
-            bool match = false, cand = false;
-            float w = 0.0f; uint32_t mix = 0, dd = 0, drw = 0;
-            if(i < A.NW) {
-                const size_t at = (size_t)i * A.plane + pix;
-                const Col bc = ((const Col*)A.lw_color)[at]; const Desc bd = ((const Desc*)A.lw_desc)[at];
-                w = paw_weight(A.lw_key[at], P.wk);
-                const uint32_t l1 = paw_l1<CH>(P.cur32, col_as_u32(bc));
-                if((CH == 1 ? l1 : (l1 >> 1)) <= P.thrC) {
-                    mix = CH == 1 ? l1 : (l1 >> 1) + paw_cdist3(P.cur32, col_as_u32(bc)) * 4u;
-                    if(mix <= P.thrC) {
-                        const uint32_t ihd = paw_hdist(P.intra_pack, bd);
-                        uint32_t ehd = 0;
+        bool zero_den = false;
 #pragma unroll
-                        for(int c = 0; c < CH; ++c) {
-                            const uint32_t b = col_get(bc, c);
-                            ehd += __popc(lbsp_threshold<T7>(P.L[c], b, s_lut[b]) ^ desc_get(bd, c));
+        for(int t = 0; t < 2; ++t) {
+            const int j = (int)lane + 32 * t;
+            w[t] = j < A.NW ? paw_weight(key[t], P.wk) : 0.0f;
+            zero_den |= j < A.NW && P.wk == key[t].y;
+        }
+#pragma unroll
+        for(int t = 0; t < 2; ++t) {
+            const int base = 32 * t;
+            if(base < A.NW && S.sum < P.wthr) { // (warp-uniform condition)
+                const int i = base + (int)lane;
+                bool match = false, cand = false;
+                uint32_t mix = 0, dd = 0, drw = 0;
+                if(i < A.NW) {
+                    const size_t at = (size_t)i * A.plane + pix;
+                    bc[t] = ((const Col*)A.lw_color)[at]; bd[t] = ((const Desc*)A.lw_desc)[at]; have_cd[t] = true;
+                    const uint32_t l1 = paw_l1<CH>(P.cur32, col_as_u32(bc[t]));
+                    if((CH == 1 ? l1 : (l1 >> 1)) <= P.thrC) {
+                        mix = CH == 1 ? l1 : (l1 >> 1) + paw_cdist3(P.cur32, col_as_u32(bc[t])) * 4u;
+                        if(mix <= P.thrC) {
+                            const uint32_t ihd = paw_hdist(P.intra_pack, bd[t]);
+                            uint32_t ehd = 0;
+#pragma unroll
+                            for(int c = 0; c < CH; ++c) {
+                                const uint32_t b = col_get(bc[t], c);
+                                ehd += __popc(lbsp_threshold<T7>(P.L[c], b, s_lut[b]) ^ desc_get(bd[t], c));
+                            }
+                            dd = (ihd + ehd) >> 1;
+                            cand = (!P.unst || P.flat || P.border) && l1 >= P.thrC / 2u && ihd <= P.thrD / 2u; // :1014-1030
+                            match = dd <= P.thrD;
                         }
-                        dd = (ihd + ehd) >> 1;
-                        cand = (!P.unst || P.flat || P.border) && l1 >= P.thrC / 2u && ihd <= P.thrD / 2u; // :1014-1030
-                        match = dd <= P.thrD;
+                    }
+                    if(cand) drw = philox_draw(A.seed, P.frame, P.pixid, 4u + (uint32_t)i, DOM_PAWCS_A);
+                }
+                const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match), cm = __ballot_sync(0xFFFFFFFFu, cand);
+                uint32_t evm = mm | cm, done = 0;
+                bool stop = false;
+                while(evm && !stop) { // the reference's loop order over the words that do something
+                    const int j = __ffs(evm) - 1;
+                    evm &= evm - 1u;
+                    if((cm >> j) & 1u) {
+                        const uint32_t mod = S.illum_cur ? (P.rate / 2u + 1u) : P.rate;
+                        if((__shfl_sync(0xFFFFFFFFu, drw, j) % mod) == 0u) { done |= 1u << j; S.did = true; S.illum_cur = 2u; }
+                    }
+                    if((mm >> j) & 1u) {
+                        S.sum = __fadd_rn(S.sum, __shfl_sync(0xFFFFFFFFu, w[t], j));
+                        if(t == 0) S.mlo |= 1u << j; else S.mhi |= 1u << j;
+                        S.minColor = min(S.minColor, __shfl_sync(0xFFFFFFFFu, mix, j)); S.minDesc = min(S.minDesc, __shfl_sync(0xFFFFFFFFu, dd, j));
+                        if(!(S.sum < P.wthr)) { stop = true; S.scanned = (uint32_t)(base + j + 1); }
                     }
                 }
-                if(cand) drw = philox_draw(A.seed, P.frame, P.pixid, 4u + (uint32_t)i, DOM_PAWCS_A);
-            }
-            const uint32_t mm = __ballot_sync(0xFFFFFFFFu, match), cm = __ballot_sync(0xFFFFFFFFu, cand);
-            uint32_t evm = mm | cm, done = 0;
-            bool stop = false;
-            while(evm && !stop) { // the reference's loop order over the words that do something
-                const int j = __ffs(evm) - 1;
-                evm &= evm - 1u;
-                if((cm >> j) & 1u) {
-                    const uint32_t mod = S.illum_cur ? (P.rate / 2u + 1u) : P.rate;
-                    if((__shfl_sync(0xFFFFFFFFu, drw, j) % mod) == 0u) { done |= 1u << j; S.did = true; S.illum_cur = 2u; }
-                }
-                if((mm >> j) & 1u) {
-                    S.sum = __fadd_rn(S.sum, __shfl_sync(0xFFFFFFFFu, w, j));
-                    if(base == 0) S.mlo |= 1u << j; else S.mhi |= 1u << j;
-                    S.minColor = min(S.minColor, __shfl_sync(0xFFFFFFFFu, mix, j)); S.minDesc = min(S.minDesc, __shfl_sync(0xFFFFFFFFu, dd, j));
-                    if(!(S.sum < P.wthr)) { stop = true; S.scanned = (uint32_t)(base + j + 1); }
+                if(!stop) S.scanned = (uint32_t)min(base + 32, A.NW);
+                if((done >> lane) & 1u) { // illumination update of word i, in place (the bubble pass below moves it with the rest of the word)
+                    const size_t at = (size_t)i * A.plane + pix;
+                    ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack;
+                    bc[t] = P.cur_pack; bd[t] = P.intra_pack;
                 }
             }
-            if(!stop) S.scanned = (uint32_t)min(base + 32, A.NW);
-            if((done >> lane) & 1u) { const size_t at = (size_t)i * A.plane + pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
         }
         // global-word look-up (:1073-1079 / :1119-1125), one LUT position per lane, first hit in LUT order
         int g = -1;
-        for(int gb0 = 0; gb0 < A.NG && g < 0; gb0 += 32) {
-            const int gi = gb0 + (int)lane;
-            bool hit = false; int gv = 0;
-            if(gi < A.NG) {
-                gv = A.glut[(size_t)gi * A.plane + pix];
-                const uint32_t gb = s_gbits[gv];
-                if((P.bits > gb ? P.bits - gb : gb - P.bits) <= P.thrD / 4u) hit = paw_color_within<CH>(P.cur32, s_gcolor[gv], P.thrC);
+        {
+            bool hit = false;
+            if((int)lane < A.NG) {
+                const uint32_t gb = s_gbits[gv_lane];
+                if((P.bits > gb ? P.bits - gb : gb - P.bits) <= P.thrD / 4u) hit = paw_color_within<CH>(P.cur32, s_gcolor[gv_lane], P.thrC);
             }
             const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
-            if(hm) g = __shfl_sync(0xFFFFFFFFu, gv, __ffs(hm) - 1);
+            if(hm) g = (int)__shfl_sync(0xFFFFFFFFu, gv_lane, __ffs(hm) - 1);
+            for(int gb0 = 32; gb0 < A.NG && g < 0; gb0 += 32) { // more than 32 global words (not with the reference's defaults)
+                const int gi = gb0 + (int)lane;
+                bool hit2 = false; uint32_t gv = 0;
+                if(gi < A.NG) {
+                    gv = A.glut[(size_t)gi * A.plane + pix];
+                    const uint32_t gb = s_gbits[gv];
+                    if((P.bits > gb ? P.bits - gb : gb - P.bits) <= P.thrD / 4u) hit2 = paw_color_within<CH>(P.cur32, s_gcolor[gv], P.thrC);
+                }
+                const uint32_t hm2 = __ballot_sync(0xFFFFFFFFu, hit2);
+                if(hm2) g = (int)__shfl_sync(0xFFFFFFFFu, gv, __ffs(hm2) - 1);
+            }
         }
         uint32_t hand_y = 0;
         if(lane == 0) {
@@ -574,32 +607,42 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
             if(B.has_intent) atomicOr(&A.intent_bits[(size_t)B.intent_row * A.bitplane + wi], lane_bit);
             scanned_acc += S.scanned; fg_acc += B.seg ? 1u : 0u;
         }
-        // the pixel's bubble pass (what pawcs_bubble does for the other pixels, which runs beside this kernel): lane j holds words j
-        // and j + 32; weights by the reference's division, the carry chain replayed over shuffles, then every word that moves or
-        // was matched is loaded by its lane, and stored at its final position once all lanes have loaded
+        // the pixel's bubble pass (what pawcs_bubble does for the other pixels, which runs beside this kernel). The carry chain
+        // "if(w_i > carried) swap else carried = w_i" keeps carried = min(w_0..w_i), so bit i of the swap mask is
+        // w_i > min(w_0..w_{i-1}): an exclusive prefix minimum over the warp's two slots (no NaN: every denominator is non-zero,
+        // checked; otherwise the chain is replayed step by step). Every word that moves or was matched is stored at its final position
+        // once all lanes hold theirs in registers.
         {
             hand_y = __shfl_sync(0xFFFFFFFFu, hand_y, 0);
             const unsigned long long matched = ((unsigned long long)(hand_y & 0x00FFFFFFu) << 32) | S.mlo;
             const bool occ_en = (hand_y & PAW_H_OCC) != 0;
             const uint32_t occ_incr = (1u + A.ctl->cooldown) << ((P.flat || P.boot) ? 1 : 0);
-            uint2 key[2]; float w[2];
-#pragma unroll
-            for(int t = 0; t < 2; ++t) {
-                const int j = (int)lane + 32 * t;
-                key[t] = j < A.NW ? A.lw_key[(size_t)j * A.plane + pix] : make_uint2(0u, 0u);
-                w[t] = j < A.NW ? paw_weight(key[t], P.wk) : 0.0f;
-            }
             unsigned long long swaps = 0ull;
-            float last_w = FLT_MAX;
-            for(int i = 0; i < A.NW; ++i) { // :1044-1052 (warp-uniform)
-                const float wi = __shfl_sync(0xFFFFFFFFu, i < 32 ? w[0] : w[1], i & 31);
-                if(wi > last_w) swaps |= 1ull << i; else last_w = wi;
+            if(__any_sync(0xFFFFFFFFu, zero_den)) {
+                float last_w = FLT_MAX;
+                for(int i = 0; i < A.NW; ++i) { // :1044-1052 (warp-uniform)
+                    const float wi_ = __shfl_sync(0xFFFFFFFFu, i < 32 ? w[0] : w[1], i & 31);
+                    if(wi_ > last_w) swaps |= 1ull << i; else last_w = wi_;
+                }
+            } else {
+                float sA = w[0], sB = (int)lane + 32 < A.NW ? w[1] : FLT_MAX;
+#pragma unroll
+                for(int d = 1; d < 32; d <<= 1) {
+                    const float ta = __shfl_up_sync(0xFFFFFFFFu, sA, d), tb = __shfl_up_sync(0xFFFFFFFFu, sB, d);
+                    if((int)lane >= d) { sA = fminf(sA, ta); sB = fminf(sB, tb); }
+                }
+                const float totA = __shfl_sync(0xFFFFFFFFu, sA, 31);
+                float exA = __shfl_up_sync(0xFFFFFFFFu, sA, 1), exB = __shfl_up_sync(0xFFFFFFFFu, sB, 1);
+                if(lane == 0) { exA = FLT_MAX; exB = totA; } else exB = fminf(exB, totA);
+                const uint32_t lo = __ballot_sync(0xFFFFFFFFu, (int)lane < A.NW && w[0] > exA);
+                const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (int)lane + 32 < A.NW && w[1] > exB);
+                swaps = ((unsigned long long)hi << 32) | lo;
             }
-            bool moved[2], upd[2]; size_t dst[2]; uint32_t first[2]; Col mc[2]; Desc md[2];
+            bool moved[2], upd[2]; size_t dst[2]; uint32_t first[2];
 #pragma unroll
             for(int t = 0; t < 2; ++t) {
                 const int j = (int)lane + 32 * t;
-                moved[t] = false; upd[t] = false; dst[t] = 0; first[t] = 0; mc[t] = Col(); md[t] = Desc();
+                moved[t] = false; upd[t] = false; dst[t] = 0; first[t] = 0;
                 if(j < A.NW) {
                     const size_t at = (size_t)j * A.plane + pix;
                     const bool down = (swaps >> j) & 1ull;
@@ -607,14 +650,14 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
                     moved[t] = pos != j; upd[t] = (matched >> j) & 1ull;
                     dst[t] = (size_t)pos * A.plane + pix;
                     if(moved[t] || upd[t]) first[t] = A.lw_first[at];
+                    if(moved[t] && !have_cd[t]) { bc[t] = ((const Col*)A.lw_color)[at]; bd[t] = ((const Desc*)A.lw_desc)[at]; }
                     if(upd[t]) key[t] = make_uint2((occ_en && w[t] < 1.0f) ? key[t].x + occ_incr : key[t].x, first[t] + P.frame); // :1035-1038
-                    if(moved[t]) { mc[t] = ((const Col*)A.lw_color)[at]; md[t] = ((const Desc*)A.lw_desc)[at]; }
                 }
             }
             __syncwarp();
 #pragma unroll
             for(int t = 0; t < 2; ++t) {
-                if(moved[t]) { A.lw_key[dst[t]] = key[t]; A.lw_first[dst[t]] = first[t]; ((Col*)A.lw_color)[dst[t]] = mc[t]; ((Desc*)A.lw_desc)[dst[t]] = md[t]; }
+                if(moved[t]) { A.lw_key[dst[t]] = key[t]; A.lw_first[dst[t]] = first[t]; ((Col*)A.lw_color)[dst[t]] = bc[t]; ((Desc*)A.lw_desc)[dst[t]] = bd[t]; }
                 else if(upd[t]) A.lw_key[dst[t]] = key[t];
             }
             __syncwarp();
@@ -832,7 +875,7 @@ __global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A, int t
 #define PAWB_MIN_BLOCKS 5
 #endif
 #ifndef PAWB_KW
-#define PAWB_KW 3
+#define PAWB_KW 4
 #endif
 constexpr int PAWB_K = PAWB_KW;
 template<int CH> struct PawHit {
@@ -874,12 +917,12 @@ __device__ __forceinline__ uint32_t paw_hit_word(const PawArgs& A, const PawHit<
 }
 /// counter / colour / descriptor updates of a credited word (Q8: the 1-channel path of the reference updates a by-value copy, PAWCS.cpp:838)
 template<int CH>
-__device__ __forceinline__ void paw_hit_commit(const PawArgs& A, const PawHit<CH>& Hh, size_t at, uint32_t flags, uint2 key, float w, typename Pack<CH>::Desc bd, uint32_t frame) {
+__device__ __forceinline__ void paw_hit_commit(const PawArgs& A, const PawHit<CH>& Hh, size_t at, uint32_t flags, uint2 key, uint32_t first, float w, typename Pack<CH>::Desc bd, uint32_t frame) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     if(CH == 1) return;
     const uint32_t incr = paw_bits(bd) < (CH == 1 ? 2u : 4u) ? Hh.occ_incr * 2u : Hh.occ_incr;
-    A.lw_key[at] = make_uint2(w < 1.0f ? key.x + incr : key.x, A.lw_first[at] + frame); // last = frame
+    A.lw_key[at] = make_uint2(w < 1.0f ? key.x + incr : key.x, first + frame); // last = frame
     if(flags & 2u) ((Desc*)A.lw_desc)[at] = Hh.sd;
     if(flags & 4u) ((Col*)A.lw_color)[at] = Hh.sc;
 }
@@ -949,14 +992,17 @@ __global__ void __launch_bounds__(256, PAWB_MIN_BLOCKS) pawcs_phaseB(const PawAr
         }
 #pragma unroll
         for(int j = 0; j < PAWB_K; ++j)
-            if(fl[j] & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl[j], key[j], w[j], bd[j], frame);
+            if(fl[j] & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl[j], key[j], CH == 1 ? 0u : A.lw_first[(size_t)j * A.plane + pix], w[j], bd[j], frame);
         if(sum < init_w) paw_hit_new_word<CH>(A, Hh, pix, frame);
         hits &= hits - 1u;
     }
 }
 
+#ifndef PAWBT_MIN_BLOCKS
+#define PAWBT_MIN_BLOCKS 6
+#endif
 template<int CH>
-__global__ void __launch_bounds__(PAW_TAIL_THREADS) pawcs_phaseB_tail(const PawArgs A) {
+__global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWBT_MIN_BLOCKS) pawcs_phaseB_tail(const PawArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
     constexpr uint32_t WPB = PAW_TAIL_THREADS / 32;
@@ -977,13 +1023,15 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS) pawcs_phaseB_tail(const PawA
             const int r_ = hi_ / 5, k = hi_ - r_ * 5;
             PawHit<CH> Hh;
             paw_hit_load<CH>(A, Hh, x, y, x - 2 + k, y + r_ - 2, cooldown, boot);
+            // a word costs a 32-byte sector per plane here (one target per warp): colour / descriptor round by round, key and first only
+            // for the credited words
             float sum = 0.0f;
             bool stop = false;
-            for(int base = 0; base < A.NW && !stop; base += 32) {
+            for(int base = 0; base < A.NW && !stop; base += 32) { // (warp-uniform)
                 const int j = base + (int)lane;
-                uint32_t fl = 0u; float w = 0.0f; uint2 key = make_uint2(0, 0); Desc bd = Desc();
+                const size_t at = (size_t)j * A.plane + pix;
+                uint32_t fl = 0u; float w = 0.0f; uint2 key = make_uint2(0u, 0u); Desc bd = Desc();
                 if(j < A.NW) {
-                    const size_t at = (size_t)j * A.plane + pix;
                     bd = ((const Desc*)A.lw_desc)[at];
                     fl = paw_hit_word<CH>(A, Hh, j, ((const Col*)A.lw_color)[at], bd, frame, boot);
                     if(fl & 1u) { key = A.lw_key[at]; w = paw_weight(key, wk); }
@@ -996,7 +1044,7 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS) pawcs_phaseB_tail(const PawA
                     upto |= 1u << jj;
                     if(!(sum < Hh.wthr)) stop = true;
                 }
-                if((upto >> lane) & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl, key, w, bd, frame);
+                if((upto >> lane) & 1u) paw_hit_commit<CH>(A, Hh, at, fl, key, CH == 1 ? 0u : A.lw_first[at], w, bd, frame);
             }
             if(sum < init_w && lane == 0) paw_hit_new_word<CH>(A, Hh, pix, frame);
             __syncwarp();
