@@ -305,6 +305,69 @@ def bench_streams64(lv, torch, dev, local, rank, world, barrier, all_max):
     return out
 
 
+def bench_other_configs(lv, torch, dev, local, rank, world, barrier, all_max, hbm_peak):
+    """BASELINE configs[0..2] (parity-test cases, reported so that a driver-run record holds them): one stream per GPU, frames resident in
+    HBM, CUDA events on the instance stream, median of 5 blocks of 100 frames after 60 untimed bootstrap frames"""
+    from litiv_b200.synth import SynthSequence
+    out = {}
+    cases = [("subsense_320x240_rgb", "SuBSENSE 320x240 RGB (BASELINE.json configs[0])", lv.BackgroundSubtractorSuBSENSE, 320, 240, 3),
+             ("lobster_320x240_gray", "LOBSTER 320x240 gray (BASELINE.json configs[1])", lv.BackgroundSubtractorLOBSTER, 320, 240, 1),
+             ("pawcs_640x480_rgb", "PAWCS 640x480 RGB (BASELINE.json configs[2])", lv.BackgroundSubtractorPAWCS, 640, 480, 3)]
+    for key, name, cls, w, h, c in cases:
+        n_unique, blocks, steps = 48, 5, 100
+        seq = SynthSequence(w, h, c, seed=7000 + rank, fg_area=FG_AREA)
+        frames = [seq.frame(t) for t in range(n_unique)]
+        pitch = (w * c + 127) // 128 * 128
+        d_frames = torch.zeros((n_unique, h, pitch), dtype=torch.uint8, device=dev)
+        for i, f in enumerate(frames):
+            d_frames[i, :, :w * c] = torch.from_numpy(f.reshape(h, w * c)).to(dev)
+        d_mask = torch.zeros((h, w), dtype=torch.uint8, device=dev)
+        sub = cls(device=local, seed=rank)
+        sub.initialize(frames[0])
+        stream = torch.cuda.ExternalStream(sub.stream, device=dev)
+        k = [0]
+
+        def step():
+            k[0] += 1
+            sub.apply_device(d_frames[pingpong(k[0], n_unique)].data_ptr(), pitch, d_mask.data_ptr(), lr_for(k[0]) if cls is not lv.BackgroundSubtractorPAWCS else 0.0)
+        for _ in range(BOOT_FRAMES):
+            step()
+        sub.sync()
+        barrier()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+        evs[0].record(stream)
+        for b in range(blocks):
+            for _ in range(steps):
+                step()
+            if b == blocks - 1 and hasattr(sub, "flush"):
+                sub.flush()
+            evs[b + 1].record(stream)
+        sub.sync()
+        torch.cuda.synchronize()
+        ms = float(np.median(all_max([evs[b].elapsed_time(evs[b + 1]) for b in range(blocks)]))) / steps
+        o = {"workload": name, "frame": [w, h, c], "ms_per_frame": ms, "fps_per_stream": 1e3 / ms, "mpx_per_s": w * h * world / (ms * 1e-3) / 1e6,
+             "timing": f"median of {blocks} blocks of {steps} frames, CUDA events on the instance stream, max over ranks"}
+        if cls is lv.BackgroundSubtractorPAWCS:
+            sub.set_collect_stats(True)
+            for _ in range(32):
+                step()
+            sub.sync()
+            st = sub.stats()
+            roi_px = st["roi_px"] / max(st["frames"], 1)
+            sw = st["samples_scanned"] / max(st["roi_px"], 1)
+            # SURVEY.md 8(d): B_alg = 125 + 21 (s_w + u_w) + 25 + 4 g; u_w (word updates) and g (global-map touches) are not instrumented: 0.3 and 1
+            b_alg = 125.0 + 21.0 * (sw + 0.3) + 25.0 + 4.0
+            # the formula leaves out what the reference's per-frame bubble pass over ALL words has to read: 50 keys x 8 B per pixel
+            b_keys = 8.0 * 50
+            o["roofline"] = {"bound": "hbm", "words_scanned_per_px": sw, "alg_bytes_per_px": b_alg, "achieved": roi_px * b_alg / (ms * 1e-3) / 1e9,
+                             "frac": roi_px * b_alg / (ms * 1e-3) / 1e9 / hbm_peak, "peak": hbm_peak, "unit": "GB/s",
+                             "frac_with_bubble_pass_keys": roi_px * (b_alg + b_keys) / (ms * 1e-3) / 1e9 / hbm_peak,
+                             "classified_fg_share": st["fg_px"] / max(st["roi_px"], 1)}
+        out[key] = o
+        del sub
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,6 +376,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streams64", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--repeats", type=int, default=REPEATS)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -454,9 +518,12 @@ def main():
     ms_blk, sync_ms, e2e_ms = float(np.median(block_all)), float(np.median(sync_all)), float(np.median(e2e_all))
 
     s64 = None
+    del sub
     if not args.no_streams64:
-        del sub
         s64 = bench_streams64(lv, torch, dev, local, rank, world, barrier, all_max)
+    others = None
+    if not args.no_other_configs:
+        others = bench_other_configs(lv, torch, dev, local, rank, world, barrier, all_max, hbm_peak)
 
     if rank == 0:
         ms_step = ms_blk / args.steps
@@ -492,6 +559,8 @@ def main():
         }
         if s64 is not None:
             line["streams64_vga"] = s64
+        if others is not None:
+            line["other_configs"] = others
         if not args.no_cpu_baseline:
             v, kind, wall = run_cpu(1, 12)
             line["cpu_baseline"] = {"value": v, "unit": "Mpx/s", "cores": 1, "kind": kind,

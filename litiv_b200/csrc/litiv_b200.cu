@@ -174,7 +174,7 @@ struct lvb_context {
     // PAWCS
     int NW = 0, NG = 0, gW = 0, gH = 0;
     uint32_t paw_frame = 1;   // host mirror of FrameCtl::frame_idx (decides which frames run maintenance / the 500-frame check)
-    uint2* lw_key = nullptr; uint32_t* lw_first = nullptr; void *lw_color = nullptr, *lw_desc = nullptr;   // key = (occurrences, first + last), pawcs.cuh
+    uint2* lw_key = nullptr; void* lw_rec = nullptr;   // key = (occurrences, first + last), record = (colour, descriptors, first): pawcs.cuh
     uint8_t* glut = nullptr; float *gmap = nullptr, *gmap_tmp = nullptr; GDict* gd = nullptr;
     uint32_t *roi255 = nullptr, *illum = nullptr, *did = nullptr, *dil = nullptr, *gop_bits = nullptr;
     uint4* paw_intents = nullptr; float* gop_w = nullptr; uint8_t* gop_g = nullptr; uint8_t* ds_roi = nullptr; uint8_t* bgimg = nullptr;
@@ -183,15 +183,16 @@ struct lvb_context {
     size_t col_bytes() const { return C == 1 ? 1 : 4; }
     size_t desc_bytes() const { return C == 1 ? 2 : 8; }
     size_t rec_bytes() const { return C == 1 ? 4 : 16; }
+    size_t paw_rec_bytes() const { return C == 1 ? 8 : 16; }   // PawRec<C>::T
 
     void free_all() {
         void* ptrs[] = {own_slot, wl_ctx, wl2_idx, eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
-                        lw_first, lw_key, lw_color, lw_desc, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
+                        lw_rec, lw_key, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
         own_slot = nullptr; wl_ctx = nullptr; wl2_idx = nullptr; wl_cap = 0;
         eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; fin_pending = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
-        lw_first = nullptr; lw_key = nullptr; lw_color = lw_desc = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
+        lw_rec = nullptr; lw_key = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
         if(h_img) cudaFreeHost(h_img);
         if(h_mask) cudaFreeHost(h_mask);
@@ -379,12 +380,14 @@ void paw_initialize(lvb_context* c, FrameCtl& f, size_t orig) {
     f.median_k = c->median_k; f.auto_reset = 1;
     const int NW = c->NW, NG = c->NG;
     cudaStream_t st = c->stream;
-    c->lw_first = dalloc<uint32_t>(st, (size_t)NW * c->plane, false);
     c->lw_key = dalloc<uint2>(st, (size_t)NW * c->plane, false);
-    c->lw_color = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->col_bytes());
-    c->lw_desc = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->desc_bytes());
-    { std::vector<uint32_t> ones((size_t)NW * c->plane, 1u); h2d(st, c->lw_first, ones.data(), ones.size() * 4);   // (first=1,last=0,occ=0): word not created yet
-      std::vector<uint2> keys((size_t)NW * c->plane, make_uint2(0u, 1u)); h2d(st, c->lw_key, keys.data(), keys.size() * 8); }
+    c->lw_rec = dalloc<uint8_t>(st, (size_t)NW * c->plane * c->paw_rec_bytes(), false);
+    { // (first=1,last=0,occ=0): word not created yet
+      std::vector<uint2> keys((size_t)NW * c->plane, make_uint2(0u, 1u)); h2d(st, c->lw_key, keys.data(), keys.size() * 8);
+      std::vector<uint32_t> recs((size_t)NW * c->plane * (c->paw_rec_bytes() / 4), 0u);
+      const size_t rw = c->paw_rec_bytes() / 4;
+      for(size_t i = 0; i < (size_t)NW * c->plane; ++i) recs[i * rw + rw - 1] = 1u;
+      h2d(st, c->lw_rec, recs.data(), recs.size() * 4); }
     c->gmap = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
     c->gmap_tmp = dalloc<float>(st, (size_t)NG * c->gW * c->gH);
     c->gd = dalloc<GDict>(st, 1);
@@ -421,7 +424,7 @@ PawArgs paw_args(lvb_context* c, const uint8_t* img, size_t pitch, int use_tma, 
     PawArgs A{};
     A.W = c->W; A.H = c->H; A.Wp = c->Wp; A.WW = c->WW; A.NW = c->NW; A.NG = c->NG; A.gW = c->gW; A.gH = c->gH; A.plane = c->plane;
     A.img = img; A.ipitch = pitch;
-    A.lw_first = c->lw_first; A.lw_key = c->lw_key; A.lw_color = c->lw_color; A.lw_desc = c->lw_desc;
+    A.lw_key = c->lw_key; A.lw_rec = c->lw_rec;
     A.glut = c->glut; A.gmap = c->gmap; A.gmap_tmp = c->gmap_tmp; A.gd = c->gd;
     A.maps = c->maps; A.fin = c->fin; A.last_color = c->last_color; A.last_desc = c->last_desc;
     A.roi_bits = c->roi_bits; A.roi255_bits = c->roi255; A.raw_bits = c->raw; A.unstable_bits = c->unstable; A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg;
@@ -1052,36 +1055,21 @@ void state_get(lvb_context* c, const std::string& n, void* out, size_t bytes) {
             d[6] = c->median_k; d[7] = g.weight_offset; d[8] = g.moving_camera; d[9] = g.last_nonflat_ratio; d[10] = (double)c->roi_count; d[11] = (double)c->orig_roi_count; d[12] = f.refresh_epoch;
             return;
         }
-        if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
-            std::vector<uint32_t> fi(nw * c->plane); std::vector<uint2> ke(nw * c->plane); // device layout: first, key = (occ, first + last)
-            d2h(c->stream, fi.data(), c->lw_first, fi.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
-            uint32_t* o = (uint32_t*)out;
+        if(n == "lw_first" || n == "lw_last" || n == "lw_occ" || n == "lw_color" || n == "lw_desc") {
+            // device layout (pawcs.cuh): key = (occ, first + last); record = (colour, d0|d1<<16, d2, first) / 1 channel (colour | desc<<16, first)
+            const size_t rw = c->paw_rec_bytes() / 4;
+            std::vector<uint32_t> re(nw * c->plane * rw); std::vector<uint2> ke(nw * c->plane);
+            d2h(c->stream, re.data(), c->lw_rec, re.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
             for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                const uint32_t last = ke[at].y - fi[at];
-                uint32_t v = n == "lw_first" ? fi[at] : n == "lw_last" ? last : ke[at].x;
-                if(n == "lw_first" && v == 1u && last == 0u) v = 0; // "not created" marker (non-ROI pixels)
-                o[((size_t)y * W + x) * nw + i] = v;
-            }
-            return;
-        }
-        if(n == "lw_color") {
-            std::vector<uint8_t> h(nw * c->plane * c->col_bytes());
-            d2h(c->stream, h.data(), c->lw_color, h.size());
-            uint8_t* o = (uint8_t*)out;
-            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                o[(((size_t)y * W + x) * nw + i) * C + k] = C == 1 ? h[at] : h[at * 4 + k];
-            }
-            return;
-        }
-        if(n == "lw_desc") {
-            std::vector<uint16_t> h(nw * c->plane * c->desc_bytes() / 2);
-            d2h(c->stream, h.data(), c->lw_desc, h.size() * 2);
-            uint16_t* o = (uint16_t*)out;
-            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                o[(((size_t)y * W + x) * nw + i) * C + k] = C == 1 ? h[at] : h[at * 4 + k];
+                const size_t at = i * c->plane + (size_t)y * Wp + x, o = ((size_t)y * W + x) * nw + i;
+                const uint32_t* r = &re[at * rw];
+                const uint32_t first = r[rw - 1], last = ke[at].y - first;
+                if(n == "lw_first") ((uint32_t*)out)[o] = (first == 1u && last == 0u) ? 0u : first; // "not created" marker (non-ROI pixels)
+                else if(n == "lw_last") ((uint32_t*)out)[o] = last;
+                else if(n == "lw_occ") ((uint32_t*)out)[o] = ke[at].x;
+                else if(n == "lw_color") { for(int k = 0; k < C; ++k) ((uint8_t*)out)[o * C + k] = (uint8_t)(r[0] >> (8 * k)); }
+                else { if(C == 1) ((uint16_t*)out)[o] = (uint16_t)(r[0] >> 16);
+                       else { ((uint16_t*)out)[o * 3] = (uint16_t)(r[1] & 0xFFFFu); ((uint16_t*)out)[o * 3 + 1] = (uint16_t)(r[1] >> 16); ((uint16_t*)out)[o * 3 + 2] = (uint16_t)(r[2] & 0xFFFFu); } }
             }
             return;
         }
@@ -1190,38 +1178,27 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             c->paw_frame = f.frame_idx;
             return;
         }
-        if(n == "lw_first" || n == "lw_last" || n == "lw_occ") {
-            std::vector<uint32_t> fi(nw * c->plane); std::vector<uint2> ke(nw * c->plane); // device layout: first, key = (occ, first + last)
-            d2h(c->stream, fi.data(), c->lw_first, fi.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
-            const uint32_t* sI = (const uint32_t*)in;
+        if(n == "lw_first" || n == "lw_last" || n == "lw_occ" || n == "lw_color" || n == "lw_desc") {
+            const size_t rw = c->paw_rec_bytes() / 4;
+            std::vector<uint32_t> re(nw * c->plane * rw); std::vector<uint2> ke(nw * c->plane);
+            d2h(c->stream, re.data(), c->lw_rec, re.size() * 4); d2h(c->stream, ke.data(), c->lw_key, ke.size() * 8);
             for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                const uint32_t v = sI[((size_t)y * W + x) * nw + i], last = ke[at].y - fi[at];
-                if(n == "lw_first") { fi[at] = v; ke[at].y = v + last; }
-                else if(n == "lw_last") ke[at].y = fi[at] + v;
-                else ke[at].x = v;
+                const size_t at = i * c->plane + (size_t)y * Wp + x, o = ((size_t)y * W + x) * nw + i;
+                uint32_t* r = &re[at * rw];
+                const uint32_t first = r[rw - 1], last = ke[at].y - first;
+                if(n == "lw_first") { const uint32_t v = ((const uint32_t*)in)[o]; r[rw - 1] = v; ke[at].y = v + last; }
+                else if(n == "lw_last") ke[at].y = first + ((const uint32_t*)in)[o];
+                else if(n == "lw_occ") ke[at].x = ((const uint32_t*)in)[o];
+                else if(n == "lw_color") {
+                    uint32_t v = 0; for(int k = 0; k < C; ++k) v |= (uint32_t)((const uint8_t*)in)[o * C + k] << (8 * k);
+                    r[0] = C == 1 ? ((r[0] & 0xFFFF0000u) | v) : v;
+                } else {
+                    const uint16_t* d = (const uint16_t*)in + o * C;
+                    if(C == 1) r[0] = (r[0] & 0x0000FFFFu) | ((uint32_t)d[0] << 16);
+                    else { r[1] = (uint32_t)d[0] | ((uint32_t)d[1] << 16); r[2] = d[2]; }
+                }
             }
-            h2d(c->stream, c->lw_first, fi.data(), fi.size() * 4); h2d(c->stream, c->lw_key, ke.data(), ke.size() * 8);
-            return;
-        }
-        if(n == "lw_color") {
-            std::vector<uint8_t> h(nw * c->plane * c->col_bytes(), 0);
-            const uint8_t* sI = (const uint8_t*)in;
-            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                if(C == 1) h[at] = sI[((size_t)y * W + x) * nw + i]; else h[at * 4 + k] = sI[(((size_t)y * W + x) * nw + i) * C + k];
-            }
-            h2d(c->stream, c->lw_color, h.data(), h.size());
-            return;
-        }
-        if(n == "lw_desc") {
-            std::vector<uint16_t> h(nw * c->plane * c->desc_bytes() / 2, 0);
-            const uint16_t* sI = (const uint16_t*)in;
-            for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(size_t i = 0; i < nw; ++i) for(int k = 0; k < C; ++k) {
-                const size_t at = i * c->plane + (size_t)y * Wp + x;
-                if(C == 1) h[at] = sI[((size_t)y * W + x) * nw + i]; else h[at * 4 + k] = sI[(((size_t)y * W + x) * nw + i) * C + k];
-            }
-            h2d(c->stream, c->lw_desc, h.data(), h.size() * 2);
+            h2d(c->stream, c->lw_rec, re.data(), re.size() * 4); h2d(c->stream, c->lw_key, ke.data(), ke.size() * 8);
             return;
         }
         if(n == "glut") {

@@ -10,8 +10,10 @@
 //       -> motion analysis + frame tail (LUT adaptation, reset / moving-camera logic on the device) -> conditional refresh.
 // The deterministic parallel semantics ("snapshot" semantics) are specified in DESIGN.md section 2.
 //
-// HBM layout (per stream; Wp = W rounded up to 32): local words are four sample-major SoA planes [NW][H][Wp]:
-// key uint2 (occurrences, first + last mod 2^32), first u32, colour u32 B,G,R,0, descriptors uint2. The weight of a word,
+// HBM layout (per stream; Wp = W rounded up to 32): local words are two sample-major planes [NW][H][Wp]:
+// key uint2 (occurrences, first + last mod 2^32) and a record uint4 (colour B,G,R,0 | d0|d1<<16 | d2 | first; 1 channel: uint2
+// colour|desc<<16, first): colour, descriptors and `first` always travel together (scan, swaps, new words), and the kernels that
+// work one pixel per warp pay one 32-byte sector per word and plane, so one 16-byte record instead of three planes. The weight of a word,
 // occ / ((last - first) + 2 (frame - last) + offset) = occ / (2 frame + offset - (first + last)), only needs the key, and every
 // frame every pixel re-weights all NW words: 8 B per word in one 64-bit load instead of three 32-bit planes. `first` is touched
 // only when a word is matched (last = frame  =>  key.y = first + frame), created or moved; colour / descriptor only while the
@@ -49,7 +51,7 @@ struct PawArgs {
     int W, H, Wp, WW, NW, NG, gW, gH;
     size_t plane;
     const uchar* img; size_t ipitch;
-    uint2* lw_key; uint32_t* lw_first; void* lw_color; void* lw_desc;   // key = (occurrences, first + last)
+    uint2* lw_key; void* lw_rec;   // key = (occurrences, first + last); record = (colour, descriptors, first): PawRec<CH>
     uchar* glut; float* gmap; float* gmap_tmp; GDict* gd;
     float4* maps; float2* fin; void* last_color; void* last_desc;
     const uint32_t* roi_bits; const uint32_t* roi255_bits;
@@ -123,6 +125,32 @@ __device__ __forceinline__ bool paw_color_within(uint32_t cur, uint32_t bg, uint
     return (l1 >> 1) + paw_cdist3(cur, bg) * 4u <= thr;
 }
 
+/// word record (see the layout note at the top of the file)
+template<int CH> struct PawRec;
+template<> struct PawRec<3> {
+    typedef uint4 T;
+    static __device__ __forceinline__ uint32_t col(const T& r) { return r.x; }
+    static __device__ __forceinline__ uint2 desc(const T& r) { return make_uint2(r.y, r.z); }
+    static __device__ __forceinline__ uint32_t first(const T& r) { return r.w; }
+    static __device__ __forceinline__ T make(uint32_t c, uint2 d, uint32_t f) { return make_uint4(c, d.x, d.y, f); }
+    static __device__ __forceinline__ void store_cd(T* p, uint32_t c, uint2 d) { *(uint2*)p = make_uint2(c, d.x); ((uint32_t*)p)[2] = d.y; }
+    static __device__ __forceinline__ void store_col(T* p, uint32_t c) { ((uint32_t*)p)[0] = c; }
+    static __device__ __forceinline__ void store_desc(T* p, uint2 d) { ((uint32_t*)p)[1] = d.x; ((uint32_t*)p)[2] = d.y; }
+    static __device__ __forceinline__ uint32_t load_first(const T* p) { return ((const uint32_t*)p)[3]; }
+};
+template<> struct PawRec<1> {
+    typedef uint2 T;
+    static __device__ __forceinline__ uchar col(const T& r) { return (uchar)(r.x & 0xFFu); }
+    static __device__ __forceinline__ ushort desc(const T& r) { return (ushort)(r.x >> 16); }
+    static __device__ __forceinline__ uint32_t first(const T& r) { return r.y; }
+    static __device__ __forceinline__ T make(uchar c, ushort d, uint32_t f) { return make_uint2((uint32_t)c | ((uint32_t)d << 16), f); }
+    static __device__ __forceinline__ void store_cd(T* p, uchar c, ushort d) { ((uint32_t*)p)[0] = (uint32_t)c | ((uint32_t)d << 16); }
+    static __device__ __forceinline__ void store_col(T* p, uchar c) { ((uchar*)p)[0] = c; }
+    static __device__ __forceinline__ void store_desc(T* p, ushort d) { ((ushort*)p)[1] = d; }
+    static __device__ __forceinline__ uint32_t load_first(const T* p) { return ((const uint32_t*)p)[1]; }
+};
+#define PAW_REC(A) ((typename PawRec<CH>::T*)(A).lw_rec)
+
 template<int CH> struct PawPlanes {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -130,17 +158,13 @@ template<int CH> struct PawPlanes {
 __device__ __forceinline__ uint32_t col_as_u32(const uint32_t& v) { return v; }
 __device__ __forceinline__ uint32_t col_as_u32(const uchar& v) { return v; }
 
-/// exchange dictionary positions i and i-1 of one pixel (all four planes)
+/// exchange dictionary positions i and i-1 of one pixel (both planes)
 template<int CH>
 __device__ __forceinline__ void paw_swap(const PawArgs& A, size_t pix, int i) {
-    typedef typename Pack<CH>::Col Col;
-    typedef typename Pack<CH>::Desc Desc;
     const size_t a = (size_t)i * A.plane + pix, b = a - A.plane;
-    const uint2 k = A.lw_key[a]; const uint32_t f = A.lw_first[a];
-    const Col c = ((Col*)A.lw_color)[a]; const Desc d = ((Desc*)A.lw_desc)[a];
-    A.lw_key[a] = A.lw_key[b]; A.lw_first[a] = A.lw_first[b];
-    ((Col*)A.lw_color)[a] = ((Col*)A.lw_color)[b]; ((Desc*)A.lw_desc)[a] = ((Desc*)A.lw_desc)[b];
-    A.lw_key[b] = k; A.lw_first[b] = f; ((Col*)A.lw_color)[b] = c; ((Desc*)A.lw_desc)[b] = d;
+    const uint2 k = A.lw_key[a]; const typename PawRec<CH>::T r = PAW_REC(A)[a];
+    A.lw_key[a] = A.lw_key[b]; PAW_REC(A)[a] = PAW_REC(A)[b];
+    A.lw_key[b] = k; PAW_REC(A)[b] = r;
 }
 
 /// search the pixel's sorted global-word LUT (PAWCS.cpp:1073-1079 / :1119-1125); returns the identity or -1.
@@ -250,7 +274,7 @@ __device__ __forceinline__ void paw_test_word(const PawArgs& A, const uchar* s_l
         const uint32_t mod = S.illum_cur ? (P.rate / 2u + 1u) : P.rate;
         if((philox_draw(A.seed, P.frame, P.pixid, 4u + (uint32_t)i, DOM_PAWCS_A) % mod) == 0u) {
             if(DEFER) deferred |= 1u << i;
-            else { const size_t at = (size_t)i * A.plane + P.pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
+            else PawRec<CH>::store_cd(PAW_REC(A) + (size_t)i * A.plane + P.pix, P.cur_pack, P.intra_pack);
             S.did = true; S.illum_cur = 2u;
         }
     }
@@ -382,7 +406,7 @@ pawcs_scan(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
             if(k < A.NW) {
                 const size_t at = (size_t)k * A.plane + pix;
                 wkey[k] = A.lw_key[at];
-                bc[k] = ((const Col*)A.lw_color)[at]; bd[k] = ((const Desc*)A.lw_desc)[at];
+                { const typename PawRec<CH>::T r = PAW_REC(A)[at]; bc[k] = PawRec<CH>::col(r); bd[k] = PawRec<CH>::desc(r); }
             }
         m0 = A.maps[pix * 2]; m1 = A.maps[pix * 2 + 1]; fin = A.fin[pix];
     }
@@ -416,7 +440,7 @@ pawcs_scan(const PawArgs A, const __grid_constant__ CUtensorMap tmap) {
         if(finished) {
 #pragma unroll
             for(int k = 0; k < PAW_K; ++k)
-                if((deferred >> k) & 1u) { const size_t at = (size_t)k * A.plane + pix; ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack; }
+                if((deferred >> k) & 1u) PawRec<CH>::store_cd(PAW_REC(A) + (size_t)k * A.plane + pix, P.cur_pack, P.intra_pack);
             B = paw_finish<CH>(A, s_gbits, s_gcolor, P, S, M, x, y);
             did = S.did; scanned = S.scanned;
         }
@@ -503,11 +527,11 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
         for(int c = 0; c < CH; ++c) { P.L[c] = lbsp_lookup_smem<CH>(A.img, (int)A.ipitch, x, y, c); cur[c] = A.img[(size_t)y * A.ipitch + (size_t)x * CH + c]; }
         // lane j holds words j and j + 32. All keys at once (the bubble pass below needs every weight); colour / descriptor round by
         // round: a word costs a 32-byte sector per plane here (one pixel per warp), and most pixels of the list stop within the first round
-        Col bc[2]; Desc bd[2]; uint2 key[2]; float w[2]; bool have_cd[2];
+        Col bc[2]; Desc bd[2]; uint2 key[2]; float w[2]; bool have_cd[2]; uint32_t first[2];
 #pragma unroll
         for(int t = 0; t < 2; ++t) {
             const int j = (int)lane + 32 * t;
-            bc[t] = Col(); bd[t] = Desc(); have_cd[t] = false;
+            bc[t] = Col(); bd[t] = Desc(); have_cd[t] = false; first[t] = 0;
             key[t] = j < A.NW ? A.lw_key[(size_t)j * A.plane + pix] : make_uint2(0u, 0u);
         }
         const uint32_t gv_lane = (int)lane < A.NG ? (uint32_t)A.glut[(size_t)lane * A.plane + pix] : 0u; // global-word LUT, position = lane
@@ -530,7 +554,7 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
                 uint32_t mix = 0, dd = 0, drw = 0;
                 if(i < A.NW) {
                     const size_t at = (size_t)i * A.plane + pix;
-                    bc[t] = ((const Col*)A.lw_color)[at]; bd[t] = ((const Desc*)A.lw_desc)[at]; have_cd[t] = true;
+                    { const typename PawRec<CH>::T r = PAW_REC(A)[at]; bc[t] = PawRec<CH>::col(r); bd[t] = PawRec<CH>::desc(r); first[t] = PawRec<CH>::first(r); have_cd[t] = true; }
                     const uint32_t l1 = paw_l1<CH>(P.cur32, col_as_u32(bc[t]));
                     if((CH == 1 ? l1 : (l1 >> 1)) <= P.thrC) {
                         mix = CH == 1 ? l1 : (l1 >> 1) + paw_cdist3(P.cur32, col_as_u32(bc[t])) * 4u;
@@ -569,7 +593,7 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
                 if(!stop) S.scanned = (uint32_t)min(base + 32, A.NW);
                 if((done >> lane) & 1u) { // illumination update of word i, in place (the bubble pass below moves it with the rest of the word)
                     const size_t at = (size_t)i * A.plane + pix;
-                    ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack;
+                    PawRec<CH>::store_cd(PAW_REC(A) + at, P.cur_pack, P.intra_pack);
                     bc[t] = P.cur_pack; bd[t] = P.intra_pack;
                 }
             }
@@ -638,33 +662,33 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
                 const uint32_t hi = __ballot_sync(0xFFFFFFFFu, (int)lane + 32 < A.NW && w[1] > exB);
                 swaps = ((unsigned long long)hi << 32) | lo;
             }
-            bool moved[2], upd[2]; size_t dst[2]; uint32_t first[2];
+            bool moved[2], upd[2]; size_t dst[2];
 #pragma unroll
             for(int t = 0; t < 2; ++t) {
                 const int j = (int)lane + 32 * t;
-                moved[t] = false; upd[t] = false; dst[t] = 0; first[t] = 0;
+                moved[t] = false; upd[t] = false; dst[t] = 0;
                 if(j < A.NW) {
                     const size_t at = (size_t)j * A.plane + pix;
                     const bool down = (swaps >> j) & 1ull;
                     const int pos = down ? j - 1 : j + (__ffsll((long long)~(swaps >> (j + 1))) - 1); // carried up through the run of swaps that follows
                     moved[t] = pos != j; upd[t] = (matched >> j) & 1ull;
                     dst[t] = (size_t)pos * A.plane + pix;
-                    if(moved[t] || upd[t]) first[t] = A.lw_first[at];
-                    if(moved[t] && !have_cd[t]) { bc[t] = ((const Col*)A.lw_color)[at]; bd[t] = ((const Desc*)A.lw_desc)[at]; }
+                    if(moved[t] && !have_cd[t]) { const typename PawRec<CH>::T r = PAW_REC(A)[at]; bc[t] = PawRec<CH>::col(r); bd[t] = PawRec<CH>::desc(r); first[t] = PawRec<CH>::first(r); }
+                    else if(upd[t] && !have_cd[t]) first[t] = PawRec<CH>::load_first(PAW_REC(A) + at);
                     if(upd[t]) key[t] = make_uint2((occ_en && w[t] < 1.0f) ? key[t].x + occ_incr : key[t].x, first[t] + P.frame); // :1035-1038
                 }
             }
             __syncwarp();
 #pragma unroll
             for(int t = 0; t < 2; ++t) {
-                if(moved[t]) { A.lw_key[dst[t]] = key[t]; A.lw_first[dst[t]] = first[t]; ((Col*)A.lw_color)[dst[t]] = bc[t]; ((Desc*)A.lw_desc)[dst[t]] = bd[t]; }
+                if(moved[t]) { A.lw_key[dst[t]] = key[t]; PAW_REC(A)[dst[t]] = PawRec<CH>::make(bc[t], bd[t], first[t]); }
                 else if(upd[t]) A.lw_key[dst[t]] = key[t];
             }
             __syncwarp();
             if((hand_y & PAW_H_NEW) && lane == 0) { // new local word over the last one (:1142-1153)
                 const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
-                ((Col*)A.lw_color)[at] = P.cur_pack; ((Desc*)A.lw_desc)[at] = P.intra_pack;
-                A.lw_key[at] = make_uint2(occ_incr, P.frame * 2u); A.lw_first[at] = P.frame;
+                PAW_REC(A)[at] = PawRec<CH>::make(P.cur_pack, P.intra_pack, P.frame);
+                A.lw_key[at] = make_uint2(occ_incr, P.frame * 2u);
             }
         }
     }
@@ -752,20 +776,18 @@ __global__ void __launch_bounds__(256, PAWU_MIN_BLOCKS) pawcs_bubble(const PawAr
     const uint32_t occ_incr = (1u + ctl->cooldown) << (((hand.y & PAW_H_FLAT) || gd->boot) ? 1 : 0);
     const unsigned long long matched = ((unsigned long long)(hand.y & 0x00FFFFFFu) << 32) | hand.x;
     unsigned long long ev = matched | swaps | (swaps >> 1);
-    uint2 ckey = make_uint2(0, 0); uint32_t cfirst = 0; Col ccol = Col(); Desc cdesc = Desc(); // the carried word of the current run
+    uint2 ckey = make_uint2(0, 0); typename PawRec<CH>::T crec = typename PawRec<CH>::T(); // the carried word of the current run
     // events in word order; the next event's word is fetched while the current one is stored (an event at i writes positions i-1
     // and i only, the next one reads a position > i)
-    struct Ev { int i; uint2 key; uint32_t first; Col col; Desc desc; };
+    struct Ev { int i; uint2 key; typename PawRec<CH>::T rec; };
     auto fetch = [&](Ev& e) {
         e.i = __ffsll((long long)ev) - 1;
         if(e.i < 0) return;
         ev &= ev - 1ull;
         const size_t at = (size_t)e.i * A.plane + pix;
-        e.key = A.lw_key[at]; e.first = A.lw_first[at];
-        if((swaps >> e.i) & 3ull) { e.col = ((const Col*)A.lw_color)[at]; e.desc = ((const Desc*)A.lw_desc)[at]; } // moves (down, or carried up)
+        e.key = A.lw_key[at]; e.rec = PAW_REC(A)[at];
     };
     Ev cur, nxt;
-    cur.col = Col(); cur.desc = Desc(); nxt.col = Col(); nxt.desc = Desc();
     fetch(cur);
     while(cur.i >= 0) {
         fetch(nxt);
@@ -775,22 +797,21 @@ __global__ void __launch_bounds__(256, PAWU_MIN_BLOCKS) pawcs_bubble(const PawAr
         const bool down = (swaps >> i) & 1ull, next_down = (swaps >> (i + 1)) & 1ull;
         if((matched >> i) & 1ull) { // :1035-1038: last = frame, occurrences += incr while the (old) weight is below 1
             const float w = paw_weight(key, K);
-            key = make_uint2((occ_en && w < 1.0f) ? key.x + occ_incr : key.x, cur.first + frame);
+            key = make_uint2((occ_en && w < 1.0f) ? key.x + occ_incr : key.x, PawRec<CH>::first(cur.rec) + frame);
         }
         if(down) { // word i -> position i-1; the run ends here if word i+1 stays
             const size_t ab = at - A.plane;
-            ((Col*)A.lw_color)[ab] = cur.col; ((Desc*)A.lw_desc)[ab] = cur.desc;
-            A.lw_key[ab] = key; A.lw_first[ab] = cur.first;
-            if(!next_down) { A.lw_key[at] = ckey; A.lw_first[at] = cfirst; ((Col*)A.lw_color)[at] = ccol; ((Desc*)A.lw_desc)[at] = cdesc; }
+            PAW_REC(A)[ab] = cur.rec; A.lw_key[ab] = key;
+            if(!next_down) { A.lw_key[at] = ckey; PAW_REC(A)[at] = crec; }
         } else if(next_down) { // word i is carried up through the run that starts at i+1
-            ckey = key; cfirst = cur.first; ccol = cur.col; cdesc = cur.desc;
+            ckey = key; crec = cur.rec;
         } else A.lw_key[at] = key; // matched, stays where it is
         cur = nxt;
     }
     if(hand.y & PAW_H_NEW) { // new local word over the last one (:1142-1153)
         const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
-        ((Col*)A.lw_color)[at] = ((const Col*)A.last_color)[pix]; ((Desc*)A.lw_desc)[at] = ((const Desc*)A.last_desc)[pix];
-        A.lw_key[at] = make_uint2(occ_incr, frame * 2u); A.lw_first[at] = frame;
+        PAW_REC(A)[at] = PawRec<CH>::make(((const Col*)A.last_color)[pix], ((const Desc*)A.last_desc)[pix], frame);
+        A.lw_key[at] = make_uint2(occ_incr, frame * 2u);
     }
 }
 
@@ -872,7 +893,7 @@ __global__ void __launch_bounds__(128) pawcs_gword_finish(const PawArgs A, int t
 /// a list with its remaining hits and finished by pawcs_phaseB_tail: one target per WARP, one word per lane, the sequential part
 /// (weight sum in word order) replayed over the ballot of the credited words.
 #ifndef PAWB_MIN_BLOCKS
-#define PAWB_MIN_BLOCKS 5
+#define PAWB_MIN_BLOCKS 4
 #endif
 #ifndef PAWB_KW
 #define PAWB_KW 4
@@ -923,14 +944,14 @@ __device__ __forceinline__ void paw_hit_commit(const PawArgs& A, const PawHit<CH
     if(CH == 1) return;
     const uint32_t incr = paw_bits(bd) < (CH == 1 ? 2u : 4u) ? Hh.occ_incr * 2u : Hh.occ_incr;
     A.lw_key[at] = make_uint2(w < 1.0f ? key.x + incr : key.x, first + frame); // last = frame
-    if(flags & 2u) ((Desc*)A.lw_desc)[at] = Hh.sd;
-    if(flags & 4u) ((Col*)A.lw_color)[at] = Hh.sc;
+    if(flags & 2u) PawRec<CH>::store_desc(PAW_REC(A) + at, Hh.sd);
+    if(flags & 4u) PawRec<CH>::store_col(PAW_REC(A) + at, Hh.sc);
 }
 template<int CH>
 __device__ __forceinline__ void paw_hit_new_word(const PawArgs& A, const PawHit<CH>& Hh, size_t pix, uint32_t frame) {
     const size_t at = (size_t)(A.NW - 1) * A.plane + pix;
-    ((typename Pack<CH>::Col*)A.lw_color)[at] = Hh.sc; ((typename Pack<CH>::Desc*)A.lw_desc)[at] = Hh.sd;
-    A.lw_key[at] = make_uint2(Hh.occ_incr, frame * 2u); A.lw_first[at] = frame;
+    PAW_REC(A)[at] = PawRec<CH>::make(Hh.sc, Hh.sd, frame);
+    A.lw_key[at] = make_uint2(Hh.occ_incr, frame * 2u);
 }
 
 template<int CH>
@@ -970,11 +991,11 @@ __global__ void __launch_bounds__(256, PAWB_MIN_BLOCKS) pawcs_phaseB(const PawAr
         const int r_ = hi_ / 5, k = hi_ - r_ * 5;
         PawHit<CH> Hh;
         paw_hit_load<CH>(A, Hh, x, y, x - 2 + k, y + r_ - 2, cooldown, boot);
-        Col bc[PAWB_K]; Desc bd[PAWB_K]; uint2 key[PAWB_K];
+        Col bc[PAWB_K]; Desc bd[PAWB_K]; uint2 key[PAWB_K]; uint32_t first[PAWB_K];
 #pragma unroll
         for(int j = 0; j < PAWB_K; ++j) {
-            if(j < A.NW) { const size_t at = (size_t)j * A.plane + pix; bc[j] = ((const Col*)A.lw_color)[at]; bd[j] = ((const Desc*)A.lw_desc)[at]; key[j] = A.lw_key[at]; }
-            else { bc[j] = Col(); bd[j] = Desc(); key[j] = make_uint2(0, 0); }
+            if(j < A.NW) { const size_t at = (size_t)j * A.plane + pix; const typename PawRec<CH>::T r = PAW_REC(A)[at]; bc[j] = PawRec<CH>::col(r); bd[j] = PawRec<CH>::desc(r); first[j] = PawRec<CH>::first(r); key[j] = A.lw_key[at]; }
+            else { bc[j] = Col(); bd[j] = Desc(); key[j] = make_uint2(0, 0); first[j] = 0; }
         }
         float sum = 0.0f, w[PAWB_K]; uint32_t fl[PAWB_K];
 #pragma unroll
@@ -992,7 +1013,7 @@ __global__ void __launch_bounds__(256, PAWB_MIN_BLOCKS) pawcs_phaseB(const PawAr
         }
 #pragma unroll
         for(int j = 0; j < PAWB_K; ++j)
-            if(fl[j] & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl[j], key[j], CH == 1 ? 0u : A.lw_first[(size_t)j * A.plane + pix], w[j], bd[j], frame);
+            if(fl[j] & 1u) paw_hit_commit<CH>(A, Hh, (size_t)j * A.plane + pix, fl[j], key[j], first[j], w[j], bd[j], frame);
         if(sum < init_w) paw_hit_new_word<CH>(A, Hh, pix, frame);
         hits &= hits - 1u;
     }
@@ -1030,10 +1051,11 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWBT_MIN_BLOCKS) pawcs_phas
             for(int base = 0; base < A.NW && !stop; base += 32) { // (warp-uniform)
                 const int j = base + (int)lane;
                 const size_t at = (size_t)j * A.plane + pix;
-                uint32_t fl = 0u; float w = 0.0f; uint2 key = make_uint2(0u, 0u); Desc bd = Desc();
+                uint32_t fl = 0u, first = 0u; float w = 0.0f; uint2 key = make_uint2(0u, 0u); Desc bd = Desc();
                 if(j < A.NW) {
-                    bd = ((const Desc*)A.lw_desc)[at];
-                    fl = paw_hit_word<CH>(A, Hh, j, ((const Col*)A.lw_color)[at], bd, frame, boot);
+                    const typename PawRec<CH>::T r = PAW_REC(A)[at];
+                    bd = PawRec<CH>::desc(r); first = PawRec<CH>::first(r);
+                    fl = paw_hit_word<CH>(A, Hh, j, PawRec<CH>::col(r), bd, frame, boot);
                     if(fl & 1u) { key = A.lw_key[at]; w = paw_weight(key, wk); }
                 }
                 uint32_t m = __ballot_sync(0xFFFFFFFFu, fl & 1u), upto = 0u;
@@ -1044,7 +1066,7 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWBT_MIN_BLOCKS) pawcs_phas
                     upto |= 1u << jj;
                     if(!(sum < Hh.wthr)) stop = true;
                 }
-                if((upto >> lane) & 1u) paw_hit_commit<CH>(A, Hh, at, fl, key, CH == 1 ? 0u : A.lw_first[at], w, bd, frame);
+                if((upto >> lane) & 1u) paw_hit_commit<CH>(A, Hh, at, fl, key, first, w, bd, frame);
             }
             if(sum < init_w && lane == 0) paw_hit_new_word<CH>(A, Hh, pix, frame);
             __syncwarp();
@@ -1202,10 +1224,11 @@ __global__ void __launch_bounds__(256) pawcs_background_kernel(const PawArgs A, 
     for(int i = 0; i < A.NW; ++i) {
         const size_t at = (size_t)i * A.plane + pix;
         const float w = paw_weight(A.lw_key[at], wk);
-        if(out_color) { const Col bc = ((const Col*)A.lw_color)[at];
+        const typename PawRec<CH>::T rec = PAW_REC(A)[at];
+        if(out_color) { const Col bc = PawRec<CH>::col(rec);
 #pragma unroll
             for(int c = 0; c < CH; ++c) tc[c] = __fadd_rn(tc[c], __fmul_rn((float)col_get(bc, c), w)); }
-        if(out_desc) { const Desc bd = ((const Desc*)A.lw_desc)[at];
+        if(out_desc) { const Desc bd = PawRec<CH>::desc(rec);
 #pragma unroll
             for(int c = 0; c < CH; ++c) td[c] = __fadd_rn(td[c], __fmul_rn((float)desc_get(bd, c), w)); }
         tw = __fadd_rn(tw, w);
@@ -1359,7 +1382,7 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
     const uint32_t thrD = CH == 1 ? dbase : dbase * 3u;
     const int NW = A.NW;
     // occurrence == 0 && last == 0 && first == 1 marks a word that does not exist yet (initialisation only)
-    auto valid = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return !(A.lw_first[at] == 1u && A.lw_key[at].y == 1u); }; // first == 1 && last == 0
+    auto valid = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return !(PawRec<CH>::load_first(PAW_REC(A) + at) == 1u && A.lw_key[at].y == 1u); }; // first == 1 && last == 0
     const uint32_t wk = paw_wk(frame, woff);
     auto weight = [&](int i) { const size_t at = (size_t)i * A.plane + pix; return paw_weight(A.lw_key[at], wk); };
     if(decr > 0.0f)
@@ -1380,15 +1403,16 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
             if(!valid(i)) continue;
             const size_t at = (size_t)i * A.plane + pix;
             uint32_t l1, cd;
-            if(paw_color_dist<CH>(col_as_u32(scol), col_as_u32(((const Col*)A.lw_color)[at]), l1, cd) <= thrC && paw_hdist(sdesc, ((const Desc*)A.lw_desc)[at]) <= thrD) {
-                A.lw_key[at] = make_uint2(A.lw_key[at].x + 1u, A.lw_first[at] + frame); break; // last = frame
+            const typename PawRec<CH>::T r = PAW_REC(A)[at];
+            if(paw_color_dist<CH>(col_as_u32(scol), col_as_u32(PawRec<CH>::col(r)), l1, cd) <= thrC && paw_hdist(sdesc, PawRec<CH>::desc(r)) <= thrD) {
+                A.lw_key[at] = make_uint2(A.lw_key[at].x + 1u, PawRec<CH>::first(r) + frame); break; // last = frame
             }
         }
         if(i == NW) {
             i = NW - 1;
             const size_t at = (size_t)i * A.plane + pix;
-            ((Col*)A.lw_color)[at] = scol; ((Desc*)A.lw_desc)[at] = sdesc;
-            A.lw_key[at] = make_uint2(base_occ, frame * 2u); A.lw_first[at] = frame;
+            PAW_REC(A)[at] = PawRec<CH>::make(scol, sdesc, frame);
+            A.lw_key[at] = make_uint2(base_occ, frame * 2u);
         }
         while(i > 0 && (!valid(i - 1) || weight(i) > weight(i - 1))) { paw_swap<CH>(A, pix, i); --i; }
     }
@@ -1399,13 +1423,15 @@ __global__ void __launch_bounds__(256) pawcs_refresh_local(const PawArgs A, uint
         const size_t ar = (size_t)r * A.plane + pix;
         const uint32_t d2 = draw();
         const int off = CH == 1 ? (int)(d2 % (thrC + 1u)) - (int)thrC / 2 : (int)(d2 % (thrC / 3u + 1u)) - (int)(thrC / 6u);
-        const Col rc = ((const Col*)A.lw_color)[ar];
-        if constexpr (CH == 1) ((Col*)A.lw_color)[at] = (uchar)min(max((int)rc + off, 0), 255);
-        else ((Col*)A.lw_color)[at] = (uint32_t)min(max((int)(rc & 0xFFu) + off, 0), 255) | ((uint32_t)min(max((int)((rc >> 8) & 0xFFu) + off, 0), 255) << 8)
-                                    | ((uint32_t)min(max((int)((rc >> 16) & 0xFFu) + off, 0), 255) << 16);
-        ((Desc*)A.lw_desc)[at] = ((const Desc*)A.lw_desc)[ar];
+        const typename PawRec<CH>::T rr = PAW_REC(A)[ar];
+        const Col rc = PawRec<CH>::col(rr);
+        Col nc;
+        if constexpr (CH == 1) nc = (uchar)min(max((int)rc + off, 0), 255);
+        else nc = (uint32_t)min(max((int)(rc & 0xFFu) + off, 0), 255) | ((uint32_t)min(max((int)((rc >> 8) & 0xFFu) + off, 0), 255) << 8)
+                | ((uint32_t)min(max((int)((rc >> 16) & 0xFFu) + off, 0), 255) << 16);
+        PAW_REC(A)[at] = PawRec<CH>::make(nc, PawRec<CH>::desc(rr), frame);
         const uint32_t o = (uint32_t)__fmul_rn((float)A.lw_key[ar].x, __fdiv_rn((float)(NW - i), (float)NW));
-        A.lw_key[at] = make_uint2(max(o, 1u), frame * 2u); A.lw_first[at] = frame;
+        A.lw_key[at] = make_uint2(max(o, 1u), frame * 2u);
     }
 }
 /// global resampling (:342-408): sequential by nature (<= ~4*NG pixels); thread 0 decides, the CTA zeroes maps
@@ -1437,7 +1463,8 @@ __global__ void __launch_bounds__(1024) pawcs_refresh_global(const PawArgs A, ui
                 const uint32_t thrC = CH == 1 ? cbase / 2u : cbase * 3u;
                 const uint32_t dbase = (1u << (uint32_t)floorf(__fadd_rn(R, 0.5f))) + (uint32_t)A.desc_off + (unst ? (uint32_t)A.desc_off : 0u);
                 const uint32_t thrD = CH == 1 ? dbase : dbase * 3u;
-                const Col bc = ((const Col*)A.lw_color)[pix]; const Desc bd = ((const Desc*)A.lw_desc)[pix];
+                const typename PawRec<CH>::T r0 = PAW_REC(A)[pix];
+                const Col bc = PawRec<CH>::col(r0); const Desc bd = PawRec<CH>::desc(r0);
                 const uint32_t bits = paw_bits(bd);
                 bool found_uninit = false;
                 for(i = 0; i < NG; ++i) {
