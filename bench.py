@@ -329,7 +329,8 @@ def bench_other_configs(lv, torch, dev, local, rank, world, barrier, all_max, hb
 
         def step():
             k[0] += 1
-            sub.apply_device(d_frames[pingpong(k[0], n_unique)].data_ptr(), pitch, d_mask.data_ptr(), lr_for(k[0]) if cls is not lv.BackgroundSubtractorPAWCS else 0.0)
+            lr = lr_for(k[0]) if cls is lv.BackgroundSubtractorSuBSENSE else 16.0 if cls is lv.BackgroundSubtractorLOBSTER else 0.0   # the classes' default rates
+            sub.apply_device(d_frames[pingpong(k[0], n_unique)].data_ptr(), pitch, d_mask.data_ptr(), lr)
         for _ in range(BOOT_FRAMES):
             step()
         sub.sync()

@@ -208,6 +208,9 @@ void* lvb_pbas_stream(lvb_pbas_handle h);
 typedef struct lvb_edge_context* lvb_edge_handle;
 int lvb_edge_create(int levels, double hyst_low_factor, int device, lvb_edge_handle* out);
 int lvb_edge_destroy(lvb_edge_handle h);
+/* EdgeDetectorLBSP's third constructor argument bNormalizeOutput (EdgeDetectorLBSP.cpp:26-34, 431-432): lvb_edge_apply min-max
+ * normalises its confidence map to [0,255] like cv::normalize(NORM_MINMAX). Default off, as in the reference. */
+int lvb_edge_set_normalize(lvb_edge_handle h, int normalize_output);
 double lvb_edge_default_threshold(void);
 int lvb_edge_apply_threshold(lvb_edge_handle h, const uint8_t* img, int width, int height, int channels, uint8_t* edges, double threshold);
 int lvb_edge_apply(lvb_edge_handle h, const uint8_t* img, int width, int height, int channels, uint8_t* confidence);

@@ -320,10 +320,10 @@ private:
 /// EdgeDetectorLBSP (imgproc/include/litiv/imgproc/EdgeDetectorLBSP.hpp:33-83): same constructor defaults and method names; masks are
 /// caller-owned rows*cols bytes. Like the reference object, the detector keeps its maps between calls and is not thread-safe.
 struct EdgeDetectorLBSP {
-    /// bNormalizeOutput (EdgeDetectorLBSP.cpp:431-432, default false in the reference) is not supported: normalise the confidence map yourself
+    /// bNormalizeOutput (EdgeDetectorLBSP.cpp:431-432): apply() min-max normalises its confidence map like cv::normalize(NORM_MINMAX)
     explicit EdgeDetectorLBSP(size_t nLevels = 3, double dHystLowThrshFactor = 0.5, bool bNormalizeOutput = false, int device = 0) {
-        if(bNormalizeOutput) throw Exception("bNormalizeOutput=true is not supported (min-max normalisation of the confidence map is left to the caller)");
         check(lvb_edge_create((int)nLevels, dHystLowThrshFactor, device, &m_h));
+        if(bNormalizeOutput) check(lvb_edge_set_normalize(m_h, 1));
     }
     ~EdgeDetectorLBSP() { lvb_edge_destroy(m_h); }
     EdgeDetectorLBSP(const EdgeDetectorLBSP&) = delete;
@@ -352,7 +352,7 @@ struct EdgeDetectorLBSP {
     lvb_edge_handle handle() const { return m_h; }
 private:
     static void checkInput(const ImageView& img) {
-        if(img.empty() || !img.isContinuous() || (img.channels != 1 && img.channels != 3)) throw Exception("input image must be non-empty and continuous, 8UC1 or 8UC3");
+        if(img.empty() || !img.isContinuous() || img.channels < 1 || img.channels > 4) throw Exception("input image must be non-empty and continuous, 8UC1 .. 8UC4");
     }
     lvb_edge_handle m_h = nullptr;
 };

@@ -31,7 +31,7 @@ EXPORTS = [
     "lvb_pbas_create", "lvb_pbas_destroy", "lvb_pbas_initialize", "lvb_pbas_apply", "lvb_pbas_apply_device", "lvb_pbas_sync",
     "lvb_pbas_get_background_image", "lvb_pbas_state", "lvb_pbas_set_collect_stats", "lvb_pbas_get_stats", "lvb_pbas_set_profile",
     "lvb_pbas_get_profile", "lvb_pbas_stream", "lvb_lbsp_gradient",
-    "lvb_edge_create", "lvb_edge_destroy", "lvb_edge_default_threshold", "lvb_edge_apply_threshold", "lvb_edge_apply",
+    "lvb_edge_create", "lvb_edge_destroy", "lvb_edge_set_normalize", "lvb_edge_default_threshold", "lvb_edge_apply_threshold", "lvb_edge_apply",
     "lvb_edge_get_gradient_map", "lvb_edge_flood_sweeps", "lvb_edge_apply_threshold_device", "lvb_edge_stream",
 ]
 
@@ -96,6 +96,7 @@ def lib():
         L.lvb_lbsp_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.lvb_edge_create.argtypes = [C.c_int, C.c_double, C.c_int, C.c_void_p]
         L.lvb_edge_destroy.argtypes = [C.c_void_p]
+        L.lvb_edge_set_normalize.argtypes = [C.c_void_p, C.c_int]
         L.lvb_edge_default_threshold.restype = C.c_double
         L.lvb_edge_apply_threshold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double]
         L.lvb_edge_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -673,9 +674,9 @@ class EdgeDetectorLBSP:
 
     def __init__(self, nLevels=3, dHystLowThrshFactor=0.5, bNormalizeOutput=False, device=0):
         self._h = C.c_void_p()
-        if bNormalizeOutput:   # EdgeDetectorLBSP.cpp:431-432 (cv::normalize of the confidence map); the reference's default is false
-            raise LitivError("bNormalizeOutput=true is not supported (min-max normalisation of the confidence map is left to the caller)")
         _chk(lib().lvb_edge_create(int(nLevels), float(dHystLowThrshFactor), device, C.byref(self._h)))
+        if bNormalizeOutput:   # EdgeDetectorLBSP.cpp:431-432: cv::normalize(NORM_MINMAX) of the confidence map; the reference's default is false
+            _chk(lib().lvb_edge_set_normalize(self._h, 1))
         self._shape = None
 
     def __del__(self):
@@ -689,8 +690,8 @@ class EdgeDetectorLBSP:
     @staticmethod
     def _img(img):
         img = np.ascontiguousarray(img)
-        if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0 or (img.ndim == 3 and img.shape[2] not in (1, 3)):
-            raise LitivError("input image must be non-empty and continuous, 8UC1 or 8UC3")
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or img.size == 0 or (img.ndim == 3 and img.shape[2] not in (1, 2, 3, 4)):
+            raise LitivError("input image must be non-empty and continuous, 8UC1 .. 8UC4")
         return img, (1 if img.ndim == 2 else img.shape[2])
 
     def apply_threshold(self, img, dDetThreshold=0.5):

@@ -75,4 +75,25 @@ __global__ void __launch_bounds__(256) edge_output_kernel(uchar* mask, int W, in
     else out[i] = on ? 255 : 0;
 }
 
+/// cv::normalize(confidence, confidence, 0, UCHAR_MAX, NORM_MINMAX) of apply() when the detector was built with bNormalizeOutput
+/// (EdgeDetectorLBSP.cpp:431-432): min / max of the map (mm[0] starts at 255, mm[1] at 0) ...
+__global__ void __launch_bounds__(256) edge_minmax_kernel(const uchar* out, size_t n, unsigned* mm) {
+    unsigned lo = 255u, hi = 0u;
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { const unsigned v = out[i]; lo = min(lo, v); hi = max(hi, v); }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o)); hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o)); }
+    if((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+}
+/// ... then OpenCV's arithmetic: scale and shift in double, the conversion in float (multiply, add, round half to even, saturate);
+/// the same restatement as the oracle's, which the CPU tests pin bit-exactly against cv2 4.13
+__global__ void __launch_bounds__(256) edge_normalize_kernel(uchar* out, size_t n, const unsigned* mm) {
+    const double smin = (double)mm[0], smax = (double)mm[1];
+    const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.);
+    const float a = (float)scale, b = (float)(0.0 - smin * scale);
+    for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = __float2int_rn(__fadd_rn(__fmul_rn((float)out[i], a), b));
+        out[i] = (uchar)(r < 0 ? 0 : r > 255 ? 255 : r);
+    }
+}
+
 } // namespace lvb_edge

@@ -9,12 +9,12 @@
 #include "edge.cuh"
 
 struct lvb_edge_context {
-    int device = 0, levels = 3; double hyst = 0.5;
+    int device = 0, levels = 3; double hyst = 0.5; bool normalize = false;   // m_bNormalizeOutput
     int W = 0, H = 0, C = 0;
     cudaStream_t stream = nullptr;
     std::vector<int> Wl, Hl; std::vector<size_t> pitch;
     std::vector<uint8_t*> img; std::vector<uchar4*> V; std::vector<CUtensorMap> tmap; std::vector<int> use_tma;
-    uint8_t *mask = nullptr, *out = nullptr; int* flag = nullptr;
+    uint8_t *mask = nullptr, *out = nullptr; int* flag = nullptr; unsigned* minmax = nullptr;
     uint64_t flood_sweeps = 0;   // relaxation sweeps of the latest call (diagnostic)
 
     void free_all() {
@@ -23,15 +23,16 @@ struct lvb_edge_context {
         if(mask) cudaFree(mask);
         if(out) cudaFree(out);
         if(flag) cudaFree(flag);
+        if(minmax) cudaFree(minmax);
         img.clear(); V.clear(); tmap.clear(); use_tma.clear(); Wl.clear(); Hl.clear(); pitch.clear();
-        mask = out = nullptr; flag = nullptr; W = H = C = 0;
+        mask = out = nullptr; flag = nullptr; minmax = nullptr; W = H = C = 0;
     }
 };
 
 namespace {
 
 void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, size_t src_step = 0, cudaMemcpyKind kind = cudaMemcpyHostToDevice) {
-    REQUIRE(src && (C == 1 || C == 3), "input image must be non-empty and continuous, 8UC1 or 8UC3");   // EdgeDetectorLBSP.cpp:392-393
+    REQUIRE(src && C >= 1 && C <= 4, "input image must be non-empty and continuous, 8UC1 .. 8UC4");   // EdgeDetectorLBSP.cpp:144-160, 392-393
     std::vector<int> Wl(1, W), Hl(1, H);
     for(int l = 1; l < c->levels; ++l) { Wl.push_back((Wl.back() + 1) / 2); Hl.push_back((Hl.back() + 1) / 2); }
     REQUIRE(Wl.back() >= 5 && Hl.back() >= 5, "image too small for the number of pyramid levels");
@@ -50,6 +51,7 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
         c->mask = dalloc<uint8_t>(c->stream, (size_t)W * H);   // zero = "may belong to an edge", the fresh vector of the reference
         c->out = dalloc<uint8_t>(c->stream, (size_t)W * H);
         c->flag = dalloc<int>(c->stream, 1);
+        c->minmax = dalloc<unsigned>(c->stream, 2);
         c->W = W; c->H = H; c->C = C;   // last: a failed allocation leaves W == 0, so the next call starts over instead of using half a set of maps
     }
     cudaStream_t st = c->stream;
@@ -64,7 +66,8 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
         LbspGradArgs A{};
         A.W = Wl[l]; A.H = Hl[l]; A.img = c->img[l]; A.ipitch = c->pitch[l]; A.out = c->V[l]; A.use_tma = c->use_tma[l];
         const dim3 gg((Wl[l] + TILE_W - 1) / TILE_W, (Hl[l] + TILE_H - 1) / TILE_H), gb(TILE_W, TILE_H);
-        if(C == 1) lbsp_gradient_kernel<1><<<gg, gb, 0, st>>>(A, c->tmap[l]); else lbsp_gradient_kernel<3><<<gg, gb, 0, st>>>(A, c->tmap[l]);
+        if(C == 1) lbsp_gradient_kernel<1><<<gg, gb, 0, st>>>(A, c->tmap[l]); else if(C == 2) lbsp_gradient_kernel<2><<<gg, gb, 0, st>>>(A, c->tmap[l]);
+        else if(C == 3) lbsp_gradient_kernel<3><<<gg, gb, 0, st>>>(A, c->tmap[l]); else lbsp_gradient_kernel<4><<<gg, gb, 0, st>>>(A, c->tmap[l]);
         LAUNCHED();
         const dim3 g((Wl[l] + 31) / 32, (Hl[l] + 7) / 8);
         lvb_edge::edge_combine_kernel<<<g, b, 0, st>>>(c->V[l], Wl[l], Hl[l], l + 1 < c->levels ? c->V[l + 1] : nullptr, l + 1 < c->levels ? Wl[l + 1] : 0, c->V[l]);
@@ -131,6 +134,13 @@ int lvb_edge_destroy(lvb_edge_handle h) {
     return 0;
 }
 
+int lvb_edge_set_normalize(lvb_edge_handle h, int normalize_output) {
+    LVB_TRY
+    REQUIRE(h != nullptr, "null argument");
+    h->normalize = normalize_output != 0;
+    LVB_CATCH
+}
+
 double lvb_edge_default_threshold(void) { return 8.0 / 16.0; }   // EDGLBSP_DEFAULT_DET_THRESHOLD (EdgeDetectorLBSP.hpp:30)
 
 int lvb_edge_apply_threshold(lvb_edge_handle h, const uint8_t* img, int W, int H, int C, uint8_t* edges, double threshold) {
@@ -152,6 +162,14 @@ int lvb_edge_apply(lvb_edge_handle h, const uint8_t* img, int W, int H, int C, u
     edge_prepare(h, img, W, H, C);
     CK(cudaMemsetAsync(h->out, 0, (size_t)W * H, h->stream));
     for(unsigned t = 0; t < 16; ++t) edge_pass(h, t, 1);   // :418-430: the gradient map does not depend on the threshold
+    if(h->normalize) {                                     // :431-432
+        const unsigned init[2] = {255u, 0u};
+        CK(cudaMemcpyAsync(h->minmax, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+        const size_t n = (size_t)W * H;
+        const int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+        lvb_edge::edge_minmax_kernel<<<grid, 256, 0, h->stream>>>(h->out, n, h->minmax); LAUNCHED();
+        lvb_edge::edge_normalize_kernel<<<grid, 256, 0, h->stream>>>(h->out, n, h->minmax); LAUNCHED();
+    }
     CK(cudaMemcpyAsync(confidence, h->out, (size_t)W * H, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     LVB_CATCH

@@ -292,6 +292,8 @@ int lvo_edge_create(int levels, double hyst_low_factor, void** out) {
     LVO_CATCH
 }
 int lvo_edge_destroy(void* h) { delete (EdgeDetectorLBSP*)h; return 0; }
+int lvo_edge_set_normalize(void* h, int on) { ((EdgeDetectorLBSP*)h)->normalize_output = on != 0; return 0; }
+int lvo_normalize_minmax_u8(uint8_t* buf, size_t n) { EdgeDetectorLBSP::normalize_minmax_u8(buf, n); return 0; }
 int lvo_edge_apply_threshold(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out, double thr) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply_threshold(img, w, hh, c, out, thr); LVO_CATCH }
 int lvo_edge_apply(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply(img, w, hh, c, out); LVO_CATCH }
 /// gradient map of the latest pass without its padding: [H][W][4] = gradX, gradY, magnitude (min over the scales), pad

@@ -31,7 +31,7 @@ struct EdgeDetectorLBSP {
     /// neighbours of level-l pixel (r, c) per channel, or the pixel itself within the 2-px border. (The lookup maps themselves are
     /// recomputed where needed instead of being stored.)
     void build_pyramid(const uchar* img, int W, int H, int C) {
-        if(!img || (C != 1 && C != 3)) throw std::runtime_error("input image must be non-empty and continuous, 8UC1 or 8UC3");
+        if(!img || C < 1 || C > 4) throw std::runtime_error("input image must be non-empty and continuous, 8UC1 .. 8UC4"); // :144-160: 1 to 4 channels
         if(n_levels < 1) throw std::runtime_error("number of pyramid levels must be positive");
         sizes.assign(1, std::make_pair(H, W));
         for(int l = 1; l < n_levels; ++l) sizes.push_back(std::make_pair((sizes.back().first + 1) / 2, (sizes.back().second + 1) / 2));
@@ -146,7 +146,28 @@ struct EdgeDetectorLBSP {
         threshold_pass(img, W, H, C, out, (uchar)(thr * 16));
     }
 
-    /// apply (:412-433) without normalisation: every threshold 0..15 contributes saturate(cvRound(255 / 16.0)) = 16 where it finds an edge
+    bool normalize_output = false;    // m_bNormalizeOutput (third constructor argument, default false)
+
+    /// cv::normalize(x, x, 0, UCHAR_MAX, NORM_MINMAX) on an 8-bit map (:431-432; OpenCV core norm.cpp + convertTo): scale and shift in
+    /// double, the conversion itself in float (multiply, add, round half to even, saturate). Pinned bit-exactly against cv2 4.13
+    /// (tests/test_edge_oracle_cpu.py).
+    static void normalize_minmax_u8(uchar* buf, size_t n) {
+        if(!n) return;
+        uchar lo = 255, hi = 0;
+        for(size_t i = 0; i < n; ++i) { lo = std::min(lo, buf[i]); hi = std::max(hi, buf[i]); }
+        const double smin = lo, smax = hi;
+        const double scale = 255.0 * (smax - smin > 2.220446049250313e-16 ? 1. / (smax - smin) : 0.);
+        const double shift = 0.0 - smin * scale;
+        const float a = (float)scale, b = (float)shift;
+        for(size_t i = 0; i < n; ++i) {
+            volatile float m = (float)buf[i] * a;   // two roundings, as OpenCV's scalar and SIMD paths produce here (checked against cv2)
+            const float v = m + b;
+            const long r = std::lrint(v);
+            buf[i] = (uchar)(r < 0 ? 0 : r > 255 ? 255 : r);
+        }
+    }
+
+    /// apply (:412-433): every threshold 0..15 contributes saturate(cvRound(255 / 16.0)) = 16 where it finds an edge; optional normalisation
     void apply(const uchar* img, int W, int H, int C, uchar* out) {
         build_pyramid(img, W, H, C);
         std::vector<uchar> tmp((size_t)W * H);
@@ -155,6 +176,7 @@ struct EdgeDetectorLBSP {
             threshold_pass(img, W, H, C, tmp.data(), (uchar)t);
             for(size_t i = 0; i < tmp.size(); ++i) out[i] = (uchar)std::min(255, (int)out[i] + (tmp[i] ? 16 : 0));
         }
+        if(normalize_output) normalize_minmax_u8(out, (size_t)W * H);
     }
 };
 

@@ -292,9 +292,11 @@ class EdgeDetectorLBSPOracle:
     """EdgeDetectorLBSP (imgproc/src/EdgeDetectorLBSP.cpp) over the CPU restatement (oracle/lvo_edge_lbsp.hpp); like the reference
     object it keeps its gradient / mask buffers between calls"""
 
-    def __init__(self, levels=3, hyst_low_factor=0.5):
+    def __init__(self, levels=3, hyst_low_factor=0.5, normalize_output=False):
         self._h = C.c_void_p()
         _chk(lib().lvo_edge_create(levels, C.c_double(hyst_low_factor), C.byref(self._h)))
+        if normalize_output:
+            lib().lvo_edge_set_normalize(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None) and _LIB is not None:
@@ -320,6 +322,13 @@ class EdgeDetectorLBSPOracle:
         out = np.empty((h, w, 4), np.uint8)
         _chk(lib().lvo_edge_gradient_map(self._h, w, h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+def normalize_minmax_u8(a):
+    """cv::normalize(a, a, 0, 255, NORM_MINMAX) for an 8-bit array (the restatement EdgeDetectorLBSP's normalised output uses)"""
+    a = np.ascontiguousarray(a, np.uint8).copy()
+    lib().lvo_normalize_minmax_u8(a.ctypes.data_as(C.c_void_p), C.c_size_t(a.size))
+    return a
 
 
 def vibe_match(model_channels, thr, a, b):

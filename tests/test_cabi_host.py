@@ -55,8 +55,8 @@ def test_no_cpu_fallback_without_device():
         lv.mask_op(lv.MASK_DILATE, np.zeros((16, 16), np.uint8), 1)
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.EdgeDetectorLBSP()
-    with pytest.raises(lv.LitivError, match="bNormalizeOutput"):
-        lv.EdgeDetectorLBSP(3, 0.5, True)            # the reference's optional third argument (default false) is declined, not ignored
+    with pytest.raises(lv.LitivError, match="no CPU fallback"):
+        lv.EdgeDetectorLBSP(3, 0.5, True)            # the reference's optional third argument bNormalizeOutput
     with pytest.raises(lv.LitivError, match="no CPU fallback"):
         lv.lbsp_gradient(np.zeros((16, 16), np.uint8))
 

@@ -31,15 +31,20 @@ def emul(tmp_path_factory):
 
 def _frame(seq, t, ch):
     f = np.ascontiguousarray(seq.frame(t))
-    return np.ascontiguousarray(f[..., 0]) if ch == 1 and f.ndim == 3 else f
+    if ch == 1 and f.ndim == 3:
+        return np.ascontiguousarray(f[..., 0])
+    if ch in (2, 4):   # the reference instantiates the detector for 1 to 4 channels (EdgeDetectorLBSP.cpp:144-160)
+        extra = (f[..., :1].astype(np.int32) * 3 + f[..., 1:2] * 5 + 17 * t) % 256
+        return np.ascontiguousarray(np.concatenate([f, extra.astype(np.uint8)], axis=2)[..., :ch] if ch == 4 else f[..., :2])
+    return f
 
 
 @pytest.mark.parametrize("size", [(96, 72), (97, 73), (96, 73), (97, 72), (43, 41)])
-@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
 @pytest.mark.parametrize("levels", [1, 2, 3])
 def test_kernel_bodies_equal_the_sequential_oracle(oracle, emul, size, ch, levels):
     w, h = size
-    seq = SynthSequence(w, h, ch, seed=w + h + ch)
+    seq = SynthSequence(w, h, 1 if ch == 1 else 3, seed=w + h + ch)
     o, e = oracle.EdgeDetectorLBSPOracle(levels=levels), emul.emul_create(levels, 0.5)
     try:
         for t, thr in [(3, 0.5), (5, 0.25), (7, 0.75), (9, 0.0), (11, 0.9), (12, -1.0)]:   # one object, a sequence of calls (the maps persist)

@@ -57,6 +57,46 @@ def test_thresholds_are_monotone_and_confidence_map_counts_them(oracle):
     assert np.array_equal(O.EdgeDetectorLBSPOracle().apply_threshold(f, -1.0), O.EdgeDetectorLBSPOracle().apply_threshold(f, 0.5))   # default
 
 
+def test_normalized_output_restatement_equals_cv2_normalize(oracle):
+    """bNormalizeOutput (EdgeDetectorLBSP.cpp:431-432): cv::normalize(x, x, 0, UCHAR_MAX, NORM_MINMAX). The confidence map only holds
+    0, 16, .., 240, 255: every (min, max) pair of those values, array lengths that exercise OpenCV's vector body and its scalar tail,
+    random maps over that value set, and the detector's own output, against cv2"""
+    cv2 = pytest.importorskip("cv2")
+    vals = [16 * i for i in range(16)] + [255]
+    for lo in vals:
+        for hi in vals:
+            if hi < lo:
+                continue
+            inner = [v for v in vals if lo <= v <= hi]
+            for n in (1, 3, 7, 16, 33, 64, 100):
+                src = np.array((inner * (n // len(inner) + 1))[:n], np.uint8)
+                src[0] = lo
+                if n > 1:
+                    src[-1] = hi
+                src = src.reshape(1, -1)
+                assert np.array_equal(oracle.normalize_minmax_u8(src), cv2.normalize(src, None, 0, 255, cv2.NORM_MINMAX)), (lo, hi, n)
+    # (arbitrary 8-bit maps are out of scope: there OpenCV's result depends on whether its build fuses the multiply-add, e.g. 190 in a
+    # map spanning 181..199 comes out as 127 or 128; on the detector's value set fused and unfused arithmetic agree everywhere)
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        src = np.array(vals, np.uint8)[rng.integers(0, 17, size=(rng.integers(1, 40), rng.integers(1, 70)))]
+        assert np.array_equal(oracle.normalize_minmax_u8(src), cv2.normalize(src, None, 0, 255, cv2.NORM_MINMAX))
+    img = _square()
+    plain, norm = oracle.EdgeDetectorLBSPOracle().apply(img), oracle.EdgeDetectorLBSPOracle(normalize_output=True).apply(img)
+    assert np.array_equal(norm, cv2.normalize(plain, None, 0, 255, cv2.NORM_MINMAX)) and norm.max() == 255
+
+
+def test_two_and_four_channel_images(oracle):
+    """the reference instantiates the detector for 1 to 4 channels (EdgeDetectorLBSP.cpp:144-160); the gradient takes the channel with the
+    largest response (LBSP.hpp:235-256), so replicating a gray image into 2 or 4 channels must not change the result"""
+    img = _square()
+    want = oracle.EdgeDetectorLBSPOracle().apply_threshold(img, 0.5)
+    for c in (2, 4):
+        assert np.array_equal(oracle.EdgeDetectorLBSPOracle().apply_threshold(np.repeat(img[..., None], c, axis=2), 0.5), want)
+    with pytest.raises(Exception):
+        oracle.EdgeDetectorLBSPOracle().apply_threshold(np.repeat(img[..., None], 5, axis=2), 0.5)
+
+
 def test_repeatable_on_one_object_and_errors(oracle):
     O = oracle
     f = SynthSequence(96, 80, 3, seed=1).frame(7)

@@ -12,15 +12,20 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 def _frame(seq, t, ch):
     f = np.ascontiguousarray(seq.frame(t))
-    return np.ascontiguousarray(f[..., 0]) if ch == 1 and f.ndim == 3 else f
+    if ch == 1 and f.ndim == 3:
+        return np.ascontiguousarray(f[..., 0])
+    if ch in (2, 4):   # the reference instantiates the detector for 1 to 4 channels (EdgeDetectorLBSP.cpp:144-160)
+        extra = (f[..., :1].astype(np.int32) * 3 + f[..., 1:2] * 5 + 17 * t) % 256
+        return np.ascontiguousarray(np.concatenate([f, extra.astype(np.uint8)], axis=2)[..., :ch] if ch == 4 else f[..., :2])
+    return f
 
 
 @pytest.mark.parametrize("size", [(96, 72), (97, 73), (320, 240), (641, 479)])
-@pytest.mark.parametrize("ch", [1, 3])
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
 @pytest.mark.parametrize("levels", [1, 3])
 def test_edge_masks_and_gradient_map_match_oracle(lv, oracle, size, ch, levels):
     w, h = size
-    seq = SynthSequence(w, h, ch, seed=w + h + ch)
+    seq = SynthSequence(w, h, 1 if ch == 1 else 3, seed=w + h + ch)
     o, e = oracle.EdgeDetectorLBSPOracle(levels=levels), lv.EdgeDetectorLBSP(levels)
     for t, thr in [(3, 0.5), (5, 0.25), (7, 0.75), (9, 0.0), (12, -1.0)]:
         f = _frame(seq, t, ch)
@@ -39,6 +44,24 @@ def test_edge_1080p_and_size_change(lv, oracle):
     assert e.flood_sweeps() >= 4
     small = SynthSequence(160, 120, 3, seed=4).frame(20)
     assert np.array_equal(e.apply_threshold(small, 0.3), oracle.EdgeDetectorLBSPOracle().apply_threshold(small, 0.3))
+
+
+@pytest.mark.parametrize("size,ch", [((160, 120), 3), ((97, 73), 1), ((320, 240), 4)])
+def test_edge_normalized_confidence_map(lv, oracle, size, ch):
+    """bNormalizeOutput=true (EdgeDetectorLBSP.cpp:431-432): cv::normalize(NORM_MINMAX) of the confidence map; the oracle's restatement of
+    it is pinned against cv2 on the CPU (tests/test_edge_oracle_cpu.py)"""
+    w, h = size
+    seq = SynthSequence(w, h, 1 if ch == 1 else 3, seed=31)
+    e, o = lv.EdgeDetectorLBSP(3, 0.5, True), oracle.EdgeDetectorLBSPOracle(normalize_output=True)
+    plain = oracle.EdgeDetectorLBSPOracle()
+    for t in (4, 9):
+        f = _frame(seq, t, ch)
+        want, got = o.apply(f), e.apply(f)
+        assert np.array_equal(got, want), int((got != want).sum())
+        assert want.max() == 255 and not np.array_equal(want, plain.apply(f))
+    # a map whose minimum is not zero (every pixel an edge at some threshold) cannot come out of real images easily: a flat image instead
+    flat = np.full((h, w) if ch == 1 else (h, w, ch), 90, np.uint8)
+    assert np.array_equal(e.apply(flat), o.apply(flat)) and not o.apply(flat).any()
 
 
 def test_edge_argument_checks(lv):
