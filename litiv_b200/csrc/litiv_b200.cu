@@ -691,7 +691,11 @@ void paw_enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const C
     pawcs_gword_apply<<<dim3((c->gW + 31) / 32, (c->gH + 7) / 8), 256, 0, st>>>(A); LAUNCHED();
     pawcs_gword_finish<<<1, 128, 0, st>>>(A, !(recalc || update)); LAUNCHED();
     if(recalc || update) {
-        pawcs_gword_maintain<<<c->NG, 1024, 0, st>>>(A, recalc, update); LAUNCHED();
+        const dim3 gmg((c->gW * c->gH + PAW_GM_THREADS * PAW_GM_PER_THREAD - 1) / (PAW_GM_THREADS * PAW_GM_PER_THREAD), c->NG);
+        if(recalc) { pawcs_gmaint_sum<<<gmg, PAW_GM_THREADS, 0, st>>>(A); LAUNCHED(); }
+        pawcs_gmaint_weights<<<1, PAW_MAXG, 0, st>>>(A, recalc, update); LAUNCHED();
+        pawcs_gmaint_blur<<<gmg, PAW_GM_THREADS, 0, st>>>(A, update); LAUNCHED();
+        if(update) { pawcs_gmaint_copy<<<gmg, PAW_GM_THREADS, 0, st>>>(A); LAUNCHED(); }
         pawcs_gdict_bubble<<<1, 1, 0, st>>>(A); LAUNCHED();
     }
     if(update) { pawcs_glut_bubble<<<tg, tb, 0, st>>>(A, 0); LAUNCHED(); }

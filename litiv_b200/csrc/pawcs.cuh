@@ -45,6 +45,7 @@ struct GDict { // global dictionary (indexed by word identity) + the PAWCS frame
     uint32_t ds_roi_count, nST, tail_gate;
     uint32_t wlB_count;                // phase B work-list (reset by the frame tail)
     uint32_t refresh_ticket;           // CTAs of the conditional refresh's last kernel that are done
+    uint32_t mflags[PAW_MAXG];         // global maintenance: bit 0 zero the word's map, bit 1 update it
 };
 
 struct PawArgs {
@@ -714,6 +715,11 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWT_MIN_BLOCKS) pawcs_scan_
 #ifndef PAWU_MIN_BLOCKS
 #define PAWU_MIN_BLOCKS 5
 #endif
+/// near tie of two word weights: the reference's comparison of the rounded quotients (kept out of line: it is rare, and inlined the two
+/// IEEE divisions are if-converted into every step of the chain)
+__device__ __noinline__ bool paw_near_tie(uint32_t oi, uint32_t di, uint32_t oc, uint32_t dc) {
+    return __fdiv_rn((float)oi, (float)di) > __fdiv_rn((float)oc, (float)dc);
+}
 __device__ __noinline__ unsigned long long paw_swaps_by_division(const uint2* pk, size_t plane, int NW, uint32_t K) {
     unsigned long long swaps = 0ull;
     float last_w = FLT_MAX;
@@ -752,7 +758,7 @@ __global__ void __launch_bounds__(256, PAWU_MIN_BLOCKS) pawcs_bubble(const PawAr
                 unsafe |= oi | (di - 1u);
                 const unsigned long long a = (unsigned long long)oi * dc, b = (unsigned long long)oc * di;
                 bool s = a > b;
-                if(s && !((a - b) > (b >> 22))) s = __fdiv_rn((float)oi, (float)di) > __fdiv_rn((float)oc, (float)dc); // near tie
+                if(s && !((a - b) > (b >> 22))) s = paw_near_tie(oi, di, oc, dc);
                 sw |= s ? (1u << k) : 0u;
                 oc = s ? oc : oi; dc = s ? dc : di;
             }
@@ -765,7 +771,7 @@ __global__ void __launch_bounds__(256, PAWU_MIN_BLOCKS) pawcs_bubble(const PawAr
             unsafe |= oi | (di - 1u);
             const unsigned long long a = (unsigned long long)oi * dc, b = (unsigned long long)oc * di;
             bool s = a > b;
-            if(s && !((a - b) > (b >> 22))) s = __fdiv_rn((float)oi, (float)di) > __fdiv_rn((float)oc, (float)dc);
+            if(s && !((a - b) > (b >> 22))) s = paw_near_tie(oi, di, oc, dc);
             swaps |= s ? (1ull << i0) : 0ull;
             oc = s ? oc : oi; dc = s ? dc : di;
             pk += A.plane;
@@ -1075,60 +1081,85 @@ __global__ void __launch_bounds__(PAW_TAIL_THREADS, PAWBT_MIN_BLOCKS) pawcs_phas
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// global maintenance (PAWCS.cpp:1300-1334): one CTA per global word, then the dictionary bubble pass, then the per-pixel LUTs
+// global maintenance (PAWCS.cpp:1300-1334): sum / weights / decay+blur / copy kernels over (map chunks x words), then the dictionary bubble pass, then the per-pixel LUTs
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) pawcs_gword_maintain(const PawArgs A, int recalc, int update) {
-    __shared__ unsigned long long s_sum;
-    __shared__ int s_zero, s_upd;
+// (one CTA per word took 0.87 ms at 1080p; now every step is spread over (chunks x words) CTAs)
+constexpr int PAW_GM_THREADS = 256, PAW_GM_PER_THREAD = 8;   // a CTA covers 2048 map cells of one word
+/// recalculation (every 32 maintenance rounds): fixed-point sum of the word's occupancy map (:1304-1311)
+__global__ void __launch_bounds__(PAW_GM_THREADS) pawcs_gmaint_sum(const PawArgs A) {
     GDict* gd = A.gd;
-    const int g = blockIdx.x; // identity; every word is maintained exactly once whatever the dictionary order
+    const int g = blockIdx.y; // identity; every word is maintained exactly once whatever the dictionary order
+    if(!(gd->weight[g] > 0.0f)) return;
     const int n = A.gW * A.gH;
+    const float* m = A.gmap + (size_t)g * n;
+    long long acc = 0;
+    const int i0 = blockIdx.x * PAW_GM_THREADS * PAW_GM_PER_THREAD + threadIdx.x;
+#pragma unroll
+    for(int k = 0; k < PAW_GM_PER_THREAD; ++k) { const int i = i0 + k * PAW_GM_THREADS; if(i < n) acc += __double2ll_rn((double)m[i] * 4294967296.0); }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if((threadIdx.x & 31) == 0 && acc) atomicAdd(&gd->mapsum[g], (unsigned long long)acc);
+}
+/// one thread per word: new weight after a recalculation (below 1: the word dies and its map is zeroed), which words take part in
+/// the update, weight *= 0.9 (:1312-1314). mflags: bit 0 zero the map, bit 1 update the map
+__global__ void __launch_bounds__(PAW_MAXG) pawcs_gmaint_weights(const PawArgs A, int recalc, int update) {
+    GDict* gd = A.gd;
+    const int g = threadIdx.x;
+    if(g >= A.NG) return;
+    const bool live = gd->weight[g] > 0.0f;
+    uint32_t flags = 0;
+    if(recalc && live) {
+        float w = (float)((double)(long long)gd->mapsum[g] / 4294967296.0);
+        if(w < 1.0f) { w = 0.0f; flags |= 1u; }
+        gd->weight[g] = w;
+        if(w > 0.0f) flags |= 2u;
+    } else if(live) flags |= 2u;
+    if(update && (flags & 2u)) gd->weight[g] = __fmul_rn(gd->weight[g], 0.9f);
+    gd->mflags[g] = flags; gd->mapsum[g] = 0ull;
+}
+/// accumulateProduct(map, -0.1, map, mask = nearest-downscaled ~dilate(lastFG)) followed by blur 3x3 (replicated border) (:1312-1315),
+/// in one pass: the decayed neighbours are recomputed on the fly, the result goes to the scratch map
+__global__ void __launch_bounds__(PAW_GM_THREADS) pawcs_gmaint_blur(const PawArgs A, int update) {
+    const GDict* gd = A.gd;
+    const int g = blockIdx.y, n = A.gW * A.gH;
+    const uint32_t flags = gd->mflags[g];
     float* m = A.gmap + (size_t)g * n;
     float* tmp = A.gmap_tmp + (size_t)g * n;
-    if(threadIdx.x == 0) { s_sum = 0ull; s_zero = 0; s_upd = 0; }
-    __syncthreads();
-    const bool live = gd->weight[g] > 0.0f;
-    if(recalc && live) {
-        long long acc = 0;
-        for(int i = threadIdx.x; i < n; i += blockDim.x) acc += __double2ll_rn((double)m[i] * 4294967296.0);
+    const int i0 = blockIdx.x * PAW_GM_THREADS * PAW_GM_PER_THREAD + threadIdx.x;
+    if(flags & 1u) {
 #pragma unroll
-        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-        if((threadIdx.x & 31) == 0) atomicAdd(&s_sum, (unsigned long long)acc);
-        __syncthreads();
-        if(threadIdx.x == 0) {
-            float w = (float)((double)(long long)s_sum / 4294967296.0);
-            if(w < 1.0f) { w = 0.0f; s_zero = 1; }
-            gd->weight[g] = w;
-            s_upd = w > 0.0f;
-        }
-        __syncthreads();
-        if(s_zero) for(int i = threadIdx.x; i < n; i += blockDim.x) m[i] = 0.0f;
-    } else {
-        if(threadIdx.x == 0) s_upd = live;
-        __syncthreads();
+        for(int k = 0; k < PAW_GM_PER_THREAD; ++k) { const int i = i0 + k * PAW_GM_THREADS; if(i < n) m[i] = 0.0f; }
+        return;
     }
-    if(update && s_upd) {
-        // accumulateProduct(map, -0.1, map, mask = nearest-downscaled ~dilate(lastFG)), weight *= 0.9, blur 3x3 replicate
-        for(int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int cx = i % A.gW, cy = i / A.gW, x = cx * 2, y = cy * 2;
-            if((A.dilinv_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u) { const float v = m[i]; m[i] = __fadd_rn(v, __fmul_rn(v, -0.1f)); }
-        }
-        if(threadIdx.x == 0) gd->weight[g] = __fmul_rn(gd->weight[g], 0.9f);
-        __syncthreads();
-        for(int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int cx = i % A.gW, cy = i / A.gW;
-            const int xl = max(cx - 1, 0), xr = min(cx + 1, A.gW - 1);
-            double s = 0.0;
+    if(!(update && (flags & 2u))) return;
+    auto decayed = [&](int cx, int cy) {
+        const float v = m[(size_t)cy * A.gW + cx];
+        const int x = cx * 2, y = cy * 2;
+        return ((A.dilinv_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u) ? __fadd_rn(v, __fmul_rn(v, -0.1f)) : v;
+    };
+#pragma unroll 1
+    for(int k = 0; k < PAW_GM_PER_THREAD; ++k) {
+        const int i = i0 + k * PAW_GM_THREADS;
+        if(i >= n) break;
+        const int cx = i % A.gW, cy = i / A.gW;
+        const int xl = max(cx - 1, 0), xr = min(cx + 1, A.gW - 1);
+        double s = 0.0;
 #pragma unroll
-            for(int d = -1; d <= 1; ++d) {
-                const float* r = m + (size_t)min(max(cy + d, 0), A.gH - 1) * A.gW;
-                s += ((double)r[xl] + (double)r[cx]) + (double)r[xr];
-            }
-            tmp[i] = (float)(s * (1.0 / 9.0));
+        for(int d = -1; d <= 1; ++d) {
+            const int yy = min(max(cy + d, 0), A.gH - 1);
+            s += ((double)decayed(xl, yy) + (double)decayed(cx, yy)) + (double)decayed(xr, yy);
         }
-        __syncthreads();
-        for(int i = threadIdx.x; i < n; i += blockDim.x) m[i] = tmp[i];
+        tmp[i] = (float)(s * (1.0 / 9.0));
     }
+}
+__global__ void __launch_bounds__(PAW_GM_THREADS) pawcs_gmaint_copy(const PawArgs A) {
+    const int g = blockIdx.y, n = A.gW * A.gH;
+    if(!(A.gd->mflags[g] & 2u)) return;
+    float* m = A.gmap + (size_t)g * n;
+    const float* tmp = A.gmap_tmp + (size_t)g * n;
+    const int i0 = blockIdx.x * PAW_GM_THREADS * PAW_GM_PER_THREAD + threadIdx.x;
+#pragma unroll
+    for(int k = 0; k < PAW_GM_PER_THREAD; ++k) { const int i = i0 + k * PAW_GM_THREADS; if(i < n) m[i] = tmp[i]; }
 }
 __global__ void pawcs_gdict_bubble(const PawArgs A) { paw_gdict_bubble_pass(A); }
 /// one bubble pass over the per-pixel global-word LUT (:1319-1334 / :411-428); `only_if_refresh`: last kernel of a conditional refresh:
