@@ -464,7 +464,46 @@ void blur(InputArray src_, OutputArray dst, Size ksize, Point, int borderType) {
     }
     dst.getMatRef() = out;
 }
-void GaussianBlur(InputArray, OutputArray, Size, double, double, int) { unsupported("GaussianBlur"); }
+static inline int reflect101(int p, int len) { if(len == 1) return 0; while(p < 0 || p >= len) { if(p < 0) p = -p; if(p >= len) p = 2 * len - 2 - p; } return p; }
+/// cv::GaussianBlur(8-bit, 3x3, sigma 0, BORDER_DEFAULT) as PBAS calls it (PBAS.cpp:83, :117): kernel [1 2 1]/4 per axis, OpenCV's fixed-point
+/// path for 8-bit images (exact weighted sum, + 8, >> 4). The chain blur -> Scharr -> convertScaleAbs -> addWeighted(0.5, 0.5) is pinned
+/// bit-exactly against cv2 4.13 as the oracle's pbas_gradient_image (tests/test_pbas_oracle_cpu.py); the stages here use the same arithmetic.
+void GaussianBlur(InputArray src_, OutputArray dst, Size ksize, double sx, double sy, int borderType) {
+    Mat src = continuous_u8(src_.getMat());
+    CV_Assert(src.depth() == CV_8U && ksize == Size(3, 3) && sx == 0 && sy == 0 && borderType == BORDER_DEFAULT);
+    const int W = src.cols, H = src.rows, C = src.channels();
+    Mat out(H, W, src.type());
+    static const int w3[3] = {1, 2, 1};
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int c = 0; c < C; ++c) {
+        int s = 0;
+        for(int dy = -1; dy <= 1; ++dy) for(int dx = -1; dx <= 1; ++dx) s += w3[dy + 1] * w3[dx + 1] * src.ptr(reflect101(y + dy, H))[reflect101(x + dx, W) * C + c];
+        out.ptr(y)[x * C + c] = (uchar)((s + 8) >> 4);
+    }
+    dst.getMatRef() = out;
+}
+/// cv::Scharr(8-bit -> 16S, (dx,dy) = (1,0) or (0,1), scale 1, delta 0, BORDER_DEFAULT): [-3 0 3; -10 0 10; -3 0 3] and its transpose
+void Scharr(InputArray src_, OutputArray dst, int ddepth, int dx, int dy, double scale, double delta, int borderType) {
+    Mat src = continuous_u8(src_.getMat());
+    CV_Assert(src.depth() == CV_8U && ddepth == CV_16S && scale == 1 && delta == 0 && borderType == BORDER_DEFAULT && dx + dy == 1 && dx >= 0 && dy >= 0);
+    const int W = src.cols, H = src.rows, C = src.channels();
+    Mat out(H, W, CV_MAKETYPE(CV_16S, C));
+    auto B = [&](int y, int x, int c) { return (int)src.ptr(reflect101(y, H))[reflect101(x, W) * C + c]; };
+    for(int y = 0; y < H; ++y) for(int x = 0; x < W; ++x) for(int c = 0; c < C; ++c) {
+        const int g = dx ? 3 * (B(y - 1, x + 1, c) - B(y - 1, x - 1, c)) + 10 * (B(y, x + 1, c) - B(y, x - 1, c)) + 3 * (B(y + 1, x + 1, c) - B(y + 1, x - 1, c))
+                         : 3 * (B(y + 1, x - 1, c) - B(y - 1, x - 1, c)) + 10 * (B(y + 1, x, c) - B(y - 1, x, c)) + 3 * (B(y + 1, x + 1, c) - B(y - 1, x + 1, c));
+        out.ptr<short>(y)[x * C + c] = (short)g;
+    }
+    dst.getMatRef() = out;
+}
+/// cv::convertScaleAbs(16S -> 8U, alpha 1, beta 0): saturate(|v|)
+void convertScaleAbs(InputArray src_, OutputArray dst, double alpha, double beta) {
+    Mat src = src_.getMat();
+    CV_Assert(src.depth() == CV_16S && alpha == 1 && beta == 0);
+    Mat out(src.rows, src.cols, CV_MAKETYPE(CV_8U, src.channels()));
+    const int n = src.cols * src.channels();
+    for(int y = 0; y < src.rows; ++y) { const short* p = src.ptr<short>(y); uchar* o = out.ptr(y); for(int x = 0; x < n; ++x) o[x] = (uchar)std::min(std::abs((int)p[x]), 255); }
+    dst.getMatRef() = out;
+}
 /// cv::accumulateWeighted(u8 -> f32): dst = src*alpha + dst*(1-alpha), in float with separate multiplies and add (Appendix E)
 void accumulateWeighted(InputArray src_, InputOutputArray dst_, double alpha, InputArray mask) {
     CV_Assert(mask.empty());
@@ -481,7 +520,14 @@ void accumulateProduct(InputArray s1_, InputArray s2_, InputOutputArray dst_, In
     for(int y = 0; y < s1.rows; ++y) { const float* p = s1.ptr<float>(y); const float* q = s2.ptr<float>(y); float* d = dst.ptr<float>(y); const uchar* k = mask.empty() ? nullptr : mask.ptr(y);
         for(int x = 0; x < s1.cols; ++x) if(!k || k[x]) { const float t = p[x] * q[x]; d[x] += t; } }
 }
-void cvtColor(InputArray, OutputArray, int, int) { unsupported("cvtColor"); }
+/// cv::cvtColor(COLOR_GRAY2BGR) (ViBe.cpp / PBAS.cpp: gray frames into the 3-channel model): the value replicated
+void cvtColor(InputArray src_, OutputArray dst, int code, int) {
+    Mat src = src_.getMat();
+    if(code != COLOR_GRAY2BGR || src.type() != CV_8UC1) unsupported("cvtColor");
+    Mat out(src.rows, src.cols, CV_8UC3);
+    for(int y = 0; y < src.rows; ++y) { const uchar* p = src.ptr(y); uchar* o = out.ptr(y); for(int x = 0; x < src.cols; ++x) o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = p[x]; }
+    dst.getMatRef() = out;
+}
 void circle(InputOutputArray, Point, int, const Scalar&, int, int, int) {}
 void putText(InputOutputArray, const String&, Point, int, double, Scalar, int, int, bool) {}
 void rectangle(InputOutputArray, Rect, const Scalar&, int, int, int) {}

@@ -653,6 +653,7 @@ void absdiff(InputArray a, InputArray b, OutputArray dst);
 void compare(InputArray a, InputArray b, OutputArray dst, int cmpop);
 void normalize(InputArray src, InputOutputArray dst, double alpha = 1, double beta = 0, int norm_type = NORM_L2, int dtype = -1, InputArray mask = noArray());
 void addWeighted(InputArray a, double alpha, InputArray b, double beta, double gamma, OutputArray dst, int dtype = -1);
+void convertScaleAbs(InputArray src, OutputArray dst, double alpha = 1, double beta = 0);
 void minMaxIdx(InputArray src, double* minVal, double* maxVal = nullptr, int* minIdx = nullptr, int* maxIdx = nullptr, InputArray mask = noArray());
 void minMaxLoc(InputArray src, double* minVal, double* maxVal = nullptr, Point* minLoc = nullptr, Point* maxLoc = nullptr, InputArray mask = noArray());
 double norm(InputArray a, int normType = NORM_L2, InputArray mask = noArray());

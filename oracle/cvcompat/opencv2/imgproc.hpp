@@ -28,6 +28,7 @@ int floodFill(InputOutputArray image, Point seedPoint, Scalar newVal, Rect* rect
 void accumulateWeighted(InputArray src, InputOutputArray dst, double alpha, InputArray mask = noArray());
 void accumulateProduct(InputArray src1, InputArray src2, InputOutputArray dst, InputArray mask = noArray());
 void cvtColor(InputArray src, OutputArray dst, int code, int dstCn = 0);
+void Scharr(InputArray src, OutputArray dst, int ddepth, int dx, int dy, double scale = 1, double delta = 0, int borderType = BORDER_DEFAULT);
 // drawing (debug displays of the reference only; no-ops here)
 void circle(InputOutputArray img, Point center, int radius, const Scalar& color, int thickness = 1, int lineType = LINE_8, int shift = 0);
 void putText(InputOutputArray img, const String& text, Point org, int fontFace, double fontScale, Scalar color, int thickness = 1, int lineType = LINE_8,

@@ -5,11 +5,12 @@
 // reference's behaviour, not copied from it.  Every function cites the reference file:line it follows
 // (paths relative to the reference root, modules/...).
 //
-// Parity status: LBSP is pinned by the reference's own golden vector (features2d/test/data/test_lbsp.bin,
-// see tests/golden/).  SuBSENSE / LOBSTER / PAWCS apply() have NO test or golden vector in the reference
-// (modules/video has no test/ directory) and the reference cannot be built here (OpenCV C++ absent):
-// for those "parity unpinned" applies; the oracle is a source-faithful restatement (quirks Q1-Q8 of
-// SURVEY.md §8a) and its OpenCV-equivalent mask ops are cross-checked against cv2 in tests/.
+// Parity status: PINNED. LBSP by the reference's own golden vector (features2d/test/data/test_lbsp.bin, see
+// tests/golden/); SuBSENSE / LOBSTER / PAWCS / ViBe / PBAS (initialize, apply, refreshModel, getBackgroundImage) by
+// the reference itself: oracle/_ref/liblitiv_ref.so is built from the reference's own unmodified sources against
+// oracle/cvcompat (`make _ref`), and tests/test_ref_pin_cpu.py holds the reference-order mode of these
+// restatements equal to it bit for bit (masks, models, float maps). The OpenCV-equivalent image operations are
+// cross-checked against cv2 in tests/. Only the edge detector (lvo_edge_lbsp.hpp) remains unpinned.
 #pragma once
 #include <cstdint>
 #include <cstddef>

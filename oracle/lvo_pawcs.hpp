@@ -2,7 +2,8 @@
 //
 // CPU restatement of BackgroundSubtractorPAWCS (reference: modules/video/src/BackgroundSubtractorPAWCS.cpp, cited as
 // PAWCS.cpp:line below; header modules/video/include/litiv/video/BackgroundSubtractorPAWCS.hpp).
-// Parity unpinned: the reference has no test or golden vector for PAWCS and cannot be built here (OpenCV C++ absent).
+// Parity pinned: MODE_REFERENCE equals the reference's own BackgroundSubtractorPAWCS.cpp (oracle/_ref) bit for bit, dictionaries included
+// (tests/test_ref_pin_cpu.py); the reference holds no test or golden vector for PAWCS.
 //
 // Two modes, like the SuBSENSE oracle:
 //   MODE_REFERENCE : the reference's raster order, libc rand() clone, every in-loop coupling (neighbour dictionaries,

@@ -1,7 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see lvo_common.hpp header).
 // CPU restatement of BackgroundSubtractorPBAS_1ch / _3ch (reference video/src/BackgroundSubtractorPBAS.cpp,
 // video/include/litiv/video/BackgroundSubtractorPBAS.hpp; compile-time switches as shipped: SELF_DIFFUSION 1, R2_ACCELERATION 0,
-// ADVANCED_MORPH_OPS 0, SC_THRS_VALIDATION 0). Parity unpinned: the reference has no test or golden vector for PBAS; the OpenCV
+// ADVANCED_MORPH_OPS 0, SC_THRS_VALIDATION 0). Parity pinned: MODE_REFERENCE equals the reference's own BackgroundSubtractorPBAS.cpp
+// (oracle/_ref) bit for bit: masks, colour / gradient models, R(x), T(x), mean-min-distance maps (tests/test_ref_pin_cpu.py); the OpenCV
 // calls of the gradient image (GaussianBlur 3x3, Scharr, convertScaleAbs, addWeighted) are restated in integers and pinned against
 // cv2 4.13 by tests/test_pbas_oracle_cpu.py.
 //

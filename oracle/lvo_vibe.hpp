@@ -1,7 +1,8 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see lvo_common.hpp header).
 // CPU restatement of BackgroundSubtractorViBe_1ch / _3ch (reference video/src/BackgroundSubtractorViBe.cpp,
 // video/include/litiv/video/BackgroundSubtractorViBe.hpp), the colour-only ancestor of LOBSTER's sample-consensus scan.
-// Parity unpinned: the reference has no test, golden vector or fixture for ViBe (modules/video has no test/ directory).
+// Parity pinned: MODE_REFERENCE equals the reference's own BackgroundSubtractorViBe.cpp (oracle/_ref) bit for bit, masks and models
+// (tests/test_ref_pin_cpu.py); the reference holds no test, golden vector or fixture for ViBe.
 //
 // Two modes, like the other oracles:
 //   MODE_REFERENCE  the reference's raster loop with the glibc rand() clone (same draw order as the source);

@@ -145,3 +145,85 @@ def lbsp_compute(img, ref=None, rel=None, thr=0):
     _chk(lib().ref_lbsp_compute(img.ctypes.data_as(C.c_void_p), rp, w, h, c, int(rel is not None), C.c_float(rel if rel is not None else 0.0),
                                 int(thr), out.ctypes.data_as(C.c_void_p)))
     return out[..., 0] if c == 1 else out
+
+
+class ReferenceViBe:
+    """BackgroundSubtractorViBe_1ch / _3ch of the reference itself (video/src/BackgroundSubtractorViBe.cpp, compiled unmodified)"""
+
+    def __init__(self, model_channels=3, color_dist_threshold=20, n_samples=20, n_required=2, seed=0):
+        self._h = C.c_void_p()
+        self.C, self.N = model_channels, n_samples
+        _chk(lib().ref_vibe_create(model_channels, color_dist_threshold, n_samples, n_required, C.c_uint(seed), C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.ref_vibe_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def _img(img):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        return img, (1 if img.ndim == 2 else img.shape[2])
+
+    def initialize(self, img):
+        img, c = self._img(img)
+        h, w = img.shape[:2]
+        _chk(lib().ref_vibe_initialize(self._h, img.ctypes.data_as(C.c_void_p), w, h, c))
+        self.shape = (h, w)
+
+    def apply(self, img, lr=16.0):
+        img, c = self._img(img)
+        mask = np.empty(self.shape, np.uint8)
+        _chk(lib().ref_vibe_apply(self._h, img.ctypes.data_as(C.c_void_p), c, mask.ctypes.data_as(C.c_void_p), C.c_double(lr)))
+        return mask
+
+    def model(self):
+        out = np.empty((self.N,) + self.shape + (self.C,), np.uint8)
+        _chk(lib().ref_vibe_model(self._h, out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out
+
+    def get_background_image(self):
+        out = np.empty(self.shape + (self.C,), np.uint8)
+        _chk(lib().ref_vibe_get_background_image(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[..., 0] if self.C == 1 else out
+
+
+class ReferencePBAS:
+    """BackgroundSubtractorPBAS_1ch / _3ch of the reference itself (video/src/BackgroundSubtractorPBAS.cpp, compiled unmodified)"""
+    STATE = {"bg_color": np.uint8, "bg_grad": np.uint8, "R": np.float32, "T": np.float32, "meanmin": np.float32, "scalars": np.float64}
+
+    def __init__(self, model_channels=3, color_dist_threshold=30, update_rate=16.0, n_samples=35, n_required=2, seed=0):
+        self._h = C.c_void_p()
+        self.C, self.N = model_channels, n_samples
+        _chk(lib().ref_pbas_create(model_channels, color_dist_threshold, C.c_float(update_rate), n_samples, n_required, C.c_uint(seed), C.byref(self._h)))
+        self.shape = None
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.ref_pbas_destroy(self._h)
+            self._h = None
+
+    def initialize(self, img):
+        img, c = ReferenceViBe._img(img)
+        h, w = img.shape[:2]
+        _chk(lib().ref_pbas_initialize(self._h, img.ctypes.data_as(C.c_void_p), w, h, c))
+        self.shape = (h, w)
+
+    def apply(self, img, lr=-1.0):
+        img, c = ReferenceViBe._img(img)
+        mask = np.empty(self.shape, np.uint8)
+        _chk(lib().ref_pbas_apply(self._h, img.ctypes.data_as(C.c_void_p), c, mask.ctypes.data_as(C.c_void_p), C.c_double(lr)))
+        return mask
+
+    def state_get(self, name):
+        shape = (self.N,) + self.shape + (self.C,) if name in ("bg_color", "bg_grad") else (2,) if name == "scalars" else self.shape
+        out = np.empty(shape, self.STATE[name])
+        _chk(lib().ref_pbas_state_get(self._h, name.encode(), out.ctypes.data_as(C.c_void_p), C.c_size_t(out.nbytes)))
+        return out
+
+    def get_background_image(self):
+        out = np.empty(self.shape + (self.C,), np.uint8)
+        _chk(lib().ref_pbas_get_background_image(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out[..., 0] if self.C == 1 else out
+

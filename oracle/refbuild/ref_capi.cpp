@@ -8,6 +8,8 @@
 #include "litiv/video/BackgroundSubtractorLOBSTER.hpp"
 #include "litiv/video/BackgroundSubtractorPAWCS.hpp"
 #include "litiv/features2d/LBSP.hpp"
+#include "litiv/video/BackgroundSubtractorViBe.hpp"
+#include "litiv/video/BackgroundSubtractorPBAS.hpp"
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -292,4 +294,107 @@ void ref_sample_pos_7x7(int rnd, int ox, int oy, int border, int w, int h, int* 
 void ref_neighbor_pos_3x3(int rnd, int ox, int oy, int border, int w, int h, int* nx, int* ny) { lv::getNeighborPosition_3x3(rnd, *nx, *ny, ox, oy, border, cv::Size(w, h)); }
 void ref_neighbor_pos_5x5(int rnd, int ox, int oy, int border, int w, int h, int* nx, int* ny) { lv::getNeighborPosition_5x5(rnd, *nx, *ny, ox, oy, border, cv::Size(w, h)); }
 
+} // extern "C"
+
+// ---- ViBe / PBAS: the reference's own BackgroundSubtractorViBe_1ch/_3ch and BackgroundSubtractorPBAS_1ch/_3ch ----
+namespace {
+struct VibeBase { virtual ~VibeBase() {} virtual BackgroundSubtractorViBe& algo() = 0; virtual const std::vector<cv::Mat>& model() const = 0; int W = 0, H = 0, C = 0; };
+struct RefViBe1 : BackgroundSubtractorViBe_1ch, VibeBase { using BackgroundSubtractorViBe_1ch::BackgroundSubtractorViBe_1ch;
+    BackgroundSubtractorViBe& algo() override { return *this; } const std::vector<cv::Mat>& model() const override { return m_voBGImg; } };
+struct RefViBe3 : BackgroundSubtractorViBe_3ch, VibeBase { using BackgroundSubtractorViBe_3ch::BackgroundSubtractorViBe_3ch;
+    BackgroundSubtractorViBe& algo() override { return *this; } const std::vector<cv::Mat>& model() const override { return m_voBGImg; } };
+struct PbasBase { virtual ~PbasBase() {} virtual BackgroundSubtractorPBAS& algo() = 0; virtual bool get(const std::string& n, Bytes& out) = 0; int W = 0, H = 0, C = 0; };
+#define PBAS_GET \
+    bool get(const std::string& n, Bytes& out) override { \
+        if(n == "bg_color") { put_samples(m_voBGImg, out); return true; } \
+        if(n == "bg_grad") { put_samples(m_voBGGrad, out); return true; } \
+        if(n == "R") { put_mat(m_oDistThresholdFrame, out); return true; } \
+        if(n == "T") { put_mat(m_oUpdateRateFrame, out); return true; } \
+        if(n == "meanmin") { put_mat(m_oMeanMinDistFrame, out); return true; } \
+        if(n == "scalars") { const double d[2] = {0.0, (double)m_fFormerMeanGradDist}; out.assign((const unsigned char*)d, (const unsigned char*)d + sizeof(d)); return true; } \
+        return false; }
+struct RefPBAS1 : BackgroundSubtractorPBAS_1ch, PbasBase { using BackgroundSubtractorPBAS_1ch::BackgroundSubtractorPBAS_1ch;
+    BackgroundSubtractorPBAS& algo() override { return *this; } PBAS_GET };
+struct RefPBAS3 : BackgroundSubtractorPBAS_3ch, PbasBase { using BackgroundSubtractorPBAS_3ch::BackgroundSubtractorPBAS_3ch;
+    BackgroundSubtractorPBAS& algo() override { return *this; } PBAS_GET };
+}
+
+extern "C" {
+int ref_vibe_create(int model_channels, int color_dist_threshold, int n_samples, int n_required, unsigned seed, void** out) {
+    REF_TRY
+    if(model_channels != 1 && model_channels != 3) throw std::runtime_error("model channels must be 1 or 3");
+    srand(seed);
+    VibeBase* b = model_channels == 1 ? (VibeBase*)new RefViBe1((size_t)color_dist_threshold, (size_t)n_samples, (size_t)n_required)
+                                      : (VibeBase*)new RefViBe3((size_t)color_dist_threshold, (size_t)n_samples, (size_t)n_required);
+    b->C = model_channels; *out = b;
+    REF_CATCH
+}
+int ref_vibe_destroy(void* h) { delete (VibeBase*)h; return 0; }
+int ref_vibe_initialize(void* h, const unsigned char* img, int w, int hh, int c) {
+    REF_TRY
+    VibeBase* b = (VibeBase*)h; b->W = w; b->H = hh;
+    b->algo().initialize(cv::Mat(hh, w, CV_8UC(c), (void*)img).clone());
+    REF_CATCH
+}
+int ref_vibe_apply(void* h, const unsigned char* img, int c, unsigned char* mask, double lr) {
+    REF_TRY
+    VibeBase* b = (VibeBase*)h; cv::Mat m;
+    b->algo().apply(cv::Mat(b->H, b->W, CV_8UC(c), (void*)img), m, lr);
+    if(m.type() != CV_8UC1 || m.rows != b->H || m.cols != b->W) throw std::runtime_error("unexpected mask type");
+    Bytes t; put_mat(m, t); std::memcpy(mask, t.data(), t.size());
+    REF_CATCH
+}
+int ref_vibe_model(void* h, unsigned char* out, size_t bytes) {
+    REF_TRY
+    Bytes t; put_samples(((VibeBase*)h)->model(), t);
+    if(t.size() != bytes) throw std::runtime_error("size mismatch for the ViBe model");
+    std::memcpy(out, t.data(), bytes);
+    REF_CATCH
+}
+int ref_vibe_get_background_image(void* h, unsigned char* out) {
+    REF_TRY
+    VibeBase* b = (VibeBase*)h; cv::Mat m; b->algo().getBackgroundImage(m);
+    if(m.type() != CV_8UC(b->C) || m.rows != b->H || m.cols != b->W) throw std::runtime_error("unexpected background image type");
+    Bytes t; put_mat(m, t); std::memcpy(out, t.data(), t.size());
+    REF_CATCH
+}
+int ref_pbas_create(int model_channels, int color_dist_threshold, float update_rate, int n_samples, int n_required, unsigned seed, void** out) {
+    REF_TRY
+    if(model_channels != 1 && model_channels != 3) throw std::runtime_error("model channels must be 1 or 3");
+    srand(seed);
+    PbasBase* b = model_channels == 1 ? (PbasBase*)new RefPBAS1((size_t)color_dist_threshold, update_rate, (size_t)n_samples, (size_t)n_required)
+                                      : (PbasBase*)new RefPBAS3((size_t)color_dist_threshold, update_rate, (size_t)n_samples, (size_t)n_required);
+    b->C = model_channels; *out = b;
+    REF_CATCH
+}
+int ref_pbas_destroy(void* h) { delete (PbasBase*)h; return 0; }
+int ref_pbas_initialize(void* h, const unsigned char* img, int w, int hh, int c) {
+    REF_TRY
+    PbasBase* b = (PbasBase*)h; b->W = w; b->H = hh;
+    b->algo().initialize(cv::Mat(hh, w, CV_8UC(c), (void*)img).clone());
+    REF_CATCH
+}
+int ref_pbas_apply(void* h, const unsigned char* img, int c, unsigned char* mask, double lr) {
+    REF_TRY
+    PbasBase* b = (PbasBase*)h; cv::Mat m;
+    b->algo().apply(cv::Mat(b->H, b->W, CV_8UC(c), (void*)img), m, lr);
+    if(m.type() != CV_8UC1 || m.rows != b->H || m.cols != b->W) throw std::runtime_error("unexpected mask type");
+    Bytes t; put_mat(m, t); std::memcpy(mask, t.data(), t.size());
+    REF_CATCH
+}
+int ref_pbas_state_get(void* h, const char* name, void* out, size_t bytes) {
+    REF_TRY
+    Bytes t;
+    if(!((PbasBase*)h)->get(name, t)) throw std::runtime_error(std::string("unknown state buffer: ") + name);
+    if(t.size() != bytes) throw std::runtime_error(std::string("size mismatch for state buffer ") + name);
+    std::memcpy(out, t.data(), bytes);
+    REF_CATCH
+}
+int ref_pbas_get_background_image(void* h, unsigned char* out) {
+    REF_TRY
+    PbasBase* b = (PbasBase*)h; cv::Mat m; b->algo().getBackgroundImage(m);
+    if(m.type() != CV_8UC(b->C) || m.rows != b->H || m.cols != b->W) throw std::runtime_error("unexpected background image type");
+    Bytes t; put_mat(m, t); std::memcpy(out, t.data(), t.size());
+    REF_CATCH
+}
 } // extern "C"

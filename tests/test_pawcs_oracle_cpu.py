@@ -1,5 +1,5 @@
 """CPU tests of the PAWCS restatement (oracle/lvo_pawcs.hpp). The reference holds no test or golden vector for PAWCS
-("parity unpinned"): these tests check the restatement's invariants, its cv2-equivalent float ops, and that the snapshot
+(the restatement is pinned to the reference's own source by tests/test_ref_pin_cpu.py): these tests check the restatement's invariants, its cv2-equivalent float ops, and that the snapshot
 semantics the GPU implements stay within the seed-to-seed noise of the reference-order semantics."""
 import numpy as np
 import pytest

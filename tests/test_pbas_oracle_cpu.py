@@ -1,4 +1,4 @@
-"""CPU tests of the PBAS oracle (oracle/lvo_pbas.hpp). The reference has no test for PBAS (parity unpinned); these pin the restated
+"""CPU tests of the PBAS oracle (oracle/lvo_pbas.hpp). The reference has no test for PBAS (the restatement itself is pinned to the reference's source by tests/test_ref_pin_cpu.py); these pin the restated
 OpenCV arithmetic of the gradient image against cv2 and measure the gap between the two oracle modes."""
 import numpy as np
 import pytest

@@ -7,6 +7,7 @@ reference-order mode (same raster order, a clone of glibc rand()) must reproduce
 float map, the LUT and the frame-level scalars, from initialize() through apply(), refreshModel() and getBackgroundImage().
 With this, `SuBSENSE / LOBSTER / PAWCS::apply` are no longer "parity unpinned": GPU == oracle(snapshot) is tested on the device,
 oracle(reference order) == reference source is tested here, and the two oracle modes share every per-pixel function.
+The same holds for ViBe and PBAS (BackgroundSubtractorViBe.cpp / BackgroundSubtractorPBAS.cpp are part of the same library).
 """
 import numpy as np
 import pytest
@@ -220,3 +221,53 @@ def test_reference_errors():
         r.initialize(np.zeros((40, 40, 3), np.uint8), np.full((40, 40), 7, np.uint8))
     with pytest.raises(R.ReferenceError_, match="no useful pixels"):
         r.initialize(np.zeros((40, 40, 3), np.uint8), np.zeros((40, 40), np.uint8))
+
+
+# ---- ViBe / PBAS: the reference's own BackgroundSubtractorViBe.cpp / BackgroundSubtractorPBAS.cpp, compiled unmodified ----
+def _vp_frame(seq, t, c_in):
+    f = seq.frame(t)
+    return np.ascontiguousarray(f[..., 0]) if c_in == 1 and f.ndim == 3 else f
+
+
+@pytest.mark.parametrize("model_c,c_in,w,h,n,seed", [(3, 3, 160, 120, 24, 0), (1, 1, 160, 120, 24, 1), (3, 1, 97, 73, 12, 2), (3, 3, 64, 48, 40, 3), (1, 1, 33, 7, 16, 4)])
+def test_vibe_oracle_reference_order_equals_reference_source(model_c, c_in, w, h, n, seed):
+    """masks every frame, the whole sample model every few frames, getBackgroundImage; learning rates 16 (default), 2 and 1; gray frames
+    into the 3-channel model (cvtColor GRAY2BGR); the uint16-wrapping L2 distance of the 3-channel class included (math.hpp:301-306)"""
+    seq = SynthSequence(w, h, 3 if c_in == 3 else 1, seed=40 + seed)
+    r = R.ReferenceViBe(model_c, seed=seed)
+    o = O.ViBeOracle(model_c, mode=O.MODE_REFERENCE, seed=seed)
+    f0 = _vp_frame(seq, 0, c_in)
+    r.initialize(f0); o.initialize(f0)
+    _same(r.model(), o.model(), "ViBe model after initialize")
+    for t in range(1, n + 1):
+        f = _vp_frame(seq, t, c_in)
+        lr = 16.0 if t % 5 else (2.0 if t % 10 else 1.0)
+        _same(r.apply(f, lr), o.apply(f, lr), f"ViBe mask, frame {t}")
+        if t % 4 == 0 or t == n:
+            _same(r.model(), o.model(), f"ViBe model, frame {t}")
+    _same(r.get_background_image(), o.get_background_image(), "ViBe getBackgroundImage")
+
+
+@pytest.mark.parametrize("model_c,c_in,w,h,n,seed", [(3, 3, 160, 120, 20, 0), (1, 1, 160, 120, 20, 1), (3, 1, 97, 73, 10, 2), (3, 3, 64, 48, 40, 3), (1, 1, 40, 9, 16, 4)])
+def test_pbas_oracle_reference_order_equals_reference_source(model_c, c_in, w, h, n, seed):
+    """masks every frame; colour and gradient models, R(x), T(x), mean-min-distance maps (floats bit for bit) and m_fFormerMeanGradDist every
+    few frames; learning-rate overrides; the gradient image goes through the cvcompat stages (blur, Scharr, convertScaleAbs, addWeighted),
+    whose composition is pinned against cv2 in tests/test_pbas_oracle_cpu.py"""
+    seq = SynthSequence(w, h, 3 if c_in == 3 else 1, seed=60 + seed)
+    r = R.ReferencePBAS(model_c, seed=seed)
+    o = O.PBASOracle(model_c, mode=O.MODE_REFERENCE, seed=seed)
+    f0 = _vp_frame(seq, 0, c_in)
+    r.initialize(f0); o.initialize(f0)
+
+    def compare(tag):
+        for name in ("bg_color", "bg_grad", "R", "T", "meanmin"):
+            _same(r.state_get(name), o.state_get(name), f"PBAS '{name}', {tag}")
+        assert r.state_get("scalars")[1] == o.state_get("scalars")[1], f"PBAS former mean gradient distance, {tag}"
+    compare("after initialize")
+    for t in range(1, n + 1):
+        f = _vp_frame(seq, t, c_in)
+        lr = -1.0 if t % 6 else (4.0 if t % 12 else 1.0)
+        _same(r.apply(f, lr), o.apply(f, lr), f"PBAS mask, frame {t}")
+        if t % 4 == 0 or t == n:
+            compare(f"frame {t}")
+    _same(r.get_background_image(), o.get_background_image(), "PBAS getBackgroundImage")

@@ -1,5 +1,5 @@
 """CPU tests of the ViBe oracle (oracle/lvo_vibe.hpp): known answers of the distance quirk, the two oracle modes against each other,
-and the restated getBackgroundImage. The reference has no test for ViBe (parity unpinned): these pin the restatement to the
+and the restated getBackgroundImage. The reference has no test for ViBe (the restatement itself is pinned to the reference's source by tests/test_ref_pin_cpu.py): these pin it to the
 source's arithmetic (video/src/BackgroundSubtractorViBe.cpp, utils/math.hpp:301-306, 391-397)."""
 import numpy as np
 import pytest
