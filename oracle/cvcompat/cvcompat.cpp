@@ -8,6 +8,7 @@
 #include "opencv2/highgui.hpp"
 #include "opencv2/features2d.hpp"
 #include "../lvo_common.hpp"
+#include "../lvo_edge_lbsp.hpp"   // normalize_minmax_u8 (the restatement of cv::normalize pinned against cv2)
 
 namespace cv {
 
@@ -268,6 +269,20 @@ Mat operator^(const Mat& a, const Mat& b) { Mat r; bitwise_xor(a, b, r); return 
 Mat operator~(const Mat& a) { Mat r; bitwise_not(a, r); return r; }
 Mat operator/(const Mat& a, double s) { Mat r; a.convertTo(r, a.type(), 1.0 / s, 0.0); return r; }
 Mat operator*(const Mat& a, double s) { Mat r; a.convertTo(r, a.type(), s, 0.0); return r; }
+Mat& operator+=(Mat& a, const Mat& b) {
+    CV_Assert(a.type() == b.type() && a.rows == b.rows && a.cols == b.cols);
+    const int dp = a.depth(), n = a.cols * a.channels(); const size_t e = a.elemSize1();
+    for(int y = 0; y < a.rows; ++y) { uchar* p = a.ptr(y); const uchar* q = b.ptr(y); for(int x = 0; x < n; ++x) set_elem(p + e * x, dp, get_elem(p + e * x, dp) + get_elem(q + e * x, dp)); }
+    return a;
+}
+Mat Mat::mul(const Mat& m, double scale) const {
+    CV_Assert(type() == m.type() && rows == m.rows && cols == m.cols);
+    Mat r(rows, cols, type());
+    const int dp = depth(), n = cols * channels(); const size_t e = elemSize1();
+    for(int y = 0; y < rows; ++y) { const uchar* p = ptr(y); const uchar* q = m.ptr(y); uchar* o = r.ptr(y); for(int x = 0; x < n; ++x) set_elem(o + e * x, dp, get_elem(p + e * x, dp) * get_elem(q + e * x, dp) * scale); }
+    return r;
+}
+double kmeans(InputArray, int, InputOutputArray, TermCriteria, int, int, OutputArray) { unsupported("kmeans"); return 0; }
 template<typename F> static Mat& bits_scalar(Mat& a, const Scalar& s, F f) {
     CV_Assert(a.depth() == CV_8U);
     const int cn = a.channels();
@@ -363,9 +378,18 @@ double determinant(InputArray) { unsupported("determinant"); return 0; }
 double invert(InputArray, OutputArray, int) { unsupported("invert"); return 0; }
 void copyMakeBorder(InputArray, OutputArray, int, int, int, int, int, const Scalar&) { unsupported("copyMakeBorder"); }
 void normalize(InputArray src_, InputOutputArray dst, double alpha, double beta, int norm_type, int dtype, InputArray mask) {
-    // only reached from the reference's debug displays; NORM_MINMAX to [alpha,beta]
+    // reached from the reference's debug displays and from EdgeDetectorLBSP::apply (bNormalizeOutput); NORM_MINMAX to [alpha,beta]
     CV_Assert(mask.empty() && norm_type == NORM_MINMAX);
     Mat src = src_.getMat(); double mn, mx; minMaxIdx(src.reshape(1), &mn, &mx);
+    if(src.type() == CV_8UC1 && dtype < 0 && std::min(alpha, beta) == 0 && std::max(alpha, beta) == 255) {
+        // OpenCV converts in FLOAT here (multiply, add, round half to even): the oracle's restatement, pinned against cv2 4.13
+        Mat out = src.clone(); CV_Assert(out.isContinuous());
+        lvo::EdgeDetectorLBSP::normalize_minmax_u8(out.data, (size_t)out.rows * out.cols);
+        Mat& d = dst.getMatRef();   // like convertTo: an output of the right size and type is written in place (the caller may hold another header on it)
+        if(d.data && d.rows == out.rows && d.cols == out.cols && d.type() == out.type()) { for(int y = 0; y < out.rows; ++y) std::memcpy(d.ptr(y), out.ptr(y), (size_t)out.cols); }
+        else d = out;
+        return;
+    }
     const double lo = std::min(alpha, beta), hi = std::max(alpha, beta), sc = mx > mn ? (hi - lo) / (mx - mn) : 0.0;
     Mat out; src.convertTo(out, dtype < 0 ? src.type() : dtype, sc, lo - mn * sc); dst.getMatRef() = out;
 }

@@ -390,6 +390,7 @@ public:
     Mat operator()(const std::vector<Range>& ranges) const;
     Mat operator()(const Range* ranges) const;
     Mat operator()(Range rowRange, Range colRange) const;
+    Mat mul(const Mat& m, double scale = 1) const;   // element-wise product (8-bit, saturating)
     Mat row(int y) const { return Mat(*this, Rect(0, y, cols, 1)); }
     Mat col(int x) const { return Mat(*this, Rect(x, 0, 1, rows)); }
     Mat rowRange(int a, int b) const { return Mat(*this, Rect(0, a, cols, b - a)); }
@@ -496,6 +497,9 @@ public:
     void create(int ndims, const int* sizes) { Mat::create(ndims, sizes, DataType<T>::type); }
     Mat_ clone() const { return Mat_(Mat::clone()); }
     Mat_ operator()(const Rect& roi) const { return Mat_(*this, roi); }
+    Mat_ operator()(const Range& rowRange, const Range& colRange) const { return Mat_(Mat::operator()(rowRange, colRange)); }
+    static Mat_ zeros(Size s) { return Mat_(Mat::zeros(s, DataType<T>::type)); }
+    static Mat_ ones(Size s) { Mat_ m(s); m = T(1); return m; }
     Mat_ operator()(const std::vector<Range>& ranges) const { return Mat_(Mat::operator()(ranges)); }
     int type() const { return DataType<T>::type; }
     int depth() const { return DataType<T>::depth; }
@@ -599,6 +603,8 @@ Mat operator^(const Mat& a, const Mat& b);
 Mat operator~(const Mat& a);
 Mat operator/(const Mat& a, double s);   // == a.convertTo(., a.type(), 1/s): float multiply, round half to even, saturate
 Mat operator*(const Mat& a, double s);
+inline Mat operator*(double s, const Mat& a) { return a * s; }
+Mat& operator+=(Mat& a, const Mat& b);   // saturating element-wise add (same type)
 Mat& operator|=(Mat& a, const Scalar& s);
 Mat& operator&=(Mat& a, const Scalar& s);
 inline Mat& operator|=(Mat& a, int s) { return a |= Scalar::all((double)s); }
@@ -653,6 +659,12 @@ void absdiff(InputArray a, InputArray b, OutputArray dst);
 void compare(InputArray a, InputArray b, OutputArray dst, int cmpop);
 void normalize(InputArray src, InputOutputArray dst, double alpha = 1, double beta = 0, int norm_type = NORM_L2, int dtype = -1, InputArray mask = noArray());
 void addWeighted(InputArray a, double alpha, InputArray b, double beta, double gamma, OutputArray dst, int dtype = -1);
+// only named by templates of the reference's umbrella headers that the compiled sources never instantiate (litiv/imgproc.hpp)
+struct TermCriteria { enum { COUNT = 1, MAX_ITER = 1, EPS = 2 }; int type, maxCount; double epsilon; TermCriteria(int t = 0, int n = 0, double e = 0) : type(t), maxCount(n), epsilon(e) {} };
+#define CV_TERMCRIT_ITER 1
+#define CV_TERMCRIT_EPS 2
+enum KmeansFlags { KMEANS_RANDOM_CENTERS = 0, KMEANS_PP_CENTERS = 2, KMEANS_USE_INITIAL_LABELS = 1 };
+double kmeans(InputArray data, int K, InputOutputArray bestLabels, TermCriteria criteria, int attempts, int flags, OutputArray centers = noArray());
 void convertScaleAbs(InputArray src, OutputArray dst, double alpha = 1, double beta = 0);
 void minMaxIdx(InputArray src, double* minVal, double* maxVal = nullptr, int* minIdx = nullptr, int* maxIdx = nullptr, InputArray mask = noArray());
 void minMaxLoc(InputArray src, double* minVal, double* maxVal = nullptr, Point* minLoc = nullptr, Point* maxLoc = nullptr, InputArray mask = noArray());

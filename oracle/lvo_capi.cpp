@@ -297,6 +297,15 @@ int lvo_normalize_minmax_u8(uint8_t* buf, size_t n) { EdgeDetectorLBSP::normaliz
 int lvo_edge_apply_threshold(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out, double thr) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply_threshold(img, w, hh, c, out, thr); LVO_CATCH }
 int lvo_edge_apply(void* h, const uint8_t* img, int w, int hh, int c, uint8_t* out) { LVO_TRY ((EdgeDetectorLBSP*)h)->apply(img, w, hh, c, out); LVO_CATCH }
 /// gradient map of the latest pass without its padding: [H][W][4] = gradX, gradY, magnitude (min over the scales), pad
+/// the detector's persistent buffers as they are: which = 0 gradient map (4 bytes per cell, padded by 2 on every side), 1 edge mask (padded)
+int lvo_edge_raw(void* h, int which, uint8_t* out, size_t* bytes) {
+    LVO_TRY
+    const std::vector<uchar>& v = which == 0 ? ((EdgeDetectorLBSP*)h)->grad : ((EdgeDetectorLBSP*)h)->edge;
+    if(!out) { *bytes = v.size(); return 0; }
+    if(*bytes != v.size()) throw std::runtime_error("size mismatch for the edge detector buffer");
+    std::memcpy(out, v.data(), v.size());
+    LVO_CATCH
+}
 int lvo_edge_gradient_map(void* h, int w, int hh, uint8_t* out) {
     LVO_TRY
     EdgeDetectorLBSP* e = (EdgeDetectorLBSP*)h;

@@ -6,11 +6,11 @@
 // (paths relative to the reference root, modules/...).
 //
 // Parity status: PINNED. LBSP by the reference's own golden vector (features2d/test/data/test_lbsp.bin, see
-// tests/golden/); SuBSENSE / LOBSTER / PAWCS / ViBe / PBAS (initialize, apply, refreshModel, getBackgroundImage) by
+// tests/golden/); SuBSENSE / LOBSTER / PAWCS / ViBe / PBAS (initialize, apply, refreshModel, getBackgroundImage) and EdgeDetectorLBSP by
 // the reference itself: oracle/_ref/liblitiv_ref.so is built from the reference's own unmodified sources against
 // oracle/cvcompat (`make _ref`), and tests/test_ref_pin_cpu.py holds the reference-order mode of these
 // restatements equal to it bit for bit (masks, models, float maps). The OpenCV-equivalent image operations are
-// cross-checked against cv2 in tests/. Only the edge detector (lvo_edge_lbsp.hpp) remains unpinned.
+// cross-checked against cv2 in tests/.
 #pragma once
 #include <cstdint>
 #include <cstddef>

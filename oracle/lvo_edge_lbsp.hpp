@@ -2,7 +2,8 @@
 // CPU restatement of EdgeDetectorLBSP (reference imgproc/src/EdgeDetectorLBSP.cpp:26-417, imgproc/include/litiv/imgproc/
 // EdgeDetectorLBSP.hpp; compile-time switches as shipped: USE_5x5_NON_MAX_SUPP 1, USE_MIN_GRAD_ORIENT 1, USE_3_AXIS_ORIENT 1; Gaussian
 // sigma 0, i.e. no pre-blur). SURVEY §8f rank 4: the checker of lvb_edge_*  and of the per-pixel
-// primitive (lvb_lbsp_gradient). Parity unpinned: the reference has no test or golden vector for the detector.
+// primitive (lvb_lbsp_gradient). Parity pinned: equals the reference's own imgproc/src/EdgeDetectorLBSP.cpp (oracle/_ref) bit for bit: edge masks,
+// confidence maps and the detector's two persistent buffers after every call (tests/test_ref_pin_cpu.py); the reference holds no test for the detector.
 //
 // The restatement keeps the reference's OBSERVABLE behaviour, including three things that look unintended:
 //   * the non-maximum-suppression loop classifies gradient row r+2 into mask row r (:263, :270-272), so the output is shifted up by two rows;

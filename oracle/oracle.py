@@ -323,6 +323,14 @@ class EdgeDetectorLBSPOracle:
         _chk(lib().lvo_edge_gradient_map(self._h, w, h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def raw(self, which):
+        """the persistent buffers as they are: 0 = gradient map (4 bytes per cell, padded by 2 on every side), 1 = edge mask (padded)"""
+        n = C.c_size_t(0)
+        _chk(lib().lvo_edge_raw(self._h, which, None, C.byref(n)))
+        out = np.empty(n.value, np.uint8)
+        _chk(lib().lvo_edge_raw(self._h, which, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+
 
 def normalize_minmax_u8(a):
     """cv::normalize(a, a, 0, 255, NORM_MINMAX) for an 8-bit array (the restatement EdgeDetectorLBSP's normalised output uses)"""

@@ -227,3 +227,38 @@ class ReferencePBAS:
         _chk(lib().ref_pbas_get_background_image(self._h, out.ctypes.data_as(C.c_void_p)))
         return out[..., 0] if self.C == 1 else out
 
+
+class ReferenceEdgeDetectorLBSP:
+    """EdgeDetectorLBSP of the reference itself (imgproc/src/EdgeDetectorLBSP.cpp, compiled unmodified)"""
+
+    def __init__(self, levels=3, hyst_low_factor=0.5, normalize_output=False):
+        self._h = C.c_void_p()
+        _chk(lib().ref_edge_create(levels, C.c_double(hyst_low_factor), int(bool(normalize_output)), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.ref_edge_destroy(self._h)
+            self._h = None
+
+    def apply_threshold(self, img, thr=0.5):
+        img, c = ReferenceViBe._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().ref_edge_apply_threshold(self._h, img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p), C.c_double(thr)))
+        return out
+
+    def apply(self, img):
+        img, c = ReferenceViBe._img(img)
+        h, w = img.shape[:2]
+        out = np.empty((h, w), np.uint8)
+        _chk(lib().ref_edge_apply(self._h, img.ctypes.data_as(C.c_void_p), w, h, c, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def raw(self, which):
+        """the detector's persistent buffers as they are: 0 = gradient map (4 bytes per cell, padded), 1 = edge mask (padded)"""
+        n = C.c_size_t(0)
+        _chk(lib().ref_edge_raw(self._h, which, None, C.byref(n)))
+        out = np.empty(n.value, np.uint8)
+        _chk(lib().ref_edge_raw(self._h, which, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return out
+

@@ -10,6 +10,7 @@
 #include "litiv/features2d/LBSP.hpp"
 #include "litiv/video/BackgroundSubtractorViBe.hpp"
 #include "litiv/video/BackgroundSubtractorPBAS.hpp"
+#include "litiv/imgproc/EdgeDetectorLBSP.hpp"
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -398,3 +399,46 @@ int ref_pbas_get_background_image(void* h, unsigned char* out) {
     REF_CATCH
 }
 } // extern "C"
+
+// ---- EdgeDetectorLBSP: the reference's own imgproc/src/EdgeDetectorLBSP.cpp ----
+namespace {
+struct RefEdge : EdgeDetectorLBSP {
+    using EdgeDetectorLBSP::EdgeDetectorLBSP;
+    const lv::aligned_vector<uchar,32>& grad() const { return m_vuLBSPGradMapData; }
+    const lv::aligned_vector<uchar,32>& edge() const { return m_vuEdgeTempMaskData; }
+};
+}
+extern "C" {
+int ref_edge_create(int levels, double hyst_low_factor, int normalize_output, void** out) {
+    REF_TRY
+    *out = new RefEdge((size_t)levels, hyst_low_factor, normalize_output != 0);
+    REF_CATCH
+}
+int ref_edge_destroy(void* h) { delete (RefEdge*)h; return 0; }
+int ref_edge_apply_threshold(void* h, const unsigned char* img, int w, int hh, int c, unsigned char* out, double thr) {
+    REF_TRY
+    cv::Mat m;
+    ((RefEdge*)h)->apply_threshold(cv::Mat(hh, w, CV_8UC(c), (void*)img), m, thr);
+    if(m.type() != CV_8UC1 || m.rows != hh || m.cols != w) throw std::runtime_error("unexpected edge mask type");
+    Bytes t; put_mat(m, t); std::memcpy(out, t.data(), t.size());
+    REF_CATCH
+}
+int ref_edge_apply(void* h, const unsigned char* img, int w, int hh, int c, unsigned char* out) {
+    REF_TRY
+    cv::Mat m;
+    ((RefEdge*)h)->apply(cv::Mat(hh, w, CV_8UC(c), (void*)img), m);
+    if(m.type() != CV_8UC1 || m.rows != hh || m.cols != w) throw std::runtime_error("unexpected confidence map type");
+    Bytes t; put_mat(m, t); std::memcpy(out, t.data(), t.size());
+    REF_CATCH
+}
+/// the detector's persistent buffers as they are: which = 0 gradient map (4 bytes per cell, padded by 2 on every side), 1 edge mask (padded)
+int ref_edge_raw(void* h, int which, unsigned char* out, size_t* bytes) {
+    REF_TRY
+    const lv::aligned_vector<uchar,32>& v = which == 0 ? ((RefEdge*)h)->grad() : ((RefEdge*)h)->edge();
+    if(!out) { *bytes = v.size(); return 0; }
+    if(*bytes != v.size()) throw std::runtime_error("size mismatch for the edge detector buffer");
+    std::memcpy(out, v.data(), v.size());
+    REF_CATCH
+}
+} // extern "C"
+

@@ -1,5 +1,6 @@
 """CPU tests of the EdgeDetectorLBSP oracle (oracle/lvo_edge_lbsp.hpp; the CUDA counterpart is lvb_edge_*, tests/test_gpu_edge.py).
-The reference has no test or golden vector for the detector (parity unpinned); these tests pin the restatement's documented properties,
+The reference has no test or golden vector for the detector (the restatement itself is pinned to the reference's own source by
+tests/test_ref_pin_cpu.py); these tests pin the restatement's documented properties,
 including the three observable quirks of the source listed in DESIGN.md (row shift, unwritten mask rows, little-endian initial value)."""
 import numpy as np
 import pytest

@@ -7,7 +7,8 @@ reference-order mode (same raster order, a clone of glibc rand()) must reproduce
 float map, the LUT and the frame-level scalars, from initialize() through apply(), refreshModel() and getBackgroundImage().
 With this, `SuBSENSE / LOBSTER / PAWCS::apply` are no longer "parity unpinned": GPU == oracle(snapshot) is tested on the device,
 oracle(reference order) == reference source is tested here, and the two oracle modes share every per-pixel function.
-The same holds for ViBe and PBAS (BackgroundSubtractorViBe.cpp / BackgroundSubtractorPBAS.cpp are part of the same library).
+The same holds for ViBe, PBAS and EdgeDetectorLBSP (BackgroundSubtractorViBe.cpp, BackgroundSubtractorPBAS.cpp and
+imgproc/src/EdgeDetectorLBSP.cpp are part of the same library).
 """
 import numpy as np
 import pytest
@@ -271,3 +272,43 @@ def test_pbas_oracle_reference_order_equals_reference_source(model_c, c_in, w, h
         if t % 4 == 0 or t == n:
             compare(f"frame {t}")
     _same(r.get_background_image(), o.get_background_image(), "PBAS getBackgroundImage")
+
+
+# ---- EdgeDetectorLBSP: the reference's own imgproc/src/EdgeDetectorLBSP.cpp, compiled unmodified ----
+def _edge_frame(seq, t, ch):
+    f = np.ascontiguousarray(seq.frame(t))
+    if ch == 1 and f.ndim == 3:
+        return np.ascontiguousarray(f[..., 0])
+    if ch in (2, 4):
+        extra = (f[..., :1].astype(np.int32) * 3 + f[..., 1:2] * 5 + 17 * t) % 256
+        return np.ascontiguousarray(np.concatenate([f, extra.astype(np.uint8)], axis=2)[..., :ch] if ch == 4 else f[..., :2])
+    return f
+
+
+@pytest.mark.parametrize("w,h,ch,levels,hyst", [(96, 72, 3, 3, 0.5), (97, 73, 1, 3, 0.5), (96, 73, 3, 2, 0.25), (97, 72, 1, 1, 0.75), (160, 120, 4, 3, 0.5),
+                                                 (43, 41, 2, 2, 0.5), (320, 240, 3, 3, 0.5)])
+def test_edge_oracle_equals_reference_source(w, h, ch, levels, hyst):
+    """one object per side, a sequence of calls (the detector's maps persist between calls): edge masks for several thresholds incl. out-of-range
+    ones, the confidence map of apply(), and after every call the detector's two persistent buffers byte for byte (padded gradient map with the
+    little-endian initial value, padded edge mask with the two rows the suppression never writes)"""
+    seq = SynthSequence(w, h, 1 if ch == 1 else 3, seed=w + h + ch)
+    r, o = R.ReferenceEdgeDetectorLBSP(levels, hyst), O.EdgeDetectorLBSPOracle(levels, hyst)
+    for t, thr in [(3, 0.5), (5, 0.25), (7, 0.75), (9, 0.0), (11, 0.9), (12, -1.0), (13, 1.0)]:
+        f = _edge_frame(seq, t, ch)
+        _same(r.apply_threshold(f, thr), o.apply_threshold(f, thr), f"edge mask, frame {t}, threshold {thr}")
+        _same(r.raw(0), o.raw(0), f"gradient map buffer, frame {t}")
+        _same(r.raw(1), o.raw(1), f"edge mask buffer, frame {t}")
+    f = _edge_frame(seq, 14, ch)
+    a, b = r.apply(f), o.apply(f)
+    _same(a, b, "confidence map of apply()")
+    assert b.any()
+    _same(r.raw(1), o.raw(1), "edge mask buffer after apply()")
+
+
+def test_edge_normalized_output_equals_reference_source():
+    """bNormalizeOutput = true: cv::normalize(NORM_MINMAX) of the confidence map (the cvcompat call forwards to the restatement that
+    tests/test_edge_oracle_cpu.py pins against cv2)"""
+    seq = SynthSequence(160, 120, 3, seed=31)
+    r, o = R.ReferenceEdgeDetectorLBSP(3, 0.5, True), O.EdgeDetectorLBSPOracle(3, 0.5, normalize_output=True)
+    for t in (4, 9):
+        _same(r.apply(seq.frame(t)), o.apply(seq.frame(t)), f"normalised confidence map, frame {t}")
