@@ -4,7 +4,7 @@
 // call per full-resolution pixel, three levels (sizes 1 + 1/4 + 1/16 = 1.31): image read C and 4-byte map written, re-read and rewritten by
 // the combination (C + 13 per level pixel, + C for writing the two coarser images), the suppression's map read 4 and mask write 1 (its 5x5
 // window is served by L1 / L2), one mask read per flood sweep, mask read + result write 2: about 33 B/px for RGB with four sweeps
-// (tools/bench_edge.py). The detector is launch bound at CDnet sizes (16 launches and one flag read-back per call).
+// (tools/bench_edge.py). The detector is launch bound at CDnet sizes (14 launches per call, no host round trip).
 #pragma once
 #include "edge_px.cuh"
 
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) edge_nms_kernel(const EdgeMaps m, unsigne
     mask[(size_t)y * m.W + x] = edge_mask_value(m, y, x, lo, hi, mask);
 }
 
-/// hysteresis (:353-372): one relaxation sweep. Every CTA iterates its 32x16 tile (+1 halo) in shared memory until the tile is stable
+/// hysteresis (:353-372), round-1 form kept for cross-checks (LVB_EDGE_SWEEPS=1): one relaxation sweep. Every CTA iterates its 32x16 tile (+1 halo) in shared memory until the tile is stable
 /// (bounded), then writes back the pixels it turned from "maybe" to "edge" and raises *changed. The host repeats sweeps until a sweep
 /// changes nothing; transitions are monotone (0 -> 2 only), so concurrent tiles reading each other's halo mid-sweep is harmless.
 constexpr int FL_W = 32, FL_H = 16, FL_LOCAL_ITERS = 64;
@@ -60,6 +60,103 @@ __global__ void __launch_bounds__(FL_W * FL_H) edge_flood_kernel(uchar* mask, in
     }
     if(turned) mask[(size_t)y * W + x] = EDGE_YES;
     if(__syncthreads_or(turned ? 1 : 0) && tx == 0 && ty == 0) *changed = 1;
+}
+
+// ---- hysteresis as connected components (replaces the relaxation sweeps above on the product path) ---------------------------------------
+// The flood turns every "maybe" pixel that is 8-connected, through "maybe" / "edge" pixels, to an "edge" pixel into an edge. That is: the
+// connected components (8-neighbourhood) of E = {maybe, edge} that contain a seed S = {edge}. Same machinery as the hole filling of the
+// SuBSENSE mask chain (postproc.cuh): nodes = ROW RUNS of E, lock-free union-find, node 0 = "holds a seed"; three contact masks per row pair
+// (straight, two diagonals) each give one union per maximal run of the contact. Cost independent of the edge geometry, no host round trip
+// (the sweeps needed 12 launches and three flag read-backs at 1080p).
+struct EdgeUF { int W, H, WW, RS; uint32_t* E; uint32_t* S; uint32_t* parent; ushort* rankbase; uchar* mask; };
+
+/// byte mask -> bit planes E (maybe or edge) and S (edge); one warp per 32 pixels of a row
+__global__ void __launch_bounds__(256) edge_pack_kernel(const EdgeUF A) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(y >= A.H) return;
+    const uchar v = x < A.W ? A.mask[(size_t)y * A.W + x] : (uchar)EDGE_NONE;
+    const uint32_t e = __ballot_sync(0xFFFFFFFFu, v == EDGE_MAYBE || v == EDGE_YES), sd = __ballot_sync(0xFFFFFFFFu, v == EDGE_YES);
+    if(threadIdx.x == 0) { A.E[(size_t)y * A.WW + blockIdx.x] = e; A.S[(size_t)y * A.WW + blockIdx.x] = sd; }
+}
+__device__ __forceinline__ uint32_t euf_word(const uint32_t* __restrict__ P, int y, int wi, int WW) { return (wi < 0 || wi >= WW) ? 0u : P[(size_t)y * WW + wi]; }
+/// node id of the E run of row y that contains bit b of word wi
+__device__ __forceinline__ uint32_t euf_run_id(const EdgeUF& A, int y, int wi, int b) {
+    const uint32_t st = lvb::run_starts(euf_word(A.E, y, wi, A.WW), euf_word(A.E, y, wi - 1, A.WW));
+    const uint32_t upto = b == 31 ? 0xFFFFFFFFu : ((2u << b) - 1u);
+    return 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi] + __popc(st & upto) - 1u;
+}
+/// per row (one warp): number the runs of E, every run its own root
+__global__ void __launch_bounds__(256) edge_uf_init(const EdgeUF A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    const int nchunks = (A.WW + 31) >> 5;
+    uint32_t base = 0;
+    for(int k = 0; k < nchunks; ++k) {
+        const int wi = k * 32 + lane;
+        const uint32_t st = lvb::run_starts(euf_word(A.E, y, wi, A.WW), euf_word(A.E, y, wi - 1, A.WW));
+        uint32_t cnt = __popc(st), incl = cnt;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if(lane >= o) incl += v; }
+        const uint32_t excl = base + incl - cnt;
+        if(wi < A.WW) {
+            A.rankbase[(size_t)y * A.WW + wi] = (ushort)excl;
+            for(uint32_t r = 0; r < cnt; ++r) { const uint32_t id = 1u + (uint32_t)y * A.RS + excl + r; A.parent[id] = id; }
+        }
+        base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if(y == 0 && threadIdx.x == 0) A.parent[0] = 0u;
+}
+/// per row (one warp): runs that hold a seed go under node 0; runs of rows y-1 and y that touch (8-neighbourhood) are united
+__global__ void __launch_bounds__(256) edge_uf_union(const EdgeUF A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    for(int wi = lane; wi < A.WW; wi += 32) {
+        const uint32_t e = euf_word(A.E, y, wi, A.WW), ep = euf_word(A.E, y, wi - 1, A.WW);
+        {   // seeds: one union per maximal run of S (S is a subset of E)
+            const uint32_t sd = euf_word(A.S, y, wi, A.WW);
+            uint32_t ss = lvb::run_starts(sd, euf_word(A.S, y, wi - 1, A.WW));
+            while(ss) { const int b = __ffs(ss) - 1; ss &= ss - 1; lvb::uf_union(A.parent, euf_run_id(A, y, wi, b), 0u); }
+        }
+        if(y == 0) continue;
+        const uint32_t u = euf_word(A.E, y - 1, wi, A.WW), ul = euf_word(A.E, y - 1, wi - 1, A.WW), ur = euf_word(A.E, y - 1, wi + 1, A.WW);
+        const uint32_t ull = euf_word(A.E, y - 1, wi - 2, A.WW);
+        // contact masks in row-y coordinates: bit x set when pixel (y,x) touches pixel (y-1, x+d)
+#pragma unroll
+        for(int d = -1; d <= 1; ++d) {
+            // up_d: bit x = E[y-1][x+d] for this word and the previous one (a contact run may continue from the previous word)
+            const uint32_t up = d == 0 ? u : d < 0 ? ((u << 1) | (ul >> 31)) : ((u >> 1) | (ur << 31));
+            const uint32_t upp = d == 0 ? ul : d < 0 ? ((ul << 1) | (ull >> 31)) : ((ul >> 1) | (u << 31));
+            uint32_t cs = lvb::run_starts(e & up, ep & upp);
+            while(cs) {
+                const int b = __ffs(cs) - 1; cs &= cs - 1;
+                int wb = wi, bb = b + d;                       // the touched pixel of row y-1
+                if(bb < 0) { bb = 31; --wb; } else if(bb > 31) { bb = 0; ++wb; }
+                lvb::uf_union(A.parent, euf_run_id(A, y - 1, wb, bb), euf_run_id(A, y, wi, b));
+            }
+        }
+    }
+}
+/// per row (one warp): the runs whose root is node 0 become edges (only their "maybe" pixels change in the byte mask)
+__global__ void __launch_bounds__(256) edge_uf_apply(const EdgeUF A) {
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if(y >= A.H) return;
+    const int nchunks = (A.WW + 31) >> 5;
+    uint32_t carry = 0;
+    for(int k = 0; k < nchunks; ++k) {
+        const int wi = k * 32 + lane;
+        const uint32_t m = euf_word(A.E, y, wi, A.WW);
+        uint32_t st = lvb::run_starts(m, euf_word(A.E, y, wi - 1, A.WW)), rs = 0;
+        if(wi < A.WW) {
+            const uint32_t base = 1u + (uint32_t)y * A.RS + A.rankbase[(size_t)y * A.WW + wi];
+            uint32_t r = 0;
+            while(st) { const int b = __ffs(st) - 1; st &= st - 1; if(lvb::uf_find(A.parent, base + r) == 0u) rs |= 1u << b; ++r; }
+        }
+        const uint32_t reach = lvb::fill_up_chunk(m, rs, carry);
+        if(wi < A.WW) {
+            uint32_t turn = reach & ~A.S[(size_t)y * A.WW + wi];   // "maybe" pixels of seeded components
+            while(turn) { const int b = __ffs(turn) - 1; turn &= turn - 1; A.mask[(size_t)y * A.W + (size_t)wi * 32 + b] = EDGE_YES; }
+        }
+    }
 }
 
 /// the output of one threshold pass (:374: 255 where the mask holds 2), the 2 -> 3 relabel of the two persisted rows, and for apply()

@@ -15,6 +15,9 @@ struct lvb_edge_context {
     std::vector<int> Wl, Hl; std::vector<size_t> pitch;
     std::vector<uint8_t*> img; std::vector<uchar4*> V; std::vector<CUtensorMap> tmap; std::vector<int> use_tma;
     uint8_t *mask = nullptr, *out = nullptr; int* flag = nullptr; unsigned* minmax = nullptr;
+    // hysteresis by union-find on row runs (edge.cuh): bit planes, parents, per-word run ranks
+    uint32_t *uf_E = nullptr, *uf_S = nullptr, *uf_parent = nullptr; uint16_t* uf_rank = nullptr; int WW = 0, RS = 0;
+    bool use_sweeps = getenv("LVB_EDGE_SWEEPS") != nullptr;   // debugging aid: the relaxation sweeps of round 1 instead
     uint64_t flood_sweeps = 0;   // relaxation sweeps of the latest call (diagnostic)
 
     void free_all() {
@@ -24,6 +27,8 @@ struct lvb_edge_context {
         if(out) cudaFree(out);
         if(flag) cudaFree(flag);
         if(minmax) cudaFree(minmax);
+        for(void* p : {(void*)uf_E, (void*)uf_S, (void*)uf_parent, (void*)uf_rank}) if(p) cudaFree(p);
+        uf_E = uf_S = uf_parent = nullptr; uf_rank = nullptr;
         img.clear(); V.clear(); tmap.clear(); use_tma.clear(); Wl.clear(); Hl.clear(); pitch.clear();
         mask = out = nullptr; flag = nullptr; minmax = nullptr; W = H = C = 0;
     }
@@ -52,6 +57,9 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
         c->out = dalloc<uint8_t>(c->stream, (size_t)W * H);
         c->flag = dalloc<int>(c->stream, 1);
         c->minmax = dalloc<unsigned>(c->stream, 2);
+        c->WW = (W + 31) / 32; c->RS = (W + 1) / 2 + 1;   // at most ceil(W/2) runs per row
+        c->uf_E = dalloc<uint32_t>(c->stream, (size_t)H * c->WW); c->uf_S = dalloc<uint32_t>(c->stream, (size_t)H * c->WW);
+        c->uf_parent = dalloc<uint32_t>(c->stream, 1 + (size_t)H * c->RS); c->uf_rank = dalloc<uint16_t>(c->stream, (size_t)H * c->WW);
         c->W = W; c->H = H; c->C = C;   // last: a failed allocation leaves W == 0, so the next call starts over instead of using half a set of maps
     }
     cudaStream_t st = c->stream;
@@ -85,21 +93,31 @@ void edge_pass(lvb_edge_context* c, unsigned hi, int accumulate) {
     if(c->levels > 1) { m.V1 = c->V[1]; m.W1 = c->Wl[1]; m.H1 = c->Hl[1]; }
     const dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     lvb_edge::edge_nms_kernel<<<g, b, 0, st>>>(m, lo, hi, c->mask); LAUNCHED();
-    const dim3 fb(lvb_edge::FL_W, lvb_edge::FL_H), fg((W + lvb_edge::FL_W - 1) / lvb_edge::FL_W, (H + lvb_edge::FL_H - 1) / lvb_edge::FL_H);
-    constexpr int SWEEPS_PER_CHECK = 4;
-    const uint64_t cap = (uint64_t)W * H + SWEEPS_PER_CHECK;   // every sweep but the last turns at least one pixel
-    for(uint64_t done = 0;;) {
-        // only the last sweep of a group reports: a group ends the loop when its last sweep found nothing left to turn
-        for(int i = 0; i < SWEEPS_PER_CHECK; ++i) {
-            if(i == SWEEPS_PER_CHECK - 1) CK(cudaMemsetAsync(c->flag, 0, sizeof(int), st));
-            lvb_edge::edge_flood_kernel<<<fg, fb, 0, st>>>(c->mask, W, H, c->flag); LAUNCHED();
+    if(!c->use_sweeps) {   // hysteresis (:353-372) as connected components of {maybe, edge} that hold an edge: no host round trip
+        lvb_edge::EdgeUF U{};
+        U.W = W; U.H = H; U.WW = c->WW; U.RS = c->RS; U.E = c->uf_E; U.S = c->uf_S; U.parent = c->uf_parent; U.rankbase = c->uf_rank; U.mask = c->mask;
+        const int rb = (H + 7) / 8;
+        lvb_edge::edge_pack_kernel<<<dim3(c->WW, rb), dim3(32, 8), 0, st>>>(U); LAUNCHED();
+        lvb_edge::edge_uf_init<<<rb, 256, 0, st>>>(U); LAUNCHED();
+        lvb_edge::edge_uf_union<<<rb, 256, 0, st>>>(U); LAUNCHED();
+        lvb_edge::edge_uf_apply<<<rb, 256, 0, st>>>(U); LAUNCHED();
+    } else {
+        const dim3 fb(lvb_edge::FL_W, lvb_edge::FL_H), fg((W + lvb_edge::FL_W - 1) / lvb_edge::FL_W, (H + lvb_edge::FL_H - 1) / lvb_edge::FL_H);
+        constexpr int SWEEPS_PER_CHECK = 4;
+        const uint64_t cap = (uint64_t)W * H + SWEEPS_PER_CHECK;   // every sweep but the last turns at least one pixel
+        for(uint64_t done = 0;;) {
+            // only the last sweep of a group reports: a group ends the loop when its last sweep found nothing left to turn
+            for(int i = 0; i < SWEEPS_PER_CHECK; ++i) {
+                if(i == SWEEPS_PER_CHECK - 1) CK(cudaMemsetAsync(c->flag, 0, sizeof(int), st));
+                lvb_edge::edge_flood_kernel<<<fg, fb, 0, st>>>(c->mask, W, H, c->flag); LAUNCHED();
+            }
+            done += SWEEPS_PER_CHECK; c->flood_sweeps += SWEEPS_PER_CHECK;
+            int changed = 0;
+            CK(cudaMemcpyAsync(&changed, c->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if(!changed) break;
+            REQUIRE(done < cap, "edge hysteresis did not converge");
         }
-        done += SWEEPS_PER_CHECK; c->flood_sweeps += SWEEPS_PER_CHECK;
-        int changed = 0;
-        CK(cudaMemcpyAsync(&changed, c->flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if(!changed) break;
-        REQUIRE(done < cap, "edge hysteresis did not converge");
     }
     lvb_edge::edge_output_kernel<<<g, b, 0, st>>>(c->mask, W, H, c->out, accumulate); LAUNCHED();
 }

@@ -95,12 +95,10 @@ __device__ __forceinline__ uint32_t paw_isqrt(uint32_t n) {
     return r;
 }
 __device__ __forceinline__ uint32_t paw_cdist3(uint32_t cur, uint32_t bg) { // math.hpp:474-496 for uchar triplets
-    const uint32_t c0 = cur & 0xFFu, c1 = (cur >> 8) & 0xFFu, c2 = (cur >> 16) & 0xFFu;
-    const uint32_t b0 = bg & 0xFFu, b1 = (bg >> 8) & 0xFFu, b2 = (bg >> 16) & 0xFFu;
-    const bool nonconst = (c1 != c0) || (b1 != b0) || (c2 != c1) || (b2 != b1);
-    const bool nonnull = ((cur ^ bg) & 0x00FFFFFFu) != 0u;
-    if(!(nonconst && nonnull)) return 0u;
-    const uint32_t cs = c0 * c0 + c1 * c1 + c2 * c2, bs = b0 * b0 + b1 * b1 + b2 * b2, mix = c0 * b0 + c1 * b1 + c2 * b2;
+    const uint32_t cu = cur & 0x00FFFFFFu, bu = bg & 0x00FFFFFFu;
+    const bool isconst = cu == (cu & 0xFFu) * 0x010101u && bu == (bu & 0xFFu) * 0x010101u; // every channel of both colours equal
+    if(isconst || cu == bu) return 0u;
+    const uint32_t cs = __dp4a(cu, cu, 0u), bs = __dp4a(bu, bu, 0u), mix = __dp4a(cu, bu, 0u); // sums of squares and the dot product
     // floor(mix^2 / max(bs,1)) exactly, without a 64-bit or double division: q <= cs < 2^18 (Cauchy-Schwarz), so a single-
     // precision estimate (relative error < 2^-21) is off by at most one; the remainder (|r| < 2^19, so 32-bit wrapping arithmetic
     // holds it exactly although mix^2 does not fit) fixes it

@@ -41,7 +41,7 @@ def test_edge_1080p_and_size_change(lv, oracle):
     e, o = lv.EdgeDetectorLBSP(), oracle.EdgeDetectorLBSPOracle()
     f = SynthSequence(1920, 1080, 3, seed=4).frame(20)
     assert np.array_equal(e.apply_threshold(f), o.apply_threshold(f))
-    assert e.flood_sweeps() >= 4
+    assert e.flood_sweeps() == 0     # hysteresis by union-find on row runs: no relaxation sweeps, no host round trip
     small = SynthSequence(160, 120, 3, seed=4).frame(20)
     assert np.array_equal(e.apply_threshold(small, 0.3), oracle.EdgeDetectorLBSPOracle().apply_threshold(small, 0.3))
 
@@ -62,6 +62,27 @@ def test_edge_normalized_confidence_map(lv, oracle, size, ch):
     # a map whose minimum is not zero (every pixel an edge at some threshold) cannot come out of real images easily: a flat image instead
     flat = np.full((h, w) if ch == 1 else (h, w, ch), 90, np.uint8)
     assert np.array_equal(e.apply(flat), o.apply(flat)) and not o.apply(flat).any()
+
+
+def test_edge_hysteresis_by_sweeps_equals_union_find(lv, oracle, monkeypatch):
+    """LVB_EDGE_SWEEPS=1 (read when the detector is created) selects round 1's relaxation sweeps; both forms of the hysteresis must give
+    the oracle's masks on images with long thin edges, blobs and noise"""
+    rng = np.random.default_rng(8)
+    img = np.full((241, 333), 90, np.uint8)
+    img[40:200, 50:53] = 200; img[100:103, 20:300] = 30                         # long thin structures
+    img[150:230, 200:320] = rng.integers(0, 256, (80, 120), dtype=np.int64).astype(np.uint8)   # noise block: many small components
+    yy, xx = np.mgrid[0:241, 0:333]
+    img[(yy - 60) ** 2 + (xx - 250) ** 2 < 900] = 170                            # disc
+    uf = lv.EdgeDetectorLBSP(3)
+    monkeypatch.setenv("LVB_EDGE_SWEEPS", "1")
+    sw = lv.EdgeDetectorLBSP(3)
+    monkeypatch.delenv("LVB_EDGE_SWEEPS")
+    o = oracle.EdgeDetectorLBSPOracle(3)
+    for thr in (0.5, 0.2, 0.8, 0.05):
+        want = o.apply_threshold(img, thr)
+        assert np.array_equal(uf.apply_threshold(img, thr), want), thr
+        assert np.array_equal(sw.apply_threshold(img, thr), want), thr
+    assert uf.flood_sweeps() == 0 and sw.flood_sweeps() >= 4 and want.any()
 
 
 def test_edge_argument_checks(lv):
