@@ -4,7 +4,7 @@
 // call per full-resolution pixel, three levels (sizes 1 + 1/4 + 1/16 = 1.31): image read C and 4-byte map written, re-read and rewritten by
 // the combination (C + 13 per level pixel, + C for writing the two coarser images), the suppression's map read 4 and mask write 1 (its 5x5
 // window is served by L1 / L2), one mask read per flood sweep, mask read + result write 2: about 33 B/px for RGB with four sweeps
-// (tools/bench_edge.py). The detector is launch bound at CDnet sizes (14 launches per call, no host round trip).
+// (tools/bench_edge.py). The detector is launch bound at CDnet sizes (10 launches per call, no host round trip).
 #pragma once
 #include "edge_px.cuh"
 
@@ -18,19 +18,22 @@ __global__ void __launch_bounds__(256) edge_pyr_down_kernel(const uchar* cur, si
     nxt[(size_t)y * npitch + xk] = pyr_down_px(cur, cpitch, Wc, Hc, C, 2 * y, 2 * x, k);
 }
 
-/// V_l = combine(own gradient, coarser V or the initial value); `own` and `out` may alias (one thread per pixel, read before write)
-__global__ void __launch_bounds__(256) edge_combine_kernel(const uchar4* own, int Wl, int Hl, const uchar4* coarse, int Wc, uchar4* out) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if(x >= Wl || y >= Hl) return;
-    const uchar4 c = coarse ? coarse[(size_t)(y >> 1) * Wc + (x >> 1)] : edge_init_value();
-    out[(size_t)y * Wl + x] = edge_combine(own[(size_t)y * Wl + x], c);
-}
+// (V_l = combine(own gradient, coarser V or the initial value) is the epilogue of lbsp_gradient_kernel, lobster.cuh)
 
-/// mask rows 0 .. H-3 <- suppression class of gradient rows 2 .. H-1; rows H-2, H-1 are left as the previous call left them
-__global__ void __launch_bounds__(256) edge_nms_kernel(const EdgeMaps m, unsigned lo, unsigned hi, uchar* mask) {
+/// mask rows 0 .. H-3 <- suppression class of gradient rows 2 .. H-1; rows H-2, H-1 are left as the previous call left them.
+/// E / S (optional): the bit planes of the hysteresis (E: maybe or edge, S: edge), all H rows, one word per warp (blockDim = (32, 8))
+__global__ void __launch_bounds__(256) edge_nms_kernel(const EdgeMaps m, unsigned lo, unsigned hi, uchar* mask, uint32_t* E, uint32_t* S, int WW) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if(x >= m.W || y >= m.H - 2) return;
-    mask[(size_t)y * m.W + x] = edge_mask_value(m, y, x, lo, hi, mask);
+    if(y >= m.H) return;
+    uchar v = EDGE_NONE;
+    if(x < m.W) {
+        if(y < m.H - 2) { v = edge_mask_value(m, y, x, lo, hi, mask); mask[(size_t)y * m.W + x] = v; }
+        else v = mask[(size_t)y * m.W + x];
+    }
+    if(E) {
+        const uint32_t e = __ballot_sync(0xFFFFFFFFu, v == EDGE_MAYBE || v == EDGE_YES), sd = __ballot_sync(0xFFFFFFFFu, v == EDGE_YES);
+        if(threadIdx.x == 0) { E[(size_t)y * WW + blockIdx.x] = e; S[(size_t)y * WW + blockIdx.x] = sd; }
+    }
 }
 
 /// hysteresis (:353-372), round-1 form kept for cross-checks (LVB_EDGE_SWEEPS=1): one relaxation sweep. Every CTA iterates its 32x16 tile (+1 halo) in shared memory until the tile is stable
@@ -70,14 +73,7 @@ __global__ void __launch_bounds__(FL_W * FL_H) edge_flood_kernel(uchar* mask, in
 // (the sweeps needed 12 launches and three flag read-backs at 1080p).
 struct EdgeUF { int W, H, WW, RS; uint32_t* E; uint32_t* S; uint32_t* parent; ushort* rankbase; uchar* mask; };
 
-/// byte mask -> bit planes E (maybe or edge) and S (edge); one warp per 32 pixels of a row
-__global__ void __launch_bounds__(256) edge_pack_kernel(const EdgeUF A) {
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if(y >= A.H) return;
-    const uchar v = x < A.W ? A.mask[(size_t)y * A.W + x] : (uchar)EDGE_NONE;
-    const uint32_t e = __ballot_sync(0xFFFFFFFFu, v == EDGE_MAYBE || v == EDGE_YES), sd = __ballot_sync(0xFFFFFFFFu, v == EDGE_YES);
-    if(threadIdx.x == 0) { A.E[(size_t)y * A.WW + blockIdx.x] = e; A.S[(size_t)y * A.WW + blockIdx.x] = sd; }
-}
+// (the bit planes E / S are written by edge_nms_kernel)
 __device__ __forceinline__ uint32_t euf_word(const uint32_t* __restrict__ P, int y, int wi, int WW) { return (wi < 0 || wi >= WW) ? 0u : P[(size_t)y * WW + wi]; }
 /// node id of the E run of row y that contains bit b of word wi
 __device__ __forceinline__ uint32_t euf_run_id(const EdgeUF& A, int y, int wi, int b) {

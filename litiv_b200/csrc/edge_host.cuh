@@ -70,15 +70,13 @@ void edge_prepare(lvb_edge_context* c, const uint8_t* src, int W, int H, int C, 
         lvb_edge::edge_pyr_down_kernel<<<g, b, 0, st>>>(c->img[l], c->pitch[l], Wl[l], Hl[l], C, c->img[l + 1], c->pitch[l + 1], Wl[l + 1], Hl[l + 1]);
         LAUNCHED();
     }
-    for(int l = c->levels - 1; l >= 0; --l) {  // per-level LBSP gradient, then the min-|.| combination with the coarser level
+    for(int l = c->levels - 1; l >= 0; --l) {  // per-level LBSP gradient with the min-|.| combination with the coarser level in its epilogue
         LbspGradArgs A{};
         A.W = Wl[l]; A.H = Hl[l]; A.img = c->img[l]; A.ipitch = c->pitch[l]; A.out = c->V[l]; A.use_tma = c->use_tma[l];
+        A.combine = 1; A.coarse = l + 1 < c->levels ? c->V[l + 1] : nullptr; A.Wc = l + 1 < c->levels ? Wl[l + 1] : 0;
         const dim3 gg((Wl[l] + TILE_W - 1) / TILE_W, (Hl[l] + TILE_H - 1) / TILE_H), gb(TILE_W, TILE_H);
         if(C == 1) lbsp_gradient_kernel<1><<<gg, gb, 0, st>>>(A, c->tmap[l]); else if(C == 2) lbsp_gradient_kernel<2><<<gg, gb, 0, st>>>(A, c->tmap[l]);
         else if(C == 3) lbsp_gradient_kernel<3><<<gg, gb, 0, st>>>(A, c->tmap[l]); else lbsp_gradient_kernel<4><<<gg, gb, 0, st>>>(A, c->tmap[l]);
-        LAUNCHED();
-        const dim3 g((Wl[l] + 31) / 32, (Hl[l] + 7) / 8);
-        lvb_edge::edge_combine_kernel<<<g, b, 0, st>>>(c->V[l], Wl[l], Hl[l], l + 1 < c->levels ? c->V[l + 1] : nullptr, l + 1 < c->levels ? Wl[l + 1] : 0, c->V[l]);
         LAUNCHED();
     }
 }
@@ -92,12 +90,11 @@ void edge_pass(lvb_edge_context* c, unsigned hi, int accumulate) {
     m.V0 = c->V[0]; m.W = W; m.H = H;
     if(c->levels > 1) { m.V1 = c->V[1]; m.W1 = c->Wl[1]; m.H1 = c->Hl[1]; }
     const dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    lvb_edge::edge_nms_kernel<<<g, b, 0, st>>>(m, lo, hi, c->mask); LAUNCHED();
+    lvb_edge::edge_nms_kernel<<<g, b, 0, st>>>(m, lo, hi, c->mask, c->use_sweeps ? nullptr : c->uf_E, c->use_sweeps ? nullptr : c->uf_S, c->WW); LAUNCHED();
     if(!c->use_sweeps) {   // hysteresis (:353-372) as connected components of {maybe, edge} that hold an edge: no host round trip
         lvb_edge::EdgeUF U{};
         U.W = W; U.H = H; U.WW = c->WW; U.RS = c->RS; U.E = c->uf_E; U.S = c->uf_S; U.parent = c->uf_parent; U.rankbase = c->uf_rank; U.mask = c->mask;
         const int rb = (H + 7) / 8;
-        lvb_edge::edge_pack_kernel<<<dim3(c->WW, rb), dim3(32, 8), 0, st>>>(U); LAUNCHED();
         lvb_edge::edge_uf_init<<<rb, 256, 0, st>>>(U); LAUNCHED();
         lvb_edge::edge_uf_union<<<rb, 256, 0, st>>>(U); LAUNCHED();
         lvb_edge::edge_uf_apply<<<rb, 256, 0, st>>>(U); LAUNCHED();

@@ -1792,7 +1792,7 @@ int lvb_lbsp_compute(const uint8_t* img, const uint8_t* ref, int W, int H, int C
 
 int lvb_lbsp_gradient(const uint8_t* img, int W, int H, int C, uint8_t* out, int device) {
     LVB_TRY
-    REQUIRE(img && out && (C == 1 || C == 3), "input image must be non-empty, continuous, and of type 8UC1/8UC3");
+    REQUIRE(img && out && C >= 1 && C <= 4, "input image must be non-empty, continuous, and of type 8UC1 .. 8UC4");   // LBSP.hpp:235: any channel count
     REQUIRE(W >= 5 && H >= 5, "input image size is too small to compute descriptors with current patch size");
     REQUIRE(lvb_device_count() > 0, "no CUDA device available: litiv_b200 has no CPU fallback");
     CK(cudaSetDevice(device));
@@ -1807,7 +1807,8 @@ int lvb_lbsp_gradient(const uint8_t* img, int W, int H, int C, uint8_t* out, int
         A.W = W; A.H = H; A.img = d_img; A.ipitch = pitch; A.out = d_out;
         A.use_tma = make_image_tmap(&tmap, d_img, W, H, C, pitch) ? 1 : 0;
         const dim3 g((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H), b(TILE_W, TILE_H);
-        if(C == 1) lbsp_gradient_kernel<1><<<g, b>>>(A, tmap); else lbsp_gradient_kernel<3><<<g, b>>>(A, tmap);
+        if(C == 1) lbsp_gradient_kernel<1><<<g, b>>>(A, tmap); else if(C == 2) lbsp_gradient_kernel<2><<<g, b>>>(A, tmap);
+        else if(C == 3) lbsp_gradient_kernel<3><<<g, b>>>(A, tmap); else lbsp_gradient_kernel<4><<<g, b>>>(A, tmap);
         LAUNCHED();
         d2h((cudaStream_t)0, out, d_out, npx * 4);
     } catch(...) { cudaFree(d_img); cudaFree(d_out); throw; }

@@ -3,6 +3,7 @@
 // (LBSP::compute2, features2d/src/LBSP.cpp:102-152) and the shared initialisation / background-image kernels.
 #pragma once
 #include "subsense.cuh"
+#include "edge_px.cuh"
 
 namespace lvb {
 
@@ -239,7 +240,9 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_dense_kernel(const LbspA
 /// dense LBSP gradient map (LBSP::computeDescriptor_gradient<C, 20, 2>, features2d/include/litiv/features2d/LBSP.hpp:235-256, the
 /// per-pixel primitive of imgproc/src/EdgeDetectorLBSP.cpp:253): 4 bytes per pixel = gradX (int8), gradY (int8), magnitude, 0.
 /// Pixels within the 2-px border get (0,0,0,0), the value the edge detector's all-equal border lookup yields (:84-100).
-struct LbspGradArgs { int W, H; const uchar* img; size_t ipitch; uchar4* out; int use_tma; };
+/// `combine` (EdgeDetectorLBSP, edge_px.cuh): the value written is edge_combine(gradient, coarser level's map at (y/2, x/2)), or with the
+/// detector's initial value when `coarse` is null (the coarsest level)
+struct LbspGradArgs { int W, H; const uchar* img; size_t ipitch; uchar4* out; int use_tma; int combine; const uchar4* coarse; int Wc; };
 template<int CH>
 __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_gradient_kernel(const LbspGradArgs A, const __grid_constant__ CUtensorMap tmap) {
     constexpr int PITCH = tile_pitch(CH);
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_gradient_kernel(const Lb
         o.y = (uchar)(signed char)(__popc(best & YP) - __popc(best & YN));
         o.z = (uchar)best_mag;
     }
+    if(A.combine) o = lvb_edge::edge_combine(o, A.coarse ? A.coarse[(size_t)(y >> 1) * A.Wc + (x >> 1)] : lvb_edge::edge_init_value());
     A.out[(size_t)y * A.W + x] = o;
 }
 

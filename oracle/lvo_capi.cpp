@@ -276,7 +276,7 @@ double lvo_apply_sequence(void* hv, const uint8_t* frames, int n, size_t frame_b
 
 int lvo_lbsp_gradient(const uint8_t* img, int w, int h, int c, uint8_t* out) {
     LVO_TRY
-    if(!img || (c != 1 && c != 3) || w < 5 || h < 5) throw std::runtime_error("input image must be non-empty, 8UC1/8UC3 and at least 5x5");
+    if(!img || c < 1 || c > 4 || w < 5 || h < 5) throw std::runtime_error("input image must be non-empty, 8UC1 .. 8UC4 and at least 5x5");
     lbsp_gradient_dense(img, w, h, c, out);
     LVO_CATCH
 }

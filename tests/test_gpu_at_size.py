@@ -78,6 +78,23 @@ def test_config3_pawcs_vga_vs_oracle(lv, oracle):
     assert np.array_equal(g.getBackgroundImage(), o.get_background_image())
 
 
+def test_pawcs_1080p_vs_oracle(lv, oracle):
+    """PAWCS at 1920x1080 RGB (the size its kernels are timed at): work-lists of the scan tail and of the phase-B tail with tens of
+    thousands of entries, global-word maps of 960x540, maintenance on frame 8; masks every frame, full dictionary state at checkpoints"""
+    w, h = 1920, 1080
+    seq = SynthSequence(w, h, 3, seed=6)
+    g, o = TP._mk(lv, oracle, seed=2)
+    f0 = seq.frame(0)
+    g.initialize(f0)
+    o.initialize(f0)
+    for t in range(1, 10):
+        f = seq.frame(t)
+        mg, mo = g.apply(f, 0.0), o.apply(f, 0.0)
+        assert np.array_equal(mg, mo), f"PAWCS 1080p frame {t}: final masks differ in {(mg != mo).sum()} px"
+        if t in (1, 9):                                  # 9: right after the first global-dictionary maintenance (frame 8)
+            TP._compare(g, o, f"PAWCS 1080p frame {t}")
+
+
 def test_config5_batched_vga_streams_vs_per_stream_oracles(lv, oracle):
     """BASELINE config #5 path: lvb_apply_batch_device over VGA streams with device-resident frames; every stream is held against
     ITS OWN oracle instance (seed = stream id), masks every round and full state at the end"""

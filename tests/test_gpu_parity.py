@@ -46,7 +46,7 @@ def test_lbsp_matches_oracle(lv, oracle, shape, mode):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("shape", [(37, 53, 3), (64, 64, 1), (5, 5, 3), (9, 130, 1), (240, 320, 3), (1080, 1920, 3)])
+@pytest.mark.parametrize("shape", [(37, 53, 3), (64, 64, 1), (5, 5, 3), (9, 130, 1), (240, 320, 3), (1080, 1920, 3), (61, 97, 2), (48, 80, 4)])
 def test_lbsp_gradient_matches_oracle(lv, oracle, shape):
     """dense LBSP::computeDescriptor_gradient (the per-pixel primitive of EdgeDetectorLBSP): bit-exact gradX / gradY / magnitude"""
     rng = np.random.RandomState(hash(shape) & 0xFFFF)
