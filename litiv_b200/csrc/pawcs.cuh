@@ -216,7 +216,10 @@ __device__ __forceinline__ int paw_find_gword(const PawArgs& A, const uint32_t* 
 //                    updates of the matched words (hand-off mask), the new word over the last one (:1142-1153).
 // Hand-off per pixel (uint2): matched-word mask bits 0..55, flags in the top byte.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PAW_K = 4;
+#ifndef PAW_KW
+#define PAW_KW 4
+#endif
+constexpr int PAW_K = PAW_KW;
 constexpr int PAW_SPLIT_MAX_NW = 56;
 constexpr uint32_t PAW_H_OCC = 1u << 24, PAW_H_NEW = 1u << 25, PAW_H_FLAT = 1u << 26, PAW_H_SKIP = 1u << 27; // hand.y: mask bits 32..55 in bits 0..23; SKIP: pawcs_scan_tail owns the pixel
 
