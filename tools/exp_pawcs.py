@@ -47,5 +47,5 @@ for _ in range(32):
 torch.cuda.synchronize()
 pms, pn = sub.get_profile()
 st = sub.stats()
-print(json.dumps({"W": W, "H": H, "frame_us": ms * 1e3, "mpx_s": W * H / ms / 1e3, "phaseA_us": pms / pn * 1e3,
+print(json.dumps({"W": W, "H": H, "frame_us": ms * 1e3, "mpx_s": W * H / ms / 1e3, "scan_plus_tail_us": pms / pn * 1e3,
                   "words_scanned_per_px": st["samples_scanned"] / max(st["roi_px"], 1), "fg_frac": st["fg_px"] / max(st["roi_px"], 1)}))
