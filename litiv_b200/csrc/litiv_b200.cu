@@ -876,7 +876,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         const bool serial = (size_t)W * H <= (size_t)640 * 480;
         cudaStream_t sb = serial ? st : c->s_aux;
         if(!serial) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0)); }
-        if(C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, sb>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, sb>>>(B);
+        if(C == 1) neighbor_write_phaseB<1, 1><<<tg, tb, 0, sb>>>(B); else neighbor_write_phaseB<3, 1><<<tg, tb, 0, sb>>>(B);   // LOBSTER: 3x3 intents only
         LAUNCHED();
         if(!serial) CK(cudaEventRecord(c->ev_join, c->s_aux));
         pp_median<<<mg, tb, 0, st>>>(c->raw, c->lastfg, d_mask_out, (size_t)W, W, H, c->WW, c->median_k); LAUNCHED();

@@ -943,7 +943,9 @@ struct PhaseBArgs {
     uint32_t* bump_frame;      // LOBSTER: FrameCtl::frame_idx, advanced by one thread here (the frame's pixel pass is over; saves a launch)
 };
 
-template<int CH>
+/// RAD: radius of the neighbourhood the intents were drawn from (2: SuBSENSE's 5x5 / 3x3 switch; 1: LOBSTER always draws from the 3x3 pattern,
+/// so 9 window positions are tested per target instead of 25)
+template<int CH, int RAD = 2>
 __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A) {
     typedef typename Pack<CH>::Col Col;
     typedef typename Pack<CH>::Desc Desc;
@@ -970,9 +972,9 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     // pass 1: which of the 25 sources aim at this pixel (no global access); bit i = window position i = (dy+2)*5 + k
     uint32_t hits = 0;
 #pragma unroll
-    for(int dy = -2; dy <= 2; ++dy) {
+    for(int dy = -RAD; dy <= RAD; ++dy) {
 #pragma unroll
-        for(int k = 0; k < 5; ++k) {
+        for(int k = 2 - RAD; k <= 2 + RAD; ++k) {
             const uint32_t it = s_int[threadIdx.y + 2 + dy][threadIdx.x + k];
             if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) hits |= 1u << ((dy + 2) * 5 + k);
         }
