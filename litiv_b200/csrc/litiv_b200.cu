@@ -143,6 +143,7 @@ struct lvb_context {
     ScanMaps scan_maps[2];              // SuBSENSE scan kernel: TMA maps of its per-pixel planes; [i] reads colour / descriptor plane pair i as "previous frame"
     int scan_maps_idx = 0;              // which pair is the latest frame's (follows the last_color / last_color_alt swap)
     uint8_t* own_slot = nullptr;        // SuBSENSE: queued own-sample writes (slot per pixel, 0xFF none), applied by the next scan
+    uint2* cbox = nullptr;              // SuBSENSE: per-pixel colour bounding box of the samples (subsense.cuh: ColorBox); LVB_NO_CBOX=1 disables it
     uint32_t* wl_ctx = nullptr; uint32_t* wl2_idx = nullptr; uint32_t wl_cap = 0;   // SuBSENSE scan work-list (subsense.cuh: WlCtx)
     uint8_t* lut = nullptr;
     bool lut_small = false;   // every LUT entry (now and after any +-1 adaptation) is <= 127: the kernels take the 7-bit compare path
@@ -186,11 +187,11 @@ struct lvb_context {
     size_t paw_rec_bytes() const { return C == 1 ? 8 : 16; }   // PawRec<C>::T
 
     void free_all() {
-        void* ptrs[] = {own_slot, wl_ctx, wl2_idx, eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
+        void* ptrs[] = {cbox, own_slot, wl_ctx, wl2_idx, eval_gt, eval_roi, eval_cnt, r_plane, div_tab, last_color_alt, last_desc_alt, hand, fin_alt, magic, uf_parent, uf_rankbase, d_img, d_mask, bg, maps, fin, last_color, last_desc, tmp_desc, bits, intents, lut, ctl, dsLT, dsST,
                         lw_rec, lw_key, glut, gmap, gmap_tmp, gd, paw_intents, gop_w, gop_g, ds_roi, bgimg};
         for(void* p : ptrs) if(p) cudaFree(p);
         d_img = nullptr; d_mask = nullptr; bg = nullptr; maps = nullptr; fin = nullptr; last_color = last_desc = tmp_desc = nullptr;
-        own_slot = nullptr; wl_ctx = nullptr; wl2_idx = nullptr; wl_cap = 0;
+        own_slot = nullptr; cbox = nullptr; wl_ctx = nullptr; wl2_idx = nullptr; wl_cap = 0;
         eval_gt = eval_roi = nullptr; eval_cnt = nullptr; r_plane = nullptr; div_tab = nullptr; last_color_alt = last_desc_alt = nullptr; nb_seq = 0; fin_pending = 0; hand = nullptr; fin_alt = nullptr; post_pending = false; magic = nullptr; uf_parent = nullptr; uf_rankbase = nullptr; bits = nullptr; intents = nullptr; lut = nullptr; ctl = nullptr; dsLT = dsST = nullptr;
         lw_rec = nullptr; lw_key = nullptr; glut = nullptr; gmap = gmap_tmp = nullptr; gd = nullptr;
         paw_intents = nullptr; gop_w = nullptr; gop_g = nullptr; ds_roi = nullptr; bgimg = nullptr;
@@ -257,13 +258,21 @@ void flush_pending(lvb_context* c) {
     if(c->nb_seq == 0) return;
     PhaseBArgs B{};
     B.W = c->W; B.H = c->H; B.Wp = c->Wp; B.WW = c->WW; B.CH = c->C; B.plane = c->plane;
-    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents; B.own_slot = c->own_slot;
+    B.bg = c->bg; B.last_color = c->last_color; B.last_desc = c->last_desc; B.intents = c->intents; B.own_slot = c->own_slot; B.cbox = c->cbox;
     B.ctl = c->ctl; B.pending_seq = c->nb_seq;
     const dim3 tg(c->Wp / 32, (c->H + 7) / 8), tb(32, 8);
     if(c->C == 1) neighbor_write_phaseB<1><<<tg, tb, 0, c->stream>>>(B); else neighbor_write_phaseB<3><<<tg, tb, 0, c->stream>>>(B);
     LAUNCHED();
     mark_nb_applied_kernel<<<1, 1, 0, c->stream>>>(c->ctl, c->nb_seq); LAUNCHED();
     CK(cudaStreamSynchronize(c->stream));
+}
+/// exact colour boxes from the sample model as it stands (state import, and periodically: the boxes only grow in between)
+void rebuild_cbox(lvb_context* c) {
+    if(!c->cbox || c->algo != LVB_ALGO_SUBSENSE) return;
+    const dim3 tg(c->Wp / 32, (c->H + 7) / 8), tb(32, 8);
+    if(c->C == 1) cbox_rebuild_kernel<1><<<tg, tb, 0, c->stream>>>(c->bg, c->plane, c->W, c->H, c->Wp, c->P.n_samples, c->cbox);
+    else cbox_rebuild_kernel<3><<<tg, tb, 0, c->stream>>>(c->bg, c->plane, c->W, c->H, c->Wp, c->P.n_samples, c->cbox);
+    LAUNCHED();
 }
 /// conditional refreshModel on the instance stream (exits at once unless FrameCtl::do_refresh is set)
 void launch_refresh(lvb_context* c) {
@@ -275,6 +284,7 @@ void launch_refresh(lvb_context* c) {
     const dim3 tgd = tile_grid(c);
     R.intents = c->intents; R.pending_seq = c->algo == LVB_ALGO_SUBSENSE ? c->nb_seq : 0u;
     R.own_slot = c->algo == LVB_ALGO_SUBSENSE ? c->own_slot : nullptr;
+    R.cbox = c->algo == LVB_ALGO_SUBSENSE ? c->cbox : nullptr;
     const int rgrid = (int)std::min<size_t>((size_t)tgd.x * tgd.y, 148 * 8);
     if(c->C == 1) refresh_model_kernel<1><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
     else refresh_model_kernel<3><<<rgrid, dim3(32, 8), 0, c->stream>>>(R);
@@ -589,6 +599,10 @@ void do_initialize(lvb_context* c, const uint8_t* img, int W, int H, int C, size
         c->hand = dalloc<uint2>(c->stream, c->plane);
         c->own_slot = dalloc<uint8_t>(c->stream, c->plane, false);
         CK(cudaMemsetAsync(c->own_slot, 0xFF, c->plane, c->stream));
+        if(!getenv("LVB_NO_CBOX")) {   // starts as "contains everything" (never filters); initialize()'s refreshModel makes it exact
+            c->cbox = dalloc<uint2>(c->stream, c->plane, false);
+            std::vector<uint2> full(c->plane, make_uint2(0u, 0x00FFFFFFu)); h2d(c->stream, c->cbox, full.data(), full.size() * sizeof(uint2));
+        }
         c->wl_cap = (uint32_t)c->plane;   // every pixel may be undecided after two samples (first frames after a scene change)
         c->wl_ctx = dalloc<uint32_t>(c->stream, (size_t)(C == 1 ? WlCtx<1>::FIELDS : WlCtx<3>::FIELDS) * c->wl_cap, false);
         c->wl2_idx = dalloc<uint32_t>(c->stream, c->wl_cap, false);
@@ -752,7 +766,7 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
     A.prev_color = c->last_color; A.prev_desc = c->last_desc; A.pending_seq = sub ? c->nb_seq : 0u; A.roi_bits = c->roi_bits; A.raw_bits = sub ? c->raw_alt : c->raw; A.unstable_bits = c->unstable;
     A.blinks_bits = c->blinks; A.lastfg_bits = c->lastfg; A.ghost_prev = c->ghost[c->ghost_idx]; A.ghost_cur = c->ghost[c->ghost_idx ^ 1];
     A.intents = c->intents; A.lut = c->lut; A.ctl = c->ctl; A.seed = c->seed;
-    A.wl_ctx = c->wl_ctx; A.wl_cap = c->wl_cap; A.wl2_idx = c->wl2_idx; A.own_slot = c->own_slot;
+    A.wl_ctx = c->wl_ctx; A.wl_cap = c->wl_cap; A.wl2_idx = c->wl2_idx; A.own_slot = c->own_slot; A.cbox = sub ? c->cbox : nullptr;
     A.lr_fixed = lr_to_fixed(lr); A.min_color = c->P.color_dist_threshold; A.desc_off = c->P.desc_dist_threshold;
     A.use_tma = use_tma; A.collect_stats = c->collect_stats;
     A.n_magic = (uint32_t)(0x100000000ull / (uint64_t)c->P.n_samples);
@@ -791,6 +805,9 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         // grid loses to the tail effect of its static tile assignment, the oversubscribed one lets the hardware scheduler balance it
         static const int scan_ctas = getenv("LVB_SCAN_CTAS") ? atoi(getenv("LVB_SCAN_CTAS")) : SCAN_GRID_CTAS_PER_SM;
         const dim3 sg((unsigned)std::min<int>((int)(stage_grid(c).x * stage_grid(c).y), c->sm_count * scan_ctas));
+        // the colour boxes only grow between rebuilds (every sample write widens them): an exact rebuild every 128 frames (one pass over the
+        // model, ~0.3 ms at 1080p = 2 us per frame amortised) keeps them tight. Queued writes not yet in the model grow them when the scan applies them.
+        if(c->cbox && (c->sub_frame % 128u) == 0u) rebuild_cbox(c);
         if(c->lut_small) { if(C == 1) subsense_scan<1, true><<<sg, stage_block, 0, st>>>(A, tmap, SM); else subsense_scan<3, true><<<sg, stage_block, 0, st>>>(A, tmap, SM); }
         else { if(C == 1) subsense_scan<1, false><<<sg, stage_block, 0, st>>>(A, tmap, SM); else subsense_scan<3, false><<<sg, stage_block, 0, st>>>(A, tmap, SM); }
         LAUNCHED();
@@ -1308,6 +1325,7 @@ void state_set(lvb_context* c, const std::string& n, const void* in, size_t byte
             }
             h2d(c->stream, (uint8_t*)c->bg + (size_t)s * h.size(), h.data(), h.size());
         }
+        if(n == "bg_color") rebuild_cbox(c);
         return;
     }
     throw std::runtime_error("unknown state buffer: " + n);

@@ -67,6 +67,8 @@ __device__ __forceinline__ uint32_t desc_get(const uint2& d, int c) { return c =
 __device__ __forceinline__ uint32_t desc_get(const ushort& d, int) { return d; }
 __device__ __forceinline__ uint32_t col_get(const uint32_t& v, int c) { return (v >> (8 * c)) & 0xFFu; }
 __device__ __forceinline__ uint32_t col_get(const uchar& v, int) { return v; }
+__device__ __forceinline__ uint32_t col_as_u32_(const uint32_t& v) { return v; }
+__device__ __forceinline__ uint32_t col_as_u32_(const uchar& v) { return v; }
 
 struct SubArgs {
     int W, H, Wp, WW, N, REQ;
@@ -93,6 +95,7 @@ struct SubArgs {
     int min_color, desc_off;
     int use_tma, collect_stats;
     uint32_t n_magic;          // floor(2^32 / N) for fast_mod
+    uint2* cbox;               // SuBSENSE: per-pixel colour bounding box of the sample model (ColorBox, subsense.cuh); nullptr: not kept
     const uint32_t* magic;     // [257] floor(2^32 / n) (n = 1: 0xFFFFFFFF), device table for x % ceil(T(x))
     const float* div_color;    // [colorRange + 1] i / colorRange  (IEEE quotients tabulated on the host: the feedback step
     const float* div_desc;     // [descRange + 1]  i / descRange    normalises four small integers per pixel)

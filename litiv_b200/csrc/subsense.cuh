@@ -161,6 +161,42 @@ template<int CH> struct ScanTile {
     static constexpr uint32_t TX_PENDING = (uint32_t)(BW_INT * IH * 2 + TILE_W * TILE_H);
 };
 
+// ---- colour bounding box of a pixel's samples (SuBSENSE scan: a pure acceleration structure, results unchanged) ------------------------------
+// x = per-channel minimum, y = per-channel maximum of the colours of the pixel's N samples (bytes 0..2; 1 channel: byte 0), CONSERVATIVE: it
+// contains every sample (it may be larger: it only grows between rebuilds). A sample can only match when every channel of the current colour is
+// within the single-channel colour gate of the sample (SuBSENSE.cpp:232-235 / :371-377) and the summed distance within the total gate, so when
+// the current colour lies farther from the box than that, NO sample matches: the pixel is foreground with zero matches and default minimal
+// distances, exactly what scanning all N samples yields, without reading them (94-96 % of the foreground pixels of the SURVEY 8(d) sequence).
+// Kept in step with every sample write: queued own / neighbour writes (scan kernel, standalone phase B, refresh kernel) grow it, a refresh
+// rebuilds it from the samples it leaves behind, state import and a periodic pass (every 128 frames) rebuild it exactly (cbox_rebuild_kernel).
+__device__ __forceinline__ uint2 cbox_full() { return make_uint2(0u, 0x00FFFFFFu); }       // contains everything: never filters
+__device__ __forceinline__ uint2 cbox_empty() { return make_uint2(0x00FFFFFFu, 0u); }
+__device__ __forceinline__ void cbox_grow(uint2& b, uint32_t col32) { col32 &= 0x00FFFFFFu; b.x = __vminu4(b.x, col32); b.y = __vmaxu4(b.y, col32); }
+/// true when no colour inside the box can pass the colour gates against `cur32` (gate: per channel, tot: sum over the channels)
+template<int CH>
+__device__ __forceinline__ bool cbox_excludes(const uint2 b, uint32_t cur32, uint32_t gate, uint32_t tot) {
+    cur32 &= 0x00FFFFFFu;
+    const uint32_t d4 = __vmaxu4(__vsubus4(b.x, cur32), __vsubus4(cur32, b.y)); // per channel: distance from the box (0 inside)
+    const uint32_t g4 = min(gate, 255u) * 0x00010101u;
+    if(__vcmpgtu4(d4, g4) & 0x00FFFFFFu) return true;
+    return CH != 1 && __dp4a(d4, 0x00010101u, 0u) > tot;
+}
+/// exact box of the N samples of one pixel
+template<int CH>
+__device__ __forceinline__ uint2 cbox_of_model(const void* bg, size_t plane, size_t pix, int N) {
+    typedef typename Pack<CH>::Rec Rec;
+    uint2 b = cbox_empty();
+    for(int s = 0; s < N; ++s) cbox_grow(b, col_as_u32_(rec_col(((const Rec*)bg)[(size_t)s * plane + pix])));
+    return b;
+}
+template<int CH>
+__global__ void __launch_bounds__(256) cbox_rebuild_kernel(const void* bg, size_t plane, int W, int H, int Wp, int N, uint2* cbox) {
+    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    if(x >= W || y >= H) return;
+    const size_t pix = (size_t)y * Wp + x;
+    cbox[pix] = cbox_of_model<CH>(bg, plane, pix, N);
+}
+
 /// Scan kernel: one thread per pixel of a 32x8 tile. EVERYTHING the tile reads (input tile + halo, previous colour / descriptor
 /// tiles + halo, R(x), the first two sample records of every pixel, and - when neighbour / own-sample writes of the previous frame are
 /// pending - the intent tile + halo and the own-slot tile) is staged by one elected thread with cp.async.bulk.tensor (TMA) behind a
@@ -252,6 +288,8 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap, const _
         if(y < A.H && (x >> 5) < A.WW) { w_roi = A.roi_bits[wi]; w_unst = A.unstable_bits[wi]; }
         const bool active = in_img && (w_roi & lane_bit);
         const size_t pix = (size_t)y * A.Wp + x;
+        uint2 cbx = cbox_full();
+        if(A.cbox && in_img) cbx = A.cbox[pix];   // (in flight while the tile's boxes land)
 
         mbar_wait(&s_bar[b], (uint32_t)((it >> 1) & 1));     // every TMA box of this tile has landed (async proxy -> visible after the phase flips)
 
@@ -294,11 +332,13 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap, const _
             // neighbour writes come after the loop and override it): the record is the previous frame's colour / descriptors of this
             // very pixel, which the scan holds anyway. Doing the scattered store here, where it overlaps ~1000 instructions of
             // arithmetic, costs nothing measurable; at the end of the feedback kernel it cost 27 us per 1080p frame.
+            const uint2 cbx_in = cbx;
             const uint32_t own = s_own[threadIdx.y][threadIdx.x];
             if(own != 0xFFu) {
 #ifndef LVB_EXP_NO_OWN_WRITE
                 ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(lc, ld);
 #endif
+                cbox_grow(cbx, col_as_u32_(lc));
                 if(own == 0u) { pre_c0 = lc; pre_d0 = ld; }
                 if(own == 1u) { pre_c1 = lc; pre_d1 = ld; }
             }
@@ -315,7 +355,9 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap, const _
 #endif
                 if(slot == 0u) { pre_c0 = c_; pre_d0 = d_; }
                 if(slot == 1u) { pre_c1 = c_; pre_d1 = d_; }
+                cbox_grow(cbx, col_as_u32_(c_));
             }
+            if(A.cbox && (cbx.x != cbx_in.x || cbx.y != cbx_in.y)) A.cbox[pix] = cbx;
         }
         s_hits2[b ^ 1][threadIdx.y][threadIdx.x] = 0; // the other hit plane, for the next tile (last read before the barrier that closed the previous tile)
 
@@ -347,6 +389,8 @@ subsense_scan(const SubArgs A, const __grid_constant__ CUtensorMap tmap, const _
             if constexpr (CH == 1) { cur_pack = (uchar)cur[0]; intra_pack = (ushort)intra[0]; }
             else { cur_pack = cur[0] | (cur[1] << 8) | (cur[2] << 16); intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]); }
 
+            // no sample can pass the colour gates (ColorBox above): foreground with zero matches, as if all N samples had been scanned
+            if(A.cbox && cbox_excludes<CH>(cbx, col_as_u32_(cur_pack), CH == 1 ? thrC : (thrC * 3u) >> 1, thrC * 3u)) s = N;
             // samples 0 and 1 were staged with the tile
             uint32_t d_, s_;
             if(good < REQ && s < N) { if(subsense_test_sample<CH, T7>(L, cur, intra, pre_c0, pre_d0, thrC, thrD, s_lut, d_, s_)) { minDesc = min(minDesc, d_); minSum = min(minSum, s_); ++good; } ++s; }
@@ -941,6 +985,7 @@ struct PhaseBArgs {
     const uchar* own_slot;     // SuBSENSE: queued own-sample writes (applied before the neighbour writes, which override them); LOBSTER: nullptr
     const FrameCtl* ctl; uint32_t pending_seq; // pending_seq != 0: skip when FrameCtl::nb_applied_seq says these writes are already in the model
     uint32_t* bump_frame;      // LOBSTER: FrameCtl::frame_idx, advanced by one thread here (the frame's pixel pass is over; saves a launch)
+    uint2* cbox;               // SuBSENSE: colour boxes, grown with every record written here (nullptr: not kept)
 };
 
 /// RAD: radius of the neighbourhood the intents were drawn from (2: SuBSENSE's 5x5 / 3x3 switch; 1: LOBSTER always draws from the 3x3 pattern,
@@ -966,7 +1011,11 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     if(A.own_slot && x < A.W && y < A.H) { // the pixel's own queued update first
         const size_t p = (size_t)y * A.Wp + x;
         const uint32_t own = A.own_slot[p];
-        if(own != 0xFFu) ((Rec*)A.bg)[(size_t)own * A.plane + p] = rec_make(((const Col*)A.last_color)[p], ((const Desc*)A.last_desc)[p]);
+        if(own != 0xFFu) {
+            const Col oc = ((const Col*)A.last_color)[p];
+            ((Rec*)A.bg)[(size_t)own * A.plane + p] = rec_make(oc, ((const Desc*)A.last_desc)[p]);
+            if(A.cbox) { uint2 bx = A.cbox[p]; cbox_grow(bx, col_as_u32_(oc)); A.cbox[p] = bx; }
+        }
     }
     if(x < 2 || y < 2 || x > A.W - 3 || y > A.H - 3) return; // clamped targets never leave [2,dim-3]
     // pass 1: which of the 25 sources aim at this pixel (no global access); bit i = window position i = (dy+2)*5 + k
@@ -984,6 +1033,9 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
     const Col* lcol = (const Col*)A.last_color;
     const Desc* ldes = (const Desc*)A.last_desc;
     const size_t tpix = (size_t)y * A.Wp + x;
+    uint2 bx = cbox_full();
+    const bool keep_box = A.cbox != nullptr && hits != 0u;
+    if(keep_box) bx = A.cbox[tpix];
     while(hits) {
         const int i0 = __ffs(hits) - 1;
         hits &= hits - 1;
@@ -1002,11 +1054,14 @@ __global__ void __launch_bounds__(256) neighbor_write_phaseB(const PhaseBArgs A)
         }
         const size_t dst0 = (size_t)(it0 & 0xFFu) * A.plane + tpix;
         ((Rec*)A.bg)[dst0] = rec_make(c0, d0);
+        cbox_grow(bx, col_as_u32_(c0));
         if(i1 >= 0) {
             const size_t dst1 = (size_t)(it1 & 0xFFu) * A.plane + tpix;
             ((Rec*)A.bg)[dst1] = rec_make(c1, d1);
+            cbox_grow(bx, col_as_u32_(c1));
         }
     }
+    if(keep_box) A.cbox[tpix] = bx;
 }
 
 /// refreshModel (SuBSENSE.cpp:80-105 / LOBSTER.cpp:410-441): one thread per ROI pixel; runs only when
@@ -1024,6 +1079,7 @@ struct RefreshArgs {
     int recompute_desc;        // LOBSTER: descriptor of the sampled pixel is recomputed from last_color
     const ushort* intents; uint32_t pending_seq; // SuBSENSE: neighbour writes of this frame not yet in the model are applied first
     const uchar* own_slot;     // SuBSENSE: ... and before them the queued own-sample writes
+    uint2* cbox;               // SuBSENSE: colour boxes (nullptr: not kept): rebuilt for every pixel this kernel writes to
 };
 
 template<int CH>
@@ -1041,9 +1097,10 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
     const int x = (tile % tiles_x) * 32 + threadIdx.x, y = (tile / tiles_x) * 8 + threadIdx.y;
     if(x >= A.W || y >= A.H) continue;
     const size_t pix = (size_t)y * A.Wp + x;
+    bool wrote = false;
     if(apply_nb && A.own_slot) {
         const uint32_t own = A.own_slot[pix];
-        if(own != 0xFFu) ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(((const Col*)A.last_color)[pix], ((const Desc*)A.last_desc)[pix]);
+        if(own != 0xFFu) { ((Rec*)A.bg)[(size_t)own * A.plane + pix] = rec_make(((const Col*)A.last_color)[pix], ((const Desc*)A.last_desc)[pix]); wrote = true; }
     }
     if(apply_nb && x >= 2 && y >= 2 && x <= A.W - 3 && y <= A.H - 3) {
         // the reference applies the frame's neighbour writes inside its pixel loop, i.e. before refreshModel: same rule as phase B
@@ -1053,13 +1110,16 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
             if((it >> 8) == (uint32_t)((2 - dy) * 5 + (4 - k))) {
                 const size_t dst = (size_t)(it & 0xFFu) * A.plane + pix;
                 ((Rec*)A.bg)[dst] = rec_make(((const Col*)A.last_color)[q], ((const Desc*)A.last_desc)[q]);
+                wrote = true;
             }
         }
     }
     if(ctl->set_T_one && A.maps) A.maps[pix * 2].x = 1.0f;
-    if(!((A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u)) continue;
+    // a pixel that is not resampled below but received queued writes: its colour box is rebuilt from its samples (own stores are visible to own loads)
+    const bool roi_px = (A.roi_bits[y * A.WW + (x >> 5)] >> (x & 31)) & 1u;
     const bool force = ctl->refresh_force != 0;
-    if(!force && ((__ldcg(A.lastfg_bits + y * A.WW + (x >> 5)) >> (x & 31)) & 1u)) continue;
+    const bool skip = !roi_px || (!force && ((__ldcg(A.lastfg_bits + y * A.WW + (x >> 5)) >> (x & 31)) & 1u));
+    if(skip) { if(A.cbox && wrote) A.cbox[pix] = cbox_of_model<CH>(A.bg, A.plane, pix, A.N); continue; }
     const uint32_t N = (uint32_t)A.N, start = ctl->refresh_start, count = ctl->refresh_count, epoch = ctl->refresh_epoch;
     const uint32_t pixid = (uint32_t)(y * A.W + x);
     const Col* lc = (const Col*)A.last_color;
@@ -1099,6 +1159,7 @@ __global__ void __launch_bounds__(256) refresh_model_kernel(const RefreshArgs A)
         } else d = ((const Desc*)A.last_desc)[sp];
         ((Rec*)A.bg)[(size_t)rs * A.plane + pix] = rec_make(col, d);
     }
+    if(A.cbox) A.cbox[pix] = cbox_of_model<CH>(A.bg, A.plane, pix, A.N);   // exact box of what the refresh leaves behind
     }
     // the last CTA to finish retires the request (every CTA has read it by then) and bumps the epoch it consumed
     __syncthreads();
