@@ -171,10 +171,22 @@ template<int CH> struct ScanTile {
 // rebuilds it from the samples it leaves behind, state import and a periodic pass (every 128 frames) rebuild it exactly (cbox_rebuild_kernel).
 __device__ __forceinline__ uint2 cbox_full() { return make_uint2(0u, 0x00FFFFFFu); }       // contains everything: never filters
 __device__ __forceinline__ uint2 cbox_empty() { return make_uint2(0x00FFFFFFu, 0u); }
-__device__ __forceinline__ void cbox_grow(uint2& b, uint32_t col32) { col32 &= 0x00FFFFFFu; b.x = __vminu4(b.x, col32); b.y = __vmaxu4(b.y, col32); }
+/// colour inside the box? per byte |c - mn| + |mx - c| == mx - mn exactly when mn <= c <= mx (two native VABSDIFF4; a byte that lies outside
+/// exceeds its width by an even amount, so a carry from the byte below cannot make it look equal; an empty box is never "contained")
+__device__ __forceinline__ bool cbox_contains(const uint2 b, uint32_t col32) {
+    col32 &= 0x00FFFFFFu;
+    return __vabsdiffu4(col32, b.x) + __vabsdiffu4(b.y, col32) == b.y - b.x;
+}
+/// (the per-byte min / max / saturating-subtract intrinsics are emulated on this architecture: they sit behind the containment test,
+/// which is what almost every colour written to a model passes)
+__device__ __forceinline__ void cbox_grow(uint2& b, uint32_t col32) {
+    if(cbox_contains(b, col32)) return;
+    col32 &= 0x00FFFFFFu; b.x = __vminu4(b.x, col32); b.y = __vmaxu4(b.y, col32);
+}
 /// true when no colour inside the box can pass the colour gates against `cur32` (gate: per channel, tot: sum over the channels)
 template<int CH>
 __device__ __forceinline__ bool cbox_excludes(const uint2 b, uint32_t cur32, uint32_t gate, uint32_t tot) {
+    if(cbox_contains(b, cur32)) return false;   // (most background pixels)
     cur32 &= 0x00FFFFFFu;
     const uint32_t d4 = __vmaxu4(__vsubus4(b.x, cur32), __vsubus4(cur32, b.y)); // per channel: distance from the box (0 inside)
     const uint32_t g4 = min(gate, 255u) * 0x00010101u;
