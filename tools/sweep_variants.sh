@@ -19,7 +19,7 @@ else
     if [[ "$v" == *@* ]]; then envs=$(echo "${v#*@}" | tr ',' ' '); fi
     so=litiv_b200/liblitiv_b200.so
     [ "$name" != base ] && so=exp_build/lib_$name.so
-    out=$(env $envs LVB_SO=$PWD/$so python bench.py --steps 40 --warmup 5 --repeats 5 --no-cpu-baseline --no-streams64 2>&1 | tail -1)
+    out=$(env $envs LVB_SO=$PWD/$so python bench.py --steps 40 --warmup 5 --repeats 5 --no-cpu-baseline --no-streams64 --no-other-configs 2>&1 | tail -1)
     echo "$v $(echo "$out" | python -c "
 import sys,json
 try:
