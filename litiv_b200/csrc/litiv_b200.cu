@@ -884,7 +884,8 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
         c->sub_frame += 1;
         launch_refresh(c); mark(st, "refresh"); // reads lastfg(k), only when the frame tail requested it (the tail waited for the mask)
     } else { // LOBSTER
-        if(C == 1) lobster_phaseA<1><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3><<<stage_grid(c), stage_block, 0, st>>>(A, tmap);
+        if(c->lut_small) { if(C == 1) lobster_phaseA<1, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3, true><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
+        else { if(C == 1) lobster_phaseA<1, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); else lobster_phaseA<3, false><<<stage_grid(c), stage_block, 0, st>>>(A, tmap); }
         LAUNCHED();
         if(c->profile) { CK(cudaEventRecord(ev1, st)); c->prof_events.push_back(ev0); c->prof_events.push_back(ev1); }
         B.bump_frame = &c->ctl->frame_idx; // the frame counter (Philox index) advances in phase B: no tail kernel

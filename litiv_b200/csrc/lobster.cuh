@@ -14,7 +14,8 @@ namespace lvb {
 #ifndef LOB_CHUNK
 #define LOB_CHUNK (CH == 1 ? 4 : 2)
 #endif
-template<int CH>
+/// T7: every LBSP threshold of the LUT is <= 127 (true for the reference's defaults): the 7-bit compare of lbsp_threshold
+template<int CH, bool T7>
 __global__ void __launch_bounds__(TILE_W * TILE_H, LOB_MIN_BLOCKS)
 lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
     typedef typename Pack<CH>::Col Col;
@@ -88,7 +89,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
 #pragma unroll
                         for(int c = 0; c < CH; ++c) {
                             const uint32_t b = col_get(bc, c);
-                            const uint32_t dd = __popc(lbsp_threshold(L[c], b, s_lut[b]) ^ desc_get(bd, c));
+                            const uint32_t dd = __popc(lbsp_threshold<T7>(L[c], b, s_lut[b]) ^ desc_get(bd, c));
                             ok = ok && (dd <= (CH == 1 ? descThr : scD));
                             td += dd;
                         }
@@ -110,7 +111,7 @@ lobster_phaseA(const SubArgs A, const __grid_constant__ CUtensorMap tmap) {
             if(own || nb) {
                 uint32_t intra[CH];
 #pragma unroll
-                for(int c = 0; c < CH; ++c) intra[c] = lbsp_threshold(L[c], cur[c], s_lut[cur[c]]);
+                for(int c = 0; c < CH; ++c) intra[c] = lbsp_threshold<T7>(L[c], cur[c], s_lut[cur[c]]);
                 Desc intra_pack;
                 if constexpr (CH == 1) intra_pack = (ushort)intra[0]; else intra_pack = make_uint2(intra[0] | (intra[1] << 16), intra[2]);
                 if(own) {
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(TILE_W * TILE_H) lbsp_gradient_kernel(const Lb
             const int c = k == 0 ? CH - 1 : k - 1; // the reference starts from the last channel and replaces on strictly greater
             const uint32_t ref = s_tile[tile_shift(CH) + sy * PITCH + sx * CH + c];
             const Lookup16 L = lbsp_lookup_smem<CH>(s_tile + tile_shift(CH), PITCH, sx, sy, c);
-            const uint32_t d = lbsp_threshold(L, ref, ((ref >> 2) + 20u) >> 1);
+            const uint32_t d = lbsp_threshold<true>(L, ref, ((ref >> 2) + 20u) >> 1);   // threshold <= 41: the 7-bit compare path
             const int m = __popc(d);
             if(best_mag < m) { best_mag = m; best = d; }
         }
