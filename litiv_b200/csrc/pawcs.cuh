@@ -69,6 +69,9 @@ struct PawArgs {
     const uchar* ds_roi; float* dsLT; float* dsST; uchar* bgimg; // frame-level analysis
 };
 
+/// draw % n == 0 for a learning rate n that is 1 for most pixels most of the time (T(x) sits at its floor on a quiet background):
+/// the integer division (~20 instructions) is skipped by the warps whose lanes all have n == 1
+__device__ __forceinline__ bool paw_draw_hits(uint32_t draw, uint32_t n) { return n == 1u || (draw % n) == 0u; }
 /// PAWCS.cpp:1596-1598: occ / ((last - first) + (frame - last) * 2 + offset), all uint32 (wrapping) = occ / (K - (first + last)), K = 2 frame + offset
 __device__ __forceinline__ uint32_t paw_wk(uint32_t frame, uint32_t off) { return frame * 2u + off; }
 __device__ __forceinline__ float paw_weight(const uint2 key, uint32_t K) { return __fdiv_rn((float)key.x, (float)(K - key.y)); }
@@ -312,9 +315,9 @@ __device__ __forceinline__ PawBits paw_finish(const PawArgs& A, const uint32_t* 
         M.DminLT = __fadd_rn(__fmul_rn(M.DminLT, oneLT), __fmul_rn(baseMin, aLT));
         M.DminST = __fadd_rn(__fmul_rn(M.DminST, oneST), __fmul_rn(baseMin, aST));
         M.rawLT = __fmul_rn(M.rawLT, oneLT); M.rawST = __fmul_rn(M.rawST, oneST);
-        if((rnd.x % rate) == 0u) {
+        if(paw_draw_hits(rnd.x, rate)) {
             const int g = GPRE ? g_pre : paw_find_gword<CH>(A, s_gbits, s_gcolor, P.pix, P.cur32, P.bits, P.thrC, P.thrD);
-            const uint32_t rep = rate >= 0x40000000u ? rnd.y : rnd.y % (rate * 2u);
+            const uint32_t rep = rate == 1u ? (rnd.y & 1u) : rate >= 0x40000000u ? rnd.y : rnd.y % (rate * 2u);
             if(g >= 0 || rep == 0u) {
                 A.gop_g[P.pix] = g >= 0 ? (uchar)g : (uchar)0xFE; A.gop_w[P.pix] = sum; B.has_gop = true;
                 if(g < 0) atomicMin(&A.gd->rep_winner, P.pixid);
@@ -325,7 +328,7 @@ __device__ __forceinline__ PawBits paw_finish(const PawArgs& A, const uint32_t* 
         M.DminLT = __fadd_rn(__fmul_rn(M.DminLT, oneLT), __fmul_rn(nmin, aLT));
         M.DminST = __fadd_rn(__fmul_rn(M.DminST, oneST), __fmul_rn(nmin, aST));
         M.rawLT = __fadd_rn(__fmul_rn(M.rawLT, oneLT), aLT); M.rawST = __fadd_rn(__fmul_rn(M.rawST, oneST), aST);
-        if(P.flat || (rnd.x % rate) == 0u) {
+        if(P.flat || paw_draw_hits(rnd.x, rate)) {
             const int g = GPRE ? g_pre : paw_find_gword<CH>(A, s_gbits, s_gcolor, P.pix, P.cur32, P.bits, P.thrC, P.thrD);
             if(g < 0) B.seg = true;
             else if(__fadd_rn(sum, __fdiv_rn(A.gmap[(size_t)g * A.gW * A.gH + cell], P.flat ? 2.0f : 4.0f)) < wthr) B.seg = true;
@@ -333,7 +336,7 @@ __device__ __forceinline__ PawBits paw_finish(const PawArgs& A, const uint32_t* 
         new_word = sum < __fdiv_rn(1.0f, (float)P.woff); // new local word over the last one (:1142-1153): written by pawcs_bubble
     }
     // neighbour dictionary update, queued (:1164-1247)
-    if((!B.seg && (rnd.z % rate) == 0u) || P.border || P.moving) {
+    if((!B.seg && paw_draw_hits(rnd.z, rate)) || P.border || P.moving) {
         int dx, dy;
         neighbor_offset(!(P.flat || P.border || P.moving), rnd.w, dx, dy);
         const int nx = clampi(x + dx, 2, A.W - 3), ny = clampi(y + dy, 2, A.H - 3);
