@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Parity fuzz of the PAWCS kernels (not part of the product, run once per kernel change on the GPU box): random frame sizes incl. tiny and
+"""Parity fuzz of the PAWCS kernels (test infrastructure: it executes the oracle, so it lives under tests/; run once per kernel change on the GPU box): random frame sizes incl. tiny and
 ragged ones, gray / RGB, random ROIs, learning-rate overrides; the CUDA path against the CPU oracle (snapshot mode), full dictionary state
-after every frame. usage: python tools/fuzz_pawcs.py [cases] [seed]"""
+after every frame. usage: python tests/fuzz_pawcs.py [cases] [seed]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import litiv_b200 as lv
 from oracle import oracle as O

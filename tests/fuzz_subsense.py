@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""Parity fuzz of the SuBSENSE / LOBSTER paths (not part of the product, run once per kernel change on the GPU box): random frame sizes,
+"""Parity fuzz of the SuBSENSE / LOBSTER paths (test infrastructure: it executes the oracle, so it lives under tests/; run once per kernel change on the GPU box): random frame sizes,
 gray / RGB, random ROIs, scene cuts (frame-level reset -> device-side refreshModel), host operations between frames that flush the queued
 sample writes (state export, getBackgroundImage), host refreshModel, sample-model re-import, runs that cross the 128-frame rebuild of the
 colour boxes; the CUDA path against the CPU oracle (snapshot mode), masks every frame and the full state at random frames.
-usage: python tools/fuzz_subsense.py [cases] [seed]"""
+usage: python tests/fuzz_subsense.py [cases] [seed]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import litiv_b200 as lv
 from oracle import oracle as O
