@@ -824,12 +824,31 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
             const int npx = W * H;
             const int g1 = std::max(1, std::min(c->sm_count * TAIL1_MINB, (npx / 4 + 127) / 128)), g2 = std::max(1, std::min(c->sm_count * TAIL2_MINB, (npx / 8 + 127) / 128));
             TP.in_idx = nullptr; TP.in_count = &c->ctl->wl_count; TP.cursor = &c->ctl->wl_cursor; TP.out_idx = c->wl2_idx; TP.out_count = &c->ctl->wl2_count; TP.s_limit = TAIL_PASS1_LIMIT;
+#if LVB_PDL
+            // programmatic dependent launch: the pass becomes resident while its predecessor drains (the kernels order themselves with pdl_wait())
+            cudaLaunchAttribute pdl_at[1];
+            pdl_at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; pdl_at[0].val.programmaticStreamSerializationAllowed = 1;
+            static const bool pdl_on = !(getenv("LVB_NO_PDL") && atoi(getenv("LVB_NO_PDL")));
+            auto pdl_launch = [&](void (*k)(const TailPassArgs), int g) {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = pdl_at; cfg.numAttrs = (pdl_on && !c->profile) ? 1 : 0;
+                CK(cudaLaunchKernelEx(&cfg, k, TP));
+            };
+            if(c->lut_small) { if(C == 1) pdl_launch(subsense_tail_pass<1, true, TAIL1_B, TAIL1_MINB, false>, g1); else pdl_launch(subsense_tail_pass<3, true, TAIL1_B, TAIL1_MINB, false>, g1); }
+            else { if(C == 1) pdl_launch(subsense_tail_pass<1, false, TAIL1_B, TAIL1_MINB, false>, g1); else pdl_launch(subsense_tail_pass<3, false, TAIL1_B, TAIL1_MINB, false>, g1); }
+#else
             if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
             else { if(C == 1) subsense_tail_pass<1, false, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, TAIL1_B, TAIL1_MINB, false><<<g1, 128, 0, st>>>(TP); }
+#endif
             LAUNCHED();
             TP.in_idx = c->wl2_idx; TP.in_count = &c->ctl->wl2_count; TP.cursor = &c->ctl->wl2_cursor; TP.out_idx = nullptr; TP.out_count = nullptr; TP.s_limit = 0xFFFFFFFFu;
+#if LVB_PDL
+            if(c->lut_small) { if(C == 1) pdl_launch(subsense_tail_pass<1, true, TAIL2_B, TAIL2_MINB, true>, g2); else pdl_launch(subsense_tail_pass<3, true, TAIL2_B, TAIL2_MINB, true>, g2); }
+            else { if(C == 1) pdl_launch(subsense_tail_pass<1, false, TAIL2_B, TAIL2_MINB, true>, g2); else pdl_launch(subsense_tail_pass<3, false, TAIL2_B, TAIL2_MINB, true>, g2); }
+#else
             if(c->lut_small) { if(C == 1) subsense_tail_pass<1, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, true, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); }
             else { if(C == 1) subsense_tail_pass<1, false, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); else subsense_tail_pass<3, false, TAIL2_B, TAIL2_MINB, true><<<g2, 128, 0, st>>>(TP); }
+#endif
             LAUNCHED();
             if(c->profile) { CK(cudaEventRecord(tp1, st)); c->prof3_events.push_back(tp0); c->prof3_events.push_back(tp1); }
             mark(st, "scan tail passes");
