@@ -829,9 +829,11 @@ void enqueue_frame(lvb_context* c, const uint8_t* img, size_t pitch, const CUten
             cudaLaunchAttribute pdl_at[1];
             pdl_at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; pdl_at[0].val.programmaticStreamSerializationAllowed = 1;
             static const bool pdl_on = !(getenv("LVB_NO_PDL") && atoi(getenv("LVB_NO_PDL")));
+            // frames up to 640x480 are bound by the host's launch rate, where the attribute costs more than the overlap returns (320x240: 57 -> 68 us)
+            const bool pdl_size = (size_t)W * H > (size_t)640 * 480;
             auto pdl_launch = [&](void (*k)(const TailPassArgs), int g) {
                 cudaLaunchConfig_t cfg{};
-                cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = pdl_at; cfg.numAttrs = (pdl_on && !c->profile) ? 1 : 0;
+                cfg.gridDim = dim3((unsigned)g); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = pdl_at; cfg.numAttrs = (pdl_on && pdl_size && !c->profile) ? 1 : 0;
                 CK(cudaLaunchKernelEx(&cfg, k, TP));
             };
             if(c->lut_small) { if(C == 1) pdl_launch(subsense_tail_pass<1, true, TAIL1_B, TAIL1_MINB, false>, g1); else pdl_launch(subsense_tail_pass<3, true, TAIL1_B, TAIL1_MINB, false>, g1); }
